@@ -1,0 +1,97 @@
+"""Deterministic synthetic RSNA/SPIDER-shaped inputs (there is no dataset access).
+
+Shapes follow what the reference produces after ``resample_to_isotropic`` +
+``extract_middle_slice`` (``datasets/classification/cropping.py:37-79``): a
+float32 sagittal plane at 0.3 mm isotropic spacing, e.g. 512 px @ 0.7 mm ->
+``int(round(512*0.7/0.3)) = 1195`` px.  Intensities are
+MRI-like: non-negative, smooth anatomy + a bright vertebral column with five
+darker discs + noise, background exactly 0.
+
+Only NumPy's PCG64 ``Generator`` streams are used, which are stable across
+NumPy versions, so a seed names the same slice in the build container and on
+the GPU box.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+ISO_SPACING = 0.3
+LEVEL_Y = (0.28, 0.38, 0.48, 0.58, 0.66)
+COLUMN_X = 0.48
+
+
+def iso_size(size_px: int, spacing_mm: float, iso: float = ISO_SPACING) -> int:
+    """cropping.py:45-48: ``int(round(osz * osp / nsp))``."""
+    return int(round(size_px * spacing_mm / iso))
+
+
+def _upsample_linear(low: np.ndarray, h: int, w: int) -> np.ndarray:
+    ly, lx = low.shape
+    ys = np.linspace(0, ly - 1, h, dtype=np.float32)
+    xs = np.linspace(0, lx - 1, w, dtype=np.float32)
+    y0 = np.minimum(ys.astype(np.int32), ly - 2)
+    x0 = np.minimum(xs.astype(np.int32), lx - 2)
+    fy = (ys - y0)[:, None]
+    fx = (xs - x0)[None, :]
+    a = low[y0][:, x0]
+    b = low[y0][:, x0 + 1]
+    c = low[y0 + 1][:, x0]
+    d = low[y0 + 1][:, x0 + 1]
+    return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
+
+
+def make_iso_slice(seed: int, h: int = 1195, w: int = 1195, dtype=np.float32) -> np.ndarray:
+    """One synthetic isotropic middle sagittal slice, ``[h, w]`` float32, range ~0..1500."""
+    rng = np.random.default_rng(seed)
+    low = rng.random((20, 20), dtype=np.float32)
+    img = 250.0 + 450.0 * _upsample_linear(low, h, w)
+    yy = np.linspace(0, 1, h, dtype=np.float32)[:, None]
+    xx = np.linspace(0, 1, w, dtype=np.float32)[None, :]
+    cx = COLUMN_X + 0.02 * np.float32(rng.standard_normal())
+    # vertebral column: bright band, gently curved
+    curve = cx + 0.04 * np.sin((yy - 0.2) * 3.0)
+    img += 500.0 * np.exp(-(((xx - curve) / 0.06) ** 2))
+    # five discs: darker flattened blobs
+    for ly in LEVEL_Y:
+        y0 = ly + 0.01 * np.float32(rng.standard_normal())
+        cxl = cx + 0.04 * np.sin((y0 - 0.2) * 3.0)
+        img -= 420.0 * np.exp(-(((xx - cxl) / 0.05) ** 2) - (((yy - y0) / 0.012) ** 2))
+    # body outline: zero background outside an ellipse
+    body = (((xx - 0.5) / 0.47) ** 2 + ((yy - 0.5) / 0.49) ** 2) < 1.0
+    noise = rng.gamma(4.0, 12.0, size=(h, w)).astype(np.float32)
+    img = np.maximum(img + noise - 48.0, 0.0) * body
+    return np.ascontiguousarray(img.astype(dtype))
+
+
+def make_batch(seeds, h: int = 1195, w: int = 1195) -> list[np.ndarray]:
+    return [make_iso_slice(int(s), h, w) for s in seeds]
+
+
+def ragged_shapes(n: int, seed: int = 0) -> list[tuple[int, int]]:
+    """Config 3: in-plane H,W ~ U{320..1024}, spacing ~ U(0.30, 0.95) mm -> iso sizes."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        hh, ww = int(rng.integers(320, 1025)), int(rng.integers(320, 1025))
+        sp = float(rng.uniform(0.30, 0.95))
+        out.append((iso_size(hh, sp), iso_size(ww, sp)))
+    return out
+
+
+def make_coords(n_series: int, seed: int = 0, border_frac: float = 0.01, hw=(1195, 1195)) -> np.ndarray:
+    """Config 4: ``[n,5,2]`` float32 (x,y); x ~ N(0.48,0.03), y ~ level mean + N(0,0.02);
+    ``border_frac`` of the points are forced within 40 px of a border to exercise clipping."""
+    rng = np.random.default_rng(seed)
+    xy = np.empty((n_series, 5, 2), dtype=np.float32)
+    xy[:, :, 0] = rng.normal(COLUMN_X, 0.03, size=(n_series, 5))
+    xy[:, :, 1] = np.asarray(LEVEL_Y, dtype=np.float32)[None, :] + rng.normal(0, 0.02, size=(n_series, 5))
+    force = rng.random((n_series, 5)) < border_frac
+    side = rng.integers(0, 4, size=(n_series, 5))
+    off = rng.random((n_series, 5)) * 40.0
+    h, w = hw
+    xy[:, :, 0] = np.where(force & (side == 0), off / w, xy[:, :, 0])
+    xy[:, :, 0] = np.where(force & (side == 1), 1.0 - (off + 1) / w, xy[:, :, 0])
+    xy[:, :, 1] = np.where(force & (side == 2), off / h, xy[:, :, 1])
+    xy[:, :, 1] = np.where(force & (side == 3), 1.0 - (off + 1) / h, xy[:, :, 1])
+    return np.clip(xy, 0.0, np.float32(0.99999)).astype(np.float32)
