@@ -1,0 +1,177 @@
+/*
+ * spine_b200.h -- C ABI of libspine_b200.so: the sm_100a implementation of
+ * spine-vision's localization-and-crop hot path.
+ *
+ * The reference (nghiant03/spine-vision, pure Python) has no FFI layer; the
+ * path sits behind plain Python callables.  Each entry point below replaces
+ * the device-side work of the reference callables it cites (paths relative to
+ * the reference root).  The Python host mirror in spine_vision_b200/ binds
+ * these with ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller
+ *    (PyTorch tensors: tensor.data_ptr()); workspaces are caller-owned too.
+ *    The library owns only svb_model handles.
+ *  - calls are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *    with no hidden synchronisation or allocation, except svb_model_create /
+ *    svb_model_destroy which allocate and synchronise.
+ *  - return value: 0 on success, negative svb_status otherwise; the message
+ *    is available from svb_last_error() (thread local).  Nothing throws.
+ *  - there is no CPU fallback: a device that is not sm_100 gives
+ *    SVB_ERR_UNSUPPORTED_DEVICE.
+ *  - a handle is bound to the device current at creation and is not
+ *    thread-safe; one process per GPU.
+ */
+#ifndef SPINE_B200_H_
+#define SPINE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVB_VERSION 100 /* 0.1.0 */
+
+typedef enum svb_status {
+    SVB_OK = 0,
+    SVB_ERR_INVALID_ARG = -1,
+    SVB_ERR_CUDA = -2,
+    SVB_ERR_UNSUPPORTED_DEVICE = -3,
+    SVB_ERR_WORKSPACE_TOO_SMALL = -4,
+    SVB_ERR_BOX_TOO_LARGE = -5,
+    SVB_ERR_MISSING_WEIGHT = -6,
+    SVB_ERR_UNSUPPORTED_MODEL = -7
+} svb_status;
+
+typedef enum svb_dtype {
+    SVB_BF16 = 0, /* bf16 operands, fp32 accumulate (BASELINE.json north_star) */
+    SVB_FP16 = 1  /* fp16 operands, fp32 accumulate: same tensor rate, 3 more mantissa bits */
+} svb_dtype;
+
+int svb_version(void);
+const char* svb_last_error(void);
+/* 0 if the current CUDA device is sm_100 (B200), else SVB_ERR_UNSUPPORTED_DEVICE. */
+int svb_device_check(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1 -- fused min-max normalise + antialiased bilinear resize to uint8.
+ * Replaces, per slice: normalize_to_uint8 (spine_vision/io/__init__.py:15-30) followed by
+ * PIL "L"->"RGB" + torchvision Resize (Pillow BILINEAR with antialias, uint8 fixed point)
+ * in predict_ivd_locations (spine_vision/datasets/classification/cropping.py:463-472).
+ * The three RGB planes are identical, so one plane is produced; /255 and mean/std are
+ * folded into the model's stem (svb_model_create).
+ *
+ *  d_slices : float32 pool holding every slice, slice b starts at element d_offs[b]
+ *  d_offs   : int64 [B]   element offsets into d_slices
+ *  d_hw     : int32 [B,2] (height, width) of each slice
+ *  max_h/w  : host-side maxima over the batch (launch sizing only)
+ *  d_out_u8 : uint8 [B, out_h, out_w]
+ *  d_minmax : float32 [B,2] (min, max) of each slice -- written, may be NULL
+ *  d_ws     : workspace of at least svb_k1_workspace_bytes(...) bytes
+ */
+size_t svb_k1_workspace_bytes(int B, int max_h, int max_w, int out_h, int out_w);
+int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B,
+                            int max_h, int max_w, int out_h, int out_w, uint8_t* d_out_u8,
+                            float* d_minmax, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K3 -- batched coordinate-driven crop + per-crop min-max normalise + letterboxed bilinear
+ * resize (OpenCV 8U INTER_LINEAR fixed point), plus the classifier's Pillow bilinear
+ * Resize of the crop as an optional second output.
+ * Replaces CropContext.crop -> crop_region_horizontal (cropping.py:316-354, 377-404) with
+ * normalize_to_uint8 (io/__init__.py:15-30) and resize_with_padding (cropping.py:104-146),
+ * and the Resize step of ClassificationDataset._build_transforms
+ * (spine_vision/training/datasets/classification.py:247-278) for one channel.
+ *
+ *  d_slice_idx : int32 [N]   which slice each crop is cut from
+ *  d_xy        : float32 [N,2] normalised (x, y) centre in [0,1] (model output)
+ *  d_delta_px  : int32 [N,4] (left, right, top, bottom) from mm_to_pixels (cropping.py:149-169)
+ *  d_crops     : uint8 [N, ch, cw]
+ *  d_crops2    : uint8 [N, oh2, ow2] or NULL
+ *  d_geom      : int32 [N,8] (x1,x2,y1,y2,new_h,new_w,y_off,x_off) or NULL
+ *  max_box_h/w : host-side upper bound of the clipped box size (<= max delta sums); used
+ *                to size shared memory.  SVB_ERR_BOX_TOO_LARGE if it cannot fit on chip.
+ *  flags       : SVB_K3_NO_NORMALIZE = the slices already hold uint8 values (0..255 as float):
+ *                skip the per-crop min-max and only cast -- resize_with_padding on uint8 input.
+ */
+#define SVB_K3_NO_NORMALIZE 1
+size_t svb_k3_workspace_bytes(int ch, int cw, int oh2, int ow2);
+int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                         const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
+                         int N, int max_box_h, int max_box_w, int ch, int cw, uint8_t* d_crops,
+                         int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags, void* d_ws,
+                         size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K2 -- CoordinateRegressor forward (ConvNeXt backbone + MLP head + sigmoid).
+ * Replaces model(tensor) in predict_ivd_locations (cropping.py:474-475) =
+ * CoordinateRegressor.forward (spine_vision/training/models/generic.py:389-391) over the
+ * timm convnext backbone made by BackboneFactory.create
+ * (spine_vision/training/models/backbone.py:165-172) and the head at generic.py:343-351.
+ *
+ * svb_model_create takes the checkpoint's "model_state_dict" (load_localization_model,
+ * cropping.py:436-437) as an array of HOST fp32 tensors under their state-dict names; it
+ * folds /255 + ImageNet mean/std + RGB replication into the 4x4 stem, repacks the weights
+ * for the tensor-core kernels and uploads them.
+ */
+typedef struct svb_model svb_model;
+
+typedef struct svb_weight_desc {
+    const char* name;    /* e.g. "backbone.stages.2.blocks.13.mlp.fc1.weight" */
+    const float* data;   /* host, fp32, contiguous */
+    int32_t ndim;
+    int64_t shape[4];
+} svb_weight_desc;
+
+int svb_model_create(svb_model** out, const svb_weight_desc* weights, int n_weights, int dtype);
+int svb_model_destroy(svb_model* m);
+/* bytes of workspace svb_model_forward needs for micro-batches of `micro_batch` images */
+size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int W);
+/*  d_in_u8  : uint8 [B, H, W] -- K1 output (one plane)
+ *  d_coords : float32 [B, num_levels, 2] in [0,1]
+ *  micro_batch : images per pass through the network (activation working set ~ L2-sized)
+ *  d_times_ms : optional HOST float[SVB_NUM_KERNEL_CLASSES]; when non-NULL the call records
+ *               CUDA events around every launch, synchronises at the end and accumulates
+ *               per-kernel-class milliseconds (profiling / roofline only).
+ */
+enum { SVB_KC_STEM = 0, SVB_KC_DWCONV_LN = 1, SVB_KC_GEMM = 2, SVB_KC_LN_PATCHIFY = 3, SVB_KC_HEAD = 4, SVB_NUM_KERNEL_CLASSES = 5 };
+int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
+                      int micro_batch, void* d_ws, size_t ws_bytes, void* stream, float* times_ms);
+/* model geometry: out[0]=num_levels, out[1]=num_outputs, out[2..5]=dims, out[6..9]=depths */
+int svb_model_info(const svb_model* m, int32_t out[10]);
+/* total tensor-core GEMM flops and launches of one forward over B images (for the roofline) */
+int svb_model_cost(const svb_model* m, int B, int H, int W, double* gemm_flops, int64_t* launches);
+
+/* Standalone GEMM entry for unit tests / ncu: D[M,N] = epilogue(A[M,K] * Wt[N,K]^T).
+ * mode 0: out = gelu(acc + bias)            (fc1)
+ * mode 1: out = resid + gamma*(acc + bias)  (fc2; resid may alias out)
+ * mode 2: out = acc + bias                  (downsample conv as GEMM)
+ * All matrices row-major 16-bit of `dtype`; bias/gamma fp32 [N]. */
+int svb_gemm(const void* d_a, const void* d_w, void* d_out, const void* d_resid, const float* d_bias,
+             const float* d_gamma, int M, int N, int K, int mode, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Standalone layer entries (unit tests / ncu captures of one kernel).  Same kernels the model runs.
+ * x/out are NHWC 16-bit of `dtype`.
+ *  svb_stem_ln     : u8 [B,H,W] -> [B,H/4,W/4,C0]; wf [C0][16], bf [C0] are the FOLDED stem (fp32)
+ *  svb_dwconv_ln   : depthwise 7x7 (taps [49][C] fp32, tap-major) + bias + LayerNorm(C) eps 1e-6
+ *  svb_ln_patchify : LayerNorm2d + 2x2/s2 gather -> [B,H/2,W/2,4C]
+ *  svb_head        : avg-pool over `tokens` + LayerNorm(eps 1e-6) + LayerNorm(eps 1e-5)
+ *                    + Linear(C,HID) + GELU + Linear(HID,NOUT) + sigmoid -> coords fp32 [B,NOUT]
+ */
+int svb_stem_ln(const uint8_t* d_in, const float* d_wf, const float* d_bf, const float* d_lnw, const float* d_lnb,
+                void* d_out, int B, int H, int W, int C0, int dtype, void* stream);
+int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* d_bias, const float* d_lnw,
+                  const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream);
+int svb_ln_patchify(const void* d_x, const float* d_lnw, const float* d_lnb, void* d_out, int B, int H, int W,
+                    int C, int dtype, void* stream);
+int svb_head(const void* d_x, int B, int tokens, int C, const float* n0w, const float* n0b, const float* n1w,
+             const float* n1b, const float* w1, const float* b1, int HID, const float* w2, const float* b2,
+             int NOUT, float* d_coords, int dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPINE_B200_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of ``libspine_b200.so`` (the C ABI in ``include/spine_b200.h``).
+
+There is no CPU fallback: if the shared library is missing or a call fails the
+caller gets an exception, never a silently different code path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = Path(os.environ.get("SPINE_B200_LIB", _PKG / "libspine_b200.so"))
+
+SVB_BF16, SVB_FP16 = 0, 1
+DTYPES = {"bf16": SVB_BF16, "bfloat16": SVB_BF16, "fp16": SVB_FP16, "float16": SVB_FP16, "half": SVB_FP16}
+KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
+
+# every symbol include/spine_b200.h declares
+EXPORTS = (
+    "svb_version", "svb_last_error", "svb_device_check",
+    "svb_k1_workspace_bytes", "svb_k1_normalize_resize",
+    "svb_k3_workspace_bytes", "svb_k3_crop_resample",
+    "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
+    "svb_model_info", "svb_model_cost", "svb_gemm",
+    "svb_stem_ln", "svb_dwconv_ln", "svb_ln_patchify", "svb_head",
+)
+
+
+class SvbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libspine_b200 error {code}: {msg}")
+        self.code = code
+
+
+class WeightDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("ndim", C.c_int32), ("shape", C.c_int64 * 4)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C spine_vision_b200/csrc`). There is no CPU fallback."
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.svb_version.restype = C.c_int
+    lib.svb_last_error.restype = C.c_char_p
+    lib.svb_device_check.restype = C.c_int
+    lib.svb_k1_workspace_bytes.restype = sz
+    lib.svb_k1_workspace_bytes.argtypes = [i32] * 5
+    lib.svb_k1_normalize_resize.restype = C.c_int
+    lib.svb_k1_normalize_resize.argtypes = [vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.svb_k3_workspace_bytes.restype = sz
+    lib.svb_k3_workspace_bytes.argtypes = [i32] * 4
+    lib.svb_k3_crop_resample.restype = C.c_int
+    lib.svb_k3_crop_resample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
+    lib.svb_model_create.restype = C.c_int
+    lib.svb_model_create.argtypes = [C.POINTER(vp), C.POINTER(WeightDesc), i32, i32]
+    lib.svb_model_destroy.restype = C.c_int
+    lib.svb_model_destroy.argtypes = [vp]
+    lib.svb_model_workspace_bytes.restype = sz
+    lib.svb_model_workspace_bytes.argtypes = [vp, i32, i32, i32]
+    lib.svb_model_forward.restype = C.c_int
+    lib.svb_model_forward.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, sz, vp, vp]
+    lib.svb_model_info.restype = C.c_int
+    lib.svb_model_info.argtypes = [vp, C.POINTER(C.c_int32 * 10)]
+    lib.svb_model_cost.restype = C.c_int
+    lib.svb_model_cost.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    lib.svb_gemm.restype = C.c_int
+    lib.svb_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_stem_ln.restype = C.c_int
+    lib.svb_stem_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_dwconv_ln.restype = C.c_int
+    lib.svb_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_ln_patchify.restype = C.c_int
+    lib.svb_ln_patchify.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_head.restype = C.c_int
+    lib.svb_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise SvbError(rc, load().svb_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t) -> int | None:
+    """Device/host pointer of a torch tensor (None passes NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,177 @@
+"""Host-side mirror of the reference's hot-path module, backed by the sm_100a kernels.
+
+Same names, argument meaning and error behaviour as
+``spine_vision/datasets/classification/cropping.py`` and
+``spine_vision/io/__init__.py`` (numpy in / numpy out, host memory), so the
+reference's drivers (``spider.py:114-152``, ``phenikaa.py:178-208``) can import
+these instead.  These per-call wrappers exist for drop-in compatibility; the
+throughput path is the batched ``spine_vision_b200.pipeline.localize_and_crop``.
+
+No function here falls back to the CPU: without the CUDA library and a B200
+every call raises.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Literal
+
+import numpy as np
+import torch
+
+from . import ops
+
+CropMode = Literal["horizontal", "rotated"]
+
+ISOTROPIC_SPACING = (0.3, 0.3, 0.3)  # cropping.py:22
+DEFAULT_IVD_CENTERS = {0: (0.5, 0.25), 1: (0.5, 0.35), 2: (0.5, 0.45), 3: (0.5, 0.55), 4: (0.5, 0.65)}  # cropping.py:28-34
+
+_DEFAULT_DEVICE = "cuda:0"
+
+
+def get_center_fallback_locations() -> dict[int, tuple[float, float]]:
+    """cropping.py:486-492."""
+    return DEFAULT_IVD_CENTERS.copy()
+
+
+def mm_to_pixels(delta_mm, spacing) -> tuple[int, int, int, int]:
+    """cropping.py:149-169 -- pure host arithmetic (Python ``round`` = banker's rounding)."""
+    row_spacing, col_spacing = spacing
+    left_mm, right_mm, top_mm, bottom_mm = delta_mm
+    return (
+        int(round(left_mm / col_spacing)),
+        int(round(right_mm / col_spacing)),
+        int(round(top_mm / row_spacing)),
+        int(round(bottom_mm / row_spacing)),
+    )
+
+
+def normalize_to_uint8(arr: np.ndarray, device: str = _DEFAULT_DEVICE) -> np.ndarray:
+    """io/__init__.py:15-30 on the GPU (K1 with an identity resize).
+
+    Min-max is global and the map is elementwise, so the array is processed as a flat
+    ``[rows, 4096]`` sheet padded with copies of its first element (which cannot move
+    the minimum or the maximum)."""
+    a = np.asarray(arr)
+    if a.size == 0:
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")  # numpy's error
+    flat = a.astype(np.float32).ravel()
+    cols = 4096 if flat.size >= 4096 else (flat.size + 3) // 4 * 4
+    rows = (flat.size + cols - 1) // cols
+    sheet = np.full(rows * cols, flat[0], dtype=np.float32)
+    sheet[: flat.size] = flat
+    pool = ops.SlicePool.from_numpy([sheet.reshape(rows, cols)], device)
+    out = ops.normalize_resize(pool, (rows, cols))
+    return out.cpu().numpy().ravel()[: flat.size].reshape(a.shape)
+
+
+def resize_with_padding(image: np.ndarray, target_size: tuple[int, int], device: str = _DEFAULT_DEVICE) -> np.ndarray:
+    """cropping.py:104-146 for uint8 input: letterboxed cv2-compatible INTER_LINEAR resize (K3 on
+    the whole image with the per-crop normalisation switched off)."""
+    img = np.asarray(image)
+    if img.dtype != np.uint8:
+        raise TypeError("resize_with_padding: the GPU path takes uint8 images (the reference's own call site, "
+                        "cropping.py:354, always passes uint8)")
+    h, w = img.shape[:2]
+    pool = ops.SlicePool.from_numpy([img.astype(np.float32)], device)
+    dev = pool.data.device
+    idx = torch.zeros(1, dtype=torch.int32, device=dev)
+    xy = torch.zeros((1, 2), dtype=torch.float32, device=dev)
+    delta = torch.tensor([[0, w, 0, h]], dtype=torch.int32, device=dev)
+    crops, _, _ = ops.crop_resample(pool, idx, xy, delta, (h, w), target_size, None, normalize=False)
+    return crops[0].cpu().numpy()
+
+
+def crop_region_horizontal(image, center_x, center_y, crop_size, crop_delta, device: str = _DEFAULT_DEVICE) -> np.ndarray:
+    """cropping.py:316-354."""
+    ctx = CropContext(np.asarray(image), {0: (center_x, center_y)}, tuple(crop_size), tuple(crop_delta), "horizontal", device=device)
+    return ctx.crop(0)
+
+
+@dataclass
+class CropContext:
+    """cropping.py:357-404.  The image is staged to the device once; ``crop`` is one K3 launch,
+    ``crop_all`` cuts every requested level in a single launch."""
+
+    image: np.ndarray
+    ivd_locations: dict
+    crop_size: tuple
+    crop_delta_px: tuple
+    mode: CropMode = "horizontal"
+    last_disc_angle_boost: float = 1.0
+    rotation_angles: dict | None = None
+    device: str = _DEFAULT_DEVICE
+
+    def __post_init__(self) -> None:
+        if self.mode != "horizontal":
+            raise NotImplementedError("crop mode 'rotated' (cropping.py:172-313) is a SURVEY 8(f) next-row; "
+                                      "only the default 'horizontal' mode is built")
+        self._pool = None
+
+    def _ensure_pool(self):
+        if self._pool is None:
+            self._pool = ops.SlicePool.from_numpy([np.asarray(self.image)], self.device)
+        return self._pool
+
+    def crop_all(self, level_indices) -> dict[int, np.ndarray]:
+        levels = [i for i in level_indices if i in self.ivd_locations]
+        if not levels:
+            return {}
+        pool = self._ensure_pool()
+        dev = pool.data.device
+        xy = torch.tensor([[float(self.ivd_locations[i][0]), float(self.ivd_locations[i][1])] for i in levels],
+                          dtype=torch.float32).to(dev)
+        idx = torch.zeros(len(levels), dtype=torch.int32, device=dev)
+        l, r, t, b = (int(v) for v in self.crop_delta_px)
+        delta = torch.tensor([[l, r, t, b]] * len(levels), dtype=torch.int32).to(dev)
+        h, w = pool.shapes[0]
+        crops, _, _ = ops.crop_resample(pool, idx, xy, delta, (min(h, max(t + b, 1)), min(w, max(l + r, 1))),
+                                        self.crop_size, None)
+        host = crops.cpu().numpy()
+        return {lvl: host[k] for k, lvl in enumerate(levels)}
+
+    def crop(self, level_idx: int) -> np.ndarray | None:
+        if level_idx not in self.ivd_locations:
+            return None
+        return self.crop_all([level_idx])[level_idx]
+
+
+class LocalizationModel:
+    """What ``load_localization_model`` returns: the reference hands back an ``nn.Module`` in eval
+    mode; this is its inference-only device twin (``eval()`` / ``to()`` are accepted no-ops)."""
+
+    def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 32):
+        import os
+
+        dtype = dtype or os.environ.get("SPINE_B200_DTYPE", "bf16")
+        self.device = device
+        self.engine = ops.LocalizationEngine(state_dict, device, dtype, micro_batch)
+        self.num_levels = self.engine.num_levels
+
+    def eval(self):
+        return self
+
+    def to(self, *_a, **_k):
+        return self
+
+    def predict_u8(self, planes_u8: torch.Tensor, times: dict | None = None) -> torch.Tensor:
+        return self.engine.forward(planes_u8, times)
+
+
+def load_localization_model(model_path: Path, variant: str, device: str, dtype: str | None = None) -> LocalizationModel:
+    """cropping.py:407-441 -- same checkpoint format (``torch.save`` dict whose
+    ``"model_state_dict"`` holds the 348 ``backbone.*`` / ``head.*`` tensors,
+    trainers/base.py:695-706), strict key check, weights repacked for the tensor cores."""
+    if variant.startswith("v2_"):
+        raise NotImplementedError("ConvNeXt-V2 backbones (GRN) are not built; ConvNeXt v1 widths that are multiples of 128 are")
+    checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
+    return LocalizationModel(checkpoint["model_state_dict"], device, dtype)
+
+
+def predict_ivd_locations(model: LocalizationModel, image: np.ndarray, device: str, image_size: tuple[int, int]):
+    """cropping.py:444-483 -- one series, batch 1 (drop-in signature).  K1 then the model, one D2H."""
+    pool = ops.SlicePool.from_numpy([np.asarray(image)], device)
+    planes = ops.normalize_resize(pool, image_size)
+    out = model.predict_u8(planes).cpu().numpy()[0]
+    return {i: (float(out[i, 0]), float(out[i, 1])) for i in range(out.shape[0])}

@@ -1,0 +1,707 @@
+// svb_convnext.cu -- host side of the CoordinateRegressor forward: state-dict ingestion
+// (timm ConvNeXt key scheme), stem fold, 16-bit repack, TMA descriptors, launch plan.
+//
+// Replaces the device work of predict_ivd_locations' model(tensor)
+// (spine_vision/datasets/classification/cropping.py:474-475) for the module built by
+// load_localization_model (cropping.py:407-441).
+#include "svb_convnext_kernels.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace svb;
+
+namespace svb {
+
+static const double IMAGENET_MEAN[3] = {0.485, 0.456, 0.406};  // cropping.py:23
+static const double IMAGENET_STD[3] = {0.229, 0.224, 0.225};   // cropping.py:24
+
+struct BlockParams {
+    float *wdw, *bdw, *lnw, *lnb, *b1, *b2, *gamma;
+    void *w1, *w2;  // 16-bit [4C][C], [C][4C]
+    CUtensorMap wdw_map, w1_map, w2_map;
+};
+struct DownParams {
+    float *lnw, *lnb, *bias;
+    void* w;  // 16-bit [Cout][4*Cin], k = (ky*2+kx)*Cin + ci
+    CUtensorMap w_map;
+};
+struct ActPlan {  // tensor maps that depend on the workspace pointer and the micro-batch geometry
+    const void* ws = nullptr;
+    int nb = 0, H = 0, W = 0;
+    CUtensorMap x_map[4];   // 4-D NHWC halo maps per stage
+    CUtensorMap a_map[4];   // [M, C]   fc1 A operand
+    CUtensorMap h_map[4];   // [M, 4C]  fc2 A operand
+    CUtensorMap a2_map[4];  // [M/4, 4C_prev] downsample A operand (index = destination stage)
+};
+
+}  // namespace svb
+
+struct svb_model {
+    int dtype = SVB_BF16;
+    int dims[4] = {0, 0, 0, 0};
+    int depths[4] = {0, 0, 0, 0};
+    int hid = 0, nout = 0;
+    int device = 0;
+    void* slab = nullptr;
+    size_t slab_bytes = 0;
+    float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
+    std::vector<BlockParams> blocks[4];
+    DownParams down[4];
+    float *hn0w = nullptr, *hn0b = nullptr, *hn1w = nullptr, *hn1b = nullptr, *hw1 = nullptr, *hb1 = nullptr,
+          *hw2 = nullptr, *hb2 = nullptr;
+    ActPlan plans[2];
+    int next_plan = 0;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace svb {
+
+static CUtensorMapDataType tmap_dtype(int dtype) {
+    return dtype == SVB_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+}
+static uint16_t to16(float v, int dtype) {
+    if (dtype == SVB_FP16) {
+        float c = v > 65504.f ? 65504.f : (v < -65504.f ? -65504.f : v);
+        __half h = __float2half_rn(c);
+        uint16_t u;
+        memcpy(&u, &h, 2);
+        return u;
+    }
+    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    uint16_t u;
+    memcpy(&u, &h, 2);
+    return u;
+}
+
+// K-major 2-D operand map: rows x K, box {64, box_rows}, 128-byte swizzle
+static int make_operand_map(CUtensorMap* map, int dtype, const void* base, uint64_t rows, uint64_t K, uint32_t box_rows) {
+    const uint64_t dims[2] = {K, rows};
+    const uint64_t strides[1] = {K * 2};
+    const uint32_t box[2] = {64, box_rows};
+    return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int gemm_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
+static int dw_th(int C) { return C >= 1024 ? 4 : 8; }
+
+struct HostWeights {
+    std::map<std::string, const svb_weight_desc*> by_name;
+    const svb_weight_desc* get(const std::string& n) const {
+        auto it = by_name.find(n);
+        return it == by_name.end() ? nullptr : it->second;
+    }
+};
+static int64_t numel(const svb_weight_desc* w) {
+    int64_t n = 1;
+    for (int i = 0; i < w->ndim; ++i) n *= w->shape[i];
+    return n;
+}
+
+// bump allocator over one device slab (two passes: size, then fill)
+struct Slab {
+    uint8_t* base = nullptr;
+    size_t off = 0;
+    std::vector<uint8_t> host;
+    void* put(const void* src, size_t bytes) {
+        off = align_up(off, 256);
+        if (host.size() < off + bytes) host.resize(off + bytes);
+        memcpy(host.data() + off, src, bytes);
+        void* p = reinterpret_cast<void*>(off);  // offset now, rebased after upload
+        off += bytes;
+        return p;
+    }
+};
+template <typename P> static void rebase(P*& p, uint8_t* base) { p = reinterpret_cast<P*>(base + reinterpret_cast<size_t>(p)); }
+
+}  // namespace svb
+
+extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights, int n_weights, int dtype) {
+    SVB_REQUIRE(out && weights && n_weights > 0, SVB_ERR_INVALID_ARG, "model_create: null/empty arguments");
+    SVB_REQUIRE(dtype == SVB_BF16 || dtype == SVB_FP16, SVB_ERR_INVALID_ARG, "model_create: dtype %d", dtype);
+    if (int rc = check_device_sm100()) return rc;
+    *out = nullptr;
+    HostWeights hwts;
+    for (int i = 0; i < n_weights; ++i) {
+        SVB_REQUIRE(weights[i].name && weights[i].data, SVB_ERR_INVALID_ARG, "model_create: weight %d has null name/data", i);
+        hwts.by_name[weights[i].name] = &weights[i];
+    }
+    auto need = [&](const std::string& n, const svb_weight_desc** w) -> int {
+        *w = hwts.get(n);
+        SVB_REQUIRE(*w != nullptr, SVB_ERR_MISSING_WEIGHT, "model_create: state dict has no '%s'", n.c_str());
+        return SVB_OK;
+    };
+#define NEED(var, name)                                   \
+    const svb_weight_desc* var = nullptr;                 \
+    if (int rc = need((name), &var)) return rc;
+
+    svb_model* m = new svb_model();
+    std::unique_ptr<svb_model> guard(m);
+    m->dtype = dtype;
+    SVB_CUDA_OK(cudaGetDevice(&m->device));
+
+    // ---- geometry from the state dict -------------------------------------------------------
+    NEED(stem_w, "backbone.stem.0.weight");
+    SVB_REQUIRE(stem_w->ndim == 4 && stem_w->shape[1] == 3 && stem_w->shape[2] == 4 && stem_w->shape[3] == 4,
+                SVB_ERR_UNSUPPORTED_MODEL, "stem conv must be [C0,3,4,4]");
+    for (int s = 0; s < 4; ++s) {
+        int d = 0;
+        while (hwts.get("backbone.stages." + std::to_string(s) + ".blocks." + std::to_string(d) + ".gamma")) ++d;
+        SVB_REQUIRE(d > 0, SVB_ERR_MISSING_WEIGHT, "no blocks found for stage %d", s);
+        m->depths[s] = d;
+        const svb_weight_desc* g = hwts.get("backbone.stages." + std::to_string(s) + ".blocks.0.gamma");
+        m->dims[s] = (int)g->shape[0];
+        SVB_REQUIRE(m->dims[s] % 128 == 0 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
+                    "stage %d width %d: this build supports ConvNeXt widths that are multiples of 128 "
+                    "(base, xlarge); tiny/small/large are not built yet", s, m->dims[s]);
+    }
+    SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
+    SVB_REQUIRE(m->dims[0] == 128 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL, "stem width %d unsupported", m->dims[0]);
+    NEED(head_w1, "head.2.weight");
+    NEED(head_w2, "head.5.weight");
+    m->hid = (int)head_w1->shape[0];
+    m->nout = (int)head_w2->shape[0];
+    SVB_REQUIRE(head_w1->shape[1] == m->dims[3] && head_w2->shape[1] == m->hid && m->nout % 2 == 0,
+                SVB_ERR_UNSUPPORTED_MODEL, "head shapes do not match generic.py:343-351");
+
+    Slab slab;
+    auto put_f32 = [&](const svb_weight_desc* w, int64_t expect) -> float* {
+        if (numel(w) != expect) return nullptr;
+        return static_cast<float*>(slab.put(w->data, (size_t)expect * 4));
+    };
+#define PUT_F32(dst, name, count)                                                                             \
+    {                                                                                                         \
+        NEED(_w, (name));                                                                                     \
+        dst = put_f32(_w, (count));                                                                           \
+        SVB_REQUIRE(numel(_w) == (int64_t)(count), SVB_ERR_UNSUPPORTED_MODEL, "'%s' has %lld elements, expected %lld", \
+                    std::string(name).c_str(), (long long)numel(_w), (long long)(count));                     \
+    }
+
+    // ---- stem: fold /255, mean/std and the 3 identical input planes ------
+    {
+        const int C0 = m->dims[0];
+        NEED(stem_b, "backbone.stem.0.bias");
+        SVB_REQUIRE(numel(stem_b) == C0, SVB_ERR_UNSUPPORTED_MODEL, "stem bias size");
+        std::vector<float> wf((size_t)C0 * 16), bf(C0);
+        for (int co = 0; co < C0; ++co) {
+            double bacc = stem_b->data[co];
+            for (int p = 0; p < 16; ++p) {
+                double acc = 0.0;
+                for (int c = 0; c < 3; ++c) {
+                    const double w = stem_w->data[((size_t)co * 3 + c) * 16 + p];
+                    acc += w / (255.0 * IMAGENET_STD[c]);
+                    bacc -= w * IMAGENET_MEAN[c] / IMAGENET_STD[c];
+                }
+                wf[(size_t)co * 16 + p] = (float)acc;
+            }
+            bf[co] = (float)bacc;
+        }
+        m->stem_w = static_cast<float*>(slab.put(wf.data(), wf.size() * 4));
+        m->stem_b = static_cast<float*>(slab.put(bf.data(), bf.size() * 4));
+        PUT_F32(m->stem_lnw, "backbone.stem.1.weight", C0);
+        PUT_F32(m->stem_lnb, "backbone.stem.1.bias", C0);
+    }
+    // ---- stages ----------------------------------------------------------------------------
+    std::vector<uint16_t> tmp16;
+    for (int s = 0; s < 4; ++s) {
+        const int C = m->dims[s];
+        const std::string sp = "backbone.stages." + std::to_string(s) + ".";
+        if (s > 0) {
+            const int Cin = m->dims[s - 1];
+            DownParams& d = m->down[s];
+            PUT_F32(d.lnw, sp + "downsample.0.weight", Cin);
+            PUT_F32(d.lnb, sp + "downsample.0.bias", Cin);
+            PUT_F32(d.bias, sp + "downsample.1.bias", C);
+            NEED(dw, sp + "downsample.1.weight");
+            SVB_REQUIRE(numel(dw) == (int64_t)C * Cin * 4, SVB_ERR_UNSUPPORTED_MODEL, "downsample conv size (stage %d)", s);
+            tmp16.resize((size_t)C * Cin * 4);
+            for (int co = 0; co < C; ++co)
+                for (int ci = 0; ci < Cin; ++ci)
+                    for (int ky = 0; ky < 2; ++ky)
+                        for (int kx = 0; kx < 2; ++kx)
+                            tmp16[(size_t)co * 4 * Cin + (size_t)(ky * 2 + kx) * Cin + ci] =
+                                to16(dw->data[(((size_t)co * Cin + ci) * 2 + ky) * 2 + kx], dtype);
+            d.w = slab.put(tmp16.data(), tmp16.size() * 2);
+        }
+        m->blocks[s].resize(m->depths[s]);
+        for (int j = 0; j < m->depths[s]; ++j) {
+            BlockParams& bp = m->blocks[s][j];
+            const std::string bn = sp + "blocks." + std::to_string(j) + ".";
+            NEED(cw, bn + "conv_dw.weight");
+            SVB_REQUIRE(numel(cw) == (int64_t)C * 49, SVB_ERR_UNSUPPORTED_MODEL, "conv_dw must be [C,1,7,7]");
+            std::vector<float> taps((size_t)49 * C);  // [tap][C]
+            for (int c = 0; c < C; ++c)
+                for (int t = 0; t < 49; ++t) taps[(size_t)t * C + c] = cw->data[(size_t)c * 49 + t];
+            bp.wdw = static_cast<float*>(slab.put(taps.data(), taps.size() * 4));
+            PUT_F32(bp.bdw, bn + "conv_dw.bias", C);
+            PUT_F32(bp.lnw, bn + "norm.weight", C);
+            PUT_F32(bp.lnb, bn + "norm.bias", C);
+            PUT_F32(bp.b1, bn + "mlp.fc1.bias", 4 * C);
+            PUT_F32(bp.b2, bn + "mlp.fc2.bias", C);
+            PUT_F32(bp.gamma, bn + "gamma", C);
+            NEED(w1, bn + "mlp.fc1.weight");
+            NEED(w2, bn + "mlp.fc2.weight");
+            SVB_REQUIRE(numel(w1) == (int64_t)4 * C * C && numel(w2) == (int64_t)4 * C * C, SVB_ERR_UNSUPPORTED_MODEL,
+                        "mlp weights must be [4C,C] and [C,4C]");
+            tmp16.resize((size_t)4 * C * C);
+            for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(w1->data[i], dtype);
+            bp.w1 = slab.put(tmp16.data(), tmp16.size() * 2);
+            for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(w2->data[i], dtype);
+            bp.w2 = slab.put(tmp16.data(), tmp16.size() * 2);
+        }
+    }
+    // ---- head --------------------------------------------------------------------------------
+    {
+        const int C = m->dims[3];
+        PUT_F32(m->hn0w, "backbone.head.norm.weight", C);
+        PUT_F32(m->hn0b, "backbone.head.norm.bias", C);
+        PUT_F32(m->hn1w, "head.0.weight", C);
+        PUT_F32(m->hn1b, "head.0.bias", C);
+        PUT_F32(m->hw1, "head.2.weight", (int64_t)m->hid * C);
+        PUT_F32(m->hb1, "head.2.bias", m->hid);
+        PUT_F32(m->hw2, "head.5.weight", (int64_t)m->nout * m->hid);
+        PUT_F32(m->hb2, "head.5.bias", m->nout);
+    }
+    // ---- upload + rebase + weight tensor maps ------------------------------------------------
+    m->slab_bytes = align_up(slab.off, 256);
+    SVB_CUDA_OK(cudaMalloc(&m->slab, m->slab_bytes));
+    SVB_CUDA_OK(cudaMemcpy(m->slab, slab.host.data(), slab.off, cudaMemcpyHostToDevice));
+    uint8_t* base = static_cast<uint8_t*>(m->slab);
+    rebase(m->stem_w, base); rebase(m->stem_b, base); rebase(m->stem_lnw, base); rebase(m->stem_lnb, base);
+    rebase(m->hn0w, base); rebase(m->hn0b, base); rebase(m->hn1w, base); rebase(m->hn1b, base);
+    rebase(m->hw1, base); rebase(m->hb1, base); rebase(m->hw2, base); rebase(m->hb2, base);
+    for (int s = 0; s < 4; ++s) {
+        const int C = m->dims[s];
+        if (s > 0) {
+            DownParams& d = m->down[s];
+            rebase(d.lnw, base); rebase(d.lnb, base); rebase(d.bias, base);
+            uint8_t* w = base + reinterpret_cast<size_t>(d.w);
+            d.w = w;
+            if (int rc = make_operand_map(&d.w_map, dtype, d.w, C, 4 * (uint64_t)m->dims[s - 1], gemm_bn(C))) return rc;
+        }
+        for (auto& bp : m->blocks[s]) {
+            rebase(bp.wdw, base); rebase(bp.bdw, base); rebase(bp.lnw, base); rebase(bp.lnb, base);
+            rebase(bp.b1, base); rebase(bp.b2, base); rebase(bp.gamma, base);
+            bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
+            bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
+            if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C))) return rc;
+            if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C))) return rc;
+            const uint64_t dims[2] = {(uint64_t)C, 49};
+            const uint64_t strides[1] = {(uint64_t)C * 4};
+            const uint32_t box[2] = {64, 49};
+            if (int rc = encode_tmap(&bp.wdw_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, bp.wdw, dims, strides, box,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE))
+                return rc;
+        }
+    }
+    *out = guard.release();
+    return SVB_OK;
+#undef NEED
+#undef PUT_F32
+}
+
+extern "C" int svb_model_destroy(svb_model* m) {
+    if (!m) return SVB_OK;
+    for (auto e : m->events) cudaEventDestroy(e);
+    if (m->slab) cudaFree(m->slab);
+    delete m;
+    return SVB_OK;
+}
+
+extern "C" int svb_model_info(const svb_model* m, int32_t out[10]) {
+    SVB_REQUIRE(m && out, SVB_ERR_INVALID_ARG, "model_info: null argument");
+    out[0] = m->nout / 2;
+    out[1] = 2;
+    for (int i = 0; i < 4; ++i) { out[2 + i] = m->dims[i]; out[6 + i] = m->depths[i]; }
+    return SVB_OK;
+}
+
+namespace svb {
+
+struct WsLayout {
+    size_t x, a, h, total;
+};
+static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
+    // stage 0 is the largest for every buffer (tokens/4, channels*2 per stage)
+    const size_t t0 = (size_t)nb * (H / 4) * (W / 4);
+    const size_t c0 = m->dims[0];
+    WsLayout L;
+    size_t o = 0;
+    L.x = o; o += align_up(t0 * c0 * 2, 1024);
+    L.a = o; o += align_up(t0 * c0 * 2, 1024);
+    L.h = o; o += align_up(t0 * c0 * 4 * 2, 1024);
+    L.total = o;
+    return L;
+}
+
+static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int W) {
+    const WsLayout L = ws_layout(m, nb, H, W);
+    int h = H / 4, w = W / 4;
+    for (int s = 0; s < 4; ++s) {
+        const uint64_t C = m->dims[s];
+        const uint64_t M = (uint64_t)nb * h * w;
+        {
+            const uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
+            const uint64_t strides[3] = {C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+            const uint32_t box[4] = {64, 14, (uint32_t)(dw_th((int)C) + 6), 1};
+            if (int rc = encode_tmap(&p->x_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE))
+                return rc;
+        }
+        if (int rc = make_operand_map(&p->a_map[s], m->dtype, ws + L.a, M, C, 128)) return rc;
+        if (int rc = make_operand_map(&p->h_map[s], m->dtype, ws + L.h, M, 4 * C, 128)) return rc;
+        if (s > 0) {
+            if (int rc = make_operand_map(&p->a2_map[s], m->dtype, ws + L.a, M, 4 * (uint64_t)m->dims[s - 1], 128)) return rc;
+        }
+        h /= 2;
+        w /= 2;
+    }
+    p->ws = ws;
+    p->nb = nb;
+    p->H = H;
+    p->W = W;
+    return SVB_OK;
+}
+
+static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** out) {
+    for (auto& p : m->plans)
+        if (p.ws == ws && p.nb == nb && p.H == H && p.W == W) { *out = &p; return SVB_OK; }
+    ActPlan* p = &m->plans[m->next_plan];
+    m->next_plan ^= 1;
+    if (int rc = build_plan(m, p, ws, nb, H, W)) { p->ws = nullptr; return rc; }
+    *out = p;
+    return SVB_OK;
+}
+
+// ---- launchers -------------------------------------------------------------------------------
+template <typename T, int BN, int MODE>
+static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, void* out, const void* resid, const float* bias,
+                         const float* gamma, int M, int N, int K, cudaStream_t st) {
+    using Cfg = GemmCfg<BN>;
+    auto kern = gemm_kernel<T, BN, MODE>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = ceil_div(M, 128) * ceil_div(N, BN);
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(a, w, static_cast<T*>(out), static_cast<const T*>(resid), bias,
+                                                          gamma, M, N, K);
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}
+template <typename T>
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, void* out, const void* resid, const float* bias,
+                       const float* gamma, int M, int N, int K, int mode, cudaStream_t st) {
+    SVB_REQUIRE(N % 32 == 0 && K % 8 == 0, SVB_ERR_INVALID_ARG, "gemm: N (%d) must be a multiple of 32, K (%d) of 8", N, K);
+    const int bn = gemm_bn(N);
+#define SVB_GEMM_CASE(BN_, MODE_)                                                                       \
+    if (bn == BN_ && mode == MODE_) return launch_gemm_t<T, BN_, MODE_>(a, w, out, resid, bias, gamma, M, N, K, st);
+    SVB_GEMM_CASE(256, GEMM_GELU)
+    SVB_GEMM_CASE(128, GEMM_GELU)
+    SVB_GEMM_CASE(256, GEMM_RESID)
+    SVB_GEMM_CASE(128, GEMM_RESID)
+    SVB_GEMM_CASE(256, GEMM_BIAS)
+    SVB_GEMM_CASE(128, GEMM_BIAS)
+#undef SVB_GEMM_CASE
+    return set_error(SVB_ERR_INVALID_ARG, "gemm: unsupported mode %d", mode);
+}
+
+template <typename T, int C, int TH>
+static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* out, int nb, int H, int W, cudaStream_t st) {
+    using Cfg = DwCfg<C, TH>;
+    auto kern = dwconv_ln_kernel<T, C, TH>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tx = ceil_div(W, Cfg::TW), ty = ceil_div(H, TH);
+    kern<<<nb * tx * ty, 256, Cfg::SMEM_BYTES, st>>>(x, bp.wdw_map, bp.bdw, bp.lnw, bp.lnb, static_cast<T*>(out), H, W, tx, ty);
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}
+template <typename T>
+static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out, int C, int nb, int H, int W, cudaStream_t st) {
+    switch (C) {
+        case 128: return launch_dwconv_t<T, 128, 8>(x, bp, out, nb, H, W, st);
+        case 256: return launch_dwconv_t<T, 256, 8>(x, bp, out, nb, H, W, st);
+        case 512: return launch_dwconv_t<T, 512, 8>(x, bp, out, nb, H, W, st);
+        case 1024: return launch_dwconv_t<T, 1024, 4>(x, bp, out, nb, H, W, st);
+        case 2048: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: width 2048 (xlarge stage 3) is not built yet");
+    }
+    return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: unsupported width %d", C);
+}
+template <typename T>
+static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int Cin, int nb, int H, int W, cudaStream_t st) {
+    const long long tokens = (long long)nb * H * W;
+    long long blocks = ceil_div<long long>(tokens, 8);
+    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    const T* xp = static_cast<const T*>(x);
+    T* ap = static_cast<T*>(a2);
+    switch (Cin) {
+        case 128: ln_patchify_kernel<T, 128><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 256: ln_patchify_kernel<T, 256><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 512: ln_patchify_kernel<T, 512><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 1024: ln_patchify_kernel<T, 1024><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        default: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "ln_patchify: unsupported width %d", Cin);
+    }
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}
+
+struct Timer {  // optional per-launch CUDA-event timing, accumulated per kernel class
+    svb_model* m;
+    cudaStream_t st;
+    bool on;
+    std::vector<int> classes;
+    size_t used = 0;
+    int begin(int cls) {
+        if (!on) return SVB_OK;
+        while (m->events.size() < used + 2) {
+            cudaEvent_t e;
+            SVB_CUDA_OK(cudaEventCreate(&e));
+            m->events.push_back(e);
+        }
+        classes.push_back(cls);
+        SVB_CUDA_OK(cudaEventRecord(m->events[used], st));
+        return SVB_OK;
+    }
+    int end() {
+        if (!on) return SVB_OK;
+        SVB_CUDA_OK(cudaEventRecord(m->events[used + 1], st));
+        used += 2;
+        return SVB_OK;
+    }
+    int finish(float* times) {
+        if (!on) return SVB_OK;
+        SVB_CUDA_OK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < classes.size(); ++i) {
+            float ms = 0.f;
+            SVB_CUDA_OK(cudaEventElapsedTime(&ms, m->events[2 * i], m->events[2 * i + 1]));
+            times[classes[i]] += ms;
+        }
+        return SVB_OK;
+    }
+};
+
+template <typename T>
+static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, float* coords, uint8_t* ws, cudaStream_t st,
+                         Timer& tm) {
+    ActPlan* plan = nullptr;
+    if (int rc = get_plan(m, ws, nb, H, W, &plan)) return rc;
+    const WsLayout L = ws_layout(m, nb, H, W);
+    T* X = reinterpret_cast<T*>(ws + L.x);
+    T* A = reinterpret_cast<T*>(ws + L.a);
+    T* Hd = reinterpret_cast<T*>(ws + L.h);
+#define RUN(cls, call)                             \
+    {                                              \
+        if (int rc = tm.begin(cls)) return rc;     \
+        if (int rc = (call)) return rc;            \
+        if (int rc = tm.end()) return rc;          \
+    }
+    // stem
+    {
+        const long long tokens = (long long)nb * (H / 4) * (W / 4);
+        long long blocks = ceil_div<long long>(tokens, 8 * 16);
+        if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+        if (blocks < 1) blocks = 1;
+        if (int rc = tm.begin(SVB_KC_STEM)) return rc;
+        if (m->dims[0] == 128)
+            stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
+        else
+            stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
+        SVB_CUDA_OK(cudaGetLastError());
+        if (int rc = tm.end()) return rc;
+    }
+    int h = H / 4, w = W / 4;
+    for (int s = 0; s < 4; ++s) {
+        const int C = m->dims[s];
+        if (s > 0) {
+            const int Cin = m->dims[s - 1];
+            RUN(SVB_KC_LN_PATCHIFY, launch_ln_patchify<T>(X, m->down[s], A, Cin, nb, h, w, st));
+            h /= 2;
+            w /= 2;
+            const int M2 = nb * h * w;
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a2_map[s], m->down[s].w_map, X, nullptr, m->down[s].bias, nullptr, M2, C,
+                                            4 * Cin, GEMM_BIAS, st));
+        }
+        const int M = nb * h * w;
+        for (const BlockParams& bp : m->blocks[s]) {
+            RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, Hd, nullptr, bp.b1, nullptr, M, 4 * C, C, GEMM_GELU, st));
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, X, X, bp.b2, bp.gamma, M, C, 4 * C, GEMM_RESID, st));
+        }
+    }
+    {
+        const int C = m->dims[3];
+        const size_t smem = (size_t)(C + m->hid + 8) * 4;
+        if (int rc = tm.begin(SVB_KC_HEAD)) return rc;
+        head_kernel<T><<<nb, 256, smem, st>>>(X, h * w, C, m->hn0w, m->hn0b, m->hn1w, m->hn1b, m->hw1, m->hb1, m->hid, m->hw2,
+                                              m->hb2, m->nout, coords);
+        SVB_CUDA_OK(cudaGetLastError());
+        if (int rc = tm.end()) return rc;
+    }
+#undef RUN
+    return SVB_OK;
+}
+
+}  // namespace svb
+
+extern "C" size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int W) {
+    if (!m || micro_batch <= 0 || H <= 0 || W <= 0) return 0;
+    return ws_layout(m, micro_batch, H, W).total;
+}
+
+extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
+                                 int micro_batch, void* d_ws, size_t ws_bytes, void* stream_, float* times_ms) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    SVB_REQUIRE(m && d_in_u8 && d_coords && d_ws, SVB_ERR_INVALID_ARG, "model_forward: null argument");
+    SVB_REQUIRE(B >= 0 && micro_batch > 0, SVB_ERR_INVALID_ARG, "model_forward: B=%d micro_batch=%d", B, micro_batch);
+    SVB_REQUIRE(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, SVB_ERR_INVALID_ARG,
+                "model_forward: input %dx%d must be a positive multiple of 32 (ConvNeXt stride)", H, W);
+    if (micro_batch > B && B > 0) micro_batch = B;
+    const size_t need = ws_layout(m, micro_batch, H, W).total;
+    SVB_REQUIRE(ws_bytes >= need, SVB_ERR_WORKSPACE_TOO_SMALL, "model_forward: workspace %zu < %zu bytes", ws_bytes, need);
+    SVB_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 1023) == 0, SVB_ERR_INVALID_ARG, "model_forward: workspace must be 1024-byte aligned");
+    Timer tm{m, st, times_ms != nullptr};
+    for (int b0 = 0; b0 < B; b0 += micro_batch) {
+        const int nb = (B - b0) < micro_batch ? (B - b0) : micro_batch;
+        int rc;
+        if (m->dtype == SVB_FP16)
+            rc = forward_chunk<__half>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout,
+                                       static_cast<uint8_t*>(d_ws), st, tm);
+        else
+            rc = forward_chunk<__nv_bfloat16>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout,
+                                              static_cast<uint8_t*>(d_ws), st, tm);
+        if (rc) return rc;
+    }
+    return tm.finish(times_ms);
+}
+
+extern "C" int svb_model_cost(const svb_model* m, int B, int H, int W, double* gemm_flops, int64_t* launches) {
+    SVB_REQUIRE(m, SVB_ERR_INVALID_ARG, "model_cost: null model");
+    double fl = 0.0;
+    int64_t n = 1;  // stem
+    int h = H / 4, w = W / 4;
+    for (int s = 0; s < 4; ++s) {
+        const double C = m->dims[s];
+        if (s > 0) {
+            h /= 2;
+            w /= 2;
+            fl += 2.0 * B * h * w * C * 4.0 * m->dims[s - 1];
+            n += 2;
+        }
+        fl += (double)m->depths[s] * 2.0 * (2.0 * B * h * w * C * 4.0 * C);
+        n += 3 * (int64_t)m->depths[s];
+    }
+    n += 1;  // head
+    if (gemm_flops) *gemm_flops = fl;
+    if (launches) *launches = n;
+    return SVB_OK;
+}
+
+extern "C" int svb_gemm(const void* d_a, const void* d_w, void* d_out, const void* d_resid, const float* d_bias,
+                        const float* d_gamma, int M, int N, int K, int mode, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_a && d_w && d_out && d_bias, SVB_ERR_INVALID_ARG, "gemm: null argument");
+    SVB_REQUIRE(mode != GEMM_RESID || (d_resid && d_gamma), SVB_ERR_INVALID_ARG, "gemm: residual mode needs resid and gamma");
+    SVB_REQUIRE(M > 0 && N > 0 && K > 0, SVB_ERR_INVALID_ARG, "gemm: bad shape");
+    CUtensorMap a_map, w_map;
+    if (int rc = make_operand_map(&a_map, dtype, d_a, M, K, 128)) return rc;
+    if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn(N))) return rc;
+    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, d_out, d_resid, d_bias, d_gamma, M, N, K, mode, st);
+    return launch_gemm<__nv_bfloat16>(a_map, w_map, d_out, d_resid, d_bias, d_gamma, M, N, K, mode, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone layer entries (tests / profiling): the same kernels, tensor maps built per call
+template <typename T>
+static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const float* lnw, const float* lnb, void* out,
+                      int B, int H, int W, int C0, cudaStream_t st) {
+    const long long tokens = (long long)B * (H / 4) * (W / 4);
+    long long blocks = ceil_div<long long>(tokens, 8 * 16);
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    if (blocks < 1) blocks = 1;
+    if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
+    else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
+    else return set_error(SVB_ERR_UNSUPPORTED_MODEL, "stem: width %d unsupported", C0);
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}
+
+extern "C" int svb_stem_ln(const uint8_t* d_in, const float* d_wf, const float* d_bf, const float* d_lnw, const float* d_lnb,
+                           void* d_out, int B, int H, int W, int C0, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_in && d_wf && d_bf && d_lnw && d_lnb && d_out && B > 0 && H % 4 == 0 && W % 4 == 0, SVB_ERR_INVALID_ARG,
+                "stem_ln: bad arguments");
+    if (dtype == SVB_FP16) return stem_entry<__half>(d_in, d_wf, d_bf, d_lnw, d_lnb, d_out, B, H, W, C0, st);
+    return stem_entry<__nv_bfloat16>(d_in, d_wf, d_bf, d_lnw, d_lnb, d_out, B, H, W, C0, st);
+}
+
+extern "C" int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* d_bias, const float* d_lnw,
+                             const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_taps && d_bias && d_lnw && d_lnb && d_out && B > 0 && H > 0 && W > 0, SVB_ERR_INVALID_ARG,
+                "dwconv_ln: bad arguments");
+    BlockParams bp{};
+    bp.wdw = const_cast<float*>(d_taps);
+    bp.bdw = const_cast<float*>(d_bias);
+    bp.lnw = const_cast<float*>(d_lnw);
+    bp.lnb = const_cast<float*>(d_lnb);
+    {
+        const uint64_t dims[2] = {(uint64_t)C, 49};
+        const uint64_t strides[1] = {(uint64_t)C * 4};
+        const uint32_t box[2] = {64, 49};
+        if (int rc = encode_tmap(&bp.wdw_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_taps, dims, strides, box,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE))
+            return rc;
+    }
+    CUtensorMap x_map;
+    {
+        const uint64_t uC = C;
+        const uint64_t dims[4] = {uC, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {uC * 2, (uint64_t)W * uC * 2, (uint64_t)H * W * uC * 2};
+        const uint32_t box[4] = {64, 14, (uint32_t)(dw_th(C) + 6), 1};
+        if (int rc = encode_tmap(&x_map, tmap_dtype(dtype), 4, d_x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    }
+    if (dtype == SVB_FP16) return launch_dwconv<__half>(x_map, bp, d_out, C, B, H, W, st);
+    return launch_dwconv<__nv_bfloat16>(x_map, bp, d_out, C, B, H, W, st);
+}
+
+extern "C" int svb_ln_patchify(const void* d_x, const float* d_lnw, const float* d_lnb, void* d_out, int B, int H, int W,
+                               int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_lnw && d_lnb && d_out && B > 0 && H % 2 == 0 && W % 2 == 0, SVB_ERR_INVALID_ARG,
+                "ln_patchify: bad arguments");
+    DownParams d{};
+    d.lnw = const_cast<float*>(d_lnw);
+    d.lnb = const_cast<float*>(d_lnb);
+    if (dtype == SVB_FP16) return launch_ln_patchify<__half>(d_x, d, d_out, C, B, H, W, st);
+    return launch_ln_patchify<__nv_bfloat16>(d_x, d, d_out, C, B, H, W, st);
+}
+
+extern "C" int svb_head(const void* d_x, int B, int tokens, int C, const float* n0w, const float* n0b, const float* n1w,
+                        const float* n1b, const float* w1, const float* b1, int HID, const float* w2, const float* b2,
+                        int NOUT, float* d_coords, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_coords && B > 0 && tokens > 0 && C % 2 == 0, SVB_ERR_INVALID_ARG, "head: bad arguments");
+    const size_t smem = (size_t)(C + HID + 8) * 4;
+    if (dtype == SVB_FP16)
+        head_kernel<__half><<<B, 256, smem, st>>>(static_cast<const __half*>(d_x), tokens, C, n0w, n0b, n1w, n1b, w1, b1, HID,
+                                                  w2, b2, NOUT, d_coords);
+    else
+        head_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(d_x), tokens, C, n0w, n0b, n1w,
+                                                         n1b, w1, b1, HID, w2, b2, NOUT, d_coords);
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}

@@ -1,0 +1,663 @@
+// svb_resize.cu -- K1 (min-max normalise + Pillow antialiased bilinear resize) and
+// K3 (coordinate-driven crop + per-crop normalise + OpenCV fixed-point letterbox resize
+// + Pillow bilinear second output).  Both are HBM-bound integer/byte kernels: coalesced
+// 128-bit loads, shared-memory staging, no tensor cores.
+//
+// Arithmetic follows, step for step, what the reference executes through NumPy, Pillow and
+// OpenCV (restated in oracle/fixedpoint.py):
+//   normalize_to_uint8          spine_vision/io/__init__.py:15-30
+//   predict_ivd_locations       spine_vision/datasets/classification/cropping.py:463-472
+//   crop_region_horizontal      cropping.py:316-354
+//   resize_with_padding         cropping.py:104-146
+//   ClassificationDataset Resize  spine_vision/training/datasets/classification.py:247-278
+#include "svb_common.cuh"
+
+namespace svb {
+
+constexpr int PIL_PRECISION_BITS = 22;  // Pillow: 32 - 8 - 2
+constexpr int CV_COEF_BITS = 11;        // OpenCV INTER_RESIZE_COEF_BITS
+
+// ============================================================================ Pillow coefficients
+// precompute_coeffs + normalize_coeffs_8bpc (Pillow src/libImaging/Resample.c) for the
+// BILINEAR (triangle, support 1) filter, in IEEE double with explicit round-to-nearest ops so
+// that nvcc cannot contract to FMA: the integer coefficients must equal the CPU's bit for bit.
+__host__ __device__ inline int pil_ksize(int in_size, int out_size) {
+    double scale = (double)(float)in_size / (double)out_size;
+    double fs = scale < 1.0 ? 1.0 : scale;
+    return (int)ceil(fs) * 2 + 1;
+}
+
+// One output index xx of one axis.  bounds = {xmin, n}; kk[0..ksize_max) zero padded.
+__device__ void pil_coeff_entry(int in_size, int out_size, int xx, int ksize_max, int* bounds, int* kk) {
+    const double scale = __ddiv_rn((double)(float)in_size, (double)out_size);
+    const double fs = scale < 1.0 ? 1.0 : scale;
+    const double support = fs;  // filter support 1.0 * filterscale
+    const double ss = __ddiv_rn(1.0, fs);
+    const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    int n = xmax - xmin;
+    if (n > ksize_max) n = ksize_max;  // cannot happen (ksize_max >= ksize); guards the table
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+        double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        if (a < 0.0) a = -a;
+        double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+        ww = __dadd_rn(ww, w);
+    }
+    for (int x = 0; x < ksize_max; ++x) {
+        int k = 0;
+        if (x < n) {
+            double a = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+            if (a < 0.0) a = -a;
+            double w = a < 1.0 ? __dsub_rn(1.0, a) : 0.0;
+            if (ww != 0.0) w = __ddiv_rn(w, ww);
+            // bilinear weights are never negative, the -0.5 branch of normalize_coeffs_8bpc is dead
+            k = (int)__dadd_rn(0.5, __dmul_rn(w, (double)(1 << PIL_PRECISION_BITS)));
+        }
+        kk[x] = k;
+    }
+    bounds[0] = xmin;
+    bounds[1] = n;
+}
+
+__device__ __forceinline__ uint32_t pil_clip8(int acc) {
+    int v = acc >> PIL_PRECISION_BITS;
+    return (uint32_t)min(max(v, 0), 255);
+}
+
+// ============================================================================ K1
+// Workspace layout (all int32 unless noted):
+//   keys   [B][2]                  ordered-uint min / max keys
+//   hb     [B][out_w][2]           horizontal bounds
+//   hk     [B][out_w][ksw]         horizontal coefficients
+//   vb     [B][out_h][2]
+//   vk     [B][out_h][ksh]
+struct K1Layout {
+    size_t keys, hb, hk, vb, vk, total;
+    int ksw, ksh;
+};
+static K1Layout k1_layout(int B, int max_h, int max_w, int out_h, int out_w) {
+    K1Layout L;
+    L.ksw = pil_ksize(max_w, out_w);
+    L.ksh = pil_ksize(max_h, out_h);
+    size_t o = 0;
+    L.keys = o; o += align_up((size_t)B * 2 * 4, 256);
+    L.hb = o;   o += align_up((size_t)B * out_w * 2 * 4, 256);
+    L.hk = o;   o += align_up((size_t)B * out_w * L.ksw * 4, 256);
+    L.vb = o;   o += align_up((size_t)B * out_h * 2 * 4, 256);
+    L.vk = o;   o += align_up((size_t)B * out_h * L.ksh * 4, 256);
+    L.total = o;
+    return L;
+}
+
+// grid (ceil(max(out_w,out_h)/128), 2, B): axis 0 = horizontal, 1 = vertical.  Also resets the keys.
+__global__ void k1_coeff_kernel(const int32_t* __restrict__ hw, int out_h, int out_w, int ksh, int ksw,
+                                uint32_t* __restrict__ keys, int* __restrict__ hb, int* __restrict__ hk,
+                                int* __restrict__ vb, int* __restrict__ vk) {
+    const int b = blockIdx.z;
+    const int axis = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (axis == 0 && i == 0) {
+        keys[2 * b + 0] = 0xFFFFFFFFu;  // min key
+        keys[2 * b + 1] = 0u;           // max key
+    }
+    const int h = hw[2 * b + 0], w = hw[2 * b + 1];
+    if (axis == 0) {
+        if (i < out_w) pil_coeff_entry(w, out_w, i, ksw, hb + ((size_t)b * out_w + i) * 2, hk + ((size_t)b * out_w + i) * ksw);
+    } else {
+        if (i < out_h) pil_coeff_entry(h, out_h, i, ksh, vb + ((size_t)b * out_h + i) * 2, vk + ((size_t)b * out_h + i) * ksh);
+    }
+}
+
+// grid (chunks, nb): 128-bit coalesced min/max over slice (b0 + blockIdx.y)
+__global__ void __launch_bounds__(512) k1_minmax_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
+                                                        const int32_t* __restrict__ hw, int b0,
+                                                        uint32_t* __restrict__ keys) {
+    const int b = b0 + blockIdx.y;
+    const float* base = slices + offs[b];
+    const long long n = (long long)hw[2 * b] * hw[2 * b + 1];
+    const long long per = (n + gridDim.x - 1) / gridDim.x;
+    long long lo = per * blockIdx.x, hi = min(lo + per, n);
+    float mn = INFINITY, mx = -INFINITY;
+    if (lo < hi) {
+        const float* p = base + lo;
+        long long cnt = hi - lo;
+        // head up to 16-byte alignment
+        int head = (int)(((16 - ((uintptr_t)p & 15)) & 15) >> 2);
+        if (head > cnt) head = (int)cnt;
+        if ((int)threadIdx.x < head) { float v = p[threadIdx.x]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+        const float4* p4 = reinterpret_cast<const float4*>(p + head);
+        long long n4 = (cnt - head) >> 2;
+        for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+            float4 v = __ldg(p4 + i);
+            mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+            mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+        }
+        long long done = head + (n4 << 2);
+        if (done + threadIdx.x < cnt) { float v = p[done + threadIdx.x]; mn = fminf(mn, v); mx = fmaxf(mx, v); }
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __shared__ float smn[16], smx[16];
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+        mn = lane < nw ? smn[lane] : INFINITY;
+        mx = lane < nw ? smx[lane] : -INFINITY;
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0 && lo < hi) {
+            atomicMin(&keys[2 * b + 0], float_key(mn));
+            atomicMax(&keys[2 * b + 1], float_key(mx));
+        }
+    }
+}
+
+// grid (ceil(out_h / R), nb).  CTA = R output rows of slice b, all out_w columns.
+// smem: [src u8: rows_in_max * w_max + 8][tmp u8: rows_in_max * out_w][hk int: out_w * ksw][hb int: out_w*2]
+__global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
+                                                        const int32_t* __restrict__ hw, int b0, int out_h, int out_w,
+                                                        int R, int ksh, int ksw, int src_cap, int rows_cap,
+                                                        const uint32_t* __restrict__ keys, const int* __restrict__ hb,
+                                                        const int* __restrict__ hk, const int* __restrict__ vb,
+                                                        const int* __restrict__ vk, uint8_t* __restrict__ out,
+                                                        float* __restrict__ minmax) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int b = b0 + blockIdx.y;
+    const int H = hw[2 * b], W = hw[2 * b + 1];
+    const int r0 = blockIdx.x * R;
+    const int r1 = min(r0 + R, out_h);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+
+    uint8_t* s_src = smem;                                   // src_cap bytes (multiple of 16)
+    uint8_t* s_tmp = s_src + src_cap;                        // rows_cap * out_w (multiple of 16)
+    int* s_hk = reinterpret_cast<int*>(s_tmp + (size_t)rows_cap * out_w);
+    int* s_hb = s_hk + out_w * ksw;
+
+    const float mn = key_float(keys[2 * b + 0]);
+    const float mx = key_float(keys[2 * b + 1]);
+    const float rng = __fsub_rn(mx, mn);
+    if (blockIdx.x == 0 && tid == 0 && minmax != nullptr) { minmax[2 * b] = mn; minmax[2 * b + 1] = mx; }
+
+    const int* vb_b = vb + (size_t)b * out_h * 2;
+    const int* vk_b = vk + (size_t)b * out_h * ksh;
+    const int y_first = vb_b[2 * r0];
+    const int y_last = vb_b[2 * (r1 - 1)] + vb_b[2 * (r1 - 1) + 1];  // bounds are monotone in the row index
+    const int rows_in = y_last - y_first;
+
+    // stage the horizontal tables
+    {
+        const int* hk_b = hk + (size_t)b * out_w * ksw;
+        const int* hb_b = hb + (size_t)b * out_w * 2;
+        for (int i = tid; i < out_w * ksw; i += nthr) s_hk[i] = hk_b[i];
+        for (int i = tid; i < out_w * 2; i += nthr) s_hb[i] = hb_b[i];
+    }
+
+    // phase A: contiguous span of rows_in full rows -> normalised u8 in smem (128-bit loads)
+    {
+        const float* g = slices + offs[b] + (long long)y_first * W;
+        const long long cnt = (long long)rows_in * W;
+        const int mis = (int)(((uintptr_t)g >> 2) & 3);  // element misalignment of the span start
+        const int head = (4 - mis) & 3;
+        uint8_t* dst = s_src + mis;  // element i lives at dst[i]; dst + head is 4-byte aligned
+        if (tid < head && tid < cnt) dst[tid] = (uint8_t)normalize_px(g[tid], mn, rng);
+        const float4* g4 = reinterpret_cast<const float4*>(g + head);
+        const long long n4 = cnt > head ? ((cnt - head) >> 2) : 0;
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
+        for (long long i = tid; i < n4; i += nthr) {
+            float4 v = __ldg(g4 + i);
+            uint32_t p = normalize_px(v.x, mn, rng) | (normalize_px(v.y, mn, rng) << 8) |
+                         (normalize_px(v.z, mn, rng) << 16) | (normalize_px(v.w, mn, rng) << 24);
+            d4[i] = p;
+        }
+        const long long done = head + (n4 << 2);
+        if (done + tid < cnt) dst[done + tid] = (uint8_t)normalize_px(g[done + tid], mn, rng);
+    }
+    __syncthreads();
+
+    // phase B: horizontal pass, u8 rounding between passes (ImagingResampleHorizontal_8bpc)
+    {
+        const uint8_t* src = s_src + (int)((((uintptr_t)(slices + offs[b] + (long long)y_first * W)) >> 2) & 3);
+        if (out_w == W) {
+            for (int i = tid; i < rows_in * out_w; i += nthr) s_tmp[i] = src[i];
+        } else {
+            for (int i = tid; i < rows_in * out_w; i += nthr) {
+                const int row = i / out_w, xx = i - row * out_w;
+                const int xmin = s_hb[2 * xx], n = s_hb[2 * xx + 1];
+                const uint8_t* sp = src + (size_t)row * W + xmin;
+                const int* kp = s_hk + xx * ksw;
+                int acc = 1 << (PIL_PRECISION_BITS - 1);
+                for (int j = 0; j < n; ++j) acc += (int)sp[j] * kp[j];
+                s_tmp[i] = (uint8_t)pil_clip8(acc);
+            }
+        }
+    }
+    __syncthreads();
+
+    // phase C: vertical pass (ImagingResampleVertical_8bpc), 4 output pixels per thread
+    {
+        uint8_t* out_b = out + (size_t)b * out_h * out_w;
+        const int w4 = out_w >> 2;  // out_w % 4 == 0 is required by the host wrapper
+        const int items = (r1 - r0) * w4;
+        for (int i = tid; i < items; i += nthr) {
+            const int rr = i / w4, x4 = (i - rr * w4) << 2;
+            const int r = r0 + rr;
+            uint32_t packed;
+            if (out_h == H) {
+                packed = *reinterpret_cast<const uint32_t*>(s_tmp + (size_t)(r - y_first) * out_w + x4);
+            } else {
+                const int ymin = vb_b[2 * r] - y_first, n = vb_b[2 * r + 1];
+                const int* kp = vk_b + (size_t)r * ksh;
+                int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+                for (int j = 0; j < n; ++j) {
+                    const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp + (size_t)(ymin + j) * out_w + x4);
+                    const int k = __ldg(kp + j);
+                    a0 += (int)(px & 0xFF) * k;
+                    a1 += (int)((px >> 8) & 0xFF) * k;
+                    a2 += (int)((px >> 16) & 0xFF) * k;
+                    a3 += (int)(px >> 24) * k;
+                }
+                packed = pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
+            }
+            *reinterpret_cast<uint32_t*>(out_b + (size_t)r * out_w + x4) = packed;
+        }
+    }
+}
+
+// rows of input one CTA of R output rows can need, for the largest slice of the batch
+static int k1_rows_in(int in_h, int out_h, int R) {
+    double scale = (double)in_h / out_h;
+    double fs = scale < 1.0 ? 1.0 : scale;
+    return (int)(R * scale + 2.0 * fs + 3.0);
+}
+
+}  // namespace svb
+
+using namespace svb;
+
+extern "C" size_t svb_k1_workspace_bytes(int B, int max_h, int max_w, int out_h, int out_w) {
+    if (B <= 0 || max_h <= 0 || max_w <= 0 || out_h <= 0 || out_w <= 0) return 0;
+    return k1_layout(B, max_h, max_w, out_h, out_w).total;
+}
+
+extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B,
+                                       int max_h, int max_w, int out_h, int out_w, uint8_t* d_out_u8,
+                                       float* d_minmax, void* d_ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(B >= 0 && max_h > 0 && max_w > 0 && out_h > 0 && out_w > 0, SVB_ERR_INVALID_ARG,
+                "k1: bad sizes B=%d max_hw=(%d,%d) out=(%d,%d)", B, max_h, max_w, out_h, out_w);
+    if (B == 0) return SVB_OK;
+    SVB_REQUIRE(d_slices && d_offs && d_hw && d_out_u8 && d_ws, SVB_ERR_INVALID_ARG, "k1: null pointer argument");
+    SVB_REQUIRE(out_w % 4 == 0, SVB_ERR_INVALID_ARG, "k1: out_w (%d) must be a multiple of 4", out_w);
+    const K1Layout L = k1_layout(B, max_h, max_w, out_h, out_w);
+    SVB_REQUIRE(ws_bytes >= L.total, SVB_ERR_WORKSPACE_TOO_SMALL, "k1: workspace %zu < %zu bytes", ws_bytes, L.total);
+    uint8_t* ws = static_cast<uint8_t*>(d_ws);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws + L.keys);
+    int* hb = reinterpret_cast<int*>(ws + L.hb);
+    int* hk = reinterpret_cast<int*>(ws + L.hk);
+    int* vb = reinterpret_cast<int*>(ws + L.vb);
+    int* vk = reinterpret_cast<int*>(ws + L.vk);
+
+    {
+        dim3 grid(ceil_div(out_w > out_h ? out_w : out_h, 128), 2, B);
+        k1_coeff_kernel<<<grid, 128, 0, stream>>>(d_hw, out_h, out_w, L.ksh, L.ksw, keys, hb, hk, vb, vk);
+        SVB_CUDA_OK(cudaGetLastError());
+    }
+
+    // rows per CTA: largest power of two whose staging fits ~100 KB (2 CTAs / SM), else smaller
+    const size_t table_bytes = (size_t)out_w * L.ksw * 4 + (size_t)out_w * 2 * 4;
+    int R = 32;
+    size_t smem_bytes = 0;
+    int src_cap = 0, rows_cap = 0;
+    for (;; R >>= 1) {
+        rows_cap = k1_rows_in(max_h, out_h, R);
+        if (rows_cap > max_h) rows_cap = max_h;
+        src_cap = (int)align_up((size_t)rows_cap * max_w + 16, 16);
+        smem_bytes = (size_t)src_cap + align_up((size_t)rows_cap * out_w, 16) + table_bytes;
+        const size_t budget = R > 1 ? 100 * 1024 : 227 * 1024;
+        if (smem_bytes <= budget || R == 1) break;
+    }
+    SVB_REQUIRE(smem_bytes <= 227 * 1024, SVB_ERR_INVALID_ARG,
+                "k1: a %dx%d slice needs %zu bytes of shared memory per output row (limit 232448)", max_h, max_w,
+                smem_bytes);
+    SVB_CUDA_OK(cudaFuncSetAttribute(k1_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    const int rows_cap_al = (int)(align_up((size_t)rows_cap * out_w, 16) / out_w);  // keep s_hk 16B aligned
+    (void)rows_cap_al;
+
+    // L2-chunked two-pass: min/max then resize over groups of slices that fit in L2, so the second
+    // read of each slice is an L2 hit and HBM sees the fp32 data once.
+    const size_t slice_bytes = (size_t)max_h * max_w * 4;
+    int chunk = (int)((size_t)64 * 1024 * 1024 / (slice_bytes ? slice_bytes : 1));
+    if (chunk < 1) chunk = 1;
+    if (chunk > 65535) chunk = 65535;
+    int mm_blocks = (int)ceil_div<size_t>(slice_bytes, (size_t)512 * 16 * 8);  // ~8 float4 per thread
+    if (mm_blocks < 1) mm_blocks = 1;
+    if (mm_blocks > 1024) mm_blocks = 1024;
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = (B - b0) < chunk ? (B - b0) : chunk;
+        k1_minmax_kernel<<<dim3(mm_blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys);
+        SVB_CUDA_OK(cudaGetLastError());
+        k1_resize_kernel<<<dim3(ceil_div(out_h, R), nb), 512, smem_bytes, stream>>>(
+            d_slices, d_offs, d_hw, b0, out_h, out_w, R, L.ksh, L.ksw, src_cap, rows_cap, keys, hb, hk, vb, vk,
+            d_out_u8, d_minmax);
+        SVB_CUDA_OK(cudaGetLastError());
+    }
+    return SVB_OK;
+}
+
+// ============================================================================ K3
+namespace svb {
+
+struct K3Geom {
+    int x1, x2, y1, y2, new_h, new_w, y_off, x_off;
+};
+
+// Workspace: Pillow tables for the second output: hb2[ow2][2], hk2[ow2][ks2w], vb2[oh2][2], vk2[oh2][ks2h]
+struct K3Layout {
+    size_t hb, hk, vb, vk, total;
+    int ksw, ksh;
+};
+static K3Layout k3_layout(int ch, int cw, int oh2, int ow2) {
+    K3Layout L{};
+    if (oh2 <= 0 || ow2 <= 0) { L.total = 256; L.ksw = L.ksh = 1; return L; }
+    L.ksw = pil_ksize(cw, ow2);
+    L.ksh = pil_ksize(ch, oh2);
+    size_t o = 0;
+    L.hb = o; o += align_up((size_t)ow2 * 2 * 4, 256);
+    L.hk = o; o += align_up((size_t)ow2 * L.ksw * 4, 256);
+    L.vb = o; o += align_up((size_t)oh2 * 2 * 4, 256);
+    L.vk = o; o += align_up((size_t)oh2 * L.ksh * 4, 256);
+    L.total = o;
+    return L;
+}
+
+__global__ void k3_coeff_kernel(int ch, int cw, int oh2, int ow2, int ksh, int ksw, int* __restrict__ hb,
+                                int* __restrict__ hk, int* __restrict__ vb, int* __restrict__ vk) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.y == 0) {
+        if (i < ow2) pil_coeff_entry(cw, ow2, i, ksw, hb + 2 * i, hk + (size_t)i * ksw);
+    } else {
+        if (i < oh2) pil_coeff_entry(ch, oh2, i, ksh, vb + 2 * i, vk + (size_t)i * ksh);
+    }
+}
+
+// OpenCV resizeGeneric_ linear table entry (modules/imgproc/src/resize.cpp): source index and the
+// two 11-bit weights for destination index i.  `horizontal` zeroes the fraction when clamped.
+__device__ __forceinline__ void cv_axis_entry(int i, int src, double scale, bool horizontal, int& si, int& a0, int& a1) {
+    float f = (float)__dsub_rn(__dmul_rn(__dadd_rn((double)i, 0.5), scale), 0.5);
+    int s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (horizontal) {
+        if (s < 0) { f = 0.f; s = 0; }
+        if (s >= src - 1) { f = 0.f; s = src - 1; }
+    }
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), (float)(1 << CV_COEF_BITS)));
+    a1 = __float2int_rn(__fmul_rn(f, (float)(1 << CV_COEF_BITS)));
+    si = s;
+}
+
+// One CTA per crop.
+// smem: [box u8: box_cap][canvas u8: ch*cw][tmp2 u8: ch*ow2 (if second output needs a pass)]
+//       [xs,xa0,xa1: 3*cw int][ys,yb0,yb1: 3*ch int]
+__global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
+                                                      const int32_t* __restrict__ hw, const int32_t* __restrict__ slice_idx,
+                                                      const float* __restrict__ xy, const int32_t* __restrict__ delta_px,
+                                                      int ch, int cw, uint8_t* __restrict__ crops, int oh2, int ow2,
+                                                      uint8_t* __restrict__ crops2, int32_t* __restrict__ geom_out,
+                                                      int flags, int box_cap, int ksh2, int ksw2, const int* __restrict__ hb2,
+                                                      const int* __restrict__ hk2, const int* __restrict__ vb2,
+                                                      const int* __restrict__ vk2) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int n = blockIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5, nwarps = nthr >> 5;
+    const bool second = crops2 != nullptr;
+    const bool second_identity = second && oh2 == ch && ow2 == cw;
+
+    uint8_t* s_box = smem;
+    uint8_t* s_canvas = s_box + box_cap;  // box_cap is a multiple of 16
+    uint8_t* s_tmp2 = s_canvas + (size_t)ch * cw;
+    int* s_tab = reinterpret_cast<int*>(s_tmp2 + ((second && !second_identity) ? (size_t)ch * ow2 : 0));
+    int* xs = s_tab;
+    int* xa0 = xs + cw;
+    int* xa1 = xa0 + cw;
+    int* ys = xa1 + cw;
+    int* yb0 = ys + ch;
+    int* yb1 = yb0 + ch;
+
+    __shared__ K3Geom g;
+    __shared__ float s_red[2][8];
+    __shared__ float s_mm[2];
+
+    const int b = slice_idx[n];
+    const int H = hw[2 * b], W = hw[2 * b + 1];
+    if (tid == 0) {
+        // cropping.py:338-348: cx = int(x*w), cy = int(y*h) in Python float (double) arithmetic
+        const int cx = (int)__dmul_rn((double)xy[2 * n + 0], (double)W);
+        const int cy = (int)__dmul_rn((double)xy[2 * n + 1], (double)H);
+        const int left = delta_px[4 * n + 0], right = delta_px[4 * n + 1];
+        const int top = delta_px[4 * n + 2], bottom = delta_px[4 * n + 3];
+        K3Geom q;
+        q.x1 = max(0, cx - left);
+        q.x2 = min(W, cx + right);
+        q.y1 = max(0, cy - top);
+        q.y2 = min(H, cy + bottom);
+        const int bh = q.y2 - q.y1, bw = q.x2 - q.x1;
+        q.new_h = q.new_w = q.y_off = q.x_off = 0;
+        if (bh > 0 && bw > 0 && (long long)bh * bw <= box_cap) {
+            // cropping.py:121-141: scale = min(th/h, tw/w); new = int(round(dim*scale)); offsets (t-new)//2
+            const double sh = __ddiv_rn((double)ch, (double)bh), sw = __ddiv_rn((double)cw, (double)bw);
+            const double scale = sh < sw ? sh : sw;
+            q.new_h = (int)rint(__dmul_rn((double)bh, scale));
+            q.new_w = (int)rint(__dmul_rn((double)bw, scale));
+            q.y_off = (ch - q.new_h) >> 1;  // floor division, also for a negative numerator
+            q.x_off = (cw - q.new_w) >> 1;
+            if (q.new_h <= 0 || q.new_w <= 0 || q.new_h > ch || q.new_w > cw) q.new_h = q.new_w = 0;
+        }
+        g = q;
+        if (geom_out != nullptr) {
+            int32_t* go = geom_out + 8 * (size_t)n;
+            go[0] = q.x1; go[1] = q.x2; go[2] = q.y1; go[3] = q.y2;
+            go[4] = q.new_h; go[5] = q.new_w; go[6] = q.y_off; go[7] = q.x_off;
+        }
+    }
+    __syncthreads();
+    const int bh = g.y2 - g.y1, bw = g.x2 - g.x1;
+    const bool valid = g.new_h > 0 && g.new_w > 0;
+    const float* src = slices + offs[b] + (long long)g.y1 * W + g.x1;
+
+    if (valid) {
+        // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350)
+        float mn = INFINITY, mx = -INFINITY;
+        for (int y = wid; y < bh; y += nwarps) {
+            const float* row = src + (long long)y * W;
+            for (int x = lane; x < bw; x += 32) {
+                const float v = __ldg(row + x);
+                mn = fminf(mn, v);
+                mx = fmaxf(mx, v);
+            }
+        }
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0) { s_red[0][wid] = mn; s_red[1][wid] = mx; }
+        __syncthreads();
+        if (wid == 0) {
+            mn = lane < nwarps ? s_red[0][lane] : INFINITY;
+            mx = lane < nwarps ? s_red[1][lane] : -INFINITY;
+            mn = warp_min(mn);
+            mx = warp_max(mx);
+            if (lane == 0) { s_mm[0] = mn; s_mm[1] = mx; }
+        }
+        // resize tables while the reduction finishes
+        {
+            const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)g.new_w, (double)bw));
+            const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)g.new_h, (double)bh));
+            for (int i = tid; i < g.new_w; i += nthr) cv_axis_entry(i, bw, scale_x, true, xs[i], xa0[i], xa1[i]);
+            for (int i = tid; i < g.new_h; i += nthr) cv_axis_entry(i, bh, scale_y, false, ys[i], yb0[i], yb1[i]);
+        }
+        __syncthreads();
+        const float mnv = s_mm[0];
+        // rng <= 0 makes normalize_px a plain cast: the max == min case, and SVB_K3_NO_NORMALIZE
+        const float rng = (flags & SVB_K3_NO_NORMALIZE) ? 0.0f : __fsub_rn(s_mm[1], mnv);
+        // pass 2: normalise the box into shared memory (second read is an L1/L2 hit)
+        for (int y = wid; y < bh; y += nwarps) {
+            const float* row = src + (long long)y * W;
+            uint8_t* drow = s_box + (size_t)y * bw;
+            for (int x = lane; x < bw; x += 32) drow[x] = (uint8_t)normalize_px(__ldg(row + x), mnv, rng);
+        }
+    }
+    __syncthreads();
+
+    // letterboxed fixed-point bilinear resize (cv2.resize 8U INTER_LINEAR) onto the zero canvas
+    {
+        const int cw4 = cw >> 2;
+        for (int i = tid; i < ch * cw4; i += nthr) {
+            const int oy = i / cw4, ox4 = (i - oy * cw4) << 2;
+            uint32_t packed = 0;
+            const int dy = oy - g.y_off;
+            if (valid && dy >= 0 && dy < g.new_h) {
+                const bool same = (g.new_h == bh && g.new_w == bw);  // cv2.resize returns a copy
+                const int sy = ys[dy];
+                const int r0 = min(max(sy, 0), bh - 1), r1 = min(max(sy + 1, 0), bh - 1);
+                const int b0 = yb0[dy], b1 = yb1[dy];
+                const uint8_t* p0 = s_box + (size_t)r0 * bw;
+                const uint8_t* p1 = s_box + (size_t)r1 * bw;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int dx = ox4 + k - g.x_off;
+                    uint32_t v = 0;
+                    if (dx >= 0 && dx < g.new_w) {
+                        if (same) {
+                            v = s_box[(size_t)dy * bw + dx];
+                        } else {
+                            const int sx = xs[dx];
+                            const int sx1 = min(sx + 1, bw - 1);
+                            const int a0 = xa0[dx], a1 = xa1[dx];
+                            const int h0 = (int)p0[sx] * a0 + (int)p0[sx1] * a1;
+                            const int h1 = (int)p1[sx] * a0 + (int)p1[sx1] * a1;
+                            const int t = ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16);
+                            v = (uint32_t)min(max((t + 2) >> 2, 0), 255);
+                        }
+                    }
+                    packed |= v << (8 * k);
+                }
+            }
+            *reinterpret_cast<uint32_t*>(s_canvas + (size_t)oy * cw + ox4) = packed;
+        }
+    }
+    __syncthreads();
+
+    // crop out: ch*cw bytes, 32-bit coalesced
+    {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(crops + (size_t)n * ch * cw);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(s_canvas);
+        for (int i = tid; i < (ch * cw) >> 2; i += nthr) dst[i] = s[i];
+    }
+    if (!second) return;
+
+    uint8_t* out2 = crops2 + (size_t)n * oh2 * ow2;
+    if (second_identity) {  // Pillow skips both passes when the size is unchanged
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out2);
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(s_canvas);
+        for (int i = tid; i < (ch * cw) >> 2; i += nthr) dst[i] = s[i];
+        return;
+    }
+    // second output: Pillow BILINEAR (ch,cw) -> (oh2,ow2): horizontal pass into tmp2, vertical to global
+    if (ow2 == cw) {
+        for (int i = tid; i < ch * ow2; i += nthr) s_tmp2[i] = s_canvas[i];
+    } else {
+        for (int i = tid; i < ch * ow2; i += nthr) {
+            const int row = i / ow2, xx = i - row * ow2;
+            const int xmin = __ldg(hb2 + 2 * xx), cnt = __ldg(hb2 + 2 * xx + 1);
+            const uint8_t* sp = s_canvas + (size_t)row * cw + xmin;
+            const int* kp = hk2 + (size_t)xx * ksw2;
+            int acc = 1 << (PIL_PRECISION_BITS - 1);
+            for (int j = 0; j < cnt; ++j) acc += (int)sp[j] * __ldg(kp + j);
+            s_tmp2[i] = (uint8_t)pil_clip8(acc);
+        }
+    }
+    __syncthreads();
+    {
+        const int w4 = ow2 >> 2;
+        for (int i = tid; i < oh2 * w4; i += nthr) {
+            const int r = i / w4, x4 = (i - r * w4) << 2;
+            uint32_t packed;
+            if (oh2 == ch) {
+                packed = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)r * ow2 + x4);
+            } else {
+                const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);
+                const int* kp = vk2 + (size_t)r * ksh2;
+                int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+                for (int j = 0; j < cnt; ++j) {
+                    const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)(ymin + j) * ow2 + x4);
+                    const int k = __ldg(kp + j);
+                    a0 += (int)(px & 0xFF) * k;
+                    a1 += (int)((px >> 8) & 0xFF) * k;
+                    a2 += (int)((px >> 16) & 0xFF) * k;
+                    a3 += (int)(px >> 24) * k;
+                }
+                packed = pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
+            }
+            *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) = packed;
+        }
+    }
+}
+
+}  // namespace svb
+
+extern "C" size_t svb_k3_workspace_bytes(int ch, int cw, int oh2, int ow2) {
+    return k3_layout(ch, cw, oh2, ow2).total;
+}
+
+extern "C" int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                    const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px, int N,
+                                    int max_box_h, int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2,
+                                    uint8_t* d_crops2, int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes,
+                                    void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(N >= 0 && ch > 0 && cw > 0 && max_box_h > 0 && max_box_w > 0, SVB_ERR_INVALID_ARG,
+                "k3: bad sizes N=%d crop=(%d,%d) max_box=(%d,%d)", N, ch, cw, max_box_h, max_box_w);
+    if (N == 0) return SVB_OK;
+    SVB_REQUIRE(d_slices && d_offs && d_hw && d_slice_idx && d_xy && d_delta_px && d_crops, SVB_ERR_INVALID_ARG,
+                "k3: null pointer argument");
+    SVB_REQUIRE(cw % 4 == 0, SVB_ERR_INVALID_ARG, "k3: crop width (%d) must be a multiple of 4", cw);
+    const bool second = d_crops2 != nullptr;
+    if (second) {
+        SVB_REQUIRE(oh2 > 0 && ow2 > 0 && ow2 % 4 == 0, SVB_ERR_INVALID_ARG,
+                    "k3: second output size (%d,%d) invalid (width must be a multiple of 4)", oh2, ow2);
+        SVB_REQUIRE(d_ws != nullptr, SVB_ERR_INVALID_ARG, "k3: workspace required for the second output");
+    }
+    const K3Layout L = k3_layout(ch, cw, second ? oh2 : 0, second ? ow2 : 0);
+    SVB_REQUIRE(!second || ws_bytes >= L.total, SVB_ERR_WORKSPACE_TOO_SMALL, "k3: workspace %zu < %zu bytes", ws_bytes,
+                L.total);
+    const bool identity = second && oh2 == ch && ow2 == cw;
+    const size_t box_cap = align_up((size_t)max_box_h * max_box_w, 16);
+    const size_t smem_bytes = box_cap + (size_t)ch * cw + ((second && !identity) ? (size_t)ch * ow2 : 0) +
+                              (size_t)3 * (cw + ch) * 4;
+    SVB_REQUIRE(smem_bytes <= 227 * 1024, SVB_ERR_BOX_TOO_LARGE,
+                "k3: crop box %dx%d with crop %dx%d (second %dx%d) needs %zu bytes of shared memory (limit 232448)",
+                max_box_h, max_box_w, ch, cw, oh2, ow2, smem_bytes);
+    int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr;
+    if (second && !identity) {
+        uint8_t* ws = static_cast<uint8_t*>(d_ws);
+        hb = reinterpret_cast<int*>(ws + L.hb);
+        hk = reinterpret_cast<int*>(ws + L.hk);
+        vb = reinterpret_cast<int*>(ws + L.vb);
+        vk = reinterpret_cast<int*>(ws + L.vk);
+        dim3 grid(ceil_div(ow2 > oh2 ? ow2 : oh2, 128), 2);
+        k3_coeff_kernel<<<grid, 128, 0, stream>>>(ch, cw, oh2, ow2, L.ksh, L.ksw, hb, hk, vb, vk);
+        SVB_CUDA_OK(cudaGetLastError());
+    }
+    SVB_CUDA_OK(cudaFuncSetAttribute(k3_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    k3_crop_kernel<<<N, 256, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
+                                                   oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk);
+    SVB_CUDA_OK(cudaGetLastError());
+    return SVB_OK;
+}

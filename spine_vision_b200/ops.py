@@ -1,0 +1,285 @@
+"""Batched device operators over ``libspine_b200.so``.
+
+PyTorch is plumbing here (device memory, streams, pinned staging); every
+operator is one C-ABI call into hand-written sm_100a kernels.  Nothing in this
+module computes on the CPU and nothing imports ``oracle/``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda" or not torch.cuda.is_available():
+        raise RuntimeError(
+            f"spine_vision_b200 needs a CUDA (B200, sm_100) device, got {device!r}; there is no CPU fallback"
+        )
+    return dev
+
+
+@dataclass
+class SlicePool:
+    """A ragged batch of float32 slices resident in HBM: one flat pool plus
+    per-slice element offsets and (H, W).  Offsets are 4-element aligned so each
+    slice starts on a 16-byte boundary (128-bit loads)."""
+
+    data: torch.Tensor  # float32 [total]
+    offs: torch.Tensor  # int64 [B] (device)
+    hw: torch.Tensor  # int32 [B,2] (device)
+    shapes: list  # host copy [(h, w)]
+    h2d_bytes: int = 0
+
+    @property
+    def n(self) -> int:
+        return len(self.shapes)
+
+    @property
+    def max_hw(self) -> tuple[int, int]:
+        return max(s[0] for s in self.shapes), max(s[1] for s in self.shapes)
+
+    @staticmethod
+    def layout(shapes):
+        offs, o = [], 0
+        for h, w in shapes:
+            offs.append(o)
+            o += (h * w + 3) // 4 * 4
+        return offs, o
+
+    @classmethod
+    def pin(cls, slices):
+        """Stage host slices into one pinned float32 buffer (done once; outside any timed region)."""
+        shapes = [tuple(int(v) for v in s.shape) for s in slices]
+        offs, total = cls.layout(shapes)
+        host = torch.empty(max(total, 4), dtype=torch.float32).pin_memory()
+        hv = host.numpy()
+        for s, o in zip(slices, offs):
+            # spine_vision/io/__init__.py:26: arr.astype(np.float32) happens on the host, exactly as the reference
+            hv[o : o + s.size] = np.asarray(s).astype(np.float32, copy=False).ravel()
+        return host, offs, shapes
+
+    @classmethod
+    def from_pinned(cls, host: torch.Tensor, offs, shapes, device="cuda:0") -> "SlicePool":
+        dev = _require_cuda(device)
+        data = host.to(dev, non_blocking=True)
+        meta = torch.tensor(offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+        hw = torch.tensor(shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True)
+        return cls(data, meta, hw, list(shapes), h2d_bytes=host.numel() * 4 + meta.numel() * 8 + hw.numel() * 4)
+
+    @classmethod
+    def from_numpy(cls, slices, device="cuda:0") -> "SlicePool":
+        _require_cuda(device)
+        host, offs, shapes = cls.pin(slices)
+        return cls.from_pinned(host, offs, shapes, device)
+
+    @classmethod
+    def from_device_batch(cls, batch: torch.Tensor) -> "SlicePool":
+        """Uniform batch already on the device: float32 [B,H,W] (H*W % 4 == 0 or B == 1)."""
+        assert batch.is_cuda and batch.dtype == torch.float32 and batch.dim() == 3 and batch.is_contiguous()
+        b, h, w = batch.shape
+        assert (h * w) % 4 == 0 or b == 1, "uniform device batches need H*W % 4 == 0"
+        offs = torch.arange(b, dtype=torch.int64, device=batch.device) * (h * w)
+        hw = torch.tensor([[h, w]] * b, dtype=torch.int32, device=batch.device)
+        return cls(batch.reshape(-1), offs, hw, [(h, w)] * b)
+
+
+class _Workspace:
+    """Grow-only device scratch, one per (device, tag)."""
+
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, tag: str, nbytes: int, device) -> torch.Tensor:
+        key = (tag, str(device))
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1024) + 1024, dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def _aligned_ptr(buf: torch.Tensor, align: int = 1024) -> tuple[int, int]:
+    p = buf.data_ptr()
+    a = (p + align - 1) // align * align
+    return a, buf.numel() - (a - p)
+
+
+def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | None = None, return_minmax: bool = False):
+    """K1: per-slice global min-max -> uint8 (truncating) -> Pillow antialiased bilinear resize.
+    Device mirror of ``normalize_to_uint8`` (io/__init__.py:15-30) + ``transforms.Resize``
+    (cropping.py:463-472).  Returns uint8 ``[B, out_h, out_w]`` (one plane; R=G=B)."""
+    lib = _lib.load()
+    dev = pool.data.device
+    B = pool.n
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if out is None:
+        out = torch.empty((B, oh, ow), dtype=torch.uint8, device=dev)
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev) if return_minmax else None
+    if B == 0:
+        return (out, minmax) if return_minmax else out
+    mh, mw = pool.max_hw
+    need = lib.svb_k1_workspace_bytes(B, mh, mw, oh, ow)
+    ws = _Workspace.get("k1", need, dev)
+    wp, wn = _aligned_ptr(ws, 256)
+    _lib.check(lib.svb_k1_normalize_resize(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), B, mh, mw, oh, ow,
+                                           out.data_ptr(), _lib.ptr(minmax), wp, wn, _lib.current_stream()))
+    return (out, minmax) if return_minmax else out
+
+
+def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, delta_px: torch.Tensor, max_box_hw,
+                  crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True):
+    """K3: one crop per (slice_idx, xy, delta_px) row.  Device mirror of
+    ``CropContext.crop`` -> ``crop_region_horizontal`` (cropping.py:316-404) and, for the
+    second output, the classifier's ``Resize`` (training/datasets/classification.py:247-278).
+    Returns ``(crops u8 [N,ch,cw], crops2 u8 [N,oh2,ow2] | None, geom int32 [N,8] | None)``."""
+    lib = _lib.load()
+    dev = pool.data.device
+    N = int(xy.shape[0])
+    ch, cw = int(crop_size[0]), int(crop_size[1])
+    crops = torch.empty((N, ch, cw), dtype=torch.uint8, device=dev)
+    crops2 = None
+    oh2 = ow2 = 0
+    if second_size is not None:
+        oh2, ow2 = int(second_size[0]), int(second_size[1])
+        crops2 = torch.empty((N, oh2, ow2), dtype=torch.uint8, device=dev)
+    geom = torch.empty((N, 8), dtype=torch.int32, device=dev) if return_geom else None
+    if N == 0:
+        return crops, crops2, geom
+    assert slice_idx.dtype == torch.int32 and xy.dtype == torch.float32 and delta_px.dtype == torch.int32
+    assert slice_idx.is_contiguous() and xy.is_contiguous() and delta_px.is_contiguous()
+    need = lib.svb_k3_workspace_bytes(ch, cw, oh2, ow2)
+    ws = _Workspace.get("k3", need, dev)
+    wp, wn = _aligned_ptr(ws, 256)
+    _lib.check(lib.svb_k3_crop_resample(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), slice_idx.data_ptr(),
+                                        xy.data_ptr(), delta_px.data_ptr(), N, int(max_box_hw[0]), int(max_box_hw[1]), ch, cw,
+                                        crops.data_ptr(), oh2, ow2, _lib.ptr(crops2), _lib.ptr(geom), 0 if normalize else 1, wp, wn,
+                                        _lib.current_stream()))
+    return crops, crops2, geom
+
+
+class LocalizationEngine:
+    """Owns one ``svb_model`` handle: the ``CoordinateRegressor`` forward
+    (training/models/generic.py:389-391) as sm_100a kernels.  Input is the K1 output
+    (uint8 ``[B,H,W]``); /255 and ImageNet mean/std live in the folded stem."""
+
+    def __init__(self, state_dict, device="cuda:0", dtype: str = "bf16", micro_batch: int = 32):
+        self.device = _require_cuda(device)
+        self.dtype = dtype
+        self.micro_batch = int(micro_batch)
+        lib = _lib.load()
+        keep, descs = [], (_lib.WeightDesc * len(state_dict))()
+        for i, (name, t) in enumerate(state_dict.items()):
+            a = t.detach().to("cpu", torch.float32).contiguous()
+            keep.append(a)
+            descs[i].name = name.encode()
+            descs[i].data = a.data_ptr()
+            descs[i].ndim = a.dim()
+            for k in range(4):
+                descs[i].shape[k] = a.shape[k] if k < a.dim() else 1
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.svb_model_create(C.byref(handle), descs, len(state_dict), _lib.DTYPES[dtype]))
+        self._h = handle
+        info = (C.c_int32 * 10)()
+        _lib.check(lib.svb_model_info(self._h, C.byref(info)))
+        self.num_levels, self.num_outputs = int(info[0]), int(info[1])
+        self.dims, self.depths = tuple(info[2:6]), tuple(info[6:10])
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.load().svb_model_destroy(h)
+            except Exception:
+                pass
+
+    def cost(self, B: int, H: int, W: int) -> tuple[float, int]:
+        fl, n = C.c_double(), C.c_int64()
+        _lib.check(_lib.load().svb_model_cost(self._h, B, H, W, C.byref(fl), C.byref(n)))
+        return fl.value, n.value
+
+    def forward(self, u8: torch.Tensor, times: dict | None = None) -> torch.Tensor:
+        """uint8 [B,H,W] on the device -> float32 [B, num_levels, 2] in [0,1]."""
+        assert u8.is_cuda and u8.dtype == torch.uint8 and u8.dim() == 3 and u8.is_contiguous()
+        lib = _lib.load()
+        B, H, W = u8.shape
+        coords = torch.empty((B, self.num_levels, self.num_outputs), dtype=torch.float32, device=u8.device)
+        if B == 0:
+            return coords
+        mb = min(self.micro_batch, B)
+        need = lib.svb_model_workspace_bytes(self._h, mb, H, W)
+        ws = _Workspace.get("model", need, u8.device)
+        wp, wn = _aligned_ptr(ws, 1024)
+        tbuf = (C.c_float * len(_lib.KERNEL_CLASSES))() if times is not None else None
+        _lib.check(lib.svb_model_forward(self._h, u8.data_ptr(), B, H, W, coords.data_ptr(), mb, wp, wn, _lib.current_stream(),
+                                         C.cast(tbuf, C.c_void_p) if tbuf is not None else None))
+        if times is not None:
+            for k, name in enumerate(_lib.KERNEL_CLASSES):
+                times[name] = times.get(name, 0.0) + float(tbuf[k])
+        return coords
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int, resid: torch.Tensor | None = None,
+         gamma: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Standalone tcgen05 GEMM (unit tests / profiling): ``epilogue(a @ w.T)``; a [M,K], w [N,K]."""
+    lib = _lib.load()
+    assert a.dtype == w.dtype and a.dtype in (torch.bfloat16, torch.float16) and a.is_contiguous() and w.is_contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+    dt = _lib.SVB_BF16 if a.dtype == torch.bfloat16 else _lib.SVB_FP16
+    _lib.check(lib.svb_gemm(a.data_ptr(), w.data_ptr(), out.data_ptr(), _lib.ptr(resid), bias.data_ptr(), _lib.ptr(gamma), M, N, K,
+                            mode, dt, _lib.current_stream()))
+    return out
+
+
+# ------------------------------------------------------------------ standalone layers (tests / ncu)
+def _dt(t: torch.Tensor) -> int:
+    assert t.dtype in (torch.bfloat16, torch.float16)
+    return _lib.SVB_BF16 if t.dtype == torch.bfloat16 else _lib.SVB_FP16
+
+
+def stem_ln(u8: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor, dtype=torch.bfloat16):
+    """u8 [B,H,W] -> [B,H/4,W/4,C0] with the folded stem (wf [C0,16], bf [C0])."""
+    B, H, W = u8.shape
+    C0 = wf.shape[0]
+    out = torch.empty((B, H // 4, W // 4, C0), dtype=dtype, device=u8.device)
+    _lib.check(_lib.load().svb_stem_ln(u8.data_ptr(), wf.data_ptr(), bf.data_ptr(), lnw.data_ptr(), lnb.data_ptr(), out.data_ptr(),
+                                       B, H, W, C0, _dt(out), _lib.current_stream()))
+    return out
+
+
+def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
+    """x NHWC 16-bit [B,H,W,C]; taps fp32 [49,C] (tap-major) -> LayerNorm(dwconv7x7(x)+bias) [B,H,W,C]."""
+    B, H, W, Cc = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.load().svb_dwconv_ln(x.data_ptr(), taps.data_ptr(), bias.data_ptr(), lnw.data_ptr(), lnb.data_ptr(),
+                                         out.data_ptr(), B, H, W, Cc, _dt(x), _lib.current_stream()))
+    return out
+
+
+def ln_patchify(x: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
+    B, H, W, Cc = x.shape
+    out = torch.empty((B, H // 2, W // 2, 4 * Cc), dtype=x.dtype, device=x.device)
+    _lib.check(_lib.load().svb_ln_patchify(x.data_ptr(), lnw.data_ptr(), lnb.data_ptr(), out.data_ptr(), B, H, W, Cc, _dt(x),
+                                           _lib.current_stream()))
+    return out
+
+
+def head(x: torch.Tensor, n0w, n0b, n1w, n1b, w1, b1, w2, b2):
+    """x [B,tokens,C] 16-bit -> sigmoid coords fp32 [B,NOUT]."""
+    B, tokens, Cc = x.shape
+    hid, nout = w1.shape[0], w2.shape[0]
+    out = torch.empty((B, nout), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().svb_head(x.data_ptr(), B, tokens, Cc, n0w.data_ptr(), n0b.data_ptr(), n1w.data_ptr(), n1b.data_ptr(),
+                                    w1.data_ptr(), b1.data_ptr(), hid, w2.data_ptr(), b2.data_ptr(), nout, out.data_ptr(), _dt(x),
+                                    _lib.current_stream()))
+    return out

@@ -1,0 +1,138 @@
+"""Batched localize-and-crop: the hot loop of ``process_spider`` / ``process_phenikaa``
+(``datasets/classification/spider.py:90-152``, ``phenikaa.py:142-208``) run over many series
+at once instead of one series per iteration with two device round trips each.
+
+    slices (host, float32, ragged)  --H2D-->  K1 normalise+resize  -->  ConvNeXt localizer
+        -->  K3 crop+letterbox (+ classifier-size resample)  --D2H-->  coords, crops
+
+Series are independent, so multi-GPU is a plain shard by series index
+(``shard_series``) plus one gather of crops and coordinates at the end
+(``gather_results``); there is no per-op collective.
+"""
+
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import ops
+from .cropping import LocalizationModel, get_center_fallback_locations, mm_to_pixels
+
+NUM_LEVELS = 5
+
+
+@dataclass
+class CropBatch:
+    coords: torch.Tensor  # float32 [B,5,2] (device)
+    crops: torch.Tensor  # uint8 [B,5,ch,cw] (device)
+    crops2: torch.Tensor | None  # uint8 [B,5,oh2,ow2] (device) -- classifier-size resample
+    planes: torch.Tensor | None = None  # uint8 [B,H,W] K1 output (kept for inspection)
+    times: dict = field(default_factory=dict)
+
+    def to_host(self):
+        return (self.coords.cpu().numpy(), self.crops.cpu().numpy(), None if self.crops2 is None else self.crops2.cpu().numpy())
+
+
+def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacings=None, crop_size=(128, 128),
+                second_size=(256, 256), return_geom: bool = False):
+    """K3 over every (series, level): coords float32 [B,L,2] on the device.  ``spacings`` is a
+    list of per-series (row, col) mm/px (``get_slice_spacing``, cropping.py:82-101); the
+    reference always crops the 0.3 mm isotropic slice, so the default is (0.3, 0.3)."""
+    B, L = int(coords.shape[0]), int(coords.shape[1])
+    dev = coords.device
+    if spacings is None:
+        spacings = [(0.3, 0.3)] * B
+    deltas = [mm_to_pixels(crop_delta_mm, sp) for sp in spacings]  # cropping.py:149-169, host ints
+    delta = torch.tensor(deltas, dtype=torch.int32).repeat_interleave(L, dim=0).contiguous()
+    max_box = (max(1, max(d[2] + d[3] for d in deltas)), max(1, max(d[0] + d[1] for d in deltas)))
+    mh, mw = pool.max_hw
+    max_box = (min(max_box[0], mh), min(max_box[1], mw))
+    idx = torch.arange(B, dtype=torch.int32).repeat_interleave(L).contiguous()
+    crops, crops2, geom = ops.crop_resample(pool, idx.to(dev, non_blocking=True), coords.reshape(B * L, 2).contiguous(),
+                                            delta.to(dev, non_blocking=True), max_box, crop_size, second_size, return_geom)
+    crops = crops.view(B, L, *crops.shape[1:])
+    if crops2 is not None:
+        crops2 = crops2.view(B, L, *crops2.shape[1:])
+    if geom is not None:
+        geom = geom.view(B, L, 8)
+    return crops, crops2, geom
+
+
+def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop_delta_mm=(55, 15, 17.5, 20),
+                      crop_size=(256, 256), image_size=(512, 512), second_size=(256, 256), spacings=None,
+                      keep_planes: bool = False, times: dict | None = None) -> CropBatch:
+    """One batched pass of the hot path over a pool of middle slices already in HBM.
+    ``model=None`` reproduces the reference's centre-crop fallback (__init__.py:194-197)."""
+    dev = pool.data.device
+    B = pool.n
+    planes = None
+    if model is not None:
+        planes = ops.normalize_resize(pool, image_size)
+        coords = model.predict_u8(planes, times)
+    else:
+        fb = get_center_fallback_locations()
+        one = torch.tensor([fb[i] for i in range(NUM_LEVELS)], dtype=torch.float32)
+        coords = one.unsqueeze(0).repeat(B, 1, 1).to(dev)
+    crops, crops2, _ = crop_levels(pool, coords, crop_delta_mm, spacings, crop_size, second_size)
+    return CropBatch(coords, crops, crops2, planes if keep_planes else None, times or {})
+
+
+# ------------------------------------------------------------------------------------------ multi-GPU
+def shard_series(sizes, world_size: int) -> list[list[int]]:
+    """Greedy size-balanced partition of series indices (cost = H'*W' pixels) over ranks.
+    Deterministic: every rank computes the same assignment with no communication."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    loads = [0] * world_size
+    shards: list[list[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (loads[k], k))
+        shards[r].append(i)
+        loads[r] += int(sizes[i])
+    for s in shards:
+        s.sort()
+    return shards
+
+
+def gather_results(local_index: list[int], coords: torch.Tensor, crops: torch.Tensor, n_total: int, group=None):
+    """The one exchange of the path: all ranks' (index, coords, crops) gathered on every rank
+    with a padded ``all_gather`` (NCCL over NVLink on GPUs, gloo in the CPU tests) and
+    scattered back into series order.  Returns ``(coords [n_total,5,2], crops [n_total,5,h,w])``."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        out_c = torch.zeros((n_total,) + tuple(coords.shape[1:]), dtype=coords.dtype, device=coords.device)
+        out_k = torch.zeros((n_total,) + tuple(crops.shape[1:]), dtype=crops.dtype, device=crops.device)
+        if len(local_index):
+            ix = torch.as_tensor(local_index, dtype=torch.long, device=coords.device)
+            out_c[ix] = coords
+            out_k[ix] = crops
+        return out_c, out_k
+    world = dist.get_world_size(group)
+    dev = coords.device
+    n_local = torch.tensor([len(local_index)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(counts, n_local, group=group)
+    n_max = max(int(c.item()) for c in counts)
+    pad_idx = torch.full((n_max,), -1, dtype=torch.int64, device=dev)
+    pad_c = torch.zeros((n_max,) + tuple(coords.shape[1:]), dtype=coords.dtype, device=dev)
+    pad_k = torch.zeros((n_max,) + tuple(crops.shape[1:]), dtype=crops.dtype, device=dev)
+    k = len(local_index)
+    if k:
+        pad_idx[:k] = torch.as_tensor(local_index, dtype=torch.int64, device=dev)
+        pad_c[:k] = coords
+        pad_k[:k] = crops
+    all_idx = [torch.empty_like(pad_idx) for _ in range(world)]
+    all_c = [torch.empty_like(pad_c) for _ in range(world)]
+    all_k = [torch.empty_like(pad_k) for _ in range(world)]
+    dist.all_gather(all_idx, pad_idx, group=group)
+    dist.all_gather(all_c, pad_c, group=group)
+    dist.all_gather(all_k, pad_k, group=group)
+    out_c = torch.zeros((n_total,) + tuple(coords.shape[1:]), dtype=coords.dtype, device=dev)
+    out_k = torch.zeros((n_total,) + tuple(crops.shape[1:]), dtype=crops.dtype, device=dev)
+    for ix, c, kk in zip(all_idx, all_c, all_k):
+        valid = ix >= 0
+        out_c[ix[valid]] = c[valid]
+        out_k[ix[valid]] = kk[valid]
+    return out_c, out_k

@@ -1,0 +1,101 @@
+"""GPU numerics: the tcgen05 GEMM and the other ConvNeXt layer kernels vs plain PyTorch fp32 references."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from gpu_util import dev
+from spine_vision_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DT = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _ref_gemm(a, w, bias, mode, resid=None, gamma=None):
+    acc = a.float() @ w.float().t() + bias
+    if mode == 0:
+        return F.gelu(acc)
+    if mode == 1:
+        return resid.float() + gamma * acc
+    return acc
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K,mode", [
+    (128, 128, 64, 2), (128, 256, 128, 2), (256, 512, 128, 0), (1000, 256, 512, 2), (4096, 128, 512, 1),
+    (2048, 1024, 256, 0), (640, 256, 1024, 1), (128 * 150, 512, 128, 0), (3000, 2048, 512, 0), (3000, 512, 2048, 1),
+    (512, 1024, 4096, 1), (777, 4096, 1024, 0), (128 * 300 + 5, 128, 512, 1),
+])
+def test_gemm_vs_torch(M, N, K, mode, dtype):
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + mode)
+    a = (torch.randn(M, K, generator=g)).to(DT[dtype]).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DT[dtype]).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    gamma = (torch.rand(N, generator=g) + 0.1).to(dev())
+    resid = torch.randn(M, N, generator=g).to(DT[dtype]).to(dev())
+    want = _ref_gemm(a, w, bias, mode, resid, gamma)
+    if mode == 1:
+        out = resid.clone()
+        got = ops.gemm(a, w, bias, 1, resid=out, gamma=gamma, out=out)  # in place, as the model runs it
+    else:
+        got = ops.gemm(a, w, bias, mode)
+    torch.cuda.synchronize()
+    err = (got.float() - want).abs()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)  # output rounding to 16 bits
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{bad} of {err.numel()} beyond tolerance; max err {err.max().item():.4g} at {np.unravel_index(int(err.argmax()), err.shape)}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024),
+                                     (1, 15, 23, 1024), (1, 128, 128, 128)])
+def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
+    g = torch.Generator().manual_seed(B + H + W + C)
+    x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
+    wt = torch.randn(C, 1, 7, 7, generator=g) * 0.1
+    bias = torch.randn(C, generator=g) * 0.1
+    lnw = 1 + 0.2 * torch.randn(C, generator=g)
+    lnb = 0.1 * torch.randn(C, generator=g)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (C,), lnw, lnb, 1e-6)
+    taps = wt.reshape(C, 49).t().contiguous()
+    got = ops.dwconv_ln(x.to(dev()), taps.to(dev()), bias.to(dev()), lnw.to(dev()), lnb.to(dev())).float().cpu()
+    err = (got - want).abs()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int((err > tol).sum()) == 0, f"max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+def test_stem_patchify_head_vs_torch(dtype):
+    g = torch.Generator().manual_seed(5)
+    d = dev()
+    # stem: folded single-channel conv4x4/s4 + LayerNorm2d
+    u8 = torch.randint(0, 256, (2, 64, 96), generator=g, dtype=torch.uint8)
+    wf = torch.randn(128, 16, generator=g) * 0.01
+    bf = torch.randn(128, generator=g) * 0.1
+    lnw, lnb = 1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    y = F.conv2d(u8.float().unsqueeze(1), wf.view(128, 1, 4, 4), bf, stride=4).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (128,), lnw, lnb, 1e-6)
+    got = ops.stem_ln(u8.to(d), wf.to(d), bf.to(d), lnw.to(d), lnb.to(d), DT[dtype]).float().cpu()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int(((got - want).abs() > tol).sum()) == 0
+    # LayerNorm2d + 2x2 patchify
+    x = torch.randn(2, 8, 12, 256, generator=g).to(DT[dtype])
+    lw, lb = 1 + 0.1 * torch.randn(256, generator=g), 0.1 * torch.randn(256, generator=g)
+    n = F.layer_norm(x.float(), (256,), lw, lb, 1e-6)
+    want = n.view(2, 4, 2, 6, 2, 256).permute(0, 1, 3, 2, 4, 5).reshape(2, 4, 6, 1024)
+    got = ops.ln_patchify(x.to(d), lw.to(d), lb.to(d)).float().cpu()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int(((got - want).abs() > tol).sum()) == 0
+    # pool + head
+    xs = torch.randn(3, 256, 1024, generator=g).to(DT[dtype])
+    p = [1 + 0.1 * torch.randn(1024, generator=g), 0.1 * torch.randn(1024, generator=g),
+         1 + 0.1 * torch.randn(1024, generator=g), 0.1 * torch.randn(1024, generator=g),
+         torch.randn(256, 1024, generator=g) / 32, 0.1 * torch.randn(256, generator=g),
+         torch.randn(10, 256, generator=g) / 16, 0.1 * torch.randn(10, generator=g)]
+    f = xs.float().mean(1)
+    f = F.layer_norm(f, (1024,), p[0], p[1], 1e-6)
+    f = F.layer_norm(f, (1024,), p[2], p[3], 1e-5)
+    want = torch.sigmoid(F.gelu(f @ p[4].t() + p[5]) @ p[6].t() + p[7])
+    got = ops.head(xs.to(d), *[t.to(d) for t in p]).cpu()
+    assert (got - want).abs().max() < 2e-5

@@ -1,0 +1,89 @@
+"""GPU parity: the CoordinateRegressor forward and the whole localize-and-crop path vs the fp32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from gpu_util import dev
+from oracle import reference_path as ref
+from oracle.convnext import make_model
+from spine_vision_b200 import cropping, ops, pipeline, synthetic
+
+pytestmark = pytest.mark.gpu
+PX = 512.0
+SLICES = [(20, 1195, 1195), (21, 640, 650), (22, 900, 700), (23, 512, 512)]
+
+
+def _oracle_coords(model, slices):
+    out = []
+    for sl in slices:
+        _, t = ref.preprocess_slice(sl, (512, 512))
+        with torch.no_grad():
+            out.append(model(t.unsqueeze(0))[0].numpy())
+    return np.stack(out)
+
+
+# tolerance stated by BASELINE.json north_star: 0.5 px at 512^2 on random-init weights.  The
+# "trained-like" weights (layer-scale U(0.1,1)) make 36 blocks of 16-bit rounding visible: fp16
+# operands hold 0.5 px, bf16 operands are held to 1.0 px (measured ~0.5-0.7 px; DESIGN.md, precision).
+@pytest.mark.parametrize("dtype,trained,tol_px", [("bf16", False, 0.5), ("fp16", False, 0.5), ("fp16", True, 0.5), ("bf16", True, 1.0)])
+def test_model_coords_vs_oracle(dtype, trained, tol_px):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    om = make_model("base", seed=0, trained_like=trained)
+    slices = [synthetic.make_iso_slice(*c) for c in SLICES]
+    want = _oracle_coords(om, slices)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype=dtype, micro_batch=3)  # 3 + 1: exercises the tail chunk
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    planes = ops.normalize_resize(pool, (512, 512))
+    got = model.predict_u8(planes).cpu().numpy()
+    err_px = np.abs(got - want).max() * PX
+    assert got.shape == (4, 5, 2) and np.isfinite(got).all()
+    assert err_px <= tol_px, f"{dtype} trained={trained}: max coordinate error {err_px:.3f} px (tolerance {tol_px})"
+    # golden coordinates frozen from the reference's own predict_ivd_locations
+    g = np.load(GOLDEN / "model_coords.npz")
+    tag = "trained" if trained else "init"
+    for i, (seed, h, w) in enumerate(SLICES[:2]):
+        gerr = np.abs(got[i] - g[f"coords_{tag}_{seed}_{h}_{w}"]).max() * PX
+        assert gerr <= tol_px, f"vs reference golden: {gerr:.3f} px"
+
+
+def test_checkpoint_roundtrip_and_predict_api(tmp_path):
+    om = make_model("base", seed=0)
+    ck = tmp_path / "best_model.pt"
+    torch.save({"epoch": 3, "model_state_dict": om.state_dict(), "optimizer_state_dict": {}, "scheduler_state_dict": None,
+                "best_metric": 0.0, "best_epoch": 3, "history": {}, "config": {}}, ck)  # trainers/base.py:695-706
+    model = cropping.load_localization_model(ck, "base", dev())
+    img = synthetic.make_iso_slice(21, 640, 650)
+    locs = cropping.predict_ivd_locations(model, img, dev(), (512, 512))
+    want = ref.predict_ivd_locations(om, img, "cpu", (512, 512))
+    assert set(locs) == {0, 1, 2, 3, 4} and all(isinstance(v[0], float) for v in locs.values())
+    assert max(abs(locs[i][k] - want[i][k]) for i in range(5) for k in range(2)) * PX <= 0.5
+    bad = dict(om.state_dict())
+    bad.pop("backbone.stages.1.blocks.0.gamma")
+    with pytest.raises(Exception, match="gamma|stage"):
+        cropping.LocalizationModel(bad, dev())
+
+
+def test_pipeline_end_to_end_vs_oracle():
+    om = make_model("base", seed=0)
+    slices = [synthetic.make_iso_slice(30 + i, h, w) for i, (h, w) in enumerate([(1195, 1195), (640, 650), (880, 1000)])]
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16")
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    batch = pipeline.localize_and_crop(pool, model, (50, 20, 30, 30), (128, 128), keep_planes=True)
+    coords, crops, crops2 = batch.to_host()
+    planes = batch.planes.cpu().numpy()
+    dpx = ref.mm_to_pixels((50, 20, 30, 30), (0.3, 0.3))
+    for i, sl in enumerate(slices):
+        plane, _ = ref.preprocess_slice(sl, (512, 512))
+        assert np.array_equal(planes[i], plane)
+        for lvl in range(5):
+            # crops are bit-exact given the coordinates the device produced
+            want = ref.crop_region_horizontal(sl, float(coords[i, lvl, 0]), float(coords[i, lvl, 1]), (128, 128), dpx)
+            assert np.array_equal(crops[i, lvl], want)
+    want_c = _oracle_coords(om, slices)
+    assert np.abs(coords - want_c).max() * PX <= 0.5
+    # centre-crop fallback when no model is given (__init__.py:194-197)
+    fb = pipeline.localize_and_crop(pool, None, (50, 20, 30, 30), (128, 128))
+    c0 = fb.crops.cpu().numpy()
+    for lvl, (x, y) in cropping.get_center_fallback_locations().items():
+        assert np.array_equal(c0[0, lvl], ref.crop_region_horizontal(slices[0], x, y, (128, 128), dpx))

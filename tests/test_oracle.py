@@ -1,0 +1,172 @@
+"""CPU: the oracle against the golden vectors frozen from the reference's own functions
+(oracle/make_golden.py) and against the libraries the reference calls."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import fixedpoint as fx
+from oracle import reference_path as ref
+from oracle.convnext import make_model
+from spine_vision_b200 import synthetic
+
+
+def _cases(npz, prefix):
+    for k in npz.files:
+        if k.startswith(prefix):
+            yield k, [int(v) for v in k[len(prefix):].split("_")[:3]]
+
+
+def test_mm_to_pixels_known_answers():
+    g = np.load(GOLDEN / "mm_to_pixels.npz")
+    # notebooks/compare_crop_modes.ipynb:65,255 -> left=117, right=17, top=67, bottom=67
+    assert fx.mm_to_pixels((35, 5, 20, 20), (0.3, 0.3)) == (117, 17, 67, 67)
+    for d, s, o in zip(g["delta_mm"], g["spacing"], g["out"]):
+        assert fx.mm_to_pixels(tuple(d), tuple(s)) == tuple(int(v) for v in o)
+        assert ref.mm_to_pixels(tuple(d), tuple(s)) == tuple(int(v) for v in o)
+
+
+def test_normalize_edge_cases_match_reference():
+    g = np.load(GOLDEN / "normalize_edge.npz")
+    for k in g.files:
+        if k.startswith("in_"):
+            want = g["out_" + k[3:]]
+            assert np.array_equal(fx.normalize_to_uint8(g[k]), want), k
+            assert np.array_equal(ref.normalize_to_uint8(g[k]), want), k
+    assert fx.normalize_to_uint8(np.full((2, 2), 300.0))[0, 0] == 44  # wraps mod 256
+
+
+def test_k1_restatement_matches_reference_golden():
+    g = np.load(GOLDEN / "k1_normalize_resize.npz")
+    n = 0
+    for k, (seed, h, w) in _cases(g, "plane_"):
+        img = synthetic.make_iso_slice(seed, h, w)
+        u8 = fx.normalize_to_uint8(img)
+        s = g[f"u8sum_{seed}_{h}_{w}"]
+        assert int(u8.astype(np.int64).sum()) == int(s[0]) and int(u8[::7, ::5].astype(np.int64).sum()) == int(s[1])
+        assert np.array_equal(fx.pillow_resize_u8(u8, (512, 512)), g[k]), k
+        plane, _ = ref.preprocess_slice(img, (512, 512))
+        assert np.array_equal(plane, g[k]), k
+        n += 1
+    assert n >= 4
+
+
+@pytest.mark.parametrize("shape", [(1195, 1195, 512, 512), (3400 // 4, 1100 // 4, 128, 128), (350, 420, 512, 512),
+                                   (128, 128, 256, 256), (109, 128, 256, 256), (64, 64, 64, 96)])
+def test_pillow_restatement_vs_pillow(shape):
+    Image = pytest.importorskip("PIL.Image")
+    h, w, oh, ow = shape
+    img = np.random.default_rng(h * 7 + w).integers(0, 256, (h, w), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((ow, oh), Image.BILINEAR))
+    assert np.array_equal(fx.pillow_resize_u8(img, (oh, ow)), want)
+
+
+@pytest.mark.parametrize("shape", [(200, 234, 109, 128), (234, 200, 128, 109), (125, 233, 69, 128), (50, 60, 128, 107),
+                                   (256, 200, 128, 100), (1, 7, 18, 128), (128, 128, 128, 128), (3, 5, 77, 128)])
+def test_opencv_restatement_vs_opencv(shape):
+    cv2 = pytest.importorskip("cv2")
+    h, w, oh, ow = shape
+    img = np.random.default_rng(h * 13 + w).integers(0, 256, (h, w), dtype=np.uint8)
+    want = cv2.resize(img, (ow, oh), interpolation=cv2.INTER_LINEAR)
+    assert np.array_equal(fx.cv_resize_u8(img, (oh, ow)), want)
+
+
+def test_crops_match_reference_golden():
+    g = np.load(GOLDEN / "k3_crops.npz")
+    n = 0
+    deltas = [(50, 20, 30, 30), (55, 15, 17.5, 20)]
+    for k in g.files:
+        if not k.startswith("crops_"):
+            continue
+        seed, h, w, d, c = k[len("crops_"):].split("_")
+        seed, h, w, di, cs = int(seed), int(h), int(w), int(d[1:]), int(c[1:])
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        dpx = fx.mm_to_pixels(deltas[di], (0.3, 0.3))
+        for s in (0, 2):
+            for lvl in range(5):
+                x, y = float(xy[s, lvl, 0]), float(xy[s, lvl, 1])
+                assert np.array_equal(fx.crop_region_horizontal(img, x, y, (cs, cs), dpx), g[k][s, lvl]), (k, s, lvl)
+                assert np.array_equal(ref.crop_region_horizontal(img, x, y, (cs, cs), dpx), g[k][s, lvl]), (k, s, lvl)
+                n += 1
+    assert n >= 80
+
+
+def test_classifier_input_matches_reference_golden():
+    g = np.load(GOLDEN / "classifier_input.npz")
+    u8, t = ref.classifier_input(g["t2"], g["t1"])
+    assert np.array_equal(u8, g["up"])
+    assert t.shape == (3, 256, 256)
+    # per-channel Pillow resize == restated integer resize of each plane
+    assert np.array_equal(fx.pillow_resize_u8(g["t2"], (256, 256)), g["up"][..., 0])
+    assert np.array_equal(fx.pillow_resize_u8(g["t1"], (256, 256)), g["up"][..., 1])
+
+
+def test_convnext_restatement_equals_torchvision():
+    """timm is absent; the restated backbone must be the same function as torchvision's
+    convnext_base once the weights are mapped across."""
+    tv = pytest.importorskip("torchvision.models")
+    m = make_model("base", seed=3, trained_like=True)
+    t = tv.convnext_base(weights=None).eval()
+    sd = m.backbone.state_dict()
+    tsd = t.state_dict()
+    # torchvision: features.0 = stem, features.{1,3,5,7} = stages, features.{2,4,6} = downsample
+    tsd["features.0.0.weight"], tsd["features.0.0.bias"] = sd["stem.0.weight"], sd["stem.0.bias"]
+    tsd["features.0.1.weight"], tsd["features.0.1.bias"] = sd["stem.1.weight"], sd["stem.1.bias"]
+    for s in range(4):
+        if s > 0:
+            f = 2 * s
+            tsd[f"features.{f}.0.weight"], tsd[f"features.{f}.0.bias"] = sd[f"stages.{s}.downsample.0.weight"], sd[f"stages.{s}.downsample.0.bias"]
+            tsd[f"features.{f}.1.weight"], tsd[f"features.{f}.1.bias"] = sd[f"stages.{s}.downsample.1.weight"], sd[f"stages.{s}.downsample.1.bias"]
+        f = 2 * s + 1
+        j = 0
+        while f"stages.{s}.blocks.{j}.gamma" in sd:
+            p = f"stages.{s}.blocks.{j}."
+            q = f"features.{f}.{j}."
+            tsd[q + "layer_scale"] = sd[p + "gamma"].reshape(-1, 1, 1)
+            tsd[q + "block.0.weight"], tsd[q + "block.0.bias"] = sd[p + "conv_dw.weight"], sd[p + "conv_dw.bias"]
+            tsd[q + "block.2.weight"], tsd[q + "block.2.bias"] = sd[p + "norm.weight"], sd[p + "norm.bias"]
+            tsd[q + "block.3.weight"], tsd[q + "block.3.bias"] = sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]
+            tsd[q + "block.5.weight"], tsd[q + "block.5.bias"] = sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"]
+            j += 1
+    tsd["classifier.0.weight"], tsd["classifier.0.bias"] = sd["head.norm.weight"], sd["head.norm.bias"]
+    t.load_state_dict(tsd)
+    t.classifier[2] = torch.nn.Identity()
+    x = torch.randn(1, 3, 128, 128, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        a, b = m.backbone(x), t(x)
+    assert a.shape == b.shape == (1, 1024)
+    assert torch.allclose(a, b, atol=2e-5, rtol=1e-5), (a - b).abs().max()
+    assert len(m.state_dict()) == 348  # 342 backbone + 6 head tensors
+
+
+def test_model_coords_match_reference_golden():
+    g = np.load(GOLDEN / "model_coords.npz")
+    torch.set_num_threads(8)
+    for tag, tl in (("init", False), ("trained", True)):
+        m = make_model("base", seed=0, trained_like=tl)
+        sd = m.state_dict()
+        fp = np.array([float(sd["backbone.stem.0.weight"].double().sum()),
+                       float(sd["backbone.stages.2.blocks.13.mlp.fc1.weight"].double().sum()),
+                       float(sd["head.5.weight"].double().sum())])
+        assert np.allclose(fp, g[f"wsum_{tag}"], rtol=0, atol=1e-9), "torch RNG drift: seeded weights differ from the golden run"
+        k = f"coords_{tag}_21_640_650"
+        locs = ref.predict_ivd_locations(m, synthetic.make_iso_slice(21, 640, 650), "cpu", (512, 512))
+        got = np.array([locs[i] for i in range(5)])
+        assert np.abs(got - g[k]).max() < 2e-6, np.abs(got - g[k]).max()
+
+
+def test_gelu_fast_formula():
+    """NumPy replica of gelu_fast (csrc/svb_convnext_kernels.cuh) vs exact erf GELU."""
+    from scipy.special import erf
+
+    x = np.linspace(-12, 12, 200001).astype(np.float32)
+    u = np.minimum(np.abs(x), np.float32(5.65685425))
+    r = np.float32(-5.20460508e-04)
+    for c in (7.39751849e-03, -5.25612477e-02, -4.59254682e-01, -1.15109138e+00):
+        r = r * u + np.float32(c)
+    r = r * u
+    e = np.exp2(r.astype(np.float32))
+    got = np.maximum(x, 0) - np.abs(np.float32(0.5) * x * e)
+    want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
+    assert np.abs(got - want).max() < 3e-6
