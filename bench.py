@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""Headline benchmark: series/sec of the localize-and-crop hot path (BASELINE.json).
+
+    python bench.py --gpus 1 --steps K --warmup W          # this repo's sm_100a path
+    python bench.py --impl reference ...                   # the reference's CPU path (oracle port) on host cores
+
+One step = one pass of the hot path over one batch of synthetic middle slices:
+K1 normalise+resize -> ConvNeXt-base localizer -> K3 crops (128^2 + 256^2).  Workload (N=1):
+BASELINE.json configs[1] -- 256 series of 1195x1195 fp32 (512 px @ 0.7 mm resampled to 0.3 mm),
+convnext_base random init, 5 levels, crop_delta_mm 50/20/30/30.  `value` is measured with the
+slices resident in HBM; `e2e` through the public API with pinned-host inputs (H2D inside the timed
+region) and the crops/coords read back to the host.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+CROP_DELTA_MM = (50, 20, 30, 30)
+CROP_SIZE = (128, 128)
+SECOND_SIZE = (256, 256)
+IMAGE_SIZE = (512, 512)
+SLICE_HW = (1195, 1195)
+WORKLOAD = ("configs[1]: 256 synthetic sagittal middle slices 1195x1195 fp32 (512px@0.7mm -> 0.3mm iso) per GPU, "
+            "convnext_base random-init localizer @512x512, 5 IVD levels, crop_delta_mm 50/20/30/30, 128x128 crops + 256x256 classifier input")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="series per GPU per step")
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic slices (tiled to the batch)")
+    ap.add_argument("--ref-series", type=int, default=4, help="series per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_rate(n_series: int, steps: int, warmup: int):
+    """The reference's own CPU path (oracle/reference_path.py: NumPy + Pillow + OpenCV + torch fp32,
+    batch-1 loop exactly as process_spider runs it) on this box's host cores."""
+    import torch
+
+    from oracle import reference_path as ref
+    from oracle.convnext import make_model
+    from spine_vision_b200 import synthetic
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    try:
+        import cv2
+
+        cv2.setNumThreads(cores)
+    except Exception:
+        pass
+    model = make_model("base", seed=0)
+    slices = [synthetic.make_iso_slice(s, *SLICE_HW) for s in range(n_series)]
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        ref.localize_and_crop_series(model, slices, CROP_SIZE, CROP_DELTA_MM, IMAGE_SIZE)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    mean = sum(times) / len(times)
+    return n_series / mean, mean, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, mean, cores = cpu_reference_rate(args.ref_series, args.steps, args.warmup)
+    sample = f"{args.ref_series} series/step of the same workload, batch-1 loop (reference-faithful), {args.steps} steps after {args.warmup} warm-up"
+    line = {
+        "impl": "reference", "metric": "series/sec", "value": rate, "unit": "series/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "series_per_step": args.ref_series},
+        "crops_per_sec": rate * 5,
+        "cpu_baseline": {"value": rate, "unit": "series/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "series/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # NVML unavailable: report that rather than invent numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from spine_vision_b200 import ops, pipeline, synthetic
+    from spine_vision_b200.cropping import LocalizationModel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py (impl b200) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    B = args.batch
+    # synthetic data (per-rank seeds: weak scaling, every rank owns its own series)
+    base = [synthetic.make_iso_slice(1000 * rank + s, *SLICE_HW) for s in range(min(args.distinct, B))]
+    slices = [base[i % len(base)] for i in range(B)]
+    host, offs, shapes = ops.SlicePool.pin(slices)  # pinned staging, filled once outside the timed region
+    model = LocalizationModel(synthetic.random_state_dict("base", seed=0), dev, dtype=args.dtype, micro_batch=args.micro_batch)
+    n_crops = B * 5
+    pin_coords = torch.empty((B, 5, 2), dtype=torch.float32).pin_memory()
+    pin_crops = torch.empty((B, 5, *CROP_SIZE), dtype=torch.uint8).pin_memory()
+    pin_crops2 = torch.empty((B, 5, *SECOND_SIZE), dtype=torch.uint8).pin_memory()
+
+    def step_resident(pool, times=None):
+        return pipeline.localize_and_crop(pool, model, CROP_DELTA_MM, CROP_SIZE, IMAGE_SIZE, SECOND_SIZE, times=times)
+
+    def gather(batch):
+        if world > 1:  # the path's one exchange: crops + coordinates to every rank (NCCL over NVLink)
+            gc = torch.empty((world,) + tuple(batch.coords.shape), dtype=batch.coords.dtype, device=dev)
+            gk = torch.empty((world,) + tuple(batch.crops.shape), dtype=batch.crops.dtype, device=dev)
+            dist.all_gather_into_tensor(gc, batch.coords)
+            dist.all_gather_into_tensor(gk, batch.crops)
+
+    def step_e2e():
+        pool = ops.SlicePool.from_pinned(host, offs, shapes, dev)  # H2D of this step's inputs
+        batch = step_resident(pool)
+        gather(batch)
+        pin_coords.copy_(batch.coords, non_blocking=True)  # D2H of the step's result
+        pin_crops.copy_(batch.crops, non_blocking=True)
+        pin_crops2.copy_(batch.crops2, non_blocking=True)
+        return pool
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    pool = ops.SlicePool.from_pinned(host, offs, shapes, dev)
+    torch.cuda.synchronize()
+
+    def resident_step():
+        gather(step_resident(pool))
+
+    for _ in range(args.warmup):
+        resident_step()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(resident_step, args.steps)
+    # roofline pass: same steps with a CUDA event pair around every launch of the model, and around
+    # K1 / K3 with their (tiny) index tensors prebuilt so that no host work sits between the events
+    times: dict = {}
+    k1_ms = k3_ms = 0.0
+    dpx = pipeline.mm_to_pixels(CROP_DELTA_MM, (0.3, 0.3))
+    k3_idx = torch.arange(B, dtype=torch.int32).repeat_interleave(5).contiguous().to(dev)
+    k3_delta = torch.tensor([dpx] * n_crops, dtype=torch.int32).to(dev)
+    max_box = (dpx[2] + dpx[3], dpx[0] + dpx[1])
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        planes = ops.normalize_resize(pool, IMAGE_SIZE)
+        ev[1].record()
+        coords = model.predict_u8(planes, times)
+        xy = coords.reshape(n_crops, 2)
+        torch.cuda.synchronize()
+        ev[2].record()
+        ops.crop_resample(pool, k3_idx, xy, k3_delta, max_box, CROP_SIZE, SECOND_SIZE)
+        ev[3].record()
+        torch.cuda.synchronize()
+        k1_ms += ev[0].elapsed_time(ev[1])
+        k3_ms += ev[2].elapsed_time(ev[3])
+    # end-to-end pass through the public API: pinned host -> H2D -> kernels -> D2H
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step * 1e-3)
+        e2e = world * B / (ms_e2e / args.steps * 1e-3)
+        gemm_flops, launches = model.engine.cost(B, *IMAGE_SIZE)
+        n_chunks = (B + args.micro_batch - 1) // args.micro_batch
+        fwd_launches, _ = launches, None
+        _, per_chunk = model.engine.cost(min(args.micro_batch, B), *IMAGE_SIZE)
+        k1_chunks = max(1, (B * SLICE_HW[0] * SLICE_HW[1] * 4 + (64 << 20) - 1) // (64 << 20))
+        gpu_launches = args.steps * (1 + 2 * k1_chunks + per_chunk * n_chunks + 2)
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+        gemm_ms = times.get("gemm", 0.0) / args.steps
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        hbm = float(peaks.get("hbm_gbs", 6650.0))
+        k1_bytes = B * (SLICE_HW[0] * SLICE_HW[1] * 4 + IMAGE_SIZE[0] * IMAGE_SIZE[1])
+        k3_bytes = n_crops * (234 * 200 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])
+        line = {
+            "metric": "series/sec", "value": value, "unit": "series/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+            "data": f"synthetic ({len(base)} distinct seeded slices tiled to {B}; random-init convnext_base)",
+            "config": {"workload": WORKLOAD, "series_per_gpu_per_step": B, "micro_batch": args.micro_batch,
+                       "l2": "inputs larger than L2 (1.46 GB of fp32 slices per step; 6.4 GB of activations)"},
+            "crops_per_sec": value * 5,
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e, "unit": "series/s", "h2d_bytes_per_step": int(host.numel() * 4 + B * 16),
+                    "d2h_bytes_per_step": int(pin_coords.numel() * 4 + pin_crops.numel() + pin_crops2.numel()),
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(gpu_launches),
+            "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
+                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
+                         "traffic": None, "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
+                         "timing": "CUDA event pair around every launch, separate pass over the same steps"},
+            "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
+                                   "k3_crop_resample": k3_ms / args.steps},
+            "hbm_kernels": {
+                "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None, "peak_gbs": hbm},
+                "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None, "peak_gbs": hbm},
+            },
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, mean, cores = cpu_reference_rate(args.ref_series, 2, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",
+                                    "sample": f"{args.ref_series} series of the same workload through oracle/reference_path.py (batch-1 loop), 2 timed passes after 1 warm-up"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -95,3 +95,44 @@ def make_coords(n_series: int, seed: int = 0, border_frac: float = 0.01, hw=(119
     xy[:, :, 1] = np.where(force & (side == 2), off / h, xy[:, :, 1])
     xy[:, :, 1] = np.where(force & (side == 3), 1.0 - (off + 1) / h, xy[:, :, 1])
     return np.clip(xy, 0.0, np.float32(0.99999)).astype(np.float32)
+
+
+CONVNEXT_VARIANTS = {
+    "base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
+    "xlarge": ((3, 3, 27, 3), (256, 512, 1024, 2048)),
+}
+
+
+def random_state_dict(variant: str = "base", seed: int = 0, num_levels: int = 5, trained_like: bool = False):
+    """Random-init ``CoordinateRegressor`` state dict under the reference's key names
+    (timm ConvNeXt scheme + ``head.{0,2,5}``): conv/linear ~ trunc_normal(std=0.02),
+    zero biases, LayerNorm (1, 0), layer-scale 1e-6 -- timm's init.  ``trained_like`` widens the
+    layer scale to U(0.1, 1) so that every block contributes."""
+    import torch
+
+    depths, dims = CONVNEXT_VARIANTS[variant]
+    g = torch.Generator().manual_seed(seed)
+
+    def tn(*shape):
+        return torch.nn.init.trunc_normal_(torch.empty(*shape), std=0.02, generator=g)
+
+    sd = {}
+    sd["backbone.stem.0.weight"], sd["backbone.stem.0.bias"] = tn(dims[0], 3, 4, 4), torch.zeros(dims[0])
+    sd["backbone.stem.1.weight"], sd["backbone.stem.1.bias"] = torch.ones(dims[0]), torch.zeros(dims[0])
+    for s, (d, c) in enumerate(zip(depths, dims)):
+        p = f"backbone.stages.{s}."
+        if s > 0:
+            sd[p + "downsample.0.weight"], sd[p + "downsample.0.bias"] = torch.ones(dims[s - 1]), torch.zeros(dims[s - 1])
+            sd[p + "downsample.1.weight"], sd[p + "downsample.1.bias"] = tn(c, dims[s - 1], 2, 2), torch.zeros(c)
+        for j in range(d):
+            q = p + f"blocks.{j}."
+            sd[q + "gamma"] = (torch.rand(c, generator=g) * 0.9 + 0.1) if trained_like else torch.full((c,), 1e-6)
+            sd[q + "conv_dw.weight"], sd[q + "conv_dw.bias"] = tn(c, 1, 7, 7), torch.zeros(c)
+            sd[q + "norm.weight"], sd[q + "norm.bias"] = torch.ones(c), torch.zeros(c)
+            sd[q + "mlp.fc1.weight"], sd[q + "mlp.fc1.bias"] = tn(4 * c, c), torch.zeros(4 * c)
+            sd[q + "mlp.fc2.weight"], sd[q + "mlp.fc2.bias"] = tn(c, 4 * c), torch.zeros(c)
+    sd["backbone.head.norm.weight"], sd["backbone.head.norm.bias"] = torch.ones(dims[3]), torch.zeros(dims[3])
+    sd["head.0.weight"], sd["head.0.bias"] = torch.ones(dims[3]), torch.zeros(dims[3])
+    sd["head.2.weight"], sd["head.2.bias"] = tn(256, dims[3]), torch.zeros(256)
+    sd["head.5.weight"], sd["head.5.bias"] = tn(num_levels * 2, 256), torch.zeros(num_levels * 2)
+    return sd
