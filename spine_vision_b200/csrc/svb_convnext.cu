@@ -7,6 +7,7 @@
 #include "svb_convnext_kernels.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -37,6 +38,8 @@ struct ActPlan {  // tensor maps that depend on the workspace pointer and the mi
     CUtensorMap a_map[4];   // [M, C]   fc1 A operand
     CUtensorMap h_map[4];   // [M, 4C]  fc2 A operand
     CUtensorMap a2_map[4];  // [M/4, 4C_prev] downsample A operand (index = destination stage)
+    CUtensorMap ox_map[4];  // [M, C]   32x32 epilogue boxes over the residual stream X (fc2 / downsample output, fc2 residual)
+    CUtensorMap oh_map[4];  // [M, 4C]  32x32 epilogue boxes over the hidden buffer (fc1 output)
 };
 
 }  // namespace svb
@@ -85,7 +88,27 @@ static int make_operand_map(CUtensorMap* map, int dtype, const void* base, uint6
     const uint32_t box[2] = {64, box_rows};
     return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
+// epilogue box map: rows x N 16-bit row-major, box {32 columns, 32 rows}, 64-byte swizzle (gemm_kernel epilogue)
+static int make_epilogue_map(CUtensorMap* map, int dtype, const void* base, uint64_t rows, uint64_t N) {
+    const uint64_t dims[2] = {N, rows};
+    const uint64_t strides[1] = {N * 2};
+    const uint32_t box[2] = {32, 32};
+    return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+}
 static int gemm_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
+// CTA-pair (cta_group::2) tiles pay off when the K loop is long enough to hide the pair's tile hand-over
+// (measured on B200, profiles/r01_gemm_shapes.txt): K >= 1024, or K >= 512 with at least two N tiles of 256.
+// SVB_GEMM_CG=1|2 forces one kernel for A/B testing.
+static int gemm_cg(int N, int K) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("SVB_GEMM_CG");
+        forced = (e && (e[0] == '1' || e[0] == '2')) ? (e[0] - '0') : 0;
+    }
+    if (forced) return forced;
+    return (K >= 1024 || (K >= 512 && N >= 512)) ? 2 : 1;
+}
+
 static int dw_th(int C) { return C >= 1024 ? 4 : 8; }
 
 struct HostWeights {
@@ -280,15 +303,15 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             rebase(d.lnw, base); rebase(d.lnb, base); rebase(d.bias, base);
             uint8_t* w = base + reinterpret_cast<size_t>(d.w);
             d.w = w;
-            if (int rc = make_operand_map(&d.w_map, dtype, d.w, C, 4 * (uint64_t)m->dims[s - 1], gemm_bn(C))) return rc;
+            if (int rc = make_operand_map(&d.w_map, dtype, d.w, C, 4 * (uint64_t)m->dims[s - 1], gemm_bn(C) / gemm_cg(C, 4 * m->dims[s - 1]))) return rc;
         }
         for (auto& bp : m->blocks[s]) {
             rebase(bp.wdw, base); rebase(bp.bdw, base); rebase(bp.lnw, base); rebase(bp.lnb, base);
             rebase(bp.b1, base); rebase(bp.b2, base); rebase(bp.gamma, base);
             bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
             bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
-            if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C))) return rc;
-            if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C))) return rc;
+            if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C) / gemm_cg(4 * C, C))) return rc;
+            if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C) / gemm_cg(C, 4 * C))) return rc;
             const uint64_t dims[2] = {(uint64_t)C, 49};
             const uint64_t strides[1] = {(uint64_t)C * 4};
             const uint32_t box[2] = {64, 49};
@@ -356,6 +379,8 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
         if (s > 0) {
             if (int rc = make_operand_map(&p->a2_map[s], m->dtype, ws + L.a, M, 4 * (uint64_t)m->dims[s - 1], 128)) return rc;
         }
+        if (int rc = make_epilogue_map(&p->ox_map[s], m->dtype, ws + L.x, M, C)) return rc;
+        if (int rc = make_epilogue_map(&p->oh_map[s], m->dtype, ws + L.h, M, 4 * C)) return rc;
         h /= 2;
         w /= 2;
     }
@@ -377,36 +402,55 @@ static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** o
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-template <typename T, int BN, int MODE>
-static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, void* out, const void* resid, const float* bias,
-                         const float* gamma, int M, int N, int K, cudaStream_t st) {
-    using Cfg = GemmCfg<BN>;
-    auto kern = gemm_kernel<T, BN, MODE>;
+template <typename T, int BN, int MODE, int CG>
+static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
+                         const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st) {
+    using Cfg = GemmCfg<BN, CG>;
+    auto kern = gemm_kernel<T, BN, MODE, CG>;
     static bool attr_done = false;
     if (!attr_done) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_done = true;
     }
-    const int tiles = ceil_div(M, 128) * ceil_div(N, BN);
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    kern<<<grid, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(a, w, static_cast<T*>(out), static_cast<const T*>(resid), bias,
-                                                          gamma, M, N, K);
-    SVB_CUDA_OK(cudaGetLastError());
+    const int tiles = ceil_div(M, 128 * CG) * ceil_div(N, BN);
+    const int units = num_sms() / CG;  // CTAs, or CTA pairs
+    const int grid = (tiles < units ? tiles : units) * CG;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K));
     return SVB_OK;
 }
 template <typename T>
-static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, void* out, const void* resid, const float* bias,
-                       const float* gamma, int M, int N, int K, int mode, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
+                       const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st) {
     SVB_REQUIRE(N % 32 == 0 && K % 8 == 0, SVB_ERR_INVALID_ARG, "gemm: N (%d) must be a multiple of 32, K (%d) of 8", N, K);
     const int bn = gemm_bn(N);
-#define SVB_GEMM_CASE(BN_, MODE_)                                                                       \
-    if (bn == BN_ && mode == MODE_) return launch_gemm_t<T, BN_, MODE_>(a, w, out, resid, bias, gamma, M, N, K, st);
-    SVB_GEMM_CASE(256, GEMM_GELU)
-    SVB_GEMM_CASE(128, GEMM_GELU)
-    SVB_GEMM_CASE(256, GEMM_RESID)
-    SVB_GEMM_CASE(128, GEMM_RESID)
-    SVB_GEMM_CASE(256, GEMM_BIAS)
-    SVB_GEMM_CASE(128, GEMM_BIAS)
+    const int cg = gemm_cg(N, K);
+#define SVB_GEMM_CASE(BN_, MODE_, CG_)                                          \
+    if (bn == BN_ && mode == MODE_ && cg == CG_)                                \
+        return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st);
+    SVB_GEMM_CASE(256, GEMM_GELU, 2)
+    SVB_GEMM_CASE(128, GEMM_GELU, 2)
+    SVB_GEMM_CASE(256, GEMM_RESID, 2)
+    SVB_GEMM_CASE(128, GEMM_RESID, 2)
+    SVB_GEMM_CASE(256, GEMM_BIAS, 2)
+    SVB_GEMM_CASE(128, GEMM_BIAS, 2)
+    SVB_GEMM_CASE(256, GEMM_GELU, 1)
+    SVB_GEMM_CASE(128, GEMM_GELU, 1)
+    SVB_GEMM_CASE(256, GEMM_RESID, 1)
+    SVB_GEMM_CASE(128, GEMM_RESID, 1)
+    SVB_GEMM_CASE(256, GEMM_BIAS, 1)
+    SVB_GEMM_CASE(128, GEMM_BIAS, 1)
 #undef SVB_GEMM_CASE
     return set_error(SVB_ERR_INVALID_ARG, "gemm: unsupported mode %d", mode);
 }
@@ -507,8 +551,8 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
     // stem
     {
         const long long tokens = (long long)nb * (H / 4) * (W / 4);
-        long long blocks = ceil_div<long long>(tokens, 8 * 16);
-        if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+        long long blocks = ceil_div<long long>(tokens, 8 * STEM_TPW * 4);
+        if (blocks > (long long)num_sms() * 2) blocks = (long long)num_sms() * 2;
         if (blocks < 1) blocks = 1;
         if (int rc = tm.begin(SVB_KC_STEM)) return rc;
         if (m->dims[0] == 128)
@@ -527,19 +571,22 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
             h /= 2;
             w /= 2;
             const int M2 = nb * h * w;
-            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a2_map[s], m->down[s].w_map, X, nullptr, m->down[s].bias, nullptr, M2, C,
-                                            4 * Cin, GEMM_BIAS, st));
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a2_map[s], m->down[s].w_map, plan->ox_map[s], plan->ox_map[s], m->down[s].bias,
+                                            nullptr, M2, C, 4 * Cin, GEMM_BIAS, st));
         }
         const int M = nb * h * w;
         for (const BlockParams& bp : m->blocks[s]) {
             RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
-            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, Hd, nullptr, bp.b1, nullptr, M, 4 * C, C, GEMM_GELU, st));
-            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, X, X, bp.b2, bp.gamma, M, C, 4 * C, GEMM_RESID, st));
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
+                                            GEMM_GELU, st));
+            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
+                                            GEMM_RESID, st));
         }
     }
     {
         const int C = m->dims[3];
-        const size_t smem = (size_t)(C + m->hid + 8) * 4;
+        const size_t smem = (size_t)(C + m->hid + 8 + 8 * C) * 4;
+        SVB_REQUIRE(smem <= 48 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
         if (int rc = tm.begin(SVB_KC_HEAD)) return rc;
         head_kernel<T><<<nb, 256, smem, st>>>(X, h * w, C, m->hn0w, m->hn0b, m->hn1w, m->hn1b, m->hw1, m->hb1, m->hid, m->hw2,
                                               m->hb2, m->nout, coords);
@@ -612,11 +659,13 @@ extern "C" int svb_gemm(const void* d_a, const void* d_w, void* d_out, const voi
     SVB_REQUIRE(d_a && d_w && d_out && d_bias, SVB_ERR_INVALID_ARG, "gemm: null argument");
     SVB_REQUIRE(mode != GEMM_RESID || (d_resid && d_gamma), SVB_ERR_INVALID_ARG, "gemm: residual mode needs resid and gamma");
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, SVB_ERR_INVALID_ARG, "gemm: bad shape");
-    CUtensorMap a_map, w_map;
+    CUtensorMap a_map, w_map, out_map, resid_map;
     if (int rc = make_operand_map(&a_map, dtype, d_a, M, K, 128)) return rc;
-    if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn(N))) return rc;
-    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, d_out, d_resid, d_bias, d_gamma, M, N, K, mode, st);
-    return launch_gemm<__nv_bfloat16>(a_map, w_map, d_out, d_resid, d_bias, d_gamma, M, N, K, mode, st);
+    if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn(N) / gemm_cg(N, K))) return rc;
+    if (int rc = make_epilogue_map(&out_map, dtype, d_out, M, N)) return rc;
+    if (int rc = make_epilogue_map(&resid_map, dtype, mode == GEMM_RESID ? d_resid : d_out, M, N)) return rc;
+    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
+    return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -625,8 +674,8 @@ template <typename T>
 static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const float* lnw, const float* lnb, void* out,
                       int B, int H, int W, int C0, cudaStream_t st) {
     const long long tokens = (long long)B * (H / 4) * (W / 4);
-    long long blocks = ceil_div<long long>(tokens, 8 * 16);
-    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    long long blocks = ceil_div<long long>(tokens, 8 * STEM_TPW * 4);
+    if (blocks > (long long)num_sms() * 2) blocks = (long long)num_sms() * 2;
     if (blocks < 1) blocks = 1;
     if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
@@ -694,8 +743,9 @@ extern "C" int svb_head(const void* d_x, int B, int tokens, int C, const float* 
                         int NOUT, float* d_coords, int dtype, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (int rc = check_device_sm100()) return rc;
-    SVB_REQUIRE(d_x && d_coords && B > 0 && tokens > 0 && C % 2 == 0, SVB_ERR_INVALID_ARG, "head: bad arguments");
-    const size_t smem = (size_t)(C + HID + 8) * 4;
+    SVB_REQUIRE(d_x && d_coords && B > 0 && tokens > 0 && C % 8 == 0, SVB_ERR_INVALID_ARG, "head: bad arguments (C must be a multiple of 8)");
+    const size_t smem = (size_t)(C + HID + 8 + 8 * C) * 4;
+    SVB_REQUIRE(smem <= 48 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
     if (dtype == SVB_FP16)
         head_kernel<__half><<<B, 256, smem, st>>>(static_cast<const __half*>(d_x), tokens, C, n0w, n0b, n1w, n1b, w1, b1, HID,
                                                   w2, b2, NOUT, d_coords);

@@ -40,63 +40,119 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 // ============================================================================ stem
 // in  u8 [B,H,W] (K1 output, one plane); /255, ImageNet mean/std and the RGB replication of
 // cropping.py:463-472 are folded into wf/bf.  out [B,H/4,W/4,C0].
+// One warp = STEM_TPW tokens per iteration (independent load / FMA / shuffle chains in flight: the
+// kernel is latency-bound otherwise), lane = CPL consecutive output channels as packed fp32 pairs.
+constexpr int STEM_TPW = 4;
+
 template <typename T, int CPL>
-__global__ void __launch_bounds__(256) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
-                                                      const float* __restrict__ bf, const float* __restrict__ lnw,
-                                                      const float* __restrict__ lnb, T* __restrict__ out, int B, int H,
-                                                      int W) {
-    constexpr int C0 = 32 * CPL;
+__global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
+                                                         const float* __restrict__ bf, const float* __restrict__ lnw,
+                                                         const float* __restrict__ lnb, T* __restrict__ out, int B, int H,
+                                                         int W) {
+    static_assert(CPL % 2 == 0, "stem packs channel pairs");
+    constexpr int C0 = 32 * CPL, NP = CPL / 2, TPW = STEM_TPW;
     const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int Ho = H >> 2, Wo = W >> 2;
     const long long tokens = (long long)B * Ho * Wo;
 
-    float w[CPL][16], bias[CPL], g[CPL], be[CPL];
+    uint64_t w2[NP][16], bias2[NP];
+    float g[CPL], be[CPL];
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) {
-        const int c = lane * CPL + j;
+    for (int j = 0; j < NP; ++j) {
+        const int c = lane * CPL + 2 * j;
 #pragma unroll
-        for (int p = 0; p < 16; ++p) w[j][p] = wf[c * 16 + p];
-        bias[j] = bf[c];
-        g[j] = lnw[c];
-        be[j] = lnb[c];
+        for (int p = 0; p < 16; ++p) w2[j][p] = pk2(wf[c * 16 + p], wf[(c + 1) * 16 + p]);
+        bias2[j] = pk2(bf[c], bf[c + 1]);
     }
-    for (long long t = warp; t < tokens; t += nwarps) {
-        const int b = (int)(t / (Ho * Wo));
-        const int rem = (int)(t - (long long)b * Ho * Wo);
-        const int ty = rem / Wo, tx = rem - ty * Wo;
-        const uint8_t* p = in + ((size_t)b * H + (size_t)ty * 4) * W + (size_t)tx * 4;
-        float px[16];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * W));
-            px[r * 4 + 0] = (float)(v & 0xFF);
-            px[r * 4 + 1] = (float)((v >> 8) & 0xFF);
-            px[r * 4 + 2] = (float)((v >> 16) & 0xFF);
-            px[r * 4 + 3] = (float)(v >> 24);
+    for (int j = 0; j < CPL; ++j) { g[j] = lnw[lane * CPL + j]; be[j] = lnb[lane * CPL + j]; }
+
+    auto load_px = [&](long long t0, uint32_t (&px)[TPW][4]) {
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            long long t = t0 + k < tokens ? t0 + k : tokens - 1;  // clamp: stores are masked
+            if (t < 0) t = 0;
+            const int b = (int)(t / (Ho * Wo));
+            const int rem = (int)(t - (long long)b * Ho * Wo);
+            const int ty = rem / Wo, tx = rem - ty * Wo;
+            const uint8_t* p = in + ((size_t)b * H + (size_t)ty * 4) * W + (size_t)tx * 4;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) px[k][r] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * W));
         }
-        float acc[CPL];
-        float s = 0.f;
+    };
+    uint32_t px[TPW][4], px_next[TPW][4];
+    if (warp * TPW < tokens) load_px(warp * TPW, px_next);
+    for (long long t0 = warp * TPW; t0 < tokens; t0 += nwarps * TPW) {
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) {
-            float a = bias[j];
+        for (int k = 0; k < TPW; ++k)
 #pragma unroll
-            for (int q = 0; q < 16; ++q) a = fmaf(px[q], w[j][q], a);
-            acc[j] = a;
-            s += a;
+            for (int r = 0; r < 4; ++r) px[k][r] = px_next[k][r];
+        if (t0 + nwarps * TPW < tokens) load_px(t0 + nwarps * TPW, px_next);  // next iteration's pixels are in flight during this one
+        uint64_t acc[TPW][NP];
+        float s[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) acc[k][j] = bias2[j];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float f = (float)((px[k][q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                const uint64_t f2 = pk2(f, f);
+#pragma unroll
+                for (int j = 0; j < NP; ++j) acc[k][j] = fma2(f2, w2[j][q], acc[k][j]);
+            }
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) { float lo, hi; upk2(acc[k][j], lo, hi); a += lo + hi; }
+            s[k] = a;
         }
-        const float mean = warp_sum(s) * (1.0f / C0);
-        float v2 = 0.f;
 #pragma unroll
-        for (int j = 0; j < CPL; ++j) { const float d = acc[j] - mean; v2 = fmaf(d, d, v2); }
-        const float rstd = 1.0f / sqrtf(warp_sum(v2) * (1.0f / C0) + LN_EPS_BACKBONE);
-        static_assert(CPL % 2 == 0, "stem packs channel pairs");
-        uint32_t* o = reinterpret_cast<uint32_t*>(out + (size_t)t * C0 + lane * CPL);
+        for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int j = 0; j < CPL; j += 2)
-            o[j >> 1] = Cvt<T>::pack2(fmaf((acc[j] - mean) * rstd, g[j], be[j]),
-                                      fmaf((acc[j + 1] - mean) * rstd, g[j + 1], be[j + 1]));
+            for (int k = 0; k < TPW; ++k) s[k] += __shfl_xor_sync(0xffffffffu, s[k], o);
+        }
+        float mean[TPW], v2[TPW];
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            mean[k] = s[k] * (1.0f / C0);
+            float q = 0.f;
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                float lo, hi;
+                upk2(acc[k][j], lo, hi);
+                lo -= mean[k]; hi -= mean[k];
+                q = fmaf(lo, lo, q);
+                q = fmaf(hi, hi, q);
+            }
+            v2[k] = q;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) v2[k] += __shfl_xor_sync(0xffffffffu, v2[k], o);
+        }
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
+            if (t0 + k >= tokens) break;
+            const float rstd = 1.0f / sqrtf(v2[k] * (1.0f / C0) + LN_EPS_BACKBONE);
+            uint32_t o[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                float lo, hi;
+                upk2(acc[k][j], lo, hi);
+                o[j] = Cvt<T>::pack2(fmaf((lo - mean[k]) * rstd, g[2 * j], be[2 * j]),
+                                     fmaf((hi - mean[k]) * rstd, g[2 * j + 1], be[2 * j + 1]));
+            }
+            uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(t0 + k) * C0 + lane * CPL);
+            if (NP == 2) *reinterpret_cast<uint2*>(op) = make_uint2(o[0], o[1]);
+            else if (NP == 4) *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[NP > 2 ? 2 : 0], o[NP > 3 ? 3 : 0]);
+            else {
+#pragma unroll
+                for (int j = 0; j < NP; ++j) op[j] = o[j];
+            }
+        }
     }
 }
 
@@ -229,62 +285,118 @@ __global__ void __launch_bounds__(256) dwconv_ln_kernel(const __grid_constant__ 
 
 // ============================================================================ tcgen05 GEMM
 // D[M,N] = epilogue(A[M,K] * Wt[N,K]^T); A, Wt K-major 16-bit; fp32 accumulation in TMEM.
-// Persistent CTAs (one per SM), 128 x BN tiles, BK = 64 (one 128-byte swizzle atom), warp roles:
-//   warp 0      TMA producer (one elected lane)           smem ring: STAGES x (A 16 KB + B BN*128 B)
-//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane)
-//   warps 2..9  epilogue: tcgen05.ld -> bias / GELU / gamma+residual -> 16-bit global stores
+// Persistent CTAs, BK = 64 (one 128-byte swizzle atom), warp roles:
+//   warp 0      TMA producer (one elected lane)
+//   warp 1      TMEM allocator + tcgen05.mma issuer (one lane; the pair leader only when CG == 2)
+//   warps 2..17 epilogue: tcgen05.ld -> bias / GELU / gamma*+residual -> 16-bit, staged through a
+//               per-warp 32x32 swizzled shared-memory box and written (residual: also read) by TMA,
+//               so global traffic is whole 64-byte row segments instead of 32 scattered rows per store.
 // Two TMEM accumulator stages (2 x BN columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// CG == 2 (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
+// 128 rows of A and HALF of the W tile (BN/2 rows), so the W traffic from L2 per output element is
+// halved; the leader issues tcgen05.mma.cta_group::2 for both and multicasts the commits.
 enum GemmMode { GEMM_GELU = 0, GEMM_RESID = 1, GEMM_BIAS = 2 };
 
-template <int BN>
+template <int BN, int CG>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;
-    static constexpr int STAGES = BN == 256 ? 4 : 6;
+    static constexpr int B_ROWS = BN / CG;             // rows of W this CTA stages
     static constexpr int A_BYTES = BM * BK * 2;
-    static constexpr int B_BYTES = BN * BK * 2;
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 4 (48 KB), 6 (32 KB) or 8 (24 KB)
+    static constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter: the epilogue is latency-bound per warp
+    static constexpr int EPI_BUF_BYTES = 32 * 32 * 2;          // one 32x32 16-bit box per warp
+    static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;
+    static constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS;
     static constexpr int TMEM_COLS = 2 * BN;  // 256 or 512: power of two
-    static constexpr int NUM_THREADS = 320;
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
+    static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 512 + 1024;
+    static_assert(NUM_BARS * 8 + 8 <= 512, "barrier area");
+    static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte (swizzle atom) alignment");
 };
 
 template <typename T> struct UmmaFmt;
 template <> struct UmmaFmt<__nv_bfloat16> { static constexpr uint32_t v = 1; };
 template <> struct UmmaFmt<__half> { static constexpr uint32_t v = 0; };
 
-template <typename T, int BN, int MODE>
-__global__ void __launch_bounds__(320, 1) gemm_kernel(const __grid_constant__ CUtensorMap a_map,
-                                                      const __grid_constant__ CUtensorMap w_map, T* out,
-                                                      const T* resid, const float* __restrict__ bias,
-                                                      const float* __restrict__ gamma, int M, int N, int K) {
-    using Cfg = GemmCfg<BN>;
+// GELU of a packed pair: gelu_fast's erfc fit on FFMA2, arranged as relu(x) - |x| * (erfc(|x|/sqrt2) / 2).
+// No clamp on |x|: the fit's exponent u*p(u) stays negative and decreasing for every u > 0
+// (p(u) < -1.15 on [0, inf)), so large |x| gives exp2(-big) = 0 and the result is relu(x).
+template <typename T>
+__device__ __forceinline__ uint32_t gelu_pack2(uint64_t x) {
+    float x0, x1;
+    upk2(x, x0, x1);
+    const uint64_t u = pk2(fabsf(x0), fabsf(x1));
+    uint64_t r = pk2(-5.20460508e-04f, -5.20460508e-04f);
+    r = fma2(r, u, pk2(7.39751849e-03f, 7.39751849e-03f));
+    r = fma2(r, u, pk2(-5.25612477e-02f, -5.25612477e-02f));
+    r = fma2(r, u, pk2(-4.59254682e-01f, -4.59254682e-01f));
+    r = fma2(r, u, pk2(-1.15109138e+00f, -1.15109138e+00f));
+    r = fma2(r, u, pk2(-1.0f, -1.0f));  // exponent - 1: exp2 then yields erfc/2
+    float r0, r1, e0, e1;
+    upk2(r, r0, r1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(r0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r1));
+    const uint64_t t = mul2(u, pk2(e0, e1));                      // |x| * erfc / 2
+    const uint64_t s = add2(x, u);                                // 2 * relu(x)
+    const uint64_t y = fma2(s, pk2(0.5f, 0.5f), mul2(t, pk2(-1.0f, -1.0f)));
+    float y0, y1;
+    upk2(y, y0, y1);
+    return Cvt<T>::pack2(y0, y1);
+}
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <typename T, int BN, int MODE, int CG>
+__global__ void __launch_bounds__(GemmCfg<BN, CG>::NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
+            const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap resid_map,
+            const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K) {
+    using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (Cfg::A_BYTES + Cfg::B_BYTES));
-    uint64_t* full = bars;                 // [STAGES] TMA -> MMA
-    uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA
-    uint64_t* tfull = bars + 2 * STAGES;   // [2] MMA -> epilogue
-    uint64_t* tempty = tfull + 2;          // [2] epilogue -> MMA
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sEpi + Cfg::EPI_BYTES);
+    uint64_t* full = bars;                 // [STAGES] TMA -> MMA   (the leader's copy is the live one when CG == 2)
+    uint64_t* empty = bars + STAGES;       // [STAGES] MMA -> TMA   (multicast to both CTAs)
+    uint64_t* tfull = bars + 2 * STAGES;   // [2] MMA -> epilogue   (multicast to both CTAs)
+    uint64_t* tempty = tfull + 2;          // [2] epilogue -> MMA   (leader's copy; both CTAs' epilogue warps arrive)
+    uint64_t* rfull = tempty + 2;          // [EPI_WARPS] residual box landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int tiles_n = (N + BN - 1) / BN;
-    const int tiles_m = (M + Cfg::BM - 1) / Cfg::BM;
+    const int tiles_m = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
+    const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&a_map);
         tma_prefetch_desc(&w_map);
+        tma_prefetch_desc(&out_map);
+        if (MODE == GEMM_RESID) tma_prefetch_desc(&resid_map);
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], Cfg::EPI_WARPS * CG); }
+        for (int s = 0; s < Cfg::EPI_WARPS; ++s) mbar_init(&rfull[s], 1);
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc<CG>(tmem_ptr, Cfg::TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -292,27 +404,37 @@ __global__ void __launch_bounds__(320, 1) gemm_kernel(const __grid_constant__ CU
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+                const int row_a = (m_blk * CG + (int)rank) * Cfg::BM;
+                const int row_b = n_blk * BN + (int)rank * Cfg::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], Cfg::A_BYTES + Cfg::B_BYTES);
-                    tma_load_2d(sA + stage * Cfg::A_BYTES, &a_map, &full[stage], kb * Cfg::BK, m_blk * Cfg::BM);
-                    tma_load_2d(sB + stage * Cfg::B_BYTES, &w_map, &full[stage], kb * Cfg::BK, n_blk * BN);
+                    if (CG == 1) {
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_2d(sA + stage * Cfg::A_BYTES, &a_map, &full[stage], kb * Cfg::BK, row_a);
+                        tma_load_2d(sB + stage * Cfg::B_BYTES, &w_map, &full[stage], kb * Cfg::BK, row_b);
+                    } else {
+                        // both CTAs' bytes are counted on the leader's barrier; only the leader arrives
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+                        const uint32_t lbar = mapa_shared(smem_u32(&full[stage]), 0);
+                        tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &a_map, lbar, kb * Cfg::BK, row_a);
+                        tma_load_2d_pair(sB + stage * Cfg::B_BYTES, &w_map, lbar, kb * Cfg::BK, row_b);
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A/B = T, both K-major, M=128, N=BN
+        if (lane == 0 && rank == 0) {
+            // instruction descriptor: D=f32, A/B = T, both K-major, M = 128*CG, N = BN
             constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) |
-                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(Cfg::BM >> 4) << 24);
+                                       ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((Cfg::BM * CG) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
             uint32_t aphase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -323,77 +445,113 @@ __global__ void __launch_bounds__(320, 1) gemm_kernel(const __grid_constant__ CU
                     const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
 #pragma unroll
                     for (int k = 0; k < Cfg::BK / 16; ++k)  // +32 B per UMMA_K inside the swizzle atom
-                        tc_mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit(&empty[stage]);  // frees the smem slot once these MMAs retire
+                        tc_mma_f16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit<CG>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit(&tfull[as]);  // accumulator complete -> epilogue
+                tc_commit<CG>(&tfull[as]);  // accumulator complete -> epilogue (both CTAs)
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
     } else {
+        const int ew = warp - 2;
         const int q = warp & 3;             // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;   // which half of the BN columns
-        constexpr int CH = BN / 2 / 32;     // 32-column chunks per warp
+        const int slice = ew >> 2;          // which quarter of the BN columns
+        constexpr int CW = BN / 4;          // columns per warp: 64 or 32
+        constexpr int CH = CW / 32;         // 32-column chunks per warp
+        uint8_t* ebuf_p = sEpi + ew * Cfg::EPI_BUF_BYTES;
+        const uint32_t ebuf = smem_u32(ebuf_p);
+        uint64_t* rf = rfull + ew;
+        // 64-byte rows, SWIZZLE_64B: 16-byte piece i of row r lives at r*64 + ((i ^ ((r >> 1) & 3)) << 4)
+        const uint32_t row_off = ebuf + (uint32_t)lane * 64u;
+        const uint32_t swz = ((uint32_t)lane >> 1) & 3u;
+        uint32_t rph = 0;
         int as = 0;
         uint32_t aphase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
+            const int row0 = (m_blk * CG + (int)rank) * Cfg::BM + q * 32;
+            const int colw = n_blk * BN + slice * CW;
+            const bool active = colw < N && row0 < M;  // warp-uniform
+            if (MODE == GEMM_RESID && active && lane == 0) {
+                // the first residual box of the tile arrives while the MMAs are still running
+                bulk_wait_read<0>();
+                mbar_expect_tx(rf, Cfg::EPI_BUF_BYTES);
+                tma_load_2d(ebuf_p, &resid_map, rf, colw, row0);
+            }
             mbar_wait(&tfull[as], aphase);
             tc_fence_after();
-            const int row = m_blk * Cfg::BM + q * 32 + lane;
-#pragma unroll 1
+#pragma unroll
             for (int c = 0; c < CH; ++c) {
-                const int col = n_blk * BN + half * (BN / 2) + c * 32;
+                const int col = colw + c * 32;
+                if (!active || col >= N) break;
                 uint32_t r[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + half * (BN / 2) + c * 32), r);
+                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + slice * CW + c * 32), r);
+                if (MODE == GEMM_RESID) {
+                    if (c > 0 && lane == 0) {
+                        bulk_wait_read<0>();
+                        mbar_expect_tx(rf, Cfg::EPI_BUF_BYTES);
+                        tma_load_2d(ebuf_p, &resid_map, rf, col, row0);
+                    }
+                } else {
+                    if (lane == 0) bulk_wait_read<0>();  // the previous store has left the buffer
+                    __syncwarp();
+                }
                 tmem_ld_wait();
-                if (row < M && col < N) {
-                    T* optr = out + (size_t)row * N + col;
-                    uint32_t packed[16];
-                    if (MODE == GEMM_RESID) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(resid + (size_t)row * N + col);
+                if (MODE == GEMM_RESID) {
+                    mbar_wait(rf, rph);
+                    rph ^= 1u;
+                }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint4 rv = rp[i];
-                            packed[4 * i + 0] = rv.x; packed[4 * i + 1] = rv.y;
-                            packed[4 * i + 2] = rv.z; packed[4 * i + 3] = rv.w;
+                for (int i = 0; i < 4; ++i) {
+                    const uint32_t addr = row_off + ((((uint32_t)i) ^ swz) << 4);
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * i);
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * i + 1);
+                    uint64_t v01 = add2(pk2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), pk2(b0.x, b0.y));
+                    uint64_t v23 = add2(pk2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), pk2(b0.z, b0.w));
+                    uint64_t v45 = add2(pk2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), pk2(b1.x, b1.y));
+                    uint64_t v67 = add2(pk2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), pk2(b1.z, b1.w));
+                    uint4 o;
+                    if (MODE == GEMM_GELU) {
+                        o = make_uint4(gelu_pack2<T>(v01), gelu_pack2<T>(v23), gelu_pack2<T>(v45), gelu_pack2<T>(v67));
+                    } else {
+                        if (MODE == GEMM_RESID) {
+                            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i);
+                            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i + 1);
+                            const uint4 rv = lds128(addr);
+                            const float2 x01 = Cvt<T>::unpack2(rv.x), x23 = Cvt<T>::unpack2(rv.y);
+                            const float2 x45 = Cvt<T>::unpack2(rv.z), x67 = Cvt<T>::unpack2(rv.w);
+                            v01 = fma2(pk2(g0.x, g0.y), v01, pk2(x01.x, x01.y));
+                            v23 = fma2(pk2(g0.z, g0.w), v23, pk2(x23.x, x23.y));
+                            v45 = fma2(pk2(g1.x, g1.y), v45, pk2(x45.x, x45.y));
+                            v67 = fma2(pk2(g1.z, g1.w), v67, pk2(x67.x, x67.y));
                         }
+                        float f0, f1, f2, f3, f4, f5, f6, f7;
+                        upk2(v01, f0, f1); upk2(v23, f2, f3); upk2(v45, f4, f5); upk2(v67, f6, f7);
+                        o = make_uint4(Cvt<T>::pack2(f0, f1), Cvt<T>::pack2(f2, f3), Cvt<T>::pack2(f4, f5), Cvt<T>::pack2(f6, f7));
                     }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 bv = __ldg(reinterpret_cast<const float4*>(bias + col) + i);
-                        float v0 = __uint_as_float(r[4 * i + 0]) + bv.x;
-                        float v1 = __uint_as_float(r[4 * i + 1]) + bv.y;
-                        float v2 = __uint_as_float(r[4 * i + 2]) + bv.z;
-                        float v3 = __uint_as_float(r[4 * i + 3]) + bv.w;
-                        if (MODE == GEMM_GELU) {
-                            v0 = gelu_fast(v0); v1 = gelu_fast(v1); v2 = gelu_fast(v2); v3 = gelu_fast(v3);
-                        } else if (MODE == GEMM_RESID) {
-                            const float4 gv = __ldg(reinterpret_cast<const float4*>(gamma + col) + i);
-                            const float2 x01 = Cvt<T>::unpack2(packed[2 * i]);
-                            const float2 x23 = Cvt<T>::unpack2(packed[2 * i + 1]);
-                            v0 = fmaf(gv.x, v0, x01.x); v1 = fmaf(gv.y, v1, x01.y);
-                            v2 = fmaf(gv.z, v2, x23.x); v3 = fmaf(gv.w, v3, x23.y);
-                        }
-                        packed[2 * i] = Cvt<T>::pack2(v0, v1);
-                        packed[2 * i + 1] = Cvt<T>::pack2(v2, v3);
-                    }
-                    uint4* op = reinterpret_cast<uint4*>(optr);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        op[i] = make_uint4(packed[4 * i], packed[4 * i + 1], packed[4 * i + 2], packed[4 * i + 3]);
+                    sts128(addr, o);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&out_map, ebuf_p, col, row0);
+                    bulk_commit();
                 }
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (CG == 1 || rank == 0) mbar_arrive(&tempty[as]);
+                else mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));
+            }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
+        if (lane == 0) bulk_wait_all();  // shared memory must outlive the last TMA stores
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ============================================================================ LayerNorm2d + 2x2/s2 patchify
@@ -469,22 +627,36 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
                                                    const float* __restrict__ w1 /*[HID][C]*/, const float* __restrict__ b1,
                                                    int HID, const float* __restrict__ w2 /*[NOUT][HID]*/,
                                                    const float* __restrict__ b2, int NOUT, float* __restrict__ coords) {
-    extern __shared__ float sm[];
-    float* s_feat = sm;          // [C]
-    float* s_hid = sm + C;       // [HID]
-    float* s_red = s_hid + HID;  // [8]
+    extern __shared__ __align__(16) float sm[];
+    float* s_feat = sm;              // [C]
+    float* s_hid = sm + C;           // [HID]
+    float* s_red = s_hid + HID;      // [8]
+    float* s_part = s_red + 8;       // [8][C] per-warp partial pools
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const T* xb = x + (size_t)b * tokens * C;
-    // global average pool (coalesced: consecutive threads = consecutive channel pairs)
-    for (int c2 = tid; c2 < C / 2; c2 += 256) {
-        float sx = 0.f, sy = 0.f;
-        for (int t = 0; t < tokens; ++t) {
-            const float2 v = Cvt<T>::unpack2(__ldg(reinterpret_cast<const uint32_t*>(xb + (size_t)t * C) + c2));
-            sx += v.x;
-            sy += v.y;
+    // global average pool: warp w sums tokens w, w+8, ...; a lane owns 8 consecutive channels per 256-channel group
+    // (128-bit loads, every load independent); the 8 partial sums meet in shared memory.
+    for (int c0 = 0; c0 < C; c0 += 256) {
+        const int c = c0 + lane * 8;
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (c + 8 <= C) {
+#pragma unroll 4
+            for (int t = wid; t < tokens; t += 8) {
+                const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * C + c));
+                const float2 p0 = Cvt<T>::unpack2(u.x), p1 = Cvt<T>::unpack2(u.y), p2 = Cvt<T>::unpack2(u.z), p3 = Cvt<T>::unpack2(u.w);
+                a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y;
+                a[4] += p2.x; a[5] += p2.y; a[6] += p3.x; a[7] += p3.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_part[wid * C + c + j] = a[j];
         }
-        s_feat[2 * c2] = sx / (float)tokens;
-        s_feat[2 * c2 + 1] = sy / (float)tokens;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += 256) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_part[w * C + c];
+        s_feat[c] = v / (float)tokens;
     }
     __syncthreads();
     // two LayerNorms back to back (backbone.head.norm eps 1e-6, head.0 eps 1e-5)
@@ -501,11 +673,17 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
         for (int c = tid; c < C; c += 256) s_feat[c] = fmaf((s_feat[c] - mean) * rstd, gw[c], gb[c]);
         __syncthreads();
     }
-    // Linear(C, HID) + exact GELU: one warp per output, lanes stride the row
+    // Linear(C, HID) + exact GELU: one warp per output, lanes stride the row in float4
     for (int j = wid; j < HID; j += 8) {
-        const float* wr = w1 + (size_t)j * C;
+        const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * C);
+        const float4* fr = reinterpret_cast<const float4*>(s_feat);
         float s = 0.f;
-        for (int c = lane; c < C; c += 32) s = fmaf(__ldg(wr + c), s_feat[c], s);
+#pragma unroll 4
+        for (int c = lane; c < C / 4; c += 32) {
+            const float4 w = __ldg(wr + c);
+            const float4 f = fr[c];
+            s = fmaf(w.x, f.x, s); s = fmaf(w.y, f.y, s); s = fmaf(w.z, f.z, s); s = fmaf(w.w, f.w, s);
+        }
         s = warp_sum(s);
         if (lane == 0) s_hid[j] = gelu_exact(s + b1[j]);
     }
