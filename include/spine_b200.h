@@ -54,6 +54,9 @@ int svb_version(void);
 const char* svb_last_error(void);
 /* 0 if the current CUDA device is sm_100 (B200), else SVB_ERR_UNSUPPORTED_DEVICE. */
 int svb_device_check(void);
+/* Number of CUDA kernels this library has launched in the process (all streams); reset != 0 zeroes the
+ * counter after reading.  Instrumentation only (bench.py reports it as gpu_launches). */
+long long svb_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------
  * K1 -- fused min-max normalise + antialiased bilinear resize to uint8.

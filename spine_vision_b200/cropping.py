@@ -141,7 +141,7 @@ class LocalizationModel:
     """What ``load_localization_model`` returns: the reference hands back an ``nn.Module`` in eval
     mode; this is its inference-only device twin (``eval()`` / ``to()`` are accepted no-ops)."""
 
-    def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 32):
+    def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 37):
         import os
 
         dtype = dtype or os.environ.get("SPINE_B200_DTYPE", "bf16")
@@ -155,8 +155,8 @@ class LocalizationModel:
     def to(self, *_a, **_k):
         return self
 
-    def predict_u8(self, planes_u8: torch.Tensor, times: dict | None = None) -> torch.Tensor:
-        return self.engine.forward(planes_u8, times)
+    def predict_u8(self, planes_u8: torch.Tensor, times: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+        return self.engine.forward(planes_u8, times, out)
 
 
 def load_localization_model(model_path: Path, variant: str, device: str, dtype: str | None = None) -> LocalizationModel:

@@ -1,6 +1,7 @@
 // svb_common.cu -- host utilities: error string, device check, TMA descriptor encoding.
 #include "svb_common.cuh"
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -21,6 +22,10 @@ int set_error(int code, const char* fmt, ...) {
     return code;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launches_total(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
+
 int check_device_sm100() {
     int dev = 0;
     SVB_CUDA_OK(cudaGetDevice(&dev));
@@ -33,6 +38,7 @@ int check_device_sm100() {
     return SVB_OK;
 }
 
+long long launches_total(bool reset);
 int num_sms() {
     static int cached = 0;
     if (cached) return cached;
@@ -88,4 +94,5 @@ extern "C" {
 int svb_version(void) { return SVB_VERSION; }
 const char* svb_last_error(void) { return svb::last_error_ref().c_str(); }
 int svb_device_check(void) { return svb::check_device_sm100(); }
+long long svb_launch_count(int reset) { return svb::launches_total(reset != 0); }
 }

@@ -32,6 +32,14 @@ int set_error(int code, const char* fmt, ...);
         if (!(cond)) return svb::set_error((code), __VA_ARGS__);                                   \
     } while (0)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void count_launch();
+#define SVB_LAUNCHED()                          \
+    do {                                        \
+        svb::count_launch();                    \
+        SVB_CUDA_OK(cudaGetLastError());        \
+    } while (0)
+
 int check_device_sm100();
 int num_sms();
 

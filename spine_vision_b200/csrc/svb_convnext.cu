@@ -109,7 +109,7 @@ static int gemm_cg(int N, int K) {
     return (K >= 1024 || (K >= 512 && N >= 512)) ? 2 : 1;
 }
 
-static int dw_th(int C) { return C >= 1024 ? 4 : 8; }
+static int dw_th(int C) { return C >= 512 ? 8 : 16; }
 
 struct HostWeights {
     std::map<std::string, const svb_weight_desc*> by_name;
@@ -428,6 +428,7 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K));
+    count_launch();
     return SVB_OK;
 }
 template <typename T>
@@ -465,17 +466,20 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
         attr_done = true;
     }
     const int tx = ceil_div(W, Cfg::TW), ty = ceil_div(H, TH);
-    kern<<<nb * tx * ty, 256, Cfg::SMEM_BYTES, st>>>(x, bp.wdw_map, bp.bdw, bp.lnw, bp.lnb, static_cast<T*>(out), H, W, tx, ty);
-    SVB_CUDA_OK(cudaGetLastError());
+    const int tiles = nb * tx * ty;
+    const int slots = num_sms() * Cfg::CTAS_PER_SM;  // persistent CTAs
+    kern<<<tiles < slots ? tiles : slots, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(x, bp.wdw_map, bp.bdw, bp.lnw, bp.lnb,
+                                                                                   static_cast<T*>(out), H, W, tx, ty, tiles);
+    SVB_LAUNCHED();
     return SVB_OK;
 }
 template <typename T>
 static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out, int C, int nb, int H, int W, cudaStream_t st) {
     switch (C) {
-        case 128: return launch_dwconv_t<T, 128, 8>(x, bp, out, nb, H, W, st);
-        case 256: return launch_dwconv_t<T, 256, 8>(x, bp, out, nb, H, W, st);
+        case 128: return launch_dwconv_t<T, 128, 16>(x, bp, out, nb, H, W, st);
+        case 256: return launch_dwconv_t<T, 256, 16>(x, bp, out, nb, H, W, st);
         case 512: return launch_dwconv_t<T, 512, 8>(x, bp, out, nb, H, W, st);
-        case 1024: return launch_dwconv_t<T, 1024, 4>(x, bp, out, nb, H, W, st);
+        case 1024: return launch_dwconv_t<T, 1024, 8>(x, bp, out, nb, H, W, st);
         case 2048: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: width 2048 (xlarge stage 3) is not built yet");
     }
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: unsupported width %d", C);
@@ -494,7 +498,7 @@ static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int 
         case 1024: ln_patchify_kernel<T, 1024><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         default: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "ln_patchify: unsupported width %d", Cin);
     }
-    SVB_CUDA_OK(cudaGetLastError());
+    SVB_LAUNCHED();
     return SVB_OK;
 }
 
@@ -559,7 +563,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
             stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         else
             stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
         if (int rc = tm.end()) return rc;
     }
     int h = H / 4, w = W / 4;
@@ -590,7 +594,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
         if (int rc = tm.begin(SVB_KC_HEAD)) return rc;
         head_kernel<T><<<nb, 256, smem, st>>>(X, h * w, C, m->hn0w, m->hn0b, m->hn1w, m->hn1b, m->hw1, m->hb1, m->hid, m->hw2,
                                               m->hb2, m->nout, coords);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
         if (int rc = tm.end()) return rc;
     }
 #undef RUN
@@ -680,7 +684,7 @@ static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const
     if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else return set_error(SVB_ERR_UNSUPPORTED_MODEL, "stem: width %d unsupported", C0);
-    SVB_CUDA_OK(cudaGetLastError());
+    SVB_LAUNCHED();
     return SVB_OK;
 }
 
@@ -752,6 +756,6 @@ extern "C" int svb_head(const void* d_x, int B, int tokens, int C, const float* 
     else
         head_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(d_x), tokens, C, n0w, n0b, n1w,
                                                          n1b, w1, b1, HID, w2, b2, NOUT, d_coords);
-    SVB_CUDA_OK(cudaGetLastError());
+    SVB_LAUNCHED();
     return SVB_OK;
 }

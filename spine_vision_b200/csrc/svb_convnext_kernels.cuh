@@ -16,6 +16,9 @@ namespace svb {
 
 constexpr float LN_EPS_BACKBONE = 1e-6f;  // timm ConvNeXt LayerNorm / LayerNorm2d
 constexpr float LN_EPS_HEAD = 1e-5f;      // nn.LayerNorm default (generic.py:344)
+// depthwise conv: the 7 kx steps stay a rolled loop so that each step is one clean run of FFMA2s
+// (operand-reuse friendly) behind its own batch of shared-memory loads
+constexpr int DW_KX_UNROLL = 1;
 
 // --------------------------------------------------------------------------------------------
 // GELU(x) = x * Phi(x) with Phi through erfc(|x|/sqrt2) ~= exp2(poly5(|x|)), |x| clamped at 4*sqrt2.
@@ -42,7 +45,7 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 // cropping.py:463-472 are folded into wf/bf.  out [B,H/4,W/4,C0].
 // One warp = STEM_TPW tokens per iteration (independent load / FMA / shuffle chains in flight: the
 // kernel is latency-bound otherwise), lane = CPL consecutive output channels as packed fp32 pairs.
-constexpr int STEM_TPW = 4;
+constexpr int STEM_TPW = 4;  // the 128-bit pixel-row load below assumes 4
 
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
@@ -69,27 +72,31 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const 
 #pragma unroll
     for (int j = 0; j < CPL; ++j) { g[j] = lnw[lane * CPL + j]; be[j] = lnb[lane * CPL + j]; }
 
-    auto load_px = [&](long long t0, uint32_t (&px)[TPW][4]) {
-#pragma unroll
-        for (int k = 0; k < TPW; ++k) {
-            long long t = t0 + k < tokens ? t0 + k : tokens - 1;  // clamp: stores are masked
-            if (t < 0) t = 0;
-            const int b = (int)(t / (Ho * Wo));
-            const int rem = (int)(t - (long long)b * Ho * Wo);
+    const bool row_quad = (Wo % TPW) == 0;  // the TPW tokens of an iteration are x-adjacent: one 128-bit load per pixel row
+    for (long long t0 = warp * TPW; t0 < tokens; t0 += nwarps * TPW) {
+        uint32_t px[TPW][4];
+        if (row_quad) {
+            const int b = (int)(t0 / (Ho * Wo));
+            const int rem = (int)(t0 - (long long)b * Ho * Wo);
             const int ty = rem / Wo, tx = rem - ty * Wo;
             const uint8_t* p = in + ((size_t)b * H + (size_t)ty * 4) * W + (size_t)tx * 4;
 #pragma unroll
-            for (int r = 0; r < 4; ++r) px[k][r] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * W));
+            for (int r = 0; r < 4; ++r) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p + (size_t)r * W));
+                px[0][r] = v.x; px[1][r] = v.y; px[2][r] = v.z; px[3][r] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                const long long t = t0 + k < tokens ? t0 + k : tokens - 1;  // clamp: the store below is masked
+                const int b = (int)(t / (Ho * Wo));
+                const int rem = (int)(t - (long long)b * Ho * Wo);
+                const int ty = rem / Wo, tx = rem - ty * Wo;
+                const uint8_t* p = in + ((size_t)b * H + (size_t)ty * 4) * W + (size_t)tx * 4;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) px[k][r] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * W));
+            }
         }
-    };
-    uint32_t px[TPW][4], px_next[TPW][4];
-    if (warp * TPW < tokens) load_px(warp * TPW, px_next);
-    for (long long t0 = warp * TPW; t0 < tokens; t0 += nwarps * TPW) {
-#pragma unroll
-        for (int k = 0; k < TPW; ++k)
-#pragma unroll
-            for (int r = 0; r < 4; ++r) px[k][r] = px_next[k][r];
-        if (t0 + nwarps * TPW < tokens) load_px(t0 + nwarps * TPW, px_next);  // next iteration's pixels are in flight during this one
         uint64_t acc[TPW][NP];
         float s[TPW];
 #pragma unroll
@@ -157,130 +164,264 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const 
 }
 
 // ============================================================================ depthwise 7x7 + LayerNorm
-// One CTA = TH x 8 output pixels x all C channels.  The (TH+6) x 14 x 64-channel halo tile of
-// each 64-channel chunk arrives by TMA (4-D tensor map over NHWC, out-of-bounds = zero padding)
-// together with the chunk's [49][64] fp32 taps; 8 warps = 8 pixel columns, lane = channel pair,
-// each thread slides a TH-row window down its column.  Conv results stay on chip in fp32
-// (res[TH*8][C]); LayerNorm over C is a warp-per-pixel shuffle reduction; the 16-bit normalised
-// row is the K-major A operand of the fc1 GEMM.
+// One CTA = TH x 8 output pixels x all C channels; 8 consumer warps (one pixel column each, lane =
+// channel pair) + 1 TMA producer warp.  Per 64-channel chunk the (TH+6) x 14 x 64 halo tile (4-D
+// tensor map over NHWC, out-of-bounds = zero padding) and the chunk's [49][64] fp32 taps arrive in
+// a STAGES-deep mbarrier ring.  Each thread slides a TH-row window down its column with packed
+// FFMA2 (both channels of the pair per instruction; every halo value and tap is read from shared
+// memory once per chunk).  The fp32 conv results of all chunks are parked in TENSOR MEMORY
+// (tcgen05.st, the warp's own 32 lanes x 2*NCH*TH columns) instead of shared memory, so the ring
+// can be deep and two CTAs fit per SM; LayerNorm then reads a pixel's C channels back with one
+// tcgen05.ld per pixel, reduces with warp shuffles and writes the 16-bit K-major fc1 operand.
 template <int C, int TH>
 struct DwCfg {
-    static constexpr int TW = 8, CC = 64, STAGES = 2;
+    static constexpr int TW = 8, CC = 64, NCH = C / CC, NV = 2 * NCH;
     static constexpr int HALO_H = TH + 6, HALO_W = TW + 6;
     static constexpr int HALO_BYTES = HALO_H * HALO_W * CC * 2;
     static constexpr int W_BYTES = 49 * CC * 4;
     static constexpr int STAGE_BYTES = ((HALO_BYTES + W_BYTES + 127) / 128) * 128;
-    static constexpr int RES_BYTES = TH * TW * C * 4;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 64 + 1024;  // + barriers + align slack
+    static constexpr int COLS_PER_WARP = NV * TH;           // fp32 columns of TMEM per warp
+    static constexpr int TMEM_COLS = 2 * COLS_PER_WARP;     // two warps share a lane quarter
+    static constexpr int CTAS_PER_SM = TMEM_COLS <= 256 ? 2 : 1;
+    static constexpr int STAGES_WANT = ((CTAS_PER_SM == 2 ? 110 * 1024 : 216 * 1024) - 2 * C * 4) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_WANT < NCH ? STAGES_WANT : NCH;
+    static constexpr int NUM_THREADS = 32 * (TW + 1);
+    static constexpr int LN_BYTES = 2 * C * 4;             // LayerNorm weight + bias, fp32
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + LN_BYTES + 256 + 1024;  // + barriers + align slack
     static_assert(C % CC == 0, "C must be a multiple of 64");
     static_assert(HALO_BYTES % 128 == 0, "halo stage must keep the tap buffer 128B aligned");
+    static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns: power of two <= 512");
+    static_assert(STAGES >= 1, "at least one stage");
 };
 
+template <int N> struct TmemLd;  // 32 lanes x N consecutive fp32 columns: thread i gets lane (base+i)
+template <> struct TmemLd<4> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t* r = reinterpret_cast<uint32_t*>(v);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<8> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t* r = reinterpret_cast<uint32_t*>(v);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<16> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t* r = reinterpret_cast<uint32_t*>(v);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+template <> struct TmemLd<32> {
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        uint32_t* r = reinterpret_cast<uint32_t*>(v);
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                     : "r"(taddr)
+                     : "memory");
+    }
+};
+
+// thread i of the warp -> TMEM lane (base + i), two consecutive 32-bit columns
+__device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint64_t v) {
+    float lo, hi;
+    upk2(v, lo, hi);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(lo)),
+                 "r"(__float_as_uint(hi))
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <typename T> __device__ __forceinline__ uint64_t unpack2_pk(uint32_t u);
+template <> __device__ __forceinline__ uint64_t unpack2_pk<__nv_bfloat16>(uint32_t u) {
+    return (static_cast<uint64_t>(u & 0xFFFF0000u) << 32) | static_cast<uint64_t>(u << 16);
+}
+template <> __device__ __forceinline__ uint64_t unpack2_pk<__half>(uint32_t u) {
+    const float2 f = Cvt<__half>::unpack2(u);
+    return pk2(f.x, f.y);
+}
+
+// sum of PG=4 per-lane values over the 32 lanes, every lane receiving all 4 totals: recursive halving
+// (10 shuffles) instead of 4 butterflies (20 shuffles).
+__device__ __forceinline__ void warp_sum4(float (&a)[4], int lane) {
+    const bool hi4 = (lane & 16) != 0, hi3 = (lane & 8) != 0;
+    const float t0 = __shfl_xor_sync(0xffffffffu, hi4 ? a[0] : a[2], 16);
+    const float t1 = __shfl_xor_sync(0xffffffffu, hi4 ? a[1] : a[3], 16);
+    const float b0 = (hi4 ? a[2] : a[0]) + t0;  // lanes 0-15: pixel 0 / 1, lanes 16-31: pixel 2 / 3
+    const float b1 = (hi4 ? a[3] : a[1]) + t1;
+    float c = (hi3 ? b1 : b0) + __shfl_xor_sync(0xffffffffu, hi3 ? b0 : b1, 8);
+    c += __shfl_xor_sync(0xffffffffu, c, 4);
+    c += __shfl_xor_sync(0xffffffffu, c, 2);
+    c += __shfl_xor_sync(0xffffffffu, c, 1);
+    // lane group (bit4, bit3) now holds the total of pixel 2*bit4 + bit3
+    a[0] = __shfl_sync(0xffffffffu, c, 0);
+    a[1] = __shfl_sync(0xffffffffu, c, 8);
+    a[2] = __shfl_sync(0xffffffffu, c, 16);
+    a[3] = __shfl_sync(0xffffffffu, c, 24);
+}
+
 template <typename T, int C, int TH>
-__global__ void __launch_bounds__(256) dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map,
-                                                        const __grid_constant__ CUtensorMap w_map,
-                                                        const float* __restrict__ bdw, const float* __restrict__ lnw,
-                                                        const float* __restrict__ lnb, T* __restrict__ out, int H, int W,
-                                                        int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(DwCfg<C, TH>::NUM_THREADS, DwCfg<C, TH>::CTAS_PER_SM)
+dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map,
+                 const float* __restrict__ bdw, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                 T* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int num_tiles) {
     using Cfg = DwCfg<C, TH>;
-    constexpr int TW = Cfg::TW, CC = Cfg::CC, STAGES = Cfg::STAGES, HALO_W = Cfg::HALO_W;
-    constexpr int NCHUNK = C / CC;
+    constexpr int TW = Cfg::TW, CC = Cfg::CC, STAGES = Cfg::STAGES, HALO_W = Cfg::HALO_W, NCH = Cfg::NCH, NV = Cfg::NV;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
     uint8_t* s_stage = smem;
-    float* s_res = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::RES_BYTES);
+    float* s_ln = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);  // [C] weight, [C] bias
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES + Cfg::LN_BYTES);
+    uint64_t* s_empty = s_full + STAGES;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_empty + STAGES);
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    int t = blockIdx.x;
-    const int tx = t % tiles_x; t /= tiles_x;
-    const int ty = t % tiles_y;
-    const int b = t / tiles_y;
-    const int x0 = tx * TW, y0 = ty * TH;
 
     if (tid == 0) {
         tma_prefetch_desc(&x_map);
         tma_prefetch_desc(&w_map);
-        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], TW); }
         mbar_fence_init();
     }
+    if (wid == TW) tmem_alloc<1>(s_tmem, Cfg::TMEM_COLS);
+    for (int c = tid; c < C; c += Cfg::NUM_THREADS) { s_ln[c] = lnw[c]; s_ln[C + c] = lnb[c]; }
+    tc_fence_before();
     __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
 
-    auto issue = [&](int stage, int chunk) {
-        uint8_t* dst = s_stage + stage * Cfg::STAGE_BYTES;
-        mbar_expect_tx(&s_full[stage], Cfg::HALO_BYTES + Cfg::W_BYTES);
-        tma_load_4d(dst, &x_map, &s_full[stage], chunk * CC, x0 - 3, y0 - 3, b);
-        tma_load_2d(dst + Cfg::HALO_BYTES, &w_map, &s_full[stage], chunk * CC, 0);
-    };
-    if (tid == 0) {
-        for (int s = 0; s < STAGES && s < NCHUNK; ++s) issue(s, s);
-    }
-
-    for (int k = 0; k < NCHUNK; ++k) {
-        const int stage = k % STAGES;
-        mbar_wait(&s_full[stage], (k / STAGES) & 1);
-        const uint32_t* halo = reinterpret_cast<const uint32_t*>(s_stage + stage * Cfg::STAGE_BYTES);  // [HALO_H][HALO_W][32] ch pairs
-        const float2* taps = reinterpret_cast<const float2*>(s_stage + stage * Cfg::STAGE_BYTES + Cfg::HALO_BYTES);  // [49][32]
-        const int c0 = k * CC + 2 * lane;
-        const float2 bias = *reinterpret_cast<const float2*>(bdw + c0);
-        float2 acc[TH];
-#pragma unroll
-        for (int i = 0; i < TH; ++i) acc[i] = bias;
-#pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-            float2 col[TH + 6];
-#pragma unroll
-            for (int r = 0; r < TH + 6; ++r) col[r] = Cvt<T>::unpack2(halo[(r * HALO_W + wid + kx) * 32 + lane]);
-#pragma unroll
-            for (int ky = 0; ky < 7; ++ky) {
-                const float2 wv = taps[(ky * 7 + kx) * 32 + lane];
-#pragma unroll
-                for (int i = 0; i < TH; ++i) {
-                    acc[i].x = fmaf(col[i + ky].x, wv.x, acc[i].x);
-                    acc[i].y = fmaf(col[i + ky].y, wv.y, acc[i].y);
+    // persistent CTA: tiles blockIdx.x, +gridDim.x, ...; the stage ring runs on across tiles, so the
+    // producer is already fetching the next tile while the consumers normalise this one
+    if (wid == TW) {
+        // ---- TMA producer
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                int t = tile;
+                const int tx = t % tiles_x; t /= tiles_x;
+                const int ty = t % tiles_y;
+                const int b = t / tiles_y;
+                for (int k = 0; k < NCH; ++k, ++it) {
+                    const int stage = it % STAGES;
+                    if (it >= STAGES) mbar_wait(&s_empty[stage], ((it / STAGES) - 1) & 1);
+                    uint8_t* dst = s_stage + stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&s_full[stage], Cfg::HALO_BYTES + Cfg::W_BYTES);
+                    tma_load_4d(dst, &x_map, &s_full[stage], k * CC, tx * TW - 3, ty * TH - 3, b);
+                    tma_load_2d(dst + Cfg::HALO_BYTES, &w_map, &s_full[stage], k * CC, 0);
                 }
             }
         }
+    } else {
+        // ---- consumers: warp = pixel column x0 + wid, lane = channel pair
+        const uint32_t tcol0 = tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((wid >> 2) * Cfg::COLS_PER_WARP);
+        const uint64_t* s_gw = reinterpret_cast<const uint64_t*>(s_ln) + lane;       // channel pair (2*lane, 2*lane+1) of chunk kk at [kk*32]
+        const uint64_t* s_gb = reinterpret_cast<const uint64_t*>(s_ln + C) + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tx = t % tiles_x; t /= tiles_x;
+            const int ty = t % tiles_y;
+            const int b = t / tiles_y;
+            const int x = tx * TW + wid, y0 = ty * TH;
+            float2 bias_next = __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane));
+            for (int k = 0; k < NCH; ++k, ++it) {
+                const int stage = it % STAGES;
+                const float2 bias = bias_next;  // loaded one chunk ahead: no global-load latency in front of the FMAs
+                if (k + 1 < NCH) bias_next = __ldg(reinterpret_cast<const float2*>(bdw + (k + 1) * CC + 2 * lane));
+                mbar_wait(&s_full[stage], (it / STAGES) & 1);
+                const uint32_t* halo = reinterpret_cast<const uint32_t*>(s_stage + stage * Cfg::STAGE_BYTES) + wid * 32 + lane;  // [HALO_H][HALO_W][32] ch pairs
+                const uint64_t* taps = reinterpret_cast<const uint64_t*>(s_stage + stage * Cfg::STAGE_BYTES + Cfg::HALO_BYTES) + lane;  // [49][32] fp32 pairs
+                uint64_t acc[TH];
 #pragma unroll
-        for (int i = 0; i < TH; ++i) *reinterpret_cast<float2*>(s_res + (size_t)(i * TW + wid) * C + c0) = acc[i];
-        __syncthreads();  // every warp is done with this stage (and res of this chunk is visible)
-        if (tid == 0 && k + STAGES < NCHUNK) issue(stage, k + STAGES);
-    }
+                for (int i = 0; i < TH; ++i) acc[i] = pk2(bias.x, bias.y);
+#pragma unroll DW_KX_UNROLL
+                for (int kx = 0; kx < 7; ++kx) {
+                    uint64_t col[TH + 6], wv[7];
+#pragma unroll
+                    for (int r = 0; r < TH + 6; ++r) col[r] = unpack2_pk<T>(halo[(r * HALO_W + kx) * 32]);
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky) wv[ky] = taps[(ky * 7 + kx) * 32];
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky) {
+#pragma unroll
+                        for (int i = 0; i < TH; ++i) acc[i] = fma2(col[i + ky], wv[ky], acc[i]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp is done with the stage
+                // park the chunk's results: pixel i of the column -> columns [i*NV + 2k, +2)
+#pragma unroll
+                for (int i = 0; i < TH; ++i) tmem_st_x2(tcol0 + (uint32_t)(i * NV + 2 * k), acc[i]);
+            }
+            tmem_st_wait();
 
-    // LayerNorm over C, one warp per pixel
-    constexpr int V4 = C / 128;  // float4 groups per lane
-    for (int p = wid; p < TH * TW; p += 8) {
-        const int oy = p / TW, ox = p - oy * TW;
-        const int y = y0 + oy, x = x0 + ox;
-        if (y >= H || x >= W) continue;  // warp-uniform
-        const float4* rp = reinterpret_cast<const float4*>(s_res + (size_t)p * C);
-        float4 v[V4];
-        float s = 0.f;
+            // ---- LayerNorm over C: one tcgen05.ld per pixel gives the lane its 2 channels of every chunk
+            constexpr int PG = 4;  // pixels in flight
+            static_assert(TH % PG == 0, "TH must be a multiple of 4");
+#pragma unroll 1
+            for (int p0 = 0; p0 < TH; p0 += PG) {
+                float v[PG][NV];
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            v[j] = rp[lane + 32 * j];
-            s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-        }
-        const float mean = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
+                for (int g = 0; g < PG; ++g) TmemLd<NV>::ld(tcol0 + (uint32_t)((p0 + g) * NV), v[g]);
+                tmem_ld_wait();
+                float s[PG], q[PG];
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            const float a = v[j].x - mean, bb = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
-            q += (a * a + bb * bb) + (cc * cc + d * d);
-        }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + LN_EPS_BACKBONE);
-        uint2* op = reinterpret_cast<uint2*>(out + (((size_t)b * H + y) * W + x) * C);
+                for (int g = 0; g < PG; ++g) {
+                    uint64_t a2 = pk2(v[g][0], v[g][1]);
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            const int c4 = lane + 32 * j;
-            const float4 g = __ldg(reinterpret_cast<const float4*>(lnw) + c4);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(lnb) + c4);
-            uint2 o;
-            o.x = Cvt<T>::pack2(fmaf((v[j].x - mean) * rstd, g.x, be.x), fmaf((v[j].y - mean) * rstd, g.y, be.y));
-            o.y = Cvt<T>::pack2(fmaf((v[j].z - mean) * rstd, g.z, be.z), fmaf((v[j].w - mean) * rstd, g.w, be.w));
-            op[c4] = o;
+                    for (int kk = 1; kk < NCH; ++kk) a2 = add2(a2, pk2(v[g][2 * kk], v[g][2 * kk + 1]));
+                    float lo, hi;
+                    upk2(a2, lo, hi);
+                    s[g] = lo + hi;
+                }
+                warp_sum4(s, lane);
+                uint64_t d[PG][NCH];
+#pragma unroll
+                for (int g = 0; g < PG; ++g) {
+                    const float nm = -s[g] * (1.0f / C);
+                    const uint64_t nm2 = pk2(nm, nm);
+                    uint64_t a2 = pk2(0.f, 0.f);
+#pragma unroll
+                    for (int kk = 0; kk < NCH; ++kk) {
+                        d[g][kk] = add2(pk2(v[g][2 * kk], v[g][2 * kk + 1]), nm2);
+                        a2 = fma2(d[g][kk], d[g][kk], a2);
+                    }
+                    float lo, hi;
+                    upk2(a2, lo, hi);
+                    q[g] = lo + hi;
+                }
+                warp_sum4(q, lane);
+#pragma unroll
+                for (int g = 0; g < PG; ++g) {
+                    const int y = y0 + p0 + g;
+                    if (y < H && x < W) {  // warp-uniform
+                        const float rstd = 1.0f / sqrtf(q[g] * (1.0f / C) + LN_EPS_BACKBONE);
+                        const uint64_t r2 = pk2(rstd, rstd);
+                        uint32_t* op = reinterpret_cast<uint32_t*>(out + (((size_t)b * H + y) * W + x) * C) + lane;
+#pragma unroll
+                        for (int kk = 0; kk < NCH; ++kk) {
+                            float lo, hi;
+                            upk2(fma2(mul2(d[g][kk], r2), s_gw[kk * 32], s_gb[kk * 32]), lo, hi);
+                            op[kk * (CC / 2)] = Cvt<T>::pack2(lo, hi);
+                        }
+                    }
+                }
+            }
         }
     }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == TW) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
 }
 
 // ============================================================================ tcgen05 GEMM
@@ -364,7 +505,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
     using Cfg = GemmCfg<BN, CG>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint8_t* sEpi = smem + STAGES * Cfg::STAGE_BYTES;

@@ -307,7 +307,7 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
     {
         dim3 grid(ceil_div(out_w > out_h ? out_w : out_h, 128), 2, B);
         k1_coeff_kernel<<<grid, 128, 0, stream>>>(d_hw, out_h, out_w, L.ksh, L.ksw, keys, hb, hk, vb, vk);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
     }
 
     // rows per CTA: largest power of two whose staging fits ~100 KB (2 CTAs / SM), else smaller
@@ -342,11 +342,11 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int nb = (B - b0) < chunk ? (B - b0) : chunk;
         k1_minmax_kernel<<<dim3(mm_blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
         k1_resize_kernel<<<dim3(ceil_div(out_h, R), nb), 512, smem_bytes, stream>>>(
             d_slices, d_offs, d_hw, b0, out_h, out_w, R, L.ksh, L.ksw, src_cap, rows_cap, keys, hb, hk, vb, vk,
             d_out_u8, d_minmax);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
     }
     return SVB_OK;
 }
@@ -653,11 +653,11 @@ extern "C" int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs
         vk = reinterpret_cast<int*>(ws + L.vk);
         dim3 grid(ceil_div(ow2 > oh2 ? ow2 : oh2, 128), 2);
         k3_coeff_kernel<<<grid, 128, 0, stream>>>(ch, cw, oh2, ow2, L.ksh, L.ksw, hb, hk, vb, vk);
-        SVB_CUDA_OK(cudaGetLastError());
+        SVB_LAUNCHED();
     }
     SVB_CUDA_OK(cudaFuncSetAttribute(k3_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     k3_crop_kernel<<<N, 256, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
                                                    oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk);
-    SVB_CUDA_OK(cudaGetLastError());
+    SVB_LAUNCHED();
     return SVB_OK;
 }

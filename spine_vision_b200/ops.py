@@ -134,7 +134,8 @@ def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | Non
 
 
 def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, delta_px: torch.Tensor, max_box_hw,
-                  crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True):
+                  crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True,
+                  out: torch.Tensor | None = None, out2: torch.Tensor | None = None):
     """K3: one crop per (slice_idx, xy, delta_px) row.  Device mirror of
     ``CropContext.crop`` -> ``crop_region_horizontal`` (cropping.py:316-404) and, for the
     second output, the classifier's ``Resize`` (training/datasets/classification.py:247-278).
@@ -143,12 +144,14 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     dev = pool.data.device
     N = int(xy.shape[0])
     ch, cw = int(crop_size[0]), int(crop_size[1])
-    crops = torch.empty((N, ch, cw), dtype=torch.uint8, device=dev)
+    crops = out if out is not None else torch.empty((N, ch, cw), dtype=torch.uint8, device=dev)
+    assert crops.is_contiguous() and crops.dtype == torch.uint8 and crops.numel() == N * ch * cw
     crops2 = None
     oh2 = ow2 = 0
     if second_size is not None:
         oh2, ow2 = int(second_size[0]), int(second_size[1])
-        crops2 = torch.empty((N, oh2, ow2), dtype=torch.uint8, device=dev)
+        crops2 = out2 if out2 is not None else torch.empty((N, oh2, ow2), dtype=torch.uint8, device=dev)
+        assert crops2.is_contiguous() and crops2.dtype == torch.uint8 and crops2.numel() == N * oh2 * ow2
     geom = torch.empty((N, 8), dtype=torch.int32, device=dev) if return_geom else None
     if N == 0:
         return crops, crops2, geom
@@ -205,12 +208,13 @@ class LocalizationEngine:
         _lib.check(_lib.load().svb_model_cost(self._h, B, H, W, C.byref(fl), C.byref(n)))
         return fl.value, n.value
 
-    def forward(self, u8: torch.Tensor, times: dict | None = None) -> torch.Tensor:
+    def forward(self, u8: torch.Tensor, times: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """uint8 [B,H,W] on the device -> float32 [B, num_levels, 2] in [0,1]."""
         assert u8.is_cuda and u8.dtype == torch.uint8 and u8.dim() == 3 and u8.is_contiguous()
         lib = _lib.load()
         B, H, W = u8.shape
-        coords = torch.empty((B, self.num_levels, self.num_outputs), dtype=torch.float32, device=u8.device)
+        coords = out if out is not None else torch.empty((B, self.num_levels, self.num_outputs), dtype=torch.float32, device=u8.device)
+        assert coords.is_contiguous() and coords.dtype == torch.float32 and coords.numel() == B * self.num_levels * self.num_outputs
         if B == 0:
             return coords
         mb = min(self.micro_batch, B)

@@ -79,6 +79,134 @@ def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop
     return CropBatch(coords, crops, crops2, planes if keep_planes else None, times or {})
 
 
+# ------------------------------------------------------------------------------------------ streamed host path
+class PinnedSeries:
+    """A ragged batch of float32 middle slices staged once in pinned host memory (the layout of
+    ``ops.SlicePool``): what the per-series loop of ``process_spider`` hands over after decoding."""
+
+    def __init__(self, slices):
+        self.host, self.offs, self.shapes = ops.SlicePool.pin(slices)
+        self.offs = list(self.offs)
+        self.ends = [o + (h * w + 3) // 4 * 4 for o, (h, w) in zip(self.offs, self.shapes)]
+
+    @property
+    def n(self) -> int:
+        return len(self.shapes)
+
+    @property
+    def nbytes(self) -> int:
+        return (self.ends[-1] if self.ends else 0) * 4
+
+
+class StreamedLocalizer:
+    """End-to-end driver for host-resident series: the batch is cut into chunks of ``chunk`` series and
+    the host->device copy of chunk i+1 (copy stream, pinned memory) runs under the kernels of chunk i
+    (K1 -> localizer -> K3 on the compute stream); results go back on a third stream.  Same arithmetic
+    as ``localize_and_crop``; only the schedule differs."""
+
+    def __init__(self, model: LocalizationModel | None, device="cuda:0", crop_delta_mm=(55, 15, 17.5, 20), crop_size=(256, 256),
+                 image_size=(512, 512), second_size=(256, 256), chunk: int = 37):
+        self.model, self.device = model, torch.device(device)
+        self.crop_delta_mm, self.crop_size, self.image_size, self.second_size = crop_delta_mm, tuple(crop_size), tuple(image_size), second_size
+        self.chunk = int(chunk)
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
+        self._stage = [None, None]
+        self._out = {}
+
+    def _staging(self, j: int, nelem: int) -> torch.Tensor:
+        buf = self._stage[j]
+        if buf is None or buf.numel() < nelem:
+            buf = torch.empty(nelem, dtype=torch.float32, device=self.device)
+            self._stage[j] = buf
+        return buf
+
+    def _outputs(self, B: int):
+        key = (B, self.crop_size, self.second_size)
+        if self._out.get("key") != key:
+            dev = self.device
+            o = {"key": key,
+                 "coords": torch.empty((B, NUM_LEVELS, 2), dtype=torch.float32, device=dev),
+                 "crops": torch.empty((B, NUM_LEVELS, *self.crop_size), dtype=torch.uint8, device=dev),
+                 "h_coords": torch.empty((B, NUM_LEVELS, 2), dtype=torch.float32).pin_memory(),
+                 "h_crops": torch.empty((B, NUM_LEVELS, *self.crop_size), dtype=torch.uint8).pin_memory()}
+            if self.second_size is not None:
+                o["crops2"] = torch.empty((B, NUM_LEVELS, *self.second_size), dtype=torch.uint8, device=dev)
+                o["h_crops2"] = torch.empty((B, NUM_LEVELS, *self.second_size), dtype=torch.uint8).pin_memory()
+            self._out = o
+        return self._out
+
+    def run(self, series: PinnedSeries, spacings=None):
+        """Returns pinned host tensors ``(coords [B,5,2] f32, crops [B,5,ch,cw] u8, crops2 | None)``; they are
+        complete when this call returns (it synchronises the result stream)."""
+        B, L, dev = series.n, NUM_LEVELS, self.device
+        o = self._outputs(B)
+        if B == 0:
+            return o["h_coords"], o["h_crops"], o.get("h_crops2")
+        compute = torch.cuda.current_stream(dev)
+        if spacings is None:
+            spacings = [(0.3, 0.3)] * B
+        deltas = [mm_to_pixels(self.crop_delta_mm, sp) for sp in spacings]
+        bounds = [(i0, min(i0 + self.chunk, B)) for i0 in range(0, B, self.chunk)]
+        # per-batch index tables: one small pinned upload
+        rel_offs = []
+        for i0, i1 in bounds:
+            rel_offs += [series.offs[i] - series.offs[i0] for i in range(i0, i1)]
+        offs_d = torch.tensor(rel_offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+        hw_d = torch.tensor(series.shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True)
+        delta_d = torch.tensor(deltas, dtype=torch.int32).repeat_interleave(L, dim=0).contiguous().pin_memory().to(dev, non_blocking=True)
+        idx_d = torch.arange(self.chunk, dtype=torch.int32).repeat_interleave(L).contiguous().pin_memory().to(dev, non_blocking=True)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        max_elems = max(series.ends[i1 - 1] - series.offs[i0] for i0, i1 in bounds)
+
+        def upload(c):
+            i0, i1 = bounds[c]
+            j = c & 1
+            lo, hi = series.offs[i0], series.ends[i1 - 1]
+            with torch.cuda.stream(self.copy_stream):
+                if c >= 2:
+                    self.copy_stream.wait_event(done[j])  # chunk c-2 has finished with this staging buffer
+                buf = self._staging(j, max_elems)
+                buf[: hi - lo].copy_(series.host[lo:hi], non_blocking=True)
+                ready[j].record(self.copy_stream)
+
+        self.copy_stream.wait_stream(compute)
+        upload(0)
+        for c, (i0, i1) in enumerate(bounds):
+            j = c & 1
+            if c + 1 < len(bounds):
+                upload(c + 1)
+            compute.wait_event(ready[j])
+            n = i1 - i0
+            shapes = series.shapes[i0:i1]
+            pool = ops.SlicePool(self._stage[j], offs_d[i0:i1], hw_d[i0:i1], list(shapes))
+            coords = o["coords"][i0:i1]
+            if self.model is not None:
+                planes = ops.normalize_resize(pool, self.image_size)
+                self.model.predict_u8(planes, out=coords)
+            else:
+                fb = get_center_fallback_locations()
+                coords.copy_(torch.tensor([fb[i] for i in range(L)], dtype=torch.float32, device=dev).unsqueeze(0).expand(n, L, 2))
+            dl = deltas[i0:i1]
+            mh, mw = pool.max_hw
+            max_box = (min(max(1, max(d[2] + d[3] for d in dl)), mh), min(max(1, max(d[0] + d[1] for d in dl)), mw))
+            ops.crop_resample(pool, idx_d[: n * L], coords.view(n * L, 2), delta_d[i0 * L : i1 * L], max_box, self.crop_size,
+                              self.second_size, out=o["crops"][i0:i1].view(n * L, *self.crop_size),
+                              out2=None if self.second_size is None else o["crops2"][i0:i1].view(n * L, *self.second_size))
+            done[j].record(compute)
+            with torch.cuda.stream(self.d2h_stream):
+                self.d2h_stream.wait_event(done[j])
+                o["h_coords"][i0:i1].copy_(o["coords"][i0:i1], non_blocking=True)
+                o["h_crops"][i0:i1].copy_(o["crops"][i0:i1], non_blocking=True)
+                if self.second_size is not None:
+                    o["h_crops2"][i0:i1].copy_(o["crops2"][i0:i1], non_blocking=True)
+        compute.wait_stream(self.d2h_stream)
+        compute.wait_stream(self.copy_stream)
+        self.d2h_stream.synchronize()  # the host tensors are complete on return
+        return o["h_coords"], o["h_crops"], o.get("h_crops2")
+
+
 # ------------------------------------------------------------------------------------------ multi-GPU
 def shard_series(sizes, world_size: int) -> list[list[int]]:
     """Greedy size-balanced partition of series indices (cost = H'*W' pixels) over ranks.

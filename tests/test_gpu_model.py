@@ -89,3 +89,28 @@ def test_pipeline_end_to_end_vs_oracle():
     c0 = fb.crops.cpu().numpy()
     for lvl, (x, y) in cropping.get_center_fallback_locations().items():
         assert np.array_equal(c0[0, lvl], ref.crop_region_horizontal(slices[0], x, y, (128, 128), dpx))
+
+
+def test_streamed_driver_equals_resident_path():
+    """pipeline.StreamedLocalizer (chunked H2D under compute, D2H on a third stream) is a schedule, not
+    different arithmetic: identical coordinates and crops to localize_and_crop over a resident pool,
+    on a ragged batch with a tail chunk, twice in a row (buffer reuse)."""
+    om = make_model("base", seed=0)
+    shapes = [(30, 640, 650), (31, 512, 700), (32, 900, 512), (33, 1195, 1195), (34, 350, 420), (35, 600, 600), (36, 777, 333)]
+    slices = [synthetic.make_iso_slice(*c) for c in shapes]
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16", micro_batch=3)
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    want = pipeline.localize_and_crop(pool, model, (50, 20, 30, 30), (128, 128), (512, 512), (256, 256))
+    wc, wk, wk2 = want.to_host()
+    series = pipeline.PinnedSeries(slices)
+    streamer = pipeline.StreamedLocalizer(model, dev(), (50, 20, 30, 30), (128, 128), (512, 512), (256, 256), chunk=3)
+    for _ in range(2):
+        gc, gk, gk2 = streamer.run(series)
+        assert np.array_equal(gc.numpy(), wc)
+        assert np.array_equal(gk.numpy(), wk)
+        assert np.array_equal(gk2.numpy(), wk2)
+    # centre-crop fallback (no model, __init__.py:194-197)
+    fb = pipeline.StreamedLocalizer(None, dev(), (50, 20, 30, 30), (128, 128), (512, 512), None, chunk=4)
+    fc, fk, fk2 = fb.run(series)
+    ref_fb = pipeline.localize_and_crop(pool, None, (50, 20, 30, 30), (128, 128), (512, 512), None)
+    assert fk2 is None and np.array_equal(fk.numpy(), ref_fb.crops.cpu().numpy()) and np.allclose(fc.numpy(), ref_fb.coords.cpu().numpy())
