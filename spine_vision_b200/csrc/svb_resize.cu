@@ -158,8 +158,19 @@ __global__ void __launch_bounds__(512) k1_minmax_kernel(const float* __restrict_
     }
 }
 
+// normalize_px with the IEEE division taken only when it can matter.  The reference value is
+// e = fl(fl((x - mn) / rng) * 255) truncated; y = fl((x - mn) * fl(255 / rng)) differs from e by < 5e-5 for
+// 0 <= e <= 255, so trunc(y) == trunc(e) unless y sits within 1e-3 of an integer -- only then (and for
+// NaN / inf, which fail the comparison) the exact sequence runs.  Bit-exact by construction.
+__device__ __forceinline__ uint32_t normalize_px_fast(float x, float mn, float rng, float k) {
+    const float d = __fsub_rn(x, mn);
+    const float y = __fmul_rn(d, k);
+    if (fabsf(y - rintf(y)) > 1e-3f) return static_cast<uint32_t>(__float2int_rz(y)) & 0xFFu;
+    return cast_f32_u8(__fmul_rn(__fdiv_rn(d, rng), 255.0f));
+}
+
 // grid (ceil(out_h / R), nb).  CTA = R output rows of slice b, all out_w columns.
-// smem: [src u8: rows_in_max * w_max + 8][tmp u8: rows_in_max * out_w][hk int: out_w * ksw][hb int: out_w*2]
+// smem: [src u8: rows_in_max * w_max + 8][tmp u8: rows_in_max * out_w][hk int: out_w * ksw][hb int: out_w*2][vk int: R * ksh][vb int: R*2]
 __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
                                                         const int32_t* __restrict__ hw, int b0, int out_h, int out_w,
                                                         int R, int ksh, int ksw, int src_cap, int rows_cap,
@@ -176,8 +187,10 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
 
     uint8_t* s_src = smem;                                   // src_cap bytes (multiple of 16)
     uint8_t* s_tmp = s_src + src_cap;                        // rows_cap * out_w (multiple of 16)
-    int* s_hk = reinterpret_cast<int*>(s_tmp + (size_t)rows_cap * out_w);
+    int* s_hk = reinterpret_cast<int*>(s_tmp + (((size_t)rows_cap * out_w + 15) / 16) * 16);
     int* s_hb = s_hk + out_w * ksw;
+    int* s_vk = s_hb + out_w * 2;
+    int* s_vb = s_vk + R * ksh;
 
     const float mn = key_float(keys[2 * b + 0]);
     const float mx = key_float(keys[2 * b + 1]);
@@ -190,41 +203,78 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
     const int y_last = vb_b[2 * (r1 - 1)] + vb_b[2 * (r1 - 1) + 1];  // bounds are monotone in the row index
     const int rows_in = y_last - y_first;
 
-    // stage the horizontal tables
+    // stage the coefficient tables
     {
         const int* hk_b = hk + (size_t)b * out_w * ksw;
         const int* hb_b = hb + (size_t)b * out_w * 2;
         for (int i = tid; i < out_w * ksw; i += nthr) s_hk[i] = hk_b[i];
         for (int i = tid; i < out_w * 2; i += nthr) s_hb[i] = hb_b[i];
+        for (int i = tid; i < (r1 - r0) * ksh; i += nthr) s_vk[i] = vk_b[(size_t)r0 * ksh + i];
+        for (int i = tid; i < (r1 - r0) * 2; i += nthr) s_vb[i] = vb_b[2 * r0 + i];
     }
 
-    // phase A: contiguous span of rows_in full rows -> normalised u8 in smem (128-bit loads)
+    // phase A: contiguous span of rows_in full rows -> normalised u8 in smem (128-bit loads, 4 in flight per thread)
+    const float* g = slices + offs[b] + (long long)y_first * W;
+    const int mis = (int)(((uintptr_t)g >> 2) & 3);  // element misalignment of the span start
     {
-        const float* g = slices + offs[b] + (long long)y_first * W;
         const long long cnt = (long long)rows_in * W;
-        const int mis = (int)(((uintptr_t)g >> 2) & 3);  // element misalignment of the span start
         const int head = (4 - mis) & 3;
         uint8_t* dst = s_src + mis;  // element i lives at dst[i]; dst + head is 4-byte aligned
         if (tid < head && tid < cnt) dst[tid] = (uint8_t)normalize_px(g[tid], mn, rng);
         const float4* g4 = reinterpret_cast<const float4*>(g + head);
-        const long long n4 = cnt > head ? ((cnt - head) >> 2) : 0;
+        const int n4 = cnt > head ? (int)((cnt - head) >> 2) : 0;
         uint32_t* d4 = reinterpret_cast<uint32_t*>(dst + head);
-        for (long long i = tid; i < n4; i += nthr) {
-            float4 v = __ldg(g4 + i);
-            uint32_t p = normalize_px(v.x, mn, rng) | (normalize_px(v.y, mn, rng) << 8) |
-                         (normalize_px(v.z, mn, rng) << 16) | (normalize_px(v.w, mn, rng) << 24);
-            d4[i] = p;
+        if (rng > 0.0f) {
+            const float k = __fdiv_rn(255.0f, rng);
+            int i = tid;
+            for (; i + 3 * nthr < n4; i += 4 * nthr) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = __ldg(g4 + i + u * nthr);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    d4[i + u * nthr] = normalize_px_fast(v[u].x, mn, rng, k) | (normalize_px_fast(v[u].y, mn, rng, k) << 8) |
+                                       (normalize_px_fast(v[u].z, mn, rng, k) << 16) | (normalize_px_fast(v[u].w, mn, rng, k) << 24);
+            }
+            for (; i < n4; i += nthr) {
+                const float4 v = __ldg(g4 + i);
+                d4[i] = normalize_px_fast(v.x, mn, rng, k) | (normalize_px_fast(v.y, mn, rng, k) << 8) |
+                        (normalize_px_fast(v.z, mn, rng, k) << 16) | (normalize_px_fast(v.w, mn, rng, k) << 24);
+            }
+        } else {  // constant slice: the reference casts the raw values (io/__init__.py:27-30)
+            for (int i = tid; i < n4; i += nthr) {
+                const float4 v = __ldg(g4 + i);
+                d4[i] = cast_f32_u8(v.x) | (cast_f32_u8(v.y) << 8) | (cast_f32_u8(v.z) << 16) | (cast_f32_u8(v.w) << 24);
+            }
         }
-        const long long done = head + (n4 << 2);
+        const long long done = head + ((long long)n4 << 2);
         if (done + tid < cnt) dst[done + tid] = (uint8_t)normalize_px(g[done + tid], mn, rng);
     }
     __syncthreads();
 
-    // phase B: horizontal pass, u8 rounding between passes (ImagingResampleHorizontal_8bpc)
+    // phase B: horizontal pass, u8 rounding between passes (ImagingResampleHorizontal_8bpc).
+    // thread = output column (its coefficients live in registers), loop over the staged rows
     {
-        const uint8_t* src = s_src + (int)((((uintptr_t)(slices + offs[b] + (long long)y_first * W)) >> 2) & 3);
+        const uint8_t* src = s_src + mis;
         if (out_w == W) {
             for (int i = tid; i < rows_in * out_w; i += nthr) s_tmp[i] = src[i];
+        } else if (ksw <= 8) {
+            for (int xx = tid; xx < out_w; xx += nthr) {
+                const int xmin = s_hb[2 * xx], n = s_hb[2 * xx + 1];
+                int kc[8], xo[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    kc[j] = j < n ? s_hk[xx * ksw + j] : 0;
+                    xo[j] = min(xmin + j, W - 1);  // padded taps have a zero coefficient: any valid address will do
+                }
+                for (int row = 0; row < rows_in; ++row) {
+                    const uint8_t* sp = src + (size_t)row * W;
+                    int acc = 1 << (PIL_PRECISION_BITS - 1);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc += (int)sp[xo[j]] * kc[j];
+                    s_tmp[(size_t)row * out_w + xx] = (uint8_t)pil_clip8(acc);
+                }
+            }
         } else {
             for (int i = tid; i < rows_in * out_w; i += nthr) {
                 const int row = i / out_w, xx = i - row * out_w;
@@ -251,12 +301,12 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
             if (out_h == H) {
                 packed = *reinterpret_cast<const uint32_t*>(s_tmp + (size_t)(r - y_first) * out_w + x4);
             } else {
-                const int ymin = vb_b[2 * r] - y_first, n = vb_b[2 * r + 1];
-                const int* kp = vk_b + (size_t)r * ksh;
+                const int ymin = s_vb[2 * rr] - y_first, n = s_vb[2 * rr + 1];
+                const int* kp = s_vk + rr * ksh;
                 int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
                 for (int j = 0; j < n; ++j) {
                     const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp + (size_t)(ymin + j) * out_w + x4);
-                    const int k = __ldg(kp + j);
+                    const int k = kp[j];
                     a0 += (int)(px & 0xFF) * k;
                     a1 += (int)((px >> 8) & 0xFF) * k;
                     a2 += (int)((px >> 16) & 0xFF) * k;
@@ -311,7 +361,6 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
     }
 
     // rows per CTA: largest power of two whose staging fits ~100 KB (2 CTAs / SM), else smaller
-    const size_t table_bytes = (size_t)out_w * L.ksw * 4 + (size_t)out_w * 2 * 4;
     int R = 32;
     size_t smem_bytes = 0;
     int src_cap = 0, rows_cap = 0;
@@ -319,6 +368,7 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
         rows_cap = k1_rows_in(max_h, out_h, R);
         if (rows_cap > max_h) rows_cap = max_h;
         src_cap = (int)align_up((size_t)rows_cap * max_w + 16, 16);
+        const size_t table_bytes = (size_t)out_w * L.ksw * 4 + (size_t)out_w * 2 * 4 + (size_t)R * L.ksh * 4 + (size_t)R * 2 * 4;
         smem_bytes = (size_t)src_cap + align_up((size_t)rows_cap * out_w, 16) + table_bytes;
         const size_t budget = R > 1 ? 100 * 1024 : 227 * 1024;
         if (smem_bytes <= budget || R == 1) break;
@@ -330,19 +380,20 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
     const int rows_cap_al = (int)(align_up((size_t)rows_cap * out_w, 16) / out_w);  // keep s_hk 16B aligned
     (void)rows_cap_al;
 
-    // L2-chunked two-pass: min/max then resize over groups of slices that fit in L2, so the second
-    // read of each slice is an L2 hit and HBM sees the fp32 data once.
+    // Two passes over the batch, each ONE launch (whole waves instead of many 1-wave launches): min/max of
+    // every slice, then normalise + resize.  The second pass re-reads the fp32 data from HBM; it is
+    // instruction-bound (fixed-point taps), so the re-read hides under the arithmetic.
     const size_t slice_bytes = (size_t)max_h * max_w * 4;
-    int chunk = (int)((size_t)64 * 1024 * 1024 / (slice_bytes ? slice_bytes : 1));
-    if (chunk < 1) chunk = 1;
-    if (chunk > 65535) chunk = 65535;
     int mm_blocks = (int)ceil_div<size_t>(slice_bytes, (size_t)512 * 16 * 8);  // ~8 float4 per thread
     if (mm_blocks < 1) mm_blocks = 1;
     if (mm_blocks > 1024) mm_blocks = 1024;
-    for (int b0 = 0; b0 < B; b0 += chunk) {
-        const int nb = (B - b0) < chunk ? (B - b0) : chunk;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
         k1_minmax_kernel<<<dim3(mm_blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys);
         SVB_LAUNCHED();
+    }
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
         k1_resize_kernel<<<dim3(ceil_div(out_h, R), nb), 512, smem_bytes, stream>>>(
             d_slices, d_offs, d_hw, b0, out_h, out_w, R, L.ksh, L.ksw, src_cap, rows_cap, keys, hb, hk, vb, vk,
             d_out_u8, d_minmax);
