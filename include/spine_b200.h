@@ -168,6 +168,10 @@ int svb_stem_ln(const uint8_t* d_in, const float* d_wf, const float* d_bf, const
                 void* d_out, int B, int H, int W, int C0, int dtype, void* stream);
 int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* d_bias, const float* d_lnw,
                   const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream);
+/* Same operator on the tensor cores (shifted-view diagonal tcgen05 MMAs); taps16 = the taps as 16-bit
+ * [49][C] of `dtype`.  Supported for C = 256 / 512 while the halo tile fits in shared memory, else SVB_ERR_UNSUPPORTED_MODEL. */
+int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,
+                     const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream);
 int svb_ln_patchify(const void* d_x, const float* d_lnw, const float* d_lnb, void* d_out, int B, int H, int W,
                     int C, int dtype, void* stream);
 int svb_head(const void* d_x, int B, int tokens, int C, const float* n0w, const float* n0b, const float* n1w,

@@ -45,6 +45,8 @@ for s, (C, hw) in enumerate([(128, 128), (256, 64), (512, 32), (1024, 16)]):
     bias = torch.zeros(C, device=dev)
     lnw, lnb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     timeit(f"dwconv_ln C={C} {hw}x{hw}", lambda: ops.dwconv_ln(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
+    if C == 512:
+        timeit(f"dwconv_ln_tc C={C} {hw}x{hw}", lambda: ops.dwconv_ln_tc(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
     a = x.view(M, C)
     w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dt).to(dev)
     b1 = torch.zeros(4 * C, device=dev)

@@ -24,7 +24,7 @@ EXPORTS = (
     "svb_k3_workspace_bytes", "svb_k3_crop_resample",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
     "svb_model_info", "svb_model_cost", "svb_gemm",
-    "svb_stem_ln", "svb_dwconv_ln", "svb_ln_patchify", "svb_head",
+    "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
 )
 
 
@@ -84,6 +84,8 @@ def load() -> C.CDLL:
     lib.svb_stem_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_dwconv_ln.restype = C.c_int
     lib.svb_dwconv_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_dwconv_ln_tc.restype = C.c_int
+    lib.svb_dwconv_ln_tc.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_ln_patchify.restype = C.c_int
     lib.svb_ln_patchify.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_head.restype = C.c_int

@@ -24,7 +24,8 @@ static const double IMAGENET_STD[3] = {0.229, 0.224, 0.225};   // cropping.py:24
 struct BlockParams {
     float *wdw, *bdw, *lnw, *lnb, *b1, *b2, *gamma;
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
-    CUtensorMap wdw_map, w1_map, w2_map;
+    void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
+    CUtensorMap wdw_map, wdw16_map, w1_map, w2_map;
 };
 struct DownParams {
     float *lnw, *lnb, *bias;
@@ -35,6 +36,8 @@ struct ActPlan {  // tensor maps that depend on the workspace pointer and the mi
     const void* ws = nullptr;
     int nb = 0, H = 0, W = 0;
     CUtensorMap x_map[4];   // 4-D NHWC halo maps per stage
+    CUtensorMap xtc_map[4]; // 4-D NHWC maps of the tensor-core depthwise kernel: box {64, W+6, rows, 1}, 128B swizzle
+    int tc_rows[4] = {0, 0, 0, 0};  // rows per box; 0 = the stage runs the CUDA-core kernel
     CUtensorMap a_map[4];   // [M, C]   fc1 A operand
     CUtensorMap h_map[4];   // [M, 4C]  fc2 A operand
     CUtensorMap a2_map[4];  // [M/4, 4C_prev] downsample A operand (index = destination stage)
@@ -110,6 +113,24 @@ static int gemm_cg(int N, int K) {
 }
 
 static int dw_th(int C) { return C >= 512 ? 8 : 16; }
+// Tensor-core depthwise kernel (shifted-view diagonal MMAs): C = 256 / 512 when one stage pair of halo tiles fits
+// in shared memory.  SVB_DWCONV_TC=0 forces the CUDA-core kernel everywhere (A/B testing).
+static int dw_tc_rows(int C, int W) {
+    // Measured on B200 (profiles/r01_dwconv_tc.txt): correct, but 3x SLOWER than the FP32-pipe kernel -- every tap re-reads
+    // its 128 x 16 operand slice from shared memory (16x redundant MMAs also mean 16x redundant operand traffic), so the
+    // kernel is bound by the shared-memory operand feed, not the tensor pipe.  Kept as tested evidence; off by default.
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SVB_DWCONV_TC");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!enabled || (C != 256 && C != 512)) return 0;
+    const int P = W + 6;
+    const int NR = (2 * P + 132) / P + 6;
+    if (P > 256 || NR > 256) return 0;
+    const int smem = C == 512 ? DwTcCfg<512>::smem_bytes(P, NR) : DwTcCfg<256>::smem_bytes(P, NR);
+    return smem <= 227 * 1024 ? NR : 0;
+}
 
 struct HostWeights {
     std::map<std::string, const svb_weight_desc*> by_name;
@@ -259,6 +280,9 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             for (int c = 0; c < C; ++c)
                 for (int t = 0; t < 49; ++t) taps[(size_t)t * C + c] = cw->data[(size_t)c * 49 + t];
             bp.wdw = static_cast<float*>(slab.put(taps.data(), taps.size() * 4));
+            tmp16.resize((size_t)49 * C);
+            for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(taps[i], dtype);
+            bp.wdw16 = slab.put(tmp16.data(), tmp16.size() * 2);
             PUT_F32(bp.bdw, bn + "conv_dw.bias", C);
             PUT_F32(bp.lnw, bn + "norm.weight", C);
             PUT_F32(bp.lnb, bn + "norm.bias", C);
@@ -310,6 +334,15 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             rebase(bp.b1, base); rebase(bp.b2, base); rebase(bp.gamma, base);
             bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
             bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
+            bp.wdw16 = base + reinterpret_cast<size_t>(bp.wdw16);
+            {
+                const uint64_t dims16[2] = {(uint64_t)C, 49};
+                const uint64_t strides16[1] = {(uint64_t)C * 2};
+                const uint32_t box16[2] = {64, 49};
+                if (int rc = encode_tmap(&bp.wdw16_map, tmap_dtype(dtype), 2, bp.wdw16, dims16, strides16, box16,
+                                         CU_TENSOR_MAP_SWIZZLE_NONE))
+                    return rc;
+            }
             if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C) / gemm_cg(4 * C, C))) return rc;
             if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C) / gemm_cg(C, 4 * C))) return rc;
             const uint64_t dims[2] = {(uint64_t)C, 49};
@@ -372,6 +405,15 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
             const uint32_t box[4] = {64, 14, (uint32_t)(dw_th((int)C) + 6), 1};
             if (int rc = encode_tmap(&p->x_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
                                      CU_TENSOR_MAP_SWIZZLE_NONE))
+                return rc;
+        }
+        p->tc_rows[s] = dw_tc_rows((int)C, w);
+        if (p->tc_rows[s]) {
+            const uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
+            const uint64_t strides[3] = {C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+            const uint32_t box[4] = {64, (uint32_t)(w + 6), (uint32_t)p->tc_rows[s], 1};
+            if (int rc = encode_tmap(&p->xtc_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
+                                     CU_TENSOR_MAP_SWIZZLE_128B))
                 return rc;
         }
         if (int rc = make_operand_map(&p->a_map[s], m->dtype, ws + L.a, M, C, 128)) return rc;
@@ -472,6 +514,31 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
                                                                                    static_cast<T*>(out), H, W, tx, ty, tiles);
     SVB_LAUNCHED();
     return SVB_OK;
+}
+template <typename T, int C>
+static int launch_dwconv_tc_t(const CUtensorMap& xtc, const BlockParams& bp, void* out, int nb, int H, int W, int NR, cudaStream_t st) {
+    using Cfg = DwTcCfg<C>;
+    auto kern = dwconv_ln_tc_kernel<T, C>;
+    const int P = W + 6;
+    const int smem = Cfg::smem_bytes(P, NR);
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_smem = smem;
+    }
+    const int tiles_per_img = ceil_div(H * P, 128);
+    const int tiles = nb * tiles_per_img;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    kern<<<grid, Cfg::NUM_THREADS, smem, st>>>(xtc, bp.wdw16_map, bp.bdw, bp.lnw, bp.lnb, static_cast<T*>(out), H, W, NR,
+                                               Cfg::stage_bytes(P, NR), tiles_per_img, tiles);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+template <typename T>
+static int launch_dwconv_tc(const CUtensorMap& xtc, const BlockParams& bp, void* out, int C, int nb, int H, int W, int NR, cudaStream_t st) {
+    if (C == 512) return launch_dwconv_tc_t<T, 512>(xtc, bp, out, nb, H, W, NR, st);
+    if (C == 256) return launch_dwconv_tc_t<T, 256>(xtc, bp, out, nb, H, W, NR, st);
+    return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv (tensor-core): unsupported width %d", C);
 }
 template <typename T>
 static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out, int C, int nb, int H, int W, cudaStream_t st) {
@@ -580,7 +647,11 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
         }
         const int M = nb * h * w;
         for (const BlockParams& bp : m->blocks[s]) {
-            RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
+            if (plan->tc_rows[s]) {
+                RUN(SVB_KC_DWCONV_LN, launch_dwconv_tc<T>(plan->xtc_map[s], bp, A, C, nb, h, w, plan->tc_rows[s], st));
+            } else {
+                RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
+            }
             RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
                                             GEMM_GELU, st));
             RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
@@ -727,6 +798,39 @@ extern "C" int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* 
     }
     if (dtype == SVB_FP16) return launch_dwconv<__half>(x_map, bp, d_out, C, B, H, W, st);
     return launch_dwconv<__nv_bfloat16>(x_map, bp, d_out, C, B, H, W, st);
+}
+
+extern "C" int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,
+                                const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_taps16 && d_bias && d_lnw && d_lnb && d_out && B > 0 && H > 0 && W > 0, SVB_ERR_INVALID_ARG,
+                "dwconv_ln_tc: bad arguments");
+    const int P = W + 6;
+    const int NR = (C == 256 || C == 512) ? (2 * P + 132) / P + 6 : 0;
+    SVB_REQUIRE(NR > 0 && (C == 512 ? DwTcCfg<512>::smem_bytes(P, NR) : DwTcCfg<256>::smem_bytes(P, NR)) <= 227 * 1024,
+                SVB_ERR_UNSUPPORTED_MODEL, "dwconv_ln_tc: C=%d W=%d is outside the tensor-core kernel's range", C, W);
+    BlockParams bp{};
+    bp.bdw = const_cast<float*>(d_bias);
+    bp.lnw = const_cast<float*>(d_lnw);
+    bp.lnb = const_cast<float*>(d_lnb);
+    {
+        const uint64_t dims[2] = {(uint64_t)C, 49};
+        const uint64_t strides[1] = {(uint64_t)C * 2};
+        const uint32_t box[2] = {64, 49};
+        if (int rc = encode_tmap(&bp.wdw16_map, tmap_dtype(dtype), 2, d_taps16, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return rc;
+    }
+    CUtensorMap x_map;
+    {
+        const uint64_t uC = C;
+        const uint64_t dims[4] = {uC, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {uC * 2, (uint64_t)W * uC * 2, (uint64_t)H * W * uC * 2};
+        const uint32_t box[4] = {64, (uint32_t)(W + 6), (uint32_t)NR, 1};
+        if (int rc = encode_tmap(&x_map, tmap_dtype(dtype), 4, d_x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+    }
+    if (dtype == SVB_FP16) return launch_dwconv_tc<__half>(x_map, bp, d_out, C, B, H, W, NR, st);
+    return launch_dwconv_tc<__nv_bfloat16>(x_map, bp, d_out, C, B, H, W, NR, st);
 }
 
 extern "C" int svb_ln_patchify(const void* d_x, const float* d_lnw, const float* d_lnb, void* d_out, int B, int H, int W,

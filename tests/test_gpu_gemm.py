@@ -99,3 +99,27 @@ def test_stem_patchify_head_vs_torch(dtype):
     want = torch.sigmoid(F.gelu(f @ p[4].t() + p[5]) @ p[6].t() + p[7])
     got = ops.head(xs.to(d), *[t.to(d) for t in p]).cpu()
     assert (got - want).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 32, 32, 512), (3, 40, 32, 256), (1, 37, 21, 512), (2, 15, 23, 256), (5, 16, 16, 512), (37, 32, 32, 512)])
+def test_dwconv_ln_tensor_core_vs_torch(B, H, W, C, dtype):
+    """The tensor-core depthwise kernel (shifted-view diagonal MMAs) against fp32 conv2d + LayerNorm with the taps
+    rounded to the operand dtype (that rounding is the kernel's only arithmetic difference from the CUDA-core one)."""
+    g = torch.Generator().manual_seed(B * 1000 + H + W + C)
+    x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
+    wt = torch.randn(C, 1, 7, 7, generator=g) * 0.1
+    bias = torch.randn(C, generator=g) * 0.1
+    lnw = 1 + 0.2 * torch.randn(C, generator=g)
+    lnb = 0.1 * torch.randn(C, generator=g)
+    wt16 = wt.to(DT[dtype]).float()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt16, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (C,), lnw, lnb, 1e-6)
+    taps = wt.reshape(C, 49).t().contiguous()
+    got = ops.dwconv_ln_tc(x.to(dev()), taps.to(dev()), bias.to(dev()), lnw.to(dev()), lnb.to(dev())).float().cpu()
+    err = (got - want).abs()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int((err > tol).sum()) == 0, f"max err {err.max().item():.4g}"
+    # and it agrees with the CUDA-core kernel to within the tap rounding
+    ref = ops.dwconv_ln(x.to(dev()), taps.to(dev()), bias.to(dev()), lnw.to(dev()), lnb.to(dev())).float().cpu()
+    assert (got - ref).abs().max().item() < (0.05 if dtype == "bf16" else 0.01)
