@@ -155,6 +155,12 @@ int svb_model_cost(const svb_model* m, int B, int H, int W, double* gemm_flops, 
 int svb_gemm(const void* d_a, const void* d_w, void* d_out, const void* d_resid, const float* d_bias,
              const float* d_gamma, int M, int N, int K, int mode, int dtype, void* stream);
 
+/* Standalone fused ConvNeXt MLP (unit tests / ncu): x <- x + gamma * (fc2(GELU(fc1(a) + b1)) + b2) in one kernel, the
+ * hidden activation [M,4C] stays on chip.  a [M,C], w1 [4C,C], w2 [C,4C], x [M,C] (in place), 16-bit of `dtype`;
+ * b1 [4C], b2 [C], gamma [C] fp32.  C = 128 or 256 (Y + two hidden accumulators must fit the 512 TMEM columns). */
+int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
+                  const float* d_gamma, void* d_x, int M, int C, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Standalone layer entries (unit tests / ncu captures of one kernel).  Same kernels the model runs.
  * x/out are NHWC 16-bit of `dtype`.

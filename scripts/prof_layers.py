@@ -58,6 +58,9 @@ for s, (C, hw) in enumerate([(128, 128), (256, 64), (512, 32), (1024, 16)]):
     xo = a.clone()
     timeit(f"fc2+resid M={M} N={C} K={4*C}", lambda: ops.gemm(hd, w2, b2, 1, resid=xo, gamma=gam, out=xo), flops=2.0 * M * 4 * C * C,
            nbytes=M * C * 2 * 6)
+    if C in (128, 256):
+        xf = a.clone()
+        timeit(f"fused MLP M={M} C={C}", lambda: ops.mlp_fused(a, w1, b1, w2, b2, gam, xf), flops=4.0 * M * 4 * C * C, nbytes=M * C * 2 * 3)
     del x, hd, xo
 u8 = torch.randint(0, 256, (NB, 512, 512), generator=g, dtype=torch.uint8).to(dev)
 wf, bf = (torch.randn(128, 16, generator=g) * 0.01).to(dev), torch.zeros(128, device=dev)

@@ -23,7 +23,7 @@ EXPORTS = (
     "svb_k1_workspace_bytes", "svb_k1_normalize_resize",
     "svb_k3_workspace_bytes", "svb_k3_crop_resample",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
-    "svb_model_info", "svb_model_cost", "svb_gemm",
+    "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused",
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
 )
 
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.svb_model_cost.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     lib.svb_gemm.restype = C.c_int
     lib.svb_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.svb_mlp_fused.restype = C.c_int
+    lib.svb_mlp_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.svb_stem_ln.restype = C.c_int
     lib.svb_stem_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_dwconv_ln.restype = C.c_int

@@ -26,6 +26,7 @@ struct BlockParams {
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
     void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
     CUtensorMap wdw_map, wdw16_map, w1_map, w2_map;
+    CUtensorMap w1f_map, w2f_map;  // fused-MLP weight boxes: W1 {64, 32}, W2 {64, C/2} (each CTA of the pair stages half a tile)
 };
 struct DownParams {
     float *lnw, *lnb, *bias;
@@ -113,6 +114,19 @@ static int gemm_cg(int N, int K) {
 }
 
 static int dw_th(int C) { return C >= 512 ? 8 : 16; }
+// fused fc1 -> GELU -> fc2 kernel (hidden activation kept on chip) for the widths whose accumulators fit TMEM:
+// C = 128 / 256 (stages 0-1 of convnext_base).  Correct (12 GPU tests) but on B200 it only TIES the un-fused pair
+// (profiles/r01_mlp_fused.txt: 317-380 us vs 323 us at C=128, 194-228 us vs 197 us at C=256 for 37 images): the GELU
+// epilogue on the FP32/MUFU pipes, not the tensor pipe or HBM, bounds both forms, and the fused form adds a
+// chunk-level MMA <-> epilogue hand-shake.  Off by default; SVB_MLP_FUSED=1 enables it.
+static bool mlp_fused(int C) {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SVB_MLP_FUSED");
+        enabled = (e && e[0] == '1') ? 1 : 0;
+    }
+    return enabled && (C == 128 || C == 256);
+}
 // Tensor-core depthwise kernel (shifted-view diagonal MMAs): C = 256 / 512 when one stage pair of halo tiles fits
 // in shared memory.  SVB_DWCONV_TC=0 forces the CUDA-core kernel everywhere (A/B testing).
 static int dw_tc_rows(int C, int W) {
@@ -345,6 +359,10 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             }
             if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C) / gemm_cg(4 * C, C))) return rc;
             if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C) / gemm_cg(C, 4 * C))) return rc;
+            if (C == 128 || C == 256) {
+                if (int rc = make_operand_map(&bp.w1f_map, dtype, bp.w1, 4 * (uint64_t)C, C, 32)) return rc;
+                if (int rc = make_operand_map(&bp.w2f_map, dtype, bp.w2, C, 4 * (uint64_t)C, C / 2)) return rc;
+            }
             const uint64_t dims[2] = {(uint64_t)C, 49};
             const uint64_t strides[1] = {(uint64_t)C * 4};
             const uint32_t box[2] = {64, 49};
@@ -496,6 +514,41 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     SVB_GEMM_CASE(128, GEMM_BIAS, 1)
 #undef SVB_GEMM_CASE
     return set_error(SVB_ERR_INVALID_ARG, "gemm: unsupported mode %d", mode);
+}
+
+template <typename T, int C>
+static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st) {
+    using Cfg = MlpCfg<C>;
+    auto kern = mlp_fused_kernel<T, C>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done = true;
+    }
+    const int tiles = ceil_div(M, 256);
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles < pairs ? tiles : pairs) * 2);
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, bp.w1f_map, bp.w2f_map, x, (const float*)bp.b1, (const float*)bp.b2,
+                                   (const float*)bp.gamma, M));
+    count_launch();
+    return SVB_OK;
+}
+template <typename T>
+static int launch_mlp_fused(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int C, int M, cudaStream_t st) {
+    if (C == 128) return launch_mlp_fused_t<T, 128>(a, bp, x, M, st);
+    if (C == 256) return launch_mlp_fused_t<T, 256>(a, bp, x, M, st);
+    return set_error(SVB_ERR_UNSUPPORTED_MODEL, "fused MLP: unsupported width %d", C);
 }
 
 template <typename T, int C, int TH>
@@ -652,10 +705,14 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
             } else {
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
             }
-            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
-                                            GEMM_GELU, st));
-            RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
-                                            GEMM_RESID, st));
+            if (mlp_fused(C)) {
+                RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
+            } else {
+                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
+                                                GEMM_GELU, st));
+                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
+                                                GEMM_RESID, st));
+            }
         }
     }
     {
@@ -741,6 +798,25 @@ extern "C" int svb_gemm(const void* d_a, const void* d_w, void* d_out, const voi
     if (int rc = make_epilogue_map(&resid_map, dtype, mode == GEMM_RESID ? d_resid : d_out, M, N)) return rc;
     if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
     return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
+}
+
+extern "C" int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
+                             const float* d_gamma, void* d_x, int M, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_a && d_w1 && d_b1 && d_w2 && d_b2 && d_gamma && d_x && M > 0, SVB_ERR_INVALID_ARG, "mlp_fused: bad arguments");
+    SVB_REQUIRE(C == 128 || C == 256, SVB_ERR_UNSUPPORTED_MODEL, "mlp_fused: width %d (supported: 128, 256)", C);
+    BlockParams bp{};
+    bp.b1 = const_cast<float*>(d_b1);
+    bp.b2 = const_cast<float*>(d_b2);
+    bp.gamma = const_cast<float*>(d_gamma);
+    CUtensorMap a_map, x_map;
+    if (int rc = make_operand_map(&a_map, dtype, d_a, M, C, 128)) return rc;
+    if (int rc = make_operand_map(&bp.w1f_map, dtype, d_w1, 4 * (uint64_t)C, C, 32)) return rc;
+    if (int rc = make_operand_map(&bp.w2f_map, dtype, d_w2, C, 4 * (uint64_t)C, C / 2)) return rc;
+    if (int rc = make_epilogue_map(&x_map, dtype, d_x, M, C)) return rc;
+    if (dtype == SVB_FP16) return launch_mlp_fused<__half>(a_map, bp, x_map, C, M, st);
+    return launch_mlp_fused<__nv_bfloat16>(a_map, bp, x_map, C, M, st);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -695,6 +695,354 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
     if (warp == 1) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ============================================================================ fused ConvNeXt MLP (CTA pair)
+// x <- x + gamma * (fc2(GELU(fc1(a) + b1)) + b2) for one block in ONE kernel: the 4C-wide hidden activation never
+// leaves the SM.  A cluster of two CTAs owns 256 tokens (128 each, cta_group::2); the hidden dimension is walked in
+// chunks of 64:
+//     Hacc[128 tok, 64]   = A[128 tok, C] * W1[chunk]^T            (tcgen05, accumulator in TMEM, NB-fold buffered)
+//     Hs  [128 tok, 64]   = bf16(GELU(Hacc + b1))                   (16 epilogue warps -> swizzled K-major smem operand)
+//     Y   [128 tok, C  ] += Hs * W2[:, chunk]^T                     (tcgen05, accumulator in TMEM for the whole tile)
+// and fc1 of chunks j+1 .. j+NB-1 is issued before fc2 of chunk j, so the GELU of chunk j runs under later MMAs.
+// Both weight matrices stream through a ring of 8/16 KB slots (each CTA stages HALF of every weight tile; the pair's MMA
+// reads both halves), so a weight byte is fetched from L2 once per 256 tokens.  TMEM: Y (C columns) + NB x 64 (Hacc).
+//   warp 0       TMA producer (A tile, weight ring)
+//   warp 1       leader: MMA issuer.  peer: relay -- it waits on the peer's LOCAL "epilogue done" barriers and forwards
+//                ONE cluster-scope arrive to the leader (a release.cluster arrive from each of 16 epilogue warps costs a
+//                cluster fence apiece: 30 % of all stall samples in the first version, profiles/r01_mlp_fused.txt)
+//   warps 2..17  epilogue: GELU chunks, then the residual epilogue of the tile (residual in / result out by TMA)
+template <int C>
+struct MlpCfg {
+    static constexpr int HC = 64;                     // hidden chunk: small, so that many chunks are in flight (the
+                                                      // fc1 -> GELU -> fc2 chain of ONE chunk is ~3 k cycles long)
+    static constexpr int NJ = 4 * C / HC;             // chunks per tile
+    static constexpr int NB = (512 - C) / HC;         // hidden accumulators / smem operand buffers in flight: 6 / 4
+    static constexpr int KB_A = C / 64;               // 64-wide k-blocks of the fc1 reduction
+    static constexpr int A_BYTES = KB_A * 16384;      // this CTA's 128 tokens x C
+    static constexpr int H_BYTES = 16384;             // one hidden chunk: 128 tokens x 64 (one k-block)
+    static constexpr int W1_KB_BYTES = 32 * 128;      // this CTA's 32 of the chunk's 64 W1 rows, one k-block
+    static constexpr int SLOT = KB_A * W1_KB_BYTES;   // = (C/2 rows) x 128 B of W2 as well: 8 KB / 16 KB
+    static constexpr int W_SLOTS = C == 128 ? 8 : 6;
+    static constexpr int EPI_WARPS = 16;
+    static constexpr int CH = C / 4 / 32;             // 32x32 output boxes per epilogue warp
+    static constexpr bool STAGE_IN_H = C == 256;      // C=256: the output boxes are staged inside the (idle) hidden buffers
+    static constexpr int STAGE_BYTES = STAGE_IN_H ? 0 : EPI_WARPS * CH * 2048;
+    static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int NUM_BARS = 2 * W_SLOTS + 2 + 6 * NB + 4 + EPI_WARPS;
+    static constexpr int SMEM_BYTES = A_BYTES + NB * H_BYTES + STAGE_BYTES + W_SLOTS * SLOT + NUM_BARS * 8 + 64 + 1024;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(C == 128 || C == 256, "Y (C columns) + NB 64-column hidden accumulators must fit 512 TMEM columns");
+    static_assert(C + NB * HC <= 512, "TMEM budget");
+    static_assert(SLOT == (C / 2) * 128, "W1 and W2 chunk halves are the same size");
+    static_assert(!STAGE_IN_H || NB * H_BYTES >= EPI_WARPS * CH * 2048, "staging must fit the hidden buffers");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+template <typename T, int C>
+__global__ void __launch_bounds__(MlpCfg<C>::NUM_THREADS, 1)
+mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w1_map,
+                 const __grid_constant__ CUtensorMap w2_map, const __grid_constant__ CUtensorMap x_map,
+                 const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ gamma, int M) {
+    using Cfg = MlpCfg<C>;
+    constexpr int NJ = Cfg::NJ, S = Cfg::W_SLOTS, NB = Cfg::NB, CH = Cfg::CH;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;
+    uint8_t* sH = sA + Cfg::A_BYTES;                   // [NB][2 k-blocks][128 rows x 128 B]
+    uint8_t* sStage = sH + NB * Cfg::H_BYTES;          // per-warp 32x32 output boxes (C=128); C=256 reuses sH
+    uint8_t* sW = sStage + Cfg::STAGE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + S * Cfg::SLOT);
+    uint64_t* wfull = bars;                 // [S]  leader's copy counts both CTAs' bytes
+    uint64_t* wempty = wfull + S;           // [S]  multicast commit
+    uint64_t* afull = wempty + S;           // leader
+    uint64_t* aempty = afull + 1;           // multicast commit
+    uint64_t* hacc_full = aempty + 1;       // [NB] multicast commit: fc1 of a chunk finished
+    uint64_t* hacc_free_l = hacc_full + NB; // [NB] local: this CTA's 16 epilogue warps have read the accumulator
+    uint64_t* hacc_free_p = hacc_free_l + NB;  // [NB] leader: the peer's relay says the same for the peer
+    uint64_t* hs_full_l = hacc_free_p + NB; // [NB] local: this CTA's epilogue warps have written the smem operand
+    uint64_t* hs_full_p = hs_full_l + NB;   // [NB] leader: relay
+    uint64_t* hs_free = hs_full_p + NB;     // [NB] multicast commit: fc2 finished reading the smem operand
+    uint64_t* yfull = hs_free + NB;         // multicast commit
+    uint64_t* yfree_l = yfull + 1;          // local
+    uint64_t* yfree_p = yfree_l + 1;        // leader: relay
+    uint64_t* rfull = yfree_p + 2;          // [EPI_WARPS] residual boxes landed
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rfull + Cfg::EPI_WARPS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int num_tiles = (M + 255) / 256;
+    const int tile0 = (int)blockIdx.x / 2, tile_step = (int)gridDim.x / 2;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&a_map);
+        tma_prefetch_desc(&w1_map);
+        tma_prefetch_desc(&w2_map);
+        tma_prefetch_desc(&x_map);
+        for (int s = 0; s < S; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+        mbar_init(afull, 1);
+        mbar_init(aempty, 1);
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&hacc_full[s], 1);
+            mbar_init(&hacc_free_l[s], Cfg::EPI_WARPS);
+            mbar_init(&hacc_free_p[s], 1);
+            mbar_init(&hs_full_l[s], Cfg::EPI_WARPS);
+            mbar_init(&hs_full_p[s], 1);
+            mbar_init(&hs_free[s], 1);
+        }
+        mbar_init(yfull, 1);
+        mbar_init(yfree_l, Cfg::EPI_WARPS);
+        mbar_init(yfree_p, 1);
+        for (int s = 0; s < Cfg::EPI_WARPS; ++s) mbar_init(&rfull[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<2>(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t tm_y = tmem_base, tm_h = tmem_base + (uint32_t)C;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            int slot = 0;
+            uint32_t wphase = 0, tcount = 0;
+            auto next_slot = [&]() -> uint8_t* {
+                mbar_wait(&wempty[slot], wphase ^ 1);
+                if (rank == 0) mbar_expect_tx(&wfull[slot], 2 * Cfg::SLOT);
+                return sW + slot * Cfg::SLOT;
+            };
+            auto advance = [&]() { if (++slot == S) { slot = 0; wphase ^= 1; } };
+            auto load_w1 = [&](int j) {  // W1 rows of chunk j: this CTA stages 32 of the 64, every k-block
+                uint8_t* dst = next_slot();
+                const uint32_t lb = mapa_shared(smem_u32(&wfull[slot]), 0);
+#pragma unroll
+                for (int kb = 0; kb < Cfg::KB_A; ++kb)
+                    tma_load_2d_pair(dst + kb * Cfg::W1_KB_BYTES, &w1_map, lb, kb * 64, j * 64 + (int)rank * 32);
+                advance();
+            };
+            auto load_w2 = [&](int jj) {  // W2 columns of chunk jj: this CTA stages C/2 of the C output rows
+                uint8_t* dst = next_slot();
+                const uint32_t lb = mapa_shared(smem_u32(&wfull[slot]), 0);
+                tma_load_2d_pair(dst, &w2_map, lb, jj * 64, (int)rank * (C / 2));
+                advance();
+            };
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
+                const int row_a = (tile * 2 + (int)rank) * 128;
+                mbar_wait(aempty, (tcount & 1) ^ 1);
+                if (rank == 0) mbar_expect_tx(afull, 2 * Cfg::A_BYTES);
+                const uint32_t la = mapa_shared(smem_u32(afull), 0);
+#pragma unroll
+                for (int kb = 0; kb < Cfg::KB_A; ++kb) tma_load_2d_pair(sA + kb * 16384, &a_map, la, kb * 64, row_a);
+                // same order as the MMA issuer consumes: fc1 runs NB-1 chunks ahead of fc2
+                for (int j = 0; j < NJ + NB - 1; ++j) {
+                    if (j < NJ) load_w1(j);
+                    if (j >= NB - 1) load_w2(j - (NB - 1));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (pair leader)
+            constexpr uint32_t idesc1 = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(Cfg::HC >> 3) << 17) |
+                                        ((uint32_t)(256 >> 4) << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(C >> 3) << 17) |
+                                        ((uint32_t)(256 >> 4) << 24);
+            int slot = 0;
+            uint32_t wphase = 0, tcount = 0, j1 = 0, j2 = 0;  // j1 / j2: running chunk counters of fc1 / fc2
+            auto wait_slot = [&]() -> uint32_t {
+                mbar_wait(&wfull[slot], wphase);
+                tc_fence_after();
+                return smem_u32(sW + slot * Cfg::SLOT);
+            };
+            auto release_slot = [&]() {
+                tc_commit<2>(&wempty[slot]);
+                if (++slot == S) { slot = 0; wphase ^= 1; }
+            };
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
+                mbar_wait(afull, tcount & 1);
+                tc_fence_after();
+                for (int j = 0; j < NJ + NB - 1; ++j) {
+                    if (j < NJ) {
+                        const uint32_t hb = j1 % NB, par = ((j1 / NB) & 1) ^ 1;
+                        mbar_wait(&hacc_free_l[hb], par);
+                        mbar_wait(&hacc_free_p[hb], par);
+                        tc_fence_after();
+                        const uint32_t d = tm_h + hb * Cfg::HC;
+                        {
+                            const uint32_t wb = wait_slot();
+#pragma unroll
+                            for (int kb = 0; kb < Cfg::KB_A; ++kb) {
+                                const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sA + kb * 16384));
+                                const uint64_t bdesc = make_sw128_kmajor_desc(wb + kb * Cfg::W1_KB_BYTES);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    tc_mma_f16<2>(d, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                            }
+                            release_slot();
+                        }
+                        if (j == NJ - 1) tc_commit<2>(aempty);  // the A tile has been read for the last time
+                        tc_commit<2>(&hacc_full[hb]);
+                        ++j1;
+                    }
+                    if (j >= NB - 1) {
+                        const int jj = j - (NB - 1);
+                        const uint32_t hb = j2 % NB, par = (j2 / NB) & 1;
+                        mbar_wait(&hs_full_l[hb], par);
+                        mbar_wait(&hs_full_p[hb], par);
+                        if (jj == 0) {  // the previous tile's Y has been read out
+                            mbar_wait(yfree_l, (tcount & 1) ^ 1);
+                            mbar_wait(yfree_p, (tcount & 1) ^ 1);
+                        }
+                        tc_fence_after();
+                        const uint32_t hs = smem_u32(sH + hb * Cfg::H_BYTES);
+                        {
+                            const uint32_t wb = wait_slot();
+                            const uint64_t adesc = make_sw128_kmajor_desc(hs);
+                            const uint64_t bdesc = make_sw128_kmajor_desc(wb);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_f16<2>(tm_y, adesc + 2 * k, bdesc + 2 * k, idesc2, (jj > 0 || k > 0) ? 1u : 0u);
+                            release_slot();
+                        }
+                        tc_commit<2>(&hs_free[hb]);
+                        ++j2;
+                    }
+                }
+                tc_commit<2>(yfull);
+            }
+        } else if (lane == 0 && rank == 1) {
+            // -------------------------------------------------------------- relay (peer): local barriers -> one arrive at the leader
+            uint32_t j1 = 0, tcount = 0;
+            for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
+                for (int j = 0; j < NJ; ++j, ++j1) {
+                    const uint32_t hb = j1 % NB, par = (j1 / NB) & 1;
+                    mbar_wait(&hacc_free_l[hb], par);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&hacc_free_p[hb]), 0));
+                    mbar_wait(&hs_full_l[hb], par);
+                    mbar_arrive_cluster(mapa_shared(smem_u32(&hs_full_p[hb]), 0));
+                }
+                mbar_wait(yfree_l, tcount & 1);
+                mbar_arrive_cluster(mapa_shared(smem_u32(yfree_p), 0));
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue warps (both CTAs)
+        const int ew = warp - 2;
+        const int q = warp & 3;          // TMEM lane quarter: tokens q*32 .. +31 of this CTA's 128
+        const int slice = ew >> 2;       // 16 of the chunk's 64 hidden columns / C/4 of the output columns
+        const int r = q * 32 + lane;     // token row inside the CTA tile
+        const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+        uint32_t j1 = 0, tcount = 0, rph = 0;
+        uint8_t* stage_p = (Cfg::STAGE_IN_H ? sH : sStage) + ew * CH * 2048;
+        const uint32_t stage_a = smem_u32(stage_p);
+        constexpr int CW = C / 4;
+        for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
+            const int row0 = (tile * 2 + (int)rank) * 128 + q * 32;
+            if (!Cfg::STAGE_IN_H && row0 < M && lane == 0) {
+                // dedicated staging: the residual boxes of this tile arrive while its chunks are computed
+                mbar_expect_tx(&rfull[ew], CH * 2048);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) tma_load_2d(stage_p + c * 2048, &x_map, &rfull[ew], slice * CW + c * 32, row0);
+            }
+            for (int j = 0; j < NJ; ++j, ++j1) {
+                const uint32_t hb = j1 % NB, u = (j1 / NB) & 1;
+                const int hcol = j * Cfg::HC + slice * 16;
+                float4 bias[4];  // in flight before the accumulator is waited for
+#pragma unroll
+                for (int i = 0; i < 4; ++i) bias[i] = __ldg(reinterpret_cast<const float4*>(b1 + hcol) + i);
+                mbar_wait(&hacc_full[hb], u);
+                tc_fence_after();
+                float v[16];
+                TmemLd<16>::ld(tm_h + lane_sel + hb * Cfg::HC + (uint32_t)(slice * 16), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hacc_free_l[hb]);
+                mbar_wait(&hs_free[hb], u ^ 1);  // fc2 of the chunk that used this operand buffer NB chunks ago is done
+                const uint32_t dst = smem_u32(sH + hb * Cfg::H_BYTES) + (uint32_t)(r * 128);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float4 c0 = bias[2 * i], c1 = bias[2 * i + 1];
+                    const uint64_t v01 = add2(pk2(v[8 * i + 0], v[8 * i + 1]), pk2(c0.x, c0.y));
+                    const uint64_t v23 = add2(pk2(v[8 * i + 2], v[8 * i + 3]), pk2(c0.z, c0.w));
+                    const uint64_t v45 = add2(pk2(v[8 * i + 4], v[8 * i + 5]), pk2(c1.x, c1.y));
+                    const uint64_t v67 = add2(pk2(v[8 * i + 6], v[8 * i + 7]), pk2(c1.z, c1.w));
+                    const uint32_t piece = (uint32_t)(slice * 2 + i);
+                    sts128(dst + ((piece ^ ((uint32_t)r & 7u)) << 4),
+                           make_uint4(gelu_pack2<T>(v01), gelu_pack2<T>(v23), gelu_pack2<T>(v45), gelu_pack2<T>(v67)));
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hs_full_l[hb]);
+            }
+            // ---- tile epilogue: x <- x + gamma * (Y + b2), residual in and result out through per-warp 32x32 boxes
+            const uint32_t swz = ((uint32_t)lane >> 1) & 3u;
+            mbar_wait(yfull, tcount & 1);  // all MMAs of the tile are done: Y is complete and the hidden buffers are idle
+            tc_fence_after();
+            if (Cfg::STAGE_IN_H && row0 < M && lane == 0) {
+                mbar_expect_tx(&rfull[ew], CH * 2048);
+#pragma unroll
+                for (int c = 0; c < CH; ++c) tma_load_2d(stage_p + c * 2048, &x_map, &rfull[ew], slice * CW + c * 32, row0);
+            }
+            if (row0 < M) {
+                mbar_wait(&rfull[ew], rph);
+                rph ^= 1u;
+            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int col = slice * CW + c * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(tm_y + lane_sel + (uint32_t)col, v);
+                tmem_ld_wait();
+                if (c == CH - 1) {  // Y has been read out: the next tile's fc2 may overwrite it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(yfree_l);
+                }
+                if (row0 < M) {
+                    const uint32_t row_off = stage_a + (uint32_t)(c * 2048) + (uint32_t)lane * 64u;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t addr = row_off + ((((uint32_t)i) ^ swz) << 4);
+                        const float4 c0 = __ldg(reinterpret_cast<const float4*>(b2 + col) + 2 * i);
+                        const float4 c1 = __ldg(reinterpret_cast<const float4*>(b2 + col) + 2 * i + 1);
+                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i);
+                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i + 1);
+                        const uint4 rv = lds128(addr);
+                        const float2 x01 = Cvt<T>::unpack2(rv.x), x23 = Cvt<T>::unpack2(rv.y);
+                        const float2 x45 = Cvt<T>::unpack2(rv.z), x67 = Cvt<T>::unpack2(rv.w);
+                        const uint64_t v01 = fma2(pk2(g0.x, g0.y), add2(pk2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1])), pk2(c0.x, c0.y)), pk2(x01.x, x01.y));
+                        const uint64_t v23 = fma2(pk2(g0.z, g0.w), add2(pk2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3])), pk2(c0.z, c0.w)), pk2(x23.x, x23.y));
+                        const uint64_t v45 = fma2(pk2(g1.x, g1.y), add2(pk2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5])), pk2(c1.x, c1.y)), pk2(x45.x, x45.y));
+                        const uint64_t v67 = fma2(pk2(g1.z, g1.w), add2(pk2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7])), pk2(c1.z, c1.w)), pk2(x67.x, x67.y));
+                        float f0, f1, f2, f3, f4, f5, f6, f7;
+                        upk2(v01, f0, f1); upk2(v23, f2, f3); upk2(v45, f4, f5); upk2(v67, f6, f7);
+                        sts128(addr, make_uint4(Cvt<T>::pack2(f0, f1), Cvt<T>::pack2(f2, f3), Cvt<T>::pack2(f4, f5), Cvt<T>::pack2(f6, f7)));
+                    }
+                }
+            }
+            if (row0 < M) {
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) tma_store_2d(&x_map, stage_p + c * 2048, slice * CW + c * 32, row0);
+                    bulk_commit();
+                }
+            }
+            // the staging boxes are re-used (next tile's residual, or -- C=256 -- the hidden buffers themselves): every
+            // warp's stores must have left shared memory first
+            if (lane == 0) bulk_wait_read<0>();
+            if (Cfg::STAGE_IN_H) asm volatile("bar.sync 1, %0;" ::"n"(Cfg::EPI_WARPS * 32) : "memory");
+            else __syncwarp();
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc<2>(tmem_base, Cfg::TMEM_COLS);
+}
+
 // ============================================================================ depthwise 7x7 + LayerNorm on the tensor cores
 // The 49-tap depthwise convolution is run as tcgen05 MMAs over SHIFTED VIEWS of one shared-memory halo tile:
 // the (zero-padded) image rows of a 64-channel chunk sit in shared memory as 128-byte pixel rows (TMA,

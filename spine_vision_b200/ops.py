@@ -245,6 +245,16 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int, resid:
     return out
 
 
+def mlp_fused(a: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, gamma: torch.Tensor,
+              x: torch.Tensor) -> torch.Tensor:
+    """Standalone fused MLP (tests / profiling): ``x += gamma * (gelu(a @ w1.T + b1) @ w2.T + b2)`` in place."""
+    assert a.dtype == w1.dtype == w2.dtype == x.dtype and a.is_contiguous() and x.is_contiguous()
+    M, Cc = a.shape
+    _lib.check(_lib.load().svb_mlp_fused(a.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr(),
+                                         x.data_ptr(), M, Cc, _dt(a), _lib.current_stream()))
+    return x
+
+
 # ------------------------------------------------------------------ standalone layers (tests / ncu)
 def _dt(t: torch.Tensor) -> int:
     assert t.dtype in (torch.bfloat16, torch.float16)

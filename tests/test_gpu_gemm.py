@@ -123,3 +123,27 @@ def test_dwconv_ln_tensor_core_vs_torch(B, H, W, C, dtype):
     # and it agrees with the CUDA-core kernel to within the tap rounding
     ref = ops.dwconv_ln(x.to(dev()), taps.to(dev()), bias.to(dev()), lnw.to(dev()), lnb.to(dev())).float().cpu()
     assert (got - ref).abs().max().item() < (0.05 if dtype == "bf16" else 0.01)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,C", [(256, 128), (1000, 128), (256 * 80 + 37, 128), (512, 256), (256 * 75 + 130, 256), (128, 256)])
+def test_fused_mlp_vs_torch(M, C, dtype):
+    """mlp_fused_kernel (fc1 -> GELU -> fc2 -> gamma, +residual with the hidden activation on chip) against fp32 torch
+    with the hidden activation rounded to the operand dtype (what the un-fused pair stores between its two GEMMs)."""
+    g = torch.Generator().manual_seed(M + C)
+    dt = DT[dtype]
+    a = torch.randn(M, C, generator=g).to(dt)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dt)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dt)
+    b1, b2 = torch.randn(4 * C, generator=g) * 0.2, torch.randn(C, generator=g) * 0.2
+    gamma = torch.rand(C, generator=g) + 0.1
+    x = torch.randn(M, C, generator=g).to(dt)
+    h = F.gelu(a.float() @ w1.float().t() + b1).to(dt).float()
+    want = x.float() + gamma * (h @ w2.float().t() + b2)
+    d = dev()
+    got = ops.mlp_fused(a.to(d), w1.to(d), b1.to(d), w2.to(d), b2.to(d), gamma.to(d), x.to(d).clone()).float().cpu()
+    err = (got - want).abs()
+    # output rounding + the propagated rounding of the hidden operand (one 16-bit ulp of h through a 4C-term dot product)
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0) * 1.5
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{bad} of {err.numel()} beyond tolerance; max err {err.max().item():.4g}"
