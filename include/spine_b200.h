@@ -107,6 +107,17 @@ int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int
                          int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags, void* d_ws,
                          size_t ws_bytes, void* stream);
 
+/* Rotated crop mode (CropContext mode="rotated": crop_region_rotated, cropping.py:258-313): same as above, but the box is
+ * cut from cv2.warpAffine(image, R, INTER_LINEAR, BORDER_REPLICATE) about the disc centre, evaluated on the fly.
+ *  d_inv_affine : float64 [N,6] -- the INVERSE of cv2.getRotationMatrix2D((cx,cy), angle, 1.0) per crop, row-major 2x3,
+ *                 computed on the host exactly as cv::warpAffine inverts it (spine_vision_b200.cropping.inverse_rotation);
+ *                 NULL = horizontal mode.  Slices are taken as float32 (integer-typed sources are converted first). */
+int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                 const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
+                                 const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
+                                 uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
+                                 void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2 -- CoordinateRegressor forward (ConvNeXt backbone + MLP head + sigmoid).
  * Replaces model(tensor) in predict_ivd_locations (cropping.py:474-475) =

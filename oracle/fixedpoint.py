@@ -226,3 +226,121 @@ def crop_region_horizontal(image: np.ndarray, x: float, y: float, crop_size, del
     x1, x2, y1, y2 = crop_box(h, w, x, y, delta_px)
     crop = image[y1:y2, x1:x2]
     return resize_with_padding(normalize_to_uint8(crop), crop_size)
+
+
+# --------------------------------------------------------------------------- OpenCV warpAffine (rotated crop mode)
+CV_AB_BITS = 10  # imgwarp.cpp: AB_BITS = MAX(10, INTER_BITS)
+CV_INTER_BITS = 5  # 1/32-pixel source coordinates
+CV_INTER_TAB = 1 << CV_INTER_BITS
+
+
+def rotation_matrix_2d(center, angle_deg: float, scale: float = 1.0) -> np.ndarray:
+    """``cv2.getRotationMatrix2D`` (imgwarp.cpp): double arithmetic, angle in degrees."""
+    a = angle_deg * (math.pi / 180.0)  # OpenCV: angle *= CV_PI/180 (one multiply by the constant)
+    alpha = math.cos(a) * scale
+    beta = math.sin(a) * scale
+    cx, cy = float(center[0]), float(center[1])
+    return np.array([[alpha, beta, (1 - alpha) * cx - beta * cy], [-beta, alpha, beta * cx + (1 - alpha) * cy]], dtype=np.float64)
+
+
+def invert_affine(m: np.ndarray) -> np.ndarray:
+    """The in-place inversion ``cv::warpAffine`` applies to a forward map (no WARP_INVERSE_MAP), same op order."""
+    M = [float(v) for v in np.asarray(m, dtype=np.float64).ravel()]
+    D = M[0] * M[4] - M[1] * M[3]
+    D = 1.0 / D if D != 0 else 0.0
+    A11, A22 = M[4] * D, M[0] * D
+    M[0] = A11
+    M[1] *= -D
+    M[3] *= -D
+    M[4] = A22
+    b1 = -M[0] * M[2] - M[1] * M[5]
+    b2 = -M[3] * M[2] - M[4] * M[5]
+    M[2], M[5] = b1, b2
+    return np.array(M, dtype=np.float64).reshape(2, 3)
+
+
+def _cv_round(v: np.ndarray) -> np.ndarray:
+    """saturate_cast<int>(double) = cvRound: round half to even, saturating."""
+    return np.clip(np.rint(v), -2147483648, 2147483647).astype(np.int64)
+
+
+def warp_affine_coords(inv: np.ndarray, xs: np.ndarray, ys: np.ndarray):
+    """Source pixel (sx, sy) and 5-bit fractions (fx, fy) OpenCV uses for destination pixels (xs, ys):
+    fixed-point AB_SCALE = 1024 coordinates rounded to 1/32 px (WarpAffineInvoker)."""
+    AB = float(1 << CV_AB_BITS)
+    rd = (1 << CV_AB_BITS) // CV_INTER_TAB // 2  # round_delta for INTER_LINEAR = 16
+    adelta = _cv_round(inv[0, 0] * xs.astype(np.float64) * AB)
+    bdelta = _cv_round(inv[1, 0] * xs.astype(np.float64) * AB)
+    X0 = _cv_round((inv[0, 1] * ys.astype(np.float64) + inv[0, 2]) * AB) + rd
+    Y0 = _cv_round((inv[1, 1] * ys.astype(np.float64) + inv[1, 2]) * AB) + rd
+    X = (X0 + adelta) >> (CV_AB_BITS - CV_INTER_BITS)
+    Y = (Y0 + bdelta) >> (CV_AB_BITS - CV_INTER_BITS)
+    # saturate_cast<short> of the integer part
+    sx = np.clip(X >> CV_INTER_BITS, -32768, 32767)
+    sy = np.clip(Y >> CV_INTER_BITS, -32768, 32767)
+    return sx, sy, X & (CV_INTER_TAB - 1), Y & (CV_INTER_TAB - 1)
+
+
+def warp_affine_f32(img: np.ndarray, m: np.ndarray, region=None) -> np.ndarray:
+    """``cv2.warpAffine(img, m, (w, h), flags=INTER_LINEAR, borderMode=BORDER_REPLICATE)`` for a float32 image
+    (the call at ``cropping.py:292-301``).  ``region=(x1, x2, y1, y2)`` evaluates only that window of the output.
+    remapBilinear<Cast<float,float>, RemapNoVec, float>: 32x32 table of exact bilinear weights, four taps
+    summed left to right in float32, replicated border."""
+    a = np.asarray(img, dtype=np.float32)
+    h, w = a.shape
+    inv = invert_affine(m)
+    x1, x2, y1, y2 = region if region is not None else (0, w, 0, h)
+    xs = np.arange(x1, x2, dtype=np.int64)[None, :]
+    ys = np.arange(y1, y2, dtype=np.int64)[:, None]
+    sx, sy, fx, fy = warp_affine_coords(inv, xs, ys)
+    sx, sy, fx, fy = np.broadcast_arrays(sx, sy, fx, fy)
+    x0, x1c = np.clip(sx, 0, w - 1), np.clip(sx + 1, 0, w - 1)
+    y0, y1c = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+    one = np.float32(1.0)
+    s = np.float32(1.0 / CV_INTER_TAB)
+    vx1 = fx.astype(np.float32) * s
+    vy1 = fy.astype(np.float32) * s
+    vx0, vy0 = one - vx1, one - vy1
+    w0, w1, w2, w3 = vy0 * vx0, vy0 * vx1, vy1 * vx0, vy1 * vx1
+    return ((a[y0, x0] * w0 + a[y0, x1c] * w1) + a[y1c, x0] * w2) + a[y1c, x1c] * w3
+
+
+def rotation_angles(ivd_locations: dict, image_shape, last_disc_angle_boost: float = 1.0) -> dict:
+    """``get_rotation_angles`` (cropping.py:172-255): tangent of the disc chain by finite differences, the last
+    point from a 3-point quadratic fit; same NumPy calls, same Python float arithmetic."""
+    if len(ivd_locations) < 2:
+        return {level: 0.0 for level in ivd_locations}
+    h, w = image_shape
+    pts = sorted(((lvl, nx * w, ny * h) for lvl, (nx, ny) in ivd_locations.items()), key=lambda p: p[2])
+    n = len(pts)
+    out = {}
+    for i, (lvl, px, py) in enumerate(pts):
+        if i == 0:
+            dx, dy = pts[1][1] - px, pts[1][2] - py
+            dxdy = dx / dy if dy != 0 else 0.0
+        elif i == n - 1:
+            if n >= 3:
+                last = pts[-3:]
+                a, b, _ = np.polyfit(np.array([p[2] for p in last]), np.array([p[1] for p in last]), deg=2)
+                dxdy = 2 * a * py + b
+            else:
+                dx, dy = px - pts[i - 1][1], py - pts[i - 1][2]
+                dxdy = dx / dy if dy != 0 else 0.0
+        else:
+            dx, dy = pts[i + 1][1] - pts[i - 1][1], pts[i + 1][2] - pts[i - 1][2]
+            dxdy = dx / dy if dy != 0 else 0.0
+        ang = float(np.degrees(np.arctan(dxdy)))
+        if i == n - 1:
+            ang *= last_disc_angle_boost
+        out[lvl] = -ang
+    return out
+
+
+def crop_region_rotated(image: np.ndarray, x: float, y: float, crop_size, delta_px, angle_deg: float) -> np.ndarray:
+    """cropping.py:258-313 for float32 slices: rotate about the disc centre, cut the box, per-crop min-max, letterbox."""
+    a = np.asarray(image, dtype=np.float32)
+    h, w = a.shape
+    cx, cy = int(x * w), int(y * h)
+    x1, x2, y1, y2 = crop_box(h, w, x, y, delta_px)
+    rot = warp_affine_f32(a, rotation_matrix_2d((cx, cy), angle_deg), (x1, x2, y1, y2))
+    return resize_with_padding(normalize_to_uint8(rot), crop_size)

@@ -33,8 +33,46 @@ CROP_DELTAS_MM = [(50, 20, 30, 30), (55, 15, 17.5, 20)]
 MODEL_SLICES = [(20, 1195, 1195), (21, 640, 650)]
 
 
+def golden_rotated(ref) -> None:
+    """Rotated crop mode (cropping.py:172-313) through the reference's own CropContext / get_rotation_angles,
+    plus the notebook's recorded angles (notebooks/compare_crop_modes.ipynb:87-161)."""
+    out = {}
+    for seed, h, w in CROP_SERIES:
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = synthetic.make_coords(2, seed=100 + seed, border_frac=0.3, hw=(h, w))
+        xy[1, 0] = (0.02, 0.03)      # corner: replicated border inside the rotated box
+        xy[1, 4] = (0.97, 0.985)
+        out[f"xy_{seed}_{h}_{w}"] = xy
+        for di, dmm in enumerate(CROP_DELTAS_MM):
+            dpx = ref.mm_to_pixels(dmm, (0.3, 0.3))
+            for boost in (1.0, 2.0):
+                res = np.zeros((2, 5, 128, 128), dtype=np.uint8)
+                ang = np.zeros((2, 5), dtype=np.float64)
+                for s in range(2):
+                    locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                    ctx = ref.CropContext(image=img, ivd_locations=locs, crop_size=(128, 128), crop_delta_px=dpx, mode="rotated",
+                                          last_disc_angle_boost=boost)
+                    for i in range(5):
+                        res[s, i] = ctx.crop(i)
+                        ang[s, i] = ctx.rotation_angles[i]
+                out[f"crops_{seed}_{h}_{w}_d{di}_b{int(boost)}"] = res
+                out[f"angles_{seed}_{h}_{w}_d{di}_b{int(boost)}"] = ang
+    # the notebook's printed coordinates (4 dp) and angles for a 1040x1040 slice, boost 2
+    nb_locs = {0: (0.5102, 0.2838), 1: (0.4773, 0.6622)}
+    out["notebook_angles_2pt"] = np.array([ref.get_rotation_angles(nb_locs, (1040, 1040), 2.0)[i] for i in (0, 1)])
+    np.savez_compressed(GOLDEN / "k3_rotated.npz", **out)
+
+
 def main() -> None:
+    import sys
+
     ref = ref_shim.load()
+    if "--rotated-only" in sys.argv:
+        golden_rotated(ref)
+        for f in sorted(GOLDEN.glob("k3_rotated.npz")):
+            print(f.name, f.stat().st_size)
+        return
+    golden_rotated(ref)
     from PIL import Image
     from torchvision import transforms
 

@@ -120,6 +120,8 @@ def load():
         resize_with_padding=cropping.resize_with_padding,
         mm_to_pixels=cropping.mm_to_pixels,
         crop_region_horizontal=cropping.crop_region_horizontal,
+        crop_region_rotated=cropping.crop_region_rotated,
+        get_rotation_angles=cropping.get_rotation_angles,
         CropContext=cropping.CropContext,
         predict_ivd_locations=cropping.predict_ivd_locations,
         load_localization_model=cropping.load_localization_model,

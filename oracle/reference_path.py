@@ -62,9 +62,34 @@ def crop_region_horizontal(image, center_x, center_y, crop_size, crop_delta) -> 
     return resize_with_padding(normalize_to_uint8(crop), crop_size)
 
 
+def get_rotation_angles(ivd_locations, image_shape, last_disc_angle_boost: float = 1.0):
+    """cropping.py:172-255 (same NumPy calls)."""
+    from oracle.fixedpoint import rotation_angles
+
+    return rotation_angles(ivd_locations, image_shape, last_disc_angle_boost)
+
+
+def crop_region_rotated(image, center_x, center_y, crop_size, crop_delta, rotation_angle) -> np.ndarray:
+    """cropping.py:258-313 (OpenCV does the rotation)."""
+    import cv2
+
+    h, w = image.shape[:2]
+    cx = int(center_x * w)
+    cy = int(center_y * h)
+    left, right, top, bottom = crop_delta
+    rotation_matrix = cv2.getRotationMatrix2D((cx, cy), rotation_angle, 1.0)
+    rotated = cv2.warpAffine(image, rotation_matrix, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+    x1 = max(0, cx - left)
+    x2 = min(w, cx + right)
+    y1 = max(0, cy - top)
+    y2 = min(h, cy + bottom)
+    crop = rotated[y1:y2, x1:x2]
+    return resize_with_padding(normalize_to_uint8(crop), crop_size)
+
+
 @dataclass
 class CropContext:
-    """cropping.py:357-404, horizontal mode (the default, config.py:44)."""
+    """cropping.py:357-404: horizontal (the default, config.py:44) and rotated modes."""
 
     image: np.ndarray
     ivd_locations: dict
@@ -72,13 +97,18 @@ class CropContext:
     crop_delta_px: tuple
     mode: str = "horizontal"
     last_disc_angle_boost: float = 1.0
+    rotation_angles: dict | None = None
+
+    def __post_init__(self) -> None:
+        if self.mode == "rotated" and self.rotation_angles is None:  # cropping.py:369-375
+            self.rotation_angles = get_rotation_angles(self.ivd_locations, self.image.shape[:2], self.last_disc_angle_boost)
 
     def crop(self, level_idx: int):
         if level_idx not in self.ivd_locations:
             return None
-        if self.mode != "horizontal":
-            raise NotImplementedError("rotated mode is a SURVEY 8(f) next-row")
         cx, cy = self.ivd_locations[level_idx]
+        if self.mode == "rotated" and self.rotation_angles:
+            return crop_region_rotated(self.image, cx, cy, self.crop_size, self.crop_delta_px, self.rotation_angles.get(level_idx, 0.0))
         return crop_region_horizontal(self.image, cx, cy, self.crop_size, self.crop_delta_px)
 
 

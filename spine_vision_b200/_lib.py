@@ -21,7 +21,7 @@ KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 EXPORTS = (
     "svb_version", "svb_last_error", "svb_device_check", "svb_launch_count",
     "svb_k1_workspace_bytes", "svb_k1_normalize_resize",
-    "svb_k3_workspace_bytes", "svb_k3_crop_resample",
+    "svb_k3_workspace_bytes", "svb_k3_crop_resample", "svb_k3_crop_resample_rotated",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
     "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused",
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
@@ -66,6 +66,8 @@ def load() -> C.CDLL:
     lib.svb_k3_workspace_bytes.argtypes = [i32] * 4
     lib.svb_k3_crop_resample.restype = C.c_int
     lib.svb_k3_crop_resample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
+    lib.svb_k3_crop_resample_rotated.restype = C.c_int
+    lib.svb_k3_crop_resample_rotated.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
     lib.svb_model_create.restype = C.c_int
     lib.svb_model_create.argtypes = [C.POINTER(vp), C.POINTER(WeightDesc), i32, i32]
     lib.svb_model_destroy.restype = C.c_int

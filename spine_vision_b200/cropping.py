@@ -13,6 +13,7 @@ every call raises.
 
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
 from pathlib import Path
 from typing import Literal
@@ -45,6 +46,57 @@ def mm_to_pixels(delta_mm, spacing) -> tuple[int, int, int, int]:
         int(round(top_mm / row_spacing)),
         int(round(bottom_mm / row_spacing)),
     )
+
+
+def get_rotation_angles(ivd_locations: dict, image_shape: tuple[int, int], last_disc_angle_boost: float = 1.0) -> dict:
+    """cropping.py:172-255 -- host arithmetic on five points (same NumPy calls as the reference): tangent of the disc
+    chain by forward / central differences, the lowest disc from a 3-point quadratic fit, negated to flatten the tilt."""
+    if len(ivd_locations) < 2:
+        return {level: 0.0 for level in ivd_locations}
+    h, w = image_shape
+    points = sorted(((lvl, nx * w, ny * h) for lvl, (nx, ny) in ivd_locations.items()), key=lambda p: p[2])
+    n = len(points)
+    angles: dict = {}
+    for i, (lvl, px, py) in enumerate(points):
+        if i == 0:
+            dx, dy = points[1][1] - px, points[1][2] - py
+            dxdy = dx / dy if dy != 0 else 0.0
+        elif i == n - 1:
+            if n >= 3:
+                last = points[-3:]
+                a, b, _ = np.polyfit(np.array([p[2] for p in last]), np.array([p[1] for p in last]), deg=2)
+                dxdy = 2 * a * py + b
+            else:
+                dx, dy = px - points[i - 1][1], py - points[i - 1][2]
+                dxdy = dx / dy if dy != 0 else 0.0
+        else:
+            dx, dy = points[i + 1][1] - points[i - 1][1], points[i + 1][2] - points[i - 1][2]
+            dxdy = dx / dy if dy != 0 else 0.0
+        angle_deg = float(np.degrees(np.arctan(dxdy)))
+        if i == n - 1:
+            angle_deg *= last_disc_angle_boost
+        angles[lvl] = -angle_deg
+    return angles
+
+
+def inverse_rotation(cx: int, cy: int, angle_deg: float) -> list[float]:
+    """The 2x3 map cv2.warpAffine actually applies for ``cv2.getRotationMatrix2D((cx, cy), angle, 1.0)``
+    (cropping.py:289-301): OpenCV builds the forward matrix in double and inverts it in place; the six doubles are
+    handed to K3, so the device never evaluates a sine."""
+    a = angle_deg * (math.pi / 180.0)  # OpenCV: angle *= CV_PI/180 (one multiply by the constant)
+    alpha, beta = math.cos(a), math.sin(a)
+    m = [alpha, beta, (1 - alpha) * cx - beta * cy, -beta, alpha, beta * cx + (1 - alpha) * cy]
+    d = m[0] * m[4] - m[1] * m[3]
+    d = 1.0 / d if d != 0 else 0.0
+    a11, a22 = m[4] * d, m[0] * d
+    m[0] = a11
+    m[1] *= -d
+    m[3] *= -d
+    m[4] = a22
+    b1 = -m[0] * m[2] - m[1] * m[5]
+    b2 = -m[3] * m[2] - m[4] * m[5]
+    m[2], m[5] = b1, b2
+    return m
 
 
 def normalize_to_uint8(arr: np.ndarray, device: str = _DEFAULT_DEVICE) -> np.ndarray:
@@ -104,9 +156,11 @@ class CropContext:
     device: str = _DEFAULT_DEVICE
 
     def __post_init__(self) -> None:
-        if self.mode != "horizontal":
-            raise NotImplementedError("crop mode 'rotated' (cropping.py:172-313) is a SURVEY 8(f) next-row; "
-                                      "only the default 'horizontal' mode is built")
+        if self.mode not in ("horizontal", "rotated"):
+            raise ValueError(f"unknown crop mode {self.mode!r}")
+        if self.mode == "rotated" and self.rotation_angles is None:  # cropping.py:369-375
+            h, w = np.asarray(self.image).shape[:2]
+            self.rotation_angles = get_rotation_angles(self.ivd_locations, (h, w), self.last_disc_angle_boost)
         self._pool = None
 
     def _ensure_pool(self):
@@ -120,14 +174,20 @@ class CropContext:
             return {}
         pool = self._ensure_pool()
         dev = pool.data.device
-        xy = torch.tensor([[float(self.ivd_locations[i][0]), float(self.ivd_locations[i][1])] for i in levels],
-                          dtype=torch.float32).to(dev)
+        h, w = pool.shapes[0]
+        xy_host = [[float(self.ivd_locations[i][0]), float(self.ivd_locations[i][1])] for i in levels]
+        xy = torch.tensor(xy_host, dtype=torch.float32).to(dev)
         idx = torch.zeros(len(levels), dtype=torch.int32, device=dev)
         l, r, t, b = (int(v) for v in self.crop_delta_px)
         delta = torch.tensor([[l, r, t, b]] * len(levels), dtype=torch.int32).to(dev)
-        h, w = pool.shapes[0]
+        inv = None
+        if self.mode == "rotated" and self.rotation_angles:  # cropping.py:390-399
+            # centre as the reference computes it: int(x * w) on the Python floats it was given
+            rows = [inverse_rotation(int(self.ivd_locations[i][0] * w), int(self.ivd_locations[i][1] * h),
+                                     self.rotation_angles.get(i, 0.0)) for i in levels]
+            inv = torch.tensor(rows, dtype=torch.float64).to(dev)
         crops, _, _ = ops.crop_resample(pool, idx, xy, delta, (min(h, max(t + b, 1)), min(w, max(l + r, 1))),
-                                        self.crop_size, None)
+                                        self.crop_size, None, inv_affine=inv)
         host = crops.cpu().numpy()
         return {lvl: host[k] for k, lvl in enumerate(levels)}
 

@@ -463,7 +463,7 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
                                                       uint8_t* __restrict__ crops2, int32_t* __restrict__ geom_out,
                                                       int flags, int box_cap, int ksh2, int ksw2, const int* __restrict__ hb2,
                                                       const int* __restrict__ hk2, const int* __restrict__ vb2,
-                                                      const int* __restrict__ vk2) {
+                                                      const int* __restrict__ vk2, const double* __restrict__ rot) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int n = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -521,15 +521,42 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
     __syncthreads();
     const int bh = g.y2 - g.y1, bw = g.x2 - g.x1;
     const bool valid = g.new_h > 0 && g.new_w > 0;
-    const float* src = slices + offs[b] + (long long)g.y1 * W + g.x1;
+    const float* img = slices + offs[b];
+    const float* src = img + (long long)g.y1 * W + g.x1;
+    // rotated mode (cropping.py:258-313): the box is cut from cv2.warpAffine(image, R, INTER_LINEAR, BORDER_REPLICATE).
+    // rot = the INVERTED 2x3 map (host, double).  Per destination pixel OpenCV takes the source position in 1/1024 px
+    // fixed point, rounds it to 1/32 px, and blends four taps with exact fp32 bilinear weights, left to right.
+    double r00 = 0, r01 = 0, r02 = 0, r10 = 0, r11 = 0, r12 = 0;
+    if (rot != nullptr) {
+        const double* rp = rot + 6 * (size_t)n;
+        r00 = rp[0]; r01 = rp[1]; r02 = rp[2]; r10 = rp[3]; r11 = rp[4]; r12 = rp[5];
+    }
+    auto box_value = [&](int bx, int by) -> float {
+        if (rot == nullptr) return __ldg(src + (long long)by * W + bx);
+        const int x = g.x1 + bx, y = g.y1 + by;
+        const int adelta = __double2int_rn(__dmul_rn(__dmul_rn(r00, (double)x), 1024.0));
+        const int bdelta = __double2int_rn(__dmul_rn(__dmul_rn(r10, (double)x), 1024.0));
+        const int X0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(r01, (double)y), r02), 1024.0)) + 16;
+        const int Y0 = __double2int_rn(__dmul_rn(__dadd_rn(__dmul_rn(r11, (double)y), r12), 1024.0)) + 16;
+        const int X = (X0 + adelta) >> 5, Y = (Y0 + bdelta) >> 5;
+        const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+        const float vx1 = __fmul_rn((float)(X & 31), 0.03125f), vy1 = __fmul_rn((float)(Y & 31), 0.03125f);
+        const float vx0 = __fsub_rn(1.0f, vx1), vy0 = __fsub_rn(1.0f, vy1);
+        const int xa = min(max(sx, 0), W - 1), xb = min(max(sx + 1, 0), W - 1);
+        const int ya = min(max(sy, 0), H - 1), yb = min(max(sy + 1, 0), H - 1);
+        const float s00 = __ldg(img + (long long)ya * W + xa), s01 = __ldg(img + (long long)ya * W + xb);
+        const float s10 = __ldg(img + (long long)yb * W + xa), s11 = __ldg(img + (long long)yb * W + xb);
+        float acc = __fadd_rn(__fmul_rn(s00, __fmul_rn(vy0, vx0)), __fmul_rn(s01, __fmul_rn(vy0, vx1)));
+        acc = __fadd_rn(acc, __fmul_rn(s10, __fmul_rn(vy1, vx0)));
+        return __fadd_rn(acc, __fmul_rn(s11, __fmul_rn(vy1, vx1)));
+    };
 
     if (valid) {
         // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350)
         float mn = INFINITY, mx = -INFINITY;
         for (int y = wid; y < bh; y += nwarps) {
-            const float* row = src + (long long)y * W;
             for (int x = lane; x < bw; x += 32) {
-                const float v = __ldg(row + x);
+                const float v = box_value(x, y);
                 mn = fminf(mn, v);
                 mx = fmaxf(mx, v);
             }
@@ -558,9 +585,8 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
         const float rng = (flags & SVB_K3_NO_NORMALIZE) ? 0.0f : __fsub_rn(s_mm[1], mnv);
         // pass 2: normalise the box into shared memory (second read is an L1/L2 hit)
         for (int y = wid; y < bh; y += nwarps) {
-            const float* row = src + (long long)y * W;
             uint8_t* drow = s_box + (size_t)y * bw;
-            for (int x = lane; x < bw; x += 32) drow[x] = (uint8_t)normalize_px(__ldg(row + x), mnv, rng);
+            for (int x = lane; x < bw; x += 32) drow[x] = (uint8_t)normalize_px(box_value(x, y), mnv, rng);
         }
     }
     __syncthreads();
@@ -666,11 +692,26 @@ extern "C" size_t svb_k3_workspace_bytes(int ch, int cw, int oh2, int ow2) {
     return k3_layout(ch, cw, oh2, ow2).total;
 }
 
+extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                            const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
+                                            const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
+                                            uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
+                                            void* d_ws, size_t ws_bytes, void* stream_);
+
 extern "C" int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                                     const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px, int N,
                                     int max_box_h, int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2,
                                     uint8_t* d_crops2, int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes,
                                     void* stream_) {
+    return svb_k3_crop_resample_rotated(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, nullptr, N, max_box_h, max_box_w,
+                                        ch, cw, d_crops, oh2, ow2, d_crops2, d_geom, flags, d_ws, ws_bytes, stream_);
+}
+
+extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                            const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
+                                            const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
+                                            uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
+                                            void* d_ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int rc = check_device_sm100()) return rc;
     SVB_REQUIRE(N >= 0 && ch > 0 && cw > 0 && max_box_h > 0 && max_box_w > 0, SVB_ERR_INVALID_ARG,
@@ -708,7 +749,7 @@ extern "C" int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs
     }
     SVB_CUDA_OK(cudaFuncSetAttribute(k3_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     k3_crop_kernel<<<N, 256, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
-                                                   oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk);
+                                                   oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk, d_inv_affine);
     SVB_LAUNCHED();
     return SVB_OK;
 }

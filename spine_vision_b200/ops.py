@@ -135,10 +135,12 @@ def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | Non
 
 def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, delta_px: torch.Tensor, max_box_hw,
                   crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True,
-                  out: torch.Tensor | None = None, out2: torch.Tensor | None = None):
+                  out: torch.Tensor | None = None, out2: torch.Tensor | None = None, inv_affine: torch.Tensor | None = None):
     """K3: one crop per (slice_idx, xy, delta_px) row.  Device mirror of
     ``CropContext.crop`` -> ``crop_region_horizontal`` (cropping.py:316-404) and, for the
     second output, the classifier's ``Resize`` (training/datasets/classification.py:247-278).
+    ``inv_affine`` (float64 ``[N,6]`` on the device, from ``cropping.inverse_rotation``) switches on the rotated crop
+    mode (``crop_region_rotated``, cropping.py:258-313).
     Returns ``(crops u8 [N,ch,cw], crops2 u8 [N,oh2,ow2] | None, geom int32 [N,8] | None)``."""
     lib = _lib.load()
     dev = pool.data.device
@@ -160,10 +162,12 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     need = lib.svb_k3_workspace_bytes(ch, cw, oh2, ow2)
     ws = _Workspace.get("k3", need, dev)
     wp, wn = _aligned_ptr(ws, 256)
-    _lib.check(lib.svb_k3_crop_resample(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), slice_idx.data_ptr(),
-                                        xy.data_ptr(), delta_px.data_ptr(), N, int(max_box_hw[0]), int(max_box_hw[1]), ch, cw,
-                                        crops.data_ptr(), oh2, ow2, _lib.ptr(crops2), _lib.ptr(geom), 0 if normalize else 1, wp, wn,
-                                        _lib.current_stream()))
+    if inv_affine is not None:
+        assert inv_affine.dtype == torch.float64 and inv_affine.is_contiguous() and tuple(inv_affine.shape) == (N, 6)
+    _lib.check(lib.svb_k3_crop_resample_rotated(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), slice_idx.data_ptr(),
+                                                xy.data_ptr(), delta_px.data_ptr(), _lib.ptr(inv_affine), N, int(max_box_hw[0]),
+                                                int(max_box_hw[1]), ch, cw, crops.data_ptr(), oh2, ow2, _lib.ptr(crops2),
+                                                _lib.ptr(geom), 0 if normalize else 1, wp, wn, _lib.current_stream()))
     return crops, crops2, geom
 
 

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from . import ops
-from .cropping import LocalizationModel, get_center_fallback_locations, mm_to_pixels
+from .cropping import LocalizationModel, get_center_fallback_locations, get_rotation_angles, inverse_rotation, mm_to_pixels
 
 NUM_LEVELS = 5
 
@@ -35,8 +35,22 @@ class CropBatch:
         return (self.coords.cpu().numpy(), self.crops.cpu().numpy(), None if self.crops2 is None else self.crops2.cpu().numpy())
 
 
+def rotation_table(coords: torch.Tensor, shapes, last_disc_angle_boost: float = 1.0) -> torch.Tensor:
+    """Rotated crop mode (cropping.py:172-313): per (series, level) the inverse rotation OpenCV would apply, as
+    float64 ``[B*L, 6]`` on the device.  The five-point angle fit is host arithmetic with the reference's own NumPy
+    calls (``np.polyfit``), so this costs one small device->host read of the coordinates."""
+    c = coords.detach().cpu().numpy()
+    rows = []
+    for b, (h, w) in enumerate(shapes):
+        locs = {i: (float(c[b, i, 0]), float(c[b, i, 1])) for i in range(c.shape[1])}
+        ang = get_rotation_angles(locs, (h, w), last_disc_angle_boost)
+        for i in range(c.shape[1]):
+            rows.append(inverse_rotation(int(locs[i][0] * w), int(locs[i][1] * h), ang[i]))
+    return torch.tensor(rows, dtype=torch.float64).to(coords.device)
+
+
 def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacings=None, crop_size=(128, 128),
-                second_size=(256, 256), return_geom: bool = False):
+                second_size=(256, 256), return_geom: bool = False, mode: str = "horizontal", last_disc_angle_boost: float = 1.0):
     """K3 over every (series, level): coords float32 [B,L,2] on the device.  ``spacings`` is a
     list of per-series (row, col) mm/px (``get_slice_spacing``, cropping.py:82-101); the
     reference always crops the 0.3 mm isotropic slice, so the default is (0.3, 0.3)."""
@@ -50,8 +64,12 @@ def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacin
     mh, mw = pool.max_hw
     max_box = (min(max_box[0], mh), min(max_box[1], mw))
     idx = torch.arange(B, dtype=torch.int32).repeat_interleave(L).contiguous()
+    if mode not in ("horizontal", "rotated"):
+        raise ValueError(f"unknown crop mode {mode!r}")
+    inv = rotation_table(coords, pool.shapes, last_disc_angle_boost) if mode == "rotated" else None
     crops, crops2, geom = ops.crop_resample(pool, idx.to(dev, non_blocking=True), coords.reshape(B * L, 2).contiguous(),
-                                            delta.to(dev, non_blocking=True), max_box, crop_size, second_size, return_geom)
+                                            delta.to(dev, non_blocking=True), max_box, crop_size, second_size, return_geom,
+                                            inv_affine=inv)
     crops = crops.view(B, L, *crops.shape[1:])
     if crops2 is not None:
         crops2 = crops2.view(B, L, *crops2.shape[1:])
@@ -62,7 +80,8 @@ def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacin
 
 def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop_delta_mm=(55, 15, 17.5, 20),
                       crop_size=(256, 256), image_size=(512, 512), second_size=(256, 256), spacings=None,
-                      keep_planes: bool = False, times: dict | None = None) -> CropBatch:
+                      keep_planes: bool = False, times: dict | None = None, crop_mode: str = "horizontal",
+                      last_disc_angle_boost: float = 1.0) -> CropBatch:
     """One batched pass of the hot path over a pool of middle slices already in HBM.
     ``model=None`` reproduces the reference's centre-crop fallback (__init__.py:194-197)."""
     dev = pool.data.device
@@ -75,7 +94,8 @@ def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop
         fb = get_center_fallback_locations()
         one = torch.tensor([fb[i] for i in range(NUM_LEVELS)], dtype=torch.float32)
         coords = one.unsqueeze(0).repeat(B, 1, 1).to(dev)
-    crops, crops2, _ = crop_levels(pool, coords, crop_delta_mm, spacings, crop_size, second_size)
+    crops, crops2, _ = crop_levels(pool, coords, crop_delta_mm, spacings, crop_size, second_size, mode=crop_mode,
+                                   last_disc_angle_boost=last_disc_angle_boost)
     return CropBatch(coords, crops, crops2, planes if keep_planes else None, times or {})
 
 

@@ -69,8 +69,13 @@ def test_k3_reference_shaped_api():
         want = ref.crop_region_horizontal(img, locs[i][0], locs[i][1], (256, 256), dpx)
         assert np.array_equal(ctx.crop(i), want)
     assert ctx.crop(7) is None
-    with pytest.raises(NotImplementedError):
-        cropping.CropContext(image=img, ivd_locations=locs, crop_size=(256, 256), crop_delta_px=dpx, mode="rotated")
+    rot = cropping.CropContext(image=img, ivd_locations=locs, crop_size=(256, 256), crop_delta_px=dpx, mode="rotated", device=dev())
+    rref = ref.CropContext(image=img, ivd_locations=locs, crop_size=(256, 256), crop_delta_px=dpx, mode="rotated")
+    assert rot.rotation_angles == rref.rotation_angles
+    for i in range(5):
+        assert np.array_equal(rot.crop(i), rref.crop(i))
+    with pytest.raises(ValueError):
+        cropping.CropContext(image=img, ivd_locations=locs, crop_size=(256, 256), crop_delta_px=dpx, mode="sideways")
     u8 = ref.normalize_to_uint8(img[100:300, 200:434])
     assert np.array_equal(cropping.resize_with_padding(u8, (128, 128), dev()), ref.resize_with_padding(u8, (128, 128)))
     # constant crop (max == min): values are cast, not scaled
@@ -103,3 +108,34 @@ def test_k3_config4_properties():
     for i in sel:
         assert gm[i, 4] == 109 and gm[i, 5] == 128 and gm[i, 6] == 9  # 234x200 -> 128x109, y_off 9
         assert ah[i, :9].max() == 0 and ah[i, 9 + 109:].max() == 0
+
+
+def test_k3_rotated_matches_reference_golden_bit_exact():
+    """Rotated crop mode (CropContext mode="rotated", cropping.py:172-313): crops frozen from the reference's own
+    CropContext (cv2.warpAffine + normalise + letterbox) against K3's on-the-fly rotation, through the drop-in
+    CropContext and through the batched pipeline entry; angles from the host mirror must equal the reference's."""
+    g = np.load(GOLDEN / "k3_rotated.npz")
+    total = bad = 0
+    for seed, h, w in [(10, 1195, 1195), (11, 1040, 1040), (12, 640, 650), (13, 400, 380)]:
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        for di, dmm in enumerate([(50, 20, 30, 30), (55, 15, 17.5, 20)]):
+            dpx = cropping.mm_to_pixels(dmm, (0.3, 0.3))
+            for boost in (1.0, 2.0):
+                want = g[f"crops_{seed}_{h}_{w}_d{di}_b{int(boost)}"]
+                wang = g[f"angles_{seed}_{h}_{w}_d{di}_b{int(boost)}"]
+                for s in range(2):
+                    locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                    ctx = cropping.CropContext(img, locs, (128, 128), dpx, "rotated", last_disc_angle_boost=boost, device=dev())
+                    assert [ctx.rotation_angles[i] for i in range(5)] == list(wang[s])
+                    got = ctx.crop_all(range(5))
+                    for i in range(5):
+                        total += 1
+                        bad += int((got[i] != want[s, i]).sum())
+                # batched entry: both coordinate sets of the series in one launch
+                pool = ops.SlicePool.from_numpy([img, img], dev())
+                crops, _, _ = pipeline.crop_levels(pool, torch.from_numpy(xy[:2]).to(dev()), dmm, None, (128, 128), None,
+                                                   mode="rotated", last_disc_angle_boost=boost)
+                assert np.array_equal(crops.cpu().numpy(), want)
+    assert total == 160 and bad == 0, f"{bad} differing pixels over {total} rotated crops"
+    assert np.allclose(g["notebook_angles_2pt"], [4.96908734, 9.93817468])

@@ -170,3 +170,36 @@ def test_gelu_fast_formula():
     got = np.maximum(x, 0) - np.abs(np.float32(0.5) * x * e)
     want = 0.5 * x.astype(np.float64) * (1 + erf(x.astype(np.float64) / np.sqrt(2)))
     assert np.abs(got - want).max() < 3e-6
+
+
+def test_rotated_crop_restatement_matches_reference_golden_and_opencv():
+    """oracle/fixedpoint.py's warpAffine / rotation-angle restatements against (a) crops and angles frozen from the
+    reference's own CropContext(mode="rotated") and (b) cv2.warpAffine directly, bit for bit."""
+    import cv2
+
+    from oracle import fixedpoint as fp
+
+    g = np.load(GOLDEN / "k3_rotated.npz")
+    seed, h, w = 13, 400, 380
+    img = synthetic.make_iso_slice(seed, h, w)
+    xy = g[f"xy_{seed}_{h}_{w}"]
+    for di, dmm in enumerate([(50, 20, 30, 30), (55, 15, 17.5, 20)]):
+        dpx = fp.mm_to_pixels(dmm, (0.3, 0.3))
+        for boost in (1.0, 2.0):
+            want = g[f"crops_{seed}_{h}_{w}_d{di}_b{int(boost)}"]
+            wang = g[f"angles_{seed}_{h}_{w}_d{di}_b{int(boost)}"]
+            for s in range(2):
+                locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                ang = fp.rotation_angles(locs, (h, w), boost)
+                for i in range(5):
+                    assert ang[i] == wang[s, i]
+                    got = fp.crop_region_rotated(img, locs[i][0], locs[i][1], (128, 128), dpx, ang[i])
+                    assert np.array_equal(got, want[s, i])
+                    assert np.array_equal(ref.CropContext(img, locs, (128, 128), dpx, "rotated", boost).crop(i), want[s, i])
+    rng = np.random.default_rng(3)
+    a = (rng.random((211, 173), dtype=np.float32) * 900).astype(np.float32)
+    for ang in (0.0, 6.98, -26.68, 45.0, 90.0):
+        M = cv2.getRotationMatrix2D((80, 120), ang, 1.0)
+        assert np.array_equal(M, fp.rotation_matrix_2d((80, 120), ang))
+        want = cv2.warpAffine(a, M, (173, 211), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+        assert np.array_equal(want.view(np.uint32), fp.warp_affine_f32(a, M).view(np.uint32))
