@@ -252,6 +252,17 @@ def run_b200(args):
         gemm_ms = times.get("gemm", 0.0) / args.steps
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         hbm = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:  # DRAM bytes of the GEMM launches of one step, from the committed ncu --set full capture of the same kernels
+            tj = json.loads((ROOT / "profiles" / "r01_gemm_traffic.json").read_text())
+            traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
+        except Exception:
+            pass
+        dw_ms = times.get("dwconv_ln", 0.0) / args.steps
+        dw_flops = 2.0 * 49 * B * sum(d * (IMAGE_SIZE[0] >> (2 + i)) * (IMAGE_SIZE[1] >> (2 + i)) * n
+                                      for i, (d, n) in enumerate(zip(model.engine.dims, model.engine.depths)))
+        dw_bytes = 2.0 * 2 * B * sum(d * (IMAGE_SIZE[0] >> (2 + i)) * (IMAGE_SIZE[1] >> (2 + i)) * n
+                                     for i, (d, n) in enumerate(zip(model.engine.dims, model.engine.depths)))
         k1_bytes = B * (SLICE_HW[0] * SLICE_HW[1] * 4 + IMAGE_SIZE[0] * IMAGE_SIZE[1])
         k3_bytes = n_crops * (234 * 200 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])
         line = {
@@ -269,10 +280,15 @@ def run_b200(args):
             "gpu_launches": int(gpu_launches),
             "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": None, "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
+                         "traffic": traffic, "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full, per-shape dram bytes x launches)",
+                         "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
                          "timing": "CUDA event pair around every launch, separate pass over the same steps"},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
                                    "k3_crop_resample": k3_ms / args.steps},
+            "fp32_kernels": {"dwconv_ln": {"flops_per_step": dw_flops, "achieved_tflops": dw_flops / (dw_ms * 1e-3) / 1e12 if dw_ms else None,
+                                           "fp32_peak_tflops_nominal": 72.0, "hbm_bytes_per_step": dw_bytes,
+                                           "achieved_gbs": dw_bytes / (dw_ms * 1e-3) / 1e9 if dw_ms else None,
+                                           "note": "FP32-pipe bound (49 FMA per output): FFMA2 issues at ~2.4 clk on B200, measured ceiling of the loop ~78 of 128 FMA/clk/SM (scripts/ubench/convloop2.cu)"}},
             "hbm_kernels": {
                 "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None, "peak_gbs": hbm},
                 "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None, "peak_gbs": hbm},
