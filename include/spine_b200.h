@@ -59,6 +59,35 @@ int svb_device_check(void);
 long long svb_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------
+ * K0 -- middle sagittal plane of the 0.3 mm isotropic resample, computed from the source volume.
+ * Replaces resample_to_isotropic + extract_middle_slice + get_slice_spacing
+ * (spine_vision/datasets/classification/cropping.py:37-101: SimpleITK ResampleImageFilter with an identity
+ * transform and sitkLinear over the WHOLE volume, DICOMOrient(LPI), arr[:, :, n // 2]) for the one plane that is kept.
+ * Parity is UNPINNED: SimpleITK is absent from the build image; the arithmetic is the restatement in
+ * oracle/itk_resample.py (continuous index (i * new_spacing) / spacing, inside test [-0.5, size - 0.5), clamped
+ * neighbours, nested double lerp x -> y -> z, default pixel 0, cast to float32).
+ * The host resolves orientation and the fixed (Left-Right) axis (spine_vision_b200.volumes.plan_midplane).
+ *
+ *  d_volumes : float32 pool; series b is the array [nz][ny][nx] (sitk.GetArrayFromImage order) at vol_off
+ *  d_desc    : svb_k0_series [B] on the device
+ *  d_out     : float32 pool of output planes [out_h][out_w] at out_off -- the SlicePool K1 and K3 take
+ */
+typedef struct svb_k0_series {
+    int64_t vol_off, out_off;          /* element offsets into d_volumes / d_out */
+    int32_t nx, ny, nz;                /* size of the (possibly slab-cut) source array */
+    int32_t ax_row, ax_col, ax_fix;    /* image axis (0 = x, 1 = y, 2 = z) running down the rows / across the columns / fixed */
+    int32_t flip_row, flip_col;        /* the oriented axis runs against the image axis */
+    int32_t out_h, out_w;              /* resampled sizes of the row / column axes: int(round(size * spacing / 0.3)) */
+    int32_t fix_lo, fix_hi, fix_inside, pad;  /* the two source planes around the fixed index (indices into the array) */
+    double fix_frac;                   /* interpolation fraction between them */
+    double sp_row, sp_col;             /* source spacing (mm) of the row / column axes */
+    double new_sp_row, new_sp_col;     /* target spacing (0.3 mm) */
+} svb_k0_series;
+size_t svb_k0_workspace_bytes(int B, int max_out_h, int max_out_w);
+int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
+                             int max_out_w, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * K1 -- fused min-max normalise + antialiased bilinear resize to uint8.
  * Replaces, per slice: normalize_to_uint8 (spine_vision/io/__init__.py:15-30) followed by
  * PIL "L"->"RGB" + torchvision Resize (Pillow BILINEAR with antialias, uint8 fixed point)

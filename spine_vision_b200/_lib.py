@@ -20,6 +20,7 @@ KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 # every symbol include/spine_b200.h declares
 EXPORTS = (
     "svb_version", "svb_last_error", "svb_device_check", "svb_launch_count",
+    "svb_k0_workspace_bytes", "svb_k0_midplane_resample",
     "svb_k1_workspace_bytes", "svb_k1_normalize_resize",
     "svb_k3_workspace_bytes", "svb_k3_crop_resample", "svb_k3_crop_resample_rotated",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
@@ -58,6 +59,10 @@ def load() -> C.CDLL:
     lib.svb_device_check.restype = C.c_int
     lib.svb_launch_count.restype = C.c_longlong
     lib.svb_launch_count.argtypes = [C.c_int]
+    lib.svb_k0_workspace_bytes.restype = sz
+    lib.svb_k0_workspace_bytes.argtypes = [i32] * 3
+    lib.svb_k0_midplane_resample.restype = C.c_int
+    lib.svb_k0_midplane_resample.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
     lib.svb_k1_workspace_bytes.restype = sz
     lib.svb_k1_workspace_bytes.argtypes = [i32] * 5
     lib.svb_k1_normalize_resize.restype = C.c_int

@@ -753,3 +753,108 @@ extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t
     SVB_LAUNCHED();
     return SVB_OK;
 }
+
+// ============================================================================ K0
+// Middle sagittal plane of the 0.3 mm isotropic resample, straight from the source volume: replaces
+// resample_to_isotropic + extract_middle_slice + get_slice_spacing (cropping.py:37-101; SimpleITK/ITK on the CPU,
+// 285 M voxels per series of which one plane is kept).  The host resolves the LPI orientation into "which image axis
+// runs down the rows / across the columns / is fixed" and the two source planes around the fixed index; the device
+// evaluates ITK's linear interpolation for the surviving plane only (double arithmetic, nested lerp x -> y -> z,
+// neighbours clamped, default pixel 0 outside [-0.5, size - 0.5)).  Arithmetic = oracle/itk_resample.py.
+namespace svb {
+
+// per-axis sample table entry
+struct K0Tap { int lo, hi, inside, pad; double frac; };
+
+// grid (ceil(max(out_h,out_w)/128), 2, B): tables for rows (y = 0) and columns (y = 1)
+__global__ void k0_table_kernel(const svb_k0_series* __restrict__ desc, int max_h, int max_w, K0Tap* __restrict__ taps) {
+    const svb_k0_series d = desc[blockIdx.z];
+    const int which = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_out = which == 0 ? d.out_h : d.out_w;
+    if (i >= n_out) return;
+    const int ax = which == 0 ? d.ax_row : d.ax_col;
+    const int size = ax == 0 ? d.nx : (ax == 1 ? d.ny : d.nz);
+    const int flip = which == 0 ? d.flip_row : d.flip_col;
+    const double sp = which == 0 ? d.sp_row : d.sp_col, nsp = which == 0 ? d.new_sp_row : d.new_sp_col;
+    const int idx = flip ? n_out - 1 - i : i;
+    const double u = __ddiv_rn(__dmul_rn((double)idx, nsp), sp);
+    K0Tap t;
+    t.inside = (u >= -0.5 && u < (double)size - 0.5) ? 1 : 0;
+    const double base = floor(u);
+    t.frac = __dsub_rn(u, base);
+    const int b = (int)base;
+    t.lo = min(max(b, 0), size - 1);
+    t.hi = min(max(b + 1, 0), size - 1);
+    t.pad = 0;
+    taps[((size_t)blockIdx.z * 2 + which) * (size_t)max(max_h, max_w) + i] = t;
+}
+
+// grid (tiles, B): one thread per output pixel
+__global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restrict__ vol, const svb_k0_series* __restrict__ desc,
+                                                          int max_h, int max_w, const K0Tap* __restrict__ taps,
+                                                          float* __restrict__ out) {
+    const svb_k0_series d = desc[blockIdx.y];
+    const int stride = max(max_h, max_w);
+    const K0Tap* rt = taps + ((size_t)blockIdx.y * 2 + 0) * stride;
+    const K0Tap* ct = taps + ((size_t)blockIdx.y * 2 + 1) * stride;
+    const float* v = vol + d.vol_off;
+    float* o = out + d.out_off;
+    const long long sx = 1, sy = d.nx, sz = (long long)d.nx * d.ny;
+    const long long s_row = d.ax_row == 0 ? sx : (d.ax_row == 1 ? sy : sz);
+    const long long s_col = d.ax_col == 0 ? sx : (d.ax_col == 1 ? sy : sz);
+    const long long s_fix = d.ax_fix == 0 ? sx : (d.ax_fix == 1 ? sy : sz);
+    const long long n = (long long)d.out_h * d.out_w;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(p / d.out_w), c = (int)(p - (long long)r * d.out_w);
+        const K0Tap tr = rt[r], tc = ct[c];
+        float res = 0.0f;
+        if (tr.inside && tc.inside && d.fix_inside) {
+            // per image axis a: (lo, hi, frac); the nested lerp always runs x, then y, then z
+            long long lo[3], hi[3];
+            double fr[3];
+            lo[d.ax_row] = tr.lo * s_row; hi[d.ax_row] = tr.hi * s_row; fr[d.ax_row] = tr.frac;
+            lo[d.ax_col] = tc.lo * s_col; hi[d.ax_col] = tc.hi * s_col; fr[d.ax_col] = tc.frac;
+            lo[d.ax_fix] = d.fix_lo * s_fix; hi[d.ax_fix] = d.fix_hi * s_fix; fr[d.ax_fix] = d.fix_frac;
+            auto g = [&](long long z, long long y, long long x) -> double { return (double)__ldg(v + z + y + x); };
+            auto lerp = [](double a, double b, double f) -> double { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), f)); };
+            double pl[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const long long z = k == 0 ? lo[2] : hi[2];
+                const double a = lerp(g(z, lo[1], lo[0]), g(z, lo[1], hi[0]), fr[0]);
+                const double b = lerp(g(z, hi[1], lo[0]), g(z, hi[1], hi[0]), fr[0]);
+                pl[k] = lerp(a, b, fr[1]);
+            }
+            res = (float)lerp(pl[0], pl[1], fr[2]);
+        }
+        o[p] = res;
+    }
+}
+
+}  // namespace svb
+
+extern "C" size_t svb_k0_workspace_bytes(int B, int max_out_h, int max_out_w) {
+    if (B <= 0 || max_out_h <= 0 || max_out_w <= 0) return 0;
+    return (size_t)B * 2 * (size_t)(max_out_h > max_out_w ? max_out_h : max_out_w) * sizeof(svb::K0Tap) + 256;
+}
+
+extern "C" int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
+                                        int max_out_w, float* d_out, void* d_ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(B >= 0 && max_out_h > 0 && max_out_w > 0, SVB_ERR_INVALID_ARG, "k0: bad sizes B=%d out=(%d,%d)", B, max_out_h, max_out_w);
+    if (B == 0) return SVB_OK;
+    SVB_REQUIRE(d_volumes && d_desc && d_out && d_ws, SVB_ERR_INVALID_ARG, "k0: null pointer argument");
+    SVB_REQUIRE(ws_bytes >= svb_k0_workspace_bytes(B, max_out_h, max_out_w), SVB_ERR_WORKSPACE_TOO_SMALL, "k0: workspace too small");
+    SVB_REQUIRE(B <= 65535, SVB_ERR_INVALID_ARG, "k0: at most 65535 series per call");
+    K0Tap* taps = reinterpret_cast<K0Tap*>((reinterpret_cast<uintptr_t>(d_ws) + 15) & ~uintptr_t(15));
+    const int m = max_out_h > max_out_w ? max_out_h : max_out_w;
+    k0_table_kernel<<<dim3(ceil_div(m, 128), 2, B), 128, 0, stream>>>(d_desc, max_out_h, max_out_w, taps);
+    SVB_LAUNCHED();
+    long long tiles = ceil_div<long long>((long long)max_out_h * max_out_w, 256 * 4);
+    if (tiles > 4096) tiles = 4096;
+    k0_midplane_kernel<<<dim3((unsigned)tiles, B), 256, 0, stream>>>(d_volumes, d_desc, max_out_h, max_out_w, taps, d_out);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}

@@ -99,6 +99,16 @@ def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop
     return CropBatch(coords, crops, crops2, planes if keep_planes else None, times or {})
 
 
+def localize_and_crop_volumes(volumes, spacings, directions, model: LocalizationModel | None, device="cuda:0", **kw) -> CropBatch:
+    """The per-series body of ``process_spider`` from the decoded volume on (spider.py:114-152): K0 (middle isotropic
+    sagittal plane + its spacing) -> K1 -> localizer -> K3.  ``volumes``: ``[z, y, x]`` arrays
+    (``sitk.GetArrayFromImage``), ``spacings`` / ``directions``: ``image.GetSpacing()`` / ``GetDirection()``."""
+    from . import volumes as _vol
+
+    pool, slice_spacings = _vol.midplane_resample(volumes, spacings, directions, device)
+    return localize_and_crop(pool, model, spacings=slice_spacings, **kw)
+
+
 # ------------------------------------------------------------------------------------------ streamed host path
 class PinnedSeries:
     """A ragged batch of float32 middle slices staged once in pinned host memory (the layout of

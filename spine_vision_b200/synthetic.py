@@ -64,6 +64,19 @@ def make_iso_slice(seed: int, h: int = 1195, w: int = 1195, dtype=np.float32) ->
     return np.ascontiguousarray(img.astype(dtype))
 
 
+def make_volume(seed: int, n_slices: int = 15, h: int = 512, w: int = 512, spacing=(0.7, 0.7, 4.0)):
+    """A synthetic sagittal SERIES as the reference reads it: array ``[z, y, x] = [L, I, P]``
+    float32 (slices stacked Left-Right, rows superior->inferior, columns anterior->posterior), ``GetSpacing()`` =
+    (P, I, L) mm, and the direction matrix of such an acquisition (image x -> Posterior, y -> Inferior, z -> Left).
+    Slices drift smoothly with z so that the interpolation between the two middle slices matters."""
+    rng = np.random.default_rng(10_000 + seed)
+    base = make_iso_slice(seed, h, w)
+    drift = _upsample_linear(rng.random((6, 6), dtype=np.float32), h, w)
+    vol = np.stack([base * (1.0 + 0.04 * (z - n_slices / 2) * (drift - 0.5)) for z in range(n_slices)]).astype(np.float32)
+    direction = (0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0)  # columns: x -> +y_LPS (P), y -> -z_LPS (I), z -> +x_LPS (L)
+    return vol, tuple(float(s) for s in spacing), direction
+
+
 def make_batch(seeds, h: int = 1195, w: int = 1195) -> list[np.ndarray]:
     return [make_iso_slice(int(s), h, w) for s in seeds]
 

@@ -203,3 +203,22 @@ def test_rotated_crop_restatement_matches_reference_golden_and_opencv():
         assert np.array_equal(M, fp.rotation_matrix_2d((80, 120), ang))
         want = cv2.warpAffine(a, M, (173, 211), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
         assert np.array_equal(want.view(np.uint32), fp.warp_affine_f32(a, M).view(np.uint32))
+
+
+def test_itk_restatement_plane_shortcut_equals_whole_volume_path():
+    """oracle/itk_resample.py (parity UNPINNED -- SimpleITK absent): the one-plane shortcut K0 is tested against equals
+    the reference's order of operations (resample the whole volume, orient to LPI, take arr[:, :, n // 2])."""
+    from oracle import itk_resample as itk
+    from spine_vision_b200 import volumes
+
+    rng = np.random.default_rng(0)
+    dirs = [None, (0, 0, 1, 1, 0, 0, 0, -1, 0), (-1, 0, 0, 0, -1, 0, 0, 0, 1), (0.05, -0.02, 0.998, 0.996, 0.08, -0.04, -0.07, -0.996, -0.03)]
+    for d in dirs:
+        for shape, sp in [((5, 12, 14), (0.7, 0.9, 4.0)), ((7, 9, 11), (0.45, 0.31, 1.3))]:
+            v = (rng.random(shape) * 1000).astype(np.float32)
+            full = itk.extract_middle_slice_full(v, sp, d)
+            fast, spc = itk.resample_middle_sagittal(v, sp, d)
+            assert np.array_equal(full, fast) and spc == (0.3, 0.3)
+            plan = volumes.plan_midplane(v, sp, d)  # host planning of the product agrees on geometry
+            assert plan.out_hw == fast.shape and plan.spacing == spc
+    assert itk.new_size((512, 512, 15), (0.7, 0.7, 4.0)) == [1195, 1195, 200]  # SURVEY 8a
