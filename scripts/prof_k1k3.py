@@ -1,0 +1,44 @@
+"""K1 / K3 on the bench shapes (256 slices of 1195^2, 1280 crops): CUDA-event timings, or one launch each for ncu (REPS=0)."""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from spine_vision_b200 import ops, pipeline, synthetic  # noqa: E402
+
+dev = "cuda:0"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
+base = [synthetic.make_iso_slice(s, 1195, 1195) for s in range(8)]
+pool = ops.SlicePool.from_numpy([base[i % 8] for i in range(B)], dev)
+xy = torch.from_numpy(synthetic.make_coords(B, seed=1)).to(dev).reshape(B * 5, 2).contiguous()
+dpx = pipeline.mm_to_pixels((50, 20, 30, 30), (0.3, 0.3))
+idx = torch.arange(B, dtype=torch.int32).repeat_interleave(5).contiguous().to(dev)
+delta = torch.tensor([dpx] * (B * 5), dtype=torch.int32).to(dev)
+out = torch.empty((B * 5, 128, 128), dtype=torch.uint8, device=dev)
+out2 = torch.empty((B * 5, 256, 256), dtype=torch.uint8, device=dev)
+planes = torch.empty((B, 512, 512), dtype=torch.uint8, device=dev)
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def k1():
+    ops.normalize_resize(pool, (512, 512), out=planes)
+
+
+def k3():
+    ops.crop_resample(pool, idx, xy, delta, (dpx[2] + dpx[3], dpx[0] + dpx[1]), (128, 128), (256, 256), out=out, out2=out2)
+
+
+for name, fn, nbytes in (("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120)):
+    if REPS == 0:
+        fn(); torch.cuda.synchronize(); continue
+    fn(); fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(REPS):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print(f"{name:22s} B={B}: {ms * 1e3:8.1f} us  {nbytes / ms / 1e6:8.1f} GB/s algorithmic (L2 flushed between reps)", flush=True)

@@ -456,7 +456,9 @@ __device__ __forceinline__ void cv_axis_entry(int i, int src, double scale, bool
 // One CTA per crop.
 // smem: [box u8: box_cap][canvas u8: ch*cw][tmp2 u8: ch*ow2 (if second output needs a pass)]
 //       [xs,xa0,xa1: 3*cw int][ys,yb0,yb1: 3*ch int]
-__global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
+constexpr int K3_THREADS = 512;  // 16 warps per crop, two crops per SM: the kernel is latency-bound, so warps are what it needs
+
+__global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
                                                       const int32_t* __restrict__ hw, const int32_t* __restrict__ slice_idx,
                                                       const float* __restrict__ xy, const int32_t* __restrict__ delta_px,
                                                       int ch, int cw, uint8_t* __restrict__ crops, int oh2, int ow2,
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
     int* yb1 = yb0 + ch;
 
     __shared__ K3Geom g;
-    __shared__ float s_red[2][8];
+    __shared__ float s_red[2][K3_THREADS / 32];
     __shared__ float s_mm[2];
 
     const int b = slice_idx[n];
@@ -552,13 +554,28 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
     };
 
     if (valid) {
-        // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350)
+        // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350).  The box is walked as one
+        // flat index range, 8 independent loads in flight per thread (the pass is pure load latency otherwise).
         float mn = INFINITY, mx = -INFINITY;
-        for (int y = wid; y < bh; y += nwarps) {
-            for (int x = lane; x < bw; x += 32) {
-                const float v = box_value(x, y);
-                mn = fminf(mn, v);
-                mx = fmaxf(mx, v);
+        const int npx = bh * bw;
+        const int step_y = nthr / bw, step_x = nthr - step_y * bw;
+        {
+            int y = tid / bw, x = tid - y * bw;
+            for (int base = tid; base < npx; base += 8 * nthr) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = (base + u * nthr < npx) ? box_value(x, y) : 0.0f;
+                    x += step_x; y += step_y;
+                    if (x >= bw) { x -= bw; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (base + u * nthr < npx) {
+                        mn = fminf(mn, v[u]);
+                        mx = fmaxf(mx, v[u]);
+                    }
+                }
             }
         }
         mn = warp_min(mn);
@@ -584,9 +601,23 @@ __global__ void __launch_bounds__(256) k3_crop_kernel(const float* __restrict__ 
         // rng <= 0 makes normalize_px a plain cast: the max == min case, and SVB_K3_NO_NORMALIZE
         const float rng = (flags & SVB_K3_NO_NORMALIZE) ? 0.0f : __fsub_rn(s_mm[1], mnv);
         // pass 2: normalise the box into shared memory (second read is an L1/L2 hit)
-        for (int y = wid; y < bh; y += nwarps) {
-            uint8_t* drow = s_box + (size_t)y * bw;
-            for (int x = lane; x < bw; x += 32) drow[x] = (uint8_t)normalize_px(box_value(x, y), mnv, rng);
+        const float kfast = rng > 0.0f ? __fdiv_rn(255.0f, rng) : 0.0f;
+        {
+            int y = tid / bw, x = tid - y * bw;
+            for (int base = tid; base < npx; base += 8 * nthr) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    v[u] = (base + u * nthr < npx) ? box_value(x, y) : 0.0f;
+                    x += step_x; y += step_y;
+                    if (x >= bw) { x -= bw; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = base + u * nthr;  // box pixels are stored row-major, so the flat index is the address
+                    if (i < npx) s_box[i] = (uint8_t)(rng > 0.0f ? normalize_px_fast(v[u], mnv, rng, kfast) : cast_f32_u8(v[u]));
+                }
+            }
         }
     }
     __syncthreads();
@@ -748,7 +779,7 @@ extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t
         SVB_LAUNCHED();
     }
     SVB_CUDA_OK(cudaFuncSetAttribute(k3_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    k3_crop_kernel<<<N, 256, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
+    k3_crop_kernel<<<N, K3_THREADS, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
                                                    oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk, d_inv_affine);
     SVB_LAUNCHED();
     return SVB_OK;
