@@ -462,27 +462,27 @@ template <typename T> struct UmmaFmt;
 template <> struct UmmaFmt<__nv_bfloat16> { static constexpr uint32_t v = 1; };
 template <> struct UmmaFmt<__half> { static constexpr uint32_t v = 0; };
 
-// GELU of a packed pair: gelu_fast's erfc fit on FFMA2, arranged as relu(x) - |x| * (erfc(|x|/sqrt2) / 2).
-// No clamp on |x|: the fit's exponent u*p(u) stays negative and decreasing for every u > 0
-// (p(u) < -1.15 on [0, inf)), so large |x| gives exp2(-big) = 0 and the result is relu(x).
+// GELU of a packed pair, 16-bit output: relu(x) - |x| * E(|x|), E(u) = erfc(u / sqrt2) / 2 = exp2(u * p(u) - 1) with a
+// cubic p fitted for min-max |GELU error| (8.6e-6 on the whole real line, scripts/fit_gelu.py; the output is rounded to
+// 16 bits, ulp >= 1.5e-5 wherever that matters).  Written in v = -min(|x|, 12) (one FMNMX with |.| and - modifiers), so
+// the product v * E is already the negative correction; beyond |x| = 12 the exponent is < -74 and the result is relu(x).
+// FMA-pipe cost per pair: 1 (bias, at the caller) + 4 (exponent) + 1 + 1 = 7 packed ops; the epilogues that call this
+// are bound by exactly that pipe (FFMA2 issues at ~2.4 clk on B200).
 template <typename T>
 __device__ __forceinline__ uint32_t gelu_pack2(uint64_t x) {
     float x0, x1;
     upk2(x, x0, x1);
-    const uint64_t u = pk2(fabsf(x0), fabsf(x1));
-    uint64_t r = pk2(-5.20460508e-04f, -5.20460508e-04f);
-    r = fma2(r, u, pk2(7.39751849e-03f, 7.39751849e-03f));
-    r = fma2(r, u, pk2(-5.25612477e-02f, -5.25612477e-02f));
-    r = fma2(r, u, pk2(-4.59254682e-01f, -4.59254682e-01f));
-    r = fma2(r, u, pk2(-1.15109138e+00f, -1.15109138e+00f));
-    r = fma2(r, u, pk2(-1.0f, -1.0f));  // exponent - 1: exp2 then yields erfc/2
+    const uint64_t v = pk2(fmaxf(-fabsf(x0), -12.0f), fmaxf(-fabsf(x1), -12.0f));
+    uint64_t r = pk2(4.16166e-03f, 4.16166e-03f);
+    r = fma2(r, v, pk2(4.573539e-02f, 4.573539e-02f));
+    r = fma2(r, v, pk2(-4.6493057e-01f, -4.6493057e-01f));
+    r = fma2(r, v, pk2(1.14956693e+00f, 1.14956693e+00f));
+    r = fma2(r, v, pk2(-1.0f, -1.0f));
     float r0, r1, e0, e1;
     upk2(r, r0, r1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(r0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(r1));
-    const uint64_t t = mul2(u, pk2(e0, e1));                      // |x| * erfc / 2
-    const uint64_t s = add2(x, u);                                // 2 * relu(x)
-    const uint64_t y = fma2(s, pk2(0.5f, 0.5f), mul2(t, pk2(-1.0f, -1.0f)));
+    const uint64_t y = fma2(v, pk2(e0, e1), pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f)));
     float y0, y1;
     upk2(y, y0, y1);
     return Cvt<T>::pack2(y0, y1);

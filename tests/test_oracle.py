@@ -172,6 +172,23 @@ def test_gelu_fast_formula():
     assert np.abs(got - want).max() < 3e-6
 
 
+def test_gelu_pack2_formula():
+    """NumPy replica of gelu_pack2 (the GEMM epilogue's GELU: cubic exponent fit in v = -min(|x|, 12)) vs exact erf GELU,
+    over the whole range incl. the clamp and huge inputs."""
+    from scipy.special import erf
+
+    x = np.concatenate([np.linspace(-40, 40, 400001), [-1e6, 1e6, -65504.0, 65504.0, 0.0]]).astype(np.float32)
+    v = np.maximum(-np.abs(x), np.float32(-12.0))
+    r = np.float32(4.16166e-03)
+    for c in (4.573539e-02, -4.6493057e-01, 1.14956693e+00, -1.0):
+        r = r * v + np.float32(c)
+    e = np.exp2(r.astype(np.float32))
+    got = v * e + np.maximum(x, 0)
+    xd = x.astype(np.float64)
+    want = 0.5 * xd * (1 + erf(xd / np.sqrt(2)))
+    assert np.isfinite(got).all() and np.abs(got - want).max() < 1.2e-5
+
+
 def test_rotated_crop_restatement_matches_reference_golden_and_opencv():
     """oracle/fixedpoint.py's warpAffine / rotation-angle restatements against (a) crops and angles frozen from the
     reference's own CropContext(mode="rotated") and (b) cv2.warpAffine directly, bit for bit."""
