@@ -209,6 +209,13 @@ __device__ __forceinline__ void bulk_wait_read() {  // at most N groups still re
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with programmaticStreamSerialization may start while its
+// predecessor in the stream is still running; it must call pdl_wait() before its first access to memory the predecessor
+// reads or writes (the wait returns once the predecessor grid has completed and its writes are visible).
+// pdl_launch_dependents() lets the successor's CTAs be scheduled as soon as every CTA of this grid has issued it.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---- thread-block cluster / CTA-pair helpers (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;

@@ -114,6 +114,17 @@ static int gemm_cg(int N, int K) {
 }
 
 static int dw_th(int C) { return C >= 512 ? 8 : 16; }
+// Programmatic dependent launch for the persistent kernels of the forward chain (depthwise conv + LN, GEMMs): the next
+// kernel's CTAs are scheduled as SMs drain and run their set-up (barriers, TMEM allocation, descriptor prefetch) under the
+// previous kernel's tail; griddepcontrol.wait in the kernels keeps the data dependence.  SVB_PDL=0 turns it off (A/B).
+static bool pdl_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SVB_PDL");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    return enabled != 0;
+}
 // fused fc1 -> GELU -> fc2 kernel (hidden activation kept on chip) for the widths whose accumulators fit TMEM:
 // C = 128 / 256 (stages 0-1 of convnext_base).  Correct (12 GPU tests) but on B200 it only TIES the un-fused pair
 // (profiles/r01_mlp_fused.txt: 317-380 us vs 323 us at C=128, 194-228 us vs 197 us at C=256 for 37 images): the GELU
@@ -480,13 +491,15 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
     cfg.blockDim = dim3(Cfg::NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K));
     count_launch();
     return SVB_OK;
@@ -563,9 +576,19 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
     const int tx = ceil_div(W, Cfg::TW), ty = ceil_div(H, TH);
     const int tiles = nb * tx * ty;
     const int slots = num_sms() * Cfg::CTAS_PER_SM;  // persistent CTAs
-    kern<<<tiles < slots ? tiles : slots, Cfg::NUM_THREADS, Cfg::SMEM_BYTES, st>>>(x, bp.wdw_map, bp.bdw, bp.lnw, bp.lnb,
-                                                                                   static_cast<T*>(out), H, W, tx, ty, tiles);
-    SVB_LAUNCHED();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles < slots ? tiles : slots);
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wdw_map, (const float*)bp.bdw, (const float*)bp.lnw, (const float*)bp.lnb,
+                                   static_cast<T*>(out), H, W, tx, ty, tiles));
+    count_launch();
     return SVB_OK;
 }
 template <typename T, int C>

@@ -299,12 +299,14 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();  // PDL: see svb_common.cuh; the waits sit in front of the first activation access
 
     // persistent CTA: tiles blockIdx.x, +gridDim.x, ...; the stage ring runs on across tiles, so the
     // producer is already fetching the next tile while the consumers normalise this one
     if (wid == TW) {
         // ---- TMA producer
         if (lane == 0) {
+            pdl_wait();
             int it = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 int t = tile;
@@ -327,6 +329,7 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
         const uint64_t* s_gw = reinterpret_cast<const uint64_t*>(s_ln) + lane;       // channel pair (2*lane, 2*lane+1) of chunk kk at [kk*32]
         const uint64_t* s_gb = reinterpret_cast<const uint64_t*>(s_ln + C) + lane;
         int it = 0;
+        pdl_wait();
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             int t = tile;
             const int tx = t % tiles_x; t /= tiles_x;
@@ -540,9 +543,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
     if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // PDL: the set-up above overlapped the previous kernel's tail; every thread that touches activations waits here
+    pdl_launch_dependents();
 
     if (warp == 0) {
         if (lane == 0) {
+            pdl_wait();
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
@@ -609,6 +615,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
         uint32_t rph = 0;
         int as = 0;
         uint32_t aphase = 0;
+        pdl_wait();
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
             const int row0 = (m_blk * CG + (int)rank) * Cfg::BM + q * 32;
