@@ -42,12 +42,15 @@ typedef enum svb_status {
     SVB_ERR_WORKSPACE_TOO_SMALL = -4,
     SVB_ERR_BOX_TOO_LARGE = -5,
     SVB_ERR_MISSING_WEIGHT = -6,
-    SVB_ERR_UNSUPPORTED_MODEL = -7
+    SVB_ERR_UNSUPPORTED_MODEL = -7,
+    SVB_ERR_IO = -8,    /* host input / output stage: file cannot be opened, read or written */
+    SVB_ERR_FORMAT = -9 /* host input stage: not a (supported) MetaImage file */
 } svb_status;
 
 typedef enum svb_dtype {
     SVB_BF16 = 0, /* bf16 operands, fp32 accumulate (BASELINE.json north_star) */
-    SVB_FP16 = 1  /* fp16 operands, fp32 accumulate: same tensor rate, 3 more mantissa bits */
+    SVB_FP16 = 1, /* fp16 operands, fp32 accumulate: same tensor rate, 3 more mantissa bits */
+    SVB_F32 = 2   /* float32 -- output type of svb_k4_classifier_input only */
 } svb_dtype;
 
 int svb_version(void);
@@ -78,7 +81,9 @@ typedef struct svb_k0_series {
     int32_t ax_row, ax_col, ax_fix;    /* image axis (0 = x, 1 = y, 2 = z) running down the rows / across the columns / fixed */
     int32_t flip_row, flip_col;        /* the oriented axis runs against the image axis */
     int32_t out_h, out_w;              /* resampled sizes of the row / column axes: int(round(size * spacing / 0.3)) */
-    int32_t fix_lo, fix_hi, fix_inside, pad;  /* the two source planes around the fixed index (indices into the array) */
+    int32_t fix_lo, fix_hi, fix_inside;       /* the two source planes around the fixed index (indices into the array) */
+    int32_t integer_pixels;            /* the source pixel type is integral: ITK casts the interpolated double back to it
+                                          (static_cast, i.e. truncation toward zero) -- the plane then holds whole numbers */
     double fix_frac;                   /* interpolation fraction between them */
     double sp_row, sp_col;             /* source spacing (mm) of the row / column axes */
     double new_sp_row, new_sp_col;     /* target spacing (0.3 mm) */
@@ -118,7 +123,10 @@ int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const 
  * (spine_vision/training/datasets/classification.py:247-278) for one channel.
  *
  *  d_slice_idx : int32 [N]   which slice each crop is cut from
- *  d_xy        : float32 [N,2] normalised (x, y) centre in [0,1] (model output)
+ *  d_xy        : float32 [N,2] normalised (x, y) centre in [0,1] (model output; widened to double like the reference's
+ *                float(output_np[i, 0]), cropping.py:481-483) -- or float64 [N,2] with SVB_K3_XY_F64, for centres that are
+ *                Python floats in the reference (get_center_fallback_locations, cropping.py:486-492): int(x * w) must
+ *                see the same double
  *  d_delta_px  : int32 [N,4] (left, right, top, bottom) from mm_to_pixels (cropping.py:149-169)
  *  d_crops     : uint8 [N, ch, cw]
  *  d_crops2    : uint8 [N, oh2, ow2] or NULL
@@ -129,6 +137,7 @@ int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const 
  *                skip the per-crop min-max and only cast -- resize_with_padding on uint8 input.
  */
 #define SVB_K3_NO_NORMALIZE 1
+#define SVB_K3_XY_F64 2
 size_t svb_k3_workspace_bytes(int ch, int cw, int oh2, int ow2);
 int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                          const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
@@ -223,6 +232,72 @@ int svb_ln_patchify(const void* d_x, const float* d_lnw, const float* d_lnb, voi
 int svb_head(const void* d_x, int B, int tokens, int C, const float* n0w, const float* n0b, const float* n1w,
              const float* n1b, const float* w1, const float* b1, int HID, const float* w2, const float* b2,
              int NOUT, float* d_coords, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * K4 -- classifier-input producer.
+ * Replaces, for a batch of (patient, level) samples, construct_3channel + transforms.Resize + ToTensor + Normalize of
+ * ClassificationDataset (spine_vision/training/datasets/classification.py:40-68, 247-278, 283-304; no augmentation):
+ * Pillow resizes each band on its own, so the resized bands are K3's second output and this call is the
+ * [T2, T1, T2] stack (one series three times when the other is missing) + /255 + (x - mean) / std, with torch's fp32
+ * operation order (bit-exact for float32 output).
+ *  d_planes   : uint8 [N, H, W]   resized crops (K3 second output)
+ *  d_t2_idx, d_t1_idx : int32 [P] plane index of each sample's T2 / T1 crop, -1 = the series is missing
+ *               (both -1: the sample is left untouched; the reference raises ValueError, so does the Python mirror)
+ *  h_mean3, h_std3 : HOST float[3], NULL = ImageNet (classification.py:270-273); normalize = 0 skips Normalize
+ *  out_dtype  : SVB_F32 (reference), SVB_BF16 or SVB_FP16 (rounded from the fp32 value)
+ *  d_out      : [P, 3, H, W] of out_dtype
+ */
+int svb_k4_classifier_input(const uint8_t* d_planes, const int32_t* d_t2_idx, const int32_t* d_t1_idx, int P, int H,
+                            int W, const float* h_mean3, const float* h_std3, int normalize, int out_dtype,
+                            void* d_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Host input / output stage: plain host code, no CUDA; h_* are HOST pointers.
+ *
+ * PNG -- replaces Image.fromarray(crop).save(path) (datasets/classification/spider.py:158, phenikaa.py:213):
+ * 8-bit greyscale (PIL mode "L"), non-interlaced, zlib `level` (Pillow's default is 6; out of range = 6), adaptive row
+ * filters.  Parity is on the decoded pixels.  The batch call encodes and writes with `n_threads` workers
+ * (<= 0: one per hardware thread); rcs (optional, [n]) receives the per-file status.
+ */
+size_t svb_png_bound(int h, int w); /* bytes svb_png_encode_gray8 may need for one image */
+int svb_png_encode_gray8(const uint8_t* h_img, int h, int w, int level, uint8_t* h_out, size_t cap, size_t* out_len);
+int svb_png_write_gray8_batch(const uint8_t* h_imgs /* [n, h, w] */, int n, int h, int w, const char* const* paths,
+                              int level, int n_threads, int32_t* rcs);
+
+/* MetaImage (.mha, .mhd + raw / zraw) -- replaces read_medical_image -> read_mha -> sitk.ReadImage for the SPIDER
+ * volumes (spine_vision/io/readers.py:65-73, 128-161; spider.py:115).  Scalar 2-D / 3-D images, binary data, raw or
+ * zlib-compressed, either byte order.  Voxels are converted to float32 in file order = sitk.GetArrayFromImage order
+ * [z][y][x] (integer types up to 24 bits and float32 exactly; wider types are rounded to float32).
+ * direction is image.GetDirection() (row-major 3x3: COLUMN a = direction cosine of image axis a, i.e. the transpose of
+ * the file's TransformMatrix), spacing = GetSpacing(), origin = GetOrigin(), dim = GetSize() (x, y, z).
+ */
+typedef enum svb_mha_type {
+    SVB_MHA_I8 = 0, SVB_MHA_U8 = 1, SVB_MHA_I16 = 2, SVB_MHA_U16 = 3, SVB_MHA_I32 = 4, SVB_MHA_U32 = 5,
+    SVB_MHA_I64 = 6, SVB_MHA_U64 = 7, SVB_MHA_F32 = 8, SVB_MHA_F64 = 9
+} svb_mha_type;
+typedef struct svb_mha_info {
+    int32_t ndim;
+    int32_t dim[3];            /* x, y, z (1 beyond ndim) */
+    double spacing[3];
+    double origin[3];
+    double direction[9];
+    int32_t element_type;      /* svb_mha_type */
+    int32_t element_bytes;
+    int32_t channels;
+    int32_t compressed;
+    int32_t big_endian;
+    int32_t has_spacing;       /* ElementSpacing was given (else ElementSize or 1.0) */
+    int64_t data_offset;       /* byte offset of the voxel data in the header file (ElementDataFile = LOCAL), else -1 */
+    int64_t header_size;       /* HeaderSize of a separate data file (-1 = data at the end of the file) */
+    int64_t compressed_size;   /* CompressedDataSize, 0 = to the end of the file */
+    char data_file[1024];      /* separate data file (resolved against the header's directory), "" when LOCAL */
+} svb_mha_info;
+int svb_mha_read_header(const char* path, svb_mha_info* info);
+int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, size_t dst_elems);
+/* n volumes on n_threads workers into caller-owned (pinned) buffers; rcs (optional, [n]) = per-file status, so that the
+ * caller can skip unreadable series the way the reference's drivers do (spider.py:139-141). */
+int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
+                           const size_t* dst_elems, int n_threads, int32_t* rcs);
 
 #ifdef __cplusplus
 }

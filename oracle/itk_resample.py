@@ -15,7 +15,8 @@ the documented behaviour of the ITK classes the calls resolve to, and is the def
   (``ImageBase::IsInsideBuffer`` / ``TransformPhysicalPointToContinuousIndex``).
 * ``LinearInterpolateImageFunction`` (3-D): ``base = floor(u)``, ``d = u - base``; neighbours outside the buffer
   are clamped to the nearest valid index; the blend is the nested lerp ``v0 + (v1 - v0) * d`` along x, then y,
-  then z, in double; the result is cast to the pixel type (float32 here).
+  then z, in double; the result is cast to the pixel type: float32 as is, integer pixel types by ``static_cast``
+  (``ResampleImageFilter::CastPixelWithBoundsChecking``), i.e. truncation toward zero.
 * ``DICOMOrient(image, "LPI")``: axes are permuted / flipped (no resampling) so that index 0 increases towards
   the patient's Left, index 1 towards Posterior, index 2 towards Inferior; each image axis is assigned the
   anatomical axis its direction cosine is largest along (ITK physical space is LPS).
@@ -87,7 +88,10 @@ def resample_volume(vol_zyx: np.ndarray, spacing_xyz, new_spacing=ISO) -> np.nda
     p0, p1 = plane(z0), plane(z1)
     out = p0 + (p1 - p0) * fz_
     inside = inz[:, None, None] & iny[None, :, None] & inx[None, None, :]
-    return np.where(inside, out, 0.0).astype(v.dtype if np.issubdtype(v.dtype, np.floating) else np.float32)
+    out = np.where(inside, out, 0.0)
+    if np.issubdtype(v.dtype, np.integer):
+        return np.trunc(out).astype(v.dtype)
+    return out.astype(v.dtype)
 
 
 def orient_lpi(arr_zyx: np.ndarray, direction=None) -> np.ndarray:
@@ -110,7 +114,7 @@ def extract_middle_slice_full(vol_zyx, spacing_xyz, direction=None) -> np.ndarra
 
 def resample_middle_sagittal(vol_zyx: np.ndarray, spacing_xyz, direction=None, new_spacing=ISO):
     """Only the plane ``extract_middle_slice(resample_to_isotropic(image))`` keeps, plus ``get_slice_spacing``.
-    Returns ``(slice [nI, nP] float32, (row_spacing, col_spacing))``."""
+    Returns ``(slice [nI, nP] of float32 -- or of the volume's integer dtype --, (row_spacing, col_spacing))``."""
     v = np.asarray(vol_zyx)
     size = (v.shape[2], v.shape[1], v.shape[0])
     ns = new_size(size, spacing_xyz, new_spacing)
@@ -144,6 +148,7 @@ def resample_middle_sagittal(vol_zyx: np.ndarray, spacing_xyz, direction=None, n
     p0, p1 = plane(lo[2]), plane(hi[2])
     out = p0 + (p1 - p0) * fr[2]
     inside = ins[0] & ins[1] & ins[2]
-    out = np.where(inside, out, 0.0).astype(np.float32)
+    out = np.where(inside, out, 0.0)
+    out = (np.trunc(out).astype(v.dtype) if np.issubdtype(v.dtype, np.integer) else out.astype(np.float32))
     out = np.broadcast_to(out, (ns[a_row], ns[a_col]))
     return np.ascontiguousarray(out), (float(new_spacing[a_row]), float(new_spacing[a_col]))

@@ -13,7 +13,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SPINE_B200_LIB", _PKG / "libspine_b200.so"))
 
-SVB_BF16, SVB_FP16 = 0, 1
+SVB_BF16, SVB_FP16, SVB_F32 = 0, 1, 2
 DTYPES = {"bf16": SVB_BF16, "bfloat16": SVB_BF16, "fp16": SVB_FP16, "float16": SVB_FP16, "half": SVB_FP16}
 KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 
@@ -26,6 +26,9 @@ EXPORTS = (
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
     "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused",
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
+    "svb_k4_classifier_input",
+    "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch",
+    "svb_mha_read_header", "svb_mha_read_f32", "svb_mha_read_batch_f32",
 )
 
 
@@ -33,6 +36,15 @@ class SvbError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libspine_b200 error {code}: {msg}")
         self.code = code
+
+
+class MhaInfo(C.Structure):
+    """``svb_mha_info`` (include/spine_b200.h)."""
+
+    _fields_ = [("ndim", C.c_int32), ("dim", C.c_int32 * 3), ("spacing", C.c_double * 3), ("origin", C.c_double * 3),
+                ("direction", C.c_double * 9), ("element_type", C.c_int32), ("element_bytes", C.c_int32), ("channels", C.c_int32),
+                ("compressed", C.c_int32), ("big_endian", C.c_int32), ("has_spacing", C.c_int32), ("data_offset", C.c_int64),
+                ("header_size", C.c_int64), ("compressed_size", C.c_int64), ("data_file", C.c_char * 1024)]
 
 
 class WeightDesc(C.Structure):
@@ -99,6 +111,20 @@ def load() -> C.CDLL:
     lib.svb_ln_patchify.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_head.restype = C.c_int
     lib.svb_head.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, i32, vp]
+    lib.svb_k4_classifier_input.restype = C.c_int
+    lib.svb_k4_classifier_input.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, i32, i32, vp, vp]
+    lib.svb_png_bound.restype = sz
+    lib.svb_png_bound.argtypes = [i32, i32]
+    lib.svb_png_encode_gray8.restype = C.c_int
+    lib.svb_png_encode_gray8.argtypes = [vp, i32, i32, i32, vp, sz, C.POINTER(sz)]
+    lib.svb_png_write_gray8_batch.restype = C.c_int
+    lib.svb_png_write_gray8_batch.argtypes = [vp, i32, i32, i32, C.POINTER(C.c_char_p), i32, i32, vp]
+    lib.svb_mha_read_header.restype = C.c_int
+    lib.svb_mha_read_header.argtypes = [C.c_char_p, C.POINTER(MhaInfo)]
+    lib.svb_mha_read_f32.restype = C.c_int
+    lib.svb_mha_read_f32.argtypes = [C.c_char_p, C.POINTER(MhaInfo), vp, sz]
+    lib.svb_mha_read_batch_f32.restype = C.c_int
+    lib.svb_mha_read_batch_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(MhaInfo), C.POINTER(vp), C.POINTER(sz), i32, vp]
     _lib = lib
     return lib
 

@@ -176,7 +176,7 @@ class CropContext:
         dev = pool.data.device
         h, w = pool.shapes[0]
         xy_host = [[float(self.ivd_locations[i][0]), float(self.ivd_locations[i][1])] for i in levels]
-        xy = torch.tensor(xy_host, dtype=torch.float32).to(dev)
+        xy = torch.tensor(xy_host, dtype=torch.float64).to(dev)  # the Python floats the caller gave: int(x * w) sees the same double
         idx = torch.zeros(len(levels), dtype=torch.int32, device=dev)
         l, r, t, b = (int(v) for v in self.crop_delta_px)
         delta = torch.tensor([[l, r, t, b]] * len(levels), dtype=torch.int32).to(dev)

@@ -1,0 +1,389 @@
+// svb_hostio.cpp -- host input / output stage either side of the GPU path.
+// Plain C++ (no CUDA): a MetaImage (.mha / .mhd) decoder that fills caller-owned (pinned) float32 buffers, and an 8-bit
+// greyscale PNG encoder, both fanned out over a small thread pool so that the host side keeps up with the GPU.
+//
+//   reference                                                        here
+//   read_medical_image -> read_mha -> sitk.ReadImage                 svb_mha_read_header / svb_mha_read_f32(_batch)
+//     (io/readers.py:65-73, 128-161; spider.py:115)
+//   Image.fromarray(crop).save(path)   (PNG "L", zlib level 6)       svb_png_encode_gray8 / svb_png_write_gray8_batch
+//     (datasets/classification/spider.py:158, phenikaa.py:213)
+//
+// PNG parity is on the DECODED pixels (the file bytes depend on the encoder's filter heuristics and are not part of the
+// reference's contract: ClassificationDataset re-opens the files with PIL, training/datasets/classification.py:288-294).
+#include <zlib.h>
+
+#include <atomic>
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/spine_b200.h"
+
+namespace svb {
+int set_error(int code, const char* fmt, ...);  // svb_common.cu (thread-local message)
+}
+using svb::set_error;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------ thread fan-out
+template <typename F>
+void parallel_for(int n, int n_threads, F&& fn) {
+    if (n <= 0) return;
+    int nt = n_threads > 0 ? n_threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > n) nt = n;
+    if (nt == 1) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> pool;
+    pool.reserve(nt);
+    for (int t = 0; t < nt; ++t)
+        pool.emplace_back([&] {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
+// ------------------------------------------------------------------------------------------------ PNG
+void put_be32(uint8_t* p, uint32_t v) {
+    p[0] = (uint8_t)(v >> 24); p[1] = (uint8_t)(v >> 16); p[2] = (uint8_t)(v >> 8); p[3] = (uint8_t)v;
+}
+// one chunk: length, type, data, crc(type + data); returns bytes written
+size_t put_chunk(uint8_t* out, const char type[4], const uint8_t* data, uint32_t len) {
+    put_be32(out, len);
+    memcpy(out + 4, type, 4);
+    if (len) memcpy(out + 8, data, len);
+    uint32_t crc = (uint32_t)crc32(0L, out + 4, 4 + len);
+    put_be32(out + 8 + len, crc);
+    return 12 + (size_t)len;
+}
+// PNG filter types 0-4 for one greyscale row (bpp = 1); picks the one with the least sum of |signed residual|
+// (the heuristic the PNG specification recommends); writes [type byte][w residuals] to dst
+void filter_row(const uint8_t* cur, const uint8_t* prev /* may be null */, int w, uint8_t* dst, std::vector<uint8_t>& scratch) {
+    // left / up / up-left neighbours as padded rows, so that every filter is one branch-free loop the compiler vectorises
+    scratch.resize((size_t)3 * (w + 1) + (size_t)4 * w);
+    uint8_t* a = scratch.data();          // a[x] = cur[x-1]
+    uint8_t* b = a + (w + 1);             // b[x] = prev[x]
+    uint8_t* c = b + (w + 1);             // c[x] = prev[x-1]
+    uint8_t* f[5] = {nullptr, c + (w + 1), c + (w + 1) + w, c + (w + 1) + 2 * (size_t)w, c + (w + 1) + 3 * (size_t)w};
+    a[0] = 0;
+    memcpy(a + 1, cur, (size_t)w - 1);
+    if (prev) {
+        memcpy(b, prev, (size_t)w);
+        c[0] = 0;
+        memcpy(c + 1, prev, (size_t)w - 1);
+    } else {
+        memset(b, 0, (size_t)w);
+        memset(c, 0, (size_t)w);
+    }
+    uint32_t sum[5] = {0, 0, 0, 0, 0};
+    for (int x = 0; x < w; ++x) sum[0] += (uint32_t)abs((int)(int8_t)cur[x]);
+    for (int x = 0; x < w; ++x) { const uint8_t r = (uint8_t)(cur[x] - a[x]); f[1][x] = r; sum[1] += (uint32_t)abs((int)(int8_t)r); }
+    for (int x = 0; x < w; ++x) { const uint8_t r = (uint8_t)(cur[x] - b[x]); f[2][x] = r; sum[2] += (uint32_t)abs((int)(int8_t)r); }
+    for (int x = 0; x < w; ++x) { const uint8_t r = (uint8_t)(cur[x] - ((a[x] + b[x]) >> 1)); f[3][x] = r; sum[3] += (uint32_t)abs((int)(int8_t)r); }
+    for (int x = 0; x < w; ++x) {
+        const int aa = a[x], bb = b[x], cc = c[x];
+        const int p = aa + bb - cc, pa = abs(p - aa), pb = abs(p - bb), pc = abs(p - cc);
+        const int pred = (pa <= pb && pa <= pc) ? aa : (pb <= pc ? bb : cc);
+        const uint8_t r = (uint8_t)(cur[x] - pred);
+        f[4][x] = r;
+        sum[4] += (uint32_t)abs((int)(int8_t)r);
+    }
+    int best = 0;
+    for (int t = 1; t < 5; ++t)
+        if (sum[t] < sum[best]) best = t;
+    dst[0] = (uint8_t)best;
+    memcpy(dst + 1, best == 0 ? cur : f[best], (size_t)w);
+}
+
+int png_encode(const uint8_t* img, int h, int w, int level, uint8_t* out, size_t cap, size_t* out_len) {
+    if (!img || !out || !out_len || h <= 0 || w <= 0) return set_error(SVB_ERR_INVALID_ARG, "png: bad arguments (h=%d w=%d)", h, w);
+    if (level < 0 || level > 9) level = 6;
+    const size_t raw_len = (size_t)h * ((size_t)w + 1);
+    std::vector<uint8_t> raw(raw_len), scratch;
+    for (int y = 0; y < h; ++y)
+        filter_row(img + (size_t)y * w, y ? img + (size_t)(y - 1) * w : nullptr, w, raw.data() + (size_t)y * (w + 1), scratch);
+    uLongf zlen = compressBound((uLong)raw_len);
+    std::vector<uint8_t> z(zlen);
+    const int zr = compress2(z.data(), &zlen, raw.data(), (uLong)raw_len, level);
+    if (zr != Z_OK) return set_error(SVB_ERR_IO, "png: zlib compress2 failed (%d)", zr);
+    const size_t need = 8 + (12 + 13) + (12 + (size_t)zlen) + 12;
+    if (cap < need) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "png: output buffer %zu < %zu bytes", cap, need);
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    size_t o = 0;
+    memcpy(out, sig, 8);
+    o += 8;
+    uint8_t ihdr[13];
+    put_be32(ihdr, (uint32_t)w);
+    put_be32(ihdr + 4, (uint32_t)h);
+    ihdr[8] = 8;   // bit depth
+    ihdr[9] = 0;   // colour type 0 = greyscale (PIL mode "L")
+    ihdr[10] = 0;  // deflate
+    ihdr[11] = 0;  // adaptive filtering
+    ihdr[12] = 0;  // no interlace
+    o += put_chunk(out + o, "IHDR", ihdr, 13);
+    o += put_chunk(out + o, "IDAT", z.data(), (uint32_t)zlen);
+    o += put_chunk(out + o, "IEND", nullptr, 0);
+    *out_len = o;
+    return SVB_OK;
+}
+
+int write_file(const char* path, const uint8_t* data, size_t len) {
+    FILE* f = fopen(path, "wb");
+    if (!f) return set_error(SVB_ERR_IO, "cannot open %s for writing: %s", path, strerror(errno));
+    const size_t n = fwrite(data, 1, len, f);
+    const int rc = fclose(f);
+    if (n != len || rc != 0) return set_error(SVB_ERR_IO, "short write to %s", path);
+    return SVB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MetaImage
+std::string trim(const std::string& s) {
+    size_t a = 0, b = s.size();
+    while (a < b && isspace((unsigned char)s[a])) ++a;
+    while (b > a && isspace((unsigned char)s[b - 1])) --b;
+    return s.substr(a, b - a);
+}
+bool truthy(const std::string& v) { return !v.empty() && (v[0] == 'T' || v[0] == 't' || v[0] == '1'); }
+int parse_doubles(const std::string& v, double* out, int max_n) {
+    int n = 0;
+    const char* p = v.c_str();
+    while (n < max_n) {
+        char* e = nullptr;
+        const double d = strtod(p, &e);
+        if (e == p) break;
+        out[n++] = d;
+        p = e;
+    }
+    return n;
+}
+struct MetType { const char* name; int id; int bytes; };
+const MetType kTypes[] = {
+    {"MET_CHAR", SVB_MHA_I8, 1},     {"MET_UCHAR", SVB_MHA_U8, 1},   {"MET_SHORT", SVB_MHA_I16, 2},  {"MET_USHORT", SVB_MHA_U16, 2},
+    {"MET_INT", SVB_MHA_I32, 4},     {"MET_UINT", SVB_MHA_U32, 4},   {"MET_LONG", SVB_MHA_I32, 4},   {"MET_ULONG", SVB_MHA_U32, 4},
+    {"MET_LONG_LONG", SVB_MHA_I64, 8}, {"MET_ULONG_LONG", SVB_MHA_U64, 8}, {"MET_FLOAT", SVB_MHA_F32, 4}, {"MET_DOUBLE", SVB_MHA_F64, 8},
+};
+
+int mha_header(const char* path, svb_mha_info* info) {
+    if (!path || !info) return set_error(SVB_ERR_INVALID_ARG, "mha: null argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    memset(info, 0, sizeof(*info));
+    info->ndim = 0;
+    info->channels = 1;
+    info->data_offset = -1;
+    info->header_size = 0;
+    for (int i = 0; i < 3; ++i) { info->dim[i] = 1; info->spacing[i] = 1.0; info->direction[4 * i] = 1.0; }
+    bool have_type = false, have_dims = false, have_file = false, binary = true;
+    double tm[9];
+    int n_tm = 0;
+    std::string line;
+    for (;;) {
+        line.clear();
+        int c;
+        while ((c = fgetc(f)) != EOF && c != '\n') {
+            line.push_back((char)c);
+            if (line.size() > 8192) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: header line too long (not a MetaImage?)", path); }
+        }
+        if (line.empty() && c == EOF) break;
+        const size_t eq = line.find('=');
+        if (eq == std::string::npos) {
+            if (trim(line).empty()) { if (c == EOF) break; continue; }
+            fclose(f);
+            return set_error(SVB_ERR_FORMAT, "%s: malformed header line '%s'", path, line.substr(0, 60).c_str());
+        }
+        const std::string key = trim(line.substr(0, eq)), val = trim(line.substr(eq + 1));
+        if (key == "NDims") info->ndim = atoi(val.c_str());
+        else if (key == "DimSize") {
+            double d[3] = {1, 1, 1};
+            const int n = parse_doubles(val, d, 3);
+            for (int i = 0; i < 3; ++i) info->dim[i] = i < n ? (int32_t)d[i] : 1;
+            have_dims = n > 0;
+        } else if (key == "ElementSpacing" || key == "ElementSize") {
+            // ElementSpacing wins when both are present (MetaIO)
+            if (key == "ElementSpacing" || !info->has_spacing) {
+                double d[3] = {1, 1, 1};
+                parse_doubles(val, d, 3);
+                for (int i = 0; i < 3; ++i) info->spacing[i] = d[i];
+                if (key == "ElementSpacing") info->has_spacing = 1;
+            }
+        } else if (key == "Offset" || key == "Position" || key == "Origin") parse_doubles(val, info->origin, 3);
+        else if (key == "TransformMatrix" || key == "Orientation" || key == "Rotation") n_tm = parse_doubles(val, tm, 9);
+        else if (key == "ElementNumberOfChannels") info->channels = atoi(val.c_str());
+        else if (key == "BinaryData") binary = truthy(val);
+        else if (key == "BinaryDataByteOrderMSB" || key == "ElementByteOrderMSB") info->big_endian = truthy(val);
+        else if (key == "CompressedData") info->compressed = truthy(val);
+        else if (key == "CompressedDataSize") info->compressed_size = atoll(val.c_str());
+        else if (key == "HeaderSize") info->header_size = atoll(val.c_str());
+        else if (key == "ElementType") {
+            for (const MetType& t : kTypes)
+                if (val == t.name) { info->element_type = t.id; info->element_bytes = t.bytes; have_type = true; }
+            if (!have_type) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: unsupported ElementType %s", path, val.c_str()); }
+        } else if (key == "ElementDataFile") {
+            have_file = true;
+            if (val == "LOCAL") info->data_offset = (int64_t)ftell(f);
+            else {
+                if (val.size() >= sizeof(info->data_file)) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: data file name too long", path); }
+                if (val == "LIST" || val.find('%') != std::string::npos) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: ElementDataFile = %s (per-slice files) is not supported", path, val.c_str()); }
+                std::string p(path);
+                const size_t slash = p.find_last_of('/');
+                const std::string full = (val[0] == '/' || slash == std::string::npos) ? val : p.substr(0, slash + 1) + val;
+                if (full.size() >= sizeof(info->data_file)) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: data file path too long", path); }
+                strcpy(info->data_file, full.c_str());
+            }
+            break;  // ElementDataFile is the last header field by definition
+        }
+    }
+    fclose(f);
+    if (!have_type || !have_dims || !have_file) return set_error(SVB_ERR_FORMAT, "%s: not a MetaImage header (DimSize / ElementType / ElementDataFile missing)", path);
+    if (!binary) return set_error(SVB_ERR_FORMAT, "%s: ASCII MetaImage data is not supported", path);
+    if (info->ndim < 2 || info->ndim > 3) return set_error(SVB_ERR_FORMAT, "%s: NDims = %d (2 or 3 supported)", path, info->ndim);
+    if (info->channels != 1) return set_error(SVB_ERR_FORMAT, "%s: %d channels (scalar images only)", path, info->channels);
+    for (int i = 0; i < 3; ++i)
+        if (info->dim[i] <= 0) return set_error(SVB_ERR_FORMAT, "%s: bad DimSize", path);
+    // ITK: row i of TransformMatrix is the direction cosine of image axis i, i.e. COLUMN i of image.GetDirection()
+    const int nd = info->ndim;
+    if (n_tm >= nd * nd) {
+        for (int i = 0; i < 9; ++i) info->direction[i] = (i % 4 == 0) ? 1.0 : 0.0;
+        for (int i = 0; i < nd; ++i)
+            for (int j = 0; j < nd; ++j) info->direction[j * 3 + i] = tm[i * nd + j];
+    }
+    return SVB_OK;
+}
+
+template <typename S>
+void convert(const uint8_t* src, size_t n, bool swap, float* dst) {
+    for (size_t i = 0; i < n; ++i) {
+        uint8_t b[sizeof(S)];
+        memcpy(b, src + i * sizeof(S), sizeof(S));
+        if (swap)
+            for (size_t k = 0; k < sizeof(S) / 2; ++k) { const uint8_t t = b[k]; b[k] = b[sizeof(S) - 1 - k]; b[sizeof(S) - 1 - k] = t; }
+        S v;
+        memcpy(&v, b, sizeof(S));
+        dst[i] = static_cast<float>(v);
+    }
+}
+
+int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_elems) {
+    if (!path || !info || !dst) return set_error(SVB_ERR_INVALID_ARG, "mha: null argument");
+    const size_t n = (size_t)info->dim[0] * info->dim[1] * info->dim[2];
+    if (dst_elems < n) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "mha: destination holds %zu elements, volume has %zu", dst_elems, n);
+    const size_t raw_bytes = n * (size_t)info->element_bytes;
+    const char* data_path = info->data_offset >= 0 ? path : info->data_file;
+    FILE* f = fopen(data_path, "rb");
+    if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", data_path, strerror(errno));
+    std::vector<uint8_t> raw(raw_bytes);
+    int rc = SVB_OK;
+    if (info->compressed) {
+        // the compressed stream runs to CompressedDataSize, or to the end of the file when the field is absent
+        int64_t start = info->data_offset >= 0 ? info->data_offset : (info->header_size > 0 ? info->header_size : 0);
+        fseek(f, 0, SEEK_END);
+        const int64_t end = (int64_t)ftell(f);
+        int64_t zbytes = info->compressed_size > 0 ? info->compressed_size : end - start;
+        if (zbytes <= 0 || start + zbytes > end) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: compressed data truncated", data_path); }
+        std::vector<uint8_t> z((size_t)zbytes);
+        fseek(f, (long)start, SEEK_SET);
+        if (fread(z.data(), 1, (size_t)zbytes, f) != (size_t)zbytes) { fclose(f); return set_error(SVB_ERR_IO, "%s: short read", data_path); }
+        uLongf out_len = (uLongf)raw_bytes;
+        const int zr = uncompress(raw.data(), &out_len, z.data(), (uLong)zbytes);
+        if (zr != Z_OK || out_len != raw_bytes) rc = set_error(SVB_ERR_FORMAT, "%s: zlib inflate failed (%d) or size mismatch (%lu of %zu bytes)", data_path, zr, (unsigned long)out_len, raw_bytes);
+    } else {
+        int64_t start;
+        if (info->data_offset >= 0) start = info->data_offset;
+        else if (info->header_size == -1) {  // MetaIO: data sits at the end of the file
+            fseek(f, 0, SEEK_END);
+            start = (int64_t)ftell(f) - (int64_t)raw_bytes;
+        } else start = info->header_size;
+        if (start < 0 || fseek(f, (long)start, SEEK_SET) != 0 || fread(raw.data(), 1, raw_bytes, f) != raw_bytes)
+            rc = set_error(SVB_ERR_FORMAT, "%s: raw data truncated (%zu bytes expected)", data_path, raw_bytes);
+    }
+    fclose(f);
+    if (rc) return rc;
+    const uint16_t probe = 1;
+    const bool host_big = *reinterpret_cast<const uint8_t*>(&probe) == 0;
+    const bool swap = (info->big_endian != 0) != host_big && info->element_bytes > 1;
+    switch (info->element_type) {
+        case SVB_MHA_I8: convert<int8_t>(raw.data(), n, false, dst); break;
+        case SVB_MHA_U8: convert<uint8_t>(raw.data(), n, false, dst); break;
+        case SVB_MHA_I16: convert<int16_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_U16: convert<uint16_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_I32: convert<int32_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_U32: convert<uint32_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_I64: convert<int64_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_U64: convert<uint64_t>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_F32: convert<float>(raw.data(), n, swap, dst); break;
+        case SVB_MHA_F64: convert<double>(raw.data(), n, swap, dst); break;
+        default: return set_error(SVB_ERR_FORMAT, "%s: unknown element type %d", path, info->element_type);
+    }
+    return SVB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t svb_png_bound(int h, int w) {
+    if (h <= 0 || w <= 0) return 0;
+    const size_t raw = (size_t)h * ((size_t)w + 1);
+    return 8 + 25 + 12 + (size_t)compressBound((uLong)raw) + 12;
+}
+
+int svb_png_encode_gray8(const uint8_t* h_img, int h, int w, int level, uint8_t* h_out, size_t cap, size_t* out_len) {
+    return png_encode(h_img, h, w, level, h_out, cap, out_len);
+}
+
+int svb_png_write_gray8_batch(const uint8_t* h_imgs, int n, int h, int w, const char* const* paths, int level, int n_threads,
+                              int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!h_imgs || !paths)) || h <= 0 || w <= 0)
+        return set_error(SVB_ERR_INVALID_ARG, "png batch: bad arguments (n=%d h=%d w=%d)", n, h, w);
+    const size_t cap = svb_png_bound(h, w);
+    std::atomic<int> first_bad{-1};
+    std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
+    parallel_for(n, n_threads, [&](int i) {
+        std::vector<uint8_t> buf(cap);
+        size_t len = 0;
+        int rc = png_encode(h_imgs + (size_t)i * h * w, h, w, level, buf.data(), cap, &len);
+        if (rc == SVB_OK) rc = write_file(paths[i], buf.data(), len);
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) {
+            msgs[i] = svb_last_error();  // thread-local in the worker
+            int expect = -1;
+            first_bad.compare_exchange_strong(expect, i);
+        }
+    });
+    const int bad = first_bad.load();
+    if (bad >= 0) return set_error(SVB_ERR_IO, "png batch: image %d failed: %s", bad, msgs[bad].c_str());
+    return SVB_OK;
+}
+
+int svb_mha_read_header(const char* path, svb_mha_info* info) { return mha_header(path, info); }
+
+int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, size_t dst_elems) {
+    return mha_read(path, info, h_dst, dst_elems);
+}
+
+int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
+                           const size_t* dst_elems, int n_threads, int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!paths || !infos || !h_dsts || !dst_elems)))
+        return set_error(SVB_ERR_INVALID_ARG, "mha batch: bad arguments (n=%d)", n);
+    std::atomic<int> n_bad{0};
+    parallel_for(n, n_threads, [&](int i) {
+        const int rc = mha_read(paths[i], &infos[i], h_dsts[i], dst_elems[i]);
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) n_bad.fetch_add(1);
+    });
+    // per-file failures are the caller's to skip (the reference's drivers skip unreadable series: spider.py:139-141)
+    return n_bad.load() ? set_error(SVB_ERR_IO, "mha batch: %d of %d volumes failed (see the per-file codes)", n_bad.load(), n) : SVB_OK;
+}
+
+}  // extern "C"

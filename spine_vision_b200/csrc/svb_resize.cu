@@ -492,8 +492,12 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     const int H = hw[2 * b], W = hw[2 * b + 1];
     if (tid == 0) {
         // cropping.py:338-348: cx = int(x*w), cy = int(y*h) in Python float (double) arithmetic
-        const int cx = (int)__dmul_rn((double)xy[2 * n + 0], (double)W);
-        const int cy = (int)__dmul_rn((double)xy[2 * n + 1], (double)H);
+        // (the model's float32 outputs widened to double, as float(output_np[i, 0]) does at cropping.py:481-483; or doubles
+        //  as given -- SVB_K3_XY_F64 -- for centres that never were float32: the fallback table, user dictionaries)
+        const double xn = (flags & SVB_K3_XY_F64) ? reinterpret_cast<const double*>(xy)[2 * n + 0] : (double)xy[2 * n + 0];
+        const double yn = (flags & SVB_K3_XY_F64) ? reinterpret_cast<const double*>(xy)[2 * n + 1] : (double)xy[2 * n + 1];
+        const int cx = (int)__dmul_rn(xn, (double)W);
+        const int cy = (int)__dmul_rn(yn, (double)H);
         const int left = delta_px[4 * n + 0], right = delta_px[4 * n + 1];
         const int top = delta_px[4 * n + 2], bottom = delta_px[4 * n + 3];
         K3Geom q;
@@ -857,7 +861,8 @@ __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restric
                 const double b = lerp(g(z, hi[1], lo[0]), g(z, hi[1], hi[0]), fr[0]);
                 pl[k] = lerp(a, b, fr[1]);
             }
-            res = (float)lerp(pl[0], pl[1], fr[2]);
+            const double rd = lerp(pl[0], pl[1], fr[2]);
+            res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
         }
         o[p] = res;
     }

@@ -139,6 +139,7 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     """K3: one crop per (slice_idx, xy, delta_px) row.  Device mirror of
     ``CropContext.crop`` -> ``crop_region_horizontal`` (cropping.py:316-404) and, for the
     second output, the classifier's ``Resize`` (training/datasets/classification.py:247-278).
+    ``xy`` is float32 (model output) or float64 (centres that are Python floats in the reference: the fallback table).
     ``inv_affine`` (float64 ``[N,6]`` on the device, from ``cropping.inverse_rotation``) switches on the rotated crop
     mode (``crop_region_rotated``, cropping.py:258-313).
     Returns ``(crops u8 [N,ch,cw], crops2 u8 [N,oh2,ow2] | None, geom int32 [N,8] | None)``."""
@@ -157,7 +158,8 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     geom = torch.empty((N, 8), dtype=torch.int32, device=dev) if return_geom else None
     if N == 0:
         return crops, crops2, geom
-    assert slice_idx.dtype == torch.int32 and xy.dtype == torch.float32 and delta_px.dtype == torch.int32
+    assert slice_idx.dtype == torch.int32 and xy.dtype in (torch.float32, torch.float64) and delta_px.dtype == torch.int32
+    flags = (0 if normalize else 1) | (2 if xy.dtype == torch.float64 else 0)  # SVB_K3_NO_NORMALIZE, SVB_K3_XY_F64
     assert slice_idx.is_contiguous() and xy.is_contiguous() and delta_px.is_contiguous()
     need = lib.svb_k3_workspace_bytes(ch, cw, oh2, ow2)
     ws = _Workspace.get("k3", need, dev)
@@ -167,8 +169,36 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     _lib.check(lib.svb_k3_crop_resample_rotated(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), slice_idx.data_ptr(),
                                                 xy.data_ptr(), delta_px.data_ptr(), _lib.ptr(inv_affine), N, int(max_box_hw[0]),
                                                 int(max_box_hw[1]), ch, cw, crops.data_ptr(), oh2, ow2, _lib.ptr(crops2),
-                                                _lib.ptr(geom), 0 if normalize else 1, wp, wn, _lib.current_stream()))
+                                                _lib.ptr(geom), flags, wp, wn, _lib.current_stream()))
     return crops, crops2, geom
+
+
+_OUT_DTYPES = {torch.float32: _lib.SVB_F32, torch.bfloat16: _lib.SVB_BF16, torch.float16: _lib.SVB_FP16}
+
+
+def classifier_input(planes: torch.Tensor, t2_idx: torch.Tensor, t1_idx: torch.Tensor, normalize: bool = True,
+                     dtype: torch.dtype = torch.float32, mean=None, std=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """K4: ``[T2, T1, T2]`` stack + ``ToTensor`` + ``Normalize`` for a batch of (patient, level) samples from the resized
+    uint8 planes K3 produced.  Device mirror of ``construct_3channel`` + the non-augmenting transform of
+    ``ClassificationDataset`` (training/datasets/classification.py:40-68, 247-278).
+    ``planes`` uint8 ``[N,H,W]``; ``t2_idx`` / ``t1_idx`` int32 ``[P]`` (-1 = series missing).  Returns ``[P,3,H,W]``."""
+    lib = _lib.load()
+    dev = planes.device
+    assert planes.dtype == torch.uint8 and planes.dim() == 3 and planes.is_contiguous()
+    assert t2_idx.dtype == torch.int32 and t1_idx.dtype == torch.int32 and t2_idx.shape == t1_idx.shape
+    P, H, W = int(t2_idx.shape[0]), int(planes.shape[1]), int(planes.shape[2])
+    if out is None:
+        out = torch.empty((P, 3, H, W), dtype=dtype, device=dev)
+    assert out.is_contiguous() and out.dtype == dtype and out.numel() == P * 3 * H * W
+    mean_c = (C.c_float * 3)(*mean) if mean is not None else None
+    std_c = (C.c_float * 3)(*std) if std is not None else None
+    for p0 in range(0, P, 65535):  # grid.y limit of one launch
+        n = min(65535, P - p0)
+        _lib.check(lib.svb_k4_classifier_input(planes.data_ptr(), t2_idx[p0:].data_ptr(), t1_idx[p0:].data_ptr(), n, H, W,
+                                               C.addressof(mean_c) if mean_c is not None else None,
+                                               C.addressof(std_c) if std_c is not None else None, int(bool(normalize)),
+                                               _OUT_DTYPES[dtype], out[p0:].data_ptr(), _lib.current_stream()))
+    return out
 
 
 class LocalizationEngine:

@@ -92,7 +92,7 @@ def localize_and_crop(pool: ops.SlicePool, model: LocalizationModel | None, crop
         coords = model.predict_u8(planes, times)
     else:
         fb = get_center_fallback_locations()
-        one = torch.tensor([fb[i] for i in range(NUM_LEVELS)], dtype=torch.float32)
+        one = torch.tensor([fb[i] for i in range(NUM_LEVELS)], dtype=torch.float64)  # Python floats in the reference, not model outputs
         coords = one.unsqueeze(0).repeat(B, 1, 1).to(dev)
     crops, crops2, _ = crop_levels(pool, coords, crop_delta_mm, spacings, crop_size, second_size, mode=crop_mode,
                                    last_disc_angle_boost=last_disc_angle_boost)
@@ -215,13 +215,17 @@ class StreamedLocalizer:
             if self.model is not None:
                 planes = ops.normalize_resize(pool, self.image_size)
                 self.model.predict_u8(planes, out=coords)
-            else:
+            xy = coords.view(n * L, 2)
+            if self.model is None:
+                # the fallback centres are Python floats in the reference: K3 gets them as float64 (int(x * w) sees the same double)
                 fb = get_center_fallback_locations()
-                coords.copy_(torch.tensor([fb[i] for i in range(L)], dtype=torch.float32, device=dev).unsqueeze(0).expand(n, L, 2))
+                fb64 = torch.tensor([fb[i] for i in range(L)], dtype=torch.float64, device=dev).unsqueeze(0).expand(n, L, 2)
+                coords.copy_(fb64)
+                xy = fb64.reshape(n * L, 2).contiguous()
             dl = deltas[i0:i1]
             mh, mw = pool.max_hw
             max_box = (min(max(1, max(d[2] + d[3] for d in dl)), mh), min(max(1, max(d[0] + d[1] for d in dl)), mw))
-            ops.crop_resample(pool, idx_d[: n * L], coords.view(n * L, 2), delta_d[i0 * L : i1 * L], max_box, self.crop_size,
+            ops.crop_resample(pool, idx_d[: n * L], xy, delta_d[i0 * L : i1 * L], max_box, self.crop_size,
                               self.second_size, out=o["crops"][i0:i1].view(n * L, *self.crop_size),
                               out2=None if self.second_size is None else o["crops2"][i0:i1].view(n * L, *self.second_size))
             done[j].record(compute)

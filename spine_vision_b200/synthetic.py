@@ -149,3 +149,83 @@ def random_state_dict(variant: str = "base", seed: int = 0, num_levels: int = 5,
     sd["head.2.weight"], sd["head.2.bias"] = tn(256, dims[3]), torch.zeros(256)
     sd["head.5.weight"], sd["head.5.bias"] = tn(num_levels * 2, 256), torch.zeros(num_levels * 2)
     return sd
+
+
+# ------------------------------------------------------------------------------------------ synthetic dataset trees
+_MET_TYPES = {"int8": "MET_CHAR", "uint8": "MET_UCHAR", "int16": "MET_SHORT", "uint16": "MET_USHORT", "int32": "MET_INT",
+              "uint32": "MET_UINT", "int64": "MET_LONG_LONG", "uint64": "MET_ULONG_LONG", "float32": "MET_FLOAT",
+              "float64": "MET_DOUBLE"}
+
+
+def write_metaimage(path, array_zyx: np.ndarray, spacing_xyz, direction=None, origin=(0.0, 0.0, 0.0), compressed: bool = True,
+                    big_endian: bool = False, separate_raw: bool = False) -> None:
+    """Write a MetaImage the way ITK's MetaImageIO lays it out (for synthetic test / bench trees only).  ``direction`` is
+    ``image.GetDirection()`` (row-major, column a = cosine of image axis a); the file's TransformMatrix is its transpose."""
+    import zlib
+    from pathlib import Path
+
+    path = Path(path)
+    a = np.ascontiguousarray(array_zyx)
+    nd = a.ndim
+    d = np.eye(nd) if direction is None else np.asarray(direction, dtype=np.float64).reshape(nd, nd)
+    raw = a.astype(a.dtype.newbyteorder(">" if big_endian else "<"), copy=False).tobytes()
+    payload = zlib.compress(raw, 6) if compressed else raw
+    fmt = lambda vals: " ".join(repr(float(v)) if not float(v).is_integer() else str(int(v)) for v in vals)  # noqa: E731
+    lines = ["ObjectType = Image", f"NDims = {nd}", "BinaryData = True", f"BinaryDataByteOrderMSB = {big_endian}",
+             f"CompressedData = {compressed}"]
+    if compressed:
+        lines.append(f"CompressedDataSize = {len(payload)}")
+    lines += [f"TransformMatrix = {fmt(d.T.ravel())}", f"Offset = {fmt(origin[:nd])}", f"CenterOfRotation = {fmt([0] * nd)}",
+              "AnatomicalOrientation = RAI", f"ElementSpacing = {fmt(spacing_xyz[:nd])}",
+              f"DimSize = {' '.join(str(s) for s in a.shape[::-1])}", f"ElementType = {_MET_TYPES[a.dtype.name]}"]
+    if separate_raw:
+        raw_name = path.with_suffix(".zraw" if compressed else ".raw").name
+        lines.append(f"ElementDataFile = {raw_name}")
+        path.write_text("\n".join(lines) + "\n")
+        (path.parent / raw_name).write_bytes(payload)
+    else:
+        lines.append("ElementDataFile = LOCAL")
+        path.write_bytes(("\n".join(lines) + "\n").encode("ascii") + payload)
+
+
+SPIDER_LABEL_COLUMNS = ["Patient", "IVD label", "Modic", "UP endplate", "LOW endplate", "Spondylolisthesis", "Disc herniation",
+                        "Disc narrowing", "Disc bulging", "Pfirrman grade"]
+
+
+def make_spider_tree(base_path, n_patients: int = 3, seed: int = 0, in_plane=(96, 88), n_slices: int = 9, dtype="int16",
+                     spacing=(0.8, 0.75, 3.3), missing_t1=(2,)):
+    """A SPIDER-shaped raw dataset under ``base_path/raw/SPIDER`` (what ``process_spider`` walks, spider.py:62-108):
+    ``images/{patient}_{t1,t2}.mha`` (sagittal stacks: image x -> Posterior, y -> Inferior, z -> Left, integer pixels,
+    zlib-compressed) and ``radiological_gradings.csv`` with SPIDER's level numbering (1 = L5/S1).  Patients listed in
+    ``missing_t1`` have no T1 file; the last patient carries a level 7 row (ignored by the drivers) and lacks level 1.
+    Deterministic in (seed, sizes); returns the list of patient ids."""
+    import csv
+    from pathlib import Path
+
+    root = Path(base_path) / "raw" / "SPIDER"
+    (root / "images").mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(50_000 + seed)
+    h, w = in_plane
+    pids = [int(p) for p in (1 + np.arange(n_patients) * 3)]
+    rows = []
+    for k, pid in enumerate(pids):
+        for si, suffix in enumerate(("t1", "t2")):
+            if suffix == "t1" and k in missing_t1:
+                continue
+            vol, _, direction = make_volume(1000 * seed + 10 * pid + si, n_slices, h, w, spacing)
+            vol = vol * (1.0 if suffix == "t2" else 0.6)
+            arr = np.clip(np.rint(vol), 0, 32000).astype(dtype) if np.issubdtype(np.dtype(dtype), np.integer) else vol.astype(dtype)
+            write_metaimage(root / "images" / f"{pid}_{suffix}.mha", arr, spacing, direction, origin=(-12.5, 30.0, 7.25))
+        levels = list(range(1, 6))
+        if k == n_patients - 1:
+            levels = [2, 3, 4, 5, 7]
+        for lvl in levels:
+            rows.append({"Patient": pid, "IVD label": lvl, "Modic": int(rng.integers(0, 4)), "UP endplate": int(rng.integers(0, 2)),
+                         "LOW endplate": int(rng.integers(0, 2)), "Spondylolisthesis": int(rng.integers(0, 2)),
+                         "Disc herniation": int(rng.integers(0, 2)), "Disc narrowing": int(rng.integers(0, 2)),
+                         "Disc bulging": int(rng.integers(0, 2)), "Pfirrman grade": int(rng.integers(1, 6))})
+    with open(root / "radiological_gradings.csv", "w", newline="") as f:
+        wr = csv.DictWriter(f, fieldnames=SPIDER_LABEL_COLUMNS)
+        wr.writeheader()
+        wr.writerows(rows)
+    return pids

@@ -27,7 +27,7 @@ class K0Series(C.Structure):
     _fields_ = [("vol_off", C.c_int64), ("out_off", C.c_int64), ("nx", C.c_int32), ("ny", C.c_int32), ("nz", C.c_int32),
                 ("ax_row", C.c_int32), ("ax_col", C.c_int32), ("ax_fix", C.c_int32), ("flip_row", C.c_int32),
                 ("flip_col", C.c_int32), ("out_h", C.c_int32), ("out_w", C.c_int32), ("fix_lo", C.c_int32),
-                ("fix_hi", C.c_int32), ("fix_inside", C.c_int32), ("pad", C.c_int32), ("fix_frac", C.c_double),
+                ("fix_hi", C.c_int32), ("fix_inside", C.c_int32), ("integer_pixels", C.c_int32), ("fix_frac", C.c_double),
                 ("sp_row", C.c_double), ("sp_col", C.c_double), ("new_sp_row", C.c_double), ("new_sp_col", C.c_double)]
 
 
@@ -58,8 +58,13 @@ class MidplanePlan:
     desc: dict
 
 
-def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spacing=ISOTROPIC_SPACING) -> MidplanePlan:
+def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spacing=ISOTROPIC_SPACING,
+                  integer_pixels: bool | None = None) -> MidplanePlan:
+    """``integer_pixels``: the image's pixel type is integral, so ITK casts every resampled value back to it (truncation);
+    None = decide from the array dtype."""
     v = np.asarray(volume_zyx)
+    if integer_pixels is None:
+        integer_pixels = bool(np.issubdtype(v.dtype, np.integer))
     if v.ndim != 3:
         raise ValueError("plan_midplane takes a 3-D volume in sitk.GetArrayFromImage order [z, y, x]")
     size = (v.shape[2], v.shape[1], v.shape[0])
@@ -80,19 +85,20 @@ def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spaci
     dims[a_fix] = slab.shape[arr_axis]
     desc = dict(nx=dims[0], ny=dims[1], nz=dims[2], ax_row=a_row, ax_col=a_col, ax_fix=a_fix, flip_row=int(flip[2]),
                 flip_col=int(flip[1]), out_h=ns[a_row], out_w=ns[a_col], fix_lo=0, fix_hi=slab.shape[arr_axis] - 1,
-                fix_inside=int(inside), fix_frac=float(u - base), sp_row=float(spacing_xyz[a_row]), sp_col=float(spacing_xyz[a_col]),
+                fix_inside=int(inside), integer_pixels=int(bool(integer_pixels)), fix_frac=float(u - base), sp_row=float(spacing_xyz[a_row]), sp_col=float(spacing_xyz[a_col]),
                 new_sp_row=float(new_spacing[a_row]), new_sp_col=float(new_spacing[a_col]))
     return MidplanePlan((ns[a_row], ns[a_col]), (float(new_spacing[a_row]), float(new_spacing[a_col])), slab, desc)
 
 
-def midplane_resample(volumes, spacings, directions=None, device="cuda:0"):
+def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integer_pixels=None):
     """K0 over a batch: list of ``[z, y, x]`` arrays + ``image.GetSpacing()`` (+ ``GetDirection()``) per series ->
     ``(ops.SlicePool of the middle isotropic sagittal slices, [(row_spacing, col_spacing)])``."""
     dev = ops._require_cuda(device)
     lib = _lib.load()
     B = len(volumes)
     directions = directions if directions is not None else [None] * B
-    plans = [plan_midplane(v, s, d) for v, s, d in zip(volumes, spacings, directions)]
+    integer_pixels = integer_pixels if integer_pixels is not None else [None] * B
+    plans = [plan_midplane(v, s, d, integer_pixels=ip) for v, s, d, ip in zip(volumes, spacings, directions, integer_pixels)]
     shapes = [p.out_hw for p in plans]
     out_offs, out_total = ops.SlicePool.layout(shapes)
     vol_offs, vol_total = [], 0

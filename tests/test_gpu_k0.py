@@ -56,3 +56,26 @@ def test_k0_config1_series_and_pipeline():
 
     b = pipeline.localize_and_crop(ops.SlicePool.from_numpy([want], dev()), model, (50, 20, 30, 30), (128, 128))
     assert torch.equal(a.coords, b.coords) and torch.equal(a.crops, b.crops) and torch.equal(a.crops2, b.crops2)
+
+
+def test_k0_integer_pixel_types_truncate_like_itk_cast():
+    """Integer-typed volumes (what SPIDER ships): ITK casts every interpolated value back to the pixel type
+    (static_cast = truncation toward zero); negative values included."""
+    rng = np.random.default_rng(9)
+    vols, sps, dirs, want = [], [], [], []
+    for dt, lo, hi in (("int16", -900, 2500), ("uint16", 0, 4000), ("uint8", 0, 256)):
+        for name in ("sagittal", "oblique"):
+            v = rng.integers(lo, hi, size=(7, 41, 37)).astype(dt)
+            vols.append(v); sps.append((0.62, 0.71, 3.9)); dirs.append(DIRS[name])
+            w, _ = itk.resample_middle_sagittal(v, sps[-1], dirs[-1])
+            assert w.dtype == np.dtype(dt)
+            want.append(w)
+    pool, _ = volumes.midplane_resample(vols, sps, dirs, dev())  # integer_pixels inferred from the dtype
+    flat, offs = pool.data.cpu().numpy(), pool.offs.cpu().numpy()
+    for i, w in enumerate(want):
+        h_, w_ = pool.shapes[i]
+        got = flat[offs[i] : offs[i] + h_ * w_].reshape(h_, w_)
+        assert np.array_equal(got, w.astype(np.float32)), f"series {i}"
+    # the same data declared float keeps the fractions
+    pool_f, _ = volumes.midplane_resample([vols[0].astype(np.float32)], sps[:1], dirs[:1], dev())
+    assert (pool_f.data[: pool.shapes[0][0] * pool.shapes[0][1]].cpu().numpy() % 1 != 0).any()

@@ -1,0 +1,152 @@
+"""CPU: the host input / output stage -- native MetaImage decoder vs oracle/metaimage.py, native PNG
+encoder vs Pillow's decoder, and the dataset driver's host logic (work list, records, CSV, resume) vs the CSVs the
+reference's OWN driver wrote (tests/golden/host_dataset.npz, oracle/make_golden_host.py).  No GPU work here."""
+import io
+import zlib
+
+import numpy as np
+import pytest
+from PIL import Image
+
+from conftest import GOLDEN
+from oracle import metaimage
+from spine_vision_b200 import _lib, dataset, hostio, synthetic
+
+
+@pytest.mark.parametrize("dtype", ["int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["local-z", "local-raw", "mhd-raw", "mhd-zraw", "big-endian"])
+def test_metaimage_reader_matches_oracle(tmp_path, dtype, layout):
+    rng = np.random.default_rng(zlib.crc32(f"{dtype}-{layout}".encode()))
+    info = np.iinfo(dtype) if np.issubdtype(np.dtype(dtype), np.integer) else None
+    lo, hi = (max(info.min, -(2**23)), min(info.max, 2**23)) if info else (-1000, 1000)
+    arr = (rng.integers(lo, hi, size=(5, 13, 11)) if info else rng.normal(0, 300, size=(5, 13, 11))).astype(dtype)
+    direction = (0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+    path = tmp_path / ("v.mhd" if layout.startswith("mhd") else "v.mha")
+    synthetic.write_metaimage(path, arr, (0.7, 0.65, 4.4), direction, origin=(1.5, -2.0, 3.25), compressed=layout in ("local-z", "mhd-zraw", "big-endian"),
+                              big_endian=layout == "big-endian", separate_raw=layout.startswith("mhd"))
+    want = metaimage.read(path)
+    got = hostio.read_medical_image(path)
+    assert got.array.dtype == np.float32 and got.array.shape == arr.shape
+    assert np.array_equal(got.array, want.array.astype(np.float32)) and np.array_equal(want.array, arr)
+    assert got.GetSpacing() == want.GetSpacing() == (0.7, 0.65, 4.4) and got.GetOrigin() == want.GetOrigin()
+    assert np.array_equal(np.array(got.GetDirection()), np.array(want.GetDirection())) and got.GetDirection() == direction
+    assert got.GetSize() == want.GetSize() == (11, 13, 5)
+    assert got.integer_pixels == (info is not None)
+
+
+def test_metaimage_2d_and_errors(tmp_path):
+    a2 = np.arange(12, dtype=np.uint16).reshape(3, 4)
+    synthetic.write_metaimage(tmp_path / "p.mha", a2, (0.5, 0.25), compressed=False)
+    v = hostio.read_medical_image(tmp_path / "p.mha")
+    assert v.array.shape == (1, 3, 4) and np.array_equal(v.array[0], a2) and v.spacing[:2] == (0.5, 0.25)
+    with pytest.raises(FileNotFoundError):
+        hostio.read_medical_image(tmp_path / "missing.mha")  # io/readers.py:143-144
+    (tmp_path / "x.bin").write_bytes(b"123")
+    with pytest.raises(ValueError, match="Unsupported format"):
+        hostio.read_medical_image(tmp_path / "x.bin")  # io/readers.py:160-161
+    (tmp_path / "series").mkdir()
+    with pytest.raises(hostio.UnsupportedFormatError):
+        hostio.read_medical_image(tmp_path / "series")  # DICOM directory: no decoder in this build
+    (tmp_path / "bad.mha").write_text("hello\nworld\n")
+    with pytest.raises(_lib.SvbError):
+        hostio.read_medical_image(tmp_path / "bad.mha")
+    # truncated compressed payload
+    synthetic.write_metaimage(tmp_path / "t.mha", np.zeros((4, 8, 8), np.int16), (1, 1, 1))
+    blob = (tmp_path / "t.mha").read_bytes()
+    (tmp_path / "t.mha").write_bytes(blob[:-7])
+    with pytest.raises(_lib.SvbError):
+        hostio.read_medical_image(tmp_path / "t.mha")
+
+
+def test_read_volumes_batch_skips_bad_files(tmp_path):
+    pids = synthetic.make_spider_tree(tmp_path, n_patients=3, seed=3)
+    img = tmp_path / "raw" / "SPIDER" / "images"
+    paths = [img / f"{pids[0]}_t2.mha", tmp_path / "nope.mha", img / f"{pids[1]}_t1.mha", tmp_path / "raw" / "SPIDER" / "radiological_gradings.csv"]
+    vols, errs = hostio.read_volumes(paths, n_threads=3, pin=False)
+    assert [v is not None for v in vols] == [True, False, True, False] and errs[0] is None and "does not exist" in errs[1]
+    for p, v in zip(paths, vols):
+        if v is not None:
+            want = metaimage.read(p)
+            assert np.array_equal(v.array, want.array.astype(np.float32)) and v.spacing == want.GetSpacing() and v.integer_pixels
+
+
+@pytest.mark.parametrize("shape", [(128, 128), (256, 256), (1, 1), (3, 1), (1, 5), (37, 129)])
+def test_png_encoder_decodes_identically(shape, tmp_path):
+    rng = np.random.default_rng(shape[0] * 1000 + shape[1])
+    h, w = shape
+    ramp = (np.add.outer(np.arange(h), 2 * np.arange(w)) % 256).astype(np.uint8)
+    for img in (rng.integers(0, 256, size=shape, dtype=np.uint8), ramp, np.zeros(shape, np.uint8), np.full(shape, 255, np.uint8)):
+        blob = hostio.encode_png(img)
+        pil = Image.open(io.BytesIO(blob))
+        assert pil.mode == "L" and pil.size == (w, h)  # what ClassificationDataset re-opens (classification.py:288-294)
+        assert np.array_equal(np.asarray(pil), img)
+    imgs = np.stack([np.roll(ramp, k, axis=0) for k in range(9)])
+    paths = [tmp_path / f"c{k}.png" for k in range(9)]
+    hostio.write_png_batch(imgs, paths, n_threads=4)
+    for k, p in enumerate(paths):
+        assert np.array_equal(np.asarray(Image.open(p).convert("L")), imgs[k])
+    with pytest.raises(_lib.SvbError):
+        hostio.write_png_batch(imgs[:1], [tmp_path / "no_such_dir" / "x.png"])
+
+
+def test_filename_parsing_and_levels():
+    assert dataset.parse_image_filename("spider_12_sag_t2_L3.png") == dataset.ParsedImageInfo("spider", "12", "sag_t2", 3, "spider_12_sag_t2_L3.png")
+    p = dataset.parse_image_filename("phenikaa_A_b_01_sag_t1_L5.png")
+    assert p is not None and p.patient_id == "A_b_01" and p.series_type == "sag_t1"
+    for bad in ("spider_1_ax_t2_L3.png", "other_1_sag_t2_L3.png", "spider_1_sag_t2_L3.jpg", "spider_1_sag_t2_L33.png"):
+        assert dataset.parse_image_filename(bad) is None
+    assert [dataset.convert_spider_to_phenikaa_level(k) for k in (1, 5)] == [5, 1]  # spider.py:31-42
+    row = {"Modic_0": "0", "Modic_1": "0", "Modic_2": "1", "Modic_3": "1", "Pfirrman grade": "4"}
+    rec = dataset.make_record("phenikaa", "phenikaa_p_sag_t2_L1.png", "p", 1, "sag_t2", row)
+    assert rec.modic == 2 and rec.pfirrmann_grade == 4 and rec.disc_bulging == 0  # phenikaa.py:88-108
+
+
+def _lines(text):
+    return text.strip().split("\n")
+
+
+def test_work_list_records_and_csv_match_reference_driver(tmp_path):
+    """The host logic alone (no pixels): jobs in the reference's iteration order, records, CSV text == what the
+    reference's create_classification_dataset wrote for the same tree; then its resume behaviour."""
+    g = np.load(GOLDEN / "host_dataset.npz")
+    synthetic.make_spider_tree(tmp_path, seed=0)
+    cfg = dataset.ClassificationDatasetConfig(base_path=tmp_path, output_name="cls", crop_size=(128, 128))
+    assert cfg.spider_path == tmp_path / "raw" / "SPIDER" and cfg.output_path == tmp_path / "processed" / "cls"
+    jobs = dataset.collect_spider_jobs(cfg, set())
+    assert [(j.patient_id, j.series_type) for j in jobs] == [("1", "sag_t1"), ("1", "sag_t2"), ("4", "sag_t1"), ("4", "sag_t2"), ("7", "sag_t2")]
+    assert sorted(jobs[-1].levels) == [1, 2, 3, 4]  # SPIDER level 7 -> -1 is dropped, dataset level 5 has no row
+    recs = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, lvl), j.patient_id, lvl, j.series_type, row)
+            for j in jobs for lvl, row in j.levels.items()]
+    dataset.write_annotations(tmp_path / "a.csv", recs)
+    assert (tmp_path / "a.csv").read_text() == g["horizontal_csv"].item()
+    assert dataset.collect_phenikaa_jobs(cfg, set()) == []  # no Phenikaa tree: warns and returns nothing (phenikaa.py:137-139)
+
+    # resume: every image exists except two -> only those two levels are jobs; recovered records come from the label file
+    names = [str(n) for n in g["horizontal_names"]]
+    deleted = [str(n) for n in g["delete_for_resume"]]
+    images = cfg.output_path / "images"
+    images.mkdir(parents=True)
+    for n in names:
+        if n not in deleted:
+            (images / n).write_bytes(b"")
+    existing = dataset.scan_existing_images(images)
+    assert sorted(e.filename for e in existing) == sorted(set(names) - set(deleted))
+    jobs2 = dataset.collect_spider_jobs(cfg, {f"images/{e.filename}" for e in existing})
+    assert [(j.patient_id, j.series_type, sorted(j.levels)) for j in jobs2] == [("4", "sag_t1", [2]), ("7", "sag_t2", [4])]
+    ph, sp = dataset.recover_annotations(existing, cfg.spider_path / "radiological_gradings.csv", cfg.phenikaa_path / "radiological_labels.csv")
+    new = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, lvl), j.patient_id, lvl, j.series_type, row)
+           for j in jobs2 for lvl, row in j.levels.items()]
+    dataset.write_annotations(tmp_path / "b.csv", ph + sp + new)
+    got, want = _lines((tmp_path / "b.csv").read_text()), _lines(g["resume_csv"].item())
+    # recovered rows follow the directory listing order (spider.py:237: glob), which is filesystem-defined: compare as a set;
+    # the new rows come last, in job order
+    assert got[0] == want[0] and got[-2:] == want[-2:] and sorted(got) == sorted(want) and ph == []
+
+
+def test_metaimage_writer_is_plain_zlib(tmp_path):
+    arr = np.arange(2 * 3 * 4, dtype=np.int16).reshape(2, 3, 4)
+    synthetic.write_metaimage(tmp_path / "w.mha", arr, (1, 2, 3))
+    blob = (tmp_path / "w.mha").read_bytes()
+    head, data = blob.split(b"ElementDataFile = LOCAL\n", 1)
+    assert b"DimSize = 4 3 2" in head and b"ElementType = MET_SHORT" in head
+    assert np.array_equal(np.frombuffer(zlib.decompress(data), dtype="<i2").reshape(2, 3, 4), arr)
