@@ -114,3 +114,55 @@ def test_streamed_driver_equals_resident_path():
     fc, fk, fk2 = fb.run(series)
     ref_fb = pipeline.localize_and_crop(pool, None, (50, 20, 30, 30), (128, 128), (512, 512), None)
     assert fk2 is None and np.array_equal(fk.numpy(), ref_fb.crops.cpu().numpy()) and np.allclose(fc.numpy(), ref_fb.coords.cpu().numpy())
+
+
+@pytest.mark.parametrize("image_size", [(768, 768), (512, 768), (640, 384)])
+def test_model_other_input_sizes_config5(image_size):
+    """BASELINE config 5 runs the localizer at 768x768; image_size is a config field (config.py:53-54), so any multiple
+    of 32 must work, square or not.  Same normalised tolerance as the 512^2 gate (0.5 px / 512)."""
+    om = make_model("base", seed=0)
+    slices = [synthetic.make_iso_slice(50, 1195, 1195), synthetic.make_iso_slice(51, 700, 900)]
+    want = []
+    for sl in slices:
+        _, t = ref.preprocess_slice(sl, image_size)
+        with torch.no_grad():
+            want.append(om(t.unsqueeze(0))[0].numpy())
+    want = np.stack(want)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16")
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    planes = ops.normalize_resize(pool, image_size)
+    for i, sl in enumerate(slices):
+        plane, _ = ref.preprocess_slice(sl, image_size)
+        assert np.array_equal(planes[i].cpu().numpy(), plane)
+    got = model.predict_u8(planes).cpu().numpy()
+    err = np.abs(got - want).max()
+    print(f"[coords] image_size={image_size}: max normalised error {err:.2e} ({err * 512:.3f} px at 512)")
+    assert err <= 0.5 / 512
+
+
+def test_config3_ragged_volumes_with_their_own_spacing():
+    """BASELINE config 3 in miniature: series of different in-plane size AND spacing (so different iso sizes and the same
+    0.3 mm crop box), from the volume on, against the oracle chain itk_resample -> preprocess -> fp32 model -> crop."""
+    from oracle import itk_resample as itk
+
+    om = make_model("base", seed=0)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16")
+    rng = np.random.default_rng(3)
+    vols, sps, dirs = [], [], []
+    for k in range(4):
+        h, w = int(rng.integers(320, 700)), int(rng.integers(320, 700))
+        sp = float(rng.uniform(0.30, 0.95))
+        v, _, d = synthetic.make_volume(60 + k, int(rng.integers(11, 24)), h, w, (sp, sp, float(rng.uniform(3.3, 4.8))))
+        vols.append(v); sps.append((sp, sp, 4.0)); dirs.append(d)
+    batch = pipeline.localize_and_crop_volumes(vols, sps, dirs, model, dev(), crop_delta_mm=(50, 20, 30, 30), crop_size=(128, 128))
+    coords, crops, _ = batch.to_host()
+    for i in range(4):
+        sl, sp2 = itk.resample_middle_sagittal(vols[i], sps[i], dirs[i])
+        _, t = ref.preprocess_slice(sl, (512, 512))
+        with torch.no_grad():
+            want_c = om(t.unsqueeze(0))[0].numpy()
+        assert np.abs(coords[i] - want_c).max() * PX <= 0.5
+        dpx = ref.mm_to_pixels((50, 20, 30, 30), sp2)
+        for lvl in range(5):
+            want = ref.crop_region_horizontal(sl, float(coords[i, lvl, 0]), float(coords[i, lvl, 1]), (128, 128), dpx)
+            assert np.array_equal(crops[i, lvl], want)
