@@ -141,6 +141,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Relaxed arrive: no fence in front.  The default (.release) compiles to MEMBAR.ALL.CTA in front of SYNCS.ARRIVE, which
+// waits for every outstanding memory operation of the thread (measured: ~18 % of the GEMM epilogue warps' samples sat in
+// MEMBAR / ERRBAR).  Safe wherever the barrier only returns a buffer whose contents the warp has already READ into
+// registers: a TMEM accumulator after tcgen05.wait::ld, a shared-memory stage whose ld.shared results have been consumed.
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 // Bounded wait: a protocol bug must trap, not hang the GPU box (see the gpurun strike rule).
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
@@ -234,6 +241,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// same hand-over to the pair leader's barrier without the MEMBAR.ALL.GPU + ERRBAR a cluster-scope release costs
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // CTA-pair TMA load: the data lands in THIS CTA's shared memory, the bytes are counted on the
 // mbarrier at shared::cluster address `bar_cluster` (the pair leader's "full" barrier).

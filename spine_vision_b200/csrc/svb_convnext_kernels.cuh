@@ -361,7 +361,7 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&s_empty[stage]);  // this warp is done with the stage
+                if (lane == 0) mbar_arrive_relaxed(&s_empty[stage]);  // this warp is done with the stage (all of it is in registers)
                 // park the chunk's results: pixel i of the column -> columns [i*NV + 2k, +2)
 #pragma unroll
                 for (int i = 0; i < TH; ++i) tmem_st_x2(tcol0 + (uint32_t)(i * NV + 2 * k), acc[i]);
@@ -690,8 +690,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CG == 1 || rank == 0) mbar_arrive(&tempty[as]);
-                else mbar_arrive_cluster(mapa_shared(smem_u32(&tempty[as]), 0));
+                // the accumulator stage is in registers (tcgen05.wait::ld above): nothing to release, so no fence
+                if (CG == 1 || rank == 0) mbar_arrive_relaxed(&tempty[as]);
+                else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[as]), 0));
             }
             if (++as == 2) { as = 0; aphase ^= 1; }
         }
