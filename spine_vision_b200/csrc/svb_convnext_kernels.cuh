@@ -924,13 +924,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
             for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
                 for (int j = 0; j < NJ; ++j, ++j1) {
                     const uint32_t hb = j1 % NB, par = (j1 / NB) & 1;
+                    // relaxed forwards: the relay publishes nothing of its own, and what the peer's epilogue warps wrote
+                    // (the smem operand) was fenced by them (fence.proxy.async = MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC) before
+                    // their local arrive; a release.cluster here costs MEMBAR.ALL.GPU + ERRBAR on the MMA's critical path
                     mbar_wait(&hacc_free_l[hb], par);
-                    mbar_arrive_cluster(mapa_shared(smem_u32(&hacc_free_p[hb]), 0));
+                    mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&hacc_free_p[hb]), 0));
                     mbar_wait(&hs_full_l[hb], par);
-                    mbar_arrive_cluster(mapa_shared(smem_u32(&hs_full_p[hb]), 0));
+                    mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&hs_full_p[hb]), 0));
                 }
                 mbar_wait(yfree_l, tcount & 1);
-                mbar_arrive_cluster(mapa_shared(smem_u32(yfree_p), 0));
+                mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(yfree_p), 0));
             }
         }
     } else {
@@ -965,7 +968,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&hacc_free_l[hb]);
+                if (lane == 0) mbar_arrive_relaxed(&hacc_free_l[hb]);  // accumulator chunk is in registers
                 mbar_wait(&hs_free[hb], u ^ 1);  // fc2 of the chunk that used this operand buffer NB chunks ago is done
                 const uint32_t dst = smem_u32(sH + hb * Cfg::H_BYTES) + (uint32_t)(r * 128);
 #pragma unroll
@@ -981,7 +984,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&hs_full_l[hb]);
+                if (lane == 0) mbar_arrive_relaxed(&hs_full_l[hb]);  // every lane fenced its stores above
             }
             // ---- tile epilogue: x <- x + gamma * (Y + b2), residual in and result out through per-warp 32x32 boxes
             const uint32_t swz = ((uint32_t)lane >> 1) & 3u;
@@ -1005,7 +1008,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                 if (c == CH - 1) {  // Y has been read out: the next tile's fc2 may overwrite it
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(yfree_l);
+                    if (lane == 0) mbar_arrive_relaxed(yfree_l);
                 }
                 if (row0 < M) {
                     const uint32_t row_off = stage_a + (uint32_t)(c * 2048) + (uint32_t)lane * 64u;
