@@ -30,6 +30,7 @@ CROP_SIZE = (128, 128)
 SECOND_SIZE = (256, 256)
 IMAGE_SIZE = (512, 512)
 SLICE_HW = (1195, 1195)
+TRAFFIC_JSON = "r01e_gemm_traffic.json"  # per-shape DRAM bytes of the GEMM launches (ncu --set full), see scripts/summarise_ncu_layers.py
 WORKLOAD = ("configs[1]: 256 synthetic sagittal middle slices 1195x1195 fp32 (512px@0.7mm -> 0.3mm iso) per GPU, "
             "convnext_base random-init localizer @512x512, 5 IVD levels, crop_delta_mm 50/20/30/30, 128x128 crops + 256x256 classifier input")
 
@@ -218,11 +219,20 @@ def run_b200(args):
     max_box = (dpx[2] + dpx[3], dpx[0] + dpx[1])
     k3_out = torch.empty((n_crops, *CROP_SIZE), dtype=torch.uint8, device=dev)   # preallocated: no allocator work between the events
     k3_out2 = torch.empty((n_crops, *SECOND_SIZE), dtype=torch.uint8, device=dev)
+    k1_out = torch.empty((B, *IMAGE_SIZE), dtype=torch.uint8, device=dev)
+    # K4 (classifier-input producer) is not part of series/s; it is timed here on this step's crops so that
+    # its roofline sits next to K1 / K3: the crops are paired as (T2, T1) samples -> float32 [P, 3, 256, 256]
+    k4_p = n_crops // 2
+    k4_t2 = torch.arange(0, k4_p, dtype=torch.int32, device=dev)
+    k4_t1 = torch.arange(k4_p, 2 * k4_p, dtype=torch.int32, device=dev)
+    k4_out = torch.empty((k4_p, 3, *SECOND_SIZE), dtype=torch.float32, device=dev)
+    k4_ms = 0.0
+    ops.normalize_resize(pool, IMAGE_SIZE, out=k1_out)  # workspace allocation outside the events
     torch.cuda.synchronize()
     for _ in range(args.steps):
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
-        planes = ops.normalize_resize(pool, IMAGE_SIZE)
+        planes = ops.normalize_resize(pool, IMAGE_SIZE, out=k1_out)
         ev[1].record()
         coords = model.predict_u8(planes, times)
         xy = coords.reshape(n_crops, 2)
@@ -230,9 +240,13 @@ def run_b200(args):
         ev[2].record()
         ops.crop_resample(pool, k3_idx, xy, k3_delta, max_box, CROP_SIZE, SECOND_SIZE, out=k3_out, out2=k3_out2)
         ev[3].record()
+        ev[4].record()
+        ops.classifier_input(k3_out2, k4_t2, k4_t1, out=k4_out)
+        ev[5].record()
         torch.cuda.synchronize()
         k1_ms += ev[0].elapsed_time(ev[1])
         k3_ms += ev[2].elapsed_time(ev[3])
+        k4_ms += ev[4].elapsed_time(ev[5])
     # end-to-end pass through the public API: pinned host -> H2D -> kernels -> D2H
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -257,7 +271,7 @@ def run_b200(args):
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
         try:  # DRAM bytes of the GEMM launches of one step, from the committed ncu --set full capture of the same kernels
-            tj = json.loads((ROOT / "profiles" / "r01_gemm_traffic.json").read_text())
+            tj = json.loads((ROOT / "profiles" / TRAFFIC_JSON).read_text())
             traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
         except Exception:
             pass
@@ -268,6 +282,7 @@ def run_b200(args):
                                      for i, (d, n) in enumerate(zip(model.engine.dims, model.engine.depths)))
         k1_bytes = B * (SLICE_HW[0] * SLICE_HW[1] * 4 + IMAGE_SIZE[0] * IMAGE_SIZE[1])
         k3_bytes = n_crops * (234 * 200 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])
+        k4_bytes = k4_p * SECOND_SIZE[0] * SECOND_SIZE[1] * (2 + 3 * 4)  # two uint8 planes in, three float32 planes out
         line = {
             "metric": "series/sec", "value": value, "unit": "series/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
@@ -283,7 +298,7 @@ def run_b200(args):
             "gpu_launches": int(gpu_launches),
             "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": traffic, "traffic_source": "profiles/r01_gemm_traffic.json (ncu --set full, per-shape dram bytes x launches)",
+                         "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_JSON} (ncu --set full, per-shape dram bytes x launches)",
                          "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
                          "timing": "CUDA event pair around every launch, separate pass over the same steps"},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
@@ -295,6 +310,10 @@ def run_b200(args):
             "hbm_kernels": {
                 "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None, "peak_gbs": hbm},
                 "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None, "peak_gbs": hbm},
+                "k4_classifier_input": {"bytes_per_step": k4_bytes, "ms_per_step": k4_ms / args.steps, "samples": k4_p,
+                                        "achieved_gbs": k4_bytes / (k4_ms / args.steps * 1e-3) / 1e9 if k4_ms else None, "peak_gbs": hbm,
+                                        "frac": k4_bytes / (k4_ms / args.steps * 1e-3) / 1e9 / hbm if k4_ms else None,
+                                        "note": "outside the series/s timed region (its consumer is the classifier's data loader)"},
             },
         }
         if world == 1 and not args.no_cpu_baseline:
