@@ -1,4 +1,4 @@
-"""K1 / K3 on the bench shapes (256 slices of 1195^2, 1280 crops): CUDA-event timings, or one launch each for ncu (REPS=0)."""
+"""K1 / K3 / K4 on the bench shapes (256 slices of 1195^2, 1280 crops): CUDA-event timings, or one launch each for ncu (REPS=0)."""
 import sys
 from pathlib import Path
 
@@ -30,7 +30,18 @@ def k3():
     ops.crop_resample(pool, idx, xy, delta, (dpx[2] + dpx[3], dpx[0] + dpx[1]), (128, 128), (256, 256), out=out, out2=out2)
 
 
-for name, fn, nbytes in (("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120)):
+P = B * 5 // 2
+k4_t2 = torch.arange(0, P, dtype=torch.int32, device=dev)
+k4_t1 = torch.arange(P, 2 * P, dtype=torch.int32, device=dev)
+k4_out = torch.empty((P, 3, 256, 256), dtype=torch.float32, device=dev)
+
+
+def k4():
+    ops.classifier_input(out2, k4_t2, k4_t1, out=k4_out)
+
+
+for name, fn, nbytes in (("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120),
+                         ("K4 classifier input", k4, P * 65536 * 14)):
     if REPS == 0:
         fn(); torch.cuda.synchronize(); continue
     fn(); fn(); torch.cuda.synchronize()

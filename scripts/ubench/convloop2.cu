@@ -8,7 +8,19 @@
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
 __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+#ifdef UNPACK_PRMT
+// both halves on the ALU pipe: the compiler turns `u << 16` into IMAD.U32 (FMA pipe), which competes with the FFMA2s
+__device__ __forceinline__ uint64_t unpack_bf16x2(uint32_t u) {
+    uint32_t lo, hi;
+    asm volatile("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(u));
+    asm volatile("lop3.b32 %0, %1, 0xffff0000, 0, 0xc0;" : "=r"(hi) : "r"(u));
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+    return r;
+}
+#else
 __device__ __forceinline__ uint64_t unpack_bf16x2(uint32_t u) { return (static_cast<uint64_t>(u & 0xFFFF0000u) << 32) | static_cast<uint64_t>(u << 16); }
+#endif
 
 // MODE 0: bf16 halo + FFMA2 (kernel as is)   1: fp32 halo (LDS.64, no unpack) + FFMA2   2: bf16 halo + scalar FFMA
 // MODE 3: bf16 halo, kx loop fully unrolled + FFMA2

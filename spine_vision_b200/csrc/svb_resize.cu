@@ -629,38 +629,83 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     // letterboxed fixed-point bilinear resize (cv2.resize 8U INTER_LINEAR) onto the zero canvas
     {
         const int cw4 = cw >> 2;
-        for (int i = tid; i < ch * cw4; i += nthr) {
-            const int oy = i / cw4, ox4 = (i - oy * cw4) << 2;
-            uint32_t packed = 0;
-            const int dy = oy - g.y_off;
-            if (valid && dy >= 0 && dy < g.new_h) {
-                const bool same = (g.new_h == bh && g.new_w == bw);  // cv2.resize returns a copy
-                const int sy = ys[dy];
-                const int r0 = min(max(sy, 0), bh - 1), r1 = min(max(sy + 1, 0), bh - 1);
-                const int b0 = yb0[dy], b1 = yb1[dy];
-                const uint8_t* p0 = s_box + (size_t)r0 * bw;
-                const uint8_t* p1 = s_box + (size_t)r1 * bw;
+        const bool same = (g.new_h == bh && g.new_w == bw);  // cv2.resize returns a copy
+        if (nthr % cw4 == 0) {
+            // a thread keeps ONE quad of output columns for all its rows: the four columns' source index and weights
+            // are fetched once, and no index has to be divided (the kernel is issue-bound, not bandwidth-bound)
+            const int ox4 = (tid % cw4) << 2, oy0 = tid / cw4, oys = nthr / cw4;
+            int sx0[4], sx1[4], wa0[4], wa1[4], dxs[4];
+            bool inx[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int dx = ox4 + k - g.x_off;
-                    uint32_t v = 0;
-                    if (dx >= 0 && dx < g.new_w) {
-                        if (same) {
-                            v = s_box[(size_t)dy * bw + dx];
-                        } else {
-                            const int sx = xs[dx];
-                            const int sx1 = min(sx + 1, bw - 1);
-                            const int a0 = xa0[dx], a1 = xa1[dx];
-                            const int h0 = (int)p0[sx] * a0 + (int)p0[sx1] * a1;
-                            const int h1 = (int)p1[sx] * a0 + (int)p1[sx1] * a1;
-                            const int t = ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16);
-                            v = (uint32_t)min(max((t + 2) >> 2, 0), 255);
-                        }
-                    }
-                    packed |= v << (8 * k);
-                }
+            for (int k = 0; k < 4; ++k) {
+                const int dx = ox4 + k - g.x_off;
+                inx[k] = valid && dx >= 0 && dx < g.new_w;
+                dxs[k] = inx[k] ? dx : 0;
+                sx0[k] = inx[k] ? xs[dx] : 0;
+                sx1[k] = min(sx0[k] + 1, bw - 1);
+                wa0[k] = inx[k] ? xa0[dx] : 0;
+                wa1[k] = inx[k] ? xa1[dx] : 0;
             }
-            *reinterpret_cast<uint32_t*>(s_canvas + (size_t)oy * cw + ox4) = packed;
+            for (int oy = oy0; oy < ch; oy += oys) {
+                uint32_t packed = 0;
+                const int dy = oy - g.y_off;
+                if (valid && dy >= 0 && dy < g.new_h) {
+                    const int sy = ys[dy];
+                    const int r0 = min(max(sy, 0), bh - 1), r1 = min(max(sy + 1, 0), bh - 1);
+                    const int b0 = yb0[dy], b1 = yb1[dy];
+                    const uint8_t* p0 = s_box + (size_t)r0 * bw;
+                    const uint8_t* p1 = s_box + (size_t)r1 * bw;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t v = 0;
+                        if (inx[k]) {
+                            if (same) {
+                                v = s_box[(size_t)dy * bw + dxs[k]];
+                            } else {
+                                const int h0 = (int)p0[sx0[k]] * wa0[k] + (int)p0[sx1[k]] * wa1[k];
+                                const int h1 = (int)p1[sx0[k]] * wa0[k] + (int)p1[sx1[k]] * wa1[k];
+                                const int t = ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16);
+                                v = (uint32_t)min(max((t + 2) >> 2, 0), 255);
+                            }
+                        }
+                        packed |= v << (8 * k);
+                    }
+                }
+                *reinterpret_cast<uint32_t*>(s_canvas + (size_t)oy * cw + ox4) = packed;
+            }
+        } else {
+            for (int i = tid; i < ch * cw4; i += nthr) {
+                const int oy = i / cw4, ox4 = (i - oy * cw4) << 2;
+                uint32_t packed = 0;
+                const int dy = oy - g.y_off;
+                if (valid && dy >= 0 && dy < g.new_h) {
+                    const int sy = ys[dy];
+                    const int r0 = min(max(sy, 0), bh - 1), r1 = min(max(sy + 1, 0), bh - 1);
+                    const int b0 = yb0[dy], b1 = yb1[dy];
+                    const uint8_t* p0 = s_box + (size_t)r0 * bw;
+                    const uint8_t* p1 = s_box + (size_t)r1 * bw;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int dx = ox4 + k - g.x_off;
+                        uint32_t v = 0;
+                        if (dx >= 0 && dx < g.new_w) {
+                            if (same) {
+                                v = s_box[(size_t)dy * bw + dx];
+                            } else {
+                                const int sx = xs[dx];
+                                const int sx1 = min(sx + 1, bw - 1);
+                                const int a0 = xa0[dx], a1 = xa1[dx];
+                                const int h0 = (int)p0[sx] * a0 + (int)p0[sx1] * a1;
+                                const int h1 = (int)p1[sx] * a0 + (int)p1[sx1] * a1;
+                                const int t = ((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16);
+                                v = (uint32_t)min(max((t + 2) >> 2, 0), 255);
+                            }
+                        }
+                        packed |= v << (8 * k);
+                    }
+                }
+                *reinterpret_cast<uint32_t*>(s_canvas + (size_t)oy * cw + ox4) = packed;
+            }
         }
     }
     __syncthreads();
@@ -680,9 +725,29 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         for (int i = tid; i < (ch * cw) >> 2; i += nthr) dst[i] = s[i];
         return;
     }
-    // second output: Pillow BILINEAR (ch,cw) -> (oh2,ow2): horizontal pass into tmp2, vertical to global
+    // second output: Pillow BILINEAR (ch,cw) -> (oh2,ow2): horizontal pass into tmp2, vertical to global.
+    // Fast mapping (taps per output <= 4, i.e. up-sampling or mild down-sampling, and a block size the row length
+    // divides): a thread owns one output column (horizontal) / one quad of columns (vertical), its taps sit in
+    // registers, and no flat index is divided.  Same sums in the same order as the generic loops below.
+    constexpr int KREG = 4;
     if (ow2 == cw) {
         for (int i = tid; i < ch * ow2; i += nthr) s_tmp2[i] = s_canvas[i];
+    } else if (ksw2 <= KREG && nthr % ow2 == 0) {
+        const int xx = tid % ow2, row0 = tid / ow2, rs = nthr / ow2;
+        const int xmin = __ldg(hb2 + 2 * xx), cnt = __ldg(hb2 + 2 * xx + 1);
+        int kk[KREG], off[KREG];
+#pragma unroll
+        for (int j = 0; j < KREG; ++j) {
+            kk[j] = j < cnt ? __ldg(hk2 + (size_t)xx * ksw2 + j) : 0;
+            off[j] = j < cnt ? xmin + j : xmin;  // unused taps re-read a valid pixel with weight 0
+        }
+        for (int row = row0; row < ch; row += rs) {
+            const uint8_t* sp = s_canvas + (size_t)row * cw;
+            int acc = 1 << (PIL_PRECISION_BITS - 1);
+#pragma unroll
+            for (int j = 0; j < KREG; ++j) acc += (int)sp[off[j]] * kk[j];
+            s_tmp2[(size_t)row * ow2 + xx] = (uint8_t)pil_clip8(acc);
+        }
     } else {
         for (int i = tid; i < ch * ow2; i += nthr) {
             const int row = i / ow2, xx = i - row * ow2;
@@ -697,26 +762,46 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     __syncthreads();
     {
         const int w4 = ow2 >> 2;
-        for (int i = tid; i < oh2 * w4; i += nthr) {
-            const int r = i / w4, x4 = (i - r * w4) << 2;
-            uint32_t packed;
-            if (oh2 == ch) {
-                packed = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)r * ow2 + x4);
-            } else {
-                const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);
-                const int* kp = vk2 + (size_t)r * ksh2;
+        if (oh2 != ch && ksh2 <= KREG && nthr % w4 == 0) {
+            const int x4 = (tid % w4) << 2, r0 = tid / w4, rs = nthr / w4;
+            for (int r = r0; r < oh2; r += rs) {
+                const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);  // warp-uniform when w4 >= 32
                 int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
-                for (int j = 0; j < cnt; ++j) {
-                    const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)(ymin + j) * ow2 + x4);
-                    const int k = __ldg(kp + j);
+#pragma unroll
+                for (int j = 0; j < KREG; ++j) {
+                    const int k = j < cnt ? __ldg(vk2 + (size_t)r * ksh2 + j) : 0;
+                    const int yy = j < cnt ? ymin + j : ymin;
+                    const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)yy * ow2 + x4);
                     a0 += (int)(px & 0xFF) * k;
                     a1 += (int)((px >> 8) & 0xFF) * k;
                     a2 += (int)((px >> 16) & 0xFF) * k;
                     a3 += (int)(px >> 24) * k;
                 }
-                packed = pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
+                *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) =
+                    pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
             }
-            *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) = packed;
+        } else {
+            for (int i = tid; i < oh2 * w4; i += nthr) {
+                const int r = i / w4, x4 = (i - r * w4) << 2;
+                uint32_t packed;
+                if (oh2 == ch) {
+                    packed = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)r * ow2 + x4);
+                } else {
+                    const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);
+                    const int* kp = vk2 + (size_t)r * ksh2;
+                    int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+                    for (int j = 0; j < cnt; ++j) {
+                        const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)(ymin + j) * ow2 + x4);
+                        const int k = __ldg(kp + j);
+                        a0 += (int)(px & 0xFF) * k;
+                        a1 += (int)((px >> 8) & 0xFF) * k;
+                        a2 += (int)((px >> 16) & 0xFF) * k;
+                        a3 += (int)(px >> 24) * k;
+                    }
+                    packed = pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
+                }
+                *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) = packed;
+            }
         }
     }
 }
