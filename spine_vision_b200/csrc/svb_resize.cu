@@ -558,26 +558,30 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     };
 
     if (valid) {
-        // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350).  The box is walked as one
-        // flat index range, 8 independent loads in flight per thread (the pass is pure load latency otherwise).
+        // pass 1: per-crop min / max (normalize_to_uint8 on the crop, cropping.py:350).  A warp walks whole box rows
+        // (lane = column, stride 32), two rows x eight column groups = up to 16 independent loads in flight per thread;
+        // the address of a load is one add away from the row pointer (the kernel is issue-bound).
         float mn = INFINITY, mx = -INFINITY;
-        const int npx = bh * bw;
-        const int step_y = nthr / bw, step_x = nthr - step_y * bw;
-        {
-            int y = tid / bw, x = tid - y * bw;
-            for (int base = tid; base < npx; base += 8 * nthr) {
-                float v[8];
+        for (int y = wid; y < bh; y += 2 * nwarps) {
+            const int y2 = y + nwarps;
+            for (int x0 = lane; x0 < bw; x0 += 256) {
+                float v[16];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    v[u] = (base + u * nthr < npx) ? box_value(x, y) : 0.0f;
-                    x += step_x; y += step_y;
-                    if (x >= bw) { x -= bw; ++y; }
+                    const int x = x0 + 32 * u;
+                    v[u] = x < bw ? box_value(x, y) : 0.0f;
+                    v[8 + u] = (x < bw && y2 < bh) ? box_value(x, y2) : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    if (base + u * nthr < npx) {
+                    const int x = x0 + 32 * u;
+                    if (x < bw) {
                         mn = fminf(mn, v[u]);
                         mx = fmaxf(mx, v[u]);
+                        if (y2 < bh) {
+                            mn = fminf(mn, v[8 + u]);
+                            mx = fmaxf(mx, v[8 + u]);
+                        }
                     }
                 }
             }
@@ -604,22 +608,26 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         const float mnv = s_mm[0];
         // rng <= 0 makes normalize_px a plain cast: the max == min case, and SVB_K3_NO_NORMALIZE
         const float rng = (flags & SVB_K3_NO_NORMALIZE) ? 0.0f : __fsub_rn(s_mm[1], mnv);
-        // pass 2: normalise the box into shared memory (second read is an L1/L2 hit)
+        // pass 2: normalise the box into shared memory (second read is an L1/L2 hit); same row-wise walk
         const float kfast = rng > 0.0f ? __fdiv_rn(255.0f, rng) : 0.0f;
-        {
-            int y = tid / bw, x = tid - y * bw;
-            for (int base = tid; base < npx; base += 8 * nthr) {
-                float v[8];
+        for (int y = wid; y < bh; y += 2 * nwarps) {
+            const int y2 = y + nwarps;
+            for (int x0 = lane; x0 < bw; x0 += 256) {
+                float v[16];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    v[u] = (base + u * nthr < npx) ? box_value(x, y) : 0.0f;
-                    x += step_x; y += step_y;
-                    if (x >= bw) { x -= bw; ++y; }
+                    const int x = x0 + 32 * u;
+                    v[u] = x < bw ? box_value(x, y) : 0.0f;
+                    v[8 + u] = (x < bw && y2 < bh) ? box_value(x, y2) : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = base + u * nthr;  // box pixels are stored row-major, so the flat index is the address
-                    if (i < npx) s_box[i] = (uint8_t)(rng > 0.0f ? normalize_px_fast(v[u], mnv, rng, kfast) : cast_f32_u8(v[u]));
+                    const int x = x0 + 32 * u;
+                    if (x < bw) {  // box pixels are stored row-major
+                        s_box[y * bw + x] = (uint8_t)(rng > 0.0f ? normalize_px_fast(v[u], mnv, rng, kfast) : cast_f32_u8(v[u]));
+                        if (y2 < bh)
+                            s_box[y2 * bw + x] = (uint8_t)(rng > 0.0f ? normalize_px_fast(v[8 + u], mnv, rng, kfast) : cast_f32_u8(v[8 + u]));
+                    }
                 }
             }
         }
