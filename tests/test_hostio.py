@@ -150,3 +150,47 @@ def test_metaimage_writer_is_plain_zlib(tmp_path):
     head, data = blob.split(b"ElementDataFile = LOCAL\n", 1)
     assert b"DimSize = 4 3 2" in head and b"ElementType = MET_SHORT" in head
     assert np.array_equal(np.frombuffer(zlib.decompress(data), dtype="<i2").reshape(2, 3, 4), arr)
+
+
+_RECORDS_WORKER = r"""
+import sys, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from spine_vision_b200 import dataset, synthetic
+from pathlib import Path
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{sys.argv[2]}", rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+cfg = dataset.ClassificationDatasetConfig(base_path=Path(sys.argv[4]), output_name="cls")
+jobs = dataset.collect_spider_jobs(cfg, set())
+mine = jobs[rank::2]                                   # the split create_classification_dataset(rank, world_size) uses
+recs = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, l), j.patient_id, l, j.series_type, row)
+        for j in mine for l, row in j.levels.items()]
+allr = dataset.gather_records(recs)
+want = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, l), j.patient_id, l, j.series_type, row)
+        for part in (jobs[0::2], jobs[1::2]) for j in part for l, row in j.levels.items()]
+assert allr == want and len(allr) == 24, (len(allr), len(want))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_gather_records_gloo_world2(tmp_path):
+    """Multi-GPU dataset creation shards the job list by rank and gathers the records once (no data-path collective)."""
+    import socket
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+
+    synthetic.make_spider_tree(tmp_path, seed=0)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "w.py"
+    script.write_text(_RECORDS_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT), str(port), str(r), str(tmp_path)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
