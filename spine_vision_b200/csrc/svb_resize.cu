@@ -162,10 +162,15 @@ __global__ void __launch_bounds__(512) k1_minmax_kernel(const float* __restrict_
 // e = fl(fl((x - mn) / rng) * 255) truncated; y = fl((x - mn) * fl(255 / rng)) differs from e by < 5e-5 for
 // 0 <= e <= 255, so trunc(y) == trunc(e) unless y sits within 1e-3 of an integer -- only then (and for
 // NaN / inf, which fail the comparison) the exact sequence runs.  Bit-exact by construction.
+// The two exact hits of that window that real slices are full of never reach the division either: a background pixel equal
+// to the minimum (d == 0 -> 0 / rng * 255 = 0) and the maximum itself (d == rng -> 1 * 255 = 255); without the shortcut every
+// warp that touches background took the IEEE-division subroutine (19 % of K1's instructions on the bench slices).
 __device__ __forceinline__ uint32_t normalize_px_fast(float x, float mn, float rng, float k) {
     const float d = __fsub_rn(x, mn);
     const float y = __fmul_rn(d, k);
     if (fabsf(y - rintf(y)) > 1e-3f) return static_cast<uint32_t>(__float2int_rz(y)) & 0xFFu;
+    if (d == 0.0f) return 0u;
+    if (d == rng) return 255u;
     return cast_f32_u8(__fmul_rn(__fdiv_rn(d, rng), 255.0f));
 }
 
