@@ -299,6 +299,30 @@ int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, s
 int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
                            const size_t* dst_elems, int n_threads, int32_t* rcs);
 
+/* DICOM series (one slice per file) -- replaces read_medical_image -> read_dicom_series -> sitk.ImageSeriesReader over
+ * GDCM for the Phenikaa series directories (spine_vision/io/readers.py:48-73, 128-161; phenikaa.py:178).  Part-10 files,
+ * implicit / explicit VR little endian or explicit big endian, NATIVE pixel data (compressed transfer syntaxes give
+ * SVB_ERR_FORMAT), monochrome 8 / 16 / 32 bit.  The C side parses and decodes single files on a thread pool; series
+ * selection, slice ordering and the volume geometry (the ITK conventions) are host logic in spine_vision_b200/hostio.py.
+ * Parity is UNPINNED (SimpleITK / GDCM are absent from the build image; restated in oracle/dicom.py).
+ */
+typedef struct svb_dicom_info {
+    int32_t rows, cols, bits_allocated, pixel_representation, samples_per_pixel, monochrome1;
+    int32_t instance_number, big_endian, has_position, has_orientation, has_spacing, pad;
+    double pixel_spacing[2];        /* (0028,0030): row spacing (between rows), column spacing */
+    double position[3];             /* (0020,0032) ImagePositionPatient */
+    double orientation[6];          /* (0020,0037) ImageOrientationPatient: row cosines, column cosines */
+    double rescale_slope, rescale_intercept; /* (0028,1053), (0028,1052); applied by svb_dicom_read_slices_f32 */
+    double slice_thickness, spacing_between_slices;
+    int64_t pixel_offset, pixel_bytes; /* (7FE0,0010) */
+    char series_uid[72];            /* (0020,000E) */
+} svb_dicom_info;
+/* rcs (optional, [n]) = per-file status: files that are not (supported) DICOM are dropped by the caller */
+int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* infos, int n_threads, int32_t* rcs);
+/* slice i -> h_dsts[i] (rows*cols float32, stored value * slope + intercept), on n_threads workers */
+int svb_dicom_read_slices_f32(const char* const* paths, int n, const svb_dicom_info* infos, float* const* h_dsts,
+                              const size_t* dst_elems, int n_threads, int32_t* rcs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,7 @@ EXPORTS = (
     "svb_k4_classifier_input",
     "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch",
     "svb_mha_read_header", "svb_mha_read_f32", "svb_mha_read_batch_f32",
+    "svb_dicom_read_headers", "svb_dicom_read_slices_f32",
 )
 
 
@@ -45,6 +46,18 @@ class MhaInfo(C.Structure):
                 ("direction", C.c_double * 9), ("element_type", C.c_int32), ("element_bytes", C.c_int32), ("channels", C.c_int32),
                 ("compressed", C.c_int32), ("big_endian", C.c_int32), ("has_spacing", C.c_int32), ("data_offset", C.c_int64),
                 ("header_size", C.c_int64), ("compressed_size", C.c_int64), ("data_file", C.c_char * 1024)]
+
+
+class DicomInfo(C.Structure):
+    """``svb_dicom_info`` (include/spine_b200.h)."""
+
+    _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("bits_allocated", C.c_int32), ("pixel_representation", C.c_int32),
+                ("samples_per_pixel", C.c_int32), ("monochrome1", C.c_int32), ("instance_number", C.c_int32), ("big_endian", C.c_int32),
+                ("has_position", C.c_int32), ("has_orientation", C.c_int32), ("has_spacing", C.c_int32), ("pad", C.c_int32),
+                ("pixel_spacing", C.c_double * 2), ("position", C.c_double * 3), ("orientation", C.c_double * 6),
+                ("rescale_slope", C.c_double), ("rescale_intercept", C.c_double), ("slice_thickness", C.c_double),
+                ("spacing_between_slices", C.c_double), ("pixel_offset", C.c_int64), ("pixel_bytes", C.c_int64),
+                ("series_uid", C.c_char * 72)]
 
 
 class WeightDesc(C.Structure):
@@ -125,6 +138,10 @@ def load() -> C.CDLL:
     lib.svb_mha_read_f32.argtypes = [C.c_char_p, C.POINTER(MhaInfo), vp, sz]
     lib.svb_mha_read_batch_f32.restype = C.c_int
     lib.svb_mha_read_batch_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(MhaInfo), C.POINTER(vp), C.POINTER(sz), i32, vp]
+    lib.svb_dicom_read_headers.restype = C.c_int
+    lib.svb_dicom_read_headers.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(DicomInfo), i32, vp]
+    lib.svb_dicom_read_slices_f32.restype = C.c_int
+    lib.svb_dicom_read_slices_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(DicomInfo), C.POINTER(vp), C.POINTER(sz), i32, vp]
     _lib = lib
     return lib
 

@@ -328,6 +328,227 @@ int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_
     return SVB_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------ DICOM (one slice per file)
+// The subset the Phenikaa series need (io/readers.py:48-73 -> sitk.ImageSeriesReader over GDCM): Part-10 files, implicit
+// or explicit VR little endian (and explicit big endian), native (uncompressed) pixel data, 8/16/32-bit monochrome.
+struct DcmCursor {
+    const uint8_t* p;
+    size_t n, pos;
+    bool explicit_vr, big;
+    uint16_t u16() {
+        const uint16_t v = big ? (uint16_t)((p[pos] << 8) | p[pos + 1]) : (uint16_t)(p[pos] | (p[pos + 1] << 8));
+        pos += 2;
+        return v;
+    }
+    uint32_t u32() {
+        const uint32_t v = big ? ((uint32_t)p[pos] << 24 | (uint32_t)p[pos + 1] << 16 | (uint32_t)p[pos + 2] << 8 | p[pos + 3])
+                               : ((uint32_t)p[pos] | (uint32_t)p[pos + 1] << 8 | (uint32_t)p[pos + 2] << 16 | (uint32_t)p[pos + 3] << 24);
+        pos += 4;
+        return v;
+    }
+};
+bool long_vr(const char vr[2]) {
+    static const char* k[] = {"OB", "OW", "OF", "OD", "OL", "SQ", "UC", "UR", "UT", "UN"};
+    for (const char* s : k)
+        if (vr[0] == s[0] && vr[1] == s[1]) return true;
+    return false;
+}
+// skip a sequence / item of undefined length: walk nested elements until the matching delimiter
+bool dcm_skip_undefined(DcmCursor& c, int depth);
+bool dcm_next(DcmCursor& c, uint16_t& g, uint16_t& e, char vr[2], uint32_t& len) {
+    if (c.pos + 8 > c.n) return false;
+    g = c.u16();
+    e = c.u16();
+    vr[0] = vr[1] = 0;
+    if (g == 0xFFFE) {  // item / delimiters: always implicit form
+        len = c.u32();
+        return true;
+    }
+    if (c.explicit_vr) {
+        vr[0] = (char)c.p[c.pos];
+        vr[1] = (char)c.p[c.pos + 1];
+        c.pos += 2;
+        if (long_vr(vr)) {
+            c.pos += 2;
+            if (c.pos + 4 > c.n) return false;
+            len = c.u32();
+        } else {
+            len = c.u16();
+        }
+    } else {
+        len = c.u32();
+    }
+    return true;
+}
+bool dcm_skip_undefined(DcmCursor& c, int depth) {
+    if (depth > 16) return false;
+    for (;;) {
+        uint16_t g, e;
+        char vr[2];
+        uint32_t len;
+        if (!dcm_next(c, g, e, vr, len)) return false;
+        if (g == 0xFFFE && (e == 0xE0DD || e == 0xE00D)) return true;  // sequence / item delimiter
+        if (len == 0xFFFFFFFFu) {
+            if (!dcm_skip_undefined(c, depth + 1)) return false;
+        } else {
+            if (c.pos + len > c.n) return false;
+            c.pos += len;
+        }
+    }
+}
+std::string dcm_str(const DcmCursor& c, uint32_t len) {
+    std::string s(reinterpret_cast<const char*>(c.p + c.pos), len);
+    while (!s.empty() && (s.back() == ' ' || s.back() == '\0')) s.pop_back();
+    size_t a = 0;
+    while (a < s.size() && s[a] == ' ') ++a;
+    return s.substr(a);
+}
+int dcm_numbers(const std::string& s, double* out, int max_n) {  // "a\b\c" decimal strings
+    int n = 0;
+    size_t pos = 0;
+    while (n < max_n && pos <= s.size()) {
+        size_t q = s.find('\\', pos);
+        if (q == std::string::npos) q = s.size();
+        const std::string t = s.substr(pos, q - pos);
+        char* e = nullptr;
+        const double d = strtod(t.c_str(), &e);
+        if (e == t.c_str()) break;
+        out[n++] = d;
+        pos = q + 1;
+    }
+    return n;
+}
+int read_whole(const char* path, std::vector<uint8_t>& buf) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    buf.resize(n > 0 ? (size_t)n : 0);
+    const size_t got = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), f);
+    fclose(f);
+    if (got != buf.size()) return set_error(SVB_ERR_IO, "%s: short read", path);
+    return SVB_OK;
+}
+
+int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* keep) {
+    if (!path || !info) return set_error(SVB_ERR_INVALID_ARG, "dicom: null argument");
+    std::vector<uint8_t> local;
+    std::vector<uint8_t>& buf = keep ? *keep : local;
+    if (int rc = read_whole(path, buf)) return rc;
+    memset(info, 0, sizeof(*info));
+    info->rescale_slope = 1.0;
+    info->samples_per_pixel = 1;
+    info->pixel_spacing[0] = info->pixel_spacing[1] = 1.0;
+    info->orientation[0] = 1.0;
+    info->orientation[4] = 1.0;
+    info->pixel_offset = -1;
+    if (buf.size() < 132 || memcmp(buf.data() + 128, "DICM", 4) != 0)
+        return set_error(SVB_ERR_FORMAT, "%s: not a DICOM Part-10 file (no DICM marker)", path);
+    DcmCursor c{buf.data(), buf.size(), 132, true, false};
+    std::string ts = "1.2.840.10008.1.2.1";
+    bool in_meta = true;
+    for (;;) {
+        const size_t at = c.pos;
+        if (in_meta) {  // leaving group 0002 switches to the data set's transfer syntax
+            if (c.pos + 2 > c.n) break;
+            const uint16_t g0 = (uint16_t)(c.p[c.pos] | (c.p[c.pos + 1] << 8));
+            if (g0 != 0x0002) {
+                in_meta = false;
+                if (ts == "1.2.840.10008.1.2") c.explicit_vr = false;
+                else if (ts == "1.2.840.10008.1.2.1") c.explicit_vr = true;
+                else if (ts == "1.2.840.10008.1.2.2") { c.explicit_vr = true; c.big = true; }
+                else return set_error(SVB_ERR_FORMAT, "%s: transfer syntax %s (compressed pixel data) is not supported", path, ts.c_str());
+                info->big_endian = c.big ? 1 : 0;
+            }
+        }
+        uint16_t g, e;
+        char vr[2];
+        uint32_t len;
+        if (!dcm_next(c, g, e, vr, len)) break;
+        if (g == 0x7FE0 && e == 0x0010) {
+            if (len == 0xFFFFFFFFu) return set_error(SVB_ERR_FORMAT, "%s: encapsulated pixel data is not supported", path);
+            info->pixel_offset = (int64_t)c.pos;
+            info->pixel_bytes = (int64_t)len;
+            break;
+        }
+        if (len == 0xFFFFFFFFu) {
+            if (!dcm_skip_undefined(c, 0)) return set_error(SVB_ERR_FORMAT, "%s: malformed sequence at byte %zu", path, at);
+            continue;
+        }
+        if (c.pos + len > c.n) return set_error(SVB_ERR_FORMAT, "%s: element (%04x,%04x) runs past the end of the file", path, g, e);
+        const uint32_t tag = ((uint32_t)g << 16) | e;
+        double d[6];
+        switch (tag) {
+            case 0x00020010: ts = dcm_str(c, len); break;
+            case 0x0020000E: { const std::string s = dcm_str(c, len); strncpy(info->series_uid, s.c_str(), sizeof(info->series_uid) - 1); } break;
+            case 0x00200013: info->instance_number = atoi(dcm_str(c, len).c_str()); break;
+            case 0x00200032: if (dcm_numbers(dcm_str(c, len), d, 3) == 3) { memcpy(info->position, d, 24); info->has_position = 1; } break;
+            case 0x00200037: if (dcm_numbers(dcm_str(c, len), d, 6) == 6) { memcpy(info->orientation, d, 48); info->has_orientation = 1; } break;
+            case 0x00280002: { DcmCursor t = c; info->samples_per_pixel = t.u16(); } break;
+            case 0x00280004: { const std::string s = dcm_str(c, len); info->monochrome1 = s == "MONOCHROME1"; } break;
+            case 0x00280010: { DcmCursor t = c; info->rows = t.u16(); } break;
+            case 0x00280011: { DcmCursor t = c; info->cols = t.u16(); } break;
+            case 0x00280030: if (dcm_numbers(dcm_str(c, len), d, 2) == 2) { info->pixel_spacing[0] = d[0]; info->pixel_spacing[1] = d[1]; info->has_spacing = 1; } break;
+            case 0x00280100: { DcmCursor t = c; info->bits_allocated = t.u16(); } break;
+            case 0x00280103: { DcmCursor t = c; info->pixel_representation = t.u16(); } break;
+            case 0x00281052: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_intercept = d[0]; break;
+            case 0x00281053: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_slope = d[0]; break;
+            case 0x00180050: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->slice_thickness = d[0]; break;
+            case 0x00180088: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->spacing_between_slices = d[0]; break;
+            default: break;
+        }
+        c.pos += len;
+    }
+    if (info->pixel_offset < 0) return set_error(SVB_ERR_FORMAT, "%s: no pixel data element", path);
+    if (info->rows <= 0 || info->cols <= 0) return set_error(SVB_ERR_FORMAT, "%s: Rows / Columns missing", path);
+    if (info->samples_per_pixel != 1) return set_error(SVB_ERR_FORMAT, "%s: %d samples per pixel (monochrome only)", path, info->samples_per_pixel);
+    if (info->bits_allocated != 8 && info->bits_allocated != 16 && info->bits_allocated != 32)
+        return set_error(SVB_ERR_FORMAT, "%s: BitsAllocated = %d", path, info->bits_allocated);
+    const int64_t need = (int64_t)info->rows * info->cols * (info->bits_allocated / 8);
+    if (info->pixel_bytes < need) return set_error(SVB_ERR_FORMAT, "%s: pixel data holds %lld bytes, %lld expected", path, (long long)info->pixel_bytes, (long long)need);
+    return SVB_OK;
+}
+
+template <typename S>
+void convert_rescaled(const uint8_t* src, size_t n, bool swap, double slope, double intercept, float* dst) {
+    const bool identity = slope == 1.0 && intercept == 0.0;
+    for (size_t i = 0; i < n; ++i) {
+        uint8_t b[sizeof(S)];
+        memcpy(b, src + i * sizeof(S), sizeof(S));
+        if (swap)
+            for (size_t k = 0; k < sizeof(S) / 2; ++k) { const uint8_t t = b[k]; b[k] = b[sizeof(S) - 1 - k]; b[sizeof(S) - 1 - k] = t; }
+        S v;
+        memcpy(&v, b, sizeof(S));
+        dst[i] = identity ? static_cast<float>(v) : static_cast<float>(static_cast<double>(v) * slope + intercept);
+    }
+}
+
+int dicom_pixels(const char* path, const svb_dicom_info* info, float* dst, size_t dst_elems) {
+    if (!path || !info || !dst) return set_error(SVB_ERR_INVALID_ARG, "dicom: null argument");
+    const size_t n = (size_t)info->rows * info->cols;
+    if (dst_elems < n) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "dicom: destination holds %zu elements, slice has %zu", dst_elems, n);
+    const size_t bytes = n * (size_t)(info->bits_allocated / 8);
+    FILE* f = fopen(path, "rb");
+    if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", path, strerror(errno));
+    std::vector<uint8_t> raw(bytes);
+    const bool ok = fseek(f, (long)info->pixel_offset, SEEK_SET) == 0 && fread(raw.data(), 1, bytes, f) == bytes;
+    fclose(f);
+    if (!ok) return set_error(SVB_ERR_IO, "%s: pixel data truncated", path);
+    const uint16_t probe = 1;
+    const bool host_big = *reinterpret_cast<const uint8_t*>(&probe) == 0;
+    const bool swap = (info->big_endian != 0) != host_big;
+    const double sl = info->rescale_slope, ic = info->rescale_intercept;
+    const bool sgn = info->pixel_representation != 0;
+    switch (info->bits_allocated) {
+        case 8: sgn ? convert_rescaled<int8_t>(raw.data(), n, false, sl, ic, dst) : convert_rescaled<uint8_t>(raw.data(), n, false, sl, ic, dst); break;
+        case 16: sgn ? convert_rescaled<int16_t>(raw.data(), n, swap, sl, ic, dst) : convert_rescaled<uint16_t>(raw.data(), n, swap, sl, ic, dst); break;
+        default: sgn ? convert_rescaled<int32_t>(raw.data(), n, swap, sl, ic, dst) : convert_rescaled<uint32_t>(raw.data(), n, swap, sl, ic, dst); break;
+    }
+    return SVB_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -384,6 +605,38 @@ int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* 
     });
     // per-file failures are the caller's to skip (the reference's drivers skip unreadable series: spider.py:139-141)
     return n_bad.load() ? set_error(SVB_ERR_IO, "mha batch: %d of %d volumes failed (see the per-file codes)", n_bad.load(), n) : SVB_OK;
+}
+
+int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* infos, int n_threads, int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!paths || !infos))) return set_error(SVB_ERR_INVALID_ARG, "dicom headers: bad arguments (n=%d)", n);
+    std::atomic<int> n_bad{0};
+    parallel_for(n, n_threads, [&](int i) {
+        const int rc = dicom_header(paths[i], &infos[i], nullptr);
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) n_bad.fetch_add(1);
+    });
+    // files that are not DICOM (or not a supported one) are the caller's to drop, like GDCM's directory scan does
+    return n_bad.load() ? set_error(SVB_ERR_FORMAT, "dicom headers: %d of %d files are not supported DICOM slices", n_bad.load(), n) : SVB_OK;
+}
+
+int svb_dicom_read_slices_f32(const char* const* paths, int n, const svb_dicom_info* infos, float* const* h_dsts,
+                              const size_t* dst_elems, int n_threads, int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!paths || !infos || !h_dsts || !dst_elems)))
+        return set_error(SVB_ERR_INVALID_ARG, "dicom slices: bad arguments (n=%d)", n);
+    std::atomic<int> first_bad{-1};
+    std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
+    parallel_for(n, n_threads, [&](int i) {
+        const int rc = dicom_pixels(paths[i], &infos[i], h_dsts[i], dst_elems[i]);
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) {
+            msgs[i] = svb_last_error();
+            int expect = -1;
+            first_bad.compare_exchange_strong(expect, i);
+        }
+    });
+    const int bad = first_bad.load();
+    if (bad >= 0) return set_error(SVB_ERR_IO, "dicom slices: file %d failed: %s", bad, msgs[bad].c_str());
+    return SVB_OK;
 }
 
 }  // extern "C"

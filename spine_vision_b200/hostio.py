@@ -8,8 +8,13 @@
 * ``write_png_batch`` mirrors ``Image.fromarray(crop).save(path)`` (spider.py:158, phenikaa.py:213) for a batch of
   equally sized uint8 crops on a thread pool.
 
-Formats that need a decoder this image does not have (DICOM series, NIfTI, NRRD) raise ``UnsupportedFormatError``;
-the dataset drivers skip such series exactly like the reference skips a series whose reader raises.
+* ``read_dicom_series`` mirrors ``read_dicom_series`` (io/readers.py:48-73: ``sitk.ImageSeriesReader`` over GDCM) for
+  native-pixel-data series, one slice per file (what the Phenikaa folders hold): the C side parses and decodes the files
+  on a thread pool, this module restates the ITK conventions around them (first series id, slices ordered along the
+  normal, origin / spacing / direction of the stack).  Parity unpinned (GDCM absent), see ``oracle/dicom.py``.
+
+Formats that need a decoder this build does not have (NIfTI, NRRD, compressed DICOM) raise ``UnsupportedFormatError`` /
+``SvbError``; the dataset drivers skip such series exactly like the reference skips a series whose reader raises.
 """
 
 from __future__ import annotations
@@ -87,6 +92,64 @@ def _volume_from(info: _lib.MhaInfo, arr: np.ndarray) -> MedicalVolume:
                          meta={"element_type": int(info.element_type), "compressed": bool(info.compressed), "ndim": int(info.ndim)})
 
 
+def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) -> MedicalVolume:
+    """``read_dicom_series`` (io/readers.py:48-73).  ITK conventions restated here (host arithmetic on a few numbers per slice):
+
+    * the directory's regular files are scanned, non-DICOM files are ignored; ``ValueError`` when none is left (:66-67);
+    * series ids = the distinct SeriesInstanceUIDs in lexicographic order, the FIRST one is read (:65, :69);
+    * slices are ordered by the projection of ImagePositionPatient on the slice normal ``row x col`` (gdcm::IPPSorter),
+      ties / missing positions by file name;
+    * ``GetOrigin`` = position of the first slice; ``GetSpacing`` = (column spacing, row spacing, |last - first| / (n - 1));
+      ``GetDirection`` columns = row cosines, column cosines, (last - first) normalised (the normal when n == 1);
+    * stored values with RescaleSlope / Intercept applied; the pixel type counts as integral when both are whole numbers.
+    """
+    lib = _lib.load()
+    folder_path = Path(folder_path)
+    files = sorted(p for p in folder_path.iterdir() if p.is_file())
+    n = len(files)
+    infos = (_lib.DicomInfo * max(n, 1))()
+    rcs = (C.c_int32 * max(n, 1))()
+    if n:
+        c_paths = (C.c_char_p * n)(*[os.fsencode(str(p)) for p in files])
+        lib.svb_dicom_read_headers(c_paths, n, infos, int(n_threads), C.addressof(rcs))
+    ok = [i for i in range(n) if rcs[i] == 0]
+    if not ok:
+        raise ValueError(f"No DICOM series found in {folder_path}")
+    uid = min(infos[i].series_uid for i in ok)
+    sel = [i for i in ok if infos[i].series_uid == uid]
+    first = infos[sel[0]]
+    row = np.array(first.orientation[0:3], dtype=np.float64)
+    col = np.array(first.orientation[3:6], dtype=np.float64)
+    normal = np.cross(row, col)
+    sel.sort(key=lambda i: (float(np.dot(np.array(infos[i].position[:]), normal)) if infos[i].has_position else 0.0, files[i].name))
+    rows, cols = first.rows, first.cols
+    for i in sel:
+        if (infos[i].rows, infos[i].cols) != (rows, cols):
+            raise ValueError(f"DICOM series in {folder_path} has slices of different sizes")
+    m = len(sel)
+    host = torch.empty(m * rows * cols, dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        host = host.pin_memory()
+    c_sel = (C.c_char_p * m)(*[os.fsencode(str(files[i])) for i in sel])
+    c_infos = (_lib.DicomInfo * m)(*[infos[i] for i in sel])
+    c_dsts = (C.c_void_p * m)(*[host.data_ptr() + 4 * k * rows * cols for k in range(m)])
+    c_sizes = (C.c_size_t * m)(*([rows * cols] * m))
+    _lib.check(lib.svb_dicom_read_slices_f32(c_sel, m, c_infos, c_dsts, c_sizes, int(n_threads), None))
+    p0 = np.array(infos[sel[0]].position[:], dtype=np.float64)
+    p1 = np.array(infos[sel[-1]].position[:], dtype=np.float64)
+    if m > 1 and float(np.linalg.norm(p1 - p0)) > 0.0:
+        dz = float(np.linalg.norm(p1 - p0)) / (m - 1)
+        third = (p1 - p0) / np.linalg.norm(p1 - p0)
+    else:
+        dz = float(first.spacing_between_slices or first.slice_thickness or 1.0)
+        third = normal
+    direction = np.stack([row, col, third], axis=1)  # columns = axes
+    integral = all(float(infos[i].rescale_slope).is_integer() and float(infos[i].rescale_intercept).is_integer() for i in sel)
+    return MedicalVolume(array=host.numpy().reshape(m, rows, cols), spacing=(float(first.pixel_spacing[1]), float(first.pixel_spacing[0]), dz),
+                         direction=tuple(float(v) for v in direction.ravel()), origin=tuple(float(v) for v in p0), integer_pixels=integral,
+                         meta={"series_uid": uid.decode("ascii", "replace"), "files": [files[i].name for i in sel]})
+
+
 def read_medical_image(path: Path) -> MedicalVolume:
     """``read_medical_image`` (io/readers.py:128-161): same error behaviour (``FileNotFoundError`` for a missing path,
     ``ValueError`` for an unknown format)."""
@@ -100,6 +163,8 @@ def read_medical_image(path: Path) -> MedicalVolume:
         arr = np.empty(n, dtype=np.float32)
         _lib.check(_lib.load().svb_mha_read_f32(os.fsencode(str(path)), C.byref(info), arr.ctypes.data, n))
         return _volume_from(info, arr)
+    if fmt == "DICOM":
+        return read_dicom_series(path)
     if fmt == "UNKNOWN":
         raise ValueError(f"Unsupported format for path: {path}")
     raise UnsupportedFormatError(f"{fmt} decoding needs SimpleITK, which this build does not link; path: {path}")

@@ -229,3 +229,125 @@ def make_spider_tree(base_path, n_patients: int = 3, seed: int = 0, in_plane=(96
         wr.writeheader()
         wr.writerows(rows)
     return pids
+
+
+# ------------------------------------------------------------------------------------------ synthetic DICOM series
+def _dcm_elem(group: int, elem: int, vr: str, value: bytes, explicit: bool = True) -> bytes:
+    import struct
+
+    if len(value) % 2:
+        value += b"\x00" if vr in ("UI", "OB", "OW") else b" "
+    tag = struct.pack("<HH", group, elem)
+    if not explicit:
+        return tag + struct.pack("<I", len(value)) + value
+    if vr in ("OB", "OW", "SQ", "UN", "UT"):
+        return tag + vr.encode() + b"\x00\x00" + struct.pack("<I", len(value)) + value
+    return tag + vr.encode() + struct.pack("<H", len(value)) + value
+
+
+def write_dicom_slice(path, pixels: np.ndarray, position, row_cos, col_cos, pixel_spacing, series_uid: str, instance: int,
+                      slice_thickness: float = 4.0, rescale=None, explicit: bool = True, with_sequence: bool = True) -> None:
+    """One single-frame MR slice as a DICOM Part-10 file with native pixel data (synthetic test / bench trees only).
+    ``explicit`` selects Explicit VR Little Endian, else Implicit VR Little Endian.  ``with_sequence`` adds a sequence and
+    an item of undefined length in front of the pixel data (real files carry them; the parser has to skip them)."""
+    import struct
+    from pathlib import Path
+
+    px = np.ascontiguousarray(pixels)
+    assert px.ndim == 2 and px.dtype in (np.uint16, np.int16, np.uint8)
+    ds = lambda vals: "\\".join(repr(float(v)) for v in vals).encode()  # noqa: E731
+    us = lambda v: struct.pack("<H", v)  # noqa: E731
+    ts = "1.2.840.10008.1.2.1" if explicit else "1.2.840.10008.1.2"
+    meta = (_dcm_elem(0x0002, 0x0001, "OB", b"\x00\x01") + _dcm_elem(0x0002, 0x0002, "UI", b"1.2.840.10008.5.1.4.1.1.4") +
+            _dcm_elem(0x0002, 0x0003, "UI", f"{series_uid}.{instance}".encode()) + _dcm_elem(0x0002, 0x0010, "UI", ts.encode()) +
+            _dcm_elem(0x0002, 0x0012, "UI", b"1.2.826.0.1.3680043.9.7433.1"))
+    meta = _dcm_elem(0x0002, 0x0000, "UL", struct.pack("<I", len(meta))) + meta
+    e = lambda g, el, vr, v: _dcm_elem(g, el, vr, v, explicit)  # noqa: E731
+    body = e(0x0008, 0x0060, "CS", b"MR")
+    if with_sequence:
+        inner = e(0x0008, 0x1150, "UI", b"1.2.840.10008.5.1.4.1.1.4")
+        item = struct.pack("<HHI", 0xFFFE, 0xE000, 0xFFFFFFFF) + inner + struct.pack("<HHI", 0xFFFE, 0xE00D, 0)
+        seq = item + struct.pack("<HHI", 0xFFFE, 0xE0DD, 0)
+        body += struct.pack("<HH", 0x0008, 0x1140) + ((b"SQ\x00\x00") if explicit else b"") + struct.pack("<I", 0xFFFFFFFF) + seq
+    body += e(0x0018, 0x0050, "DS", repr(float(slice_thickness)).encode())
+    body += e(0x0020, 0x000D, "UI", b"1.2.3.4.5") + e(0x0020, 0x000E, "UI", series_uid.encode())
+    body += e(0x0020, 0x0013, "IS", str(instance).encode())
+    body += e(0x0020, 0x0032, "DS", ds(position)) + e(0x0020, 0x0037, "DS", ds(list(row_cos) + list(col_cos)))
+    body += e(0x0028, 0x0002, "US", us(1)) + e(0x0028, 0x0004, "CS", b"MONOCHROME2")
+    body += e(0x0028, 0x0010, "US", us(px.shape[0])) + e(0x0028, 0x0011, "US", us(px.shape[1]))
+    body += e(0x0028, 0x0030, "DS", ds(pixel_spacing))
+    bits = px.dtype.itemsize * 8
+    body += e(0x0028, 0x0100, "US", us(bits)) + e(0x0028, 0x0101, "US", us(bits)) + e(0x0028, 0x0102, "US", us(bits - 1))
+    body += e(0x0028, 0x0103, "US", us(1 if px.dtype == np.int16 else 0))
+    if rescale is not None:
+        body += e(0x0028, 0x1052, "DS", repr(float(rescale[1])).encode()) + e(0x0028, 0x1053, "DS", repr(float(rescale[0])).encode())
+    body += e(0x7FE0, 0x0010, "OW" if bits > 8 else "OB", px.astype(px.dtype.newbyteorder("<"), copy=False).tobytes())
+    Path(path).write_bytes(b"\x00" * 128 + b"DICM" + meta + body)
+
+
+def write_dicom_series(folder, array_zyx: np.ndarray, spacing_xyz, direction, origin=(0.0, 0.0, 0.0), series_uid="1.2.826.1.100",
+                       explicit: bool = True, shuffle_seed: int | None = 0, rescale=None) -> None:
+    """A volume as one DICOM file per z index.  File names deliberately do NOT follow the slice order (a reader has to sort
+    by position); ``direction`` as ``image.GetDirection()`` (columns = axes)."""
+    from pathlib import Path
+
+    folder = Path(folder)
+    folder.mkdir(parents=True, exist_ok=True)
+    d = np.asarray(direction, dtype=np.float64).reshape(3, 3)
+    n = array_zyx.shape[0]
+    names = np.arange(n)
+    if shuffle_seed is not None:
+        names = np.random.default_rng(shuffle_seed).permutation(n)
+    for k in range(n):
+        pos = np.asarray(origin, dtype=np.float64) + d[:, 2] * spacing_xyz[2] * k
+        write_dicom_slice(folder / f"IM{int(names[k]):04d}.dcm", array_zyx[k], pos, d[:, 0], d[:, 1], (spacing_xyz[1], spacing_xyz[0]),
+                          series_uid, instance=n - k, slice_thickness=spacing_xyz[2], rescale=rescale, explicit=explicit)
+
+
+PHENIKAA_LABEL_COLUMNS = ["Patient ID", "IVD label", "Modic_0", "Modic_1", "Modic_2", "Modic_3", "UP endplate", "LOW endplate",
+                          "Spondylolisthesis", "Disc herniation", "Disc narrowing", "Disc bulging", "Pfirrman grade"]
+
+
+def make_phenikaa_tree(base_path, n_patients: int = 2, seed: int = 0, in_plane=(90, 84), n_slices: int = 7, spacing=(0.78, 0.82, 4.4)):
+    """A Phenikaa-shaped interim dataset under ``base_path/interim/Phenikaa`` (what ``process_phenikaa`` walks,
+    phenikaa.py:131-176): ``images/<patient>/<series folder>/*.dcm`` with the series folders named like the scanner
+    exports them ("Sag T2", "SAG  T1" -- matched case- and space-insensitively), uint16 pixels, and
+    ``radiological_labels.csv`` (levels 1 = L1/L2 ... 5 = L5/S1, one-hot Modic columns).  The first patient's T2 folder
+    also holds a second, shorter series with a lexicographically LARGER SeriesInstanceUID and a non-DICOM file; the last
+    patient has no T1 folder.  Deterministic; returns the patient ids."""
+    import csv
+    from pathlib import Path
+
+    root = Path(base_path) / "interim" / "Phenikaa"
+    (root / "images").mkdir(parents=True, exist_ok=True)
+    rng = np.random.default_rng(70_000 + seed)
+    h, w = in_plane
+    pids = [f"PK{seed:02d}{k:03d}" for k in range(n_patients)]
+    rows = []
+    for k, pid in enumerate(pids):
+        for si, folder in enumerate(("SAG  T1", "Sag T2")):
+            if si == 0 and k == n_patients - 1:
+                continue
+            vol, _, direction = make_volume(2000 * seed + 20 * k + si, n_slices, h, w, spacing)
+            arr = np.clip(np.rint(vol * (0.6 if si == 0 else 1.0)), 0, 4095).astype(np.uint16)
+            sdir = root / "images" / pid / folder
+            write_dicom_series(sdir, arr, spacing, direction, origin=(-40.0 + k, -95.5, 210.25), series_uid=f"1.2.826.1.{100 + 10 * k + si}",
+                               explicit=(k + si) % 2 == 0, shuffle_seed=seed + k + si)
+            if k == 0 and si == 1:
+                write_dicom_series(sdir / "_tmp", arr[:2] // 2, spacing, direction, series_uid="1.2.826.1.999", shuffle_seed=None)
+                for f in (sdir / "_tmp").iterdir():
+                    f.rename(sdir / f"ZZ_{f.name}")
+                (sdir / "_tmp").rmdir()
+                (sdir / "notes.txt").write_text("not a DICOM file\n")
+        for lvl in range(1, 6):
+            modic = int(rng.integers(0, 4))
+            row = {"Patient ID": pid, "IVD label": lvl, "UP endplate": int(rng.integers(0, 2)), "LOW endplate": int(rng.integers(0, 2)),
+                   "Spondylolisthesis": int(rng.integers(0, 2)), "Disc herniation": int(rng.integers(0, 2)),
+                   "Disc narrowing": int(rng.integers(0, 2)), "Disc bulging": int(rng.integers(0, 2)), "Pfirrman grade": int(rng.integers(1, 6))}
+            row.update({f"Modic_{i}": int(i == modic) for i in range(4)})
+            rows.append(row)
+    with open(root / "radiological_labels.csv", "w", newline="") as f:
+        wr = csv.DictWriter(f, fieldnames=PHENIKAA_LABEL_COLUMNS)
+        wr.writeheader()
+        wr.writerows(rows)
+    return pids

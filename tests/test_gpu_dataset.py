@@ -1,5 +1,5 @@
 """GPU parity of the drop-in entry point: ``spine_vision_b200.dataset.create_classification_dataset`` on a synthetic
-SPIDER tree vs what the reference's OWN ``create_classification_dataset`` wrote for the same tree
+SPIDER tree (MetaImage volumes) + Phenikaa tree (DICOM series folders) vs what the reference's OWN ``create_classification_dataset`` wrote for the same tree
 (tests/golden/host_dataset.npz, frozen by oracle/make_golden_host.py: PNG pixels and CSV text), both crop modes, plus the
 resume run and the checkpoint path.  Every pixel comes through the C ABI (native MetaImage decode -> K0 -> K3 -> native PNG)."""
 import numpy as np
@@ -34,7 +34,8 @@ def test_create_classification_dataset_matches_reference_driver(tmp_path):
     for mode in ("horizontal", "rotated"):
         base = tmp_path / mode
         synthetic.make_spider_tree(base, seed=0)
-        cfg = _config(base, mode, g, chunk_series=2 if mode == "horizontal" else 64)  # several GPU batches / one batch
+        synthetic.make_phenikaa_tree(base, seed=0)  # DICOM series folders: the second source of the reference's driver
+        cfg = _config(base, mode, g, chunk_series=3 if mode == "horizontal" else 64)  # several GPU batches / one batch
         res = dataset.create_classification_dataset(cfg)
         names = [str(n) for n in g[f"{mode}_names"]]
         assert res.num_samples == len(names) and res.output_path == cfg.output_path
@@ -49,7 +50,8 @@ def test_create_classification_dataset_matches_reference_driver(tmp_path):
             _check_tree(cfg.output_path, names, g["horizontal_images"])
             got = (cfg.output_path / "annotations.csv").read_text().strip().split("\n")
             want = g["resume_csv"].item().strip().split("\n")
-            assert got[0] == want[0] and got[-2:] == want[-2:] and sorted(got) == sorted(want)
+            nd = len(g["delete_for_resume"])
+            assert got[0] == want[0] and got[-nd:] == want[-nd:] and sorted(got) == sorted(want)
             # nothing missing -> nothing to do, CSV rebuilt from the label file alone
             res3 = dataset.create_classification_dataset(cfg)
             assert res3.num_samples == len(names) and "0 new" in res3.summary

@@ -9,7 +9,7 @@ import pytest
 from PIL import Image
 
 from conftest import GOLDEN
-from oracle import metaimage
+from oracle import dicom, metaimage
 from spine_vision_b200 import _lib, dataset, hostio, synthetic
 
 
@@ -44,9 +44,9 @@ def test_metaimage_2d_and_errors(tmp_path):
     (tmp_path / "x.bin").write_bytes(b"123")
     with pytest.raises(ValueError, match="Unsupported format"):
         hostio.read_medical_image(tmp_path / "x.bin")  # io/readers.py:160-161
-    (tmp_path / "series").mkdir()
+    (tmp_path / "v.nii.gz").write_bytes(b"\x1f\x8b")
     with pytest.raises(hostio.UnsupportedFormatError):
-        hostio.read_medical_image(tmp_path / "series")  # DICOM directory: no decoder in this build
+        hostio.read_medical_image(tmp_path / "v.nii.gz")  # NIfTI / NRRD: no decoder in this build (not on the dataset path)
     (tmp_path / "bad.mha").write_text("hello\nworld\n")
     with pytest.raises(_lib.SvbError):
         hostio.read_medical_image(tmp_path / "bad.mha")
@@ -105,23 +105,32 @@ def _lines(text):
     return text.strip().split("\n")
 
 
+def _records(jobs):
+    return [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, lvl), j.patient_id, lvl, j.series_type, row)
+            for j in jobs for lvl, row in j.levels.items()]
+
+
 def test_work_list_records_and_csv_match_reference_driver(tmp_path):
     """The host logic alone (no pixels): jobs in the reference's iteration order, records, CSV text == what the
-    reference's create_classification_dataset wrote for the same tree; then its resume behaviour."""
+    reference's create_classification_dataset wrote for the same trees; then its resume behaviour."""
     g = np.load(GOLDEN / "host_dataset.npz")
     synthetic.make_spider_tree(tmp_path, seed=0)
+    synthetic.make_phenikaa_tree(tmp_path, seed=0)
     cfg = dataset.ClassificationDatasetConfig(base_path=tmp_path, output_name="cls", crop_size=(128, 128))
     assert cfg.spider_path == tmp_path / "raw" / "SPIDER" and cfg.output_path == tmp_path / "processed" / "cls"
-    jobs = dataset.collect_spider_jobs(cfg, set())
-    assert [(j.patient_id, j.series_type) for j in jobs] == [("1", "sag_t1"), ("1", "sag_t2"), ("4", "sag_t1"), ("4", "sag_t2"), ("7", "sag_t2")]
-    assert sorted(jobs[-1].levels) == [1, 2, 3, 4]  # SPIDER level 7 -> -1 is dropped, dataset level 5 has no row
-    recs = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, lvl), j.patient_id, lvl, j.series_type, row)
-            for j in jobs for lvl, row in j.levels.items()]
-    dataset.write_annotations(tmp_path / "a.csv", recs)
+    assert cfg.phenikaa_path == tmp_path / "interim" / "Phenikaa"
+    sj = dataset.collect_spider_jobs(cfg, set())
+    assert [(j.patient_id, j.series_type) for j in sj] == [("1", "sag_t1"), ("1", "sag_t2"), ("4", "sag_t1"), ("4", "sag_t2"), ("7", "sag_t2")]
+    assert sorted(sj[-1].levels) == [1, 2, 3, 4]  # SPIDER level 7 -> -1 is dropped, dataset level 5 has no row
+    pj = dataset.collect_phenikaa_jobs(cfg, set())
+    assert [(j.patient_id, j.series_type, j.path.name) for j in pj] == [("PK00000", "sag_t1", "SAG  T1"), ("PK00000", "sag_t2", "Sag T2"),
+                                                                        ("PK00001", "sag_t2", "Sag T2")]  # phenikaa.py:48-65 folder match
+    dataset.write_annotations(tmp_path / "a.csv", _records(pj + sj))  # __init__.py:199-214: Phenikaa first, then SPIDER
     assert (tmp_path / "a.csv").read_text() == g["horizontal_csv"].item()
-    assert dataset.collect_phenikaa_jobs(cfg, set()) == []  # no Phenikaa tree: warns and returns nothing (phenikaa.py:137-139)
+    empty = dataset.ClassificationDatasetConfig(base_path=tmp_path / "nowhere", output_name="x")
+    assert dataset.collect_phenikaa_jobs(empty, set()) == [] and dataset.collect_spider_jobs(empty, set()) == []  # labels missing: warn, no jobs
 
-    # resume: every image exists except two -> only those two levels are jobs; recovered records come from the label file
+    # resume: every image exists except three -> only those levels are jobs; recovered records come from the label files
     names = [str(n) for n in g["horizontal_names"]]
     deleted = [str(n) for n in g["delete_for_resume"]]
     images = cfg.output_path / "images"
@@ -131,16 +140,59 @@ def test_work_list_records_and_csv_match_reference_driver(tmp_path):
             (images / n).write_bytes(b"")
     existing = dataset.scan_existing_images(images)
     assert sorted(e.filename for e in existing) == sorted(set(names) - set(deleted))
-    jobs2 = dataset.collect_spider_jobs(cfg, {f"images/{e.filename}" for e in existing})
-    assert [(j.patient_id, j.series_type, sorted(j.levels)) for j in jobs2] == [("4", "sag_t1", [2]), ("7", "sag_t2", [4])]
+    have = {f"images/{e.filename}" for e in existing}
+    jobs2 = dataset.collect_phenikaa_jobs(cfg, have) + dataset.collect_spider_jobs(cfg, have)
+    assert [(j.patient_id, j.series_type, sorted(j.levels)) for j in jobs2] == [("PK00000", "sag_t2", [3]), ("4", "sag_t1", [2]), ("7", "sag_t2", [4])]
     ph, sp = dataset.recover_annotations(existing, cfg.spider_path / "radiological_gradings.csv", cfg.phenikaa_path / "radiological_labels.csv")
-    new = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, lvl), j.patient_id, lvl, j.series_type, row)
-           for j in jobs2 for lvl, row in j.levels.items()]
-    dataset.write_annotations(tmp_path / "b.csv", ph + sp + new)
+    dataset.write_annotations(tmp_path / "b.csv", ph + sp + _records(jobs2))
     got, want = _lines((tmp_path / "b.csv").read_text()), _lines(g["resume_csv"].item())
     # recovered rows follow the directory listing order (spider.py:237: glob), which is filesystem-defined: compare as a set;
     # the new rows come last, in job order
-    assert got[0] == want[0] and got[-2:] == want[-2:] and sorted(got) == sorted(want) and ph == []
+    assert got[0] == want[0] and got[-3:] == want[-3:] and sorted(got) == sorted(want) and len(ph) == 14
+
+
+@pytest.mark.parametrize("explicit", [True, False])
+@pytest.mark.parametrize("dtype,rescale", [("uint16", None), ("int16", None), ("uint8", None), ("uint16", (2.0, -1024.0)), ("uint16", (0.5, 0.25))])
+def test_dicom_series_reader_matches_oracle(tmp_path, explicit, dtype, rescale):
+    """Native DICOM slice decoder + the ITK series conventions (hostio.read_dicom_series) vs oracle/dicom.py: scrambled
+    file names, a second series with a larger UID and a stray text file in the folder, sequences of undefined length,
+    oblique orientation, rescale."""
+    rng = np.random.default_rng(zlib.crc32(f"{dtype}-{explicit}-{rescale}".encode()))
+    info = np.iinfo(dtype)
+    arr = rng.integers(max(info.min, -2000), min(info.max, 4000), size=(6, 17, 23)).astype(dtype)
+    th = 0.2
+    direction = np.array([[0.0, 0.0, 1.0], [np.cos(th), np.sin(th), 0.0], [np.sin(th), -np.cos(th), 0.0]])  # columns = axes, oblique
+    folder = tmp_path / "Sag T2"
+    synthetic.write_dicom_series(folder, arr, (0.61, 0.73, 3.3), direction.ravel(), origin=(12.5, -40.0, 7.0), series_uid="1.2.3.50",
+                                 explicit=explicit, shuffle_seed=3, rescale=rescale)
+    synthetic.write_dicom_series(tmp_path / "other", arr[:2], (0.61, 0.73, 3.3), direction.ravel(), series_uid="1.2.3.77", shuffle_seed=None)
+    for f in (tmp_path / "other").iterdir():
+        f.rename(folder / f"A_{f.name}")  # sorts in front by name, behind by series id
+    (folder / "readme.txt").write_text("x")
+    want = dicom.read_series(folder)
+    got = hostio.read_medical_image(folder)
+    assert got.array.shape == (6, 17, 23) and got.meta["series_uid"] == "1.2.3.50"
+    assert np.array_equal(got.array, want.array.astype(np.float32))
+    assert np.allclose(got.spacing, want.GetSpacing(), rtol=0, atol=1e-12) and np.allclose(got.spacing, (0.61, 0.73, 3.3), atol=1e-9)
+    assert np.allclose(got.direction, want.GetDirection(), atol=1e-12) and np.allclose(got.origin, want.GetOrigin(), atol=1e-12)
+    assert got.integer_pixels == (rescale is None or rescale == (2.0, -1024.0))
+    # slices come back ordered along the normal (row x col), whatever the file names say
+    normal = np.cross(direction[:, 0], direction[:, 1])
+    stack = np.array(got.direction).reshape(3, 3)[:, 2]
+    assert abs(float(np.dot(stack, normal))) > 0.999
+    vals = arr.astype(np.float64) * (rescale[0] if rescale else 1.0) + (rescale[1] if rescale else 0.0)
+    order = slice(None) if float(np.dot(direction[:, 2], normal)) > 0 else slice(None, None, -1)
+    assert np.array_equal(got.array, vals[order].astype(np.float32))
+
+
+def test_dicom_errors(tmp_path):
+    (tmp_path / "empty").mkdir()
+    with pytest.raises(ValueError, match="No DICOM series found"):  # io/readers.py:66-67
+        hostio.read_medical_image(tmp_path / "empty")
+    (tmp_path / "junk").mkdir()
+    (tmp_path / "junk" / "a.dcm").write_bytes(b"\x00" * 200)
+    with pytest.raises(ValueError, match="No DICOM series found"):
+        hostio.read_medical_image(tmp_path / "junk")
 
 
 def test_metaimage_writer_is_plain_zlib(tmp_path):
