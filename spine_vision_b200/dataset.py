@@ -305,45 +305,61 @@ def _read_chunk(jobs: list[SeriesJob], n_threads: int):
 
 def process_jobs(jobs: list[SeriesJob], config: ClassificationDatasetConfig, output_images_path: Path,
                  model: LocalizationModel | None) -> list[ClassificationRecord]:
-    """Steps 2 and 3 of the module docstring for a list of jobs; returns the records of the crops written."""
+    """Steps 2 and 3 of the module docstring for a list of jobs; returns the records of the crops written.
+    The three stages overlap across chunks: while the GPU works on chunk i, one host thread decodes chunk i+1 and another
+    encodes / writes the PNGs of chunk i-1 (the native decoders and the encoder release the GIL and fan out themselves)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     records: list[ClassificationRecord] = []
     ch, cw = int(config.crop_size[0]), int(config.crop_size[1])
-    for c0 in range(0, len(jobs), max(1, config.chunk_series)):
-        chunk = jobs[c0 : c0 + max(1, config.chunk_series)]
-        vols = _read_chunk(chunk, config.io_threads)
-        live = []
-        for j, v in zip(chunk, vols):
-            if v is None:
+    step = max(1, config.chunk_series)
+    chunks = [jobs[c0 : c0 + step] for c0 in range(0, len(jobs), step)]
+    if not chunks:
+        return records
+    with ThreadPoolExecutor(max_workers=2) as pool_io:
+        next_read = pool_io.submit(_read_chunk, chunks[0], config.io_threads)
+        pending_write = None
+        for ci, chunk in enumerate(chunks):
+            vols = next_read.result()
+            if ci + 1 < len(chunks):
+                next_read = pool_io.submit(_read_chunk, chunks[ci + 1], config.io_threads)
+            live = []
+            for j, v in zip(chunk, vols):
+                if v is None:
+                    continue
+                if v.array.ndim != 3 or min(v.array.shape) < 1:
+                    logger.debug("Error processing %s: not a 3-D volume", j.path)
+                    continue
+                try:
+                    volumes.lpi_axes(v.direction)
+                except ValueError as e:
+                    logger.debug("Error processing %s: %s", j.path, e)
+                    continue
+                live.append((j, v))
+            if not live:
                 continue
-            if v.array.ndim != 3 or min(v.array.shape) < 1:
-                logger.debug("Error processing %s: not a 3-D volume", j.path)
-                continue
-            try:
-                volumes.lpi_axes(v.direction)
-            except ValueError as e:
-                logger.debug("Error processing %s: %s", j.path, e)
-                continue
-            live.append((j, v))
-        if not live:
-            continue
-        pool, spacings = volumes.midplane_resample([v.array for _, v in live], [v.spacing for _, v in live],
-                                                   [v.direction for _, v in live], config.device,
-                                                   integer_pixels=[v.integer_pixels for _, v in live])
-        batch = pipeline.localize_and_crop(pool, model, crop_delta_mm=config.crop_delta_mm, crop_size=(ch, cw),
-                                           image_size=config.image_size, second_size=None, spacings=spacings,
-                                           crop_mode=config.crop_mode, last_disc_angle_boost=config.last_disc_angle_boost)
-        crops = batch.crops.cpu().numpy()  # [B, 5, ch, cw]
-        sel, paths, recs = [], [], []
-        for b, (j, _) in enumerate(live):
-            for lvl, row in j.levels.items():
-                name = output_filename(j.source, j.patient_id, j.series_type, lvl)
-                sel.append((b, lvl - 1))
-                paths.append(output_images_path / name)
-                recs.append(make_record(j.source, name, j.patient_id, lvl, j.series_type, row))
-        if sel:
-            bi, li = zip(*sel)
-            hostio.write_png_batch(crops[list(bi), list(li)], paths, config.png_level, config.io_threads)
-            records.extend(recs)
+            pool, spacings = volumes.midplane_resample([v.array for _, v in live], [v.spacing for _, v in live],
+                                                       [v.direction for _, v in live], config.device,
+                                                       integer_pixels=[v.integer_pixels for _, v in live])
+            batch = pipeline.localize_and_crop(pool, model, crop_delta_mm=config.crop_delta_mm, crop_size=(ch, cw),
+                                               image_size=config.image_size, second_size=None, spacings=spacings,
+                                               crop_mode=config.crop_mode, last_disc_angle_boost=config.last_disc_angle_boost)
+            crops = batch.crops.cpu().numpy()  # [B, 5, ch, cw]
+            sel, paths, recs = [], [], []
+            for b, (j, _) in enumerate(live):
+                for lvl, row in j.levels.items():
+                    name = output_filename(j.source, j.patient_id, j.series_type, lvl)
+                    sel.append((b, lvl - 1))
+                    paths.append(output_images_path / name)
+                    recs.append(make_record(j.source, name, j.patient_id, lvl, j.series_type, row))
+            if sel:
+                bi, li = zip(*sel)
+                if pending_write is not None:
+                    pending_write.result()  # raises if a file of the previous chunk could not be written
+                pending_write = pool_io.submit(hostio.write_png_batch, crops[list(bi), list(li)], paths, config.png_level, config.io_threads)
+                records.extend(recs)
+        if pending_write is not None:
+            pending_write.result()
     return records
 
 
