@@ -629,9 +629,10 @@ static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out,
 }
 template <typename T>
 static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int Cin, int nb, int H, int W, cudaStream_t st) {
-    const long long tokens = (long long)nb * H * W;
-    long long blocks = ceil_div<long long>(tokens, 8);
-    if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+    const int pg = Cin <= 512 ? 4 : 2;  // LnPatchifyPG: x-adjacent tokens per warp iteration
+    const long long groups = (long long)nb * H * ceil_div(W, pg);
+    long long blocks = ceil_div<long long>(groups, 8);
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
     const T* xp = static_cast<const T*>(x);
     T* ap = static_cast<T*>(a2);
     switch (Cin) {
@@ -642,6 +643,35 @@ static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int 
         default: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "ln_patchify: unsupported width %d", Cin);
     }
     SVB_LAUNCHED();
+    return SVB_OK;
+}
+
+template <typename T>
+static int launch_head(const T* x, int nb, int tokens, int C, const float* n0w, const float* n0b, const float* n1w, const float* n1b,
+                       const float* w1, const float* b1, int hid, const float* w2, const float* b2, int nout, float* coords,
+                       cudaStream_t st) {
+    const size_t smem = (size_t)(C + hid + 8 + C + 8 * C) * 4;  // feat, hidden, reduction scratch, pool share, per-warp pools
+    SVB_REQUIRE(smem <= 99 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
+    auto kern = head_kernel<T>;
+    static size_t attr_smem = 0;
+    if (smem > 48 * 1024 && smem > attr_smem) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)nb * HEAD_CLUSTER);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = HEAD_CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, tokens, C, n0w, n0b, n1w, n1b, w1, b1, hid, w2, b2, nout, coords));
+    count_launch();
     return SVB_OK;
 }
 
@@ -740,12 +770,10 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
     }
     {
         const int C = m->dims[3];
-        const size_t smem = (size_t)(C + m->hid + 8 + 8 * C) * 4;
-        SVB_REQUIRE(smem <= 48 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
         if (int rc = tm.begin(SVB_KC_HEAD)) return rc;
-        head_kernel<T><<<nb, 256, smem, st>>>(X, h * w, C, m->hn0w, m->hn0b, m->hn1w, m->hn1b, m->hw1, m->hb1, m->hid, m->hw2,
-                                              m->hb2, m->nout, coords);
-        SVB_LAUNCHED();
+        if (int rc = launch_head<T>(X, nb, h * w, C, m->hn0w, m->hn0b, m->hn1w, m->hn1b, m->hw1, m->hb1, m->hid, m->hw2, m->hb2,
+                                    m->nout, coords, st))
+            return rc;
         if (int rc = tm.end()) return rc;
     }
 #undef RUN
@@ -951,14 +979,8 @@ extern "C" int svb_head(const void* d_x, int B, int tokens, int C, const float* 
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     if (int rc = check_device_sm100()) return rc;
     SVB_REQUIRE(d_x && d_coords && B > 0 && tokens > 0 && C % 8 == 0, SVB_ERR_INVALID_ARG, "head: bad arguments (C must be a multiple of 8)");
-    const size_t smem = (size_t)(C + HID + 8 + 8 * C) * 4;
-    SVB_REQUIRE(smem <= 48 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
     if (dtype == SVB_FP16)
-        head_kernel<__half><<<B, 256, smem, st>>>(static_cast<const __half*>(d_x), tokens, C, n0w, n0b, n1w, n1b, w1, b1, HID,
-                                                  w2, b2, NOUT, d_coords);
-    else
-        head_kernel<__nv_bfloat16><<<B, 256, smem, st>>>(static_cast<const __nv_bfloat16*>(d_x), tokens, C, n0w, n0b, n1w,
-                                                         n1b, w1, b1, HID, w2, b2, NOUT, d_coords);
-    SVB_LAUNCHED();
-    return SVB_OK;
+        return launch_head<__half>(static_cast<const __half*>(d_x), B, tokens, C, n0w, n0b, n1w, n1b, w1, b1, HID, w2, b2, NOUT, d_coords, st);
+    return launch_head<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(d_x), B, tokens, C, n0w, n0b, n1w, n1b, w1, b1, HID, w2, b2, NOUT,
+                                      d_coords, st);
 }

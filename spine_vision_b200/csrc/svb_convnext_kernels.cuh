@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const 
             for (int j = 0; j < NP; ++j) acc[k][j] = bias2[j];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const float f = (float)((px[k][q >> 2] >> (8 * (q & 3))) & 0xFFu);
+                // u8 -> f32 without the conversion unit (I2F runs on the XU pipe at 16 lanes/clk/SM and bounded this kernel):
+                // PRMT drops the byte into the mantissa of 2^23, one FADD removes the 2^23 -- exact for 0..255
+                const float f = __uint_as_float(__byte_perm(px[k][q >> 2], 0x4B000000u, 0x7650u | (uint32_t)(q & 3))) - 8388608.0f;
                 const uint64_t f2 = pk2(f, f);
 #pragma unroll
                 for (int j = 0; j < NP; ++j) acc[k][j] = fma2(f2, w2[j][q], acc[k][j]);
@@ -1343,50 +1345,76 @@ dwconv_ln_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
 // ============================================================================ LayerNorm2d + 2x2/s2 patchify
 // x [B,H,W,C] -> a2 [B,H/2,W/2,4C] with k = (ky*2+kx)*C + c, the A operand of the downsample GEMM
 // (timm stage.downsample = LayerNorm2d -> Conv2d(k=2,s=2)).
+template <int C> struct LnPatchifyPG { static constexpr int value = C <= 512 ? 4 : 2; };
+
 template <typename T, int C>
 __global__ void __launch_bounds__(256) ln_patchify_kernel(const T* __restrict__ x, const float* __restrict__ lnw,
                                                           const float* __restrict__ lnb, T* __restrict__ a2, int B, int H,
                                                           int W) {
+    // One warp = PG x-adjacent tokens per iteration: PG independent load / reduction chains in flight, the index arithmetic
+    // (three divisions) paid once per PG tokens, and the two LayerNorm reductions of all PG tokens in one recursive-halving
+    // pass (warp_sum4).  A lane owns 4 consecutive channels of every 128-channel group.
     constexpr int V4 = C / 128;
+    constexpr int PG = LnPatchifyPG<C>::value;  // 4, or 2 at C = 1024 (registers)
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const long long tokens = (long long)B * H * W;
     const int Ho = H >> 1, Wo = W >> 1;
-    for (long long t = warp; t < tokens; t += nwarps) {
-        const int b = (int)(t / ((long long)H * W));
-        const int rem = (int)(t - (long long)b * H * W);
-        const int y = rem / W, xx = rem - y * W;
-        if ((y >> 1) >= Ho || (xx >> 1) >= Wo) continue;
-        const uint2* xp = reinterpret_cast<const uint2*>(x + (size_t)t * C);
-        float4 v[V4];
-        float s = 0.f;
+    const int Wq = (W + PG - 1) / PG;
+    const long long quads = (long long)B * H * Wq;
+    for (long long qd = warp; qd < quads; qd += nwarps) {
+        const long long row = qd / Wq;  // b * H + y
+        const int x0 = (int)(qd - row * Wq) * PG;
+        const long long b = row / H;
+        const int y = (int)(row - b * H);
+        if ((y >> 1) >= Ho) continue;  // odd H: the last row has no 2x2 patch
+        bool ok[PG];
+        float4 v[PG][V4];
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            const uint2 u = __ldg(xp + lane + 32 * j);
-            const float2 a = Cvt<T>::unpack2(u.x), c = Cvt<T>::unpack2(u.y);
-            v[j] = make_float4(a.x, a.y, c.x, c.y);
-            s += (a.x + a.y) + (c.x + c.y);
+        for (int p = 0; p < PG; ++p) {
+            const int xx = x0 + p;
+            ok[p] = xx < W && (xx >> 1) < Wo;
+            const uint2* xp = reinterpret_cast<const uint2*>(x + ((size_t)row * W + (ok[p] ? xx : x0)) * C);
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < V4; ++j) {
+                const uint2 u = __ldg(xp + lane + 32 * j);
+                const float2 lo = Cvt<T>::unpack2(u.x), hi = Cvt<T>::unpack2(u.y);
+                v[p][j] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                a += (lo.x + lo.y) + (hi.x + hi.y);
+            }
+            s[p] = a;
         }
-        const float mean = warp_sum(s) * (1.0f / C);
-        float q = 0.f;
+        warp_sum4(s, lane);
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            const float a = v[j].x - mean, bb = v[j].y - mean, cc = v[j].z - mean, d = v[j].w - mean;
-            q += (a * a + bb * bb) + (cc * cc + d * d);
+        for (int p = 0; p < PG; ++p) {
+            const float mean = s[p] * (1.0f / C);
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j < V4; ++j) {
+                v[p][j].x -= mean; v[p][j].y -= mean; v[p][j].z -= mean; v[p][j].w -= mean;
+                a += (v[p][j].x * v[p][j].x + v[p][j].y * v[p][j].y) + (v[p][j].z * v[p][j].z + v[p][j].w * v[p][j].w);
+            }
+            q[p] = a;
         }
-        const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + LN_EPS_BACKBONE);
-        const size_t orow = ((size_t)b * Ho + (y >> 1)) * Wo + (xx >> 1);
-        uint2* op = reinterpret_cast<uint2*>(a2 + orow * (4 * C) + (size_t)(((y & 1) << 1) | (xx & 1)) * C);
+        warp_sum4(q, lane);
 #pragma unroll
-        for (int j = 0; j < V4; ++j) {
-            const int c4 = lane + 32 * j;
-            const float4 g = __ldg(reinterpret_cast<const float4*>(lnw) + c4);
-            const float4 be = __ldg(reinterpret_cast<const float4*>(lnb) + c4);
-            uint2 o;
-            o.x = Cvt<T>::pack2(fmaf((v[j].x - mean) * rstd, g.x, be.x), fmaf((v[j].y - mean) * rstd, g.y, be.y));
-            o.y = Cvt<T>::pack2(fmaf((v[j].z - mean) * rstd, g.z, be.z), fmaf((v[j].w - mean) * rstd, g.w, be.w));
-            op[c4] = o;
+        for (int p = 0; p < PG; ++p) {
+            if (!ok[p]) continue;  // warp-uniform
+            const int xx = x0 + p;
+            const float rstd = 1.0f / sqrtf(q[p] * (1.0f / C) + LN_EPS_BACKBONE);
+            const size_t orow = ((size_t)b * Ho + (y >> 1)) * Wo + (xx >> 1);
+            uint2* op = reinterpret_cast<uint2*>(a2 + orow * (4 * C) + (size_t)(((y & 1) << 1) | (xx & 1)) * C);
+#pragma unroll
+            for (int j = 0; j < V4; ++j) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(lnw) + lane + 32 * j);  // L1-resident after the first token
+                const float4 be = __ldg(reinterpret_cast<const float4*>(lnb) + lane + 32 * j);
+                uint2 o;
+                o.x = Cvt<T>::pack2(fmaf(v[p][j].x * rstd, g.x, be.x), fmaf(v[p][j].y * rstd, g.y, be.y));
+                o.y = Cvt<T>::pack2(fmaf(v[p][j].z * rstd, g.z, be.z), fmaf(v[p][j].w * rstd, g.w, be.w));
+                op[lane + 32 * j] = o;
+            }
         }
     }
 }
@@ -1406,6 +1434,12 @@ __device__ __forceinline__ float block_sum_256(float v, float* s_red) {
     return r;
 }
 
+// One image = one CLUSTER of HEAD_CLUSTER CTAs (a single CTA per image left 111 SMs idle and spent its time waiting on
+// its own 512 KB of activations and 1 MB of Linear weights): every CTA pools 1/8 of the tokens, the partial sums meet
+// through distributed shared memory (fixed order, so all ranks hold the same bits), every CTA runs the two cheap
+// LayerNorms redundantly and computes 1/8 of the hidden layer into rank 0's shared memory; rank 0 finishes.
+constexpr int HEAD_CLUSTER = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,tokens,C]*/, int tokens, int C,
                                                    const float* __restrict__ n0w, const float* __restrict__ n0b,
@@ -1415,19 +1449,21 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
                                                    const float* __restrict__ b2, int NOUT, float* __restrict__ coords) {
     extern __shared__ __align__(16) float sm[];
     float* s_feat = sm;              // [C]
-    float* s_hid = sm + C;           // [HID]
+    float* s_hid = sm + C;           // [HID]   (rank 0's copy is the live one)
     float* s_red = s_hid + HID;      // [8]
-    float* s_part = s_red + 8;       // [8][C] per-warp partial pools
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float* s_sum = s_red + 8;        // [C]     this CTA's share of the pool, read by every rank of the cluster
+    float* s_part = s_sum + C;       // [8][C]  per-warp partial pools
+    const uint32_t rank = cluster_ctarank();
+    const int b = blockIdx.x / HEAD_CLUSTER, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const T* xb = x + (size_t)b * tokens * C;
-    // global average pool: warp w sums tokens w, w+8, ...; a lane owns 8 consecutive channels per 256-channel group
-    // (128-bit loads, every load independent); the 8 partial sums meet in shared memory.
+    // global average pool: warp w of rank r sums tokens 8r + w, + 64, ...; a lane owns 8 consecutive channels per
+    // 256-channel group (128-bit loads, every load independent)
     for (int c0 = 0; c0 < C; c0 += 256) {
         const int c = c0 + lane * 8;
         float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (c + 8 <= C) {
 #pragma unroll 4
-            for (int t = wid; t < tokens; t += 8) {
+            for (int t = (int)rank * 8 + wid; t < tokens; t += 8 * HEAD_CLUSTER) {
                 const uint4 u = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)t * C + c));
                 const float2 p0 = Cvt<T>::unpack2(u.x), p1 = Cvt<T>::unpack2(u.y), p2 = Cvt<T>::unpack2(u.z), p3 = Cvt<T>::unpack2(u.w);
                 a[0] += p0.x; a[1] += p0.y; a[2] += p1.x; a[3] += p1.y;
@@ -1442,6 +1478,13 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
         float v = 0.f;
 #pragma unroll
         for (int w = 0; w < 8; ++w) v += s_part[w * C + c];
+        s_sum[c] = v;
+    }
+    cluster_sync_all();
+    for (int c = tid; c < C; c += 256) {
+        float v = 0.f;
+#pragma unroll
+        for (int r = 0; r < HEAD_CLUSTER; ++r) v += ld_cluster_f32(mapa_shared(smem_u32(s_sum + c), (uint32_t)r));
         s_feat[c] = v / (float)tokens;
     }
     __syncthreads();
@@ -1459,8 +1502,11 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
         for (int c = tid; c < C; c += 256) s_feat[c] = fmaf((s_feat[c] - mean) * rstd, gw[c], gb[c]);
         __syncthreads();
     }
-    // Linear(C, HID) + exact GELU: one warp per output, lanes stride the row in float4
-    for (int j = wid; j < HID; j += 8) {
+    // Linear(C, HID) + exact GELU: this rank's slice of the outputs, one warp per output, lanes stride the row in float4;
+    // the result goes straight into rank 0's hidden vector
+    const int per = (HID + HEAD_CLUSTER - 1) / HEAD_CLUSTER;
+    const int j_end = min(HID, ((int)rank + 1) * per);
+    for (int j = (int)rank * per + wid; j < j_end; j += 8) {
         const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)j * C);
         const float4* fr = reinterpret_cast<const float4*>(s_feat);
         float s = 0.f;
@@ -1471,9 +1517,10 @@ __global__ void __launch_bounds__(256) head_kernel(const T* __restrict__ x /*[B,
             s = fmaf(w.x, f.x, s); s = fmaf(w.y, f.y, s); s = fmaf(w.z, f.z, s); s = fmaf(w.w, f.w, s);
         }
         s = warp_sum(s);
-        if (lane == 0) s_hid[j] = gelu_exact(s + b1[j]);
+        if (lane == 0) st_cluster_f32(mapa_shared(smem_u32(s_hid + j), 0), gelu_exact(s + b1[j]));
     }
-    __syncthreads();
+    cluster_sync_all();  // release / acquire: the remote stores are visible to rank 0; the other ranks are done
+    if (rank != 0) return;
     for (int j = wid; j < NOUT; j += 8) {
         const float* wr = w2 + (size_t)j * HID;
         float s = 0.f;
