@@ -729,7 +729,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
     {
         const long long tokens = (long long)nb * (H / 4) * (W / 4);
         long long blocks = ceil_div<long long>(tokens, 8 * STEM_TPW * 4);
-        if (blocks > (long long)num_sms() * 2) blocks = (long long)num_sms() * 2;
+        if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;  // stem_ln_kernel: 4 resident CTAs per SM
         if (blocks < 1) blocks = 1;
         if (int rc = tm.begin(SVB_KC_STEM)) return rc;
         if (m->dims[0] == 128)
@@ -877,7 +877,7 @@ static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const
                       int B, int H, int W, int C0, cudaStream_t st) {
     const long long tokens = (long long)B * (H / 4) * (W / 4);
     long long blocks = ceil_div<long long>(tokens, 8 * STEM_TPW * 4);
-    if (blocks > (long long)num_sms() * 2) blocks = (long long)num_sms() * 2;
+    if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;  // stem_ln_kernel: 4 resident CTAs per SM
     if (blocks < 1) blocks = 1;
     if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);

@@ -48,29 +48,37 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 constexpr int STEM_TPW = 4;  // the 128-bit pixel-row load below assumes 4
 
 template <typename T, int CPL>
-__global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
+__global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
                                                          const float* __restrict__ bf, const float* __restrict__ lnw,
                                                          const float* __restrict__ lnb, T* __restrict__ out, int B, int H,
                                                          int W) {
     static_assert(CPL % 2 == 0, "stem packs channel pairs");
     constexpr int C0 = 32 * CPL, NP = CPL / 2, TPW = STEM_TPW;
+    // folded weights as packed channel pairs in shared memory, [tap][pair j][lane]: a warp's read of one (tap, j) is 256
+    // contiguous bytes.  (In registers they cost 32 * NP registers per thread and held the kernel at 16 warps per SM, where
+    // it is latency-bound; from shared memory each value is read once per TPW tokens.)
+    __shared__ uint64_t s_w[16][NP][32];
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int Ho = H >> 2, Wo = W >> 2;
     const long long tokens = (long long)B * Ho * Wo;
 
-    uint64_t w2[NP][16], bias2[NP];
+    for (int i = threadIdx.x; i < 16 * NP * 32; i += blockDim.x) {
+        const int l = i & 31, j = (i >> 5) % NP, p = i / (32 * NP);
+        const int c = l * CPL + 2 * j;
+        s_w[p][j][l] = pk2(wf[c * 16 + p], wf[(c + 1) * 16 + p]);
+    }
+    uint64_t bias2[NP];
     float g[CPL], be[CPL];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
         const int c = lane * CPL + 2 * j;
-#pragma unroll
-        for (int p = 0; p < 16; ++p) w2[j][p] = pk2(wf[c * 16 + p], wf[(c + 1) * 16 + p]);
         bias2[j] = pk2(bf[c], bf[c + 1]);
     }
 #pragma unroll
     for (int j = 0; j < CPL; ++j) { g[j] = lnw[lane * CPL + j]; be[j] = lnb[lane * CPL + j]; }
+    __syncthreads();
 
     const bool row_quad = (Wo % TPW) == 0;  // the TPW tokens of an iteration are x-adjacent: one 128-bit load per pixel row
     for (long long t0 = warp * TPW; t0 < tokens; t0 += nwarps * TPW) {
@@ -100,18 +108,26 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 2 : 1) stem_ln_kernel(const 
         uint64_t acc[TPW][NP];
         float s[TPW];
 #pragma unroll
-        for (int k = 0; k < TPW; ++k) {
+        for (int k = 0; k < TPW; ++k)
 #pragma unroll
             for (int j = 0; j < NP; ++j) acc[k][j] = bias2[j];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                // u8 -> f32 without the conversion unit (I2F runs on the XU pipe at 16 lanes/clk/SM and bounded this kernel):
+        for (int q = 0; q < 16; ++q) {
+            uint64_t wq[NP];
+#pragma unroll
+            for (int j = 0; j < NP; ++j) wq[j] = s_w[q][j][lane];
+#pragma unroll
+            for (int k = 0; k < TPW; ++k) {
+                // u8 -> f32 without the conversion unit (I2F runs on the XU pipe at 16 lanes/clk/SM):
                 // PRMT drops the byte into the mantissa of 2^23, one FADD removes the 2^23 -- exact for 0..255
                 const float f = __uint_as_float(__byte_perm(px[k][q >> 2], 0x4B000000u, 0x7650u | (uint32_t)(q & 3))) - 8388608.0f;
                 const uint64_t f2 = pk2(f, f);
 #pragma unroll
-                for (int j = 0; j < NP; ++j) acc[k][j] = fma2(f2, w2[j][q], acc[k][j]);
+                for (int j = 0; j < NP; ++j) acc[k][j] = fma2(f2, wq[j], acc[k][j]);
             }
+        }
+#pragma unroll
+        for (int k = 0; k < TPW; ++k) {
             float a = 0.f;
 #pragma unroll
             for (int j = 0; j < NP; ++j) { float lo, hi; upk2(acc[k][j], lo, hi); a += lo + hi; }
