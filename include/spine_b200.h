@@ -113,6 +113,14 @@ int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const 
                             int max_h, int max_w, int out_h, int out_w, uint8_t* d_out_u8,
                             float* d_minmax, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Normalise only (no resize): normalize_to_uint8 (io/__init__.py:15-30) over a ragged batch, as the localization dataset
+ * builder applies it to every RSNA DICOM slice and Lumbar-Coords array before saving a PNG
+ * (spine_vision/datasets/localization.py:147-151, 262-267).  d_out_u8 is a uint8 pool with the SAME element offsets as
+ * the float32 pool (d_offs); bit-exact like K1's first half.  HBM-bound: 4 B in (twice: min/max, then normalise) + 1 B out. */
+size_t svb_normalize_u8_workspace_bytes(int B);
+int svb_normalize_u8(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B, int max_h, int max_w,
+                     uint8_t* d_out_u8, float* d_minmax, void* d_ws, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K3 -- batched coordinate-driven crop + per-crop min-max normalise + letterboxed bilinear
  * resize (OpenCV 8U INTER_LINEAR fixed point), plus the classifier's Pillow bilinear
@@ -263,6 +271,9 @@ size_t svb_png_bound(int h, int w); /* bytes svb_png_encode_gray8 may need for o
 int svb_png_encode_gray8(const uint8_t* h_img, int h, int w, int level, uint8_t* h_out, size_t cap, size_t* out_len);
 int svb_png_write_gray8_batch(const uint8_t* h_imgs /* [n, h, w] */, int n, int h, int w, const char* const* paths,
                               int level, int n_threads, int32_t* rcs);
+/* images of different sizes: image i = hw[2i] x hw[2i+1] bytes at h_pool + offs[i] */
+int svb_png_write_gray8_ragged(const uint8_t* h_pool, const int64_t* offs, const int32_t* hw, int n, const char* const* paths,
+                               int level, int n_threads, int32_t* rcs);
 
 /* MetaImage (.mha, .mhd + raw / zraw) -- replaces read_medical_image -> read_mha -> sitk.ReadImage for the SPIDER
  * volumes (spine_vision/io/readers.py:65-73, 128-161; spider.py:115).  Scalar 2-D / 3-D images, binary data, raw or

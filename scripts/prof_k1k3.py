@@ -40,7 +40,14 @@ def k4():
     ops.classifier_input(out2, k4_t2, k4_t1, out=k4_out)
 
 
-for name, fn, nbytes in (("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120),
+norm_out = torch.empty(pool.data.numel(), dtype=torch.uint8, device=dev)
+
+
+def norm():
+    ops.normalize_u8(pool, out=norm_out)
+
+
+for name, fn, nbytes in (("normalize_u8 (no resize)", norm, B * 1195 * 1195 * 5), ("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120),
                          ("K4 classifier input", k4, P * 65536 * 14)):
     if REPS == 0:
         fn(); torch.cuda.synchronize(); continue

@@ -21,13 +21,13 @@ KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 EXPORTS = (
     "svb_version", "svb_last_error", "svb_device_check", "svb_launch_count",
     "svb_k0_workspace_bytes", "svb_k0_midplane_resample",
-    "svb_k1_workspace_bytes", "svb_k1_normalize_resize",
+    "svb_k1_workspace_bytes", "svb_k1_normalize_resize", "svb_normalize_u8_workspace_bytes", "svb_normalize_u8",
     "svb_k3_workspace_bytes", "svb_k3_crop_resample", "svb_k3_crop_resample_rotated",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
     "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused",
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
     "svb_k4_classifier_input",
-    "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch",
+    "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch", "svb_png_write_gray8_ragged",
     "svb_mha_read_header", "svb_mha_read_f32", "svb_mha_read_batch_f32",
     "svb_dicom_read_headers", "svb_dicom_read_slices_f32",
 )
@@ -138,6 +138,12 @@ def load() -> C.CDLL:
     lib.svb_mha_read_f32.argtypes = [C.c_char_p, C.POINTER(MhaInfo), vp, sz]
     lib.svb_mha_read_batch_f32.restype = C.c_int
     lib.svb_mha_read_batch_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(MhaInfo), C.POINTER(vp), C.POINTER(sz), i32, vp]
+    lib.svb_normalize_u8_workspace_bytes.restype = sz
+    lib.svb_normalize_u8_workspace_bytes.argtypes = [i32]
+    lib.svb_normalize_u8.restype = C.c_int
+    lib.svb_normalize_u8.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, sz, vp]
+    lib.svb_png_write_gray8_ragged.restype = C.c_int
+    lib.svb_png_write_gray8_ragged.argtypes = [vp, vp, vp, i32, C.POINTER(C.c_char_p), i32, i32, vp]
     lib.svb_dicom_read_headers.restype = C.c_int
     lib.svb_dicom_read_headers.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(DicomInfo), i32, vp]
     lib.svb_dicom_read_slices_f32.restype = C.c_int

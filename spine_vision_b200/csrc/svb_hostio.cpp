@@ -587,6 +587,35 @@ int svb_png_write_gray8_batch(const uint8_t* h_imgs, int n, int h, int w, const 
     return SVB_OK;
 }
 
+int svb_png_write_gray8_ragged(const uint8_t* h_pool, const int64_t* offs, const int32_t* hw, int n, const char* const* paths,
+                               int level, int n_threads, int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!h_pool || !offs || !hw || !paths)))
+        return set_error(SVB_ERR_INVALID_ARG, "png ragged batch: bad arguments (n=%d)", n);
+    std::atomic<int> first_bad{-1};
+    std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
+    parallel_for(n, n_threads, [&](int i) {
+        const int h = hw[2 * i], w = hw[2 * i + 1];
+        int rc = SVB_OK;
+        if (h <= 0 || w <= 0) rc = set_error(SVB_ERR_INVALID_ARG, "png ragged batch: image %d has size %d x %d", i, h, w);
+        if (rc == SVB_OK) {
+            const size_t cap = svb_png_bound(h, w);
+            std::vector<uint8_t> buf(cap);
+            size_t len = 0;
+            rc = png_encode(h_pool + offs[i], h, w, level, buf.data(), cap, &len);
+            if (rc == SVB_OK) rc = write_file(paths[i], buf.data(), len);
+        }
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) {
+            msgs[i] = svb_last_error();
+            int expect = -1;
+            first_bad.compare_exchange_strong(expect, i);
+        }
+    });
+    const int bad = first_bad.load();
+    if (bad >= 0) return set_error(SVB_ERR_IO, "png ragged batch: image %d failed: %s", bad, msgs[bad].c_str());
+    return SVB_OK;
+}
+
 int svb_mha_read_header(const char* path, svb_mha_info* info) { return mha_header(path, info); }
 
 int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, size_t dst_elems) {

@@ -324,6 +324,53 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
     }
 }
 
+// ---- normalise only (no resize): the localization dataset builder's per-image normalize_to_uint8
+// (spine_vision/datasets/localization.py:262-267, 147-151).  grid (chunks, nb); the uint8 pool uses the same element
+// offsets as the float32 pool (slices start 16-byte aligned, so every 128-bit load pairs with one 32-bit store).
+__global__ void k1_keys_reset_kernel(uint32_t* __restrict__ keys, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) { keys[2 * b + 0] = 0xFFFFFFFFu; keys[2 * b + 1] = 0u; }
+}
+
+__global__ void __launch_bounds__(512) k1_normalize_only_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
+                                                                const int32_t* __restrict__ hw, int b0,
+                                                                const uint32_t* __restrict__ keys, uint8_t* __restrict__ out,
+                                                                float* __restrict__ minmax) {
+    const int b = b0 + blockIdx.y;
+    const float* base = slices + offs[b];
+    uint8_t* dst = out + offs[b];
+    const long long n = (long long)hw[2 * b] * hw[2 * b + 1];
+    const float mn = key_float(keys[2 * b + 0]), mx = key_float(keys[2 * b + 1]);
+    const float rng = __fsub_rn(mx, mn);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && minmax != nullptr) { minmax[2 * b] = mn; minmax[2 * b + 1] = mx; }
+    const float k = rng > 0.0f ? __fdiv_rn(255.0f, rng) : 0.0f;
+    const long long n4 = n >> 2;
+    const float4* p4 = reinterpret_cast<const float4*>(base);
+    uint32_t* d4 = reinterpret_cast<uint32_t*>(dst);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 128-bit loads in flight
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(p4 + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            d4[i + u * stride] = rng > 0.0f ? (normalize_px_fast(v[u].x, mn, rng, k) | (normalize_px_fast(v[u].y, mn, rng, k) << 8) |
+                                               (normalize_px_fast(v[u].z, mn, rng, k) << 16) | (normalize_px_fast(v[u].w, mn, rng, k) << 24))
+                                            : (cast_f32_u8(v[u].x) | (cast_f32_u8(v[u].y) << 8) | (cast_f32_u8(v[u].z) << 16) | (cast_f32_u8(v[u].w) << 24));
+    }
+    for (; i < n4; i += stride) {
+        const float4 v = __ldg(p4 + i);
+        d4[i] = rng > 0.0f ? (normalize_px_fast(v.x, mn, rng, k) | (normalize_px_fast(v.y, mn, rng, k) << 8) |
+                              (normalize_px_fast(v.z, mn, rng, k) << 16) | (normalize_px_fast(v.w, mn, rng, k) << 24))
+                           : (cast_f32_u8(v.x) | (cast_f32_u8(v.y) << 8) | (cast_f32_u8(v.z) << 16) | (cast_f32_u8(v.w) << 24));
+    }
+    if (blockIdx.x == 0) {
+        const long long t = (n4 << 2) + threadIdx.x;
+        if (t < n) dst[t] = (uint8_t)normalize_px(base[t], mn, rng);
+    }
+}
+
 // rows of input one CTA of R output rows can need, for the largest slice of the batch
 static int k1_rows_in(int in_h, int out_h, int R) {
     double scale = (double)in_h / out_h;
@@ -402,6 +449,37 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
         k1_resize_kernel<<<dim3(ceil_div(out_h, R), nb), 512, smem_bytes, stream>>>(
             d_slices, d_offs, d_hw, b0, out_h, out_w, R, L.ksh, L.ksw, src_cap, rows_cap, keys, hb, hk, vb, vk,
             d_out_u8, d_minmax);
+        SVB_LAUNCHED();
+    }
+    return SVB_OK;
+}
+
+extern "C" size_t svb_normalize_u8_workspace_bytes(int B) { return B > 0 ? align_up((size_t)B * 2 * 4, 256) + 256 : 0; }
+
+extern "C" int svb_normalize_u8(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B, int max_h, int max_w,
+                                uint8_t* d_out_u8, float* d_minmax, void* d_ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(B >= 0 && max_h > 0 && max_w > 0, SVB_ERR_INVALID_ARG, "normalize_u8: bad sizes B=%d max_hw=(%d,%d)", B, max_h, max_w);
+    if (B == 0) return SVB_OK;
+    SVB_REQUIRE(d_slices && d_offs && d_hw && d_out_u8 && d_ws, SVB_ERR_INVALID_ARG, "normalize_u8: null pointer argument");
+    SVB_REQUIRE(ws_bytes >= svb_normalize_u8_workspace_bytes(B), SVB_ERR_WORKSPACE_TOO_SMALL, "normalize_u8: workspace %zu < %zu bytes",
+                ws_bytes, svb_normalize_u8_workspace_bytes(B));
+    uint32_t* keys = reinterpret_cast<uint32_t*>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~uintptr_t(255));
+    k1_keys_reset_kernel<<<ceil_div(B, 256), 256, 0, stream>>>(keys, B);
+    SVB_LAUNCHED();
+    const size_t slice_bytes = (size_t)max_h * max_w * 4;
+    int blocks = (int)ceil_div<size_t>(slice_bytes, (size_t)512 * 16 * 8);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 1024) blocks = 1024;
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        k1_minmax_kernel<<<dim3(blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys);
+        SVB_LAUNCHED();
+    }
+    for (int b0 = 0; b0 < B; b0 += 65535) {
+        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
+        k1_normalize_only_kernel<<<dim3(blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys, d_out_u8, d_minmax);
         SVB_LAUNCHED();
     }
     return SVB_OK;

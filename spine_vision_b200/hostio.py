@@ -150,6 +150,45 @@ def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) 
                          meta={"series_uid": uid.decode("ascii", "replace"), "files": [files[i].name for i in sel]})
 
 
+def read_dicom_files(paths, n_threads: int = 0):
+    """Single DICOM slices (``sitk.ReadImage(dcm)`` + ``GetArrayFromImage(...)[0]``, datasets/localization.py:262-266) decoded
+    on a thread pool.  Returns ``(arrays, errors)``: ``arrays[i]`` float32 ``[rows, cols]`` (stored value * slope + intercept),
+    or ``None`` with the reason in ``errors[i]`` -- the caller logs and skips, like the reference's ``except``."""
+    lib = _lib.load()
+    paths = [Path(p) for p in paths]
+    n = len(paths)
+    infos = (_lib.DicomInfo * max(n, 1))()
+    rcs = (C.c_int32 * max(n, 1))()
+    errors: list[str | None] = [None] * n
+    arrays: list[np.ndarray | None] = [None] * n
+    if n == 0:
+        return arrays, errors
+    c_paths = (C.c_char_p * n)(*[os.fsencode(str(p)) for p in paths])
+    lib.svb_dicom_read_headers(c_paths, n, infos, int(n_threads), C.addressof(rcs))
+    ok = [i for i in range(n) if rcs[i] == 0]
+    for i in range(n):
+        if rcs[i] != 0:
+            errors[i] = f"libspine_b200 error {rcs[i]}: not a supported DICOM slice: {paths[i]}"
+    if not ok:
+        return arrays, errors
+    m = len(ok)
+    sizes = [infos[i].rows * infos[i].cols for i in ok]
+    offs = np.concatenate([[0], np.cumsum([(s + 3) // 4 * 4 for s in sizes])]).astype(np.int64)
+    host = np.empty(int(offs[-1]), dtype=np.float32)
+    c_sel = (C.c_char_p * m)(*[os.fsencode(str(paths[i])) for i in ok])
+    c_infos = (_lib.DicomInfo * m)(*[infos[i] for i in ok])
+    c_dsts = (C.c_void_p * m)(*[host.ctypes.data + 4 * int(offs[k]) for k in range(m)])
+    c_sizes = (C.c_size_t * m)(*sizes)
+    rcs2 = (C.c_int32 * m)()
+    lib.svb_dicom_read_slices_f32(c_sel, m, c_infos, c_dsts, c_sizes, int(n_threads), C.addressof(rcs2))
+    for k, i in enumerate(ok):
+        if rcs2[k] != 0:
+            errors[i] = f"libspine_b200 error {rcs2[k]} while decoding {paths[i]}"
+        else:
+            arrays[i] = host[int(offs[k]) : int(offs[k]) + sizes[k]].reshape(infos[i].rows, infos[i].cols)
+    return arrays, errors
+
+
 def read_medical_image(path: Path) -> MedicalVolume:
     """``read_medical_image`` (io/readers.py:128-161): same error behaviour (``FileNotFoundError`` for a missing path,
     ``ValueError`` for an unknown format)."""
@@ -229,6 +268,21 @@ def encode_png(image: np.ndarray, level: int = 6) -> bytes:
     n = C.c_size_t(0)
     _lib.check(lib.svb_png_encode_gray8(img.ctypes.data, h, w, int(level), buf.ctypes.data, cap, C.byref(n)))
     return buf[: n.value].tobytes()
+
+
+def write_png_ragged(pool_u8: np.ndarray, offs, shapes, paths, level: int = 6, n_threads: int = 0) -> None:
+    """PNGs of different sizes from one flat uint8 pool: image i = ``pool_u8[offs[i] : offs[i] + h*w].reshape(h, w)``."""
+    lib = _lib.load()
+    pool = np.ascontiguousarray(pool_u8, dtype=np.uint8)
+    n = len(paths)
+    if n == 0:
+        return
+    c_offs = np.ascontiguousarray(offs, dtype=np.int64)
+    c_hw = np.ascontiguousarray(shapes, dtype=np.int32).reshape(n, 2)
+    assert c_offs.shape == (n,) and int((c_offs + c_hw[:, 0].astype(np.int64) * c_hw[:, 1]).max()) <= pool.size
+    c_paths = (C.c_char_p * n)(*[os.fsencode(str(p)) for p in paths])
+    _lib.check(lib.svb_png_write_gray8_ragged(pool.ctypes.data, c_offs.ctypes.data, c_hw.ctypes.data, n, c_paths, int(level),
+                                              int(n_threads), None))
 
 
 def write_png_batch(images: np.ndarray, paths, level: int = 6, n_threads: int = 0) -> None:

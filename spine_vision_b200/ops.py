@@ -133,6 +133,27 @@ def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | Non
     return (out, minmax) if return_minmax else out
 
 
+def normalize_u8(pool: SlicePool, out: torch.Tensor | None = None, return_minmax: bool = False):
+    """``normalize_to_uint8`` (io/__init__.py:15-30) over a ragged batch without resizing: returns a flat uint8 pool with the
+    same element offsets as ``pool`` (slice b = ``out[offs[b] : offs[b] + h*w].view(h, w)``).  Device mirror of the
+    localization dataset builder's per-image normalisation (datasets/localization.py:147-151, 262-267)."""
+    lib = _lib.load()
+    dev = pool.data.device
+    B = pool.n
+    if out is None:
+        out = torch.empty(pool.data.numel(), dtype=torch.uint8, device=dev)
+    assert out.dtype == torch.uint8 and out.is_contiguous() and out.numel() >= pool.data.numel()
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev) if return_minmax else None
+    if B == 0:
+        return (out, minmax) if return_minmax else out
+    mh, mw = pool.max_hw
+    need = lib.svb_normalize_u8_workspace_bytes(B)
+    ws = _Workspace.get("norm", need, dev)
+    _lib.check(lib.svb_normalize_u8(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), B, mh, mw, out.data_ptr(),
+                                    _lib.ptr(minmax), ws.data_ptr(), ws.numel(), _lib.current_stream()))
+    return (out, minmax) if return_minmax else out
+
+
 def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, delta_px: torch.Tensor, max_box_hw,
                   crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True,
                   out: torch.Tensor | None = None, out2: torch.Tensor | None = None, inv_affine: torch.Tensor | None = None):

@@ -351,3 +351,64 @@ def make_phenikaa_tree(base_path, n_patients: int = 2, seed: int = 0, in_plane=(
         wr.writeheader()
         wr.writerows(rows)
     return pids
+
+
+def make_localization_tree(base_path, seed: int = 0):
+    """Raw inputs of ``create_localization_dataset`` (datasets/localization.py:326-382) in miniature, deterministic:
+
+    * ``raw/Lumbar Coords/coords_pretrain.csv`` + ``data/processed_*_jpgs`` (ready-made JPGs: copied byte for byte, so any
+      bytes do) + ``data/processed_{lsd,osf}/*.npy`` (arrays that have to be normalised), incl. a repeated file, an unknown
+      source and a missing file;
+    * ``raw/Lumbar Coords/coords_rsna_improved.csv`` + ``raw/RSNA/train_series_descriptions.csv`` +
+      ``raw/RSNA/train_images/<study>/<series>/<instance>.dcm`` (single-slice DICOMs of different sizes, one with a
+      rescale, one constant image), incl. rows that every skip rule of ``process_rsna_improved`` removes.
+    """
+    import csv
+    from pathlib import Path
+
+    rng = np.random.default_rng(90_000 + seed)
+    lc = Path(base_path) / "raw" / "Lumbar Coords"
+    rs = Path(base_path) / "raw" / "RSNA"
+    for d in ("processed_spider_jpgs", "processed_lsd_jpgs", "processed_osf_jpgs", "processed_tseg_jpgs", "processed_lsd", "processed_osf",
+              "processed_tseg"):
+        (lc / "data" / d).mkdir(parents=True, exist_ok=True)
+    (lc / "data" / "processed_spider_jpgs" / "sp_001.jpg").write_bytes(b"\xff\xd8\xff\xe0" + bytes(rng.integers(0, 256, 300, dtype=np.uint8)))
+    (lc / "data" / "processed_tseg_jpgs" / "ct_7.jpg").write_bytes(b"\xff\xd8\xff\xe0" + bytes(rng.integers(0, 256, 200, dtype=np.uint8)))
+    np.save(lc / "data" / "processed_lsd" / "lsd_10.npy", make_iso_slice(300 + seed, 96, 80))
+    np.save(lc / "data" / "processed_lsd" / "lsd_11.npy", (make_iso_slice(301 + seed, 70, 131) * 3).astype(np.int16))
+    np.save(lc / "data" / "processed_osf" / "osf_3.npy", make_iso_slice(302 + seed, 64, 64).astype(np.float64))
+    pre = [("sp_001.jpg", "spider"), ("sp_001.jpg", "spider"), ("lsd_10.jpg", "lsd"), ("lsd_11.jpg", "lsd"), ("lsd_10.jpg", "lsd"),
+           ("osf_3.jpg", "osf"), ("ct_7.jpg", "tseg"), ("nope.jpg", "osf"), ("x.jpg", "mystery"), ("sp_404.jpg", "spider")]
+    levels = ["L1/L2", "L2/L3", "L3/L4", "L4/L5", "L5/S1"]
+    with open(lc / "coords_pretrain.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["filename", "source", "level", "relative_x", "relative_y"])
+        for k, (fn, src) in enumerate(pre):
+            w.writerow([fn, src, levels[k % 5], round(float(rng.uniform(0.3, 0.7)), 6), round(float(rng.uniform(0.2, 0.8)), 6)])
+    series = {(101, 1001): "Sagittal T1", (101, 1002): "Sagittal T2/STIR", (101, 1003): "Axial T2", (202, 2001): "Sagittal T2/STIR"}
+    rs.mkdir(parents=True, exist_ok=True)
+    with open(rs / "train_series_descriptions.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["study_id", "series_id", "series_description"])
+        for (study, sid), desc in series.items():
+            w.writerow([study, sid, desc])
+    shapes = {(101, 1001, 5): (88, 72), (101, 1001, 6): (88, 72), (101, 1002, 8): (120, 100), (202, 2001, 3): (64, 96), (202, 2001, 4): (64, 96)}
+    for k, ((study, sid, inst), (h, wd)) in enumerate(shapes.items()):
+        d = rs / "train_images" / str(study) / str(sid)
+        d.mkdir(parents=True, exist_ok=True)
+        img = np.clip(np.rint(make_iso_slice(400 + seed + k, h, wd)), 0, 4095).astype(np.uint16)
+        if k == 4:
+            img[:] = 777  # constant image: normalize_to_uint8 casts the raw values (wraps mod 256)
+        write_dicom_slice(d / f"{inst}.dcm", img, (0.0, 0.0, float(inst)), (0, 1, 0), (0, 0, -1), (0.6, 0.6), f"1.2.840.{sid}", inst,
+                          rescale=(2.0, -100.0) if k == 2 else None, explicit=k % 2 == 0)
+    (rs / "train_images" / "202" / "2001" / "9.dcm").write_bytes(b"broken")
+    rows = [(1001, 101, 5, "Left Neural Foraminal Narrowing"), (1001, 101, 5, "Right Neural Foraminal Narrowing"),
+            (1001, 101, 6, "Left Neural Foraminal Narrowing"), (1002, 101, 8, "Spinal Canal Stenosis"),
+            (1003, 101, 2, "Left Subarticular Stenosis"), (1002, 101, -1, "Spinal Canal Stenosis"), (2001, 202, 3, "Spinal Canal Stenosis"),
+            (2001, 202, 4, "Spinal Canal Stenosis"), (2001, 202, 9, "Spinal Canal Stenosis"), (2001, 202, 77, "Spinal Canal Stenosis"),
+            (5555, 202, 1, "Spinal Canal Stenosis"), (1003, 101, 2, "Spinal Canal Stenosis"), (2001, 202, 3, "Spinal Canal Stenosis")]
+    with open(lc / "coords_rsna_improved.csv", "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(["series_id", "study_id", "instance_number", "relative_x", "relative_y", "level", "condition"])
+        for k, (sid, study, inst, cond) in enumerate(rows):
+            w.writerow([sid, study, inst, round(float(rng.uniform(0.3, 0.7)), 6), round(float(rng.uniform(0.2, 0.8)), 6), levels[k % 5], cond])

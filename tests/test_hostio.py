@@ -246,3 +246,41 @@ def test_gather_records_gloo_world2(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+def test_ragged_png_writer_and_single_dicom_reader(tmp_path):
+    """Host pieces of the localization dataset builder: images of different sizes from one pool -> PNG (threaded), and
+    single DICOM slices decoded in a batch with per-file errors (datasets/localization.py:262-271)."""
+    rng = np.random.default_rng(5)
+    shapes = [(40, 33), (7, 120), (64, 64)]
+    offs, o = [], 0
+    for h, w in shapes:
+        offs.append(o)
+        o += (h * w + 3) // 4 * 4
+    pool = rng.integers(0, 256, size=o, dtype=np.uint8)
+    paths = [tmp_path / f"r{k}.png" for k in range(3)]
+    hostio.write_png_ragged(pool, offs, shapes, paths, n_threads=2)
+    for (h, w), off, p in zip(shapes, offs, paths):
+        assert np.array_equal(np.asarray(Image.open(p)), pool[off : off + h * w].reshape(h, w))
+    a = rng.integers(0, 4000, size=(30, 22)).astype(np.uint16)
+    b = rng.integers(-500, 500, size=(16, 48)).astype(np.int16)
+    synthetic.write_dicom_slice(tmp_path / "a.dcm", a, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3", 1, rescale=(2.0, -10.0))
+    synthetic.write_dicom_slice(tmp_path / "b.dcm", b, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3", 2, explicit=False)
+    (tmp_path / "c.dcm").write_bytes(b"nope")
+    arrays, errors = hostio.read_dicom_files([tmp_path / "a.dcm", tmp_path / "c.dcm", tmp_path / "b.dcm", tmp_path / "missing.dcm"])
+    assert np.array_equal(arrays[0], a.astype(np.float32) * 2 - 10) and np.array_equal(arrays[2], b.astype(np.float32))
+    assert arrays[1] is None and arrays[3] is None and errors[0] is None and errors[1] and errors[3]
+    assert np.array_equal(arrays[0], dicom.read_slice(tmp_path / "a.dcm")["px"].astype(np.float64) * 2 - 10)
+
+
+def test_localization_series_lookup(tmp_path):
+    from spine_vision_b200 import localization_dataset as loc
+
+    synthetic.make_localization_tree(tmp_path, seed=0)
+    m = loc.load_series_mapping(tmp_path / "raw" / "RSNA" / "train_series_descriptions.csv")
+    assert m[101]["Sagittal T1"] == 1001 and loc.get_series_type(1002, 101, m) == "Sagittal T2/STIR"  # datasets/rsna.py:7-61
+    assert loc.get_series_type(1, 101, m) is None and loc.get_series_type(1001, 999, m) is None
+    cfg = loc.LocalizationDatasetConfig(base_path=tmp_path)
+    assert cfg.lumbar_coords_path == tmp_path / "raw" / "Lumbar Coords" and cfg.rsna_path == tmp_path / "raw" / "RSNA"
+    with pytest.raises(ValueError, match="empty records"):
+        loc.write_records_csv([], tmp_path / "x.csv")  # io/tabular.py:28-29
