@@ -21,6 +21,14 @@ Two layers live here:
   is not installed).  These state, in integer / fp32 arithmetic, exactly what
   the CUDA kernels implement.
 
+* ``oracle.itk_resample`` / ``oracle.metaimage`` / ``oracle.dicom`` -- restatements of what SimpleITK 2.5.3 (ITK, MetaIO,
+  GDCM; not installed) does in front of the path: the 0.3 mm resample + LPI orientation + middle slice, MetaImage reading,
+  DICOM series reading.  **Parity unpinned** (each header says so): they restate documented conventions and are what
+  K0 and the native decoders are tested against.
+* ``oracle.make_golden`` / ``make_golden_host`` / ``make_golden_localization`` -- container-only scripts that run the
+  reference's OWN functions and OWN dataset builders (through ``oracle.ref_shim``) and freeze their outputs into
+  ``tests/golden/``.
+
 Pinning status: the reference ships **no tests and no golden vectors** for
 this path (``AGENTS.md:552-554``).  The oracle is pinned instead against
 outputs of the reference's own unmodified functions, imported in the build
