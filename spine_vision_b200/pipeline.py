@@ -128,11 +128,37 @@ class PinnedSeries:
         return (self.ends[-1] if self.ends else 0) * 4
 
 
+class PendingCrops:
+    """Handle of one ``StreamedLocalizer.run_async`` call: the pinned host tensors are complete after ``result()``."""
+
+    def __init__(self, out: dict, finished: torch.cuda.Event | None):
+        self._out, self.finished = out, finished
+
+    @property
+    def device_coords(self) -> torch.Tensor:
+        return self._out["coords"]
+
+    @property
+    def device_crops(self) -> torch.Tensor:
+        return self._out["crops"]
+
+    def result(self):
+        if self.finished is not None:
+            self.finished.synchronize()
+        o = self._out
+        return o["h_coords"], o["h_crops"], o.get("h_crops2")
+
+
 class StreamedLocalizer:
     """End-to-end driver for host-resident series: the batch is cut into chunks of ``chunk`` series and
     the host->device copy of chunk i+1 (copy stream, pinned memory) runs under the kernels of chunk i
     (K1 -> localizer -> K3 on the compute stream); results go back on a third stream.  Same arithmetic
-    as ``localize_and_crop``; only the schedule differs."""
+    as ``localize_and_crop``; only the schedule differs.
+
+    ``run`` returns completed host tensors.  ``run_async`` returns a ``PendingCrops`` handle instead, so that a caller
+    with more batches to do (a dataset is many batches) starts the next one before collecting the previous one: the first
+    upload of batch k+1 then runs under the last kernels of batch k instead of in front of an idle GPU.  Two output slots
+    alternate; a slot is reused only after its previous results have left the device."""
 
     def __init__(self, model: LocalizationModel | None, device="cuda:0", crop_delta_mm=(55, 15, 17.5, 20), crop_size=(256, 256),
                  image_size=(512, 512), second_size=(256, 256), chunk: int = 37):
@@ -142,7 +168,15 @@ class StreamedLocalizer:
         self.copy_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
         self._stage = [None, None]
-        self._out = {}
+        self._stage_free: list[torch.cuda.Event | None] = [None, None]  # last compute use of each staging buffer
+        self._slots: list[dict] = [{}, {}]
+        self._slot_busy: list[torch.cuda.Event | None] = [None, None]   # last D2H out of each output slot
+        self._tables: dict = {}
+        self._next_stage = 0
+
+    @property
+    def _out(self) -> dict:  # the slot `run` uses (kept for callers that read the device tensors after run())
+        return self._slots[0]
 
     def _staging(self, j: int, nelem: int) -> torch.Tensor:
         buf = self._stage[j]
@@ -151,9 +185,9 @@ class StreamedLocalizer:
             self._stage[j] = buf
         return buf
 
-    def _outputs(self, B: int):
+    def _outputs(self, B: int, slot: int = 0):
         key = (B, self.crop_size, self.second_size)
-        if self._out.get("key") != key:
+        if self._slots[slot].get("key") != key:
             dev = self.device
             o = {"key": key,
                  "coords": torch.empty((B, NUM_LEVELS, 2), dtype=torch.float32, device=dev),
@@ -163,51 +197,69 @@ class StreamedLocalizer:
             if self.second_size is not None:
                 o["crops2"] = torch.empty((B, NUM_LEVELS, *self.second_size), dtype=torch.uint8, device=dev)
                 o["h_crops2"] = torch.empty((B, NUM_LEVELS, *self.second_size), dtype=torch.uint8).pin_memory()
-            self._out = o
-        return self._out
+            self._slots[slot] = o
+            self._slot_busy[slot] = None
+        return self._slots[slot]
+
+    def _index_tables(self, series: PinnedSeries, spacings, bounds):
+        """Per-batch index tables (offsets inside each chunk, shapes, crop deltas, slice ids): built and uploaded once per
+        (series, spacings) and kept -- a pinned allocation per call costs more than the kernels it feeds."""
+        B, L, dev = series.n, NUM_LEVELS, self.device
+        key = (id(series), B, self.chunk, None if spacings is None else tuple(map(tuple, spacings)), tuple(self.crop_delta_mm))
+        t = self._tables.get("key") == key and self._tables
+        if t:
+            return t
+        sp = spacings if spacings is not None else [(0.3, 0.3)] * B
+        deltas = [mm_to_pixels(self.crop_delta_mm, s) for s in sp]
+        rel_offs = []
+        for i0, i1 in bounds:
+            rel_offs += [series.offs[i] - series.offs[i0] for i in range(i0, i1)]
+        t = {"key": key, "series": series, "deltas": deltas,
+             "offs": torch.tensor(rel_offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True),
+             "hw": torch.tensor(series.shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True),
+             "delta": torch.tensor(deltas, dtype=torch.int32).repeat_interleave(L, dim=0).contiguous().pin_memory().to(dev, non_blocking=True),
+             "idx": torch.arange(self.chunk, dtype=torch.int32).repeat_interleave(L).contiguous().pin_memory().to(dev, non_blocking=True)}
+        self._tables = t
+        return t
 
     def run(self, series: PinnedSeries, spacings=None):
         """Returns pinned host tensors ``(coords [B,5,2] f32, crops [B,5,ch,cw] u8, crops2 | None)``; they are
         complete when this call returns (it synchronises the result stream)."""
+        return self.run_async(series, spacings, slot=0).result()
+
+    def run_async(self, series: PinnedSeries, spacings=None, slot: int = 0) -> PendingCrops:
         B, L, dev = series.n, NUM_LEVELS, self.device
-        o = self._outputs(B)
+        o = self._outputs(B, slot)
         if B == 0:
-            return o["h_coords"], o["h_crops"], o.get("h_crops2")
+            return PendingCrops(o, None)
         compute = torch.cuda.current_stream(dev)
-        if spacings is None:
-            spacings = [(0.3, 0.3)] * B
-        deltas = [mm_to_pixels(self.crop_delta_mm, sp) for sp in spacings]
+        if self._slot_busy[slot] is not None:
+            compute.wait_event(self._slot_busy[slot])  # the slot's previous results have left the device
         bounds = [(i0, min(i0 + self.chunk, B)) for i0 in range(0, B, self.chunk)]
-        # per-batch index tables: one small pinned upload
-        rel_offs = []
-        for i0, i1 in bounds:
-            rel_offs += [series.offs[i] - series.offs[i0] for i in range(i0, i1)]
-        offs_d = torch.tensor(rel_offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
-        hw_d = torch.tensor(series.shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True)
-        delta_d = torch.tensor(deltas, dtype=torch.int32).repeat_interleave(L, dim=0).contiguous().pin_memory().to(dev, non_blocking=True)
-        idx_d = torch.arange(self.chunk, dtype=torch.int32).repeat_interleave(L).contiguous().pin_memory().to(dev, non_blocking=True)
+        t = self._index_tables(series, spacings, bounds)
+        deltas, offs_d, hw_d, delta_d, idx_d = t["deltas"], t["offs"], t["hw"], t["delta"], t["idx"]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
-        done = [torch.cuda.Event(), torch.cuda.Event()]
         max_elems = max(series.ends[i1 - 1] - series.offs[i0] for i0, i1 in bounds)
+        j0 = self._next_stage  # staging buffers keep alternating across calls
 
         def upload(c):
             i0, i1 = bounds[c]
-            j = c & 1
+            j = (j0 + c) & 1
             lo, hi = series.offs[i0], series.ends[i1 - 1]
             with torch.cuda.stream(self.copy_stream):
-                if c >= 2:
-                    self.copy_stream.wait_event(done[j])  # chunk c-2 has finished with this staging buffer
+                if self._stage_free[j] is not None:
+                    self.copy_stream.wait_event(self._stage_free[j])  # the chunk that last used this buffer is done with it
                 buf = self._staging(j, max_elems)
                 buf[: hi - lo].copy_(series.host[lo:hi], non_blocking=True)
-                ready[j].record(self.copy_stream)
+                ready[c & 1].record(self.copy_stream)
 
-        self.copy_stream.wait_stream(compute)
         upload(0)
         for c, (i0, i1) in enumerate(bounds):
-            j = c & 1
+            j = (j0 + c) & 1
             if c + 1 < len(bounds):
                 upload(c + 1)
-            compute.wait_event(ready[j])
+            compute.wait_event(ready[c & 1])
+            ready[c & 1] = torch.cuda.Event()
             n = i1 - i0
             shapes = series.shapes[i0:i1]
             pool = ops.SlicePool(self._stage[j], offs_d[i0:i1], hw_d[i0:i1], list(shapes))
@@ -228,17 +280,20 @@ class StreamedLocalizer:
             ops.crop_resample(pool, idx_d[: n * L], xy, delta_d[i0 * L : i1 * L], max_box, self.crop_size,
                               self.second_size, out=o["crops"][i0:i1].view(n * L, *self.crop_size),
                               out2=None if self.second_size is None else o["crops2"][i0:i1].view(n * L, *self.second_size))
-            done[j].record(compute)
+            done = torch.cuda.Event()
+            done.record(compute)
+            self._stage_free[j] = done
             with torch.cuda.stream(self.d2h_stream):
-                self.d2h_stream.wait_event(done[j])
+                self.d2h_stream.wait_event(done)
                 o["h_coords"][i0:i1].copy_(o["coords"][i0:i1], non_blocking=True)
                 o["h_crops"][i0:i1].copy_(o["crops"][i0:i1], non_blocking=True)
                 if self.second_size is not None:
                     o["h_crops2"][i0:i1].copy_(o["crops2"][i0:i1], non_blocking=True)
-        compute.wait_stream(self.d2h_stream)
-        compute.wait_stream(self.copy_stream)
-        self.d2h_stream.synchronize()  # the host tensors are complete on return
-        return o["h_coords"], o["h_crops"], o.get("h_crops2")
+        self._next_stage = (j0 + len(bounds)) & 1
+        finished = torch.cuda.Event()
+        finished.record(self.d2h_stream)
+        self._slot_busy[slot] = finished
+        return PendingCrops(o, finished)
 
 
 # ------------------------------------------------------------------------------------------ multi-GPU

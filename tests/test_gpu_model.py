@@ -109,6 +109,16 @@ def test_streamed_driver_equals_resident_path():
         assert np.array_equal(gc.numpy(), wc)
         assert np.array_equal(gk.numpy(), wk)
         assert np.array_equal(gk2.numpy(), wk2)
+    # batches in flight: the next one is started before the previous one is collected (two output slots, shared staging)
+    other = pipeline.PinnedSeries(slices[::-1])
+    want_o = pipeline.localize_and_crop(ops.SlicePool.from_numpy(slices[::-1], dev()), model, (50, 20, 30, 30), (128, 128), (512, 512), (256, 256)).to_host()
+    handles = [streamer.run_async(series, slot=0), streamer.run_async(other, slot=1), None]
+    a = [t.numpy().copy() for t in handles[0].result()]
+    handles[2] = streamer.run_async(series, slot=0)  # slot 0 again: waits for its previous D2H by itself
+    b = [t.numpy().copy() for t in handles[1].result()]
+    c = [t.numpy().copy() for t in handles[2].result()]
+    for got, want_t in ((a, (wc, wk, wk2)), (b, want_o), (c, (wc, wk, wk2))):
+        assert all(np.array_equal(g, w) for g, w in zip(got, want_t))
     # centre-crop fallback (no model, __init__.py:194-197)
     fb = pipeline.StreamedLocalizer(None, dev(), (50, 20, 30, 30), (128, 128), (512, 512), None, chunk=4)
     fc, fk, fk2 = fb.run(series)
