@@ -176,3 +176,39 @@ def test_config3_ragged_volumes_with_their_own_spacing():
         for lvl in range(5):
             want = ref.crop_region_horizontal(sl, float(coords[i, lvl, 0]), float(coords[i, lvl, 1]), (128, 128), dpx)
             assert np.array_equal(crops[i, lvl], want)
+
+
+def test_model_batch_composition_invariance_at_bench_size():
+    """Size-independent property at BASELINE config-2 scale (256 slices, micro-batch 37 -> 6 full chunks + a tail of 34): an
+    image's coordinates do not depend on where it sits in the batch or on the micro-batch size (every kernel is
+    deterministic and per-image), so a permuted batch gives the permuted result bit for bit."""
+    om = make_model("base", seed=0)
+    g = torch.Generator().manual_seed(5)
+    distinct = torch.randint(0, 256, (6, 512, 512), generator=g, dtype=torch.uint8)
+    idx = torch.randint(0, 6, (256,), generator=g)
+    planes = distinct[idx].contiguous().to(dev())
+    perm = torch.randperm(256, generator=g)
+    m37 = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16", micro_batch=37)
+    a = m37.predict_u8(planes).cpu()
+    b = m37.predict_u8(planes[perm.to(dev())].contiguous()).cpu()
+    assert torch.equal(b, a[perm])
+    for k in range(6):  # identical inputs -> identical outputs, wherever they sit
+        rows = a[idx == k]
+        assert (rows == rows[0]).all()
+    m5 = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16", micro_batch=5)
+    assert torch.equal(m5.predict_u8(planes[:23].contiguous()).cpu(), a[:23])
+
+
+def test_model_config5_scale_768_batch():
+    """BASELINE config 5 geometry (768 x 768 input) over more than one micro-batch: finite, in (0, 1), permutation-consistent."""
+    om = make_model("base", seed=0)
+    g = torch.Generator().manual_seed(6)
+    distinct = torch.randint(0, 256, (3, 768, 768), generator=g, dtype=torch.uint8)
+    idx = torch.randint(0, 3, (80,), generator=g)
+    planes = distinct[idx].contiguous().to(dev())
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16", micro_batch=37)
+    out = model.predict_u8(planes).cpu()
+    assert out.shape == (80, 5, 2) and torch.isfinite(out).all() and (out > 0).all() and (out < 1).all()
+    for k in range(3):
+        rows = out[idx == k]
+        assert (rows == rows[0]).all()
