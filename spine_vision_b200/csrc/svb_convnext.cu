@@ -113,7 +113,7 @@ static int gemm_cg(int N, int K) {
     return (K >= 1024 || (K >= 512 && N >= 512)) ? 2 : 1;
 }
 
-static int dw_th(int C) { return C >= 512 ? 8 : 16; }
+static int dw_th(int C) { return C >= 2048 ? 4 : (C >= 512 ? 8 : 16); }
 // Programmatic dependent launch for the persistent kernels of the forward chain (depthwise conv + LN, GEMMs): the next
 // kernel's CTAs are scheduled as SMs drain and run their set-up (barriers, TMEM allocation, descriptor prefetch) under the
 // previous kernel's tail; griddepcontrol.wait in the kernels keeps the data dependence.  SVB_PDL=0 turns it off (A/B).
@@ -623,7 +623,7 @@ static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out,
         case 256: return launch_dwconv_t<T, 256, 16>(x, bp, out, nb, H, W, st);
         case 512: return launch_dwconv_t<T, 512, 8>(x, bp, out, nb, H, W, st);
         case 1024: return launch_dwconv_t<T, 1024, 8>(x, bp, out, nb, H, W, st);
-        case 2048: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: width 2048 (xlarge stage 3) is not built yet");
+        case 2048: return launch_dwconv_t<T, 2048, 4>(x, bp, out, nb, H, W, st);  // convnext_xlarge stage 3
     }
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: unsupported width %d", C);
 }

@@ -250,6 +250,13 @@ template <> struct TmemLd<32> {
     }
 };
 
+template <> struct TmemLd<64> {  // two 32-column loads (ConvNeXt-xlarge stage 3: 2048 channels = 64 values per lane)
+    static __device__ __forceinline__ void ld(uint32_t taddr, float* v) {
+        TmemLd<32>::ld(taddr, v);
+        TmemLd<32>::ld(taddr + 32u, v + 32);
+    }
+};
+
 // thread i of the warp -> TMEM lane (base + i), two consecutive 32-bit columns
 __device__ __forceinline__ void tmem_st_x2(uint32_t taddr, uint64_t v) {
     float lo, hi;
@@ -387,8 +394,8 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             tmem_st_wait();
 
             // ---- LayerNorm over C: one tcgen05.ld per pixel gives the lane its 2 channels of every chunk
-            constexpr int PG = 4;  // pixels in flight
-            static_assert(TH % PG == 0, "TH must be a multiple of 4");
+            constexpr int PG = NV <= 32 ? 4 : 1;  // pixels in flight (one at 2048 channels: 64 values per lane already)
+            static_assert(TH % PG == 0, "TH must be a multiple of the pixel group");
 #pragma unroll 1
             for (int p0 = 0; p0 < TH; p0 += PG) {
                 float v[PG][NV];
@@ -405,7 +412,11 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     upk2(a2, lo, hi);
                     s[g] = lo + hi;
                 }
-                warp_sum4(s, lane);
+                if constexpr (PG == 4) warp_sum4(s, lane);
+                else {
+#pragma unroll
+                    for (int g = 0; g < PG; ++g) s[g] = warp_sum(s[g]);
+                }
                 uint64_t d[PG][NCH];
 #pragma unroll
                 for (int g = 0; g < PG; ++g) {
@@ -421,7 +432,11 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                     upk2(a2, lo, hi);
                     q[g] = lo + hi;
                 }
-                warp_sum4(q, lane);
+                if constexpr (PG == 4) warp_sum4(q, lane);
+                else {
+#pragma unroll
+                    for (int g = 0; g < PG; ++g) q[g] = warp_sum(q[g]);
+                }
 #pragma unroll
                 for (int g = 0; g < PG; ++g) {
                     const int y = y0 + p0 + g;

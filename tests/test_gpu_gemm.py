@@ -48,7 +48,7 @@ def test_gemm_vs_torch(M, N, K, mode, dtype):
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024),
-                                     (1, 15, 23, 1024), (1, 128, 128, 128)])
+                                     (1, 15, 23, 1024), (1, 128, 128, 128), (2, 16, 16, 2048), (1, 9, 13, 2048)])
 def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
     g = torch.Generator().manual_seed(B + H + W + C)
     x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])

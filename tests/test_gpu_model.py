@@ -212,3 +212,18 @@ def test_model_config5_scale_768_batch():
     for k in range(3):
         rows = out[idx == k]
         assert (rows == rows[0]).all()
+
+
+def test_model_xlarge_variant():
+    """config.model_variant = "xlarge" (config.py:27-39): widths 256/512/1024/2048, the other ConvNeXt-v1 variant whose widths are
+    multiples of 128.  Same gate as base: 0.5 px at 512^2 against the fp32 oracle."""
+    om = make_model("xlarge", seed=0)
+    slices = [synthetic.make_iso_slice(80, 700, 640), synthetic.make_iso_slice(81, 512, 512)]
+    want = _oracle_coords(om, slices)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16")
+    assert model.engine.dims == [256, 512, 1024, 2048] or tuple(model.engine.dims) == (256, 512, 1024, 2048)
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    got = model.predict_u8(ops.normalize_resize(pool, (512, 512))).cpu().numpy()
+    err_px = np.abs(got - want).max() * PX
+    print(f"[coords] xlarge bf16: max error {err_px:.4f} px")
+    assert np.isfinite(got).all() and err_px <= 0.5
