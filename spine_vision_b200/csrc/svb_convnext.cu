@@ -113,7 +113,8 @@ static int gemm_cg(int N, int K) {
     return (K >= 1024 || (K >= 512 && N >= 512)) ? 2 : 1;
 }
 
-static int dw_th(int C) { return C >= 2048 ? 4 : (C >= 512 ? 8 : 16); }
+// rows per depthwise tile: bounded by the 512 TMEM columns a CTA may hold (2 warps x TH pixels x NV values), see DwCfg
+static int dw_th(int C) { return C >= 1536 ? 4 : (C >= 384 ? 8 : 16); }
 // Programmatic dependent launch for the persistent kernels of the forward chain (depthwise conv + LN, GEMMs): the next
 // kernel's CTAs are scheduled as SMs drain and run their set-up (barriers, TMEM allocation, descriptor prefetch) under the
 // previous kernel's tail; griddepcontrol.wait in the kernels keeps the data dependence.  SVB_PDL=0 turns it off (A/B).
@@ -223,12 +224,13 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
         m->depths[s] = d;
         const svb_weight_desc* g = hwts.get("backbone.stages." + std::to_string(s) + ".blocks.0.gamma");
         m->dims[s] = (int)g->shape[0];
-        SVB_REQUIRE(m->dims[s] % 128 == 0 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
-                    "stage %d width %d: this build supports ConvNeXt widths that are multiples of 128 "
-                    "(base, xlarge); tiny/small/large are not built yet", s, m->dims[s]);
+        SVB_REQUIRE(m->dims[s] % 64 == 0 && m->dims[s] >= 128 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
+                    "stage %d width %d: this build supports the ConvNeXt widths of base (128..1024), large (192..1536) and "
+                    "xlarge (256..2048); tiny / small (96..768) are not built", s, m->dims[s]);
     }
     SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
-    SVB_REQUIRE(m->dims[0] == 128 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL, "stem width %d unsupported", m->dims[0]);
+    SVB_REQUIRE(m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL, "stem width %d unsupported",
+                m->dims[0]);
     NEED(head_w1, "head.2.weight");
     NEED(head_w2, "head.5.weight");
     m->hid = (int)head_w1->shape[0];
@@ -624,6 +626,10 @@ static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out,
         case 512: return launch_dwconv_t<T, 512, 8>(x, bp, out, nb, H, W, st);
         case 1024: return launch_dwconv_t<T, 1024, 8>(x, bp, out, nb, H, W, st);
         case 2048: return launch_dwconv_t<T, 2048, 4>(x, bp, out, nb, H, W, st);  // convnext_xlarge stage 3
+        case 192: return launch_dwconv_t<T, 192, 16>(x, bp, out, nb, H, W, st);   // convnext_large
+        case 384: return launch_dwconv_t<T, 384, 8>(x, bp, out, nb, H, W, st);
+        case 768: return launch_dwconv_t<T, 768, 8>(x, bp, out, nb, H, W, st);
+        case 1536: return launch_dwconv_t<T, 1536, 4>(x, bp, out, nb, H, W, st);
     }
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv: unsupported width %d", C);
 }
@@ -640,6 +646,9 @@ static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int 
         case 256: ln_patchify_kernel<T, 256><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 512: ln_patchify_kernel<T, 512><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 1024: ln_patchify_kernel<T, 1024><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 192: ln_patchify_kernel<T, 192><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 384: ln_patchify_kernel<T, 384><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 768: ln_patchify_kernel<T, 768><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         default: return set_error(SVB_ERR_UNSUPPORTED_MODEL, "ln_patchify: unsupported width %d", Cin);
     }
     SVB_LAUNCHED();
@@ -734,6 +743,8 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
         if (int rc = tm.begin(SVB_KC_STEM)) return rc;
         if (m->dims[0] == 128)
             stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
+        else if (m->dims[0] == 192)
+            stem_ln_kernel<T, 6><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         else
             stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         SVB_LAUNCHED();
@@ -880,6 +891,7 @@ static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const
     if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;  // stem_ln_kernel: 4 resident CTAs per SM
     if (blocks < 1) blocks = 1;
     if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
+    else if (C0 == 192) stem_ln_kernel<T, 6><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else return set_error(SVB_ERR_UNSUPPORTED_MODEL, "stem: width %d unsupported", C0);
     SVB_LAUNCHED();

@@ -193,7 +193,10 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const 
 // tcgen05.ld per pixel, reduces with warp shuffles and writes the 16-bit K-major fc1 operand.
 template <int C, int TH>
 struct DwCfg {
-    static constexpr int TW = 8, CC = 64, NCH = C / CC, NV = 2 * NCH;
+    static constexpr int np2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+    // NV = fp32 values a lane parks per pixel (2 per 64-channel chunk), padded to the next power of two: tcgen05.ld comes in
+    // power-of-two column counts, and widths such as 192 / 384 / 768 / 1536 (convnext_large) have 6 / 12 / 24 / 48 values
+    static constexpr int TW = 8, CC = 64, NCH = C / CC, NV = np2(2 * NCH);
     static constexpr int HALO_H = TH + 6, HALO_W = TW + 6;
     static constexpr int HALO_BYTES = HALO_H * HALO_W * CC * 2;
     static constexpr int W_BYTES = 49 * CC * 4;
@@ -1385,8 +1388,8 @@ __global__ void __launch_bounds__(256) ln_patchify_kernel(const T* __restrict__ 
     // One warp = PG x-adjacent tokens per iteration: PG independent load / reduction chains in flight, the index arithmetic
     // (three divisions) paid once per PG tokens, and the two LayerNorm reductions of all PG tokens in one recursive-halving
     // pass (warp_sum4).  A lane owns 4 consecutive channels of every 128-channel group.
-    constexpr int V4 = C / 128;
-    constexpr int PG = LnPatchifyPG<C>::value;  // 4, or 2 at C = 1024 (registers)
+    constexpr int V4 = (C + 127) / 128;  // a lane's 4-channel groups; the last one is half empty when C % 128 == 64 (192-wide)
+    constexpr int PG = LnPatchifyPG<C>::value;  // 4, or 2 beyond 512 channels (registers)
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -1410,7 +1413,8 @@ __global__ void __launch_bounds__(256) ln_patchify_kernel(const T* __restrict__ 
             float a = 0.f;
 #pragma unroll
             for (int j = 0; j < V4; ++j) {
-                const uint2 u = __ldg(xp + lane + 32 * j);
+                const bool on = (C % 128 == 0) || (lane + 32 * j) * 4 < C;
+                const uint2 u = on ? __ldg(xp + lane + 32 * j) : make_uint2(0u, 0u);
                 const float2 lo = Cvt<T>::unpack2(u.x), hi = Cvt<T>::unpack2(u.y);
                 v[p][j] = make_float4(lo.x, lo.y, hi.x, hi.y);
                 a += (lo.x + lo.y) + (hi.x + hi.y);
@@ -1424,8 +1428,9 @@ __global__ void __launch_bounds__(256) ln_patchify_kernel(const T* __restrict__ 
             float a = 0.f;
 #pragma unroll
             for (int j = 0; j < V4; ++j) {
+                const bool on = (C % 128 == 0) || (lane + 32 * j) * 4 < C;
                 v[p][j].x -= mean; v[p][j].y -= mean; v[p][j].z -= mean; v[p][j].w -= mean;
-                a += (v[p][j].x * v[p][j].x + v[p][j].y * v[p][j].y) + (v[p][j].z * v[p][j].z + v[p][j].w * v[p][j].w);
+                if (on) a += (v[p][j].x * v[p][j].x + v[p][j].y * v[p][j].y) + (v[p][j].z * v[p][j].z + v[p][j].w * v[p][j].w);
             }
             q[p] = a;
         }
@@ -1439,6 +1444,7 @@ __global__ void __launch_bounds__(256) ln_patchify_kernel(const T* __restrict__ 
             uint2* op = reinterpret_cast<uint2*>(a2 + orow * (4 * C) + (size_t)(((y & 1) << 1) | (xx & 1)) * C);
 #pragma unroll
             for (int j = 0; j < V4; ++j) {
+                if (!((C % 128 == 0) || (lane + 32 * j) * 4 < C)) continue;
                 const float4 g = __ldg(reinterpret_cast<const float4*>(lnw) + lane + 32 * j);  // L1-resident after the first token
                 const float4 be = __ldg(reinterpret_cast<const float4*>(lnb) + lane + 32 * j);
                 uint2 o;

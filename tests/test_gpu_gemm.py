@@ -25,6 +25,7 @@ def _ref_gemm(a, w, bias, mode, resid=None, gamma=None):
     (128, 128, 64, 2), (128, 256, 128, 2), (256, 512, 128, 0), (1000, 256, 512, 2), (4096, 128, 512, 1),
     (2048, 1024, 256, 0), (640, 256, 1024, 1), (128 * 150, 512, 128, 0), (3000, 2048, 512, 0), (3000, 512, 2048, 1),
     (512, 1024, 4096, 1), (777, 4096, 1024, 0), (128 * 300 + 5, 128, 512, 1),
+    (1000, 768, 192, 0), (1000, 192, 768, 1), (640, 1536, 384, 0), (300, 384, 1536, 1), (512, 384, 768, 2),  # convnext_large: N, K multiples of 64 only
 ])
 def test_gemm_vs_torch(M, N, K, mode, dtype):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + mode)
@@ -48,7 +49,8 @@ def test_gemm_vs_torch(M, N, K, mode, dtype):
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024),
-                                     (1, 15, 23, 1024), (1, 128, 128, 128), (2, 16, 16, 2048), (1, 9, 13, 2048)])
+                                     (1, 15, 23, 1024), (1, 128, 128, 128), (2, 16, 16, 2048), (1, 9, 13, 2048),
+                                     (2, 40, 24, 192), (2, 32, 32, 384), (2, 17, 32, 768), (3, 16, 16, 1536)])  # + convnext_large widths
 def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
     g = torch.Generator().manual_seed(B + H + W + C)
     x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
@@ -63,6 +65,30 @@ def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
     err = (got - want).abs()
     tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
     assert int((err > tol).sum()) == 0, f"max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("C0,C", [(192, 192), (192, 384), (256, 768)])
+def test_stem_patchify_other_widths(dtype, C0, C):
+    """The widths of convnext_large / xlarge: stem at 192 / 256 channels, LayerNorm + patchify at 192 (a half-empty last lane
+    group), 384, 768."""
+    g = torch.Generator().manual_seed(C0 + C)
+    d = dev()
+    u8 = torch.randint(0, 256, (2, 32, 64), generator=g, dtype=torch.uint8)
+    wf, bf = torch.randn(C0, 16, generator=g) * 0.01, torch.randn(C0, generator=g) * 0.1
+    lnw, lnb = 1 + 0.1 * torch.randn(C0, generator=g), 0.1 * torch.randn(C0, generator=g)
+    y = F.conv2d(u8.float().unsqueeze(1), wf.view(C0, 1, 4, 4), bf, stride=4).permute(0, 2, 3, 1)
+    want = F.layer_norm(y, (C0,), lnw, lnb, 1e-6)
+    got = ops.stem_ln(u8.to(d), wf.to(d), bf.to(d), lnw.to(d), lnb.to(d), DT[dtype]).float().cpu()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int(((got - want).abs() > tol).sum()) == 0
+    x = torch.randn(2, 6, 10, C, generator=g).to(DT[dtype])
+    lw, lb = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    n = F.layer_norm(x.float(), (C,), lw, lb, 1e-6)
+    want = n.view(2, 3, 2, 5, 2, C).permute(0, 1, 3, 2, 4, 5).reshape(2, 3, 5, 4 * C)
+    got = ops.ln_patchify(x.to(d), lw.to(d), lb.to(d)).float().cpu()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int(((got - want).abs() > tol).sum()) == 0
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])

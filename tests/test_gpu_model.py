@@ -214,16 +214,17 @@ def test_model_config5_scale_768_batch():
         assert (rows == rows[0]).all()
 
 
-def test_model_xlarge_variant():
-    """config.model_variant = "xlarge" (config.py:27-39): widths 256/512/1024/2048, the other ConvNeXt-v1 variant whose widths are
-    multiples of 128.  Same gate as base: 0.5 px at 512^2 against the fp32 oracle."""
-    om = make_model("xlarge", seed=0)
+@pytest.mark.parametrize("variant,dims", [("xlarge", (256, 512, 1024, 2048)), ("large", (192, 384, 768, 1536))])
+def test_model_other_variants(variant, dims):
+    """config.model_variant (config.py:27-39) beyond "base": large (widths that are multiples of 64 only) and xlarge.  Same
+    gate as base: 0.5 px at 512^2 against the fp32 oracle."""
+    om = make_model(variant, seed=0)
     slices = [synthetic.make_iso_slice(80, 700, 640), synthetic.make_iso_slice(81, 512, 512)]
     want = _oracle_coords(om, slices)
     model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16")
-    assert model.engine.dims == [256, 512, 1024, 2048] or tuple(model.engine.dims) == (256, 512, 1024, 2048)
+    assert tuple(model.engine.dims) == dims
     pool = ops.SlicePool.from_numpy(slices, dev())
     got = model.predict_u8(ops.normalize_resize(pool, (512, 512))).cpu().numpy()
     err_px = np.abs(got - want).max() * PX
-    print(f"[coords] xlarge bf16: max error {err_px:.4f} px")
+    print(f"[coords] {variant} bf16: max error {err_px:.4f} px")
     assert np.isfinite(got).all() and err_px <= 0.5
