@@ -224,13 +224,13 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
         m->depths[s] = d;
         const svb_weight_desc* g = hwts.get("backbone.stages." + std::to_string(s) + ".blocks.0.gamma");
         m->dims[s] = (int)g->shape[0];
-        SVB_REQUIRE(m->dims[s] % 64 == 0 && m->dims[s] >= 128 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
-                    "stage %d width %d: this build supports the ConvNeXt widths of base (128..1024), large (192..1536) and "
-                    "xlarge (256..2048); tiny / small (96..768) are not built", s, m->dims[s]);
+        SVB_REQUIRE(m->dims[s] % 32 == 0 && m->dims[s] >= 96 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
+                    "stage %d width %d: this build supports the ConvNeXt-v1 widths (tiny / small 96..768, base 128..1024, "
+                    "large 192..1536, xlarge 256..2048)", s, m->dims[s]);
     }
     SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
-    SVB_REQUIRE(m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL, "stem width %d unsupported",
-                m->dims[0]);
+    SVB_REQUIRE(m->dims[0] == 96 || m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL,
+                "stem width %d unsupported", m->dims[0]);
     NEED(head_w1, "head.2.weight");
     NEED(head_w2, "head.5.weight");
     m->hid = (int)head_w1->shape[0];
@@ -626,7 +626,8 @@ static int launch_dwconv(const CUtensorMap& x, const BlockParams& bp, void* out,
         case 512: return launch_dwconv_t<T, 512, 8>(x, bp, out, nb, H, W, st);
         case 1024: return launch_dwconv_t<T, 1024, 8>(x, bp, out, nb, H, W, st);
         case 2048: return launch_dwconv_t<T, 2048, 4>(x, bp, out, nb, H, W, st);  // convnext_xlarge stage 3
-        case 192: return launch_dwconv_t<T, 192, 16>(x, bp, out, nb, H, W, st);   // convnext_large
+        case 96: return launch_dwconv_t<T, 96, 16>(x, bp, out, nb, H, W, st);     // convnext_tiny / small stage 0
+        case 192: return launch_dwconv_t<T, 192, 16>(x, bp, out, nb, H, W, st);   // convnext_large (and tiny / small stage 1)
         case 384: return launch_dwconv_t<T, 384, 8>(x, bp, out, nb, H, W, st);
         case 768: return launch_dwconv_t<T, 768, 8>(x, bp, out, nb, H, W, st);
         case 1536: return launch_dwconv_t<T, 1536, 4>(x, bp, out, nb, H, W, st);
@@ -646,6 +647,7 @@ static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int 
         case 256: ln_patchify_kernel<T, 256><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 512: ln_patchify_kernel<T, 512><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 1024: ln_patchify_kernel<T, 1024><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
+        case 96: ln_patchify_kernel<T, 96><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 192: ln_patchify_kernel<T, 192><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 384: ln_patchify_kernel<T, 384><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
         case 768: ln_patchify_kernel<T, 768><<<(int)blocks, 256, 0, st>>>(xp, d.lnw, d.lnb, ap, nb, H, W); break;
@@ -745,6 +747,8 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
             stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         else if (m->dims[0] == 192)
             stem_ln_kernel<T, 6><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
+        else if (m->dims[0] == 96)
+            stem_ln_kernel<T, 4, 96><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         else
             stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         SVB_LAUNCHED();
@@ -892,6 +896,7 @@ static int stem_entry(const uint8_t* in, const float* wf, const float* bf, const
     if (blocks < 1) blocks = 1;
     if (C0 == 128) stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 192) stem_ln_kernel<T, 6><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
+    else if (C0 == 96) stem_ln_kernel<T, 4, 96><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else if (C0 == 256) stem_ln_kernel<T, 8><<<(int)blocks, 256, 0, st>>>(in, wf, bf, lnw, lnb, static_cast<T*>(out), B, H, W);
     else return set_error(SVB_ERR_UNSUPPORTED_MODEL, "stem: width %d unsupported", C0);
     SVB_LAUNCHED();

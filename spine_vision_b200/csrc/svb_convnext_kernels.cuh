@@ -47,18 +47,22 @@ __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f +
 // kernel is latency-bound otherwise), lane = CPL consecutive output channels as packed fp32 pairs.
 constexpr int STEM_TPW = 4;  // the 128-bit pixel-row load below assumes 4
 
-template <typename T, int CPL>
+template <typename T, int CPL, int C0 = 32 * CPL>
 __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const uint8_t* __restrict__ in, const float* __restrict__ wf /*[C0][16]*/,
                                                          const float* __restrict__ bf, const float* __restrict__ lnw,
                                                          const float* __restrict__ lnb, T* __restrict__ out, int B, int H,
                                                          int W) {
     static_assert(CPL % 2 == 0, "stem packs channel pairs");
-    constexpr int C0 = 32 * CPL, NP = CPL / 2, TPW = STEM_TPW;
+    // C0 < 32 * CPL (96 channels with CPL = 4, convnext_tiny / small): the lanes past C0 / CPL carry zero weights, stay out of
+    // the LayerNorm sums and do not store
+    constexpr int NP = CPL / 2, TPW = STEM_TPW;
+    static_assert(C0 % CPL == 0 && C0 <= 32 * CPL, "stem width");
     // folded weights as packed channel pairs in shared memory, [tap][pair j][lane]: a warp's read of one (tap, j) is 256
     // contiguous bytes.  (In registers they cost 32 * NP registers per thread and held the kernel at 16 warps per SM, where
     // it is latency-bound; from shared memory each value is read once per TPW tokens.)
     __shared__ uint64_t s_w[16][NP][32];
     const int lane = threadIdx.x & 31;
+    const bool lane_on = lane * CPL < C0;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
     const int Ho = H >> 2, Wo = W >> 2;
@@ -67,17 +71,17 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const 
     for (int i = threadIdx.x; i < 16 * NP * 32; i += blockDim.x) {
         const int l = i & 31, j = (i >> 5) % NP, p = i / (32 * NP);
         const int c = l * CPL + 2 * j;
-        s_w[p][j][l] = pk2(wf[c * 16 + p], wf[(c + 1) * 16 + p]);
+        s_w[p][j][l] = c < C0 ? pk2(wf[c * 16 + p], wf[(c + 1) * 16 + p]) : pk2(0.f, 0.f);
     }
     uint64_t bias2[NP];
     float g[CPL], be[CPL];
 #pragma unroll
     for (int j = 0; j < NP; ++j) {
         const int c = lane * CPL + 2 * j;
-        bias2[j] = pk2(bf[c], bf[c + 1]);
+        bias2[j] = lane_on ? pk2(bf[c], bf[c + 1]) : pk2(0.f, 0.f);
     }
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) { g[j] = lnw[lane * CPL + j]; be[j] = lnb[lane * CPL + j]; }
+    for (int j = 0; j < CPL; ++j) { g[j] = lane_on ? lnw[lane * CPL + j] : 0.f; be[j] = lane_on ? lnb[lane * CPL + j] : 0.f; }
     __syncthreads();
 
     const bool row_quad = (Wo % TPW) == 0;  // the TPW tokens of an iteration are x-adjacent: one 128-bit load per pixel row
@@ -151,7 +155,7 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const 
                 q = fmaf(lo, lo, q);
                 q = fmaf(hi, hi, q);
             }
-            v2[k] = q;
+            v2[k] = lane_on ? q : 0.f;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -170,6 +174,7 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const 
                 o[j] = Cvt<T>::pack2(fmaf((lo - mean[k]) * rstd, g[2 * j], be[2 * j]),
                                      fmaf((hi - mean[k]) * rstd, g[2 * j + 1], be[2 * j + 1]));
             }
+            if (!lane_on) continue;
             uint32_t* op = reinterpret_cast<uint32_t*>(out + (size_t)(t0 + k) * C0 + lane * CPL);
             if (NP == 2) *reinterpret_cast<uint2*>(op) = make_uint2(o[0], o[1]);
             else if (NP == 4) *reinterpret_cast<uint4*>(op) = make_uint4(o[0], o[1], o[NP > 2 ? 2 : 0], o[NP > 3 ? 3 : 0]);
@@ -196,7 +201,10 @@ struct DwCfg {
     static constexpr int np2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
     // NV = fp32 values a lane parks per pixel (2 per 64-channel chunk), padded to the next power of two: tcgen05.ld comes in
     // power-of-two column counts, and widths such as 192 / 384 / 768 / 1536 (convnext_large) have 6 / 12 / 24 / 48 values
-    static constexpr int TW = 8, CC = 64, NCH = C / CC, NV = np2(2 * NCH);
+    // NCH counts a trailing half chunk too (96 channels = 1.5 chunks, convnext_tiny / small): TMA zero-fills the channels past
+    // C, the LayerNorm masks them
+    static constexpr int TW = 8, CC = 64, NCH = (C + CC - 1) / CC, NV = np2(2 * NCH);
+    static constexpr bool RAGGED = (C % CC) != 0;
     static constexpr int HALO_H = TH + 6, HALO_W = TW + 6;
     static constexpr int HALO_BYTES = HALO_H * HALO_W * CC * 2;
     static constexpr int W_BYTES = 49 * CC * 4;
@@ -209,7 +217,7 @@ struct DwCfg {
     static constexpr int NUM_THREADS = 32 * (TW + 1);
     static constexpr int LN_BYTES = 2 * C * 4;             // LayerNorm weight + bias, fp32
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + LN_BYTES + 256 + 1024;  // + barriers + align slack
-    static_assert(C % CC == 0, "C must be a multiple of 64");
+    static_assert(C % 32 == 0, "C must be a multiple of 32");
     static_assert(HALO_BYTES % 128 == 0, "halo stage must keep the tap buffer 128B aligned");
     static_assert(TMEM_COLS >= 32 && TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM columns: power of two <= 512");
     static_assert(STAGES >= 1, "at least one stage");
@@ -364,11 +372,12 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
             const int ty = t % tiles_y;
             const int b = t / tiles_y;
             const int x = tx * TW + wid, y0 = ty * TH;
-            float2 bias_next = __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane));
+            auto ch_ok = [&](int kk) { return !Cfg::RAGGED || kk * CC + 2 * lane < C; };  // this lane's channel pair of chunk kk exists
+            float2 bias_next = ch_ok(0) ? __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane)) : make_float2(0.f, 0.f);
             for (int k = 0; k < NCH; ++k, ++it) {
                 const int stage = it % STAGES;
                 const float2 bias = bias_next;  // loaded one chunk ahead: no global-load latency in front of the FMAs
-                if (k + 1 < NCH) bias_next = __ldg(reinterpret_cast<const float2*>(bdw + (k + 1) * CC + 2 * lane));
+                if (k + 1 < NCH) bias_next = ch_ok(k + 1) ? __ldg(reinterpret_cast<const float2*>(bdw + (k + 1) * CC + 2 * lane)) : make_float2(0.f, 0.f);
                 mbar_wait(&s_full[stage], (it / STAGES) & 1);
                 const uint32_t* halo = reinterpret_cast<const uint32_t*>(s_stage + stage * Cfg::STAGE_BYTES) + wid * 32 + lane;  // [HALO_H][HALO_W][32] ch pairs
                 const uint64_t* taps = reinterpret_cast<const uint64_t*>(s_stage + stage * Cfg::STAGE_BYTES + Cfg::HALO_BYTES) + lane;  // [49][32] fp32 pairs
@@ -429,7 +438,7 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 #pragma unroll
                     for (int kk = 0; kk < NCH; ++kk) {
                         d[g][kk] = add2(pk2(v[g][2 * kk], v[g][2 * kk + 1]), nm2);
-                        a2 = fma2(d[g][kk], d[g][kk], a2);
+                        if (ch_ok(kk)) a2 = fma2(d[g][kk], d[g][kk], a2);  // channels past C (zero-filled) stay out of the variance
                     }
                     float lo, hi;
                     upk2(a2, lo, hi);
@@ -451,7 +460,7 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
                         for (int kk = 0; kk < NCH; ++kk) {
                             float lo, hi;
                             upk2(fma2(mul2(d[g][kk], r2), s_gw[kk * 32], s_gb[kk * 32]), lo, hi);
-                            op[kk * (CC / 2)] = Cvt<T>::pack2(lo, hi);
+                            if (ch_ok(kk)) op[kk * (CC / 2)] = Cvt<T>::pack2(lo, hi);
                         }
                     }
                 }

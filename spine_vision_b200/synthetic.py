@@ -112,6 +112,8 @@ def make_coords(n_series: int, seed: int = 0, border_frac: float = 0.01, hw=(119
 
 CONVNEXT_VARIANTS = {
     "base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
+    "tiny": ((3, 3, 9, 3), (96, 192, 384, 768)),
+    "small": ((3, 3, 27, 3), (96, 192, 384, 768)),
     "large": ((3, 3, 27, 3), (192, 384, 768, 1536)),
     "xlarge": ((3, 3, 27, 3), (256, 512, 1024, 2048)),
 }

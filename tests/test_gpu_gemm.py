@@ -26,6 +26,7 @@ def _ref_gemm(a, w, bias, mode, resid=None, gamma=None):
     (2048, 1024, 256, 0), (640, 256, 1024, 1), (128 * 150, 512, 128, 0), (3000, 2048, 512, 0), (3000, 512, 2048, 1),
     (512, 1024, 4096, 1), (777, 4096, 1024, 0), (128 * 300 + 5, 128, 512, 1),
     (1000, 768, 192, 0), (1000, 192, 768, 1), (640, 1536, 384, 0), (300, 384, 1536, 1), (512, 384, 768, 2),  # convnext_large: N, K multiples of 64 only
+    (1000, 384, 96, 0), (1000, 96, 384, 1), (300, 192, 384, 2),  # convnext_tiny / small: K = 96 is one and a half k-blocks
 ])
 def test_gemm_vs_torch(M, N, K, mode, dtype):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K + mode)
@@ -50,7 +51,8 @@ def test_gemm_vs_torch(M, N, K, mode, dtype):
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024),
                                      (1, 15, 23, 1024), (1, 128, 128, 128), (2, 16, 16, 2048), (1, 9, 13, 2048),
-                                     (2, 40, 24, 192), (2, 32, 32, 384), (2, 17, 32, 768), (3, 16, 16, 1536)])  # + convnext_large widths
+                                     (2, 40, 24, 192), (2, 32, 32, 384), (2, 17, 32, 768), (3, 16, 16, 1536),  # + convnext_large widths
+                                     (2, 33, 40, 96), (1, 128, 128, 96)])  # + convnext_tiny / small stage 0 (1.5 channel chunks)
 def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
     g = torch.Generator().manual_seed(B + H + W + C)
     x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
@@ -68,7 +70,7 @@ def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
-@pytest.mark.parametrize("C0,C", [(192, 192), (192, 384), (256, 768)])
+@pytest.mark.parametrize("C0,C", [(192, 192), (192, 384), (256, 768), (96, 96)])
 def test_stem_patchify_other_widths(dtype, C0, C):
     """The widths of convnext_large / xlarge: stem at 192 / 256 channels, LayerNorm + patchify at 192 (a half-empty last lane
     group), 384, 768."""

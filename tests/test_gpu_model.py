@@ -214,10 +214,11 @@ def test_model_config5_scale_768_batch():
         assert (rows == rows[0]).all()
 
 
-@pytest.mark.parametrize("variant,dims", [("xlarge", (256, 512, 1024, 2048)), ("large", (192, 384, 768, 1536))])
+@pytest.mark.parametrize("variant,dims", [("xlarge", (256, 512, 1024, 2048)), ("large", (192, 384, 768, 1536)),
+                                          ("small", (96, 192, 384, 768)), ("tiny", (96, 192, 384, 768))])
 def test_model_other_variants(variant, dims):
-    """config.model_variant (config.py:27-39) beyond "base": large (widths that are multiples of 64 only) and xlarge.  Same
-    gate as base: 0.5 px at 512^2 against the fp32 oracle."""
+    """config.model_variant (config.py:27-39) beyond "base": every other ConvNeXt-v1 size -- tiny / small (96-channel stem: one
+    and a half 64-channel chunks), large (multiples of 64 only), xlarge.  Same gate as base: 0.5 px at 512^2 vs the fp32 oracle."""
     om = make_model(variant, seed=0)
     slices = [synthetic.make_iso_slice(80, 700, 640), synthetic.make_iso_slice(81, 512, 512)]
     want = _oracle_coords(om, slices)
