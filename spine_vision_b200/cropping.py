@@ -224,7 +224,7 @@ def load_localization_model(model_path: Path, variant: str, device: str, dtype: 
     ``"model_state_dict"`` holds the 348 ``backbone.*`` / ``head.*`` tensors,
     trainers/base.py:695-706), strict key check, weights repacked for the tensor cores."""
     if variant.startswith("v2_"):
-        raise NotImplementedError("ConvNeXt-V2 backbones (GRN) are not built; ConvNeXt v1 base, large and xlarge are")
+        raise NotImplementedError("ConvNeXt-V2 backbones (GRN) are not built; every ConvNeXt v1 size (tiny .. xlarge) is")
     checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
     return LocalizationModel(checkpoint["model_state_dict"], device, dtype)
 
