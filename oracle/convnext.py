@@ -37,6 +37,12 @@ VARIANTS = {
     "base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
     "large": ((3, 3, 27, 3), (192, 384, 768, 1536)),
     "xlarge": ((3, 3, 27, 3), (256, 512, 1024, 2048)),
+    # timm convnextv2_*: same macro design, GlobalResponseNorm inside the MLP, no layer scale
+    "v2_tiny": ((3, 3, 9, 3), (96, 192, 384, 768)),
+    "v2_small": ((3, 3, 27, 3), (96, 192, 384, 768)),
+    "v2_base": ((3, 3, 27, 3), (128, 256, 512, 1024)),
+    "v2_large": ((3, 3, 27, 3), (192, 384, 768, 1536)),
+    "v2_huge": ((3, 3, 27, 3), (352, 704, 1408, 2816)),
 }
 LN_EPS = 1e-6
 
@@ -50,34 +56,58 @@ class LayerNorm2d(nn.LayerNorm):
         return x.permute(0, 3, 1, 2)
 
 
+class GlobalResponseNorm(nn.Module):
+    """timm ``GlobalResponseNorm`` (ConvNeXt-V2), channels-last ``[B, H, W, C]``: L2 norm over the image's tokens per channel,
+    divided by its mean over channels; ``x + bias + weight * (x * n)``.  Zero-initialised weight / bias (identity at init)."""
+
+    def __init__(self, dim: int, eps: float = 1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.zeros(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+    def forward(self, x):
+        x_g = x.norm(p=2, dim=(1, 2), keepdim=True)
+        x_n = x_g / (x_g.mean(dim=-1, keepdim=True) + self.eps)
+        return x + torch.addcmul(self.bias.view(1, 1, 1, -1), self.weight.view(1, 1, 1, -1), x * x_n)
+
+
 class Mlp(nn.Module):
-    def __init__(self, dim: int):
+    def __init__(self, dim: int, use_grn: bool = False):
         super().__init__()
         self.fc1 = nn.Linear(dim, 4 * dim)
         self.act = nn.GELU()
+        if use_grn:
+            self.grn = GlobalResponseNorm(4 * dim)
+        self.use_grn = use_grn
         self.fc2 = nn.Linear(4 * dim, dim)
 
     def forward(self, x):
-        return self.fc2(self.act(self.fc1(x)))
+        x = self.act(self.fc1(x))
+        if self.use_grn:
+            x = self.grn(x)
+        return self.fc2(x)
 
 
 class Block(nn.Module):
-    def __init__(self, dim: int, ls_init: float = 1e-6):
+    def __init__(self, dim: int, ls_init: float | None = 1e-6, use_grn: bool = False):
         super().__init__()
         self.conv_dw = nn.Conv2d(dim, dim, kernel_size=7, padding=3, groups=dim)
         self.norm = nn.LayerNorm(dim, eps=LN_EPS)
-        self.mlp = Mlp(dim)
-        self.gamma = nn.Parameter(ls_init * torch.ones(dim))
+        self.mlp = Mlp(dim, use_grn)
+        self.gamma = nn.Parameter(ls_init * torch.ones(dim)) if ls_init is not None else None
 
     def forward(self, x):
         shortcut = x
         x = self.conv_dw(x).permute(0, 2, 3, 1)
         x = self.mlp(self.norm(x)).permute(0, 3, 1, 2)
-        return shortcut + x * self.gamma.reshape(1, -1, 1, 1)
+        if self.gamma is not None:
+            x = x * self.gamma.reshape(1, -1, 1, 1)
+        return shortcut + x
 
 
 class Stage(nn.Module):
-    def __init__(self, cin: int, cout: int, depth: int, first: bool):
+    def __init__(self, cin: int, cout: int, depth: int, first: bool, v2: bool = False):
         super().__init__()
         if first:
             self.downsample = nn.Identity()
@@ -85,7 +115,7 @@ class Stage(nn.Module):
             self.downsample = nn.Sequential(
                 LayerNorm2d(cin, eps=LN_EPS), nn.Conv2d(cin, cout, kernel_size=2, stride=2)
             )
-        self.blocks = nn.Sequential(*[Block(cout) for _ in range(depth)])
+        self.blocks = nn.Sequential(*[Block(cout, None if v2 else 1e-6, use_grn=v2) for _ in range(depth)])
 
     def forward(self, x):
         return self.blocks(self.downsample(x))
@@ -114,7 +144,7 @@ class ConvNeXt(nn.Module):
         stages = []
         prev = dims[0]
         for i, (d, c) in enumerate(zip(depths, dims)):
-            stages.append(Stage(prev, c, d, first=(i == 0)))
+            stages.append(Stage(prev, c, d, first=(i == 0), v2=variant.startswith("v2_")))
             prev = c
         self.stages = nn.Sequential(*stages)
         self.head = Head(prev)
@@ -167,6 +197,8 @@ def make_model(variant: str = "base", seed: int = 0, trained_like: bool = False)
             for name, p in m.named_parameters():
                 if name.endswith("gamma"):
                     p.copy_(torch.rand(p.shape, generator=g) * 0.9 + 0.1)
+                elif ".grn." in name:  # zero at init (identity): give the response norm something to do
+                    p.copy_((0.5 if name.endswith("weight") else 0.05) * torch.randn(p.shape, generator=g))
                 elif ".norm" in name or "stem.1" in name or "downsample.0" in name or name.startswith("head.0"):
                     if name.endswith("weight"):
                         p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g))

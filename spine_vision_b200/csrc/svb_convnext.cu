@@ -23,6 +23,7 @@ static const double IMAGENET_STD[3] = {0.229, 0.224, 0.225};   // cropping.py:24
 
 struct BlockParams {
     float *wdw, *bdw, *lnw, *lnb, *b1, *b2, *gamma;
+    float *grn_w = nullptr, *grn_b = nullptr;  // ConvNeXt-V2: GlobalResponseNorm weight / bias [4C]; gamma is all ones then
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
     void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
     CUtensorMap wdw_map, wdw16_map, w1_map, w2_map;
@@ -54,6 +55,7 @@ struct svb_model {
     int depths[4] = {0, 0, 0, 0};
     int hid = 0, nout = 0;
     int device = 0;
+    bool v2 = false;  // ConvNeXt-V2: GRN in every block's MLP, no layer scale
     void* slab = nullptr;
     size_t slab_bytes = 0;
     float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
@@ -219,16 +221,18 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
                 SVB_ERR_UNSUPPORTED_MODEL, "stem conv must be [C0,3,4,4]");
     for (int s = 0; s < 4; ++s) {
         int d = 0;
-        while (hwts.get("backbone.stages." + std::to_string(s) + ".blocks." + std::to_string(d) + ".gamma")) ++d;
+        while (hwts.get("backbone.stages." + std::to_string(s) + ".blocks." + std::to_string(d) + ".conv_dw.weight")) ++d;
         SVB_REQUIRE(d > 0, SVB_ERR_MISSING_WEIGHT, "no blocks found for stage %d", s);
         m->depths[s] = d;
-        const svb_weight_desc* g = hwts.get("backbone.stages." + std::to_string(s) + ".blocks.0.gamma");
+        const svb_weight_desc* g = hwts.get("backbone.stages." + std::to_string(s) + ".blocks.0.norm.weight");
+        SVB_REQUIRE(g != nullptr, SVB_ERR_MISSING_WEIGHT, "model_create: state dict has no 'backbone.stages.%d.blocks.0.norm.weight'", s);
         m->dims[s] = (int)g->shape[0];
         SVB_REQUIRE(m->dims[s] % 32 == 0 && m->dims[s] >= 96 && m->dims[s] <= 2048, SVB_ERR_UNSUPPORTED_MODEL,
                     "stage %d width %d: this build supports the ConvNeXt-v1 widths (tiny / small 96..768, base 128..1024, "
                     "large 192..1536, xlarge 256..2048)", s, m->dims[s]);
     }
     SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
+    m->v2 = hwts.get("backbone.stages.0.blocks.0.mlp.grn.weight") != nullptr;  // timm convnextv2_*: GRN instead of layer scale
     SVB_REQUIRE(m->dims[0] == 96 || m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL,
                 "stem width %d unsupported", m->dims[0]);
     NEED(head_w1, "head.2.weight");
@@ -315,7 +319,14 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             PUT_F32(bp.lnb, bn + "norm.bias", C);
             PUT_F32(bp.b1, bn + "mlp.fc1.bias", 4 * C);
             PUT_F32(bp.b2, bn + "mlp.fc2.bias", C);
-            PUT_F32(bp.gamma, bn + "gamma", C);
+            if (m->v2) {
+                std::vector<float> ones((size_t)C, 1.0f);
+                bp.gamma = static_cast<float*>(slab.put(ones.data(), ones.size() * 4));
+                PUT_F32(bp.grn_w, bn + "mlp.grn.weight", 4 * C);
+                PUT_F32(bp.grn_b, bn + "mlp.grn.bias", 4 * C);
+            } else {
+                PUT_F32(bp.gamma, bn + "gamma", C);
+            }
             NEED(w1, bn + "mlp.fc1.weight");
             NEED(w2, bn + "mlp.fc2.weight");
             SVB_REQUIRE(numel(w1) == (int64_t)4 * C * C && numel(w2) == (int64_t)4 * C * C, SVB_ERR_UNSUPPORTED_MODEL,
@@ -359,6 +370,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
         for (auto& bp : m->blocks[s]) {
             rebase(bp.wdw, base); rebase(bp.bdw, base); rebase(bp.lnw, base); rebase(bp.lnb, base);
             rebase(bp.b1, base); rebase(bp.b2, base); rebase(bp.gamma, base);
+            if (m->v2) { rebase(bp.grn_w, base); rebase(bp.grn_b, base); }
             bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
             bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
             bp.wdw16 = base + reinterpret_cast<size_t>(bp.wdw16);
@@ -409,7 +421,7 @@ extern "C" int svb_model_info(const svb_model* m, int32_t out[10]) {
 namespace svb {
 
 struct WsLayout {
-    size_t x, a, h, total;
+    size_t x, a, h, grn_part, grn_scale, total;
 };
 static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     // stage 0 is the largest for every buffer (tokens/4, channels*2 per stage)
@@ -420,6 +432,12 @@ static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     L.x = o; o += align_up(t0 * c0 * 2, 1024);
     L.a = o; o += align_up(t0 * c0 * 2, 1024);
     L.h = o; o += align_up(t0 * c0 * 4 * 2, 1024);
+    L.grn_part = L.grn_scale = o;
+    if (m->v2) {  // partial sums of squares [nb][tokens / GRN_ROWS][4C] (stage 0 is the largest) and scales [nb][4C] (stage 3 is)
+        const size_t chunks0 = ceil_div<size_t>((size_t)(H / 4) * (W / 4), GRN_ROWS);
+        L.grn_part = o; o += align_up((size_t)nb * chunks0 * c0 * 4 * 4, 1024);
+        L.grn_scale = o; o += align_up((size_t)nb * m->dims[3] * 4 * 4, 1024);
+    }
     L.total = o;
     return L;
 }
@@ -658,6 +676,21 @@ static int launch_ln_patchify(const void* x, const DownParams& d, void* a2, int 
 }
 
 template <typename T>
+static int launch_grn(T* hd, int nb, int tokens, int C4, const float* weight, const float* bias, float* part, float* scale, cudaStream_t st) {
+    const int nchunk = ceil_div(tokens, GRN_ROWS);
+    const dim3 grid(ceil_div(C4, 512), nchunk, nb);
+    SVB_REQUIRE(nb <= 65535 && nchunk <= 65535 && C4 % 2 == 0 && (size_t)C4 * 4 <= 48 * 1024, SVB_ERR_UNSUPPORTED_MODEL,
+                "grn: nb=%d tokens=%d C4=%d out of range", nb, tokens, C4);
+    grn_sumsq_kernel<T><<<grid, 256, 0, st>>>(hd, tokens, C4, part);
+    SVB_LAUNCHED();
+    grn_finalize_kernel<<<nb, 256, (size_t)C4 * 4, st>>>(part, nchunk, C4, weight, scale);
+    SVB_LAUNCHED();
+    grn_apply_kernel<T><<<grid, 256, 0, st>>>(hd, tokens, C4, scale, bias);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+
+template <typename T>
 static int launch_head(const T* x, int nb, int tokens, int C, const float* n0w, const float* n0b, const float* n1w, const float* n1b,
                        const float* w1, const float* b1, int hid, const float* w2, const float* b2, int nout, float* coords,
                        cudaStream_t st) {
@@ -773,11 +806,13 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
             } else {
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
             }
-            if (mlp_fused(C)) {
+            if (mlp_fused(C) && !m->v2) {
                 RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
             } else {
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
                                                 GEMM_GELU, st));
+                if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd, nb, h * w, 4 * C, bp.grn_w, bp.grn_b, reinterpret_cast<float*>(ws + L.grn_part),
+                                                          reinterpret_cast<float*>(ws + L.grn_scale), st));
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
                                                 GEMM_RESID, st));
             }
@@ -842,7 +877,7 @@ extern "C" int svb_model_cost(const svb_model* m, int B, int H, int W, double* g
             n += 2;
         }
         fl += (double)m->depths[s] * 2.0 * (2.0 * B * h * w * C * 4.0 * C);
-        n += 3 * (int64_t)m->depths[s];
+        n += (m->v2 ? 6 : 3) * (int64_t)m->depths[s];
     }
     n += 1;  // head
     if (gemm_flops) *gemm_flops = fl;

@@ -1385,6 +1385,77 @@ dwconv_ln_tc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
     if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ============================================================================ Global Response Normalization (ConvNeXt-V2)
+// timm GlobalResponseNorm inside the block's MLP (fc1 -> GELU -> GRN -> fc2), channels-last:
+//     g[b, c]  = || h[b, :, :, c] ||_2                       (over the image's tokens)
+//     n[b, c]  = g[b, c] / (mean_c g[b, c] + 1e-6)
+//     h'       = h + bias[c] + weight[c] * (h * n[b, c])  =  h * (1 + weight[c] * n[b, c]) + bias[c]
+// Three launches around the hidden activation the fc1 GEMM wrote: partial sums of squares per (image, token chunk,
+// channel) -- no atomics, so the result does not depend on scheduling --, one small CTA per image that finishes the norm
+// and turns it into a per-(image, channel) scale, and an in-place scale + bias pass.  Two extra trips of the hidden
+// activation through HBM per block: the un-fused first version of this operator.
+constexpr int GRN_ROWS = 128;  // tokens per partial sum
+
+// grid (ceil(C4 / 512), ceil(tokens / GRN_ROWS), B); thread = one channel pair
+template <typename T>
+__global__ void __launch_bounds__(256) grn_sumsq_kernel(const T* __restrict__ h, int tokens, int C4, float* __restrict__ part) {
+    const int cp = blockIdx.x * 256 + threadIdx.x;
+    if (2 * cp >= C4) return;
+    const int chunk = blockIdx.y, b = blockIdx.z, nchunk = gridDim.y;
+    const int r0 = chunk * GRN_ROWS, r1 = min(r0 + GRN_ROWS, tokens);
+    const uint32_t* p = reinterpret_cast<const uint32_t*>(h + ((size_t)b * tokens + r0) * C4) + cp;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r, p += C4 / 2) {
+        const float2 v = Cvt<T>::unpack2(__ldg(p));
+        s0 = fmaf(v.x, v.x, s0);
+        s1 = fmaf(v.y, v.y, s1);
+    }
+    *reinterpret_cast<float2*>(part + ((size_t)b * nchunk + chunk) * C4 + 2 * cp) = make_float2(s0, s1);
+}
+
+// grid (B); scale[b][c] = 1 + weight[c] * g / (mean_c g + eps)
+__global__ void __launch_bounds__(256) grn_finalize_kernel(const float* __restrict__ part, int nchunk, int C4,
+                                                           const float* __restrict__ weight, float* __restrict__ scale) {
+    extern __shared__ float s_g[];  // [C4]
+    __shared__ float s_red[8];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    float local = 0.f;
+    for (int c = tid; c < C4; c += 256) {
+        float a = 0.f;
+        for (int k = 0; k < nchunk; ++k) a += part[((size_t)b * nchunk + k) * C4 + c];  // fixed order
+        const float g = sqrtf(a);
+        s_g[c] = g;
+        local += g;
+    }
+    local = warp_sum(local);
+    if ((tid & 31) == 0) s_red[tid >> 5] = local;
+    __syncthreads();
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) tot += s_red[i];
+    const float inv = 1.0f / (tot / (float)C4 + 1e-6f);
+    for (int c = tid; c < C4; c += 256) scale[(size_t)b * C4 + c] = fmaf(weight[c], s_g[c] * inv, 1.0f);
+}
+
+// same grid as grn_sumsq_kernel; h <- h * scale[b][c] + bias[c], in place
+template <typename T>
+__global__ void __launch_bounds__(256) grn_apply_kernel(T* __restrict__ h, int tokens, int C4, const float* __restrict__ scale,
+                                                        const float* __restrict__ bias) {
+    const int cp = blockIdx.x * 256 + threadIdx.x;
+    if (2 * cp >= C4) return;
+    const int chunk = blockIdx.y, b = blockIdx.z;
+    const int r0 = chunk * GRN_ROWS, r1 = min(r0 + GRN_ROWS, tokens);
+    const float2 sc = *reinterpret_cast<const float2*>(scale + (size_t)b * C4 + 2 * cp);
+    const float2 bi = *reinterpret_cast<const float2*>(bias + 2 * cp);
+    uint32_t* p = reinterpret_cast<uint32_t*>(h + ((size_t)b * tokens + r0) * C4) + cp;
+#pragma unroll 8
+    for (int r = r0; r < r1; ++r, p += C4 / 2) {
+        const float2 v = Cvt<T>::unpack2(*p);
+        *p = Cvt<T>::pack2(fmaf(v.x, sc.x, bi.x), fmaf(v.y, sc.y, bi.y));
+    }
+}
+
 // ============================================================================ LayerNorm2d + 2x2/s2 patchify
 // x [B,H,W,C] -> a2 [B,H/2,W/2,4C] with k = (ky*2+kx)*C + c, the A operand of the downsample GEMM
 // (timm stage.downsample = LayerNorm2d -> Conv2d(k=2,s=2)).

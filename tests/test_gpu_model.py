@@ -229,3 +229,25 @@ def test_model_other_variants(variant, dims):
     err_px = np.abs(got - want).max() * PX
     print(f"[coords] {variant} bf16: max error {err_px:.4f} px")
     assert np.isfinite(got).all() and err_px <= 0.5
+
+
+@pytest.mark.parametrize("variant,dims,tol_px", [("v2_base", (128, 256, 512, 1024), 0.5), ("v2_tiny", (96, 192, 384, 768), 0.5),
+                                                 ("v2_large", (192, 384, 768, 1536), 0.5)])
+def test_model_convnext_v2_grn(variant, dims, tol_px):
+    """config.model_variant = v2_* (config.py:27-39): timm convnextv2 -- GlobalResponseNorm inside every block's MLP, no layer
+    scale.  The GRN weights are zero at init (identity), so the oracle model gets random ones; fp16 operands, 0.5 px gate
+    (without the 1e-6 layer scale every block contributes, like the "trained-like" v1 case)."""
+    om = make_model(variant, seed=0, trained_like=True)
+    slices = [synthetic.make_iso_slice(90, 640, 600), synthetic.make_iso_slice(91, 512, 512), synthetic.make_iso_slice(92, 700, 512)]
+    want = _oracle_coords(om, slices)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="fp16", micro_batch=2)  # 2 + 1: the per-image norm must not mix images
+    assert tuple(model.engine.dims) == dims
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    planes = ops.normalize_resize(pool, (512, 512))
+    got = model.predict_u8(planes).cpu().numpy()
+    err_px = np.abs(got - want).max() * PX
+    print(f"[coords] {variant} fp16 (GRN): max error {err_px:.4f} px")
+    assert np.isfinite(got).all() and err_px <= tol_px
+    # per-image statistic: an image's coordinates do not depend on its neighbours in the batch
+    solo = model.predict_u8(planes[1:2].contiguous()).cpu().numpy()
+    assert np.array_equal(solo[0], got[1])
