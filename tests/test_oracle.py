@@ -239,3 +239,23 @@ def test_itk_restatement_plane_shortcut_equals_whole_volume_path():
             plan = volumes.plan_midplane(v, sp, d)  # host planning of the product agrees on geometry
             assert plan.out_hw == fast.shape and plan.spacing == spc
     assert itk.new_size((512, 512, 15), (0.7, 0.7, 4.0)) == [1195, 1195, 200]
+
+
+def test_convnext_v2_restatement_grn():
+    """oracle/convnext.py's ConvNeXt-V2 (timm convnextv2; timm absent -> restated, unpinned): GlobalResponseNorm is the identity
+    at its zero init, follows x + b + w * x * g / (mean_c g + eps) with g the per-image, per-channel L2 norm over the tokens,
+    the blocks carry no layer scale, and the state dict uses timm's key names."""
+    from oracle.convnext import GlobalResponseNorm, make_model
+
+    x = torch.randn(2, 5, 7, 12)
+    grn = GlobalResponseNorm(12)
+    assert torch.equal(grn(x), x)
+    with torch.no_grad():
+        grn.weight.copy_(torch.randn(12))
+        grn.bias.copy_(torch.randn(12))
+    g = x.pow(2).sum(dim=(1, 2), keepdim=True).sqrt()
+    want = x * (1 + grn.weight * g / (g.mean(dim=-1, keepdim=True) + 1e-6)) + grn.bias
+    assert torch.allclose(grn(x), want, atol=1e-6)
+    sd = make_model("v2_tiny", seed=0).state_dict()
+    assert "backbone.stages.2.blocks.8.mlp.grn.weight" in sd and sd["backbone.stages.0.blocks.0.mlp.grn.bias"].shape == (384,)
+    assert not any(k.endswith(".gamma") for k in sd) and len([k for k in sd if k.endswith("conv_dw.weight")]) == 18
