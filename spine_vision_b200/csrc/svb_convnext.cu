@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <algorithm>
 #include <memory>
 #include <string>
 #include <vector>
@@ -433,10 +434,15 @@ static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     L.a = o; o += align_up(t0 * c0 * 2, 1024);
     L.h = o; o += align_up(t0 * c0 * 4 * 2, 1024);
     L.grn_part = L.grn_scale = o;
-    if (m->v2) {  // partial sums of squares [nb][tokens / GRN_ROWS][4C] (stage 0 is the largest) and scales [nb][4C] (stage 3 is)
-        const size_t chunks0 = ceil_div<size_t>((size_t)(H / 4) * (W / 4), GRN_ROWS);
-        L.grn_part = o; o += align_up((size_t)nb * chunks0 * c0 * 4 * 4, 1024);
-        L.grn_scale = o; o += align_up((size_t)nb * m->dims[3] * 4 * 4, 1024);
+    if (m->v2) {  // partial sums of squares [nb][ceil(tokens / GRN_ROWS)][4C] and scales [nb][4C]: the largest stage of each
+        size_t part = 0, scale = 0;
+        for (int s = 0, hs = H / 4, wsz = W / 4; s < 4; ++s, hs /= 2, wsz /= 2) {
+            const size_t c4 = (size_t)m->dims[s] * 4;
+            part = std::max(part, ceil_div<size_t>((size_t)hs * wsz, GRN_ROWS) * c4);
+            scale = std::max(scale, c4);
+        }
+        L.grn_part = o; o += align_up((size_t)nb * part * 4, 1024);
+        L.grn_scale = o; o += align_up((size_t)nb * scale * 4, 1024);
     }
     L.total = o;
     return L;

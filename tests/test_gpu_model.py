@@ -251,3 +251,12 @@ def test_model_convnext_v2_grn(variant, dims, tol_px):
     # per-image statistic: an image's coordinates do not depend on its neighbours in the batch
     solo = model.predict_u8(planes[1:2].contiguous()).cpu().numpy()
     assert np.array_equal(solo[0], got[1])
+    # a small input (the last stage has 2 x 3 tokens): the per-stage scratch of the response norm is sized by its largest stage
+    small = ops.normalize_resize(pool, (64, 96))
+    want_s = []
+    for sl in slices:
+        _, t = ref.preprocess_slice(sl, (64, 96))
+        with torch.no_grad():
+            want_s.append(om(t.unsqueeze(0))[0].numpy())
+    got_s = model.predict_u8(small).cpu().numpy()
+    assert np.abs(got_s - np.stack(want_s)).max() <= tol_px / PX
