@@ -57,6 +57,10 @@ struct svb_model {
     int hid = 0, nout = 0;
     int device = 0;
     bool v2 = false;  // ConvNeXt-V2: GRN in every block's MLP, no layer scale
+    // two micro-batches in flight (svb_model_forward): odd micro-batches run on this stream with the second half of the
+    // workspace, so that the ramp-up and tail of one chain's persistent kernels are back-filled by the other chain's CTAs
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
     void* slab = nullptr;
     size_t slab_bytes = 0;
     float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
@@ -64,7 +68,7 @@ struct svb_model {
     DownParams down[4];
     float *hn0w = nullptr, *hn0b = nullptr, *hn1w = nullptr, *hn1b = nullptr, *hw1 = nullptr, *hb1 = nullptr,
           *hw2 = nullptr, *hb2 = nullptr;
-    ActPlan plans[2];
+    ActPlan plans[4];  // (workspace half, micro-batch size) pairs in use: two chains x {full, tail} micro-batch
     int next_plan = 0;
     std::vector<cudaEvent_t> events;
 };
@@ -397,6 +401,9 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
                 return rc;
         }
     }
+    SVB_CUDA_OK(cudaStreamCreateWithFlags(&m->aux_stream, cudaStreamNonBlocking));
+    SVB_CUDA_OK(cudaEventCreateWithFlags(&m->fork_ev, cudaEventDisableTiming));
+    SVB_CUDA_OK(cudaEventCreateWithFlags(&m->join_ev, cudaEventDisableTiming));
     *out = guard.release();
     return SVB_OK;
 #undef NEED
@@ -406,6 +413,9 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
 extern "C" int svb_model_destroy(svb_model* m) {
     if (!m) return SVB_OK;
     for (auto e : m->events) cudaEventDestroy(e);
+    if (m->aux_stream) { cudaStreamSynchronize(m->aux_stream); cudaStreamDestroy(m->aux_stream); }
+    if (m->fork_ev) cudaEventDestroy(m->fork_ev);
+    if (m->join_ev) cudaEventDestroy(m->join_ev);
     if (m->slab) cudaFree(m->slab);
     delete m;
     return SVB_OK;
@@ -492,7 +502,7 @@ static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** o
     for (auto& p : m->plans)
         if (p.ws == ws && p.nb == nb && p.H == H && p.W == W) { *out = &p; return SVB_OK; }
     ActPlan* p = &m->plans[m->next_plan];
-    m->next_plan ^= 1;
+    m->next_plan = (m->next_plan + 1) & 3;
     if (int rc = build_plan(m, p, ws, nb, H, W)) { p->ws = nullptr; return rc; }
     *out = p;
     return SVB_OK;
@@ -838,9 +848,20 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
 
 }  // namespace svb
 
+// SVB_DUAL_CHAIN=0 keeps one micro-batch in flight (A/B testing; also what a workspace of the single size selects)
+static bool dual_chain_enabled() {
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SVB_DUAL_CHAIN");
+        enabled = (e && e[0] == '0') ? 0 : 1;
+    }
+    return enabled != 0;
+}
+
 extern "C" size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int W) {
     if (!m || micro_batch <= 0 || H <= 0 || W <= 0) return 0;
-    return ws_layout(m, micro_batch, H, W).total;
+    const size_t one = align_up(ws_layout(m, micro_batch, H, W).total, 1024);
+    return dual_chain_enabled() ? 2 * one : one;
 }
 
 extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
@@ -855,16 +876,28 @@ extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, in
     SVB_REQUIRE(ws_bytes >= need, SVB_ERR_WORKSPACE_TOO_SMALL, "model_forward: workspace %zu < %zu bytes", ws_bytes, need);
     SVB_REQUIRE((reinterpret_cast<uintptr_t>(d_ws) & 1023) == 0, SVB_ERR_INVALID_ARG, "model_forward: workspace must be 1024-byte aligned");
     Timer tm{m, st, times_ms != nullptr};
-    for (int b0 = 0; b0 < B; b0 += micro_batch) {
+    const size_t one = align_up(need, 1024);
+    const bool dual = dual_chain_enabled() && times_ms == nullptr && B > micro_batch && ws_bytes >= 2 * one && m->aux_stream != nullptr;
+    if (dual) {
+        SVB_CUDA_OK(cudaEventRecord(m->fork_ev, st));
+        SVB_CUDA_OK(cudaStreamWaitEvent(m->aux_stream, m->fork_ev, 0));
+    }
+    int chunk = 0;
+    for (int b0 = 0; b0 < B; b0 += micro_batch, ++chunk) {
         const int nb = (B - b0) < micro_batch ? (B - b0) : micro_batch;
+        const bool odd = dual && (chunk & 1);
+        cudaStream_t cs = odd ? m->aux_stream : st;
+        uint8_t* ws = static_cast<uint8_t*>(d_ws) + (odd ? one : 0);
         int rc;
         if (m->dtype == SVB_FP16)
-            rc = forward_chunk<__half>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout,
-                                       static_cast<uint8_t*>(d_ws), st, tm);
+            rc = forward_chunk<__half>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
         else
-            rc = forward_chunk<__nv_bfloat16>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout,
-                                              static_cast<uint8_t*>(d_ws), st, tm);
+            rc = forward_chunk<__nv_bfloat16>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
         if (rc) return rc;
+    }
+    if (dual) {
+        SVB_CUDA_OK(cudaEventRecord(m->join_ev, m->aux_stream));
+        SVB_CUDA_OK(cudaStreamWaitEvent(st, m->join_ev, 0));
     }
     return tm.finish(times_ms);
 }
