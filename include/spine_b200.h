@@ -187,7 +187,10 @@ typedef struct svb_weight_desc {
 
 int svb_model_create(svb_model** out, const svb_weight_desc* weights, int n_weights, int dtype);
 int svb_model_destroy(svb_model* m);
-/* bytes of workspace svb_model_forward needs for micro-batches of `micro_batch` images */
+/* bytes of workspace svb_model_forward needs for micro-batches of `micro_batch` images.  By default this is TWO micro-batch
+ * workspaces: svb_model_forward then keeps two micro-batches in flight -- even ones on the caller's stream, odd ones on a
+ * stream the handle owns (created in svb_model_create), forked from and joined back into the caller's stream by events, so
+ * the call stays asynchronous and ordered on `stream`.  SVB_DUAL_CHAIN=0 (or a workspace of half the size) keeps one. */
 size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int W);
 /*  d_in_u8  : uint8 [B, H, W] -- K1 output (one plane)
  *  d_coords : float32 [B, num_levels, 2] in [0,1]
