@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace svb;
@@ -90,6 +91,34 @@ static uint16_t to16(float v, int dtype) {
     uint16_t u;
     memcpy(&u, &h, 2);
     return u;
+}
+
+// bulk fp32 -> 16-bit of the big MLP matrices (87 M of the 88 M parameters): bit arithmetic for bf16 (round to nearest even,
+// NaN kept quiet) instead of a library call per element, spread over a few host threads -- model creation is what a short
+// dataset run waits for
+static void convert16_range(const float* src, uint16_t* dst, size_t n, int dtype) {
+    if (dtype == SVB_FP16) {
+        for (size_t i = 0; i < n; ++i) dst[i] = to16(src[i], dtype);
+        return;
+    }
+    for (size_t i = 0; i < n; ++i) {
+        uint32_t u;
+        memcpy(&u, src + i, 4);
+        if ((u & 0x7FFFFFFFu) > 0x7F800000u) { dst[i] = (uint16_t)((u >> 16) | 0x0040u); continue; }  // NaN
+        u += 0x7FFFu + ((u >> 16) & 1u);
+        dst[i] = (uint16_t)(u >> 16);
+    }
+}
+static void convert16(const float* src, uint16_t* dst, size_t n, int dtype) {
+    const size_t nt = n >= (1u << 20) ? 8 : 1;
+    if (nt == 1) { convert16_range(src, dst, n, dtype); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + nt - 1) / nt;
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t lo = t * per, hi = std::min(n, lo + per);
+        if (lo < hi) th.emplace_back(convert16_range, src + lo, dst + lo, hi - lo, dtype);
+    }
+    for (auto& x : th) x.join();
 }
 
 // K-major 2-D operand map: rows x K, box {64, box_rows}, 128-byte swizzle
@@ -337,9 +366,9 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             SVB_REQUIRE(numel(w1) == (int64_t)4 * C * C && numel(w2) == (int64_t)4 * C * C, SVB_ERR_UNSUPPORTED_MODEL,
                         "mlp weights must be [4C,C] and [C,4C]");
             tmp16.resize((size_t)4 * C * C);
-            for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(w1->data[i], dtype);
+            convert16(w1->data, tmp16.data(), tmp16.size(), dtype);
             bp.w1 = slab.put(tmp16.data(), tmp16.size() * 2);
-            for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(w2->data[i], dtype);
+            convert16(w2->data, tmp16.data(), tmp16.size(), dtype);
             bp.w2 = slab.put(tmp16.data(), tmp16.size() * 2);
         }
     }
