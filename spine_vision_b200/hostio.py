@@ -4,7 +4,8 @@
   that can be decoded without SimpleITK: MetaImage ``.mha`` / ``.mhd`` (what SPIDER ships).  It returns a
   ``MedicalVolume`` carrying what the reference reads off the ``sitk.Image`` further down the path:
   ``GetArrayFromImage`` (float32 ``[z, y, x]``), ``GetSpacing``, ``GetDirection``, ``GetOrigin``.
-* ``read_volumes`` decodes a batch on a thread pool straight into ONE pinned float32 buffer (the H2D staging area).
+* ``read_volumes`` decodes a batch on a thread pool into ONE float32 buffer (K0 then stages only the two source planes per
+  volume it needs into pinned memory).
 * ``write_png_batch`` mirrors ``Image.fromarray(crop).save(path)`` (spider.py:158, phenikaa.py:213) for a batch of
   equally sized uint8 crops on a thread pool.
 
@@ -209,8 +210,9 @@ def read_medical_image(path: Path) -> MedicalVolume:
     raise UnsupportedFormatError(f"{fmt} decoding needs SimpleITK, which this build does not link; path: {path}")
 
 
-def read_volumes(paths, n_threads: int = 0, pin: bool = True):
-    """Decode many MetaImage volumes on a thread pool into one (pinned) float32 buffer.
+def read_volumes(paths, n_threads: int = 0, pin: bool = False):
+    """Decode many MetaImage volumes on a thread pool into one float32 buffer (``pin`` is accepted and ignored: whole volumes
+    never travel to the device).
     Returns ``(volumes, errors)``: ``volumes[i]`` is a ``MedicalVolume`` whose array is a view into the shared buffer, or
     ``None`` when file i could not be read (``errors[i]`` holds the reason) -- the drivers skip those series
     (spider.py:139-141)."""
@@ -235,9 +237,7 @@ def read_volumes(paths, n_threads: int = 0, pin: bool = True):
     for s in sizes:
         offs.append(total)
         total += (s + 3) // 4 * 4
-    host = torch.empty(max(total, 4), dtype=torch.float32)
-    if pin and torch.cuda.is_available():
-        host = host.pin_memory()
+    host = torch.empty(max(total, 4), dtype=torch.float32)  # plain host memory: only two planes per volume go to the device
     hv = host.numpy()
     m = len(ok)
     volumes: list[MedicalVolume | None] = [None] * n

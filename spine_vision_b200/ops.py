@@ -105,6 +105,24 @@ class _Workspace:
         return buf
 
 
+class PinnedCache:
+    """Grow-only pinned host staging buffers by tag: ``cudaHostAlloc`` costs milliseconds per call, more than the kernels a
+    chunk of a dataset run feeds.  A buffer is handed out again only by the same tag, so a caller that double-buffers uses
+    two tags.  Not thread-safe per tag (each pipeline stage owns its tags)."""
+
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, tag: str, nelem: int, dtype=torch.float32) -> torch.Tensor:
+        buf = cls._bufs.get(tag)
+        if buf is None or buf.numel() < nelem or buf.dtype != dtype:
+            buf = torch.empty(max(int(nelem), 4), dtype=dtype)
+            if torch.cuda.is_available():
+                buf = buf.pin_memory()
+            cls._bufs[tag] = buf
+        return buf[: max(int(nelem), 4)]
+
+
 def _aligned_ptr(buf: torch.Tensor, align: int = 1024) -> tuple[int, int]:
     p = buf.data_ptr()
     a = (p + align - 1) // align * align

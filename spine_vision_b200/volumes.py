@@ -90,6 +90,9 @@ def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spaci
     return MidplanePlan((ns[a_row], ns[a_col]), (float(new_spacing[a_row]), float(new_spacing[a_col])), slab, desc)
 
 
+_STAGE_FLIP = [0]
+
+
 def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integer_pixels=None):
     """K0 over a batch: list of ``[z, y, x]`` arrays + ``image.GetSpacing()`` (+ ``GetDirection()``) per series ->
     ``(ops.SlicePool of the middle isotropic sagittal slices, [(row_spacing, col_spacing)])``."""
@@ -105,7 +108,9 @@ def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integ
     for p in plans:
         vol_offs.append(vol_total)
         vol_total += (p.slab.size + 3) // 4 * 4
-    host = torch.empty(max(vol_total, 4), dtype=torch.float32).pin_memory()
+    # two alternating pinned staging buffers: the copy of call k may still be in flight when call k+1 fills its slabs
+    _STAGE_FLIP[0] ^= 1
+    host = ops.PinnedCache.get(f"k0_slabs_{_STAGE_FLIP[0]}", max(vol_total, 4))
     hv = host.numpy()
     descs = (K0Series * max(B, 1))()
     for i, p in enumerate(plans):
