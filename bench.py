@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="series per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
-    ap.add_argument("--micro-batch", type=int, default=37, help="images per pass through the network (37 x 4 = 148 SMs: whole waves)")
+    ap.add_argument("--micro-batch", type=int, default=64, help="images per pass through the network (two passes are in flight)")
     ap.add_argument("--stream-chunk", type=int, default=0, help="series per H2D chunk of the end-to-end path (0 = the micro-batch)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic slices (tiled to the batch)")
     ap.add_argument("--ref-series", type=int, default=4, help="series per step of the CPU reference arm")

@@ -201,7 +201,7 @@ class LocalizationModel:
     """What ``load_localization_model`` returns: the reference hands back an ``nn.Module`` in eval
     mode; this is its inference-only device twin (``eval()`` / ``to()`` are accepted no-ops)."""
 
-    def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 37):
+    def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 64):
         import os
 
         dtype = dtype or os.environ.get("SPINE_B200_DTYPE", "bf16")
