@@ -295,7 +295,7 @@ def run_b200(args):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": f"synthetic ({len(base)} distinct seeded slices tiled to {B}; random-init convnext_base)",
             "config": {"workload": WORKLOAD, "series_per_gpu_per_step": B, "micro_batch": args.micro_batch,
-                       "l2": "inputs larger than L2 (1.46 GB of fp32 slices per step; ~1 GB of activations per micro-batch)"},
+                       "l2": "inputs larger than L2 (1.46 GB of fp32 slices per step; ~1.8 GB of activations per micro-batch, two in flight)"},
             "crops_per_sec": value * 5,
             "clocks": sampler.summary(),
             "e2e": {"value": e2e, "unit": "series/s", "h2d_bytes_per_step": int(series.nbytes + B * 16 + n_crops * 16),
