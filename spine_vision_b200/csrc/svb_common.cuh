@@ -105,10 +105,10 @@ template <> struct Cvt<__half> {
         return __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
     }
     static __device__ __forceinline__ uint32_t pack2(float a, float b) {
-        a = fminf(fmaxf(a, -65504.0f), 65504.0f);
-        b = fminf(fmaxf(b, -65504.0f), 65504.0f);
-        __half2 p = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&p);
+        // one F2FP.SATFINITE.F16.F32.PACK_AB: round to nearest even, out-of-range values saturate at +-65504
+        uint32_t r;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+        return r;
     }
     static __device__ __forceinline__ float2 unpack2(uint32_t u) {
         __half2 p = *reinterpret_cast<__half2*>(&u);
