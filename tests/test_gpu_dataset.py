@@ -85,3 +85,18 @@ def test_dataset_with_checkpoint_and_unreadable_series(tmp_path):
     for lvl in range(1, 6):
         got = np.asarray(Image.open(cfg.output_path / "images" / f"spider_{pids[0]}_sag_t2_L{lvl}.png"))
         assert np.array_equal(got, ctx.crop(lvl - 1))
+
+
+@requires_gpu
+def test_cli_entry_point(tmp_path, capsys):
+    """``python -m spine_vision_b200 dataset classification ...`` end to end: same tree, same CSV as the reference's driver."""
+    import spine_vision_b200.__main__ as cli
+
+    g = np.load(GOLDEN / "host_dataset.npz")
+    synthetic.make_spider_tree(tmp_path, seed=0)
+    synthetic.make_phenikaa_tree(tmp_path, seed=0)
+    rc = cli.main(["dataset", "classification", "--base-path", str(tmp_path), "--output-name", "cls", "--crop-size", "128", "128",
+                   "--crop-delta-mm", *[str(float(v)) for v in g["delta_mm"]], "--last-disc-angle-boost", "1.5", "--device", dev()])
+    assert rc == 0 and "39 records" in capsys.readouterr().out
+    assert (tmp_path / "processed" / "cls" / "annotations.csv").read_text() == g["horizontal_csv"].item()
+    _check_tree(tmp_path / "processed" / "cls", [str(n) for n in g["horizontal_names"]], g["horizontal_images"])

@@ -284,3 +284,24 @@ def test_localization_series_lookup(tmp_path):
     assert cfg.lumbar_coords_path == tmp_path / "raw" / "Lumbar Coords" and cfg.rsna_path == tmp_path / "raw" / "RSNA"
     with pytest.raises(ValueError, match="empty records"):
         loc.write_records_csv([], tmp_path / "x.csv")  # io/tabular.py:28-29
+
+
+def test_cli_flags_build_the_reference_config():
+    """``python -m spine_vision_b200 dataset classification ...``: the flags tyro derives from the reference's config
+    (cli/__init__.py:30-56) -- kebab-case, tuple fields as several values, --flag / --no-flag booleans."""
+    import argparse
+
+    import spine_vision_b200.__main__ as cli
+
+    p = argparse.ArgumentParser()
+    cli._add_fields(p, dataset.ClassificationDatasetConfig)
+    ns = vars(p.parse_args(["--base-path", "/data", "--localization-model-path", "/w/best_model.pt", "--crop-size", "128", "128",
+                            "--crop-delta-mm", "50", "20", "30", "30", "--crop-mode", "rotated", "--no-include-phenikaa",
+                            "--model-variant", "v2_base", "--last-disc-angle-boost", "1.5"]))
+    cfg = dataset.ClassificationDatasetConfig(**{k: tuple(v) if isinstance(v, list) else v for k, v in ns.items()})
+    assert cfg.crop_size == (128, 128) and cfg.crop_delta_mm == (50.0, 20.0, 30.0, 30.0) and cfg.crop_mode == "rotated"
+    assert cfg.include_phenikaa is False and cfg.include_spider is True and cfg.model_variant == "v2_base"
+    assert str(cfg.localization_model_path) == "/w/best_model.pt" and cfg.last_disc_angle_boost == 1.5
+    assert dataset.ClassificationDatasetConfig(**vars(p.parse_args([]))) == dataset.ClassificationDatasetConfig()  # defaults = the reference's
+    with pytest.raises(SystemExit):
+        p.parse_args(["--crop-mode", "diagonal"])
