@@ -282,6 +282,17 @@ def run_b200(args):
             traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
         except Exception:
             pass
+        # algorithmic HBM bytes of the GEMMs of one step (A + W + out, + the residual read of fc2), 16-bit operands: what `traffic`
+        # (measured DRAM bytes) is to be compared with
+        gemm_bytes = 0.0
+        hh, ww = IMAGE_SIZE[0] // 4, IMAGE_SIZE[1] // 4
+        for si, (cd, nd) in enumerate(zip(model.engine.dims, model.engine.depths)):
+            if si > 0:
+                hh, ww = hh // 2, ww // 2
+                mm, kk = B * hh * ww, 4 * model.engine.dims[si - 1]
+                gemm_bytes += 2.0 * (mm * kk + cd * kk + mm * cd)
+            mm = B * hh * ww
+            gemm_bytes += nd * 2.0 * ((mm * cd + 4 * cd * cd + mm * 4 * cd) + (mm * 4 * cd + 4 * cd * cd + 2 * mm * cd))
         dw_ms = times.get("dwconv_ln", 0.0) / args.steps
         dw_flops = 2.0 * 49 * B * sum(d * (IMAGE_SIZE[0] >> (2 + i)) * (IMAGE_SIZE[1] >> (2 + i)) * n
                                       for i, (d, n) in enumerate(zip(model.engine.dims, model.engine.depths)))
@@ -306,7 +317,7 @@ def run_b200(args):
             "gpu_launches": int(gpu_launches),
             "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": traffic, "traffic_source": f"profiles/{TRAFFIC_JSON} (ncu --set full, per-shape dram bytes x launches)",
+                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{TRAFFIC_JSON} (ncu --set full, per-shape dram bytes x launches)",
                          "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
                          "timing": "CUDA event pair around every launch, separate pass over the same steps"},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
