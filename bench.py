@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256, help="series per GPU per step")
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
     ap.add_argument("--micro-batch", type=int, default=64, help="images per pass through the network (two passes are in flight)")
-    ap.add_argument("--stream-chunk", type=int, default=0, help="series per H2D chunk of the end-to-end path (0 = the micro-batch)")
+    ap.add_argument("--stream-chunk", type=int, default=0, help="series per H2D chunk of the end-to-end path (0 = two micro-batches: both chains of the forward busy)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic slices (tiled to the batch)")
     ap.add_argument("--ref-series", type=int, default=4, help="series per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -159,7 +159,7 @@ def run_b200(args):
     host, offs, shapes = series.host, series.offs, series.shapes
     model = LocalizationModel(synthetic.random_state_dict("base", seed=0), dev, dtype=args.dtype, micro_batch=args.micro_batch)
     n_crops = B * 5
-    streamer = pipeline.StreamedLocalizer(model, dev, CROP_DELTA_MM, CROP_SIZE, IMAGE_SIZE, SECOND_SIZE, chunk=args.stream_chunk or args.micro_batch)
+    streamer = pipeline.StreamedLocalizer(model, dev, CROP_DELTA_MM, CROP_SIZE, IMAGE_SIZE, SECOND_SIZE, chunk=args.stream_chunk or 2 * args.micro_batch)
 
     def step_resident(pool, times=None):
         return pipeline.localize_and_crop(pool, model, CROP_DELTA_MM, CROP_SIZE, IMAGE_SIZE, SECOND_SIZE, times=times)

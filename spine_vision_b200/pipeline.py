@@ -161,7 +161,7 @@ class StreamedLocalizer:
     alternate; a slot is reused only after its previous results have left the device."""
 
     def __init__(self, model: LocalizationModel | None, device="cuda:0", crop_delta_mm=(55, 15, 17.5, 20), crop_size=(256, 256),
-                 image_size=(512, 512), second_size=(256, 256), chunk: int = 64):
+                 image_size=(512, 512), second_size=(256, 256), chunk: int = 128):
         self.model, self.device = model, torch.device(device)
         self.crop_delta_mm, self.crop_size, self.image_size, self.second_size = crop_delta_mm, tuple(crop_size), tuple(image_size), second_size
         self.chunk = int(chunk)
