@@ -64,7 +64,7 @@ class ClassificationDatasetConfig(BaseModel):
     append_to_existing: bool = True
     device: str = "cuda:0"
 
-    chunk_series: int = 64
+    chunk_series: int = 128
     io_threads: int = 0
     png_level: int = 6
 
