@@ -486,13 +486,13 @@ int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* k
             case 0x00200013: info->instance_number = atoi(dcm_str(c, len).c_str()); break;
             case 0x00200032: if (dcm_numbers(dcm_str(c, len), d, 3) == 3) { memcpy(info->position, d, 24); info->has_position = 1; } break;
             case 0x00200037: if (dcm_numbers(dcm_str(c, len), d, 6) == 6) { memcpy(info->orientation, d, 48); info->has_orientation = 1; } break;
-            case 0x00280002: { DcmCursor t = c; info->samples_per_pixel = t.u16(); } break;
+            case 0x00280002: if (len >= 2) { DcmCursor t = c; info->samples_per_pixel = t.u16(); } break;
             case 0x00280004: { const std::string s = dcm_str(c, len); info->monochrome1 = s == "MONOCHROME1"; } break;
-            case 0x00280010: { DcmCursor t = c; info->rows = t.u16(); } break;
-            case 0x00280011: { DcmCursor t = c; info->cols = t.u16(); } break;
+            case 0x00280010: if (len >= 2) { DcmCursor t = c; info->rows = t.u16(); } break;
+            case 0x00280011: if (len >= 2) { DcmCursor t = c; info->cols = t.u16(); } break;
             case 0x00280030: if (dcm_numbers(dcm_str(c, len), d, 2) == 2) { info->pixel_spacing[0] = d[0]; info->pixel_spacing[1] = d[1]; info->has_spacing = 1; } break;
-            case 0x00280100: { DcmCursor t = c; info->bits_allocated = t.u16(); } break;
-            case 0x00280103: { DcmCursor t = c; info->pixel_representation = t.u16(); } break;
+            case 0x00280100: if (len >= 2) { DcmCursor t = c; info->bits_allocated = t.u16(); } break;
+            case 0x00280103: if (len >= 2) { DcmCursor t = c; info->pixel_representation = t.u16(); } break;
             case 0x00281052: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_intercept = d[0]; break;
             case 0x00281053: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_slope = d[0]; break;
             case 0x00180050: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->slice_thickness = d[0]; break;

@@ -305,3 +305,42 @@ def test_cli_flags_build_the_reference_config():
     assert dataset.ClassificationDatasetConfig(**vars(p.parse_args([]))) == dataset.ClassificationDatasetConfig()  # defaults = the reference's
     with pytest.raises(SystemExit):
         p.parse_args(["--crop-mode", "diagonal"])
+
+
+def test_dicom_parser_survives_truncated_and_corrupt_files(tmp_path):
+    """Every prefix of a valid slice file, zero-length US elements and random byte flips: the native parser answers with an
+    error (or a decoded slice), never with a crash or an out-of-bounds read -- the reference's ``except`` around
+    ``sitk.ReadImage`` (datasets/localization.py:262-270) turns such files into skipped images."""
+    import struct
+
+    px = (np.arange(12 * 10, dtype=np.uint16).reshape(12, 10) * 7) % 4000
+    good = tmp_path / "good.dcm"
+    synthetic.write_dicom_slice(good, px, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1)
+    blob = good.read_bytes()
+    arrays, errors = hostio.read_dicom_files([good])
+    assert errors == [None] and np.array_equal(arrays[0], px.astype(np.float32))
+    paths = []
+    for cut in list(range(0, 200)) + list(range(200, len(blob), 7)):
+        p = tmp_path / f"cut_{cut}.dcm"
+        p.write_bytes(blob[:cut])
+        paths.append(p)
+    rows_elem = struct.pack("<HH", 0x0028, 0x0010) + b"US" + struct.pack("<H", 2)
+    at = blob.index(rows_elem)
+    zero_len = blob[:at] + struct.pack("<HH", 0x0028, 0x0010) + b"US" + struct.pack("<H", 0) + blob[at + len(rows_elem) + 2 :]
+    (tmp_path / "zero_len.dcm").write_bytes(zero_len)
+    paths.append(tmp_path / "zero_len.dcm")
+    rng = np.random.default_rng(0)
+    for k in range(200):
+        b = bytearray(blob)
+        for pos in rng.integers(132, len(blob) - px.nbytes, size=3):
+            b[pos] = int(rng.integers(0, 256))
+        p = tmp_path / f"flip_{k}.dcm"
+        p.write_bytes(bytes(b))
+        paths.append(p)
+    arrays, errors = hostio.read_dicom_files(paths)
+    n_cut = len(paths) - 201
+    assert all(a is None and e for a, e in zip(arrays[:n_cut], errors[:n_cut]))  # every strict prefix is an error
+    assert arrays[n_cut] is None and errors[n_cut]                               # no Rows value -> error, not 0 x cols
+    for a, e in zip(arrays[n_cut + 1 :], errors[n_cut + 1 :]):
+        assert (a is None) == bool(e)
+        assert a is None or (a.ndim == 2 and a.dtype == np.float32)
