@@ -2,6 +2,7 @@
 encoder vs Pillow's decoder, and the dataset driver's host logic (work list, records, CSV, resume) vs the CSVs the
 reference's OWN driver wrote (tests/golden/host_dataset.npz, oracle/make_golden_host.py).  No GPU work here."""
 import io
+from pathlib import Path
 import zlib
 
 import numpy as np
@@ -344,3 +345,40 @@ def test_dicom_parser_survives_truncated_and_corrupt_files(tmp_path):
     for a, e in zip(arrays[n_cut + 1 :], errors[n_cut + 1 :]):
         assert (a is None) == bool(e)
         assert a is None or (a.ndim == 2 and a.dtype == np.float32)
+
+
+def test_native_decoders_under_address_sanitizer(tmp_path):
+    """tests/native/fuzz_hostio.cpp: svb_hostio.cpp itself rebuilt with -fsanitize=address,undefined and driven over mutants
+    (truncations, byte flips, extreme 32-bit fields, rewritten digits, dropped / doubled chunks) of valid MetaImage and DICOM
+    files, plus the PNG encoder at and below its buffer bound.  A sanitizer report aborts the run."""
+    import shutil
+    import subprocess
+
+    root = Path(__file__).resolve().parent.parent
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "fuzz_hostio"
+    cc = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-o", str(exe),
+                         str(root / "tests/native/fuzz_hostio.cpp"), str(root / "spine_vision_b200/csrc/svb_hostio.cpp"), "-lz", "-lpthread"],
+                        capture_output=True, text=True)
+    if cc.returncode != 0 and "asan" in cc.stderr.lower():
+        pytest.skip("libasan not installed")
+    assert cc.returncode == 0, cc.stderr[-2000:]
+    seeds = tmp_path / "seeds"
+    work = tmp_path / "work"
+    seeds.mkdir()
+    work.mkdir()
+    rng = np.random.default_rng(0)
+    vol = rng.integers(-100, 3000, size=(5, 14, 11)).astype(np.int16)
+    synthetic.write_metaimage(seeds / "a.mha", vol, (0.6, 0.7, 3.3), compressed=True)
+    synthetic.write_metaimage(seeds / "b.mha", vol.astype(np.float32), (0.6, 0.7, 3.3), compressed=False)
+    synthetic.write_metaimage(seeds / "c.mhd", vol.astype(np.uint16), (0.6, 0.7, 3.3), compressed=True, separate_raw=True)
+    synthetic.write_metaimage(seeds / "d.mha", vol.astype(np.float64), (0.6, 0.7, 3.3), compressed=False, big_endian=True)
+    px = (np.arange(12 * 10, dtype=np.uint16).reshape(12, 10) * 7) % 4000
+    synthetic.write_dicom_slice(seeds / "e.dcm", px, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1)
+    synthetic.write_dicom_slice(seeds / "i.dcm", px.astype(np.int16), (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1,
+                                explicit=False, rescale=(2.0, -1024.0))
+    files = [str(seeds / n) for n in ("a.mha", "b.mha", "c.mhd", "d.mha", "e.dcm", "i.dcm")]
+    run = subprocess.run([str(exe), str(work), "1500", *files], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
+    assert "no sanitizer report" in run.stdout
