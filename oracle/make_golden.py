@@ -63,10 +63,46 @@ def golden_rotated(ref) -> None:
     np.savez_compressed(GOLDEN / "k3_rotated.npz", **out)
 
 
+SMALL_SERIES = [(30, 150, 121), (31, 90, 300), (32, 200, 234), (33, 260, 180), (34, 64, 64), (35, 7, 500)]
+
+
+def golden_small(ref) -> None:
+    """Slices SMALLER than the crop box (the box is clipped to the whole slice on one or both axes, cropping.py:335-341) and
+    degenerate aspect ratios (a 7 x 500 strip letterboxes to 2 rows), both crop modes, crop sizes 128 and the config default
+    256 (config.py:47-48), through the reference's own CropContext."""
+    out = {}
+    for seed, h, w in SMALL_SERIES:
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = synthetic.make_coords(2, seed=200 + seed, border_frac=0.3, hw=(h, w))
+        xy[1, 0] = (0.0, 0.0)
+        xy[1, 4] = (0.99999, 0.99999)
+        out[f"xy_{seed}_{h}_{w}"] = xy
+        for di, dmm in enumerate(CROP_DELTAS_MM):
+            dpx = ref.mm_to_pixels(dmm, (0.3, 0.3))
+            for cs in (128, 256):
+                for mode in ("horizontal", "rotated"):
+                    if cs == 256 and (mode == "rotated" or di == 0):
+                        continue  # 256 x 256 (the config default): horizontal mode with the default deltas only (fixture size)
+                    res = np.zeros((2, 5, cs, cs), dtype=np.uint8)
+                    for s in range(2):
+                        locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                        ctx = ref.CropContext(image=img, ivd_locations=locs, crop_size=(cs, cs), crop_delta_px=dpx, mode=mode)
+                        for i in range(5):
+                            res[s, i] = ctx.crop(i)
+                    out[f"crops_{seed}_{h}_{w}_d{di}_c{cs}_{mode}"] = res
+    np.savez_compressed(GOLDEN / "k3_small.npz", **out)
+
+
 def main() -> None:
     import sys
 
     ref = ref_shim.load()
+    if "--small-only" in sys.argv:
+        golden_small(ref)
+        for f in sorted(GOLDEN.glob("k3_small.npz")):
+            print(f.name, f.stat().st_size)
+        return
+    golden_small(ref)
     if "--rotated-only" in sys.argv:
         golden_rotated(ref)
         for f in sorted(GOLDEN.glob("k3_rotated.npz")):

@@ -139,3 +139,29 @@ def test_k3_rotated_matches_reference_golden_bit_exact():
                 assert np.array_equal(crops.cpu().numpy(), want)
     assert total == 160 and bad == 0, f"{bad} differing pixels over {total} rotated crops"
     assert np.allclose(g["notebook_angles_2pt"], [4.96908734, 9.93817468])
+
+
+def test_k3_small_slices_match_reference_golden_bit_exact():
+    """Slices SMALLER than the crop box (150 x 121, 90 x 300, exactly 200 x 234, ...) and a 7 x 500 strip, both crop modes,
+    128 and 256 crops, corner centres (0, 0) and (0.99999, 0.99999): K3 against crops frozen from the reference's own
+    CropContext (tests/golden/k3_small.npz)."""
+    g = np.load(GOLDEN / "k3_small.npz")
+    n = bad = 0
+    for k in g.files:
+        if not k.startswith("crops_"):
+            continue
+        seed, h, w, d, c, mode = k[len("crops_"):].split("_")
+        seed, h, w, di, cs = int(seed), int(h), int(w), int(d[1:]), int(c[1:])
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        pool = ops.SlicePool.from_numpy([img, img], dev())
+        crops, _, _ = pipeline.crop_levels(pool, torch.from_numpy(xy[:2]).to(dev()), DELTAS[di], None, (cs, cs), None, mode=mode)
+        got = crops.cpu().numpy()
+        n += 10
+        bad += int((got != g[k]).sum())
+        dpx = cropping.mm_to_pixels(DELTAS[di], (0.3, 0.3))
+        locs = {i: (float(xy[1, i, 0]), float(xy[1, i, 1])) for i in range(5)}
+        ctx = cropping.CropContext(img, locs, (cs, cs), dpx, mode, device=dev())  # the one-series drop-in entry
+        for i in (0, 4):
+            assert np.array_equal(ctx.crop(i), g[k][1, i]), (k, i)
+    assert n == 6 * (2 * 2 + 1) * 10 and bad == 0, f"{bad} differing pixels over {n} crops"

@@ -259,3 +259,33 @@ def test_convnext_v2_restatement_grn():
     sd = make_model("v2_tiny", seed=0).state_dict()
     assert "backbone.stages.2.blocks.8.mlp.grn.weight" in sd and sd["backbone.stages.0.blocks.0.mlp.grn.bias"].shape == (384,)
     assert not any(k.endswith(".gamma") for k in sd) and len([k for k in sd if k.endswith("conv_dw.weight")]) == 18
+
+
+def test_small_slice_crops_match_reference_golden():
+    """Slices smaller than the crop box and degenerate strips (tests/golden/k3_small.npz, frozen from the reference's own
+    CropContext in both modes): the port and the fixed-point restatements reproduce them bit for bit."""
+    from oracle import fixedpoint as fp
+
+    g = np.load(GOLDEN / "k3_small.npz")
+    deltas = [(50, 20, 30, 30), (55, 15, 17.5, 20)]
+    n = 0
+    for k in g.files:
+        if not k.startswith("crops_"):
+            continue
+        seed, h, w, d, c, mode = k[len("crops_"):].split("_")
+        seed, h, w, di, cs = int(seed), int(h), int(w), int(d[1:]), int(c[1:])
+        img = synthetic.make_iso_slice(seed, h, w)
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        dpx = fx.mm_to_pixels(deltas[di], (0.3, 0.3))
+        for s in range(2):
+            locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+            ang = fp.rotation_angles(locs, (h, w), 1.0) if mode == "rotated" else None
+            for i in range(5):
+                if mode == "horizontal":
+                    got = fx.crop_region_horizontal(img, locs[i][0], locs[i][1], (cs, cs), dpx)
+                    assert np.array_equal(ref.crop_region_horizontal(img, locs[i][0], locs[i][1], (cs, cs), dpx), g[k][s, i]), (k, s, i)
+                else:
+                    got = fp.crop_region_rotated(img, locs[i][0], locs[i][1], (cs, cs), dpx, ang[i])
+                assert np.array_equal(got, g[k][s, i]), (k, s, i)
+                n += 1
+    assert n == 6 * (2 * 2 + 1) * 10
