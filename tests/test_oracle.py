@@ -289,3 +289,33 @@ def test_small_slice_crops_match_reference_golden():
                 assert np.array_equal(got, g[k][s, i]), (k, s, i)
                 n += 1
     assert n == 6 * (2 * 2 + 1) * 10
+
+
+def test_pillow_pass_order_for_slivers_is_pinned():
+    """The installed Pillow (12.2.0) resizes an image more than 100 times taller than wide VERTICALLY first when the height
+    shrinks (``Image.resize``: ``self.size[1] > self.size[0] * 100 and size[1] < self.size[1]``); every other shape -- and every
+    shape under the reference's pinned Pillow 10.2.0 (uv.lock:2563-2564) -- goes horizontally first.  The restatement (and K1)
+    keep the single horizontal-first order; this test pins where the two part so that the exception is a statement, not a
+    surprise: outside the rule the restatement equals Pillow, inside it Pillow equals the transposed order."""
+    from PIL import Image
+
+    rng = np.random.default_rng(5)
+
+    def pil(u8, hw):
+        return np.asarray(Image.fromarray(u8).resize((hw[1], hw[0]), Image.BILINEAR))
+
+    def vertical_first(u8, hw):
+        return fx.pillow_resize_u8(fx.pillow_resize_u8(u8, (hw[0], u8.shape[1])), hw)
+
+    for shape, out_hw in [((873, 9), (512, 512)), ((600, 6), (512, 512)), ((400, 2), (512, 512)), ((1195, 12), (512, 512)),
+                          ((2, 793), (512, 512)), ((889, 36), (64, 96))]:
+        u8 = rng.integers(0, 256, size=shape).astype(np.uint8)
+        assert not (shape[0] > 100 * shape[1] and out_hw[0] < shape[0])
+        assert np.array_equal(fx.pillow_resize_u8(u8, out_hw), pil(u8, out_hw)), shape
+    import inspect
+
+    if "self.size[0] * 100" in inspect.getsource(Image.Image.resize):  # the rule is in the installed Pillow's Python layer
+        for shape, out_hw in [((873, 5), (512, 512)), ((873, 8), (512, 512)), ((601, 6), (512, 512)), ((500, 3), (64, 96))]:
+            u8 = rng.integers(0, 256, size=shape).astype(np.uint8)
+            assert np.array_equal(vertical_first(u8, out_hw), pil(u8, out_hw)), shape
+            assert not np.array_equal(fx.pillow_resize_u8(u8, out_hw), pil(u8, out_hw)), shape
