@@ -5,4 +5,3 @@ tail -n 30 gpurun_out/final_pytest_gpu.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench24_reference.json 2> gpurun_out/bench24_reference.err; echo "ref rc=$?"
 timeout 600 python bench.py > gpurun_out/bench24.json 2> gpurun_out/bench24.err; echo "bench rc=$?"
 cat gpurun_out/bench24.json | cut -c1-600
-( time timeout 420 compute-sanitizer --tool memcheck --error-exitcode 9 python tests/sanitize_gpu.py ) > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck rc=$?"; tail -n 12 gpurun_out/sanitize_memcheck.log

@@ -1,4 +1,5 @@
-"""One small pass over EVERY kernel of libspine_b200.so, meant to run under compute-sanitizer:
+"""One small pass over EVERY kernel of libspine_b200.so, meant to run under compute-sanitizer (closed on the round-1 GPU pool:
+"runs under it have left GPUs needing a reset"; the script also runs plain as a walk over every guarded edge):
 
     compute-sanitizer --tool memcheck --error-exitcode 9 python tests/sanitize_gpu.py          # out-of-bounds / misaligned
     compute-sanitizer --tool racecheck --error-exitcode 9 python tests/sanitize_gpu.py k1k3    # shared-memory hazards (K1/K3)

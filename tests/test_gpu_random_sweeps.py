@@ -143,3 +143,26 @@ def test_k3_random_rotated_vs_reference(seed):
             assert np.array_equal(got[i], want), f"slice {(h, w)} level {i} angle {want_ctx.rotation_angles[i]:.2f}: {(got[i] != want).sum()} px differ"
             total += 1
     assert total == 30
+
+
+@pytest.mark.parametrize("image_size", [(32, 32), (64, 32), (32, 96), (96, 160), (224, 224), (352, 288), (1024, 512)])
+def test_localizer_unusual_image_sizes_vs_fp32_oracle(image_size):
+    """``image_size`` is a config field (config.py:53-54): every multiple of 32 must work, down to 32 x 32 where the last stage
+    is a single token and every depthwise window hangs over all four borders.  Same normalised gate as at 512^2 (0.5 px / 512)."""
+    from oracle.convnext import make_model
+
+    om = make_model("base", seed=0)
+    slices = [synthetic.make_iso_slice(300, 400, 380), synthetic.make_iso_slice(301, 333, 517), synthetic.make_iso_slice(302, 640, 650)]
+    model = cropping.LocalizationModel(om.state_dict(), dev(), dtype="bf16", micro_batch=2)
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    planes = ops.normalize_resize(pool, image_size)
+    want = []
+    for i, sl in enumerate(slices):
+        plane, t = ref.preprocess_slice(sl, image_size)
+        assert np.array_equal(planes[i].cpu().numpy(), plane)
+        with torch.no_grad():
+            want.append(om(t.unsqueeze(0))[0].numpy())
+    got = model.predict_u8(planes).cpu().numpy()
+    err = float(np.abs(got - np.stack(want)).max())
+    print(f"[coords] image_size={image_size}: max normalised error {err:.2e}")
+    assert np.isfinite(got).all() and err <= 0.5 / 512
