@@ -490,6 +490,7 @@ namespace svb {
 
 struct K3Geom {
     int x1, x2, y1, y2, new_h, new_w, y_off, x_off;
+    double scale_x, scale_y;  // cv2.resize: 1.0 / (dst / src) per axis, double
 };
 
 // Workspace: Pillow tables for the second output: hb2[ow2][2], hk2[ow2][ks2w], vb2[oh2][2], vk2[oh2][ks2h]
@@ -600,6 +601,11 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
             q.x_off = (cw - q.new_w) >> 1;
             if (q.new_h <= 0 || q.new_w <= 0 || q.new_h > ch || q.new_w > cw) q.new_h = q.new_w = 0;
         }
+        q.scale_x = q.scale_y = 1.0;
+        if (q.new_h > 0 && q.new_w > 0) {  // two IEEE double divisions per axis: once per crop, not once per thread
+            q.scale_x = __ddiv_rn(1.0, __ddiv_rn((double)q.new_w, (double)bw));
+            q.scale_y = __ddiv_rn(1.0, __ddiv_rn((double)q.new_h, (double)bh));
+        }
         g = q;
         if (geom_out != nullptr) {
             int32_t* go = geom_out + 8 * (size_t)n;
@@ -645,6 +651,32 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         // (lane = column, stride 32), two rows x eight column groups = up to 16 independent loads in flight per thread;
         // the address of a load is one add away from the row pointer (the kernel is issue-bound).
         float mn = INFINITY, mx = -INFINITY;
+        if (rot == nullptr) {
+            // axis-aligned box: row pointers once per row pair, every load one immediate offset away; a column beyond the
+            // box repeats the thread's first pixel and a missing second row re-reads the first (min / max do not care)
+            for (int y = wid; y < bh; y += 2 * nwarps) {
+                const float* ra = src + (long long)y * W;
+                const float* rb = (y + nwarps < bh) ? ra + (long long)nwarps * W : ra;
+                for (int x0 = lane; x0 < bw; x0 += 256) {
+                    const float* pa = ra + x0;
+                    const float* pb = rb + x0;
+                    float v[16];
+                    v[0] = __ldg(pa);
+                    v[8] = __ldg(pb);
+#pragma unroll
+                    for (int u = 1; u < 8; ++u) {
+                        const bool in = x0 + 32 * u < bw;
+                        v[u] = in ? __ldg(pa + 32 * u) : v[0];
+                        v[8 + u] = in ? __ldg(pb + 32 * u) : v[8];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        mn = fminf(mn, v[u]);
+                        mx = fmaxf(mx, v[u]);
+                    }
+                }
+            }
+        } else {
         for (int y = wid; y < bh; y += 2 * nwarps) {
             const int y2 = y + nwarps;
             for (int x0 = lane; x0 < bw; x0 += 256) {
@@ -669,6 +701,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
                 }
             }
         }
+        }
         mn = warp_min(mn);
         mx = warp_max(mx);
         if (lane == 0) { s_red[0][wid] = mn; s_red[1][wid] = mx; }
@@ -682,8 +715,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         }
         // resize tables while the reduction finishes
         {
-            const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)g.new_w, (double)bw));
-            const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)g.new_h, (double)bh));
+            const double scale_x = g.scale_x, scale_y = g.scale_y;
             for (int i = tid; i < g.new_w; i += nthr) cv_axis_entry(i, bw, scale_x, true, xs[i], xa0[i], xa1[i]);
             for (int i = tid; i < g.new_h; i += nthr) cv_axis_entry(i, bh, scale_y, false, ys[i], yb0[i], yb1[i]);
         }
@@ -693,6 +725,40 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         const float rng = (flags & SVB_K3_NO_NORMALIZE) ? 0.0f : __fsub_rn(s_mm[1], mnv);
         // pass 2: normalise the box into shared memory (second read is an L1/L2 hit); same row-wise walk
         const float kfast = rng > 0.0f ? __fdiv_rn(255.0f, rng) : 0.0f;
+        if (rot == nullptr) {
+            // axis-aligned box, same walk as pass 1; the scale-or-cast decision is taken once, outside the loops
+            auto rows = [&](auto conv) {
+                for (int y = wid; y < bh; y += 2 * nwarps) {
+                    const bool two = y + nwarps < bh;
+                    const float* ra = src + (long long)y * W;
+                    const float* rb = two ? ra + (long long)nwarps * W : ra;
+                    uint8_t* da = s_box + y * bw;  // box pixels are stored row-major
+                    uint8_t* db = da + nwarps * bw;
+                    for (int x0 = lane; x0 < bw; x0 += 256) {
+                        const float* pa = ra + x0;
+                        const float* pb = rb + x0;
+                        float v[16];
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            const bool in = x0 + 32 * u < bw;
+                            v[u] = in ? __ldg(pa + 32 * u) : 0.0f;
+                            v[8 + u] = in ? __ldg(pb + 32 * u) : 0.0f;
+                        }
+                        uint8_t* qa = da + x0;
+                        uint8_t* qb = db + x0;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            if (x0 + 32 * u < bw) {
+                                qa[32 * u] = conv(v[u]);
+                                if (two) qb[32 * u] = conv(v[8 + u]);
+                            }
+                        }
+                    }
+                }
+            };
+            if (rng > 0.0f) rows([&](float v) { return (uint8_t)normalize_px_fast(v, mnv, rng, kfast); });
+            else rows([&](float v) { return (uint8_t)cast_f32_u8(v); });
+        } else {
         for (int y = wid; y < bh; y += 2 * nwarps) {
             const int y2 = y + nwarps;
             for (int x0 = lane; x0 < bw; x0 += 256) {
@@ -713,6 +779,7 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
                     }
                 }
             }
+        }
         }
     }
     __syncthreads();
