@@ -174,6 +174,18 @@ __device__ __forceinline__ uint32_t normalize_px_fast(float x, float mn, float r
     return cast_f32_u8(__fmul_rn(__fdiv_rn(d, rng), 255.0f));
 }
 
+// Branch-free first try of normalize_px_fast for a GROUP of pixels: returns the truncated fast product and clears `ok` when
+// this pixel would have needed one of the exact paths (fast product within 1e-3 of an integer, NaN / inf).  d == 0 (a pixel
+// equal to the minimum -- the background of an MRI slice) needs no exact path: 0 * k is exactly 0.  The caller redoes the
+// whole group with normalize_px_fast when `ok` comes back false, so the result is the same function, with one branch per
+// group instead of three per pixel (control flow was a third of K3's normalise pass, ncu source view).
+__device__ __forceinline__ uint32_t normalize_px_try(float x, float mn, float k, bool& ok) {
+    const float d = __fsub_rn(x, mn);
+    const float y = __fmul_rn(d, k);
+    ok = ok && (fabsf(y - rintf(y)) > 1e-3f || d == 0.0f);
+    return static_cast<uint32_t>(__float2int_rz(y)) & 0xFFu;
+}
+
 // grid (ceil(out_h / R), nb).  CTA = R output rows of slice b, all out_w columns.
 // smem: [src u8: rows_in_max * w_max + 8][tmp u8: rows_in_max * out_w][hk int: out_w * ksw][hb int: out_w*2][vk int: R * ksh][vb int: R*2]
 __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict__ slices, const int64_t* __restrict__ offs,
@@ -237,9 +249,15 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
 #pragma unroll
                 for (int u = 0; u < 4; ++u) v[u] = __ldg(g4 + i + u * nthr);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    d4[i + u * nthr] = normalize_px_fast(v[u].x, mn, rng, k) | (normalize_px_fast(v[u].y, mn, rng, k) << 8) |
-                                       (normalize_px_fast(v[u].z, mn, rng, k) << 16) | (normalize_px_fast(v[u].w, mn, rng, k) << 24);
+                for (int u = 0; u < 4; ++u) {
+                    bool ok = true;
+                    uint32_t p = normalize_px_try(v[u].x, mn, k, ok) | (normalize_px_try(v[u].y, mn, k, ok) << 8) |
+                                 (normalize_px_try(v[u].z, mn, k, ok) << 16) | (normalize_px_try(v[u].w, mn, k, ok) << 24);
+                    if (!ok)
+                        p = normalize_px_fast(v[u].x, mn, rng, k) | (normalize_px_fast(v[u].y, mn, rng, k) << 8) |
+                            (normalize_px_fast(v[u].z, mn, rng, k) << 16) | (normalize_px_fast(v[u].w, mn, rng, k) << 24);
+                    d4[i + u * nthr] = p;
+                }
             }
             for (; i < n4; i += nthr) {
                 const float4 v = __ldg(g4 + i);
@@ -266,18 +284,18 @@ __global__ void __launch_bounds__(512) k1_resize_kernel(const float* __restrict_
         } else if (ksw <= 8) {
             for (int xx = tid; xx < out_w; xx += nthr) {
                 const int xmin = s_hb[2 * xx], n = s_hb[2 * xx + 1];
-                int kc[8], xo[8];
+                int kc[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    kc[j] = j < n ? s_hk[xx * ksw + j] : 0;
-                    xo[j] = min(xmin + j, W - 1);  // padded taps have a zero coefficient: any valid address will do
-                }
-                for (int row = 0; row < rows_in; ++row) {
-                    const uint8_t* sp = src + (size_t)row * W;
+                for (int j = 0; j < 8; ++j) kc[j] = j < n ? s_hk[xx * ksw + j] : 0;
+                // one pointer per row, the eight taps at immediate offsets.  A padded tap (zero coefficient) may read up to
+                // 7 bytes past the row: the next row, or -- after the last row -- the 16 slack bytes behind the staged span
+                const uint8_t* sp = src + xmin;
+                uint8_t* dp = s_tmp + xx;
+                for (int row = 0; row < rows_in; ++row, sp += W, dp += out_w) {
                     int acc = 1 << (PIL_PRECISION_BITS - 1);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc += (int)sp[xo[j]] * kc[j];
-                    s_tmp[(size_t)row * out_w + xx] = (uint8_t)pil_clip8(acc);
+                    for (int j = 0; j < 8; ++j) acc += (int)sp[j] * kc[j];
+                    *dp = (uint8_t)pil_clip8(acc);
                 }
             }
         } else {
@@ -756,6 +774,8 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
                     }
                 }
             };
+            // per-pixel fast / exact decision here: grouping 16 pixels behind one branch (as K1 does with 4) was measured
+            // SLOWER for crops (295.9 vs 277.5 us / 1280 crops) -- two warps in three hold at least one near-integer pixel
             if (rng > 0.0f) rows([&](float v) { return (uint8_t)normalize_px_fast(v, mnv, rng, kfast); });
             else rows([&](float v) { return (uint8_t)cast_f32_u8(v); });
         } else {
