@@ -10,6 +10,8 @@
 //   crop_region_horizontal      cropping.py:316-354
 //   resize_with_padding         cropping.py:104-146
 //   ClassificationDataset Resize  spine_vision/training/datasets/classification.py:247-278
+#include <type_traits>
+
 #include "svb_common.cuh"
 
 namespace svb {
@@ -913,19 +915,24 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     } else if (ksw2 <= KREG && nthr % ow2 == 0) {
         const int xx = tid % ow2, row0 = tid / ow2, rs = nthr / ow2;
         const int xmin = __ldg(hb2 + 2 * xx), cnt = __ldg(hb2 + 2 * xx + 1);
-        int kk[KREG], off[KREG];
+        // taps at immediate offsets from one pointer per row; a tap beyond cnt has weight 0 and may read up to 3 bytes past the
+        // canvas row (the next row, or the first bytes of s_tmp2 behind the canvas).  Up-sampling has 3 taps (ksize = 3).
+        auto hpass = [&](auto kt) {
+            constexpr int KT = decltype(kt)::value;
+            int kk[KT];
 #pragma unroll
-        for (int j = 0; j < KREG; ++j) {
-            kk[j] = j < cnt ? __ldg(hk2 + (size_t)xx * ksw2 + j) : 0;
-            off[j] = j < cnt ? xmin + j : xmin;  // unused taps re-read a valid pixel with weight 0
-        }
-        for (int row = row0; row < ch; row += rs) {
-            const uint8_t* sp = s_canvas + (size_t)row * cw;
-            int acc = 1 << (PIL_PRECISION_BITS - 1);
+            for (int j = 0; j < KT; ++j) kk[j] = j < cnt ? __ldg(hk2 + (size_t)xx * ksw2 + j) : 0;
+            const uint8_t* sp = s_canvas + (size_t)row0 * cw + xmin;
+            uint8_t* dp = s_tmp2 + (size_t)row0 * ow2 + xx;
+            for (int row = row0; row < ch; row += rs, sp += rs * cw, dp += rs * ow2) {
+                int acc = 1 << (PIL_PRECISION_BITS - 1);
 #pragma unroll
-            for (int j = 0; j < KREG; ++j) acc += (int)sp[off[j]] * kk[j];
-            s_tmp2[(size_t)row * ow2 + xx] = (uint8_t)pil_clip8(acc);
-        }
+                for (int j = 0; j < KT; ++j) acc += (int)sp[j] * kk[j];
+                *dp = (uint8_t)pil_clip8(acc);
+            }
+        };
+        if (ksw2 <= 3) hpass(std::integral_constant<int, 3>{});
+        else hpass(std::integral_constant<int, KREG>{});
     } else {
         for (int i = tid; i < ch * ow2; i += nthr) {
             const int row = i / ow2, xx = i - row * ow2;
@@ -942,22 +949,27 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         const int w4 = ow2 >> 2;
         if (oh2 != ch && ksh2 <= KREG && nthr % w4 == 0) {
             const int x4 = (tid % w4) << 2, r0 = tid / w4, rs = nthr / w4;
-            for (int r = r0; r < oh2; r += rs) {
-                const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);  // warp-uniform when w4 >= 32
-                int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
+            auto vpass = [&](auto kt) {
+                constexpr int KT = decltype(kt)::value;
+                for (int r = r0; r < oh2; r += rs) {
+                    const int ymin = __ldg(vb2 + 2 * r), cnt = __ldg(vb2 + 2 * r + 1);  // warp-uniform when w4 >= 32
+                    int a0 = 1 << (PIL_PRECISION_BITS - 1), a1 = a0, a2 = a0, a3 = a0;
 #pragma unroll
-                for (int j = 0; j < KREG; ++j) {
-                    const int k = j < cnt ? __ldg(vk2 + (size_t)r * ksh2 + j) : 0;
-                    const int yy = j < cnt ? ymin + j : ymin;
-                    const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)yy * ow2 + x4);
-                    a0 += (int)(px & 0xFF) * k;
-                    a1 += (int)((px >> 8) & 0xFF) * k;
-                    a2 += (int)((px >> 16) & 0xFF) * k;
-                    a3 += (int)(px >> 24) * k;
+                    for (int j = 0; j < KT; ++j) {
+                        const int k = j < cnt ? __ldg(vk2 + (size_t)r * ksh2 + j) : 0;
+                        const int yy = j < cnt ? ymin + j : ymin;
+                        const uint32_t px = *reinterpret_cast<const uint32_t*>(s_tmp2 + (size_t)yy * ow2 + x4);
+                        a0 += (int)(px & 0xFF) * k;
+                        a1 += (int)((px >> 8) & 0xFF) * k;
+                        a2 += (int)((px >> 16) & 0xFF) * k;
+                        a3 += (int)(px >> 24) * k;
+                    }
+                    *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) =
+                        pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
                 }
-                *reinterpret_cast<uint32_t*>(out2 + (size_t)r * ow2 + x4) =
-                    pil_clip8(a0) | (pil_clip8(a1) << 8) | (pil_clip8(a2) << 16) | (pil_clip8(a3) << 24);
-            }
+            };
+            if (ksh2 <= 3) vpass(std::integral_constant<int, 3>{});
+            else vpass(std::integral_constant<int, KREG>{});
         } else {
             for (int i = tid; i < oh2 * w4; i += nthr) {
                 const int r = i / w4, x4 = (i - r * w4) << 2;
