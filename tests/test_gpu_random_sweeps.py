@@ -166,3 +166,48 @@ def test_localizer_unusual_image_sizes_vs_fp32_oracle(image_size):
     err = float(np.abs(got - np.stack(want)).max())
     print(f"[coords] image_size={image_size}: max normalised error {err:.2e}")
     assert np.isfinite(got).all() and err <= 0.5 / 512
+
+
+def _k0_random_cases(seed, n):
+    """Volumes in every axis-aligned orientation (signed permutations), a few oblique ones, random sizes down to a single slice,
+    random anisotropic spacings, float and integer pixel types."""
+    import itertools
+
+    rng = np.random.default_rng(seed)
+    perms = list(itertools.permutations(range(3)))
+    cases = []
+    for k in range(n):
+        shape = (int(rng.integers(1, 12)), int(rng.integers(2, 60)), int(rng.integers(2, 60)))  # z, y, x
+        sp = (float(rng.uniform(0.25, 2.5)), float(rng.uniform(0.25, 2.5)), float(rng.uniform(0.3, 5.0)))
+        if k % 4 == 3:  # oblique: a random rotation close to a signed permutation
+            q, _ = np.linalg.qr(np.eye(3)[list(perms[int(rng.integers(0, 6))])] * rng.choice([-1.0, 1.0], size=3) + rng.normal(0, 0.08, (3, 3)))
+            d = tuple(float(v) for v in q.ravel())
+        else:
+            m = np.eye(3)[list(perms[(k // 8) % 6])] * np.array([1.0 if (k >> b) & 1 else -1.0 for b in range(3)])
+            d = tuple(float(v) for v in m.T.ravel())
+        kind = k % 3
+        if kind == 0:
+            v = (rng.random(shape) * 1500).astype(np.float32)
+        elif kind == 1:
+            v = rng.integers(-500, 3000, size=shape).astype(np.int16)
+        else:
+            v = rng.integers(0, 256, size=shape).astype(np.uint8)
+        cases.append((v, sp, d))
+    return cases
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_k0_random_orientations_sizes_types_vs_itk_restatement(seed):
+    """K0 against oracle/itk_resample.py (parity unpinned: SimpleITK absent) on 48 random volumes per seed."""
+    from oracle import itk_resample as itk
+    from spine_vision_b200 import volumes
+
+    cases = _k0_random_cases(4000 + seed, 48)
+    want = [itk.resample_middle_sagittal(v, sp, d) for v, sp, d in cases]
+    pool, spacings = volumes.midplane_resample([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases], dev())
+    flat, offs = pool.data.cpu().numpy(), pool.offs.cpu().numpy()
+    for i, (w, wsp) in enumerate(want):
+        h_, w_ = pool.shapes[i]
+        assert (h_, w_) == w.shape and spacings[i] == wsp, (i, (h_, w_), w.shape, spacings[i], wsp)
+        got = flat[offs[i] : offs[i] + h_ * w_].reshape(h_, w_)
+        assert np.array_equal(got, w.astype(np.float32)), f"case {i} {cases[i][0].shape} {cases[i][0].dtype} dir {cases[i][2]}: max diff {np.abs(got - w).max()}"
