@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--micro-batch", type=int, default=64, help="images per pass through the network (two passes are in flight)")
     ap.add_argument("--stream-chunk", type=int, default=0, help="series per H2D chunk of the end-to-end path (0 = two micro-batches: both chains of the forward busy)")
     ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic slices (tiled to the batch)")
-    ap.add_argument("--ref-series", type=int, default=4, help="series per step of the CPU reference arm")
+    ap.add_argument("--ref-series", type=int, default=16, help="series per step of the CPU reference arm (--impl reference)")
+    ap.add_argument("--cpu-baseline-series", type=int, default=32,
+                    help="series per pass of the cpu_baseline leg (N=1, rank 0): BASELINE configs[0]'s batch of 32, one warm-up + two timed passes = about 12 s of CPU work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -336,9 +338,9 @@ def run_b200(args):
             },
         }
         if world == 1 and not args.no_cpu_baseline:
-            rate, mean, cores = cpu_reference_rate(args.ref_series, 2, 1)
+            rate, mean, cores = cpu_reference_rate(args.cpu_baseline_series, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",
-                                    "sample": f"{args.ref_series} series of the same workload through oracle/reference_path.py (batch-1 loop), 2 timed passes after 1 warm-up"}
+                                    "sample": f"{args.cpu_baseline_series} series per pass of the same workload (BASELINE configs[0]: batch 32) through oracle/reference_path.py (batch-1 loop, reference-faithful), 2 timed passes after 1 warm-up"}
         print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
