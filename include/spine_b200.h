@@ -313,6 +313,13 @@ int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, s
 int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
                            const size_t* dst_elems, int n_threads, int32_t* rcs);
 
+/* Slices [z0[i], z1[i]) of volume i only, written at their place in the buffer of the WHOLE volume (h_dsts[i], dst_elems[i] as
+ * above; the rest of the buffer is not touched).  The dataset driver needs the two source slices around the middle sagittal
+ * plane (cropping.py:63-79 keeps one plane of the resampled volume): a zlib stream is inflated up to the slab and no further,
+ * only the slab is converted to float32. */
+int svb_mha_read_batch_slab_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
+                                const size_t* dst_elems, const int32_t* z0, const int32_t* z1, int n_threads, int32_t* rcs);
+
 /* DICOM series (one slice per file) -- replaces read_medical_image -> read_dicom_series -> sitk.ImageSeriesReader over
  * GDCM for the Phenikaa series directories (spine_vision/io/readers.py:48-73, 128-161; phenikaa.py:178).  Part-10 files,
  * implicit / explicit VR little endian or explicit big endian, NATIVE pixel data (compressed transfer syntaxes give

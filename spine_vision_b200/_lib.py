@@ -28,7 +28,7 @@ EXPORTS = (
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
     "svb_k4_classifier_input",
     "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch", "svb_png_write_gray8_ragged",
-    "svb_mha_read_header", "svb_mha_read_f32", "svb_mha_read_batch_f32",
+    "svb_mha_read_header", "svb_mha_read_f32", "svb_mha_read_batch_f32", "svb_mha_read_batch_slab_f32",
     "svb_dicom_read_headers", "svb_dicom_read_slices_f32",
 )
 
@@ -138,6 +138,9 @@ def load() -> C.CDLL:
     lib.svb_mha_read_f32.argtypes = [C.c_char_p, C.POINTER(MhaInfo), vp, sz]
     lib.svb_mha_read_batch_f32.restype = C.c_int
     lib.svb_mha_read_batch_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(MhaInfo), C.POINTER(vp), C.POINTER(sz), i32, vp]
+    lib.svb_mha_read_batch_slab_f32.restype = C.c_int
+    lib.svb_mha_read_batch_slab_f32.argtypes = [C.POINTER(C.c_char_p), i32, C.POINTER(MhaInfo), C.POINTER(vp), C.POINTER(sz),
+                                                C.POINTER(C.c_int32), C.POINTER(C.c_int32), i32, vp]
     lib.svb_normalize_u8_workspace_bytes.restype = sz
     lib.svb_normalize_u8_workspace_bytes.argtypes = [i32]
     lib.svb_normalize_u8.restype = C.c_int

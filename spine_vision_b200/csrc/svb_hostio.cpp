@@ -274,17 +274,72 @@ void convert(const uint8_t* src, size_t n, bool swap, float* dst) {
     }
 }
 
-int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_elems) {
+// Inflate `want` bytes of a zlib stream starting `skip` bytes into the inflated data (a slab of z slices): the bytes in front are
+// inflated into a scratch block and dropped, the stream is not read past the slab.
+int inflate_range(const uint8_t* z, size_t zbytes, size_t skip, uint8_t* out, size_t want) {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit(&zs) != Z_OK) return Z_MEM_ERROR;
+    zs.next_in = const_cast<Bytef*>(z);
+    zs.avail_in = (uInt)zbytes;
+    std::vector<uint8_t> scratch(skip ? (size_t)1 << 16 : 0);
+    int zr = Z_OK;
+    while (skip > 0 && zr == Z_OK) {
+        const size_t chunk = skip < scratch.size() ? skip : scratch.size();
+        zs.next_out = scratch.data();
+        zs.avail_out = (uInt)chunk;
+        zr = inflate(&zs, Z_NO_FLUSH);
+        skip -= chunk - zs.avail_out;
+        if (zr == Z_OK && zs.avail_out == chunk && zs.avail_in == 0) zr = Z_BUF_ERROR;  // no progress: truncated stream
+    }
+    if (skip == 0 && (zr == Z_OK || (zr == Z_STREAM_END && want == 0))) {
+        zs.next_out = out;
+        zs.avail_out = (uInt)want;
+        while (zs.avail_out > 0 && zr == Z_OK) {
+            const uInt before = zs.avail_out;
+            zr = inflate(&zs, Z_NO_FLUSH);
+            if (zr == Z_OK && zs.avail_out == before && zs.avail_in == 0) zr = Z_BUF_ERROR;
+        }
+        if (zs.avail_out == 0 && (zr == Z_OK || zr == Z_STREAM_END)) zr = Z_OK;
+        else if (zr == Z_OK || zr == Z_STREAM_END) zr = Z_BUF_ERROR;  // the stream ended inside the slab
+    } else if (zr == Z_OK || zr == Z_STREAM_END) {
+        zr = Z_BUF_ERROR;  // the stream ended in front of the slab
+    }
+    inflateEnd(&zs);
+    return zr;
+}
+
+// Slices [z0, z1) of the volume into dst + z0 * (slice elements); dst is the buffer of the WHOLE volume (what lies outside the
+// slab is not touched).  z0 = 0, z1 = dim[2] is the whole volume.
+int mha_read_slab(const char* path, const svb_mha_info* info, float* dst, size_t dst_elems, int z0, int z1) {
     if (!path || !info || !dst) return set_error(SVB_ERR_INVALID_ARG, "mha: null argument");
-    const size_t n = (size_t)info->dim[0] * info->dim[1] * info->dim[2];
-    if (dst_elems < n) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "mha: destination holds %zu elements, volume has %zu", dst_elems, n);
+    const size_t n_all = (size_t)info->dim[0] * info->dim[1] * info->dim[2];
+    if (dst_elems < n_all) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "mha: destination holds %zu elements, volume has %zu", dst_elems, n_all);
+    if (z0 < 0 || z1 > info->dim[2] || z0 >= z1) return set_error(SVB_ERR_INVALID_ARG, "mha: slab [%d, %d) outside the %d slices", z0, z1, info->dim[2]);
+    const bool whole = z0 == 0 && z1 == info->dim[2];
+    const size_t slice_elems = (size_t)info->dim[0] * info->dim[1];
+    const size_t n = slice_elems * (size_t)(z1 - z0);
+    const size_t skip_bytes = slice_elems * (size_t)z0 * (size_t)info->element_bytes;
+    const size_t all_bytes = n_all * (size_t)info->element_bytes;
+    dst += slice_elems * (size_t)z0;
     const size_t raw_bytes = n * (size_t)info->element_bytes;
     const char* data_path = info->data_offset >= 0 ? path : info->data_file;
     FILE* f = fopen(data_path, "rb");
     if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", data_path, strerror(errno));
     std::vector<uint8_t> raw(raw_bytes);
     int rc = SVB_OK;
-    if (info->compressed) {
+    if (info->compressed && !whole) {
+        int64_t start = info->data_offset >= 0 ? info->data_offset : (info->header_size > 0 ? info->header_size : 0);
+        fseek(f, 0, SEEK_END);
+        const int64_t end = (int64_t)ftell(f);
+        int64_t zbytes = info->compressed_size > 0 ? info->compressed_size : end - start;
+        if (zbytes <= 0 || start + zbytes > end) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: compressed data truncated", data_path); }
+        std::vector<uint8_t> z((size_t)zbytes);
+        fseek(f, (long)start, SEEK_SET);
+        if (fread(z.data(), 1, (size_t)zbytes, f) != (size_t)zbytes) { fclose(f); return set_error(SVB_ERR_IO, "%s: short read", data_path); }
+        const int zr = inflate_range(z.data(), (size_t)zbytes, skip_bytes, raw.data(), raw_bytes);
+        if (zr != Z_OK) rc = set_error(SVB_ERR_FORMAT, "%s: zlib inflate of slices [%d, %d) failed (%d)", data_path, z0, z1, zr);
+    } else if (info->compressed) {
         // the compressed stream runs to CompressedDataSize, or to the end of the file when the field is absent
         int64_t start = info->data_offset >= 0 ? info->data_offset : (info->header_size > 0 ? info->header_size : 0);
         fseek(f, 0, SEEK_END);
@@ -302,8 +357,9 @@ int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_
         if (info->data_offset >= 0) start = info->data_offset;
         else if (info->header_size == -1) {  // MetaIO: data sits at the end of the file
             fseek(f, 0, SEEK_END);
-            start = (int64_t)ftell(f) - (int64_t)raw_bytes;
+            start = (int64_t)ftell(f) - (int64_t)all_bytes;
         } else start = info->header_size;
+        if (start >= 0) start += (int64_t)skip_bytes;
         if (start < 0 || fseek(f, (long)start, SEEK_SET) != 0 || fread(raw.data(), 1, raw_bytes, f) != raw_bytes)
             rc = set_error(SVB_ERR_FORMAT, "%s: raw data truncated (%zu bytes expected)", data_path, raw_bytes);
     }
@@ -326,6 +382,11 @@ int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_
         default: return set_error(SVB_ERR_FORMAT, "%s: unknown element type %d", path, info->element_type);
     }
     return SVB_OK;
+}
+
+int mha_read(const char* path, const svb_mha_info* info, float* dst, size_t dst_elems) {
+    if (!info) return set_error(SVB_ERR_INVALID_ARG, "mha: null argument");
+    return mha_read_slab(path, info, dst, dst_elems, 0, info->dim[2]);
 }
 
 
@@ -634,6 +695,19 @@ int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* 
     });
     // per-file failures are the caller's to skip (the reference's drivers skip unreadable series: spider.py:139-141)
     return n_bad.load() ? set_error(SVB_ERR_IO, "mha batch: %d of %d volumes failed (see the per-file codes)", n_bad.load(), n) : SVB_OK;
+}
+
+int svb_mha_read_batch_slab_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
+                                const size_t* dst_elems, const int32_t* z0, const int32_t* z1, int n_threads, int32_t* rcs) {
+    if (n < 0 || (n > 0 && (!paths || !infos || !h_dsts || !dst_elems || !z0 || !z1)))
+        return set_error(SVB_ERR_INVALID_ARG, "mha slab batch: bad arguments (n=%d)", n);
+    std::atomic<int> n_bad{0};
+    parallel_for(n, n_threads, [&](int i) {
+        const int rc = mha_read_slab(paths[i], &infos[i], h_dsts[i], dst_elems[i], z0[i], z1[i]);
+        if (rcs) rcs[i] = rc;
+        if (rc != SVB_OK) n_bad.fetch_add(1);
+    });
+    return n_bad.load() ? set_error(SVB_ERR_IO, "mha slab batch: %d of %d volumes failed (see the per-file codes)", n_bad.load(), n) : SVB_OK;
 }
 
 int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* infos, int n_threads, int32_t* rcs) {

@@ -288,7 +288,7 @@ def _read_chunk(jobs: list[SeriesJob], n_threads: int):
     else through ``hostio.read_medical_image`` (which raises for formats without a decoder -> the series is skipped)."""
     vols: list[hostio.MedicalVolume | None] = [None] * len(jobs)
     mha = [i for i, j in enumerate(jobs) if hostio.detect_format(j.path) in ("MHA", "MHD")]
-    got, errs = hostio.read_volumes([jobs[i].path for i in mha], n_threads)
+    got, errs = hostio.read_volumes([jobs[i].path for i in mha], n_threads, midplane_only=True)  # the driver reads two slices per volume
     for k, i in enumerate(mha):
         vols[i] = got[k]
         if got[k] is None:

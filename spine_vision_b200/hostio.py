@@ -210,9 +210,13 @@ def read_medical_image(path: Path) -> MedicalVolume:
     raise UnsupportedFormatError(f"{fmt} decoding needs SimpleITK, which this build does not link; path: {path}")
 
 
-def read_volumes(paths, n_threads: int = 0, pin: bool = False):
+def read_volumes(paths, n_threads: int = 0, pin: bool = False, midplane_only: bool = False):
     """Decode many MetaImage volumes on a thread pool into one float32 buffer (``pin`` is accepted and ignored: whole volumes
     never travel to the device).
+    ``midplane_only`` (the dataset driver): when the left-right axis of a volume is its slowest array axis -- a sagittal
+    acquisition, what SPIDER ships -- only the two source slices ``volumes.plan_midplane`` reads are decoded (the zlib stream is
+    inflated up to them and no further); the REST OF THAT ARRAY IS UNINITIALISED, ``meta["decoded_z"]`` says which slices are
+    real.  Volumes in any other orientation are decoded whole.
     Returns ``(volumes, errors)``: ``volumes[i]`` is a ``MedicalVolume`` whose array is a view into the shared buffer, or
     ``None`` when file i could not be read (``errors[i]`` holds the reason) -- the drivers skip those series
     (spider.py:139-141)."""
@@ -247,12 +251,29 @@ def read_volumes(paths, n_threads: int = 0, pin: bool = False):
         c_dsts = (C.c_void_p * m)(*[host.data_ptr() + 4 * o for o in offs])
         c_sizes = (C.c_size_t * m)(*sizes)
         rcs = (C.c_int32 * m)()
-        lib.svb_mha_read_batch_f32(c_paths, m, c_infos, c_dsts, c_sizes, int(n_threads), C.addressof(rcs))
+        z_lo = [0] * m
+        z_hi = [int(infos[i].dim[2]) for i in ok]
+        if midplane_only:
+            from . import volumes as _vol
+
+            for j, i in enumerate(ok):
+                try:
+                    axis, lo, hi = _vol.midplane_source_planes(tuple(infos[i].dim), tuple(infos[i].spacing), tuple(infos[i].direction))[:3]
+                except ValueError:  # direction cosines that do not resolve: the driver reports it, decode whole
+                    continue
+                if axis == 0 and infos[i].ndim == 3:
+                    z_lo[j], z_hi[j] = int(lo), int(hi) + 1
+        if any(z_lo[j] != 0 or z_hi[j] != infos[i].dim[2] for j, i in enumerate(ok)):
+            lib.svb_mha_read_batch_slab_f32(c_paths, m, c_infos, c_dsts, c_sizes, (C.c_int32 * m)(*z_lo), (C.c_int32 * m)(*z_hi),
+                                            int(n_threads), C.addressof(rcs))
+        else:
+            lib.svb_mha_read_batch_f32(c_paths, m, c_infos, c_dsts, c_sizes, int(n_threads), C.addressof(rcs))
         for j, i in enumerate(ok):
             if rcs[j] != 0:
                 errors[i] = f"libspine_b200 error {rcs[j]} while decoding {paths[i]}"
             else:
                 volumes[i] = _volume_from(infos[i], hv[offs[j] : offs[j] + sizes[j]])
+                volumes[i].meta["decoded_z"] = (z_lo[j], z_hi[j])
     return volumes, errors
 
 

@@ -58,6 +58,25 @@ class MidplanePlan:
     desc: dict
 
 
+def midplane_source_planes(size_xyz, spacing_xyz, direction=None, new_spacing=ISOTROPIC_SPACING):
+    """Which source planes the middle sagittal plane of the resampled, LPI-oriented volume is interpolated from
+    (cropping.py:45-48, 63-79): ``(array axis of [z, y, x], lo, hi, inside, continuous index, resampled sizes, axis_of, flip)``.
+    Depends on the header only (size, spacing, direction), so a reader can decode just those planes."""
+    size = tuple(int(v) for v in size_xyz)
+    ns = [int(round(osz * osp / nsp)) for osz, osp, nsp in zip(size, spacing_xyz, new_spacing)]  # cropping.py:45-48
+    axis_of, flip = lpi_axes(direction)
+    a_fix = axis_of[0]
+    # middle index along Left-Right in the oriented, resampled volume (cropping.py:78-79), back in image-axis order
+    mid = ns[a_fix] // 2
+    idx = ns[a_fix] - 1 - mid if flip[0] else mid
+    u = (idx * float(new_spacing[a_fix])) / float(spacing_xyz[a_fix])
+    inside = -0.5 <= u < size[a_fix] - 0.5
+    base = math.floor(u)
+    lo = min(max(base, 0), size[a_fix] - 1)
+    hi = min(max(base + 1, 0), size[a_fix] - 1)
+    return 2 - a_fix, lo, hi, inside, u, ns, axis_of, flip
+
+
 def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spacing=ISOTROPIC_SPACING,
                   integer_pixels: bool | None = None) -> MidplanePlan:
     """``integer_pixels``: the image's pixel type is integral, so ITK casts every resampled value back to it (truncation);
@@ -68,18 +87,9 @@ def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spaci
     if v.ndim != 3:
         raise ValueError("plan_midplane takes a 3-D volume in sitk.GetArrayFromImage order [z, y, x]")
     size = (v.shape[2], v.shape[1], v.shape[0])
-    ns = [int(round(osz * osp / nsp)) for osz, osp, nsp in zip(size, spacing_xyz, new_spacing)]  # cropping.py:45-48
-    axis_of, flip = lpi_axes(direction)
+    arr_axis, lo, hi, inside, u, ns, axis_of, flip = midplane_source_planes(size, spacing_xyz, direction, new_spacing)
     a_fix, a_col, a_row = axis_of[0], axis_of[1], axis_of[2]
-    # middle index along Left-Right in the oriented, resampled volume (cropping.py:78-79), back in image-axis order
-    mid = ns[a_fix] // 2
-    idx = ns[a_fix] - 1 - mid if flip[0] else mid
-    u = (idx * float(new_spacing[a_fix])) / float(spacing_xyz[a_fix])
-    inside = -0.5 <= u < size[a_fix] - 0.5
     base = math.floor(u)
-    lo = min(max(base, 0), size[a_fix] - 1)
-    hi = min(max(base + 1, 0), size[a_fix] - 1)
-    arr_axis = 2 - a_fix
     slab = np.ascontiguousarray(np.take(v, [lo, hi] if hi != lo else [lo], axis=arr_axis).astype(np.float32, copy=False))
     dims = [size[0], size[1], size[2]]
     dims[a_fix] = slab.shape[arr_axis]

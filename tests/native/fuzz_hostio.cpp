@@ -66,6 +66,18 @@ static int decode_mha(const std::string& path) {
     if (!(n > 0) || n > (double)MAX_ELEMS) return -100;
     std::vector<float> dst((size_t)n);
     rc = svb_mha_read_f32(path.c_str(), &info, dst.data(), dst.size());
+    {  // the slab entry (the dataset driver's partial decode): random slice ranges, valid and invalid
+        const char* paths[1] = {path.c_str()};
+        float* dsts[1] = {dst.data()};
+        size_t sizes[1] = {dst.size()};
+        for (int t = 0; t < 3; ++t) {
+            int32_t z0[1] = {(int32_t)(rnd() % (uint32_t)(info.dim[2] + 2)) - 1};
+            int32_t z1[1] = {z0[0] + (int32_t)(rnd() % 3)};
+            int32_t rcs[1] = {0};
+            svb_mha_read_batch_slab_f32(paths, 1, &info, dsts, sizes, z0, z1, 1, rcs);
+            if (rcs[0] == 0 && (z0[0] < 0 || z1[0] > info.dim[2] || z0[0] >= z1[0])) { fprintf(stderr, "bad slab accepted\n"); exit(3); }
+        }
+    }
     if (rc == 0 && dst.size() > 1) {  // a shorter destination must be refused, not overrun
         std::vector<float> small(dst.size() - 1);
         if (svb_mha_read_f32(path.c_str(), &info, small.data(), small.size()) == 0) { fprintf(stderr, "short buffer accepted\n"); exit(3); }

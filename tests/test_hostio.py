@@ -382,3 +382,44 @@ def test_native_decoders_under_address_sanitizer(tmp_path):
     run = subprocess.run([str(exe), str(work), "1500", *files], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "no sanitizer report" in run.stdout
+
+
+@pytest.mark.parametrize("dtype", ["int16", "uint8", "float32", "float64"])
+@pytest.mark.parametrize("layout", ["local_zlib", "local_raw", "mhd_zraw", "big_endian_raw"])
+def test_midplane_only_decode_equals_whole_decode_where_it_matters(tmp_path, dtype, layout):
+    """``read_volumes(midplane_only=True)`` (the dataset driver's reader): for a sagittal acquisition only the two source slices
+    around the middle plane are decoded -- ``volumes.plan_midplane`` must cut the same slab out of it as out of the whole
+    volume; a volume in another orientation is decoded whole.  Even and odd slice counts, 1 and 2 slices."""
+    from spine_vision_b200 import volumes
+
+    rng = np.random.default_rng(zlib.crc32(f"{dtype}-{layout}".encode()))
+    kw = dict(compressed=layout in ("local_zlib", "mhd_zraw"), separate_raw=layout == "mhd_zraw", big_endian=layout == "big_endian_raw")
+    sag = (0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0)  # image z = Left: the slowest array axis holds the sagittal slices
+    paths, dirs = [], []
+    for k, nz in enumerate((15, 14, 2, 1, 9)):
+        arr = (rng.random((nz, 23, 31)) * 200).astype(dtype)
+        d = sag if k != 4 else None  # the last one is axial (identity direction): Left = the fastest array axis
+        p = tmp_path / (f"v{k}.mhd" if layout == "mhd_zraw" else f"v{k}.mha")
+        synthetic.write_metaimage(p, arr, (0.7, 0.7, 4.0), direction=d, **kw)
+        paths.append(p); dirs.append(d)
+    whole, e0 = hostio.read_volumes(paths)
+    part, e1 = hostio.read_volumes(paths, midplane_only=True)
+    assert e0 == e1 == [None] * 5
+    for k, (a, b) in enumerate(zip(whole, part)):
+        z0, z1 = b.meta["decoded_z"]
+        nz = a.array.shape[0]
+        if k == 4:
+            assert (z0, z1) == (0, nz) and np.array_equal(a.array, b.array)
+            continue
+        assert z1 - z0 == min(2, nz) and a.meta["decoded_z"] == (0, nz)
+        assert np.array_equal(a.array[z0:z1], b.array[z0:z1])
+        pa = volumes.plan_midplane(a.array, a.spacing, a.direction, integer_pixels=a.integer_pixels)
+        pb = volumes.plan_midplane(b.array, b.spacing, b.direction, integer_pixels=b.integer_pixels)
+        assert pa.desc == pb.desc and pa.out_hw == pb.out_hw and np.array_equal(pa.slab, pb.slab)
+    # a truncated compressed stream that still covers the slab decodes; one that ends in front of it is an error
+    if layout == "local_zlib":
+        blob = paths[0].read_bytes()
+        cut = tmp_path / "cut.mha"
+        cut.write_bytes(blob[: len(blob) // 4])
+        vols, errs = hostio.read_volumes([cut], midplane_only=True)
+        assert vols == [None] and errs[0]
