@@ -297,7 +297,7 @@ def _read_chunk(jobs: list[SeriesJob], n_threads: int):
         if i in mha:
             continue
         try:
-            vols[i] = hostio.read_medical_image(j.path)
+            vols[i] = hostio.read_medical_image(j.path, midplane_only=True)
         except Exception as e:  # noqa: BLE001 -- spider.py:139-141 / phenikaa.py:181-183: any reader error skips the series
             logger.debug("Error reading %s: %s", j.path, e)
     return vols

@@ -93,7 +93,7 @@ def _volume_from(info: _lib.MhaInfo, arr: np.ndarray) -> MedicalVolume:
                          meta={"element_type": int(info.element_type), "compressed": bool(info.compressed), "ndim": int(info.ndim)})
 
 
-def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) -> MedicalVolume:
+def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False, midplane_only: bool = False) -> MedicalVolume:
     """``read_dicom_series`` (io/readers.py:48-73).  ITK conventions restated here (host arithmetic on a few numbers per slice):
 
     * the directory's regular files are scanned, non-DICOM files are ignored; ``ValueError`` when none is left (:66-67);
@@ -103,6 +103,10 @@ def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) 
     * ``GetOrigin`` = position of the first slice; ``GetSpacing`` = (column spacing, row spacing, |last - first| / (n - 1));
       ``GetDirection`` columns = row cosines, column cosines, (last - first) normalised (the normal when n == 1);
     * stored values with RescaleSlope / Intercept applied; the pixel type counts as integral when both are whole numbers.
+
+    ``midplane_only`` (the dataset driver): every header is still read (series selection and slice order need them), but when
+    the stack direction is the left-right axis only the two slices ``volumes.plan_midplane`` reads are decoded; the rest of the
+    array is UNINITIALISED and ``meta["decoded_z"]`` says which slices are real.
     """
     lib = _lib.load()
     folder_path = Path(folder_path)
@@ -128,14 +132,6 @@ def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) 
         if (infos[i].rows, infos[i].cols) != (rows, cols):
             raise ValueError(f"DICOM series in {folder_path} has slices of different sizes")
     m = len(sel)
-    host = torch.empty(m * rows * cols, dtype=torch.float32)
-    if pin and torch.cuda.is_available():
-        host = host.pin_memory()
-    c_sel = (C.c_char_p * m)(*[os.fsencode(str(files[i])) for i in sel])
-    c_infos = (_lib.DicomInfo * m)(*[infos[i] for i in sel])
-    c_dsts = (C.c_void_p * m)(*[host.data_ptr() + 4 * k * rows * cols for k in range(m)])
-    c_sizes = (C.c_size_t * m)(*([rows * cols] * m))
-    _lib.check(lib.svb_dicom_read_slices_f32(c_sel, m, c_infos, c_dsts, c_sizes, int(n_threads), None))
     p0 = np.array(infos[sel[0]].position[:], dtype=np.float64)
     p1 = np.array(infos[sel[-1]].position[:], dtype=np.float64)
     if m > 1 and float(np.linalg.norm(p1 - p0)) > 0.0:
@@ -145,10 +141,31 @@ def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False) 
         dz = float(first.spacing_between_slices or first.slice_thickness or 1.0)
         third = normal
     direction = np.stack([row, col, third], axis=1)  # columns = axes
+    spacing = (float(first.pixel_spacing[1]), float(first.pixel_spacing[0]), dz)
+    k_lo, k_hi = 0, m
+    if midplane_only:
+        from . import volumes as _vol
+
+        try:
+            axis, lo, hi = _vol.midplane_source_planes((cols, rows, m), spacing, tuple(float(v) for v in direction.ravel()))[:3]
+            if axis == 0:
+                k_lo, k_hi = int(lo), int(hi) + 1
+        except ValueError:  # direction cosines that do not resolve: the driver reports it, decode everything
+            pass
+    host = torch.empty(m * rows * cols, dtype=torch.float32)
+    if pin and torch.cuda.is_available():
+        host = host.pin_memory()
+    part = sel[k_lo:k_hi]
+    mp = len(part)
+    c_sel = (C.c_char_p * mp)(*[os.fsencode(str(files[i])) for i in part])
+    c_infos = (_lib.DicomInfo * mp)(*[infos[i] for i in part])
+    c_dsts = (C.c_void_p * mp)(*[host.data_ptr() + 4 * k * rows * cols for k in range(k_lo, k_hi)])
+    c_sizes = (C.c_size_t * mp)(*([rows * cols] * mp))
+    _lib.check(lib.svb_dicom_read_slices_f32(c_sel, mp, c_infos, c_dsts, c_sizes, int(n_threads), None))
     integral = all(float(infos[i].rescale_slope).is_integer() and float(infos[i].rescale_intercept).is_integer() for i in sel)
-    return MedicalVolume(array=host.numpy().reshape(m, rows, cols), spacing=(float(first.pixel_spacing[1]), float(first.pixel_spacing[0]), dz),
+    return MedicalVolume(array=host.numpy().reshape(m, rows, cols), spacing=spacing,
                          direction=tuple(float(v) for v in direction.ravel()), origin=tuple(float(v) for v in p0), integer_pixels=integral,
-                         meta={"series_uid": uid.decode("ascii", "replace"), "files": [files[i].name for i in sel]})
+                         meta={"series_uid": uid.decode("ascii", "replace"), "files": [files[i].name for i in sel], "decoded_z": (k_lo, k_hi)})
 
 
 def read_dicom_files(paths, n_threads: int = 0):
@@ -190,9 +207,10 @@ def read_dicom_files(paths, n_threads: int = 0):
     return arrays, errors
 
 
-def read_medical_image(path: Path) -> MedicalVolume:
+def read_medical_image(path: Path, midplane_only: bool = False) -> MedicalVolume:
     """``read_medical_image`` (io/readers.py:128-161): same error behaviour (``FileNotFoundError`` for a missing path,
-    ``ValueError`` for an unknown format)."""
+    ``ValueError`` for an unknown format).  ``midplane_only`` is the dataset driver's switch for DICOM series (see
+    ``read_dicom_series``); the default decodes everything, like the reference."""
     path = Path(path)
     if not path.exists():
         raise FileNotFoundError(f"Path does not exist: {path}")
@@ -204,7 +222,7 @@ def read_medical_image(path: Path) -> MedicalVolume:
         _lib.check(_lib.load().svb_mha_read_f32(os.fsencode(str(path)), C.byref(info), arr.ctypes.data, n))
         return _volume_from(info, arr)
     if fmt == "DICOM":
-        return read_dicom_series(path)
+        return read_dicom_series(path, midplane_only=midplane_only)
     if fmt == "UNKNOWN":
         raise ValueError(f"Unsupported format for path: {path}")
     raise UnsupportedFormatError(f"{fmt} decoding needs SimpleITK, which this build does not link; path: {path}")

@@ -423,3 +423,28 @@ def test_midplane_only_decode_equals_whole_decode_where_it_matters(tmp_path, dty
         cut.write_bytes(blob[: len(blob) // 4])
         vols, errs = hostio.read_volumes([cut], midplane_only=True)
         assert vols == [None] and errs[0]
+
+
+@pytest.mark.parametrize("n_slices", [15, 14, 2, 1])
+def test_dicom_series_midplane_only_feeds_k0_the_same_slab(tmp_path, n_slices):
+    """``read_medical_image(folder, midplane_only=True)`` (what the dataset driver calls for the Phenikaa series): headers of
+    every file are read, pixel data only of the two slices around the middle sagittal plane -- ``volumes.plan_midplane`` cuts the
+    same slab and descriptor out of it as out of the fully decoded series; an axial stack is decoded whole."""
+    from spine_vision_b200 import volumes
+
+    rng = np.random.default_rng(n_slices)
+    arr = rng.integers(0, 3000, size=(n_slices, 19, 27)).astype(np.uint16)
+    sag = np.array([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, -1.0, 0.0]])  # columns: x -> P, y -> I, z (stack) -> L
+    synthetic.write_dicom_series(tmp_path / "sag", arr, (0.7, 0.7, 4.0), sag.ravel(), series_uid="1.2.3.60", shuffle_seed=1)
+    whole = hostio.read_medical_image(tmp_path / "sag")
+    part = hostio.read_medical_image(tmp_path / "sag", midplane_only=True)
+    z0, z1 = part.meta["decoded_z"]
+    assert whole.meta["decoded_z"] == (0, n_slices) and z1 - z0 == min(2, n_slices)
+    assert (part.spacing, part.direction, part.origin, part.integer_pixels) == (whole.spacing, whole.direction, whole.origin, whole.integer_pixels)
+    assert np.array_equal(part.array[z0:z1], whole.array[z0:z1])
+    pa = volumes.plan_midplane(whole.array, whole.spacing, whole.direction, integer_pixels=whole.integer_pixels)
+    pb = volumes.plan_midplane(part.array, part.spacing, part.direction, integer_pixels=part.integer_pixels)
+    assert pa.desc == pb.desc and pa.out_hw == pb.out_hw and np.array_equal(pa.slab, pb.slab)
+    synthetic.write_dicom_series(tmp_path / "ax", arr, (0.7, 0.7, 4.0), np.eye(3).ravel(), series_uid="1.2.3.61", shuffle_seed=2)
+    ax = hostio.read_medical_image(tmp_path / "ax", midplane_only=True)
+    assert ax.meta["decoded_z"] == (0, n_slices) and np.array_equal(ax.array, hostio.read_medical_image(tmp_path / "ax").array)
