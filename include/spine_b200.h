@@ -157,12 +157,20 @@ int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int
  * cut from cv2.warpAffine(image, R, INTER_LINEAR, BORDER_REPLICATE) about the disc centre, evaluated on the fly.
  *  d_inv_affine : float64 [N,6] -- the INVERSE of cv2.getRotationMatrix2D((cx,cy), angle, 1.0) per crop, row-major 2x3,
  *                 computed on the host exactly as cv::warpAffine inverts it (spine_vision_b200.cropping.inverse_rotation);
- *                 NULL = horizontal mode.  Slices are taken as float32 (integer-typed sources are converted first). */
+ *                 NULL = horizontal mode.
+ *  d_pixel_kind : int32 [B] per SLICE, or NULL (= all SVB_PIXEL_FLOAT): the pixel type the slice had in the file.  The
+ *                 reference hands cv2.warpAffine the slice in that type (extract_middle_slice keeps it, cropping.py:63-79), so
+ *                 int16 / uint16 sources are blended in fp32 and rounded back to the type (cvRound, saturating), uint8 sources
+ *                 take OpenCV's 15-bit fixed-point path; the values still arrive here as float32. */
+#define SVB_PIXEL_FLOAT 0
+#define SVB_PIXEL_INT16 1
+#define SVB_PIXEL_UINT16 2
+#define SVB_PIXEL_UINT8 3
 int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                                  const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
-                                 const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
-                                 uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
-                                 void* d_ws, size_t ws_bytes, void* stream);
+                                 const double* d_inv_affine, const int32_t* d_pixel_kind, int N, int max_box_h,
+                                 int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2,
+                                 int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K2 -- CoordinateRegressor forward (ConvNeXt backbone + MLP head + sigmoid).

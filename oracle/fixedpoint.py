@@ -305,6 +305,34 @@ def warp_affine_f32(img: np.ndarray, m: np.ndarray, region=None) -> np.ndarray:
     return ((a[y0, x0] * w0 + a[y0, x1c] * w1) + a[y1c, x0] * w2) + a[y1c, x1c] * w3
 
 
+def warp_affine(img: np.ndarray, m: np.ndarray, region=None) -> np.ndarray:
+    """``cv2.warpAffine(img, m, (w, h), INTER_LINEAR, BORDER_REPLICATE)`` in the image's OWN pixel type -- the reference hands
+    OpenCV the middle slice as ``sitk.GetArrayFromImage`` gave it (cropping.py:63-79, 292-301), int16 for SPIDER / MR DICOM:
+      float32         remapBilinear<Cast<float,float>>: four taps blended in float32 (``warp_affine_f32``)
+      int16 / uint16  the same float32 blend, then Cast<float,short/ushort> = cvRound (half to even), saturating
+      uint8           15-bit fixed-point weights (32-fx)(32-fy)*32 ... (exact for bilinear, they sum to 2^15), (acc + 2^14) >> 15
+    Checked bit-identical to cv2.warpAffine for all four types in tests/test_oracle.py."""
+    a = np.asarray(img)
+    if a.dtype == np.uint8:
+        h, w = a.shape
+        inv = invert_affine(m)
+        x1, x2, y1, y2 = region if region is not None else (0, w, 0, h)
+        xs = np.arange(x1, x2, dtype=np.int64)[None, :]
+        ys = np.arange(y1, y2, dtype=np.int64)[:, None]
+        sx, sy, fx, fy = np.broadcast_arrays(*warp_affine_coords(inv, xs, ys))
+        x0, x1c = np.clip(sx, 0, w - 1), np.clip(sx + 1, 0, w - 1)
+        y0, y1c = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+        ai = a.astype(np.int64)
+        acc = (ai[y0, x0] * ((32 - fy) * (32 - fx) * 32) + ai[y0, x1c] * ((32 - fy) * fx * 32)
+               + ai[y1c, x0] * (fy * (32 - fx) * 32) + ai[y1c, x1c] * (fy * fx * 32))
+        return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+    f = warp_affine_f32(a.astype(np.float32), m, region)
+    if a.dtype in (np.dtype(np.int16), np.dtype(np.uint16)):
+        info = np.iinfo(a.dtype)
+        return np.clip(np.rint(f), info.min, info.max).astype(a.dtype)
+    return f
+
+
 def rotation_angles(ivd_locations: dict, image_shape, last_disc_angle_boost: float = 1.0) -> dict:
     """``get_rotation_angles`` (cropping.py:172-255): tangent of the disc chain by finite differences, the last
     point from a 3-point quadratic fit; same NumPy calls, same Python float arithmetic."""
@@ -337,10 +365,13 @@ def rotation_angles(ivd_locations: dict, image_shape, last_disc_angle_boost: flo
 
 
 def crop_region_rotated(image: np.ndarray, x: float, y: float, crop_size, delta_px, angle_deg: float) -> np.ndarray:
-    """cropping.py:258-313 for float32 slices: rotate about the disc centre, cut the box, per-crop min-max, letterbox."""
-    a = np.asarray(image, dtype=np.float32)
+    """cropping.py:258-313: rotate about the disc centre IN THE SLICE'S PIXEL TYPE (``warp_affine``), cut the box, per-crop
+    min-max, letterbox.  Types OpenCV's remap does not take are warped as float32."""
+    a = np.asarray(image)
+    if a.dtype not in (np.dtype(np.int16), np.dtype(np.uint16), np.dtype(np.uint8)):
+        a = a.astype(np.float32)
     h, w = a.shape
     cx, cy = int(x * w), int(y * h)
     x1, x2, y1, y2 = crop_box(h, w, x, y, delta_px)
-    rot = warp_affine_f32(a, rotation_matrix_2d((cx, cy), angle_deg), (x1, x2, y1, y2))
+    rot = warp_affine(a, rotation_matrix_2d((cx, cy), angle_deg), (x1, x2, y1, y2))
     return resize_with_padding(normalize_to_uint8(rot), crop_size)

@@ -63,6 +63,44 @@ def golden_rotated(ref) -> None:
     np.savez_compressed(GOLDEN / "k3_rotated.npz", **out)
 
 
+INT_SERIES = [(12, 640, 650), (13, 400, 380)]
+INT_TYPES = {"int16": np.int16, "uint16": np.uint16, "uint8": np.uint8}
+
+
+def int_slice(seed: int, h: int, w: int, name: str) -> np.ndarray:
+    """The synthetic slice in an integer pixel type, as ``sitk.GetArrayFromImage`` hands an MR volume to the crop step:
+    int16 shifted below zero (CT-like offsets occur), uint16 as is, uint8 scaled into 0..255."""
+    img = synthetic.make_iso_slice(seed, h, w)
+    if name == "int16":
+        return (np.rint(img) - 300).astype(np.int16)
+    if name == "uint16":
+        return np.rint(img * 20).astype(np.uint16)
+    return np.rint(img * (255.0 / max(float(img.max()), 1.0))).astype(np.uint8)
+
+
+def golden_rotated_int(ref) -> None:
+    """Rotated crop mode on INTEGER-typed slices through the reference's own CropContext: cv2.warpAffine then works in the
+    slice's pixel type (rounds every warped value back to int16 / uint16; fixed-point weights for uint8) before
+    normalize_to_uint8 (cropping.py:292-311).  ADVICE r01 (svb_resize.cu:649)."""
+    out = {}
+    dpx = ref.mm_to_pixels(CROP_DELTAS_MM[0], (0.3, 0.3))
+    for seed, h, w in INT_SERIES:
+        xy = synthetic.make_coords(2, seed=300 + seed, border_frac=0.3, hw=(h, w))
+        xy[1, 0] = (0.02, 0.03)
+        xy[1, 4] = (0.97, 0.985)
+        out[f"xy_{seed}_{h}_{w}"] = xy
+        for name in INT_TYPES:
+            img = int_slice(seed, h, w, name)
+            res = np.zeros((2, 5, 128, 128), dtype=np.uint8)
+            for s in range(2):
+                locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                ctx = ref.CropContext(image=img, ivd_locations=locs, crop_size=(128, 128), crop_delta_px=dpx, mode="rotated")
+                for i in range(5):
+                    res[s, i] = ctx.crop(i)
+            out[f"crops_{seed}_{h}_{w}_{name}"] = res
+    np.savez_compressed(GOLDEN / "k3_rotated_int.npz", **out)
+
+
 SMALL_SERIES = [(30, 150, 121), (31, 90, 300), (32, 200, 234), (33, 260, 180), (34, 64, 64), (35, 7, 500)]
 
 
@@ -97,6 +135,12 @@ def main() -> None:
     import sys
 
     ref = ref_shim.load()
+    if "--rotated-int-only" in sys.argv:
+        golden_rotated_int(ref)
+        for f in sorted(GOLDEN.glob("k3_rotated_int.npz")):
+            print(f.name, f.stat().st_size)
+        return
+    golden_rotated_int(ref)
     if "--small-only" in sys.argv:
         golden_small(ref)
         for f in sorted(GOLDEN.glob("k3_small.npz")):

@@ -14,6 +14,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("SPINE_B200_LIB", _PKG / "libspine_b200.so"))
 
 SVB_BF16, SVB_FP16, SVB_F32 = 0, 1, 2
+PIXEL_FLOAT, PIXEL_INT16, PIXEL_UINT16, PIXEL_UINT8 = 0, 1, 2, 3  # SVB_PIXEL_*: the file's pixel type of a slice (rotated crops)
 DTYPES = {"bf16": SVB_BF16, "bfloat16": SVB_BF16, "fp16": SVB_FP16, "float16": SVB_FP16, "half": SVB_FP16}
 KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 
@@ -97,7 +98,7 @@ def load() -> C.CDLL:
     lib.svb_k3_crop_resample.restype = C.c_int
     lib.svb_k3_crop_resample.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
     lib.svb_k3_crop_resample_rotated.restype = C.c_int
-    lib.svb_k3_crop_resample_rotated.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
+    lib.svb_k3_crop_resample_rotated.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp, i32, vp, sz, vp]
     lib.svb_model_create.restype = C.c_int
     lib.svb_model_create.argtypes = [C.POINTER(vp), C.POINTER(WeightDesc), i32, i32]
     lib.svb_model_destroy.restype = C.c_int

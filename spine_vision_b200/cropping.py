@@ -204,7 +204,10 @@ class LocalizationModel:
     def __init__(self, state_dict, device: str = _DEFAULT_DEVICE, dtype: str | None = None, micro_batch: int = 64):
         import os
 
-        dtype = dtype or os.environ.get("SPINE_B200_DTYPE", "bf16")
+        # fp16 operands are the default: they hold the 0.5 px gate on trained-like weights (0.18 px; bf16 measures 1.0 px), at the
+        # same tensor-pipe rate.  The reference trains under fp16 autocast (trainers/base.py:229-237), so a real checkpoint's
+        # activations are in fp16 range by construction; conversions saturate.  dtype="bf16" / SPINE_B200_DTYPE=bf16 opt in.
+        dtype = dtype or os.environ.get("SPINE_B200_DTYPE", "fp16")
         self.device = device
         self.engine = ops.LocalizationEngine(state_dict, device, dtype, micro_batch)
         self.num_levels = self.engine.num_levels

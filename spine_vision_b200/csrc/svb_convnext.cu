@@ -149,6 +149,26 @@ static int gemm_cg(int N, int K) {
     return (K >= 1024 || (K >= 512 && N >= 512)) ? 2 : 1;
 }
 
+// Co-resident ("half-SM") GEMM footprint, per stage: SVB_COEX is a string of four 0/1 flags (stage 0..3), e.g. "1110".
+// A stage whose flag is set runs its fc1 / fc2 GEMMs as gemm_kernel<.., BN = 128, .., HALF = 1> (<= 113.5 KB of shared
+// memory, 256 TMEM columns), so that the other micro-batch chain's depthwise-conv CTAs fit on the same SM.
+static bool coex_stage(int s) {
+    static int mask = -1;
+    if (mask < 0) {
+        mask = 0;
+        const char* e = getenv("SVB_COEX");
+        for (int i = 0; e && i < 4 && e[i]; ++i)
+            if (e[i] == '1') mask |= 1 << i;
+    }
+    return s >= 0 && s < 4 && ((mask >> s) & 1);
+}
+// standalone svb_gemm: SVB_GEMM_HALF=1 selects the co-resident footprint (tests / experiments); read on every call
+static bool gemm_half_env() {
+    const char* e = getenv("SVB_GEMM_HALF");
+    return e && e[0] == '1';
+}
+static int gemm_bn_for(int N, bool half) { return half ? 128 : gemm_bn(N); }
+
 // rows per depthwise tile: bounded by the 512 TMEM columns a CTA may hold (2 warps x TH pixels x NV values), see DwCfg
 static int dw_th(int C) { return C >= 1536 ? 4 : (C >= 384 ? 8 : 16); }
 // Programmatic dependent launch for the persistent kernels of the forward chain (depthwise conv + LN, GEMMs): the next
@@ -416,8 +436,8 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
                                          CU_TENSOR_MAP_SWIZZLE_NONE))
                     return rc;
             }
-            if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn(4 * C) / gemm_cg(4 * C, C))) return rc;
-            if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn(C) / gemm_cg(C, 4 * C))) return rc;
+            if (int rc = make_operand_map(&bp.w1_map, dtype, bp.w1, 4 * (uint64_t)C, C, gemm_bn_for(4 * C, coex_stage(s)) / gemm_cg(4 * C, C))) return rc;
+            if (int rc = make_operand_map(&bp.w2_map, dtype, bp.w2, C, 4 * (uint64_t)C, gemm_bn_for(C, coex_stage(s)) / gemm_cg(C, 4 * C))) return rc;
             if (C == 128 || C == 256) {
                 if (int rc = make_operand_map(&bp.w1f_map, dtype, bp.w1, 4 * (uint64_t)C, C, 32)) return rc;
                 if (int rc = make_operand_map(&bp.w2f_map, dtype, bp.w2, C, 4 * (uint64_t)C, C / 2)) return rc;
@@ -538,11 +558,11 @@ static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** o
 }
 
 // ---- launchers -------------------------------------------------------------------------------
-template <typename T, int BN, int MODE, int CG>
+template <typename T, int BN, int MODE, int CG, int HALF = 0>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
                          const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st) {
-    using Cfg = GemmCfg<BN, CG>;
-    auto kern = gemm_kernel<T, BN, MODE, CG>;
+    using Cfg = GemmCfg<BN, CG, HALF>;
+    auto kern = gemm_kernel<T, BN, MODE, CG, HALF>;
     static bool attr_done = false;
     if (!attr_done) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -571,10 +591,23 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
 }
 template <typename T>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
-                       const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st) {
+                       const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st, bool half = false) {
     SVB_REQUIRE(N % 32 == 0 && K % 8 == 0, SVB_ERR_INVALID_ARG, "gemm: N (%d) must be a multiple of 32, K (%d) of 8", N, K);
-    const int bn = gemm_bn(N);
+    const int bn = gemm_bn_for(N, half);
     const int cg = gemm_cg(N, K);
+    if (half) {
+#define SVB_GEMM_HALF_CASE(MODE_, CG_)                                          \
+    if (mode == MODE_ && cg == CG_)                                             \
+        return launch_gemm_t<T, 128, MODE_, CG_, 1>(a, w, out, resid, bias, gamma, M, N, K, st);
+        SVB_GEMM_HALF_CASE(GEMM_GELU, 2)
+        SVB_GEMM_HALF_CASE(GEMM_RESID, 2)
+        SVB_GEMM_HALF_CASE(GEMM_BIAS, 2)
+        SVB_GEMM_HALF_CASE(GEMM_GELU, 1)
+        SVB_GEMM_HALF_CASE(GEMM_RESID, 1)
+        SVB_GEMM_HALF_CASE(GEMM_BIAS, 1)
+#undef SVB_GEMM_HALF_CASE
+        return set_error(SVB_ERR_INVALID_ARG, "gemm: unsupported mode %d", mode);
+    }
 #define SVB_GEMM_CASE(BN_, MODE_, CG_)                                          \
     if (bn == BN_ && mode == MODE_ && cg == CG_)                                \
         return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st);
@@ -855,11 +888,11 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
                 RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
             } else {
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
-                                                GEMM_GELU, st));
+                                                GEMM_GELU, st, coex_stage(s)));
                 if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd, nb, h * w, 4 * C, bp.grn_w, bp.grn_b, reinterpret_cast<float*>(ws + L.grn_part),
                                                           reinterpret_cast<float*>(ws + L.grn_scale), st));
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
-                                                GEMM_RESID, st));
+                                                GEMM_RESID, st, coex_stage(s)));
             }
         }
     }
@@ -962,11 +995,12 @@ extern "C" int svb_gemm(const void* d_a, const void* d_w, void* d_out, const voi
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, SVB_ERR_INVALID_ARG, "gemm: bad shape");
     CUtensorMap a_map, w_map, out_map, resid_map;
     if (int rc = make_operand_map(&a_map, dtype, d_a, M, K, 128)) return rc;
-    if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn(N) / gemm_cg(N, K))) return rc;
+    const bool half = gemm_half_env() && N % 128 == 0;
+    if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn_for(N, half) / gemm_cg(N, K))) return rc;
     if (int rc = make_epilogue_map(&out_map, dtype, d_out, M, N)) return rc;
     if (int rc = make_epilogue_map(&resid_map, dtype, mode == GEMM_RESID ? d_resid : d_out, M, N)) return rc;
-    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
-    return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st);
+    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half);
+    return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half);
 }
 
 extern "C" int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,

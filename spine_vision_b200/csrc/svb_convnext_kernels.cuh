@@ -487,15 +487,18 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 // halved; the leader issues tcgen05.mma.cta_group::2 for both and multicasts the commits.
 enum GemmMode { GEMM_GELU = 0, GEMM_RESID = 1, GEMM_BIAS = 2 };
 
-template <int BN, int CG>
+// HALF == 1: the "co-resident" footprint -- at most half of an SM (<= 113.5 KB of shared memory, 256 TMEM columns, 320
+// threads), so that a depthwise-conv CTA of the OTHER micro-batch chain (or a second GEMM CTA) fits beside it and the
+// FP32 pipe works under the tensor pipe's shadow.  BN = 128 only (2 accumulator stages x 128 columns).
+template <int BN, int CG, int HALF = 0>
 struct GemmCfg {
     static constexpr int BM = 128, BK = 64;
     static constexpr int B_ROWS = BN / CG;             // rows of W this CTA stages
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;  // 4 (48 KB), 6 (32 KB) or 8 (24 KB)
-    static constexpr int EPI_WARPS = 16;                       // 4 per TMEM lane quarter: the epilogue is latency-bound per warp
+    static constexpr int STAGES = ((HALF ? 96 : 192) * 1024) / STAGE_BYTES;  // full: 4 (48 KB), 6 (32 KB) or 8 (24 KB); half: 3 or 4
+    static constexpr int EPI_WARPS = HALF ? 8 : 16;            // 4 (2) per TMEM lane quarter: the epilogue is latency-bound per warp
     static constexpr int EPI_BUF_BYTES = 32 * 32 * 2;          // one 32x32 16-bit box per warp
     static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUF_BYTES;
     static constexpr int NUM_BARS = 2 * STAGES + 4 + EPI_WARPS;
@@ -504,6 +507,7 @@ struct GemmCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 512 + 1024;
     static_assert(NUM_BARS * 8 + 8 <= 512, "barrier area");
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte (swizzle atom) alignment");
+    static_assert(!HALF || (TMEM_COLS <= 256 && SMEM_BYTES <= 114 * 1024), "co-resident footprint");
 };
 
 template <typename T> struct UmmaFmt;
@@ -545,12 +549,12 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <typename T, int BN, int MODE, int CG>
-__global__ void __launch_bounds__(GemmCfg<BN, CG>::NUM_THREADS, 1)
+template <typename T, int BN, int MODE, int CG, int HALF = 0>
+__global__ void __launch_bounds__(GemmCfg<BN, CG, HALF>::NUM_THREADS, HALF ? 2 : 1)  // HALF: <= 102 registers, so that it fits beside a depthwise CTA
 gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
             const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap resid_map,
             const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K) {
-    using Cfg = GemmCfg<BN, CG>;
+    using Cfg = GemmCfg<BN, CG, HALF>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // pointer arithmetic keeps the shared address space
@@ -649,7 +653,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
         const int ew = warp - 2;
         const int q = warp & 3;             // TMEM lane quarter this warp may access
         const int slice = ew >> 2;          // which quarter of the BN columns
-        constexpr int CW = BN / 4;          // columns per warp: 64 or 32
+        constexpr int CW = BN / (Cfg::EPI_WARPS / 4);  // columns per warp: 64 or 32
         constexpr int CH = CW / 32;         // 32-column chunks per warp
         uint8_t* ebuf_p = sEpi + ew * Cfg::EPI_BUF_BYTES;
         const uint32_t ebuf = smem_u32(ebuf_p);

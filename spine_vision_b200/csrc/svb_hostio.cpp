@@ -20,6 +20,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -52,6 +54,21 @@ void parallel_for(int n, int n_threads, F&& fn) {
             for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
         });
     for (auto& th : pool) th.join();
+}
+
+// No C++ exception may leave an extern "C" entry or a worker thread (std::terminate would take the whole process down):
+// allocation failures and anything else thrown by the body become an error code + message.
+template <typename F>
+int guarded(const char* what, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return set_error(SVB_ERR_IO, "%s: out of host memory", what);
+    } catch (const std::exception& e) {
+        return set_error(SVB_ERR_IO, "%s: %s", what, e.what());
+    } catch (...) {
+        return set_error(SVB_ERR_IO, "%s: unknown C++ exception", what);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ PNG
@@ -207,7 +224,12 @@ int mha_header(const char* path, svb_mha_info* info) {
         else if (key == "DimSize") {
             double d[3] = {1, 1, 1};
             const int n = parse_doubles(val, d, 3);
-            for (int i = 0; i < 3; ++i) info->dim[i] = i < n ? (int32_t)d[i] : 1;
+            for (int i = 0; i < 3; ++i) {
+                // checked BEFORE the cast: a double outside int32 is undefined behaviour to convert, and a corrupt header must
+                // be a format error for this one series (spider.py:131-133 skips it), never a multi-terabyte allocation
+                if (i < n && !(d[i] >= 1.0 && d[i] <= 1048576.0)) { fclose(f); return set_error(SVB_ERR_FORMAT, "%s: DimSize[%d] = %g is outside 1 .. 2^20", path, i, d[i]); }
+                info->dim[i] = i < n ? (int32_t)d[i] : 1;
+            }
             have_dims = n > 0;
         } else if (key == "ElementSpacing" || key == "ElementSize") {
             // ElementSpacing wins when both are present (MetaIO)
@@ -251,6 +273,25 @@ int mha_header(const char* path, svb_mha_info* info) {
     if (info->channels != 1) return set_error(SVB_ERR_FORMAT, "%s: %d channels (scalar images only)", path, info->channels);
     for (int i = 0; i < 3; ++i)
         if (info->dim[i] <= 0) return set_error(SVB_ERR_FORMAT, "%s: bad DimSize", path);
+    {
+        // the voxel count must be backed by the data that is actually there: raw data by the file's bytes, a zlib stream by at
+        // most 1032x its compressed size (deflate's maximum expansion)
+        const double voxels = (double)info->dim[0] * info->dim[1] * info->dim[2];
+        if (voxels > 8589934592.0) return set_error(SVB_ERR_FORMAT, "%s: DimSize product %.0f exceeds 2^33 voxels", path, voxels);
+        const double all_bytes = voxels * info->element_bytes;
+        const char* data_path = info->data_offset >= 0 ? path : info->data_file;
+        FILE* df = fopen(data_path, "rb");
+        if (df) {
+            fseek(df, 0, SEEK_END);
+            const double file_bytes = (double)ftell(df);
+            fclose(df);
+            const double start = info->data_offset >= 0 ? (double)info->data_offset : (info->header_size > 0 ? (double)info->header_size : 0.0);
+            const double avail = info->compressed && info->compressed_size > 0 ? (double)info->compressed_size : file_bytes - start;
+            const double limit = info->compressed ? avail * 1032.0 + 65536.0 : avail;
+            if (avail < 0 || all_bytes > limit)
+                return set_error(SVB_ERR_FORMAT, "%s: DimSize asks for %.0f bytes of voxels, the data holds at most %.0f", path, all_bytes, limit);
+        }  // a missing data file is reported by the read, with its own message
+    }
     // ITK: row i of TransformMatrix is the direction cosine of image axis i, i.e. COLUMN i of image.GetDirection()
     const int nd = info->ndim;
     if (n_tm >= nd * nd) {
@@ -621,7 +662,7 @@ size_t svb_png_bound(int h, int w) {
 }
 
 int svb_png_encode_gray8(const uint8_t* h_img, int h, int w, int level, uint8_t* h_out, size_t cap, size_t* out_len) {
-    return png_encode(h_img, h, w, level, h_out, cap, out_len);
+    return guarded("png encode", [&] { return png_encode(h_img, h, w, level, h_out, cap, out_len); });
 }
 
 int svb_png_write_gray8_batch(const uint8_t* h_imgs, int n, int h, int w, const char* const* paths, int level, int n_threads,
@@ -632,10 +673,13 @@ int svb_png_write_gray8_batch(const uint8_t* h_imgs, int n, int h, int w, const 
     std::atomic<int> first_bad{-1};
     std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
     parallel_for(n, n_threads, [&](int i) {
-        std::vector<uint8_t> buf(cap);
-        size_t len = 0;
-        int rc = png_encode(h_imgs + (size_t)i * h * w, h, w, level, buf.data(), cap, &len);
-        if (rc == SVB_OK) rc = write_file(paths[i], buf.data(), len);
+        int rc = guarded("png batch", [&] {
+            std::vector<uint8_t> buf(cap);
+            size_t len = 0;
+            int r = png_encode(h_imgs + (size_t)i * h * w, h, w, level, buf.data(), cap, &len);
+            if (r == SVB_OK) r = write_file(paths[i], buf.data(), len);
+            return r;
+        });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) {
             msgs[i] = svb_last_error();  // thread-local in the worker
@@ -658,13 +702,15 @@ int svb_png_write_gray8_ragged(const uint8_t* h_pool, const int64_t* offs, const
         const int h = hw[2 * i], w = hw[2 * i + 1];
         int rc = SVB_OK;
         if (h <= 0 || w <= 0) rc = set_error(SVB_ERR_INVALID_ARG, "png ragged batch: image %d has size %d x %d", i, h, w);
-        if (rc == SVB_OK) {
-            const size_t cap = svb_png_bound(h, w);
-            std::vector<uint8_t> buf(cap);
-            size_t len = 0;
-            rc = png_encode(h_pool + offs[i], h, w, level, buf.data(), cap, &len);
-            if (rc == SVB_OK) rc = write_file(paths[i], buf.data(), len);
-        }
+        if (rc == SVB_OK)
+            rc = guarded("png ragged batch", [&] {
+                const size_t cap = svb_png_bound(h, w);
+                std::vector<uint8_t> buf(cap);
+                size_t len = 0;
+                int r = png_encode(h_pool + offs[i], h, w, level, buf.data(), cap, &len);
+                if (r == SVB_OK) r = write_file(paths[i], buf.data(), len);
+                return r;
+            });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) {
             msgs[i] = svb_last_error();
@@ -677,10 +723,12 @@ int svb_png_write_gray8_ragged(const uint8_t* h_pool, const int64_t* offs, const
     return SVB_OK;
 }
 
-int svb_mha_read_header(const char* path, svb_mha_info* info) { return mha_header(path, info); }
+int svb_mha_read_header(const char* path, svb_mha_info* info) {
+    return guarded("mha header", [&] { return mha_header(path, info); });
+}
 
 int svb_mha_read_f32(const char* path, const svb_mha_info* info, float* h_dst, size_t dst_elems) {
-    return mha_read(path, info, h_dst, dst_elems);
+    return guarded("mha read", [&] { return mha_read(path, info, h_dst, dst_elems); });
 }
 
 int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* infos, float* const* h_dsts,
@@ -689,7 +737,7 @@ int svb_mha_read_batch_f32(const char* const* paths, int n, const svb_mha_info* 
         return set_error(SVB_ERR_INVALID_ARG, "mha batch: bad arguments (n=%d)", n);
     std::atomic<int> n_bad{0};
     parallel_for(n, n_threads, [&](int i) {
-        const int rc = mha_read(paths[i], &infos[i], h_dsts[i], dst_elems[i]);
+        const int rc = guarded("mha batch", [&] { return mha_read(paths[i], &infos[i], h_dsts[i], dst_elems[i]); });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) n_bad.fetch_add(1);
     });
@@ -703,7 +751,7 @@ int svb_mha_read_batch_slab_f32(const char* const* paths, int n, const svb_mha_i
         return set_error(SVB_ERR_INVALID_ARG, "mha slab batch: bad arguments (n=%d)", n);
     std::atomic<int> n_bad{0};
     parallel_for(n, n_threads, [&](int i) {
-        const int rc = mha_read_slab(paths[i], &infos[i], h_dsts[i], dst_elems[i], z0[i], z1[i]);
+        const int rc = guarded("mha slab batch", [&] { return mha_read_slab(paths[i], &infos[i], h_dsts[i], dst_elems[i], z0[i], z1[i]); });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) n_bad.fetch_add(1);
     });
@@ -714,7 +762,7 @@ int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* info
     if (n < 0 || (n > 0 && (!paths || !infos))) return set_error(SVB_ERR_INVALID_ARG, "dicom headers: bad arguments (n=%d)", n);
     std::atomic<int> n_bad{0};
     parallel_for(n, n_threads, [&](int i) {
-        const int rc = dicom_header(paths[i], &infos[i], nullptr);
+        const int rc = guarded("dicom headers", [&] { return dicom_header(paths[i], &infos[i], nullptr); });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) n_bad.fetch_add(1);
     });
@@ -729,7 +777,7 @@ int svb_dicom_read_slices_f32(const char* const* paths, int n, const svb_dicom_i
     std::atomic<int> first_bad{-1};
     std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
     parallel_for(n, n_threads, [&](int i) {
-        const int rc = dicom_pixels(paths[i], &infos[i], h_dsts[i], dst_elems[i]);
+        const int rc = guarded("dicom slices", [&] { return dicom_pixels(paths[i], &infos[i], h_dsts[i], dst_elems[i]); });
         if (rcs) rcs[i] = rc;
         if (rc != SVB_OK) {
             msgs[i] = svb_last_error();

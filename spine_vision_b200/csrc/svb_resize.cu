@@ -569,7 +569,8 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
                                                       uint8_t* __restrict__ crops2, int32_t* __restrict__ geom_out,
                                                       int flags, int box_cap, int ksh2, int ksw2, const int* __restrict__ hb2,
                                                       const int* __restrict__ hk2, const int* __restrict__ vb2,
-                                                      const int* __restrict__ vk2, const double* __restrict__ rot) {
+                                                      const int* __restrict__ vk2, const double* __restrict__ rot,
+                                                      const int32_t* __restrict__ pixel_kind) {
     extern __shared__ __align__(16) uint8_t smem[];
     const int n = blockIdx.x;
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -641,10 +642,16 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
     // rotated mode (cropping.py:258-313): the box is cut from cv2.warpAffine(image, R, INTER_LINEAR, BORDER_REPLICATE).
     // rot = the INVERTED 2x3 map (host, double).  Per destination pixel OpenCV takes the source position in 1/1024 px
     // fixed point, rounds it to 1/32 px, and blends four taps with exact fp32 bilinear weights, left to right.
+    // The reference warps the slice in the FILE's pixel type (extract_middle_slice keeps it, cropping.py:63-79): float32
+    // sources blend in fp32 (remapBilinear<Cast<float,float>>); 16-bit integer sources blend the same way and are rounded
+    // back to the type (Cast<float,short/ushort> = cvRound, half to even); uint8 sources use OpenCV's 15-bit fixed-point
+    // weights ((32-fx)(32-fy)*32, ... exact for bilinear) and (sum + 2^14) >> 15.
     double r00 = 0, r01 = 0, r02 = 0, r10 = 0, r11 = 0, r12 = 0;
+    int kind = SVB_PIXEL_FLOAT;
     if (rot != nullptr) {
         const double* rp = rot + 6 * (size_t)n;
         r00 = rp[0]; r01 = rp[1]; r02 = rp[2]; r10 = rp[3]; r11 = rp[4]; r12 = rp[5];
+        if (pixel_kind != nullptr) kind = pixel_kind[b];
     }
     auto box_value = [&](int bx, int by) -> float {
         if (rot == nullptr) return __ldg(src + (long long)by * W + bx);
@@ -661,9 +668,18 @@ __global__ void __launch_bounds__(K3_THREADS, 2) k3_crop_kernel(const float* __r
         const int ya = min(max(sy, 0), H - 1), yb = min(max(sy + 1, 0), H - 1);
         const float s00 = __ldg(img + (long long)ya * W + xa), s01 = __ldg(img + (long long)ya * W + xb);
         const float s10 = __ldg(img + (long long)yb * W + xa), s11 = __ldg(img + (long long)yb * W + xb);
+        if (kind == SVB_PIXEL_UINT8) {
+            const int fx = X & 31, fy = Y & 31;
+            const int acc = (int)s00 * ((32 - fy) * (32 - fx) * 32) + (int)s01 * ((32 - fy) * fx * 32) +
+                            (int)s10 * (fy * (32 - fx) * 32) + (int)s11 * (fy * fx * 32);
+            return (float)min(max((acc + (1 << 14)) >> 15, 0), 255);
+        }
         float acc = __fadd_rn(__fmul_rn(s00, __fmul_rn(vy0, vx0)), __fmul_rn(s01, __fmul_rn(vy0, vx1)));
         acc = __fadd_rn(acc, __fmul_rn(s10, __fmul_rn(vy1, vx0)));
-        return __fadd_rn(acc, __fmul_rn(s11, __fmul_rn(vy1, vx1)));
+        acc = __fadd_rn(acc, __fmul_rn(s11, __fmul_rn(vy1, vx1)));
+        if (kind == SVB_PIXEL_INT16) acc = fminf(fmaxf(rintf(acc), -32768.0f), 32767.0f);
+        else if (kind == SVB_PIXEL_UINT16) acc = fminf(fmaxf(rintf(acc), 0.0f), 65535.0f);
+        return acc;
     };
 
     if (valid) {
@@ -1004,24 +1020,24 @@ extern "C" size_t svb_k3_workspace_bytes(int ch, int cw, int oh2, int ow2) {
 
 extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                                             const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
-                                            const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
-                                            uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
-                                            void* d_ws, size_t ws_bytes, void* stream_);
+                                            const double* d_inv_affine, const int32_t* d_pixel_kind, int N, int max_box_h,
+                                            int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2,
+                                            int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes, void* stream_);
 
 extern "C" int svb_k3_crop_resample(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                                     const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px, int N,
                                     int max_box_h, int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2,
                                     uint8_t* d_crops2, int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes,
                                     void* stream_) {
-    return svb_k3_crop_resample_rotated(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, nullptr, N, max_box_h, max_box_w,
-                                        ch, cw, d_crops, oh2, ow2, d_crops2, d_geom, flags, d_ws, ws_bytes, stream_);
+    return svb_k3_crop_resample_rotated(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, nullptr, nullptr, N, max_box_h,
+                                        max_box_w, ch, cw, d_crops, oh2, ow2, d_crops2, d_geom, flags, d_ws, ws_bytes, stream_);
 }
 
 extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
                                             const int32_t* d_slice_idx, const float* d_xy, const int32_t* d_delta_px,
-                                            const double* d_inv_affine, int N, int max_box_h, int max_box_w, int ch, int cw,
-                                            uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2, int32_t* d_geom, int flags,
-                                            void* d_ws, size_t ws_bytes, void* stream_) {
+                                            const double* d_inv_affine, const int32_t* d_pixel_kind, int N, int max_box_h,
+                                            int max_box_w, int ch, int cw, uint8_t* d_crops, int oh2, int ow2, uint8_t* d_crops2,
+                                            int32_t* d_geom, int flags, void* d_ws, size_t ws_bytes, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (int rc = check_device_sm100()) return rc;
     SVB_REQUIRE(N >= 0 && ch > 0 && cw > 0 && max_box_h > 0 && max_box_w > 0, SVB_ERR_INVALID_ARG,
@@ -1059,7 +1075,7 @@ extern "C" int svb_k3_crop_resample_rotated(const float* d_slices, const int64_t
     }
     SVB_CUDA_OK(cudaFuncSetAttribute(k3_crop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     k3_crop_kernel<<<N, K3_THREADS, smem_bytes, stream>>>(d_slices, d_offs, d_hw, d_slice_idx, d_xy, d_delta_px, ch, cw, d_crops,
-                                                   oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk, d_inv_affine);
+                                                   oh2, ow2, d_crops2, d_geom, flags, (int)box_cap, L.ksh, L.ksw, hb, hk, vb, vk, d_inv_affine, d_pixel_kind);
     SVB_LAUNCHED();
     return SVB_OK;
 }

@@ -340,7 +340,8 @@ def process_jobs(jobs: list[SeriesJob], config: ClassificationDatasetConfig, out
                 continue
             pool, spacings = volumes.midplane_resample([v.array for _, v in live], [v.spacing for _, v in live],
                                                        [v.direction for _, v in live], config.device,
-                                                       integer_pixels=[v.integer_pixels for _, v in live])
+                                                       integer_pixels=[v.integer_pixels for _, v in live],
+                                                       pixel_kinds=[v.pixel_kind for _, v in live])
             batch = pipeline.localize_and_crop(pool, model, crop_delta_mm=config.crop_delta_mm, crop_size=(ch, cw),
                                                image_size=config.image_size, second_size=None, spacings=spacings,
                                                crop_mode=config.crop_mode, last_disc_angle_boost=config.last_disc_angle_boost)
@@ -373,15 +374,17 @@ def process_phenikaa(config, output_images_path: Path, model, existing_image_pat
     return process_jobs(collect_phenikaa_jobs(config, existing_image_paths or set()), config, output_images_path, model)
 
 
-def gather_records(records: list[ClassificationRecord], group=None) -> list[ClassificationRecord]:
-    """All ranks' records on every rank, rank order (the per-rank order is the job order)."""
+def gather_records(records: list[ClassificationRecord], group=None, failure: str | None = None):
+    """All ranks' records on every rank, rank order (the per-rank order is the job order), and the failure messages of the
+    ranks that could not finish their shard (so that every rank leaves the collective and raises the same error)."""
     import torch.distributed as dist
 
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return records
+        return records, ([failure] if failure else [])
     parts: list = [None] * dist.get_world_size(group)
-    dist.all_gather_object(parts, [r.model_dump() for r in records], group=group)
-    return [ClassificationRecord(**d) for part in parts for d in part]
+    dist.all_gather_object(parts, {"records": [r.model_dump() for r in records], "failure": failure}, group=group)
+    return ([ClassificationRecord(**d) for part in parts for d in part["records"]],
+            [part["failure"] for part in parts if part["failure"]])
 
 
 def write_annotations(csv_path: Path, records: list[ClassificationRecord]) -> None:
@@ -394,16 +397,8 @@ def write_annotations(csv_path: Path, records: list[ClassificationRecord]) -> No
             writer.writerow(rec.model_dump())
 
 
-def create_classification_dataset(config: ClassificationDatasetConfig, rank: int = 0, world_size: int = 1) -> ProcessingResult:
-    """Drop-in for ``create_classification_dataset`` (__init__.py:122-235).  With ``world_size > 1`` (one process per
-    GPU, ``torch.distributed`` initialised) every rank takes every ``world_size``-th job, writes its own PNGs, and rank 0
-    writes the CSV from the gathered records."""
-    if config.verbose:
-        logger.setLevel(logging.DEBUG)
-    csv_path = config.output_path / "annotations.csv"
-    output_images_path = config.output_path / "images"
-    output_images_path.mkdir(parents=True, exist_ok=True)
-
+def _plan_local(config, output_images_path: Path):
+    """Everything that READS the output tree or the label files: resume scan (__init__.py:150-182), label recovery, job list."""
     existing = scan_existing_images(output_images_path)
     existing_paths: set[str] = set()
     recovered: list[ClassificationRecord] = []
@@ -416,24 +411,61 @@ def create_classification_dataset(config: ClassificationDatasetConfig, rank: int
         orphans = len(existing) - len(recovered)
         if orphans > 0:
             logger.warning("%d existing images have no matching labels (labels may have been removed from source)", orphans)
-
-    model: LocalizationModel | None = None
-    if config.localization_model_path is not None:
-        logger.info("Loading localization model from: %s", config.localization_model_path)
-        model = load_localization_model(config.localization_model_path, config.model_variant, config.device)
-    else:
-        logger.warning("No localization model provided, using center fallback locations")
-
     jobs: list[SeriesJob] = []
     if config.include_phenikaa:
         jobs += collect_phenikaa_jobs(config, existing_paths)
     if config.include_spider:
         jobs += collect_spider_jobs(config, existing_paths)
-    mine = jobs[rank::world_size] if world_size > 1 else jobs
-    with torch.cuda.device(torch.device(config.device)):
-        new_records = process_jobs(mine, config, output_images_path, model)
+    return recovered, jobs
+
+
+def plan_dataset(config, output_images_path: Path, rank: int = 0, world_size: int = 1):
+    """(recovered records, job list).  Multi-rank: the plan is made ONCE, on rank 0, and broadcast.  If every rank scanned the
+    tree itself, a late rank would see PNGs an early rank has already written, count them as existing and build a shorter job
+    list -- the ``jobs[rank::world_size]`` shards would then disagree between ranks (series dropped or done twice, duplicate
+    recovered rows)."""
+    if world_size <= 1:
+        return _plan_local(config, output_images_path)
+    import torch.distributed as dist
+
+    box = [_plan_local(config, output_images_path) if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return box[0]
+
+
+def create_classification_dataset(config: ClassificationDatasetConfig, rank: int = 0, world_size: int = 1) -> ProcessingResult:
+    """Drop-in for ``create_classification_dataset`` (__init__.py:122-235).  With ``world_size > 1`` (one process per
+    GPU, ``torch.distributed`` initialised) every rank takes every ``world_size``-th job, writes its own PNGs, and rank 0
+    writes the CSV from the gathered records."""
+    if config.verbose:
+        logger.setLevel(logging.DEBUG)
+    csv_path = config.output_path / "annotations.csv"
+    output_images_path = config.output_path / "images"
+    output_images_path.mkdir(parents=True, exist_ok=True)
+
+    recovered, jobs = plan_dataset(config, output_images_path, rank, world_size)
+
+    model: LocalizationModel | None = None
+    failure: str | None = None
+    new_records: list[ClassificationRecord] = []
+    try:
+        if config.localization_model_path is not None:
+            logger.info("Loading localization model from: %s", config.localization_model_path)
+            model = load_localization_model(config.localization_model_path, config.model_variant, config.device)
+        else:
+            logger.warning("No localization model provided, using center fallback locations")
+        mine = jobs[rank::world_size] if world_size > 1 else jobs
+        with torch.cuda.device(torch.device(config.device)):
+            new_records = process_jobs(mine, config, output_images_path, model)
+    except Exception as e:  # a failing rank must still meet the others in the gather below
+        if world_size == 1:
+            raise
+        failure = f"rank {rank}: {type(e).__name__}: {e}"
+        logger.error("dataset build failed on %s", failure)
     if world_size > 1:
-        new_records = gather_records(new_records)
+        new_records, failures = gather_records(new_records, failure=failure)
+        if failures:
+            raise RuntimeError("create_classification_dataset failed on " + "; ".join(failures))
 
     all_records = recovered + new_records
     if rank == 0:

@@ -31,6 +31,9 @@ import torch
 from . import _lib
 
 _INTEGER_TYPES = {0, 1, 2, 3, 4, 5, 6, 7}  # svb_mha_type ids of the integer element types
+# svb_mha_type -> SVB_PIXEL_* (what cv2.warpAffine does to a slice of that type in the rotated crop mode); the types OpenCV's
+# remap does not take (int8, 32 / 64-bit integers: the reference raises and skips the series) stay "float"
+_PIXEL_KIND = {1: _lib.PIXEL_UINT8, 2: _lib.PIXEL_INT16, 3: _lib.PIXEL_UINT16}
 
 
 class UnsupportedFormatError(ValueError):
@@ -46,6 +49,7 @@ class MedicalVolume:
     direction: tuple[float, ...] = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)  # image.GetDirection()
     origin: tuple[float, float, float] = (0.0, 0.0, 0.0)
     integer_pixels: bool = False  # the file's pixel type is integral (ITK casts resampled values back to it)
+    pixel_kind: int = 0  # SVB_PIXEL_*: how cv2.warpAffine treats a slice of the file's pixel type (rotated crop mode)
     meta: dict = field(default_factory=dict)
 
     def GetSize(self):
@@ -90,6 +94,7 @@ def _volume_from(info: _lib.MhaInfo, arr: np.ndarray) -> MedicalVolume:
     nx, ny, nz = info.dim[0], info.dim[1], info.dim[2]
     return MedicalVolume(array=arr.reshape(nz, ny, nx), spacing=tuple(info.spacing), direction=tuple(info.direction),
                          origin=tuple(info.origin), integer_pixels=info.element_type in _INTEGER_TYPES,
+                         pixel_kind=_PIXEL_KIND.get(int(info.element_type), _lib.PIXEL_FLOAT),
                          meta={"element_type": int(info.element_type), "compressed": bool(info.compressed), "ndim": int(info.ndim)})
 
 
@@ -163,7 +168,14 @@ def read_dicom_series(folder_path: Path, n_threads: int = 0, pin: bool = False, 
     c_sizes = (C.c_size_t * mp)(*([rows * cols] * mp))
     _lib.check(lib.svb_dicom_read_slices_f32(c_sel, mp, c_infos, c_dsts, c_sizes, int(n_threads), None))
     integral = all(float(infos[i].rescale_slope).is_integer() and float(infos[i].rescale_intercept).is_integer() for i in sel)
-    return MedicalVolume(array=host.numpy().reshape(m, rows, cols), spacing=spacing,
+    kind = _lib.PIXEL_FLOAT
+    if integral:  # the integer type ITK / GDCM give the series: 16-bit stored values (signed when stored signed or shifted below zero)
+        signed = any(infos[i].pixel_representation == 1 or infos[i].rescale_intercept < 0 for i in sel)
+        if first.bits_allocated == 16:
+            kind = _lib.PIXEL_INT16 if signed else _lib.PIXEL_UINT16
+        elif first.bits_allocated == 8 and not signed:
+            kind = _lib.PIXEL_UINT8
+    return MedicalVolume(pixel_kind=kind, array=host.numpy().reshape(m, rows, cols), spacing=spacing,
                          direction=tuple(float(v) for v in direction.ravel()), origin=tuple(float(v) for v in p0), integer_pixels=integral,
                          meta={"series_uid": uid.decode("ascii", "replace"), "files": [files[i].name for i in sel], "decoded_z": (k_lo, k_hi)})
 
@@ -254,12 +266,25 @@ def read_volumes(paths, n_threads: int = 0, pin: bool = False, midplane_only: bo
             ok.append(i)
         except Exception as e:  # noqa: BLE001 -- mirrored: any reader error skips the series
             errors[i] = str(e)
-    sizes = [infos[i].dim[0] * infos[i].dim[1] * infos[i].dim[2] for i in ok]
-    offs, total = [], 0
-    for s in sizes:
-        offs.append(total)
-        total += (s + 3) // 4 * 4
-    host = torch.empty(max(total, 4), dtype=torch.float32)  # plain host memory: only two planes per volume go to the device
+    # One plain host buffer for the chunk (virtual until touched: with ``midplane_only`` only the two decoded slices of a volume
+    # ever become resident).  The C header parser has already bounded every volume by the bytes its file really holds; should
+    # the chunk's buffer still not be obtainable, the largest volumes are dropped one at a time -- each with ITS error, so the
+    # driver skips that series (spider.py:131-133) instead of losing the whole chunk.
+    host = None
+    while host is None:
+        sizes = [infos[i].dim[0] * infos[i].dim[1] * infos[i].dim[2] for i in ok]
+        offs, total = [], 0
+        for s in sizes:
+            offs.append(total)
+            total += (s + 3) // 4 * 4
+        try:
+            host = torch.empty(max(total, 4), dtype=torch.float32)
+        except (RuntimeError, MemoryError) as e:
+            if not ok:
+                raise
+            worst = max(range(len(ok)), key=lambda k: sizes[k])
+            errors[ok[worst]] = f"cannot allocate {sizes[worst] * 4} bytes for {paths[ok[worst]]}: {e}"
+            del ok[worst]
     hv = host.numpy()
     m = len(ok)
     volumes: list[MedicalVolume | None] = [None] * n

@@ -36,6 +36,7 @@ class SlicePool:
     hw: torch.Tensor  # int32 [B,2] (device)
     shapes: list  # host copy [(h, w)]
     h2d_bytes: int = 0
+    pixel_kind: torch.Tensor | None = None  # int32 [B] (device) SVB_PIXEL_* per slice, None = all float32 (rotated crop mode only)
 
     @property
     def n(self) -> int:
@@ -73,11 +74,26 @@ class SlicePool:
         hw = torch.tensor(shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True)
         return cls(data, meta, hw, list(shapes), h2d_bytes=host.numel() * 4 + meta.numel() * 8 + hw.numel() * 4)
 
+    @staticmethod
+    def kind_of(dtype) -> int:
+        """SVB_PIXEL_* of a NumPy dtype: how ``cv2.warpAffine`` treats a slice of that type (cropping.py:292-301)."""
+        dt = np.dtype(dtype)
+        return {np.dtype(np.int16): _lib.PIXEL_INT16, np.dtype(np.uint16): _lib.PIXEL_UINT16,
+                np.dtype(np.uint8): _lib.PIXEL_UINT8}.get(dt, _lib.PIXEL_FLOAT)
+
+    def set_pixel_kinds(self, kinds) -> "SlicePool":
+        kinds = [int(k) for k in kinds]
+        assert len(kinds) == self.n
+        self.pixel_kind = torch.tensor(kinds, dtype=torch.int32).to(self.data.device) if any(kinds) else None
+        return self
+
     @classmethod
     def from_numpy(cls, slices, device="cuda:0") -> "SlicePool":
+        """Slices keep what the reference's rotated crop mode needs of their dtype (int16 / uint16 / uint8 slices are warped
+        in that type by OpenCV); the values themselves travel as float32 (io/__init__.py:26)."""
         _require_cuda(device)
         host, offs, shapes = cls.pin(slices)
-        return cls.from_pinned(host, offs, shapes, device)
+        return cls.from_pinned(host, offs, shapes, device).set_pixel_kinds([cls.kind_of(np.asarray(s).dtype) for s in slices])
 
     @classmethod
     def from_device_batch(cls, batch: torch.Tensor) -> "SlicePool":
@@ -206,7 +222,8 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
     if inv_affine is not None:
         assert inv_affine.dtype == torch.float64 and inv_affine.is_contiguous() and tuple(inv_affine.shape) == (N, 6)
     _lib.check(lib.svb_k3_crop_resample_rotated(pool.data.data_ptr(), pool.offs.data_ptr(), pool.hw.data_ptr(), slice_idx.data_ptr(),
-                                                xy.data_ptr(), delta_px.data_ptr(), _lib.ptr(inv_affine), N, int(max_box_hw[0]),
+                                                xy.data_ptr(), delta_px.data_ptr(), _lib.ptr(inv_affine),
+                                                _lib.ptr(pool.pixel_kind) if inv_affine is not None else None, N, int(max_box_hw[0]),
                                                 int(max_box_hw[1]), ch, cw, crops.data_ptr(), oh2, ow2, _lib.ptr(crops2),
                                                 _lib.ptr(geom), flags, wp, wn, _lib.current_stream()))
     return crops, crops2, geom
@@ -344,10 +361,11 @@ def stem_ln(u8: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, lnw: torch.Ten
     return out
 
 
-def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
+def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor, out: torch.Tensor | None = None):
     """x NHWC 16-bit [B,H,W,C]; taps fp32 [49,C] (tap-major) -> LayerNorm(dwconv7x7(x)+bias) [B,H,W,C]."""
     B, H, W, Cc = x.shape
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
     _lib.check(_lib.load().svb_dwconv_ln(x.data_ptr(), taps.data_ptr(), bias.data_ptr(), lnw.data_ptr(), lnb.data_ptr(),
                                          out.data_ptr(), B, H, W, Cc, _dt(x), _lib.current_stream()))
     return out

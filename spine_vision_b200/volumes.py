@@ -103,9 +103,11 @@ def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spaci
 _STAGE_FLIP = [0]
 
 
-def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integer_pixels=None):
+def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integer_pixels=None, pixel_kinds=None):
     """K0 over a batch: list of ``[z, y, x]`` arrays + ``image.GetSpacing()`` (+ ``GetDirection()``) per series ->
-    ``(ops.SlicePool of the middle isotropic sagittal slices, [(row_spacing, col_spacing)])``."""
+    ``(ops.SlicePool of the middle isotropic sagittal slices, [(row_spacing, col_spacing)])``.
+    ``pixel_kinds`` (SVB_PIXEL_* per series; default: from the arrays' dtypes) travels with the pool: the resampled slice
+    keeps the file's pixel type in the reference, which is what its rotated crop mode warps."""
     dev = ops._require_cuda(device)
     lib = _lib.load()
     B = len(volumes)
@@ -134,6 +136,7 @@ def midplane_resample(volumes, spacings, directions=None, device="cuda:0", integ
     data = torch.empty(max(out_total, 4), dtype=torch.float32, device=dev)
     pool = ops.SlicePool(data, torch.tensor(out_offs, dtype=torch.int64).to(dev), torch.tensor(shapes, dtype=torch.int32).reshape(-1, 2).to(dev),
                          list(shapes), h2d_bytes=host.numel() * 4)
+    pool.set_pixel_kinds(pixel_kinds if pixel_kinds is not None else [ops.SlicePool.kind_of(np.asarray(v).dtype) for v in volumes])
     if B:
         mh, mw = pool.max_hw
         need = lib.svb_k0_workspace_bytes(B, mh, mw)

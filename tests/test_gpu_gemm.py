@@ -49,6 +49,34 @@ def test_gemm_vs_torch(M, N, K, mode, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,N,K,mode", [(128, 128, 64, 2), (256, 512, 128, 0), (4096, 128, 512, 1), (3000, 2048, 512, 0), (3000, 512, 2048, 1),
+                                        (640, 256, 1024, 1), (777, 4096, 1024, 0), (128 * 300 + 5, 128, 512, 1), (1000, 384, 96, 0)])
+def test_gemm_half_footprint_vs_torch(M, N, K, mode, dtype, monkeypatch):
+    """The co-resident GEMM footprint (SVB_GEMM_HALF=1: BN = 128, 8 epilogue warps, <= 113.5 KB, 256 TMEM columns) computes the
+    same function as the full-SM kernel, bit for bit (same MMA order per output element)."""
+    g = torch.Generator(device="cpu").manual_seed(M * 5 + N * 3 + K + mode)
+    a = (torch.randn(M, K, generator=g)).to(DT[dtype]).to(dev())
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).to(DT[dtype]).to(dev())
+    bias = torch.randn(N, generator=g).to(dev())
+    gamma = (torch.rand(N, generator=g) + 0.1).to(dev())
+    resid = torch.randn(M, N, generator=g).to(DT[dtype]).to(dev())
+    outs = []
+    for half in ("0", "1"):
+        monkeypatch.setenv("SVB_GEMM_HALF", half)
+        if mode == 1:
+            out = resid.clone()
+            outs.append(ops.gemm(a, w, bias, 1, resid=out, gamma=gamma, out=out))
+        else:
+            outs.append(ops.gemm(a, w, bias, mode))
+    torch.cuda.synchronize()
+    want = _ref_gemm(a, w, bias, mode, resid, gamma)
+    err = (outs[1].float() - want).abs()
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0)
+    assert int((err > tol).sum()) == 0, f"max err {err.max().item():.4g}"
+    assert torch.equal(outs[0], outs[1]), "half-footprint GEMM differs from the full-SM GEMM"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024),
                                      (1, 15, 23, 1024), (1, 128, 128, 128), (2, 16, 16, 2048), (1, 9, 13, 2048),
                                      (2, 40, 24, 192), (2, 32, 32, 384), (2, 17, 32, 768), (3, 16, 16, 1536),  # + convnext_large widths

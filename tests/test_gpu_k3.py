@@ -141,6 +141,40 @@ def test_k3_rotated_matches_reference_golden_bit_exact():
     assert np.allclose(g["notebook_angles_2pt"], [4.96908734, 9.93817468])
 
 
+def test_k3_rotated_integer_slices_match_reference_golden_bit_exact():
+    """ADVICE r01 (svb_resize.cu:649): rotated crops of int16 / uint16 / uint8 slices.  The reference's cv2.warpAffine works in
+    the slice's pixel type (rounds back to int16 / uint16, fixed-point weights for uint8); K3 gets the type per slice
+    (SlicePool.pixel_kind) -- through the drop-in CropContext (dtype of the array it is given), the batched entry, and from a
+    volume on (K0 keeps the type)."""
+    from oracle.make_golden import INT_SERIES, INT_TYPES, int_slice
+
+    g = np.load(GOLDEN / "k3_rotated_int.npz")
+    dpx = cropping.mm_to_pixels((50, 20, 30, 30), (0.3, 0.3))
+    n = 0
+    for seed, h, w in INT_SERIES:
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        imgs = {name: int_slice(seed, h, w, name) for name in INT_TYPES}
+        for name, img in imgs.items():
+            want = g[f"crops_{seed}_{h}_{w}_{name}"]
+            for s in range(2):
+                locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                got = cropping.CropContext(img, locs, (128, 128), dpx, "rotated", device=dev()).crop_all(range(5))
+                for i in range(5):
+                    assert np.array_equal(got[i], want[s, i]), (seed, name, s, i)
+                    n += 1
+        # one mixed batch: the three types (and a float32 copy) side by side, per-slice kinds
+        names = list(INT_TYPES)
+        pool = ops.SlicePool.from_numpy([imgs[k] for k in names] + [imgs["int16"].astype(np.float32)], dev())
+        assert pool.pixel_kind is not None and pool.pixel_kind.cpu().tolist() == [1, 2, 3, 0]
+        coords = torch.from_numpy(np.stack([xy[0]] * 4)).to(dev())
+        crops, _, _ = pipeline.crop_levels(pool, coords, (50, 20, 30, 30), None, (128, 128), None, mode="rotated")
+        got = crops.cpu().numpy()
+        for k, name in enumerate(names):
+            assert np.array_equal(got[k], g[f"crops_{seed}_{h}_{w}_{name}"][0]), name
+        assert (got[3] != got[0]).any()  # the float32 copy of the int16 slice is NOT rounded back: a different crop
+    assert n == 60
+
+
 def test_k3_small_slices_match_reference_golden_bit_exact():
     """Slices SMALLER than the crop box (150 x 121, 90 x 300, exactly 200 x 234, ...) and a 7 x 500 strip, both crop modes,
     128 and 256 crops, corner centres (0, 0) and (0.99999, 0.99999): K3 against crops frozen from the reference's own

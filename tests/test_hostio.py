@@ -217,10 +217,25 @@ jobs = dataset.collect_spider_jobs(cfg, set())
 mine = jobs[rank::2]                                   # the split create_classification_dataset(rank, world_size) uses
 recs = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, l), j.patient_id, l, j.series_type, row)
         for j in mine for l, row in j.levels.items()]
-allr = dataset.gather_records(recs)
+allr, failures = dataset.gather_records(recs, failure="boom" if rank == 1 else None)
+assert failures == ["boom"]
 want = [dataset.make_record(j.source, dataset.output_filename(j.source, j.patient_id, j.series_type, l), j.patient_id, l, j.series_type, row)
         for part in (jobs[0::2], jobs[1::2]) for j in part for l, row in j.levels.items()]
 assert allr == want and len(allr) == 24, (len(allr), len(want))
+# the plan (resume scan + job list) is made on rank 0 and broadcast: rank 1 arrives late and, by then, sees a PNG another rank
+# "has already written" -- it must still get rank 0's job list, not a shorter one of its own (ADVICE r01, dataset.py:407)
+import time
+images = cfg.output_path / "images"
+images.mkdir(parents=True, exist_ok=True)
+if rank == 1:
+    time.sleep(1.0)
+    j0 = jobs[0]
+    (images / dataset.output_filename(j0.source, j0.patient_id, j0.series_type, 1)).write_bytes(b"x")
+recovered, planned = dataset.plan_dataset(cfg, images, rank, 2)
+assert recovered == [] and planned == jobs, (rank, len(planned), len(jobs))
+dist.barrier()
+if rank == 1:
+    assert len(dataset._plan_local(cfg, images)[1][0].levels) == len(jobs[0].levels) - 1   # what a per-rank scan would have seen
 dist.destroy_process_group()
 print("ok", rank)
 """
@@ -448,3 +463,26 @@ def test_dicom_series_midplane_only_feeds_k0_the_same_slab(tmp_path, n_slices):
     synthetic.write_dicom_series(tmp_path / "ax", arr, (0.7, 0.7, 4.0), np.eye(3).ravel(), series_uid="1.2.3.61", shuffle_seed=2)
     ax = hostio.read_medical_image(tmp_path / "ax", midplane_only=True)
     assert ax.meta["decoded_z"] == (0, n_slices) and np.array_equal(ax.array, hostio.read_medical_image(tmp_path / "ax").array)
+
+
+def test_corrupt_header_skips_the_series_not_the_chunk(tmp_path):
+    """ADVICE r01 (hostio.py:262): one corrupt header must cost one series (spider.py:131-133 except -> continue), never the chunk
+    or the process.  DimSize beyond what the file can hold (60000^3), a non-numeric / negative / NaN DimSize, and a compressed
+    stream 1000x too short for its header are format errors for THAT file; the good volume beside them still decodes."""
+    good = np.arange(3 * 8 * 8, dtype=np.int16).reshape(3, 8, 8)
+    synthetic.write_metaimage(tmp_path / "good.mha", good, (1.0, 1.0, 4.0))
+    blob = (tmp_path / "good.mha").read_bytes()
+    head, data = blob.split(b"ElementDataFile = LOCAL\n", 1)
+    cases = {"huge": b"DimSize = 60000 60000 60000", "neg": b"DimSize = -4 8 3", "nan": b"DimSize = nan 8 3",
+             "big": b"DimSize = 1e300 8 3", "more": b"DimSize = 4096 4096 64"}
+    for name, dim in cases.items():
+        lines = [dim if ln.startswith(b"DimSize") else ln for ln in head.split(b"\n")]
+        (tmp_path / f"{name}.mha").write_bytes(b"\n".join(lines) + b"ElementDataFile = LOCAL\n" + data)
+    paths = [tmp_path / "huge.mha", tmp_path / "good.mha"] + [tmp_path / f"{n}.mha" for n in ("neg", "nan", "big", "more")]
+    vols, errs = hostio.read_volumes(paths, n_threads=2)
+    assert vols[1] is not None and errs[1] is None and np.array_equal(vols[1].array, good.astype(np.float32))
+    for i in (0, 2, 3, 4, 5):
+        assert vols[i] is None and errs[i], (i, errs[i])
+    for p in paths[:1] + paths[2:]:
+        with pytest.raises(Exception):
+            hostio.read_medical_image(p)

@@ -319,3 +319,45 @@ def test_pillow_pass_order_for_slivers_is_pinned():
             u8 = rng.integers(0, 256, size=shape).astype(np.uint8)
             assert np.array_equal(vertical_first(u8, out_hw), pil(u8, out_hw)), shape
             assert not np.array_equal(fx.pillow_resize_u8(u8, out_hw), pil(u8, out_hw)), shape
+
+
+def test_rotated_crop_on_integer_slices_matches_reference_golden_and_opencv():
+    """the reference warps the slice in the FILE's pixel type (int16 for SPIDER .mha / MR DICOM), so cv2.warpAffine
+    rounds every warped value back to that type before normalize_to_uint8.  The restatement (fixedpoint.warp_affine) equals
+    cv2.warpAffine bit for bit for float32 / int16 / uint16 / uint8, and crop_region_rotated equals crops frozen from the
+    reference's own CropContext on integer-typed slices (tests/golden/k3_rotated_int.npz)."""
+    import cv2
+
+    from oracle.make_golden import INT_SERIES, INT_TYPES, int_slice
+
+    rng = np.random.default_rng(7)
+    for dt in (np.float32, np.int16, np.uint16, np.uint8):
+        for _ in range(6):
+            h, w = (int(v) for v in rng.integers(40, 160, 2))
+            if dt == np.float32:
+                img = (rng.random((h, w)) * 1500).astype(dt)
+            elif dt == np.int16:
+                img = rng.integers(-32768, 32768, (h, w)).astype(dt)
+            else:
+                img = rng.integers(0, np.iinfo(dt).max + 1, (h, w)).astype(dt)
+            m = cv2.getRotationMatrix2D((float(rng.integers(0, w)), float(rng.integers(0, h))), float(rng.uniform(-40, 40)), 1.0)
+            want = cv2.warpAffine(img, m, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REPLICATE)
+            got = fx.warp_affine(img, m)
+            assert got.dtype == want.dtype and np.array_equal(got, want), dt
+    g = np.load(GOLDEN / "k3_rotated_int.npz")
+    dpx = fx.mm_to_pixels((50, 20, 30, 30), (0.3, 0.3))
+    differs_from_float = 0
+    for seed, h, w in INT_SERIES:
+        xy = g[f"xy_{seed}_{h}_{w}"]
+        for name in INT_TYPES:
+            img = int_slice(seed, h, w, name)
+            want = g[f"crops_{seed}_{h}_{w}_{name}"]
+            for s in range(2):
+                locs = {i: (float(xy[s, i, 0]), float(xy[s, i, 1])) for i in range(5)}
+                ang = fx.rotation_angles(locs, (h, w), 1.0)
+                for i in range(5):
+                    got = fx.crop_region_rotated(img, locs[i][0], locs[i][1], (128, 128), dpx, ang[i])
+                    assert np.array_equal(got, want[s, i]), (seed, name, s, i)
+                    as_float = fx.crop_region_rotated(img.astype(np.float32), locs[i][0], locs[i][1], (128, 128), dpx, ang[i])
+                    differs_from_float += int((as_float != want[s, i]).sum())
+    assert differs_from_float > 0  # the float32 assumption of round 1 was observably wrong on integer sources
