@@ -6,10 +6,11 @@
 
 One step = one pass of the hot path over one batch of synthetic middle slices:
 K1 normalise+resize -> ConvNeXt-base localizer -> K3 crops (128^2 + 256^2).  Workload (N=1):
-BASELINE.json configs[1] -- 256 series of 1195x1195 fp32 (512 px @ 0.7 mm resampled to 0.3 mm),
-convnext_base random init, 5 levels, crop_delta_mm 50/20/30/30.  `value` is measured with the
-slices resident in HBM; `e2e` through the public API with pinned-host inputs (H2D inside the timed
-region) and the crops/coords read back to the host.  Prints ONE JSON line on rank 0.
+BASELINE.json configs[1] -- 256 series (15 x 512 x 512 fp32 @ 0.7 mm; middle plane resampled to 0.3 mm = 1195 x 1195),
+convnext_base random init, 5 levels, crop_delta_mm 50/20/30/30.  `value` is measured with the isotropic
+middle slices resident in HBM (K1 -> model -> K3); `e2e` through the public API from HOST buffers: the two
+source planes per series in pinned memory -> H2D -> K0+K1 (fused) -> model -> K3 -> crops/coords back to the
+host, every copy inside the timed region.  Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -30,9 +31,16 @@ CROP_SIZE = (128, 128)
 SECOND_SIZE = (256, 256)
 IMAGE_SIZE = (512, 512)
 SLICE_HW = (1195, 1195)
-TRAFFIC_JSON = "r01e_gemm_traffic.json"  # per-shape DRAM bytes of the GEMM launches (ncu --set full), see scripts/summarise_ncu_layers.py
-WORKLOAD = ("configs[1]: 256 synthetic sagittal middle slices 1195x1195 fp32 (512px@0.7mm -> 0.3mm iso) per GPU, "
+TRAFFIC_JSON = os.environ.get("SVB_TRAFFIC_JSON", "r02_gemm_traffic.json")  # per-shape DRAM bytes of the GEMM launches (ncu --set full), see scripts/summarise_ncu_layers.py
+WORKLOAD = ("configs[1]: 256 synthetic sagittal series per GPU (15x512x512 fp32 @0.7mm; middle plane at 0.3mm iso = 1195x1195), "
             "convnext_base random-init localizer @512x512, 5 IVD levels, crop_delta_mm 50/20/30/30, 128x128 crops + 256x256 classifier input")
+
+
+def workload_config(args):
+    """The SAME dict in both arms (the reference arm times a bounded sample of this workload; its sample is stated in
+    cpu_baseline.sample)."""
+    return {"workload": WORKLOAD, "series_per_gpu_per_step": args.batch, "micro_batch": args.micro_batch,
+            "l2": "inputs larger than L2 (1.46 GB of fp32 slices per step; ~1.8 GB of activations per micro-batch, two in flight)"}
 
 
 def parse():
@@ -42,10 +50,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="series per GPU per step")
-    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="GEMM operand type, fp32 accumulation (both 16-bit, same tensor-pipe rate; fp16 = the package default, it holds the 0.5 px gate on trained-like weights)")
     ap.add_argument("--micro-batch", type=int, default=64, help="images per pass through the network (two passes are in flight)")
     ap.add_argument("--stream-chunk", type=int, default=0, help="series per H2D chunk of the end-to-end path (0 = two micro-batches: both chains of the forward busy)")
-    ap.add_argument("--distinct", type=int, default=16, help="distinct synthetic slices (tiled to the batch)")
+    ap.add_argument("--distinct", type=int, default=0, help="distinct synthetic series (tiled to the batch); 0 = every series of the batch is distinct")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the informational stock-PyTorch-on-this-GPU leg")
     ap.add_argument("--ref-series", type=int, default=16, help="series per step of the CPU reference arm (--impl reference)")
     ap.add_argument("--cpu-baseline-series", type=int, default=32,
                     help="series per pass of the cpu_baseline leg (N=1, rank 0): BASELINE configs[0]'s batch of 32, one warm-up + two timed passes = about 12 s of CPU work")
@@ -93,12 +103,38 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "series/sec", "value": rate, "unit": "series/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "series_per_step": args.ref_series},
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args),
         "crops_per_sec": rate * 5,
         "cpu_baseline": {"value": rate, "unit": "series/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "series/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), file=JSON_OUT, flush=True)
+
+
+def gpu_eager_rate(dev: str, batch: int = 64, reps: int = 5):
+    """Informational ("the bar to beat = PyTorch eager / cuDNN / cuBLAS on the same B200"): the oracle's ConvNeXt-base
+    CoordinateRegressor as stock PyTorch runs it on this GPU -- channels_last, bf16 autocast, batch 64, model forward only (no
+    preprocessing, no crops).  Not the product path; nothing of this repo's kernels runs here."""
+    import torch
+
+    from oracle.convnext import make_model
+
+    m = make_model("base", seed=0).to(dev).eval().to(memory_format=torch.channels_last)
+    x = torch.randn(batch, 3, *IMAGE_SIZE, device=dev).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(3):
+            m(x)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            m(x)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del m, x
+    torch.cuda.empty_cache()
+    return batch / (ms * 1e-3), ms
 
 
 # ----------------------------------------------------------------------------- clocks sampler
@@ -154,11 +190,17 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device(dev))
 
     B = args.batch
-    # synthetic data (per-rank seeds: weak scaling, every rank owns its own series)
-    base = [synthetic.make_iso_slice(1000 * rank + s, *SLICE_HW) for s in range(min(args.distinct, B))]
-    slices = [base[i % len(base)] for i in range(B)]
-    series = pipeline.PinnedSeries(slices)  # pinned staging, filled once outside the timed region
-    host, offs, shapes = series.host, series.offs, series.shapes
+    # synthetic data (per-rank seeds: weak scaling, every rank owns its own series): source volumes of config 1; only the
+    # plan of each (the two planes around the middle Left-Right index + the K0 descriptor) is kept on the host
+    from concurrent.futures import ThreadPoolExecutor
+
+    from spine_vision_b200 import volumes as svb_volumes
+
+    n_distinct = min(args.distinct or B, B)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        base = list(ex.map(lambda sd: svb_volumes.plan_midplane(*synthetic.make_volume(sd)), [1000 * rank + k for k in range(n_distinct)]))
+    series = svb_volumes.PinnedVolumes.from_plans([base[i % n_distinct] for i in range(B)])  # pinned staging, filled once outside the timed region
+    assert all(tuple(hw) == SLICE_HW for hw in series.shapes)
     model = LocalizationModel(synthetic.random_state_dict("base", seed=0), dev, dtype=args.dtype, micro_batch=args.micro_batch)
     n_crops = B * 5
     streamer = pipeline.StreamedLocalizer(model, dev, CROP_DELTA_MM, CROP_SIZE, IMAGE_SIZE, SECOND_SIZE, chunk=args.stream_chunk or 2 * args.micro_batch)
@@ -205,7 +247,7 @@ def run_b200(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    pool = ops.SlicePool.from_pinned(host, offs, shapes, dev)
+    pool = series.resident_pool(dev)  # the isotropic middle slices of the batch, resident in HBM (K0 run once, outside the timed region)
     torch.cuda.synchronize()
 
     def resident_step():
@@ -279,9 +321,13 @@ def run_b200(args):
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
+        traffic_file = TRAFFIC_JSON if (ROOT / "profiles" / TRAFFIC_JSON).exists() else "r01e_gemm_traffic.json"
         try:  # DRAM bytes of the GEMM launches of one step, from the committed ncu --set full capture of the same kernels
-            tj = json.loads((ROOT / "profiles" / TRAFFIC_JSON).read_text())
-            traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
+            tj = json.loads((ROOT / "profiles" / traffic_file).read_text())
+            if "gemm_dram_bytes_per_micro_batch" in tj:
+                traffic = float(tj["gemm_dram_bytes_per_micro_batch"]) * B / float(tj["micro_batch"])
+            else:
+                traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
         except Exception:
             pass
         # algorithmic HBM bytes of the GEMMs of one step (A + W + out, + the residual read of fc2), 16-bit operands: what `traffic`
@@ -303,40 +349,57 @@ def run_b200(args):
         k1_bytes = B * (SLICE_HW[0] * SLICE_HW[1] * 4 + IMAGE_SIZE[0] * IMAGE_SIZE[1])
         k3_bytes = n_crops * (234 * 200 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])
         k4_bytes = k4_p * SECOND_SIZE[0] * SECOND_SIZE[1] * (2 + 3 * 4)  # two uint8 planes in, three float32 planes out
+        model_ms = sum(times.get(k, 0.0) for k in ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")) / args.steps
+        dw_gbs = dw_bytes / (dw_ms * 1e-3) / 1e9 if dw_ms else None
+        k1_gbs = k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None
+        k3_gbs = k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None
+        ceiling = peak_tf * 1e12 / (gemm_flops / B)  # series/s if the step were nothing but its GEMMs at the measured tensor peak
         line = {
             "metric": "series/sec", "value": value, "unit": "series/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
-            "data": f"synthetic ({len(base)} distinct seeded slices tiled to {B}; random-init convnext_base)",
-            "config": {"workload": WORKLOAD, "series_per_gpu_per_step": B, "micro_batch": args.micro_batch,
-                       "l2": "inputs larger than L2 (1.46 GB of fp32 slices per step; ~1.8 GB of activations per micro-batch, two in flight)"},
+            "data": f"synthetic ({n_distinct} distinct seeded series per rank; random-init convnext_base)",
+            "config": workload_config(args),
             "crops_per_sec": value * 5,
             "clocks": sampler.summary(),
-            "e2e": {"value": e2e, "unit": "series/s", "h2d_bytes_per_step": int(series.nbytes + B * 16 + n_crops * 16),
+            "e2e": {"value": e2e, "unit": "series/s", "h2d_bytes_per_step": int(series.nbytes),
                     "d2h_bytes_per_step": int(B * 5 * (2 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])),
                     "ms_per_step": ms_e2e / args.steps,
-                    "api": "pipeline.StreamedLocalizer.run_async(PinnedSeries).result(): chunked H2D on a copy stream overlapped with K1/model/K3, "
-                           "D2H on a third stream; batch k+1 is started before batch k is collected (two output slots)"},
+                    "api": "pipeline.StreamedLocalizer.run_async(volumes.PinnedVolumes).result(): per series the two SOURCE planes (15x512x512 volume, "
+                           "planes 7 and 8) + one K0 descriptor row go H2D in chunks on a copy stream, overlapped with K0+K1 (fused) / model / K3 "
+                           "of the previous chunk; D2H on a third stream; batch k+1 is started before batch k is collected (two output slots); "
+                           "index tables (offsets, shapes, crop deltas: 44 bytes per series) are uploaded once per batch geometry and reused"},
             "gpu_launches": int(gpu_launches),
             "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{TRAFFIC_JSON} (ncu --set full, per-shape dram bytes x launches)",
+                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{traffic_file} (ncu --set full, per-shape dram bytes x launches)",
                          "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
-                         "timing": "CUDA event pair around every launch, separate pass over the same steps"},
+                         "timing": "CUDA event pair around every launch, separate pass over the same steps",
+                         "whole_step_frac_of_tensor_ceiling": value / world / ceiling, "tensor_ceiling_series_per_s": ceiling},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
                                    "k3_crop_resample": k3_ms / args.steps},
             "fp32_kernels": {"dwconv_ln": {"flops_per_step": dw_flops, "achieved_tflops": dw_flops / (dw_ms * 1e-3) / 1e12 if dw_ms else None,
                                            "fp32_peak_tflops_nominal": 72.0, "hbm_bytes_per_step": dw_bytes,
-                                           "achieved_gbs": dw_bytes / (dw_ms * 1e-3) / 1e9 if dw_ms else None,
+                                           "achieved_gbs": dw_gbs, "hbm_peak_gbs": hbm, "frac_of_hbm": dw_gbs / hbm if dw_gbs else None,
+                                           "frac_of_fp32_nominal": dw_flops / (dw_ms * 1e-3) / 1e12 / 72.0 if dw_ms else None,
                                            "note": "FP32-pipe bound (49 FMA per output): FFMA2 issues at ~2.4 clk on B200, measured ceiling of the loop ~78 of 128 FMA/clk/SM (scripts/ubench/convloop2.cu)"}},
             "hbm_kernels": {
-                "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None, "peak_gbs": hbm},
-                "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None, "peak_gbs": hbm},
+                "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_gbs, "peak_gbs": hbm, "frac": k1_gbs / hbm if k1_gbs else None},
+                "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_gbs, "peak_gbs": hbm, "frac": k3_gbs / hbm if k3_gbs else None},
                 "k4_classifier_input": {"bytes_per_step": k4_bytes, "ms_per_step": k4_ms / args.steps, "samples": k4_p,
                                         "achieved_gbs": k4_bytes / (k4_ms / args.steps * 1e-3) / 1e9 if k4_ms else None, "peak_gbs": hbm,
                                         "frac": k4_bytes / (k4_ms / args.steps * 1e-3) / 1e9 / hbm if k4_ms else None,
                                         "note": "outside the series/s timed region (its consumer is the classifier's data loader)"},
             },
         }
+        if world == 1 and not args.no_eager_baseline:
+            try:
+                rate, ms = gpu_eager_rate(dev)
+                line["gpu_eager_baseline"] = {"value": rate, "unit": "img/s (model forward only)", "ms_per_64": ms,
+                                              "ours_img_per_s_model_only": B / (model_ms * 1e-3) if model_ms else None,
+                                              "what": "oracle ConvNeXt-base CoordinateRegressor, stock PyTorch eager on this GPU: channels_last, bf16 autocast, batch 64 "
+                                                      "(cuDNN depthwise conv + ATen LayerNorm + cuBLAS GEMMs); informational, SURVEY 2b's stated bar"}
+            except Exception as e:  # noqa: BLE001 -- informational leg: never take the bench line down
+                line["gpu_eager_baseline"] = {"unavailable": f"{type(e).__name__}: {e}"}
         if world == 1 and not args.no_cpu_baseline:
             rate, mean, cores = cpu_reference_rate(args.cpu_baseline_series, 2, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "series/s", "cores": cores, "kind": "port",

@@ -92,6 +92,17 @@ size_t svb_k0_workspace_bytes(int B, int max_out_h, int max_out_w);
 int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
                              int max_out_w, float* d_out, void* d_ws, size_t ws_bytes, void* stream);
 
+/* K0 + K1 in one call ("fuse into K1"): source planes -> isotropic middle planes (kept: K3 cuts its crops from
+ * them) + the uint8 model planes.  Replaces resample_to_isotropic + extract_middle_slice (cropping.py:37-79) AND
+ * normalize_to_uint8 + Resize of predict_ivd_locations (io/__init__.py:15-30, cropping.py:463-472) for a batch.  K0 accumulates
+ * every plane's min / max while it writes it, so K1 makes no min/max pass; the batch is walked in groups small enough for the
+ * resize launch to read the planes back from L2.  d_offs / d_hw describe the planes in d_slices (= desc.out_off, out_h, out_w). */
+size_t svb_k01_workspace_bytes(int B, int max_out_h, int max_out_w, int out_h, int out_w);
+int svb_k01_midplane_normalize_resize(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
+                                      int max_out_w, float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                      int out_h, int out_w, uint8_t* d_out_u8, float* d_minmax, void* d_ws,
+                                      size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K1 -- fused min-max normalise + antialiased bilinear resize to uint8.
  * Replaces, per slice: normalize_to_uint8 (spine_vision/io/__init__.py:15-30) followed by

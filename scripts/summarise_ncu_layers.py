@@ -10,6 +10,7 @@ import sys
 from pathlib import Path
 
 rep, tag = sys.argv[1], sys.argv[2]
+MB = int(sys.argv[3]) if len(sys.argv) > 3 else 64  # micro-batch the capture was taken at (scripts/prof_layers.py MB 0)
 ROOT = Path(__file__).resolve().parent.parent
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
 rows = list(csv.reader(raw.splitlines()))
@@ -52,10 +53,10 @@ for r, n, k in zip(gemms, names, launches):
     b = mb(r, "dram__bytes_read.sum") + mb(r, "dram__bytes_write.sum")
     per.append({"layer": n, "dram_bytes": b, "time_us": col(r, "gpu__time_duration.sum"),
                 "tensor_pipe_active_pct": col(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
-                "launches_per_micro_batch": k})
+                "launches_per_micro_batch": k, "dram_read_bytes": mb(r, "dram__bytes_read.sum"), "dram_write_bytes": mb(r, "dram__bytes_write.sum")})
     total += b * k
-js = {"source": f"ncu --set full --clock-control none, scripts/prof_layers.py 37 0 (micro-batch 37 shapes), profiles/{tag}_ncu_full_layers.csv",
-      "per_launch": per, "gemm_dram_bytes_per_micro_batch_37": total,
+js = {"source": f"ncu --set full --clock-control none, scripts/prof_layers.py {MB} 0 (micro-batch {MB} shapes), profiles/{tag}_ncu_full_layers.csv",
+      "per_launch": per, "micro_batch": MB, "gemm_dram_bytes_per_micro_batch": total,
       "note": "the 3 downsample GEMMs of a forward (0.6 % of the flops) are not in the capture"}
 (ROOT / "profiles" / f"{tag}_gemm_traffic.json").write_text(json.dumps(js, indent=1))
-print("wrote", ROOT / "profiles" / f"{tag}_gemm_traffic.json", f"{total / 1e9:.2f} GB per micro-batch of 37")
+print("wrote", ROOT / "profiles" / f"{tag}_gemm_traffic.json", f"{total / 1e9:.2f} GB per micro-batch of {MB}")

@@ -22,6 +22,7 @@ KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
 EXPORTS = (
     "svb_version", "svb_last_error", "svb_device_check", "svb_launch_count",
     "svb_k0_workspace_bytes", "svb_k0_midplane_resample",
+    "svb_k01_workspace_bytes", "svb_k01_midplane_normalize_resize",
     "svb_k1_workspace_bytes", "svb_k1_normalize_resize", "svb_normalize_u8_workspace_bytes", "svb_normalize_u8",
     "svb_k3_workspace_bytes", "svb_k3_crop_resample", "svb_k3_crop_resample_rotated",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward",
@@ -89,6 +90,10 @@ def load() -> C.CDLL:
     lib.svb_k0_workspace_bytes.argtypes = [i32] * 3
     lib.svb_k0_midplane_resample.restype = C.c_int
     lib.svb_k0_midplane_resample.argtypes = [vp, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.svb_k01_workspace_bytes.restype = sz
+    lib.svb_k01_workspace_bytes.argtypes = [i32] * 5
+    lib.svb_k01_midplane_normalize_resize.restype = C.c_int
+    lib.svb_k01_midplane_normalize_resize.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, i32, i32, vp, vp, vp, sz, vp]
     lib.svb_k1_workspace_bytes.restype = sz
     lib.svb_k1_workspace_bytes.argtypes = [i32] * 5
     lib.svb_k1_normalize_resize.restype = C.c_int

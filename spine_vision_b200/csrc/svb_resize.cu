@@ -102,7 +102,7 @@ __global__ void k1_coeff_kernel(const int32_t* __restrict__ hw, int out_h, int o
     const int b = blockIdx.z;
     const int axis = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (axis == 0 && i == 0) {
+    if (axis == 0 && i == 0 && keys != nullptr) {
         keys[2 * b + 0] = 0xFFFFFFFFu;  // min key
         keys[2 * b + 1] = 0u;           // max key
     }
@@ -407,31 +407,51 @@ extern "C" size_t svb_k1_workspace_bytes(int B, int max_h, int max_w, int out_h,
     return k1_layout(B, max_h, max_w, out_h, out_w).total;
 }
 
-extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B,
-                                       int max_h, int max_w, int out_h, int out_w, uint8_t* d_out_u8,
-                                       float* d_minmax, void* d_ws, size_t ws_bytes, void* stream_) {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (int rc = check_device_sm100()) return rc;
-    SVB_REQUIRE(B >= 0 && max_h > 0 && max_w > 0 && out_h > 0 && out_w > 0, SVB_ERR_INVALID_ARG,
-                "k1: bad sizes B=%d max_hw=(%d,%d) out=(%d,%d)", B, max_h, max_w, out_h, out_w);
-    if (B == 0) return SVB_OK;
-    SVB_REQUIRE(d_slices && d_offs && d_hw && d_out_u8 && d_ws, SVB_ERR_INVALID_ARG, "k1: null pointer argument");
+namespace svb {
+
+// launch plan of the K1 pair for one batch: validated sizes, workspace pointers, rows per CTA
+struct K1Plan {
+    K1Layout L;
+    int R = 32, src_cap = 0, rows_cap = 0, mm_blocks = 1, group = 1;
+    size_t smem_bytes = 0;
+    uint32_t* keys = nullptr;
+    int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr;
+};
+
+// Slices per (min/max, resize) launch pair -- or per (K0, resize) pair of the fused entry.  The second launch re-reads what the
+// first one read (or wrote); a group of at most ~48 MB of fp32 slices is still in the 126 MB L2 then, so the slice crosses
+// HBM once instead of twice (round 1 ran each pass over the whole batch: 1.46 GB read twice, L2 hit rate 12.6 %).
+// SVB_K1_GROUP=n forces n (0 = the whole batch, the round-1 schedule) for A/B runs.
+static int k1_group_size(int B, int max_h, int max_w) {
+    const char* e = getenv("SVB_K1_GROUP");  // read on every call (tests walk the settings)
+    const int forced = (e && e[0]) ? atoi(e) : -1;
+    if (forced == 0) return B;
+    if (forced > 0) return forced < B ? forced : B;
+    const size_t slice_bytes = (size_t)max_h * max_w * 4;
+    size_t g = ((size_t)48 << 20) / (slice_bytes ? slice_bytes : 1);
+    if (g < 1) g = 1;
+    return g < (size_t)B ? (int)g : B;
+}
+
+// validates, sizes the resize kernel, builds the Pillow coefficient tables (one launch); `reset_keys`: the same launch
+// resets the per-slice min / max keys
+static int k1_prepare(const int32_t* d_hw, int B, int max_h, int max_w, int out_h, int out_w, void* d_ws, size_t ws_bytes,
+                      bool reset_keys, cudaStream_t stream, K1Plan* P) {
     SVB_REQUIRE(out_w % 4 == 0, SVB_ERR_INVALID_ARG, "k1: out_w (%d) must be a multiple of 4", out_w);
-    const K1Layout L = k1_layout(B, max_h, max_w, out_h, out_w);
+    P->L = k1_layout(B, max_h, max_w, out_h, out_w);
+    const K1Layout& L = P->L;
     SVB_REQUIRE(ws_bytes >= L.total, SVB_ERR_WORKSPACE_TOO_SMALL, "k1: workspace %zu < %zu bytes", ws_bytes, L.total);
     uint8_t* ws = static_cast<uint8_t*>(d_ws);
-    uint32_t* keys = reinterpret_cast<uint32_t*>(ws + L.keys);
-    int* hb = reinterpret_cast<int*>(ws + L.hb);
-    int* hk = reinterpret_cast<int*>(ws + L.hk);
-    int* vb = reinterpret_cast<int*>(ws + L.vb);
-    int* vk = reinterpret_cast<int*>(ws + L.vk);
-
+    P->keys = reinterpret_cast<uint32_t*>(ws + L.keys);
+    P->hb = reinterpret_cast<int*>(ws + L.hb);
+    P->hk = reinterpret_cast<int*>(ws + L.hk);
+    P->vb = reinterpret_cast<int*>(ws + L.vb);
+    P->vk = reinterpret_cast<int*>(ws + L.vk);
     {
         dim3 grid(ceil_div(out_w > out_h ? out_w : out_h, 128), 2, B);
-        k1_coeff_kernel<<<grid, 128, 0, stream>>>(d_hw, out_h, out_w, L.ksh, L.ksw, keys, hb, hk, vb, vk);
+        k1_coeff_kernel<<<grid, 128, 0, stream>>>(d_hw, out_h, out_w, L.ksh, L.ksw, reset_keys ? P->keys : nullptr, P->hb, P->hk, P->vb, P->vk);
         SVB_LAUNCHED();
     }
-
     // rows per CTA: largest power of two whose staging fits ~100 KB (2 CTAs / SM), else smaller
     int R = 32;
     size_t smem_bytes = 0;
@@ -449,27 +469,48 @@ extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_o
                 "k1: a %dx%d slice needs %zu bytes of shared memory per output row (limit 232448)", max_h, max_w,
                 smem_bytes);
     SVB_CUDA_OK(cudaFuncSetAttribute(k1_resize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-    const int rows_cap_al = (int)(align_up((size_t)rows_cap * out_w, 16) / out_w);  // keep s_hk 16B aligned
-    (void)rows_cap_al;
-
-    // Two passes over the batch, each ONE launch (whole waves instead of many 1-wave launches): min/max of
-    // every slice, then normalise + resize.  The second pass re-reads the fp32 data from HBM; it is
-    // instruction-bound (fixed-point taps), so the re-read hides under the arithmetic.
+    P->R = R; P->src_cap = src_cap; P->rows_cap = rows_cap; P->smem_bytes = smem_bytes;
     const size_t slice_bytes = (size_t)max_h * max_w * 4;
     int mm_blocks = (int)ceil_div<size_t>(slice_bytes, (size_t)512 * 16 * 8);  // ~8 float4 per thread
-    if (mm_blocks < 1) mm_blocks = 1;
-    if (mm_blocks > 1024) mm_blocks = 1024;
-    for (int b0 = 0; b0 < B; b0 += 65535) {
-        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
-        k1_minmax_kernel<<<dim3(mm_blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, keys);
-        SVB_LAUNCHED();
-    }
-    for (int b0 = 0; b0 < B; b0 += 65535) {
-        const int nb = (B - b0) < 65535 ? (B - b0) : 65535;
-        k1_resize_kernel<<<dim3(ceil_div(out_h, R), nb), 512, smem_bytes, stream>>>(
-            d_slices, d_offs, d_hw, b0, out_h, out_w, R, L.ksh, L.ksw, src_cap, rows_cap, keys, hb, hk, vb, vk,
-            d_out_u8, d_minmax);
-        SVB_LAUNCHED();
+    P->mm_blocks = mm_blocks < 1 ? 1 : (mm_blocks > 1024 ? 1024 : mm_blocks);
+    P->group = k1_group_size(B, max_h, max_w);
+    if (P->group > 65535) P->group = 65535;
+    return SVB_OK;
+}
+static int k1_minmax_group(const K1Plan& P, const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int b0, int nb,
+                           cudaStream_t stream) {
+    k1_minmax_kernel<<<dim3(P.mm_blocks, nb), 512, 0, stream>>>(d_slices, d_offs, d_hw, b0, P.keys);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+static int k1_resize_group(const K1Plan& P, const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int b0, int nb,
+                           int out_h, int out_w, uint8_t* d_out_u8, float* d_minmax, cudaStream_t stream) {
+    k1_resize_kernel<<<dim3(ceil_div(out_h, P.R), nb), 512, P.smem_bytes, stream>>>(
+        d_slices, d_offs, d_hw, b0, out_h, out_w, P.R, P.L.ksh, P.L.ksw, P.src_cap, P.rows_cap, P.keys, P.hb, P.hk, P.vb, P.vk,
+        d_out_u8, d_minmax);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+
+}  // namespace svb
+
+extern "C" int svb_k1_normalize_resize(const float* d_slices, const int64_t* d_offs, const int32_t* d_hw, int B,
+                                       int max_h, int max_w, int out_h, int out_w, uint8_t* d_out_u8,
+                                       float* d_minmax, void* d_ws, size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(B >= 0 && max_h > 0 && max_w > 0 && out_h > 0 && out_w > 0, SVB_ERR_INVALID_ARG,
+                "k1: bad sizes B=%d max_hw=(%d,%d) out=(%d,%d)", B, max_h, max_w, out_h, out_w);
+    if (B == 0) return SVB_OK;
+    SVB_REQUIRE(d_slices && d_offs && d_hw && d_out_u8 && d_ws, SVB_ERR_INVALID_ARG, "k1: null pointer argument");
+    K1Plan P;
+    if (int rc = k1_prepare(d_hw, B, max_h, max_w, out_h, out_w, d_ws, ws_bytes, true, stream, &P)) return rc;
+    // Per group of slices: min/max of every slice (the normalisation needs the global extrema first), then normalise + resize.
+    // The second launch re-reads the group while it is still in L2.
+    for (int b0 = 0; b0 < B; b0 += P.group) {
+        const int nb = (B - b0) < P.group ? (B - b0) : P.group;
+        if (int rc = k1_minmax_group(P, d_slices, d_offs, d_hw, b0, nb, stream)) return rc;
+        if (int rc = k1_resize_group(P, d_slices, d_offs, d_hw, b0, nb, out_h, out_w, d_out_u8, d_minmax, stream)) return rc;
     }
     return SVB_OK;
 }
@@ -1119,7 +1160,7 @@ __global__ void k0_table_kernel(const svb_k0_series* __restrict__ desc, int max_
 // grid (tiles, B): one thread per output pixel
 __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restrict__ vol, const svb_k0_series* __restrict__ desc,
                                                           int max_h, int max_w, const K0Tap* __restrict__ taps,
-                                                          float* __restrict__ out) {
+                                                          float* __restrict__ out, uint32_t* __restrict__ keys) {
     const svb_k0_series d = desc[blockIdx.y];
     const int stride = max(max_h, max_w);
     const K0Tap* rt = taps + ((size_t)blockIdx.y * 2 + 0) * stride;
@@ -1131,6 +1172,7 @@ __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restric
     const long long s_col = d.ax_col == 0 ? sx : (d.ax_col == 1 ? sy : sz);
     const long long s_fix = d.ax_fix == 0 ? sx : (d.ax_fix == 1 ? sy : sz);
     const long long n = (long long)d.out_h * d.out_w;
+    float mn = INFINITY, mx = -INFINITY;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         const int r = (int)(p / d.out_w), c = (int)(p - (long long)r * d.out_w);
         const K0Tap tr = rt[r], tc = ct[c];
@@ -1156,6 +1198,28 @@ __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restric
             res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
         }
         o[p] = res;
+        mn = fminf(mn, res);
+        mx = fmaxf(mx, res);
+    }
+    if (keys != nullptr) {
+        // the plane's min / max while it is being written (same fminf / fmaxf reduction as k1_minmax_kernel, so K1 can skip
+        // its own pass over the plane): warp, then CTA, then one ordered-key atomic pair per CTA
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        __shared__ float smn[8], smx[8];
+        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
+        __syncthreads();
+        if (wid == 0) {
+            mn = lane < (int)(blockDim.x >> 5) ? smn[lane] : INFINITY;
+            mx = lane < (int)(blockDim.x >> 5) ? smx[lane] : -INFINITY;
+            mn = warp_min(mn);
+            mx = warp_max(mx);
+            if (lane == 0 && (long long)blockIdx.x * blockDim.x < n) {
+                atomicMin(&keys[2 * blockIdx.y + 0], float_key(mn));
+                atomicMax(&keys[2 * blockIdx.y + 1], float_key(mx));
+            }
+        }
     }
 }
 
@@ -1165,6 +1229,27 @@ extern "C" size_t svb_k0_workspace_bytes(int B, int max_out_h, int max_out_w) {
     if (B <= 0 || max_out_h <= 0 || max_out_w <= 0) return 0;
     return (size_t)B * 2 * (size_t)(max_out_h > max_out_w ? max_out_h : max_out_w) * sizeof(svb::K0Tap) + 256;
 }
+
+namespace svb {
+static int k0_tables(const svb_k0_series* d_desc, int B, int max_out_h, int max_out_w, K0Tap* taps, cudaStream_t stream) {
+    const int m = max_out_h > max_out_w ? max_out_h : max_out_w;
+    k0_table_kernel<<<dim3(ceil_div(m, 128), 2, B), 128, 0, stream>>>(d_desc, max_out_h, max_out_w, taps);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+// series [b0, b0 + nb) of the batch the tables were built for
+static int k0_planes(const float* d_volumes, const svb_k0_series* d_desc, int b0, int nb, int max_out_h, int max_out_w,
+                     const K0Tap* taps, float* d_out, uint32_t* keys, cudaStream_t stream) {
+    long long tiles = ceil_div<long long>((long long)max_out_h * max_out_w, 256 * 4);
+    if (tiles > 4096) tiles = 4096;
+    const size_t stride = (size_t)(max_out_h > max_out_w ? max_out_h : max_out_w);
+    k0_midplane_kernel<<<dim3((unsigned)tiles, nb), 256, 0, stream>>>(d_volumes, d_desc + b0, max_out_h, max_out_w,
+                                                                      taps + (size_t)b0 * 2 * stride, d_out,
+                                                                      keys ? keys + 2 * (size_t)b0 : nullptr);
+    SVB_LAUNCHED();
+    return SVB_OK;
+}
+}  // namespace svb
 
 extern "C" int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
                                         int max_out_w, float* d_out, void* d_ws, size_t ws_bytes, void* stream_) {
@@ -1176,12 +1261,40 @@ extern "C" int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_ser
     SVB_REQUIRE(ws_bytes >= svb_k0_workspace_bytes(B, max_out_h, max_out_w), SVB_ERR_WORKSPACE_TOO_SMALL, "k0: workspace too small");
     SVB_REQUIRE(B <= 65535, SVB_ERR_INVALID_ARG, "k0: at most 65535 series per call");
     K0Tap* taps = reinterpret_cast<K0Tap*>((reinterpret_cast<uintptr_t>(d_ws) + 15) & ~uintptr_t(15));
-    const int m = max_out_h > max_out_w ? max_out_h : max_out_w;
-    k0_table_kernel<<<dim3(ceil_div(m, 128), 2, B), 128, 0, stream>>>(d_desc, max_out_h, max_out_w, taps);
-    SVB_LAUNCHED();
-    long long tiles = ceil_div<long long>((long long)max_out_h * max_out_w, 256 * 4);
-    if (tiles > 4096) tiles = 4096;
-    k0_midplane_kernel<<<dim3((unsigned)tiles, B), 256, 0, stream>>>(d_volumes, d_desc, max_out_h, max_out_w, taps, d_out);
-    SVB_LAUNCHED();
+    if (int rc = k0_tables(d_desc, B, max_out_h, max_out_w, taps, stream)) return rc;
+    return k0_planes(d_volumes, d_desc, 0, B, max_out_h, max_out_w, taps, d_out, nullptr, stream);
+}
+
+// ============================================================================ K0 + K1 in one call
+extern "C" size_t svb_k01_workspace_bytes(int B, int max_out_h, int max_out_w, int out_h, int out_w) {
+    if (B <= 0 || max_out_h <= 0 || max_out_w <= 0 || out_h <= 0 || out_w <= 0) return 0;
+    return align_up(k1_layout(B, max_out_h, max_out_w, out_h, out_w).total, 256) + svb_k0_workspace_bytes(B, max_out_h, max_out_w);
+}
+
+extern "C" int svb_k01_midplane_normalize_resize(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
+                                                 int max_out_w, float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
+                                                 int out_h, int out_w, uint8_t* d_out_u8, float* d_minmax, void* d_ws,
+                                                 size_t ws_bytes, void* stream_) {
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(B >= 0 && max_out_h > 0 && max_out_w > 0 && out_h > 0 && out_w > 0, SVB_ERR_INVALID_ARG,
+                "k01: bad sizes B=%d iso=(%d,%d) out=(%d,%d)", B, max_out_h, max_out_w, out_h, out_w);
+    if (B == 0) return SVB_OK;
+    SVB_REQUIRE(d_volumes && d_desc && d_slices && d_offs && d_hw && d_out_u8 && d_ws, SVB_ERR_INVALID_ARG, "k01: null pointer argument");
+    SVB_REQUIRE(B <= 65535, SVB_ERR_INVALID_ARG, "k01: at most 65535 series per call");
+    SVB_REQUIRE(ws_bytes >= svb_k01_workspace_bytes(B, max_out_h, max_out_w, out_h, out_w), SVB_ERR_WORKSPACE_TOO_SMALL,
+                "k01: workspace %zu < %zu bytes", ws_bytes, svb_k01_workspace_bytes(B, max_out_h, max_out_w, out_h, out_w));
+    K1Plan P;
+    const size_t k1_bytes = align_up(k1_layout(B, max_out_h, max_out_w, out_h, out_w).total, 256);
+    if (int rc = k1_prepare(d_hw, B, max_out_h, max_out_w, out_h, out_w, d_ws, k1_bytes, true, stream, &P)) return rc;
+    K0Tap* taps = reinterpret_cast<K0Tap*>((reinterpret_cast<uintptr_t>(static_cast<uint8_t*>(d_ws) + k1_bytes) + 15) & ~uintptr_t(15));
+    if (int rc = k0_tables(d_desc, B, max_out_h, max_out_w, taps, stream)) return rc;
+    // Per group: K0 writes the group's isotropic planes AND their min / max; the resize launch that follows normalises with
+    // those extrema and reads the planes back while they are still in L2.  No min/max pass, no second trip through HBM.
+    for (int b0 = 0; b0 < B; b0 += P.group) {
+        const int nb = (B - b0) < P.group ? (B - b0) : P.group;
+        if (int rc = k0_planes(d_volumes, d_desc, b0, nb, max_out_h, max_out_w, taps, d_slices, P.keys, stream)) return rc;
+        if (int rc = k1_resize_group(P, d_slices, d_offs, d_hw, b0, nb, out_h, out_w, d_out_u8, d_minmax, stream)) return rc;
+    }
     return SVB_OK;
 }

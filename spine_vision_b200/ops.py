@@ -167,6 +167,45 @@ def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | Non
     return (out, minmax) if return_minmax else out
 
 
+def midplane_normalize_resize(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: SlicePool, out_hw=(512, 512),
+                              out: torch.Tensor | None = None, return_minmax: bool = False):
+    """K0 + K1 in one call (``svb_k01_midplane_normalize_resize``): ``vols_d`` float32 source planes and ``desc_d`` the
+    ``svb_k0_series`` rows (both on the device, see ``volumes.PinnedVolumes``); ``pool`` is the EMPTY destination pool of the
+    isotropic middle planes (offsets / shapes from the plans), filled here and kept for K3.  Returns the uint8 model planes."""
+    lib = _lib.load()
+    dev = pool.data.device
+    B = pool.n
+    oh, ow = int(out_hw[0]), int(out_hw[1])
+    if out is None:
+        out = torch.empty((B, oh, ow), dtype=torch.uint8, device=dev)
+    minmax = torch.empty((B, 2), dtype=torch.float32, device=dev) if return_minmax else None
+    if B == 0:
+        return (out, minmax) if return_minmax else out
+    assert out.is_cuda and out.dtype == torch.uint8 and out.is_contiguous() and out.numel() == B * oh * ow
+    mh, mw = pool.max_hw
+    need = lib.svb_k01_workspace_bytes(B, mh, mw, oh, ow)
+    ws = _Workspace.get("k01", need, dev)
+    wp, wn = _aligned_ptr(ws, 256)
+    _lib.check(lib.svb_k01_midplane_normalize_resize(vols_d.data_ptr(), desc_d.data_ptr(), B, mh, mw, pool.data.data_ptr(),
+                                                     pool.offs.data_ptr(), pool.hw.data_ptr(), oh, ow, out.data_ptr(), _lib.ptr(minmax),
+                                                     wp, wn, _lib.current_stream()))
+    return (out, minmax) if return_minmax else out
+
+
+def midplane_resample_into(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: SlicePool) -> SlicePool:
+    """K0 alone (``svb_k0_midplane_resample``) into an existing pool -- the no-model (centre fallback) branch of the streamed
+    driver."""
+    lib = _lib.load()
+    if pool.n == 0:
+        return pool
+    mh, mw = pool.max_hw
+    need = lib.svb_k0_workspace_bytes(pool.n, mh, mw)
+    ws = _Workspace.get("k0", need, pool.data.device)
+    _lib.check(lib.svb_k0_midplane_resample(vols_d.data_ptr(), desc_d.data_ptr(), pool.n, mh, mw, pool.data.data_ptr(), ws.data_ptr(),
+                                            ws.numel(), _lib.current_stream()))
+    return pool
+
+
 def normalize_u8(pool: SlicePool, out: torch.Tensor | None = None, return_minmax: bool = False):
     """``normalize_to_uint8`` (io/__init__.py:15-30) over a ragged batch without resizing: returns a flat uint8 pool with the
     same element offsets as ``pool`` (slice b = ``out[offs[b] : offs[b] + h*w].view(h, w)``).  Device mirror of the

@@ -168,6 +168,7 @@ class StreamedLocalizer:
         self.copy_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
         self._stage = [None, None]
+        self._iso = None  # source-plane mode: the isotropic planes K0 writes (one buffer: K0 .. K3 of a chunk run in stream order)
         self._stage_free: list[torch.cuda.Event | None] = [None, None]  # last compute use of each staging buffer
         self._slots: list[dict] = [{}, {}]
         self._slot_busy: list[torch.cuda.Event | None] = [None, None]   # last D2H out of each output slot
@@ -209,12 +210,19 @@ class StreamedLocalizer:
         t = self._tables.get("key") == key and self._tables
         if t:
             return t
+        from_source = hasattr(series, "chunk_descs")  # volumes.PinnedVolumes: K0 runs on the device
+        if spacings is None and from_source:
+            spacings = series.spacings
         sp = spacings if spacings is not None else [(0.3, 0.3)] * B
         deltas = [mm_to_pixels(self.crop_delta_mm, s) for s in sp]
+        iso_offs = series.out_offs if from_source else series.offs
         rel_offs = []
         for i0, i1 in bounds:
-            rel_offs += [series.offs[i] - series.offs[i0] for i in range(i0, i1)]
-        t = {"key": key, "series": series, "deltas": deltas,
+            rel_offs += [iso_offs[i] - iso_offs[i0] for i in range(i0, i1)]
+        extra = {}
+        if from_source:
+            extra["descs"] = [series.chunk_descs(i0, i1) for i0, i1 in bounds]
+        t = {"key": key, "series": series, "deltas": deltas, **extra,
              "offs": torch.tensor(rel_offs, dtype=torch.int64).pin_memory().to(dev, non_blocking=True),
              "hw": torch.tensor(series.shapes, dtype=torch.int32).reshape(-1, 2).pin_memory().to(dev, non_blocking=True),
              "delta": torch.tensor(deltas, dtype=torch.int32).repeat_interleave(L, dim=0).contiguous().pin_memory().to(dev, non_blocking=True),
@@ -227,8 +235,12 @@ class StreamedLocalizer:
         complete when this call returns (it synchronises the result stream)."""
         return self.run_async(series, spacings, slot=0).result()
 
-    def run_async(self, series: PinnedSeries, spacings=None, slot: int = 0) -> PendingCrops:
+    def run_async(self, series, spacings=None, slot: int = 0) -> PendingCrops:
+        """``series``: a ``PinnedSeries`` (isotropic middle slices, 5.7 MB per 1195^2 series over PCIe) or a
+        ``volumes.PinnedVolumes`` (the two SOURCE planes per series, 2.1 MB at 512^2: K0 then runs on the device, fused
+        with K1 through ``svb_k01_midplane_normalize_resize`` -- what the dataset driver's decode stage hands over)."""
         B, L, dev = series.n, NUM_LEVELS, self.device
+        from_source = hasattr(series, "chunk_descs")
         o = self._outputs(B, slot)
         if B == 0:
             return PendingCrops(o, None)
@@ -239,18 +251,27 @@ class StreamedLocalizer:
         t = self._index_tables(series, spacings, bounds)
         deltas, offs_d, hw_d, delta_d, idx_d = t["deltas"], t["offs"], t["hw"], t["delta"], t["idx"]
         ready = [torch.cuda.Event(), torch.cuda.Event()]
-        max_elems = max(series.ends[i1 - 1] - series.offs[i0] for i0, i1 in bounds)
+        src_offs, src_ends = (series.vol_offs, series.vol_ends) if from_source else (series.offs, series.ends)
+        max_elems = max(src_ends[i1 - 1] - src_offs[i0] for i0, i1 in bounds)
         j0 = self._next_stage  # staging buffers keep alternating across calls
+        desc_d = [None, None]
+        if from_source:
+            iso_elems = max(series.out_offs[i1 - 1] + (series.shapes[i1 - 1][0] * series.shapes[i1 - 1][1] + 3) // 4 * 4 - series.out_offs[i0]
+                            for i0, i1 in bounds)
+            if self._iso is None or self._iso.numel() < iso_elems:
+                self._iso = torch.empty(iso_elems, dtype=torch.float32, device=dev)
 
         def upload(c):
             i0, i1 = bounds[c]
             j = (j0 + c) & 1
-            lo, hi = series.offs[i0], series.ends[i1 - 1]
+            lo, hi = src_offs[i0], src_ends[i1 - 1]
             with torch.cuda.stream(self.copy_stream):
                 if self._stage_free[j] is not None:
                     self.copy_stream.wait_event(self._stage_free[j])  # the chunk that last used this buffer is done with it
                 buf = self._staging(j, max_elems)
                 buf[: hi - lo].copy_(series.host[lo:hi], non_blocking=True)
+                if from_source:
+                    desc_d[c & 1] = t["descs"][c].to(dev, non_blocking=True)
                 ready[c & 1].record(self.copy_stream)
 
         upload(0)
@@ -262,11 +283,21 @@ class StreamedLocalizer:
             ready[c & 1] = torch.cuda.Event()
             n = i1 - i0
             shapes = series.shapes[i0:i1]
-            pool = ops.SlicePool(self._stage[j], offs_d[i0:i1], hw_d[i0:i1], list(shapes))
             coords = o["coords"][i0:i1]
-            if self.model is not None:
-                planes = ops.normalize_resize(pool, self.image_size)
-                self.model.predict_u8(planes, out=coords)
+            if from_source:
+                # K0 (+ K1 when there is a model) on the device: the chunk's source planes -> isotropic planes -> uint8 planes
+                pool = ops.SlicePool(self._iso, offs_d[i0:i1], hw_d[i0:i1], list(shapes))
+                if self.model is not None:
+                    planes = ops.midplane_normalize_resize(self._stage[j], desc_d[c & 1], pool, self.image_size)
+                    self.model.predict_u8(planes, out=coords)
+                else:
+                    ops.midplane_resample_into(self._stage[j], desc_d[c & 1], pool)
+                desc_d[c & 1].record_stream(compute)
+            else:
+                pool = ops.SlicePool(self._stage[j], offs_d[i0:i1], hw_d[i0:i1], list(shapes))
+                if self.model is not None:
+                    planes = ops.normalize_resize(pool, self.image_size)
+                    self.model.predict_u8(planes, out=coords)
             xy = coords.view(n * L, 2)
             if self.model is None:
                 # the fallback centres are Python floats in the reference: K3 gets them as float64 (int(x * w) sees the same double)

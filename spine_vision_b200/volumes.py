@@ -100,6 +100,76 @@ def plan_midplane(volume_zyx: np.ndarray, spacing_xyz, direction=None, new_spaci
     return MidplanePlan((ns[a_row], ns[a_col]), (float(new_spacing[a_row]), float(new_spacing[a_col])), slab, desc)
 
 
+class PinnedVolumes:
+    """A batch of series as the host hands it to the streamed driver when K0 runs on the device: per series only the (at most)
+    two source planes around the middle Left-Right index (``plan_midplane``), float32, in ONE pinned buffer, plus the
+    ``svb_k0_series`` rows and the layout of the isotropic planes K0 will produce.  512 x 512 sources at 0.7 mm: 2.1 MB per
+    series cross PCIe instead of the 5.7 MB of the resampled 1195 x 1195 plane."""
+
+    def __init__(self, volumes, spacings, directions=None, integer_pixels=None, pixel_kinds=None, plans=None):
+        if plans is None:
+            B = len(volumes)
+            directions = directions if directions is not None else [None] * B
+            integer_pixels = integer_pixels if integer_pixels is not None else [None] * B
+            plans = [plan_midplane(v, s, d, integer_pixels=ip) for v, s, d, ip in zip(volumes, spacings, directions, integer_pixels)]
+            if pixel_kinds is None:
+                pixel_kinds = [ops.SlicePool.kind_of(np.asarray(v).dtype) for v in volumes]
+        B = len(plans)
+        self.shapes = [p.out_hw for p in plans]                       # isotropic planes (H', W')
+        self.spacings = [p.spacing for p in plans]                    # get_slice_spacing of each
+        self.pixel_kinds = list(pixel_kinds) if pixel_kinds is not None else [0] * B
+        self.out_offs, self.out_total = ops.SlicePool.layout(self.shapes)
+        self.vol_offs, total = [], 0
+        for p in plans:
+            self.vol_offs.append(total)
+            total += (p.slab.size + 3) // 4 * 4
+        self.vol_ends = [o + (p.slab.size + 3) // 4 * 4 for o, p in zip(self.vol_offs, plans)]
+        self.host = torch.empty(max(total, 4), dtype=torch.float32)
+        if torch.cuda.is_available():
+            self.host = self.host.pin_memory()
+        hv = self.host.numpy()
+        self.descs = (K0Series * max(B, 1))()
+        for i, p in enumerate(plans):
+            hv[self.vol_offs[i] : self.vol_offs[i] + p.slab.size] = p.slab.ravel()
+            for k, val in p.desc.items():
+                setattr(self.descs[i], k, val)
+            self.descs[i].vol_off, self.descs[i].out_off = self.vol_offs[i], self.out_offs[i]
+
+    @classmethod
+    def from_plans(cls, plans, pixel_kinds=None) -> "PinnedVolumes":
+        """From ``plan_midplane`` results (a decode stage that never holds more than one whole volume at a time)."""
+        return cls(None, None, plans=list(plans), pixel_kinds=pixel_kinds)
+
+    @property
+    def n(self) -> int:
+        return len(self.shapes)
+
+    @property
+    def nbytes(self) -> int:
+        return (self.vol_ends[-1] if self.vol_ends else 0) * 4 + C.sizeof(K0Series) * self.n
+
+    def resident_pool(self, device="cuda:0") -> "ops.SlicePool":
+        """K0 over the whole batch into a fresh pool of isotropic planes resident in HBM (one call, no streaming)."""
+        dev = ops._require_cuda(device)
+        data = torch.empty(max(self.out_total, 4), dtype=torch.float32, device=dev)
+        pool = ops.SlicePool(data, torch.tensor(self.out_offs, dtype=torch.int64).to(dev),
+                             torch.tensor(self.shapes, dtype=torch.int32).reshape(-1, 2).to(dev), list(self.shapes), h2d_bytes=self.nbytes)
+        pool.set_pixel_kinds(self.pixel_kinds)
+        if self.n:
+            ops.midplane_resample_into(self.host.to(dev, non_blocking=True), self.chunk_descs(0, self.n).to(dev, non_blocking=True), pool)
+        return pool
+
+    def chunk_descs(self, i0: int, i1: int) -> torch.Tensor:
+        """``svb_k0_series`` rows of series [i0, i1) with offsets relative to the chunk's own buffers, as pinned bytes."""
+        rows = (K0Series * (i1 - i0))()
+        for k, i in enumerate(range(i0, i1)):
+            C.memmove(C.byref(rows[k]), C.byref(self.descs[i]), C.sizeof(K0Series))
+            rows[k].vol_off = self.vol_offs[i] - self.vol_offs[i0]
+            rows[k].out_off = self.out_offs[i] - self.out_offs[i0]
+        t = torch.frombuffer(bytearray(bytes(rows)), dtype=torch.uint8)
+        return t.pin_memory() if torch.cuda.is_available() else t
+
+
 _STAGE_FLIP = [0]
 
 

@@ -79,3 +79,52 @@ def test_k0_integer_pixel_types_truncate_like_itk_cast():
     # the same data declared float keeps the fractions
     pool_f, _ = volumes.midplane_resample([vols[0].astype(np.float32)], sps[:1], dirs[:1], dev())
     assert (pool_f.data[: pool.shapes[0][0] * pool.shapes[0][1]].cpu().numpy() % 1 != 0).any()
+
+
+def test_k01_fused_equals_k0_then_k1_and_streams_from_source_planes():
+    """SURVEY 8f row 1 / VERDICT r01 #4: K0 fused into K1 (``svb_k01_midplane_normalize_resize``: K0 accumulates each plane's
+    min / max while writing it, K1 makes no min/max pass) is the same function as K0 followed by K1 -- isotropic planes, min / max
+    and uint8 planes identical -- on a ragged batch walked in several L2-sized groups; and the streamed driver fed with the two
+    SOURCE planes per series (``volumes.PinnedVolumes``) returns the bytes of the resident volume path (coords, crops, 256^2)."""
+    from spine_vision_b200 import ops
+
+    rng = np.random.default_rng(11)
+    vols, sps, dirs = [], [], []
+    for k in range(7):
+        h, w = int(rng.integers(200, 520)), int(rng.integers(200, 520))
+        sp = float(rng.uniform(0.35, 0.9))
+        v, _, d = synthetic.make_volume(70 + k, int(rng.integers(9, 17)), h, w, (sp, sp, 4.0))
+        if k == 3:
+            v = np.full_like(v, 7.0)  # a constant series: max == min, the un-scaled values are cast (io/__init__.py:28)
+        if k == 5:
+            v = np.rint(v).astype(np.int16)
+        vols.append(v); sps.append((sp, sp, 4.0)); dirs.append(d)
+    pool, _ = volumes.midplane_resample(vols, sps, dirs, dev())
+    planes, mm = ops.normalize_resize(pool, (512, 512), return_minmax=True)
+    pv = volumes.PinnedVolumes(vols, sps, dirs)
+    assert pv.shapes == pool.shapes and pv.nbytes < sum(h * w for h, w in pool.shapes) * 4
+    d = torch.device(dev())
+    pool2 = ops.SlicePool(torch.empty_like(pool.data), pool.offs, pool.hw, list(pool.shapes))
+    descs = pv.chunk_descs(0, pv.n).to(d)
+    import os
+    for group in ("0", "2", ""):  # whole batch in one group, groups of two, the L2-sized default
+        os.environ["SVB_K1_GROUP"] = group
+        planes2, mm2 = ops.midplane_normalize_resize(pv.host.to(d), descs, pool2, (512, 512), return_minmax=True)
+        torch.cuda.synchronize()
+        for i, (h, w) in enumerate(pool.shapes):
+            o = int(pool.offs[i])
+            assert torch.equal(pool2.data[o : o + h * w], pool.data[o : o + h * w]), i
+        assert torch.equal(mm2, mm) and torch.equal(planes2, planes)
+    os.environ.pop("SVB_K1_GROUP", None)
+    om = make_model("base", seed=0)
+    model = cropping.LocalizationModel(om.state_dict(), dev(), micro_batch=3)
+    want = pipeline.localize_and_crop_volumes(vols, sps, dirs, model, dev(), crop_delta_mm=(50, 20, 30, 30), crop_size=(128, 128))
+    wc, wk, wk2 = want.to_host()
+    streamer = pipeline.StreamedLocalizer(model, dev(), (50, 20, 30, 30), (128, 128), (512, 512), (256, 256), chunk=3)
+    for _ in range(2):
+        gc, gk, gk2 = streamer.run(pv)
+        assert np.array_equal(gc.numpy(), wc) and np.array_equal(gk.numpy(), wk) and np.array_equal(gk2.numpy(), wk2)
+    fb = pipeline.StreamedLocalizer(None, dev(), (50, 20, 30, 30), (128, 128), (512, 512), None, chunk=4)
+    fc, fk, _ = fb.run(pv)
+    ref_fb = pipeline.localize_and_crop_volumes(vols, sps, dirs, None, dev(), crop_delta_mm=(50, 20, 30, 30), crop_size=(128, 128), second_size=None)
+    assert np.array_equal(fk.numpy(), ref_fb.crops.cpu().numpy())
