@@ -95,8 +95,9 @@ int svb_k0_midplane_resample(const float* d_volumes, const svb_k0_series* d_desc
 /* K0 + K1 in one call ("fuse into K1"): source planes -> isotropic middle planes (kept: K3 cuts its crops from
  * them) + the uint8 model planes.  Replaces resample_to_isotropic + extract_middle_slice (cropping.py:37-79) AND
  * normalize_to_uint8 + Resize of predict_ivd_locations (io/__init__.py:15-30, cropping.py:463-472) for a batch.  K0 accumulates
- * every plane's min / max while it writes it, so K1 makes no min/max pass; the batch is walked in groups small enough for the
- * resize launch to read the planes back from L2.  d_offs / d_hw describe the planes in d_slices (= desc.out_off, out_h, out_w). */
+ * every plane's min / max while it writes it, so K1 makes no min/max pass (SVB_K1_GROUP=n walks the batch in groups of n
+ * planes that the resize launch reads back from L2: less DRAM traffic, more and smaller launches -- measured slower, off by
+ * default).  d_offs / d_hw describe the planes in d_slices (= desc.out_off, out_h, out_w). */
 size_t svb_k01_workspace_bytes(int B, int max_out_h, int max_out_w, int out_h, int out_w);
 int svb_k01_midplane_normalize_resize(const float* d_volumes, const svb_k0_series* d_desc, int B, int max_out_h,
                                       int max_out_w, float* d_slices, const int64_t* d_offs, const int32_t* d_hw,
@@ -221,6 +222,12 @@ size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int
 enum { SVB_KC_STEM = 0, SVB_KC_DWCONV_LN = 1, SVB_KC_GEMM = 2, SVB_KC_LN_PATCHIFY = 3, SVB_KC_HEAD = 4, SVB_NUM_KERNEL_CLASSES = 5 };
 int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
                       int micro_batch, void* d_ws, size_t ws_bytes, void* stream, float* times_ms);
+/* The same forward from the tensor the reference's callers build themselves: float32 NCHW [B,3,H,W], already /255 and
+ * ImageNet-normalised (cropping.py:463-472) -- what `model(tensor)` receives (generic.py:389-391; notebooks,
+ * BaseModel.test_inference base.py:153-158).  Un-folded stem conv (3 input channels); everything after the stem is the
+ * same code.  The dataset path does not use it (it feeds K1's uint8 plane to the folded stem). */
+int svb_model_forward_f32(svb_model* m, const float* d_in_nchw, int B, int H, int W, float* d_coords,
+                          int micro_batch, void* d_ws, size_t ws_bytes, void* stream, float* times_ms);
 /* model geometry: out[0]=num_levels, out[1]=num_outputs, out[2..5]=dims, out[6..9]=depths */
 int svb_model_info(const svb_model* m, int32_t out[10]);
 /* total tensor-core GEMM flops and launches of one forward over B images (for the roofline) */

@@ -85,7 +85,10 @@ def run(name, fa, fb, reps_a, reps_b):
     return ms
 
 
-for C, hw in [(512, 32), (256, 64), (128, 128)]:
+STAGES = [(512, 32), (256, 64), (128, 128)]
+if len(sys.argv) > 3:
+    STAGES = [st for st in STAGES if str(st[0]) in sys.argv[3].split(",")]
+for C, hw in STAGES:
     M = NB * hw * hw
     x = torch.randn(NB, hw, hw, C, generator=g).to(dt).to(dev)
     taps = (torch.randn(49, C, generator=g) * 0.1).to(dev)

@@ -221,6 +221,21 @@ class LocalizationModel:
     def predict_u8(self, planes_u8: torch.Tensor, times: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         return self.engine.forward(planes_u8, times, out)
 
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """``CoordinateRegressor.forward`` (generic.py:380-391) for callers that build the input themselves:
+        ``x`` = ``[B,3,H,W]`` float, /255 and ImageNet-normalised (any device / float dtype) -> ``[B, num_levels, 2]`` float32
+        on the model's device.  Inference only (no autograd graph)."""
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected a [B,3,H,W] tensor, got {tuple(x.shape)}")
+        xd = x.detach().to(self.device, torch.float32).contiguous()
+        return self.engine.forward_tensor(xd)
+
+    __call__ = forward
+
+    def predict(self, x: torch.Tensor) -> torch.Tensor:
+        """``BaseModel.predict`` (base.py:80-81 / generic.py:393-395): same as ``forward`` in eval mode."""
+        return self.forward(x)
+
 
 def load_localization_model(model_path: Path, variant: str, device: str, dtype: str | None = None) -> LocalizationModel:
     """cropping.py:407-441 -- same checkpoint format (``torch.save`` dict whose

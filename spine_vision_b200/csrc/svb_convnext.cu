@@ -65,6 +65,7 @@ struct svb_model {
     void* slab = nullptr;
     size_t slab_bytes = 0;
     float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
+    float *stem_w3 = nullptr, *stem_b3 = nullptr;  // the un-folded stem [C0][3*4*4] + bias (svb_model_forward_f32: model(tensor) callers)
     std::vector<BlockParams> blocks[4];
     DownParams down[4];
     float *hn0w = nullptr, *hn0b = nullptr, *hn1w = nullptr, *hn1b = nullptr, *hw1 = nullptr, *hb1 = nullptr,
@@ -72,6 +73,15 @@ struct svb_model {
     ActPlan plans[4];  // (workspace half, micro-batch size) pairs in use: two chains x {full, tail} micro-batch
     int next_plan = 0;
     std::vector<cudaEvent_t> events;
+    // every CUDA resource the handle owns goes here, so that an error return half-way through svb_model_create
+    // (std::unique_ptr guard) releases the slab and the streams too
+    ~svb_model() {
+        for (auto e : events) cudaEventDestroy(e);
+        if (aux_stream) { cudaStreamSynchronize(aux_stream); cudaStreamDestroy(aux_stream); }
+        if (fork_ev) cudaEventDestroy(fork_ev);
+        if (join_ev) cudaEventDestroy(join_ev);
+        if (slab) cudaFree(slab);
+    }
 };
 
 namespace svb {
@@ -135,6 +145,15 @@ static int make_epilogue_map(CUtensorMap* map, int dtype, const void* base, uint
     const uint32_t box[2] = {32, 32};
     return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
 }
+// cudaFuncSetAttribute is a per-DEVICE setting: a process that drives a second GPU must opt in there too (the caches below are
+// keyed by the current device; the flags only ever go from false to true, so a race costs a repeated call, nothing else)
+constexpr int MAX_DEVICES = 64;
+static int current_device_slot() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < MAX_DEVICES) ? d : 0;
+}
+
 static int gemm_bn(int N) { return (N % 256 == 0) ? 256 : 128; }
 // CTA-pair (cta_group::2) tiles pay off when the K loop is long enough to hide the pair's tile hand-over
 // (measured on B200, profiles/r01_gemm_shapes.txt): K >= 1024, or K >= 512 with at least two N tiles of 256.
@@ -168,6 +187,17 @@ static bool gemm_half_env() {
     return e && e[0] == '1';
 }
 static int gemm_bn_for(int N, bool half) { return half ? 128 : gemm_bn(N); }
+// SVB_CARVEOUT=1: ask for the maximum shared-memory carve-out on the persistent kernels.  Two kernels whose preferred L1 /
+// shared split differs cannot be resident on one SM at the same time (the split is an SM-wide setting), so a half-SM GEMM
+// CTA and a depthwise CTA only ever share an SM when both ask for the same split.
+static bool carveout_max() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("SVB_CARVEOUT");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
 
 // rows per depthwise tile: bounded by the 512 TMEM columns a CTA may hold (2 warps x TH pixels x NV values), see DwCfg
 static int dw_th(int C) { return C >= 1536 ? 4 : (C >= 384 ? 8 : 16); }
@@ -330,6 +360,8 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
         }
         m->stem_w = static_cast<float*>(slab.put(wf.data(), wf.size() * 4));
         m->stem_b = static_cast<float*>(slab.put(bf.data(), bf.size() * 4));
+        m->stem_w3 = static_cast<float*>(slab.put(stem_w->data, (size_t)C0 * 48 * 4));
+        m->stem_b3 = static_cast<float*>(slab.put(stem_b->data, (size_t)C0 * 4));
         PUT_F32(m->stem_lnw, "backbone.stem.1.weight", C0);
         PUT_F32(m->stem_lnb, "backbone.stem.1.bias", C0);
     }
@@ -410,6 +442,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
     SVB_CUDA_OK(cudaMemcpy(m->slab, slab.host.data(), slab.off, cudaMemcpyHostToDevice));
     uint8_t* base = static_cast<uint8_t*>(m->slab);
     rebase(m->stem_w, base); rebase(m->stem_b, base); rebase(m->stem_lnw, base); rebase(m->stem_lnb, base);
+    rebase(m->stem_w3, base); rebase(m->stem_b3, base);
     rebase(m->hn0w, base); rebase(m->hn0b, base); rebase(m->hn1w, base); rebase(m->hn1b, base);
     rebase(m->hw1, base); rebase(m->hb1, base); rebase(m->hw2, base); rebase(m->hb2, base);
     for (int s = 0; s < 4; ++s) {
@@ -461,12 +494,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
 
 extern "C" int svb_model_destroy(svb_model* m) {
     if (!m) return SVB_OK;
-    for (auto e : m->events) cudaEventDestroy(e);
-    if (m->aux_stream) { cudaStreamSynchronize(m->aux_stream); cudaStreamDestroy(m->aux_stream); }
-    if (m->fork_ev) cudaEventDestroy(m->fork_ev);
-    if (m->join_ev) cudaEventDestroy(m->join_ev);
-    if (m->slab) cudaFree(m->slab);
-    delete m;
+    delete m;  // ~svb_model releases the streams, events and the weight slab
     return SVB_OK;
 }
 
@@ -563,10 +591,12 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
                          const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st) {
     using Cfg = GemmCfg<BN, CG, HALF>;
     auto kern = gemm_kernel<T, BN, MODE, CG, HALF>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (!attr_done[dslot]) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
+        if (carveout_max()) SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done[dslot] = true;
     }
     const int tiles = ceil_div(M, 128 * CG) * ceil_div(N, BN);
     const int units = num_sms() / CG;  // CTAs, or CTA pairs
@@ -631,10 +661,11 @@ template <typename T, int C>
 static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st) {
     using Cfg = MlpCfg<C>;
     auto kern = mlp_fused_kernel<T, C>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (!attr_done[dslot]) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
+        attr_done[dslot] = true;
     }
     const int tiles = ceil_div(M, 256);
     const int pairs = num_sms() / 2;
@@ -666,10 +697,12 @@ template <typename T, int C, int TH>
 static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* out, int nb, int H, int W, cudaStream_t st) {
     using Cfg = DwCfg<C, TH>;
     auto kern = dwconv_ln_kernel<T, C, TH>;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (!attr_done[dslot]) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-        attr_done = true;
+        if (carveout_max()) SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr_done[dslot] = true;
     }
     const int tx = ceil_div(W, Cfg::TW), ty = ceil_div(H, TH);
     const int tiles = nb * tx * ty;
@@ -695,10 +728,11 @@ static int launch_dwconv_tc_t(const CUtensorMap& xtc, const BlockParams& bp, voi
     auto kern = dwconv_ln_tc_kernel<T, C>;
     const int P = W + 6;
     const int smem = Cfg::smem_bytes(P, NR);
-    static int attr_smem = 0;
-    if (smem > attr_smem) {
+    static int attr_smem[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (smem > attr_smem[dslot]) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_smem = smem;
+        attr_smem[dslot] = smem;
     }
     const int tiles_per_img = ceil_div(H * P, 128);
     const int tiles = nb * tiles_per_img;
@@ -775,10 +809,11 @@ static int launch_head(const T* x, int nb, int tokens, int C, const float* n0w, 
     const size_t smem = (size_t)(C + hid + 8 + C + 8 * C) * 4;  // feat, hidden, reduction scratch, pool share, per-warp pools
     SVB_REQUIRE(smem <= 99 * 1024, SVB_ERR_UNSUPPORTED_MODEL, "head: C=%d needs %zu bytes of shared memory", C, smem);
     auto kern = head_kernel<T>;
-    static size_t attr_smem = 0;
-    if (smem > 48 * 1024 && smem > attr_smem) {
+    static size_t attr_smem[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (smem > 48 * 1024 && smem > attr_smem[dslot]) {
         SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
+        attr_smem[dslot] = smem;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)nb * HEAD_CLUSTER);
@@ -833,8 +868,8 @@ struct Timer {  // optional per-launch CUDA-event timing, accumulated per kernel
 };
 
 template <typename T>
-static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, float* coords, uint8_t* ws, cudaStream_t st,
-                         Timer& tm) {
+static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, int nb, int H, int W, float* coords, uint8_t* ws,
+                         cudaStream_t st, Timer& tm) {
     ActPlan* plan = nullptr;
     if (int rc = get_plan(m, ws, nb, H, W, &plan)) return rc;
     const WsLayout L = ws_layout(m, nb, H, W);
@@ -854,7 +889,9 @@ static int forward_chunk(svb_model* m, const uint8_t* in, int nb, int H, int W, 
         if (blocks > (long long)num_sms() * 4) blocks = (long long)num_sms() * 4;  // stem_ln_kernel: 4 resident CTAs per SM
         if (blocks < 1) blocks = 1;
         if (int rc = tm.begin(SVB_KC_STEM)) return rc;
-        if (m->dims[0] == 128)
+        if (in_f32 != nullptr)
+            stem3_ln_kernel<T><<<(int)blocks, 256, 0, st>>>(in_f32, m->stem_w3, m->stem_b3, m->stem_lnw, m->stem_lnb, X, nb, H, W, m->dims[0]);
+        else if (m->dims[0] == 128)
             stem_ln_kernel<T, 4><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
         else if (m->dims[0] == 192)
             stem_ln_kernel<T, 6><<<(int)blocks, 256, 0, st>>>(in, m->stem_w, m->stem_b, m->stem_lnw, m->stem_lnb, X, nb, H, W);
@@ -926,10 +963,10 @@ extern "C" size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch,
     return dual_chain_enabled() ? 2 * one : one;
 }
 
-extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
-                                 int micro_batch, void* d_ws, size_t ws_bytes, void* stream_, float* times_ms) {
+static int model_forward_any(svb_model* m, const uint8_t* d_in_u8, const float* d_in_f32, int B, int H, int W, float* d_coords,
+                             int micro_batch, void* d_ws, size_t ws_bytes, void* stream_, float* times_ms) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    SVB_REQUIRE(m && d_in_u8 && d_coords && d_ws, SVB_ERR_INVALID_ARG, "model_forward: null argument");
+    SVB_REQUIRE(m && (d_in_u8 || d_in_f32) && d_coords && d_ws, SVB_ERR_INVALID_ARG, "model_forward: null argument");
     SVB_REQUIRE(B >= 0 && micro_batch > 0, SVB_ERR_INVALID_ARG, "model_forward: B=%d micro_batch=%d", B, micro_batch);
     SVB_REQUIRE(H > 0 && W > 0 && H % 32 == 0 && W % 32 == 0, SVB_ERR_INVALID_ARG,
                 "model_forward: input %dx%d must be a positive multiple of 32 (ConvNeXt stride)", H, W);
@@ -951,10 +988,12 @@ extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, in
         cudaStream_t cs = odd ? m->aux_stream : st;
         uint8_t* ws = static_cast<uint8_t*>(d_ws) + (odd ? one : 0);
         int rc;
+        const uint8_t* in8 = d_in_u8 ? d_in_u8 + (size_t)b0 * H * W : nullptr;
+        const float* in32 = d_in_f32 ? d_in_f32 + (size_t)b0 * 3 * H * W : nullptr;
         if (m->dtype == SVB_FP16)
-            rc = forward_chunk<__half>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
+            rc = forward_chunk<__half>(m, in8, in32, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
         else
-            rc = forward_chunk<__nv_bfloat16>(m, d_in_u8 + (size_t)b0 * H * W, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
+            rc = forward_chunk<__nv_bfloat16>(m, in8, in32, nb, H, W, d_coords + (size_t)b0 * m->nout, ws, cs, tm);
         if (rc) return rc;
     }
     if (dual) {
@@ -962,6 +1001,19 @@ extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, in
         SVB_CUDA_OK(cudaStreamWaitEvent(st, m->join_ev, 0));
     }
     return tm.finish(times_ms);
+}
+
+extern "C" int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
+                                 int micro_batch, void* d_ws, size_t ws_bytes, void* stream_, float* times_ms) {
+    SVB_REQUIRE(d_in_u8, SVB_ERR_INVALID_ARG, "model_forward: null argument");
+    return model_forward_any(m, d_in_u8, nullptr, B, H, W, d_coords, micro_batch, d_ws, ws_bytes, stream_, times_ms);
+}
+
+extern "C" int svb_model_forward_f32(svb_model* m, const float* d_in_nchw, int B, int H, int W, float* d_coords,
+                                     int micro_batch, void* d_ws, size_t ws_bytes, void* stream_, float* times_ms) {
+    SVB_REQUIRE(d_in_nchw, SVB_ERR_INVALID_ARG, "model_forward_f32: null argument");
+    SVB_REQUIRE(!m || m->dims[0] <= 256, SVB_ERR_UNSUPPORTED_MODEL, "model_forward_f32: stem width %d > 256", m ? m->dims[0] : 0);
+    return model_forward_any(m, nullptr, d_in_nchw, B, H, W, d_coords, micro_batch, d_ws, ws_bytes, stream_, times_ms);
 }
 
 extern "C" int svb_model_cost(const svb_model* m, int B, int H, int W, double* gemm_flops, int64_t* launches) {

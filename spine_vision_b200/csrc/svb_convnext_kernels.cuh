@@ -186,6 +186,69 @@ __global__ void __launch_bounds__(256, (CPL <= 4) ? 4 : 2) stem_ln_kernel(const 
     }
 }
 
+// ---------------------------------------------------------------------------- stem, un-folded (compatibility path)
+// in float32 NCHW [B,3,H,W] -- the tensor predict_ivd_locations builds (ToTensor + Normalize, cropping.py:463-472) and
+// hands to model(tensor) (generic.py:389-391).  Any caller that runs the module on its own tensor (notebooks,
+// BaseModel.test_inference) lands here; the dataset path uses the folded one-plane stem above.  One warp per token, lane =
+// C0 / 32 (rounded up) consecutive channels; the 48 inputs of the patch are read once per token and broadcast.
+template <typename T>
+__global__ void __launch_bounds__(256) stem3_ln_kernel(const float* __restrict__ in, const float* __restrict__ w /*[C0][48] = [co][ci][ky][kx]*/,
+                                                      const float* __restrict__ bias, const float* __restrict__ lnw,
+                                                      const float* __restrict__ lnb, T* __restrict__ out, int B, int H, int W, int C0) {
+    constexpr int MAXC = 8;  // channels per lane: C0 <= 256
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int Ho = H >> 2, Wo = W >> 2;
+    const long long tokens = (long long)B * Ho * Wo;
+    const int cpl = (C0 + 31) / 32;
+    for (long long t = warp; t < tokens; t += nwarps) {
+        const int b = (int)(t / (Ho * Wo));
+        const int rem = (int)(t - (long long)b * Ho * Wo);
+        const int ty = rem / Wo, tx = rem - ty * Wo;
+        // lane l < 48 holds input (ci, ky, kx) = (l / 16, (l % 16) / 4, l % 4); lanes 0..15 also hold 32..47
+        float x0 = 0.f, x1 = 0.f;
+        {
+            const int q = lane, ci = q >> 4, ky = (q >> 2) & 3, kx = q & 3;
+            x0 = __ldg(in + (((size_t)b * 3 + ci) * H + (size_t)ty * 4 + ky) * W + (size_t)tx * 4 + kx);
+            if (lane < 16) {
+                const int q2 = 32 + lane, ci2 = q2 >> 4, ky2 = (q2 >> 2) & 3, kx2 = q2 & 3;
+                x1 = __ldg(in + (((size_t)b * 3 + ci2) * H + (size_t)ty * 4 + ky2) * W + (size_t)tx * 4 + kx2);
+            }
+        }
+        float acc[MAXC];
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane * cpl + j;
+            acc[j] = (j < cpl && c < C0) ? bias[c] : 0.f;
+        }
+        for (int q = 0; q < 48; ++q) {
+            const float xv = __shfl_sync(0xffffffffu, q < 32 ? x0 : x1, q & 31);
+#pragma unroll
+            for (int j = 0; j < MAXC; ++j) {
+                const int c = lane * cpl + j;
+                if (j < cpl && c < C0) acc[j] = fmaf(xv, __ldg(w + (size_t)c * 48 + q), acc[j]);
+            }
+        }
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) s += acc[j];
+        const float mean = warp_sum(s) * (1.0f / C0);
+        float v2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane * cpl + j;
+            if (j < cpl && c < C0) { const float d = acc[j] - mean; v2 = fmaf(d, d, v2); }
+        }
+        const float rstd = 1.0f / sqrtf(warp_sum(v2) * (1.0f / C0) + LN_EPS_BACKBONE);
+#pragma unroll
+        for (int j = 0; j < MAXC; ++j) {
+            const int c = lane * cpl + j;
+            if (j < cpl && c < C0) out[(size_t)t * C0 + c] = Cvt<T>::from_f(fmaf((acc[j] - mean) * rstd, lnw[c], lnb[c]));
+        }
+    }
+}
+
 // ============================================================================ depthwise 7x7 + LayerNorm
 // One CTA = TH x 8 output pixels x all C channels; 8 consumer warps (one pixel column each, lane =
 // channel pair) + 1 TMA producer warp.  Per 64-channel chunk the (TH+6) x 14 x 64 halo tile (4-D

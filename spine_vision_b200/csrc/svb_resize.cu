@@ -418,19 +418,18 @@ struct K1Plan {
     int *hb = nullptr, *hk = nullptr, *vb = nullptr, *vk = nullptr;
 };
 
-// Slices per (min/max, resize) launch pair -- or per (K0, resize) pair of the fused entry.  The second launch re-reads what the
-// first one read (or wrote); a group of at most ~48 MB of fp32 slices is still in the 126 MB L2 then, so the slice crosses
-// HBM once instead of twice (round 1 ran each pass over the whole batch: 1.46 GB read twice, L2 hit rate 12.6 %).
-// SVB_K1_GROUP=n forces n (0 = the whole batch, the round-1 schedule) for A/B runs.
+// Slices per (min/max, resize) launch pair -- or per (K0, resize) pair of the fused entry.  Default: the whole batch in one
+// pair.  The second launch re-reads what the first one read (or wrote) from HBM, but it is bound by instruction issue (Pillow's
+// fixed-point taps), so the re-read hides under the arithmetic.  Measured alternative (B200, round 2, SVB_K1_GROUP=8: groups of
+// 46 MB that the second launch reads back from the 126 MB L2): DRAM reads fall to ~1.1x the algorithmic bytes but the 32 launch
+// pairs of 128 CTAs no longer fill 148 SMs x 2 -- K1 1.05 -> 1.65 ms per 256 slices, end-to-end 3,690 -> 3,448 series/s.
+// Time, not traffic, is what the step pays for; SVB_K1_GROUP=n keeps the grouped schedule available for profiling.
 static int k1_group_size(int B, int max_h, int max_w) {
+    (void)max_h; (void)max_w;
     const char* e = getenv("SVB_K1_GROUP");  // read on every call (tests walk the settings)
-    const int forced = (e && e[0]) ? atoi(e) : -1;
-    if (forced == 0) return B;
-    if (forced > 0) return forced < B ? forced : B;
-    const size_t slice_bytes = (size_t)max_h * max_w * 4;
-    size_t g = ((size_t)48 << 20) / (slice_bytes ? slice_bytes : 1);
-    if (g < 1) g = 1;
-    return g < (size_t)B ? (int)g : B;
+    const int forced = (e && e[0]) ? atoi(e) : 0;
+    if (forced <= 0) return B;
+    return forced < B ? forced : B;
 }
 
 // validates, sizes the resize kernel, builds the Pillow coefficient tables (one launch); `reset_keys`: the same launch

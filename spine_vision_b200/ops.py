@@ -25,6 +25,35 @@ def _require_cuda(device) -> torch.device:
     return dev
 
 
+def _device_of(args, kwargs):
+    for a in list(args) + list(kwargs.values()):
+        if isinstance(a, torch.Tensor) and a.is_cuda:
+            return a.device
+        d = getattr(a, "data", None)
+        if isinstance(d, torch.Tensor) and d.is_cuda:  # a SlicePool
+            return d.device
+        d = getattr(a, "device", None)
+        if isinstance(d, torch.device) and d.type == "cuda":  # a LocalizationEngine
+            return d
+    return None
+
+
+def _on_device(fn):
+    """Run ``fn`` with the CUDA device of its data current: the library launches on the CURRENT device's current stream and keeps
+    per-device kernel attributes, so an op on ``cuda:1`` tensors must not run while ``cuda:0`` is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        dev = _device_of(args, kwargs)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 @dataclass
 class SlicePool:
     """A ragged batch of float32 slices resident in HBM: one flat pool plus
@@ -145,6 +174,7 @@ def _aligned_ptr(buf: torch.Tensor, align: int = 1024) -> tuple[int, int]:
     return a, buf.numel() - (a - p)
 
 
+@_on_device
 def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | None = None, return_minmax: bool = False):
     """K1: per-slice global min-max -> uint8 (truncating) -> Pillow antialiased bilinear resize.
     Device mirror of ``normalize_to_uint8`` (io/__init__.py:15-30) + ``transforms.Resize``
@@ -167,6 +197,7 @@ def normalize_resize(pool: SlicePool, out_hw=(512, 512), out: torch.Tensor | Non
     return (out, minmax) if return_minmax else out
 
 
+@_on_device
 def midplane_normalize_resize(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: SlicePool, out_hw=(512, 512),
                               out: torch.Tensor | None = None, return_minmax: bool = False):
     """K0 + K1 in one call (``svb_k01_midplane_normalize_resize``): ``vols_d`` float32 source planes and ``desc_d`` the
@@ -192,6 +223,7 @@ def midplane_normalize_resize(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: 
     return (out, minmax) if return_minmax else out
 
 
+@_on_device
 def midplane_resample_into(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: SlicePool) -> SlicePool:
     """K0 alone (``svb_k0_midplane_resample``) into an existing pool -- the no-model (centre fallback) branch of the streamed
     driver."""
@@ -206,6 +238,7 @@ def midplane_resample_into(vols_d: torch.Tensor, desc_d: torch.Tensor, pool: Sli
     return pool
 
 
+@_on_device
 def normalize_u8(pool: SlicePool, out: torch.Tensor | None = None, return_minmax: bool = False):
     """``normalize_to_uint8`` (io/__init__.py:15-30) over a ragged batch without resizing: returns a flat uint8 pool with the
     same element offsets as ``pool`` (slice b = ``out[offs[b] : offs[b] + h*w].view(h, w)``).  Device mirror of the
@@ -227,6 +260,7 @@ def normalize_u8(pool: SlicePool, out: torch.Tensor | None = None, return_minmax
     return (out, minmax) if return_minmax else out
 
 
+@_on_device
 def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, delta_px: torch.Tensor, max_box_hw,
                   crop_size=(128, 128), second_size=(256, 256), return_geom: bool = False, normalize: bool = True,
                   out: torch.Tensor | None = None, out2: torch.Tensor | None = None, inv_affine: torch.Tensor | None = None):
@@ -271,6 +305,7 @@ def crop_resample(pool: SlicePool, slice_idx: torch.Tensor, xy: torch.Tensor, de
 _OUT_DTYPES = {torch.float32: _lib.SVB_F32, torch.bfloat16: _lib.SVB_BF16, torch.float16: _lib.SVB_FP16}
 
 
+@_on_device
 def classifier_input(planes: torch.Tensor, t2_idx: torch.Tensor, t1_idx: torch.Tensor, normalize: bool = True,
                      dtype: torch.dtype = torch.float32, mean=None, std=None, out: torch.Tensor | None = None) -> torch.Tensor:
     """K4: ``[T2, T1, T2]`` stack + ``ToTensor`` + ``Normalize`` for a batch of (patient, level) samples from the resized
@@ -337,6 +372,7 @@ class LocalizationEngine:
         _lib.check(_lib.load().svb_model_cost(self._h, B, H, W, C.byref(fl), C.byref(n)))
         return fl.value, n.value
 
+    @_on_device
     def forward(self, u8: torch.Tensor, times: dict | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
         """uint8 [B,H,W] on the device -> float32 [B, num_levels, 2] in [0,1]."""
         assert u8.is_cuda and u8.dtype == torch.uint8 and u8.dim() == 3 and u8.is_contiguous()
@@ -359,6 +395,26 @@ class LocalizationEngine:
         return coords
 
 
+    def forward_tensor(self, x: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """float32 NCHW ``[B,3,H,W]`` (already /255 and ImageNet-normalised, cropping.py:463-472) on the device -> float32
+        ``[B, num_levels, 2]``: what ``model(tensor)`` computes in the reference (generic.py:389-391), through the un-folded stem."""
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 4 and x.shape[1] == 3 and x.is_contiguous()
+        lib = _lib.load()
+        B, _, H, W = x.shape
+        coords = out if out is not None else torch.empty((B, self.num_levels, self.num_outputs), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return coords
+        mb = min(self.micro_batch, B)
+        with torch.cuda.device(x.device):
+            need = lib.svb_model_workspace_bytes(self._h, mb, H, W)
+            ws = _Workspace.get("model", need, x.device)
+            wp, wn = _aligned_ptr(ws, 1024)
+            _lib.check(lib.svb_model_forward_f32(self._h, x.data_ptr(), B, H, W, coords.data_ptr(), mb, wp, wn,
+                                                 torch.cuda.current_stream(x.device).cuda_stream, None))
+        return coords
+
+
+@_on_device
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int, resid: torch.Tensor | None = None,
          gamma: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
     """Standalone tcgen05 GEMM (unit tests / profiling): ``epilogue(a @ w.T)``; a [M,K], w [N,K]."""
@@ -374,6 +430,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, mode: int, resid:
     return out
 
 
+@_on_device
 def mlp_fused(a: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor, gamma: torch.Tensor,
               x: torch.Tensor) -> torch.Tensor:
     """Standalone fused MLP (tests / profiling): ``x += gamma * (gelu(a @ w1.T + b1) @ w2.T + b2)`` in place."""
@@ -390,6 +447,7 @@ def _dt(t: torch.Tensor) -> int:
     return _lib.SVB_BF16 if t.dtype == torch.bfloat16 else _lib.SVB_FP16
 
 
+@_on_device
 def stem_ln(u8: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor, dtype=torch.bfloat16):
     """u8 [B,H,W] -> [B,H/4,W/4,C0] with the folded stem (wf [C0,16], bf [C0])."""
     B, H, W = u8.shape
@@ -400,6 +458,7 @@ def stem_ln(u8: torch.Tensor, wf: torch.Tensor, bf: torch.Tensor, lnw: torch.Ten
     return out
 
 
+@_on_device
 def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor, out: torch.Tensor | None = None):
     """x NHWC 16-bit [B,H,W,C]; taps fp32 [49,C] (tap-major) -> LayerNorm(dwconv7x7(x)+bias) [B,H,W,C]."""
     B, H, W, Cc = x.shape
@@ -410,6 +469,7 @@ def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torc
     return out
 
 
+@_on_device
 def dwconv_ln_tc(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
     """Same operator as ``dwconv_ln`` on the tensor cores (taps are rounded to the activation dtype)."""
     B, H, W, Cc = x.shape
@@ -420,6 +480,7 @@ def dwconv_ln_tc(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: t
     return out
 
 
+@_on_device
 def ln_patchify(x: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
     B, H, W, Cc = x.shape
     out = torch.empty((B, H // 2, W // 2, 4 * Cc), dtype=x.dtype, device=x.device)
@@ -428,6 +489,7 @@ def ln_patchify(x: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
     return out
 
 
+@_on_device
 def head(x: torch.Tensor, n0w, n0b, n1w, n1b, w1, b1, w2, b2):
     """x [B,tokens,C] 16-bit -> sigmoid coords fp32 [B,NOUT]."""
     B, tokens, Cc = x.shape

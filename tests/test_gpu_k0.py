@@ -107,7 +107,7 @@ def test_k01_fused_equals_k0_then_k1_and_streams_from_source_planes():
     pool2 = ops.SlicePool(torch.empty_like(pool.data), pool.offs, pool.hw, list(pool.shapes))
     descs = pv.chunk_descs(0, pv.n).to(d)
     import os
-    for group in ("0", "2", ""):  # whole batch in one group, groups of two, the L2-sized default
+    for group in ("0", "2", "3", ""):  # whole batch in one pair (the default), groups of two / three planes (the L2-sized schedule)
         os.environ["SVB_K1_GROUP"] = group
         planes2, mm2 = ops.midplane_normalize_resize(pv.host.to(d), descs, pool2, (512, 512), return_minmax=True)
         torch.cuda.synchronize()

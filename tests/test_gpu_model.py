@@ -99,6 +99,33 @@ def test_end_to_end_crop_agreement_config1(trained):
             assert err_px <= 0.5 and (not shifts or max(shifts) <= 2)
 
 
+def test_model_call_on_reference_tensor():
+    """SURVEY 8b "model plug points": callers other than predict_ivd_locations run ``model(tensor)`` on the [B,3,H,W] float
+    tensor they normalised themselves (generic.py:389-391; notebooks, BaseModel.test_inference).  The un-folded stem gives the
+    coordinates of the folded one-plane stem (same planes) and of the fp32 oracle within the gate, for CPU and CUDA inputs,
+    and for a tensor that is NOT three copies of one plane."""
+    om = make_model("base", seed=0)
+    model = cropping.LocalizationModel(om.state_dict(), dev())
+    slices = [synthetic.make_iso_slice(40, 640, 650), synthetic.make_iso_slice(41, 1195, 1195), synthetic.make_iso_slice(42, 512, 600)]
+    tensors = torch.stack([ref.preprocess_slice(sl, (512, 512))[1] for sl in slices])
+    with torch.no_grad():
+        want = om(tensors).numpy()
+    got = model(tensors)  # CPU tensor in, as the reference's callers hold it before .to(device)
+    assert got.is_cuda and tuple(got.shape) == (3, 5, 2) and got.dtype == torch.float32
+    assert np.abs(got.cpu().numpy() - want).max() * PX <= 0.5
+    pool = ops.SlicePool.from_numpy(slices, dev())
+    folded = model.predict_u8(ops.normalize_resize(pool, (512, 512))).cpu().numpy()
+    assert np.abs(got.cpu().numpy() - folded).max() * PX <= 0.1  # same network, stem weights folded vs not
+    rgb = torch.randn(2, 3, 256, 384, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        want_rgb = om(rgb).numpy()
+    got_rgb = model(rgb.to(dev()).half()).cpu().numpy()
+    assert np.abs(got_rgb - want_rgb).max() <= 1.0 / PX
+    assert model.eval() is model and model.to("cuda:0") is model and torch.equal(model.predict(rgb), model(rgb))
+    with pytest.raises(ValueError):
+        model(torch.zeros(2, 1, 64, 64))
+
+
 def test_checkpoint_roundtrip_and_predict_api(tmp_path):
     om = make_model("base", seed=0)
     ck = tmp_path / "best_model.pt"
