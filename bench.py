@@ -280,7 +280,26 @@ def run_b200(args):
     k4_out = torch.empty((k4_p, 3, *SECOND_SIZE), dtype=torch.float32, device=dev)
     k4_ms = 0.0
     ops.normalize_resize(pool, IMAGE_SIZE, out=k1_out)  # workspace allocation outside the events
+    # K0 (+ the fused K0+K1 call of the end-to-end path) timed alone on resident source planes
+    k0_vols = series.host.to(dev)
+    k0_desc = series.chunk_descs(0, B).to(dev)
+    k0_pool = ops.SlicePool(torch.empty_like(pool.data), pool.offs, pool.hw, list(pool.shapes))
+    k0_ms = k01_ms = 0.0
+    ops.midplane_resample_into(k0_vols, k0_desc, k0_pool)
+    ops.midplane_normalize_resize(k0_vols, k0_desc, k0_pool, IMAGE_SIZE, out=k1_out)
     torch.cuda.synchronize()
+    for _ in range(args.steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record()
+        ops.midplane_resample_into(k0_vols, k0_desc, k0_pool)
+        ev[1].record()
+        ev[2].record()
+        ops.midplane_normalize_resize(k0_vols, k0_desc, k0_pool, IMAGE_SIZE, out=k1_out)
+        ev[3].record()
+        torch.cuda.synchronize()
+        k0_ms += ev[0].elapsed_time(ev[1])
+        k01_ms += ev[2].elapsed_time(ev[3])
+    del k0_vols, k0_desc, k0_pool
     for _ in range(args.steps):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
@@ -376,7 +395,8 @@ def run_b200(args):
                          "timing": "CUDA event pair around every launch, separate pass over the same steps",
                          "whole_step_frac_of_tensor_ceiling": value / world / ceiling, "tensor_ceiling_series_per_s": ceiling},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
-                                   "k3_crop_resample": k3_ms / args.steps},
+                                   "k3_crop_resample": k3_ms / args.steps, "k0_midplane_resample (e2e path only)": k0_ms / args.steps,
+                                   "k0_k1_fused (e2e path only)": k01_ms / args.steps},
             "fp32_kernels": {"dwconv_ln": {"flops_per_step": dw_flops, "achieved_tflops": dw_flops / (dw_ms * 1e-3) / 1e12 if dw_ms else None,
                                            "fp32_peak_tflops_nominal": 72.0, "hbm_bytes_per_step": dw_bytes,
                                            "achieved_gbs": dw_gbs, "hbm_peak_gbs": hbm, "frac_of_hbm": dw_gbs / hbm if dw_gbs else None,

@@ -348,22 +348,31 @@ int svb_mha_read_batch_slab_f32(const char* const* paths, int n, const svb_mha_i
 
 /* DICOM series (one slice per file) -- replaces read_medical_image -> read_dicom_series -> sitk.ImageSeriesReader over
  * GDCM for the Phenikaa series directories (spine_vision/io/readers.py:48-73, 128-161; phenikaa.py:178).  Part-10 files,
- * implicit / explicit VR little endian or explicit big endian, NATIVE pixel data (compressed transfer syntaxes give
- * SVB_ERR_FORMAT), monochrome 8 / 16 / 32 bit.  The C side parses and decodes single files on a thread pool; series
+ * implicit / explicit VR little endian or explicit big endian with native pixel data, and the two lossless ENCAPSULATED
+ * transfer syntaxes MR exports use: RLE Lossless (1.2.840.10008.1.2.5, PS3.5 Annex G) and JPEG Lossless, process 14
+ * (1.2.840.10008.1.2.4.57 and .70: ITU-T T.81 Annex H, Huffman, predictors 1-7, restart intervals); GDCM decodes both for
+ * the reference.  Lossy JPEG, JPEG-LS and JPEG 2000 give SVB_ERR_FORMAT.  Monochrome 8 / 16 / 32 bit; BitsStored <
+ * BitsAllocated is masked / sign-extended like GDCM does; MONOCHROME1 gives SVB_ERR_FORMAT (ITK inverts it to MONOCHROME2:
+ * never decoded un-inverted behind the caller's back).  The C side parses and decodes single files on a thread pool; series
  * selection, slice ordering and the volume geometry (the ITK conventions) are host logic in spine_vision_b200/hostio.py.
  * Parity is UNPINNED (SimpleITK / GDCM are absent from the build image; restated in oracle/dicom.py).
  */
 typedef struct svb_dicom_info {
     int32_t rows, cols, bits_allocated, pixel_representation, samples_per_pixel, monochrome1;
-    int32_t instance_number, big_endian, has_position, has_orientation, has_spacing, pad;
+    int32_t instance_number, big_endian, has_position, has_orientation, has_spacing;
+    int32_t encapsulation;          /* SVB_DICOM_NATIVE / _RLE / _JPEG_LOSSLESS: how (7FE0,0010) is stored */
     double pixel_spacing[2];        /* (0028,0030): row spacing (between rows), column spacing */
     double position[3];             /* (0020,0032) ImagePositionPatient */
     double orientation[6];          /* (0020,0037) ImageOrientationPatient: row cosines, column cosines */
     double rescale_slope, rescale_intercept; /* (0028,1053), (0028,1052); applied by svb_dicom_read_slices_f32 */
     double slice_thickness, spacing_between_slices;
-    int64_t pixel_offset, pixel_bytes; /* (7FE0,0010) */
+    int64_t pixel_offset, pixel_bytes; /* (7FE0,0010): native = the samples; encapsulated = the first item .. end of file */
+    int32_t bits_stored, pad;       /* (0028,0101) */
     char series_uid[72];            /* (0020,000E) */
 } svb_dicom_info;
+#define SVB_DICOM_NATIVE 0
+#define SVB_DICOM_RLE 1
+#define SVB_DICOM_JPEG_LOSSLESS 2
 /* rcs (optional, [n]) = per-file status: files that are not (supported) DICOM are dropped by the caller */
 int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* infos, int n_threads, int32_t* rcs);
 /* slice i -> h_dsts[i] (rows*cols float32, stored value * slope + intercept), on n_threads workers */

@@ -55,11 +55,11 @@ class DicomInfo(C.Structure):
 
     _fields_ = [("rows", C.c_int32), ("cols", C.c_int32), ("bits_allocated", C.c_int32), ("pixel_representation", C.c_int32),
                 ("samples_per_pixel", C.c_int32), ("monochrome1", C.c_int32), ("instance_number", C.c_int32), ("big_endian", C.c_int32),
-                ("has_position", C.c_int32), ("has_orientation", C.c_int32), ("has_spacing", C.c_int32), ("pad", C.c_int32),
+                ("has_position", C.c_int32), ("has_orientation", C.c_int32), ("has_spacing", C.c_int32), ("encapsulation", C.c_int32),
                 ("pixel_spacing", C.c_double * 2), ("position", C.c_double * 3), ("orientation", C.c_double * 6),
                 ("rescale_slope", C.c_double), ("rescale_intercept", C.c_double), ("slice_thickness", C.c_double),
                 ("spacing_between_slices", C.c_double), ("pixel_offset", C.c_int64), ("pixel_bytes", C.c_int64),
-                ("series_uid", C.c_char * 72)]
+                ("bits_stored", C.c_int32), ("pad", C.c_int32), ("series_uid", C.c_char * 72)]
 
 
 class WeightDesc(C.Structure):

@@ -24,6 +24,7 @@
 #include <stdexcept>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/spine_b200.h"
@@ -561,7 +562,9 @@ int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* k
                 if (ts == "1.2.840.10008.1.2") c.explicit_vr = false;
                 else if (ts == "1.2.840.10008.1.2.1") c.explicit_vr = true;
                 else if (ts == "1.2.840.10008.1.2.2") { c.explicit_vr = true; c.big = true; }
-                else return set_error(SVB_ERR_FORMAT, "%s: transfer syntax %s (compressed pixel data) is not supported", path, ts.c_str());
+                else if (ts == "1.2.840.10008.1.2.5") { c.explicit_vr = true; info->encapsulation = SVB_DICOM_RLE; }
+                else if (ts == "1.2.840.10008.1.2.4.57" || ts == "1.2.840.10008.1.2.4.70") { c.explicit_vr = true; info->encapsulation = SVB_DICOM_JPEG_LOSSLESS; }
+                else return set_error(SVB_ERR_FORMAT, "%s: transfer syntax %s is not supported (native, RLE Lossless and JPEG Lossless are)", path, ts.c_str());
                 info->big_endian = c.big ? 1 : 0;
             }
         }
@@ -570,9 +573,12 @@ int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* k
         uint32_t len;
         if (!dcm_next(c, g, e, vr, len)) break;
         if (g == 0x7FE0 && e == 0x0010) {
-            if (len == 0xFFFFFFFFu) return set_error(SVB_ERR_FORMAT, "%s: encapsulated pixel data is not supported", path);
+            if ((len == 0xFFFFFFFFu) != (info->encapsulation != SVB_DICOM_NATIVE))
+                return set_error(SVB_ERR_FORMAT, "%s: pixel data %s but the transfer syntax says %s", path,
+                                 len == 0xFFFFFFFFu ? "is encapsulated" : "has a defined length", info->encapsulation ? "encapsulated" : "native");
             info->pixel_offset = (int64_t)c.pos;
-            info->pixel_bytes = (int64_t)len;
+            info->pixel_bytes = len == 0xFFFFFFFFu ? (int64_t)(c.n - c.pos) : (int64_t)len;
+            if (len != 0xFFFFFFFFu && c.pos + len > c.n) return set_error(SVB_ERR_FORMAT, "%s: pixel data runs past the end of the file", path);
             break;
         }
         if (len == 0xFFFFFFFFu) {
@@ -594,6 +600,7 @@ int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* k
             case 0x00280011: if (len >= 2) { DcmCursor t = c; info->cols = t.u16(); } break;
             case 0x00280030: if (dcm_numbers(dcm_str(c, len), d, 2) == 2) { info->pixel_spacing[0] = d[0]; info->pixel_spacing[1] = d[1]; info->has_spacing = 1; } break;
             case 0x00280100: if (len >= 2) { DcmCursor t = c; info->bits_allocated = t.u16(); } break;
+            case 0x00280101: if (len >= 2) { DcmCursor t = c; info->bits_stored = t.u16(); } break;
             case 0x00280103: if (len >= 2) { DcmCursor t = c; info->pixel_representation = t.u16(); } break;
             case 0x00281052: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_intercept = d[0]; break;
             case 0x00281053: if (dcm_numbers(dcm_str(c, len), d, 1) == 1) info->rescale_slope = d[0]; break;
@@ -608,14 +615,23 @@ int dicom_header(const char* path, svb_dicom_info* info, std::vector<uint8_t>* k
     if (info->samples_per_pixel != 1) return set_error(SVB_ERR_FORMAT, "%s: %d samples per pixel (monochrome only)", path, info->samples_per_pixel);
     if (info->bits_allocated != 8 && info->bits_allocated != 16 && info->bits_allocated != 32)
         return set_error(SVB_ERR_FORMAT, "%s: BitsAllocated = %d", path, info->bits_allocated);
-    const int64_t need = (int64_t)info->rows * info->cols * (info->bits_allocated / 8);
+    if (info->bits_stored <= 0 || info->bits_stored > info->bits_allocated) info->bits_stored = info->bits_allocated;
+    if (info->monochrome1)
+        return set_error(SVB_ERR_FORMAT, "%s: PhotometricInterpretation MONOCHROME1 (ITK / GDCM invert it to MONOCHROME2; not decoded here)", path);
+    if (info->encapsulation != SVB_DICOM_NATIVE && info->bits_allocated > 16)
+        return set_error(SVB_ERR_FORMAT, "%s: encapsulated pixel data with BitsAllocated = %d", path, info->bits_allocated);
+    const int64_t need = info->encapsulation != SVB_DICOM_NATIVE ? 8 : (int64_t)info->rows * info->cols * (info->bits_allocated / 8);
     if (info->pixel_bytes < need) return set_error(SVB_ERR_FORMAT, "%s: pixel data holds %lld bytes, %lld expected", path, (long long)info->pixel_bytes, (long long)need);
     return SVB_OK;
 }
 
+// stored value -> float: BitsStored < BitsAllocated is masked (unsigned) or sign-extended from the high stored bit (signed),
+// as GDCM's "rescale stored bits" step does; then slope / intercept in double like ITK's rescale functor
 template <typename S>
-void convert_rescaled(const uint8_t* src, size_t n, bool swap, double slope, double intercept, float* dst) {
+void convert_rescaled(const uint8_t* src, size_t n, bool swap, double slope, double intercept, int bits_stored, float* dst) {
     const bool identity = slope == 1.0 && intercept == 0.0;
+    const int bits = (int)sizeof(S) * 8;
+    const bool narrow = bits_stored > 0 && bits_stored < bits;
     for (size_t i = 0; i < n; ++i) {
         uint8_t b[sizeof(S)];
         memcpy(b, src + i * sizeof(S), sizeof(S));
@@ -623,30 +639,266 @@ void convert_rescaled(const uint8_t* src, size_t n, bool swap, double slope, dou
             for (size_t k = 0; k < sizeof(S) / 2; ++k) { const uint8_t t = b[k]; b[k] = b[sizeof(S) - 1 - k]; b[sizeof(S) - 1 - k] = t; }
         S v;
         memcpy(&v, b, sizeof(S));
+        if (narrow) {
+            using U = typename std::make_unsigned<S>::type;
+            U u = static_cast<U>(v) & static_cast<U>((U(1) << bits_stored) - 1);
+            if (std::is_signed<S>::value && (u >> (bits_stored - 1)) & 1) u |= static_cast<U>(~U(0) << bits_stored);
+            v = static_cast<S>(u);
+        }
         dst[i] = identity ? static_cast<float>(v) : static_cast<float>(static_cast<double>(v) * slope + intercept);
     }
 }
 
+// ---- encapsulated pixel data (PS3.5 A.4): items (FFFE,E000) -- the first is the Basic Offset Table, the rest are fragments
+// of the one frame -- up to the sequence delimiter (FFFE,E0DD).  Returns the concatenated fragments.
+int dcm_fragments(const uint8_t* p, size_t n, std::vector<uint8_t>& out, const char* path) {
+    size_t pos = 0;
+    bool first = true;
+    out.clear();
+    for (;;) {
+        if (pos + 8 > n) return set_error(SVB_ERR_FORMAT, "%s: encapsulated pixel data ends without a sequence delimiter", path);
+        const uint16_t g = (uint16_t)(p[pos] | (p[pos + 1] << 8)), e = (uint16_t)(p[pos + 2] | (p[pos + 3] << 8));
+        const uint32_t len = (uint32_t)p[pos + 4] | (uint32_t)p[pos + 5] << 8 | (uint32_t)p[pos + 6] << 16 | (uint32_t)p[pos + 7] << 24;
+        pos += 8;
+        if (g == 0xFFFE && e == 0xE0DD) break;
+        if (g != 0xFFFE || e != 0xE000) return set_error(SVB_ERR_FORMAT, "%s: unexpected tag (%04x,%04x) inside encapsulated pixel data", path, g, e);
+        if (len == 0xFFFFFFFFu || pos + len > n) return set_error(SVB_ERR_FORMAT, "%s: pixel data fragment runs past the end of the file", path);
+        if (!first) out.insert(out.end(), p + pos, p + pos + len);
+        first = false;
+        pos += len;
+    }
+    if (out.empty()) return set_error(SVB_ERR_FORMAT, "%s: encapsulated pixel data has no fragment", path);
+    return SVB_OK;
+}
+
+// ---- RLE Lossless (PS3.5 Annex G): 64-byte header (segment count + 15 offsets), every segment one PackBits-coded BYTE plane of
+// the frame, most significant byte first.  Output: little-endian samples of `bytes_per_sample` bytes.
+int rle_decode(const std::vector<uint8_t>& cs, size_t n_px, int bytes_per_sample, std::vector<uint8_t>& raw, const char* path) {
+    if (cs.size() < 64) return set_error(SVB_ERR_FORMAT, "%s: RLE frame shorter than its header", path);
+    auto rd32 = [&](size_t o) { return (uint32_t)cs[o] | (uint32_t)cs[o + 1] << 8 | (uint32_t)cs[o + 2] << 16 | (uint32_t)cs[o + 3] << 24; };
+    const uint32_t nseg = rd32(0);
+    if ((int)nseg != bytes_per_sample) return set_error(SVB_ERR_FORMAT, "%s: RLE frame has %u segments, %d expected", path, nseg, bytes_per_sample);
+    raw.assign(n_px * (size_t)bytes_per_sample, 0);
+    for (uint32_t sgi = 0; sgi < nseg; ++sgi) {
+        const size_t lo = rd32(4 + 4 * sgi), hi = sgi + 1 < nseg ? rd32(8 + 4 * sgi) : cs.size();
+        if (lo < 64 || lo > hi || hi > cs.size()) return set_error(SVB_ERR_FORMAT, "%s: RLE segment %u has bad offsets", path, sgi);
+        const int byte_pos = bytes_per_sample - 1 - (int)sgi;  // segment 0 = most significant byte
+        size_t o = 0, q = lo;
+        while (o < n_px && q < hi) {
+            const int8_t c = (int8_t)cs[q++];
+            if (c >= 0) {  // literal run of c + 1 bytes
+                const size_t run = (size_t)c + 1;
+                if (q + run > hi) return set_error(SVB_ERR_FORMAT, "%s: RLE literal run leaves its segment", path);
+                for (size_t k = 0; k < run && o < n_px; ++k, ++o) raw[o * bytes_per_sample + byte_pos] = cs[q + k];
+                q += run;
+            } else if (c != -128) {  // replicate the next byte 1 - c times
+                if (q >= hi) return set_error(SVB_ERR_FORMAT, "%s: RLE replicate run leaves its segment", path);
+                const size_t run = (size_t)(1 - (int)c);
+                const uint8_t v = cs[q++];
+                for (size_t k = 0; k < run && o < n_px; ++k, ++o) raw[o * bytes_per_sample + byte_pos] = v;
+            }
+        }
+        if (o < n_px) return set_error(SVB_ERR_FORMAT, "%s: RLE segment %u decodes to %zu of %zu bytes", path, sgi, o, n_px);
+    }
+    return SVB_OK;
+}
+
+// ---- JPEG Lossless, process 14 (ITU-T T.81 Annex H): SOF3, one component, Huffman-coded differences to one of the seven
+// predictors, point transform, restart intervals.  Output: little-endian uint16 samples (or bytes for precision <= 8 when
+// `bytes_per_sample` is 1).
+struct JpgHuff {
+    int mincode[17], maxcode[18], valptr[17];
+    uint8_t vals[256];
+    bool present = false;
+};
+struct JpgBits {
+    const uint8_t* p;
+    size_t n, pos;
+    uint32_t acc = 0;
+    int cnt = 0;
+    bool hit_marker = false;
+    int bit() {
+        if (cnt == 0) {
+            uint8_t b = 0;
+            if (pos < n && !hit_marker) {
+                b = p[pos++];
+                if (b == 0xFF) {
+                    if (pos < n && p[pos] == 0x00) ++pos;  // stuffed zero
+                    else { hit_marker = true; --pos; b = 0; }  // a marker: feed zeros (the caller resynchronises at RSTn)
+                }
+            }
+            acc = b;
+            cnt = 8;
+        }
+        --cnt;
+        return (acc >> cnt) & 1;
+    }
+    int bits(int k) { int v = 0; while (k-- > 0) v = (v << 1) | bit(); return v; }
+};
+int jpeg_lossless_decode(const std::vector<uint8_t>& cs, int rows, int cols, int bytes_per_sample, std::vector<uint8_t>& raw, const char* path) {
+    const uint8_t* p = cs.data();
+    const size_t n = cs.size();
+    if (n < 4 || p[0] != 0xFF || p[1] != 0xD8) return set_error(SVB_ERR_FORMAT, "%s: JPEG stream has no SOI marker", path);
+    JpgHuff huff[4];
+    int precision = 0, restart = 0, comp_table = 0, predictor = 0, pt = 0, width = 0, height = 0;
+    size_t pos = 2, scan = 0;
+    while (pos + 4 <= n && scan == 0) {
+        if (p[pos] != 0xFF) return set_error(SVB_ERR_FORMAT, "%s: JPEG marker expected at byte %zu", path, pos);
+        const uint8_t m = p[pos + 1];
+        if (m == 0xFF) { ++pos; continue; }  // fill byte
+        const size_t seg = ((size_t)p[pos + 2] << 8) | p[pos + 3];
+        if (seg < 2 || pos + 2 + seg > n) return set_error(SVB_ERR_FORMAT, "%s: JPEG segment %02x runs past the stream", path, m);
+        const uint8_t* d = p + pos + 4;
+        const size_t dl = seg - 2;
+        if (m == 0xC3) {  // SOF3: lossless, Huffman
+            if (dl < 6 + 3 || d[5] != 1) return set_error(SVB_ERR_FORMAT, "%s: lossless JPEG with %d components (1 supported)", path, dl >= 6 ? d[5] : 0);
+            precision = d[0]; height = (d[1] << 8) | d[2]; width = (d[3] << 8) | d[4];
+        } else if (m >= 0xC0 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+            return set_error(SVB_ERR_FORMAT, "%s: JPEG frame type SOF%d is not lossless Huffman (SOF3)", path, m - 0xC0);
+        } else if (m == 0xC4) {  // DHT: one or more tables
+            size_t q = 0;
+            while (q + 17 <= dl) {
+                const int tc = d[q] >> 4, th = d[q] & 15;
+                if (tc != 0 || th > 3) return set_error(SVB_ERR_FORMAT, "%s: bad Huffman table id %02x", path, d[q]);
+                int counts[17] = {0}, total = 0;
+                for (int i = 1; i <= 16; ++i) { counts[i] = d[q + i]; total += counts[i]; }
+                if (total > 256 || q + 17 + (size_t)total > dl) return set_error(SVB_ERR_FORMAT, "%s: Huffman table runs past its segment", path);
+                JpgHuff& h = huff[th];
+                memcpy(h.vals, d + q + 17, (size_t)total);
+                int code = 0, k = 0;
+                for (int i = 1; i <= 16; ++i) {  // T.81 Annex C / F.2.2.3
+                    h.valptr[i] = k;
+                    h.mincode[i] = code;
+                    code += counts[i];
+                    k += counts[i];
+                    h.maxcode[i] = counts[i] ? code - 1 : -1;
+                    code <<= 1;
+                }
+                h.maxcode[17] = 0x7FFFFFFF;
+                h.present = true;
+                q += 17 + (size_t)total;
+            }
+        } else if (m == 0xDD) {  // DRI
+            if (dl >= 2) restart = (d[0] << 8) | d[1];
+        } else if (m == 0xDA) {  // SOS
+            if (dl < 6 || d[0] != 1) return set_error(SVB_ERR_FORMAT, "%s: scan with %d components (1 supported)", path, dl ? d[0] : 0);
+            comp_table = d[2] >> 4;
+            predictor = d[3];
+            pt = d[5] & 15;
+            scan = pos + 2 + seg;
+        }
+        pos += 2 + seg;
+    }
+    if (!scan || precision < 2 || precision > 16) return set_error(SVB_ERR_FORMAT, "%s: lossless JPEG without SOF3 / SOS (precision %d)", path, precision);
+    if (width != cols || height != rows) return set_error(SVB_ERR_FORMAT, "%s: JPEG frame is %dx%d, the DICOM header says %dx%d", path, height, width, rows, cols);
+    if (predictor < 1 || predictor > 7) return set_error(SVB_ERR_FORMAT, "%s: lossless predictor %d", path, predictor);
+    if (comp_table > 3 || !huff[comp_table].present) return set_error(SVB_ERR_FORMAT, "%s: scan refers to a missing Huffman table", path);
+    if (precision > 8 * bytes_per_sample) return set_error(SVB_ERR_FORMAT, "%s: JPEG precision %d exceeds BitsAllocated %d", path, precision, 8 * bytes_per_sample);
+    if (restart && restart % cols != 0) return set_error(SVB_ERR_FORMAT, "%s: restart interval %d is not a whole number of lines", path, restart);
+    const JpgHuff& h = huff[comp_table];
+    std::vector<uint16_t> img((size_t)rows * cols);
+    JpgBits br{p, n, scan};
+    const int init = 1 << (precision - pt - 1);
+    long long in_interval = 0;
+    bool fresh = true;  // the next line starts a restart interval (or the scan): predict as on the first line
+    for (int y = 0; y < rows; ++y) {
+        if (restart && y > 0 && in_interval == restart) {  // expect RSTn, byte-align, reset the prediction
+            br.cnt = 0;
+            if (!br.hit_marker) {  // skip to the marker (padding bits were 1s inside the last byte)
+                while (br.pos + 1 < n && !(p[br.pos] == 0xFF && p[br.pos + 1] >= 0xD0 && p[br.pos + 1] <= 0xD7)) ++br.pos;
+            }
+            if (br.pos + 1 >= n || p[br.pos] != 0xFF || p[br.pos + 1] < 0xD0 || p[br.pos + 1] > 0xD7)
+                return set_error(SVB_ERR_FORMAT, "%s: restart marker missing before line %d", path, y);
+            br.pos += 2;
+            br.hit_marker = false;
+            in_interval = 0;
+            fresh = true;
+        }
+        uint16_t* row = img.data() + (size_t)y * cols;
+        const uint16_t* up = y > 0 ? row - cols : nullptr;
+        for (int x = 0; x < cols; ++x) {
+            int code = 0, len = 0, s = -1;  // DECODE (T.81 F.2.2.3)
+            for (len = 1; len <= 16; ++len) {
+                code = (code << 1) | br.bit();
+                if (h.maxcode[len] >= 0 && code <= h.maxcode[len] && code >= h.mincode[len]) { s = h.vals[h.valptr[len] + code - h.mincode[len]]; break; }
+            }
+            if (s < 0 || s > 16) return set_error(SVB_ERR_FORMAT, "%s: corrupt Huffman code at line %d column %d", path, y, x);
+            int diff;
+            if (s == 0) diff = 0;
+            else if (s == 16) diff = 32768;
+            else {
+                diff = br.bits(s);
+                if (diff < (1 << (s - 1))) diff -= (1 << s) - 1;  // EXTEND
+            }
+            int pred;
+            if (fresh) pred = x == 0 ? init : row[x - 1];            // first line of the scan / of a restart interval
+            else if (x == 0) pred = up[0];                            // first sample of the other lines: the one above
+            else {
+                const int ra = row[x - 1], rb = up[x], rc = up[x - 1];
+                switch (predictor) {
+                    case 1: pred = ra; break;
+                    case 2: pred = rb; break;
+                    case 3: pred = rc; break;
+                    case 4: pred = ra + rb - rc; break;
+                    case 5: pred = ra + ((rb - rc) >> 1); break;
+                    case 6: pred = rb + ((ra - rc) >> 1); break;
+                    default: pred = (ra + rb) >> 1; break;
+                }
+            }
+            row[x] = (uint16_t)((pred + diff) & 0xFFFF);
+        }
+        if (br.hit_marker && !(restart && y + 1 < rows && in_interval + cols == restart) && y + 1 < rows)
+            return set_error(SVB_ERR_FORMAT, "%s: JPEG entropy data ends at line %d of %d", path, y + 1, rows);
+        in_interval += cols;
+        fresh = false;
+    }
+    raw.resize((size_t)rows * cols * bytes_per_sample);
+    for (size_t i = 0; i < (size_t)rows * cols; ++i) {
+        const uint16_t v = (uint16_t)(img[i] << pt);
+        raw[i * bytes_per_sample] = (uint8_t)v;
+        if (bytes_per_sample > 1) raw[i * bytes_per_sample + 1] = (uint8_t)(v >> 8);
+    }
+    return SVB_OK;
+}
+
 int dicom_pixels(const char* path, const svb_dicom_info* info, float* dst, size_t dst_elems) {
     if (!path || !info || !dst) return set_error(SVB_ERR_INVALID_ARG, "dicom: null argument");
+    if (info->rows <= 0 || info->cols <= 0) return set_error(SVB_ERR_INVALID_ARG, "dicom: bad size %d x %d", info->rows, info->cols);
     const size_t n = (size_t)info->rows * info->cols;
     if (dst_elems < n) return set_error(SVB_ERR_WORKSPACE_TOO_SMALL, "dicom: destination holds %zu elements, slice has %zu", dst_elems, n);
-    const size_t bytes = n * (size_t)(info->bits_allocated / 8);
+    const int bps = info->bits_allocated / 8;
+    const size_t bytes = n * (size_t)bps;
+    const size_t to_read = info->encapsulation != SVB_DICOM_NATIVE ? (size_t)(info->pixel_bytes > 0 ? info->pixel_bytes : 0) : bytes;
     FILE* f = fopen(path, "rb");
     if (!f) return set_error(SVB_ERR_IO, "cannot open %s: %s", path, strerror(errno));
-    std::vector<uint8_t> raw(bytes);
-    const bool ok = fseek(f, (long)info->pixel_offset, SEEK_SET) == 0 && fread(raw.data(), 1, bytes, f) == bytes;
+    std::vector<uint8_t> raw(to_read);
+    const bool ok = fseek(f, (long)info->pixel_offset, SEEK_SET) == 0 && fread(raw.data(), 1, to_read, f) == to_read;
     fclose(f);
     if (!ok) return set_error(SVB_ERR_IO, "%s: pixel data truncated", path);
-    const uint16_t probe = 1;
-    const bool host_big = *reinterpret_cast<const uint8_t*>(&probe) == 0;
-    const bool swap = (info->big_endian != 0) != host_big;
+    bool swap;
+    if (info->encapsulation != SVB_DICOM_NATIVE) {
+        std::vector<uint8_t> cs, dec;
+        if (int rc = dcm_fragments(raw.data(), raw.size(), cs, path)) return rc;
+        if (info->encapsulation == SVB_DICOM_RLE) {
+            if (int rc = rle_decode(cs, n, bps, dec, path)) return rc;
+        } else {
+            if (int rc = jpeg_lossless_decode(cs, info->rows, info->cols, bps, dec, path)) return rc;
+        }
+        raw.swap(dec);  // little-endian samples
+        const uint16_t probe = 1;
+        swap = *reinterpret_cast<const uint8_t*>(&probe) == 0;
+    } else {
+        const uint16_t probe = 1;
+        const bool host_big = *reinterpret_cast<const uint8_t*>(&probe) == 0;
+        swap = (info->big_endian != 0) != host_big;
+    }
     const double sl = info->rescale_slope, ic = info->rescale_intercept;
     const bool sgn = info->pixel_representation != 0;
+    const int bs = info->bits_stored;
     switch (info->bits_allocated) {
-        case 8: sgn ? convert_rescaled<int8_t>(raw.data(), n, false, sl, ic, dst) : convert_rescaled<uint8_t>(raw.data(), n, false, sl, ic, dst); break;
-        case 16: sgn ? convert_rescaled<int16_t>(raw.data(), n, swap, sl, ic, dst) : convert_rescaled<uint16_t>(raw.data(), n, swap, sl, ic, dst); break;
-        default: sgn ? convert_rescaled<int32_t>(raw.data(), n, swap, sl, ic, dst) : convert_rescaled<uint32_t>(raw.data(), n, swap, sl, ic, dst); break;
+        case 8: sgn ? convert_rescaled<int8_t>(raw.data(), n, false, sl, ic, bs, dst) : convert_rescaled<uint8_t>(raw.data(), n, false, sl, ic, bs, dst); break;
+        case 16: sgn ? convert_rescaled<int16_t>(raw.data(), n, swap, sl, ic, bs, dst) : convert_rescaled<uint16_t>(raw.data(), n, swap, sl, ic, bs, dst); break;
+        default: sgn ? convert_rescaled<int32_t>(raw.data(), n, swap, sl, ic, bs, dst) : convert_rescaled<uint32_t>(raw.data(), n, swap, sl, ic, bs, dst); break;
     }
     return SVB_OK;
 }
@@ -760,14 +1012,22 @@ int svb_mha_read_batch_slab_f32(const char* const* paths, int n, const svb_mha_i
 
 int svb_dicom_read_headers(const char* const* paths, int n, svb_dicom_info* infos, int n_threads, int32_t* rcs) {
     if (n < 0 || (n > 0 && (!paths || !infos))) return set_error(SVB_ERR_INVALID_ARG, "dicom headers: bad arguments (n=%d)", n);
-    std::atomic<int> n_bad{0};
+    std::atomic<int> n_bad{0}, first_bad{-1};
+    std::vector<std::string> msgs((size_t)(n > 0 ? n : 0));
     parallel_for(n, n_threads, [&](int i) {
         const int rc = guarded("dicom headers", [&] { return dicom_header(paths[i], &infos[i], nullptr); });
         if (rcs) rcs[i] = rc;
-        if (rc != SVB_OK) n_bad.fetch_add(1);
+        if (rc != SVB_OK) {
+            n_bad.fetch_add(1);
+            msgs[i] = svb_last_error();  // thread-local in the worker
+            int expect = -1;
+            first_bad.compare_exchange_strong(expect, i);
+        }
     });
     // files that are not DICOM (or not a supported one) are the caller's to drop, like GDCM's directory scan does
-    return n_bad.load() ? set_error(SVB_ERR_FORMAT, "dicom headers: %d of %d files are not supported DICOM slices", n_bad.load(), n) : SVB_OK;
+    return n_bad.load() ? set_error(SVB_ERR_FORMAT, "dicom headers: %d of %d files are not supported DICOM slices; first: %s", n_bad.load(), n,
+                                    msgs[first_bad.load()].c_str())
+                        : SVB_OK;
 }
 
 int svb_dicom_read_slices_f32(const char* const* paths, int n, const svb_dicom_info* infos, float* const* h_dsts,

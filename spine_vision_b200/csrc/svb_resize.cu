@@ -1156,49 +1156,54 @@ __global__ void k0_table_kernel(const svb_k0_series* __restrict__ desc, int max_
     taps[((size_t)blockIdx.z * 2 + which) * (size_t)max(max_h, max_w) + i] = t;
 }
 
-// grid (tiles, B): one thread per output pixel
+// grid (ceil(max_w / 32), ceil(max_h / K0_ROWS), B), block (32, 8): a thread owns one output column of a K0_ROWS-row band
+// (column tap loaded once, rows strided by 8) -- no index division per pixel, coalesced stores along the row.
+constexpr int K0_ROWS = 32;
 __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restrict__ vol, const svb_k0_series* __restrict__ desc,
                                                           int max_h, int max_w, const K0Tap* __restrict__ taps,
                                                           float* __restrict__ out, uint32_t* __restrict__ keys) {
-    const svb_k0_series d = desc[blockIdx.y];
+    const svb_k0_series d = desc[blockIdx.z];
     const int stride = max(max_h, max_w);
-    const K0Tap* rt = taps + ((size_t)blockIdx.y * 2 + 0) * stride;
-    const K0Tap* ct = taps + ((size_t)blockIdx.y * 2 + 1) * stride;
+    const K0Tap* rt = taps + ((size_t)blockIdx.z * 2 + 0) * stride;
+    const K0Tap* ct = taps + ((size_t)blockIdx.z * 2 + 1) * stride;
     const float* v = vol + d.vol_off;
     float* o = out + d.out_off;
     const long long sx = 1, sy = d.nx, sz = (long long)d.nx * d.ny;
     const long long s_row = d.ax_row == 0 ? sx : (d.ax_row == 1 ? sy : sz);
     const long long s_col = d.ax_col == 0 ? sx : (d.ax_col == 1 ? sy : sz);
     const long long s_fix = d.ax_fix == 0 ? sx : (d.ax_fix == 1 ? sy : sz);
-    const long long n = (long long)d.out_h * d.out_w;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int r0 = blockIdx.y * K0_ROWS;
     float mn = INFINITY, mx = -INFINITY;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(p / d.out_w), c = (int)(p - (long long)r * d.out_w);
-        const K0Tap tr = rt[r], tc = ct[c];
-        float res = 0.0f;
-        if (tr.inside && tc.inside && d.fix_inside) {
-            // per image axis a: (lo, hi, frac); the nested lerp always runs x, then y, then z
-            long long lo[3], hi[3];
-            double fr[3];
-            lo[d.ax_row] = tr.lo * s_row; hi[d.ax_row] = tr.hi * s_row; fr[d.ax_row] = tr.frac;
-            lo[d.ax_col] = tc.lo * s_col; hi[d.ax_col] = tc.hi * s_col; fr[d.ax_col] = tc.frac;
-            lo[d.ax_fix] = d.fix_lo * s_fix; hi[d.ax_fix] = d.fix_hi * s_fix; fr[d.ax_fix] = d.fix_frac;
-            auto g = [&](long long z, long long y, long long x) -> double { return (double)__ldg(v + z + y + x); };
-            auto lerp = [](double a, double b, double f) -> double { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), f)); };
-            double pl[2];
+    if (c < d.out_w && r0 < d.out_h) {
+        const K0Tap tc = ct[c];
+        for (int r = r0 + threadIdx.y; r < min(r0 + K0_ROWS, d.out_h); r += 8) {
+            const K0Tap tr = rt[r];
+            float res = 0.0f;
+            if (tr.inside && tc.inside && d.fix_inside) {
+                // per image axis a: (lo, hi, frac); the nested lerp always runs x, then y, then z
+                long long lo[3], hi[3];
+                double fr[3];
+                lo[d.ax_row] = tr.lo * s_row; hi[d.ax_row] = tr.hi * s_row; fr[d.ax_row] = tr.frac;
+                lo[d.ax_col] = tc.lo * s_col; hi[d.ax_col] = tc.hi * s_col; fr[d.ax_col] = tc.frac;
+                lo[d.ax_fix] = d.fix_lo * s_fix; hi[d.ax_fix] = d.fix_hi * s_fix; fr[d.ax_fix] = d.fix_frac;
+                auto g = [&](long long z, long long y, long long x) -> double { return (double)__ldg(v + z + y + x); };
+                auto lerp = [](double a, double b, double f) -> double { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), f)); };
+                double pl[2];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const long long z = k == 0 ? lo[2] : hi[2];
-                const double a = lerp(g(z, lo[1], lo[0]), g(z, lo[1], hi[0]), fr[0]);
-                const double b = lerp(g(z, hi[1], lo[0]), g(z, hi[1], hi[0]), fr[0]);
-                pl[k] = lerp(a, b, fr[1]);
+                for (int k = 0; k < 2; ++k) {
+                    const long long z = k == 0 ? lo[2] : hi[2];
+                    const double a = lerp(g(z, lo[1], lo[0]), g(z, lo[1], hi[0]), fr[0]);
+                    const double b = lerp(g(z, hi[1], lo[0]), g(z, hi[1], hi[0]), fr[0]);
+                    pl[k] = lerp(a, b, fr[1]);
+                }
+                const double rd = lerp(pl[0], pl[1], fr[2]);
+                res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
             }
-            const double rd = lerp(pl[0], pl[1], fr[2]);
-            res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
+            o[(long long)r * d.out_w + c] = res;
+            mn = fminf(mn, res);
+            mx = fmaxf(mx, res);
         }
-        o[p] = res;
-        mn = fminf(mn, res);
-        mx = fmaxf(mx, res);
     }
     if (keys != nullptr) {
         // the plane's min / max while it is being written (same fminf / fmaxf reduction as k1_minmax_kernel, so K1 can skip
@@ -1206,17 +1211,17 @@ __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restric
         mn = warp_min(mn);
         mx = warp_max(mx);
         __shared__ float smn[8], smx[8];
-        const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int wid = threadIdx.y, lane = threadIdx.x;
         if (lane == 0) { smn[wid] = mn; smx[wid] = mx; }
         __syncthreads();
         if (wid == 0) {
-            mn = lane < (int)(blockDim.x >> 5) ? smn[lane] : INFINITY;
-            mx = lane < (int)(blockDim.x >> 5) ? smx[lane] : -INFINITY;
+            mn = lane < 8 ? smn[lane] : INFINITY;
+            mx = lane < 8 ? smx[lane] : -INFINITY;
             mn = warp_min(mn);
             mx = warp_max(mx);
-            if (lane == 0 && (long long)blockIdx.x * blockDim.x < n) {
-                atomicMin(&keys[2 * blockIdx.y + 0], float_key(mn));
-                atomicMax(&keys[2 * blockIdx.y + 1], float_key(mx));
+            if (lane == 0 && mn <= mx) {  // the CTA wrote at least one pixel
+                atomicMin(&keys[2 * blockIdx.z + 0], float_key(mn));
+                atomicMax(&keys[2 * blockIdx.z + 1], float_key(mx));
             }
         }
     }
@@ -1239,10 +1244,8 @@ static int k0_tables(const svb_k0_series* d_desc, int B, int max_out_h, int max_
 // series [b0, b0 + nb) of the batch the tables were built for
 static int k0_planes(const float* d_volumes, const svb_k0_series* d_desc, int b0, int nb, int max_out_h, int max_out_w,
                      const K0Tap* taps, float* d_out, uint32_t* keys, cudaStream_t stream) {
-    long long tiles = ceil_div<long long>((long long)max_out_h * max_out_w, 256 * 4);
-    if (tiles > 4096) tiles = 4096;
     const size_t stride = (size_t)(max_out_h > max_out_w ? max_out_h : max_out_w);
-    k0_midplane_kernel<<<dim3((unsigned)tiles, nb), 256, 0, stream>>>(d_volumes, d_desc + b0, max_out_h, max_out_w,
+    k0_midplane_kernel<<<dim3(ceil_div(max_out_w, 32), ceil_div(max_out_h, K0_ROWS), nb), dim3(32, 8), 0, stream>>>(d_volumes, d_desc + b0, max_out_h, max_out_w,
                                                                       taps + (size_t)b0 * 2 * stride, d_out,
                                                                       keys ? keys + 2 * (size_t)b0 : nullptr);
     SVB_LAUNCHED();

@@ -29,7 +29,7 @@ import numpy as np
 import torch
 from pydantic import field_validator, BaseModel, ConfigDict, computed_field
 
-from . import hostio, pipeline, volumes
+from . import hostio, ops, pipeline, volumes
 from .cropping import LocalizationModel, load_localization_model
 
 logger = logging.getLogger("spine_vision_b200.dataset")
@@ -317,8 +317,17 @@ def _read_chunk(jobs: list[SeriesJob], n_threads: int):
 def process_jobs(jobs: list[SeriesJob], config: ClassificationDatasetConfig, output_images_path: Path,
                  model: LocalizationModel | None) -> list[ClassificationRecord]:
     """Steps 2 and 3 of the module docstring for a list of jobs; returns the records of the crops written.
-    The three stages overlap across chunks: while the GPU works on chunk i, one host thread decodes chunk i+1 and another
-    encodes / writes the PNGs of chunk i-1 (the native decoders and the encoder release the GIL and fan out themselves)."""
+
+    A software pipeline over chunks of ``config.chunk_series`` series, so that neither the host nor the GPU waits for the other:
+
+      read   (host thread)   decode chunk i+1 (native readers, only the two source planes K0 needs)
+      A      (GPU, async)    chunk i: H2D of the source planes -> K0+K1 (fused) -> localizer; coordinates -> pinned host (async)
+      B      (host + GPU)    chunk i-1: wait for ITS coordinates (the GPU is busy with A of chunk i meanwhile); rotated mode:
+                             the exact host angle fit (np.polyfit, as the reference) -> K3 -> crops -> pinned host (async)
+      C      (host thread)   chunk i-2: PNG encode + write, records
+
+    Round 1 ran A..C of one chunk back to back with two blocking device->host reads (and, in rotated mode, a Python loop over
+    the series between the localizer and K3): the GPU idled while the host worked."""
     from concurrent.futures import ThreadPoolExecutor
 
     records: list[ClassificationRecord] = []
@@ -327,38 +336,75 @@ def process_jobs(jobs: list[SeriesJob], config: ClassificationDatasetConfig, out
     chunks = [jobs[c0 : c0 + step] for c0 in range(0, len(jobs), step)]
     if not chunks:
         return records
-    with ThreadPoolExecutor(max_workers=2) as pool_io:
-        next_read = pool_io.submit(_read_chunk, chunks[0], config.io_threads)
-        pending_write = None
-        for ci, chunk in enumerate(chunks):
-            vols = next_read.result()
-            if ci + 1 < len(chunks):
-                next_read = pool_io.submit(_read_chunk, chunks[ci + 1], config.io_threads)
-            live = []
-            for j, v in zip(chunk, vols):
-                if v is None:
-                    continue
-                if v.array.ndim != 3 or min(v.array.shape) < 1:
-                    logger.debug("Error processing %s: not a 3-D volume", j.path)
-                    continue
-                try:
-                    volumes.lpi_axes(v.direction)
-                except ValueError as e:
-                    logger.debug("Error processing %s: %s", j.path, e)
-                    continue
-                live.append((j, v))
-            if not live:
+    dev = torch.device(config.device)
+    L = pipeline.NUM_LEVELS
+
+    def stage_a(ci: int, chunk, vols):
+        live = []
+        for j, v in zip(chunk, vols):
+            if v is None:
                 continue
-            pool, spacings = volumes.midplane_resample([v.array for _, v in live], [v.spacing for _, v in live],
-                                                       [v.direction for _, v in live], config.device,
-                                                       integer_pixels=[v.integer_pixels for _, v in live],
-                                                       pixel_kinds=[v.pixel_kind for _, v in live])
-            batch = pipeline.localize_and_crop(pool, model, crop_delta_mm=config.crop_delta_mm, crop_size=(ch, cw),
-                                               image_size=config.image_size, second_size=None, spacings=spacings,
-                                               crop_mode=config.crop_mode, last_disc_angle_boost=config.last_disc_angle_boost)
-            crops = batch.crops.cpu().numpy()  # [B, 5, ch, cw]
+            if v.array.ndim != 3 or min(v.array.shape) < 1:
+                logger.debug("Error processing %s: not a 3-D volume", j.path)
+                continue
+            try:
+                volumes.lpi_axes(v.direction)
+            except ValueError as e:
+                logger.debug("Error processing %s: %s", j.path, e)
+                continue
+            live.append((j, v))
+        if not live:
+            return None
+        n = len(live)
+        pv = volumes.PinnedVolumes([v.array for _, v in live], [v.spacing for _, v in live], [v.direction for _, v in live],
+                                   integer_pixels=[v.integer_pixels for _, v in live], pixel_kinds=[v.pixel_kind for _, v in live],
+                                   cache_tag=f"dataset_slabs_{ci % 3}")  # three chunks are in flight at most
+        pool = ops.SlicePool(torch.empty(max(pv.out_total, 4), dtype=torch.float32, device=dev),
+                             torch.tensor(pv.out_offs, dtype=torch.int64).to(dev, non_blocking=True),
+                             torch.tensor(pv.shapes, dtype=torch.int32).reshape(-1, 2).to(dev, non_blocking=True), list(pv.shapes),
+                             h2d_bytes=pv.nbytes).set_pixel_kinds(pv.pixel_kinds)
+        vols_d = pv.host.to(dev, non_blocking=True)
+        desc_d = pv.chunk_descs(0, n).to(dev, non_blocking=True)
+        if model is not None:
+            planes = ops.midplane_normalize_resize(vols_d, desc_d, pool, config.image_size)
+            coords = model.predict_u8(planes)
+        else:
+            ops.midplane_resample_into(vols_d, desc_d, pool)
+            fb = pipeline.get_center_fallback_locations()  # Python floats in the reference, not model outputs: float64 for K3
+            coords = torch.tensor([fb[i] for i in range(L)], dtype=torch.float64).unsqueeze(0).repeat(n, 1, 1).to(dev)
+        coords_h = ops.PinnedCache.get(f"dataset_coords_{ci % 3}", n * L * 2, coords.dtype).view(n, L, 2)
+        coords_h.copy_(coords, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return {"live": live, "pool": pool, "spacings": pv.spacings, "coords": coords, "coords_h": coords_h, "ev": ev, "ci": ci}
+
+    def stage_b(st):
+        if st is None:
+            return None
+        st["ev"].synchronize()  # this chunk's coordinates are on the host; the GPU is already working on the next chunk
+        inv = None
+        if config.crop_mode == "rotated":
+            inv = pipeline.rotation_rows(st["coords_h"].numpy(), st["pool"].shapes, config.last_disc_angle_boost).pin_memory()
+        crops, _, _ = pipeline.crop_levels(st["pool"], st["coords"], config.crop_delta_mm, st["spacings"], (ch, cw), None,
+                                           mode=config.crop_mode, last_disc_angle_boost=config.last_disc_angle_boost, inv_affine=inv)
+        n = len(st["live"])
+        crops_h = ops.PinnedCache.get(f"dataset_crops_{st['ci'] % 3}", n * L * ch * cw, torch.uint8).view(n, L, ch, cw)
+        crops_h.copy_(crops, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        st.update(crops=crops, crops_h=crops_h, ev=ev)
+        return st
+
+    with ThreadPoolExecutor(max_workers=2) as pool_io:
+        pending_write = [None]
+
+        def stage_c(st):
+            if st is None:
+                return
+            st["ev"].synchronize()
+            crops = st["crops_h"].numpy()  # [n, 5, ch, cw]
             sel, paths, recs = [], [], []
-            for b, (j, _) in enumerate(live):
+            for b, (j, _) in enumerate(st["live"]):
                 for lvl, row in j.levels.items():
                     name = output_filename(j.source, j.patient_id, j.series_type, lvl)
                     sel.append((b, lvl - 1))
@@ -366,12 +412,26 @@ def process_jobs(jobs: list[SeriesJob], config: ClassificationDatasetConfig, out
                     recs.append(make_record(j.source, name, j.patient_id, lvl, j.series_type, row))
             if sel:
                 bi, li = zip(*sel)
-                if pending_write is not None:
-                    pending_write.result()  # raises if a file of the previous chunk could not be written
-                pending_write = pool_io.submit(hostio.write_png_batch, crops[list(bi), list(li)], paths, config.png_level, config.io_threads)
+                picked = crops[list(bi), list(li)]  # a copy: the pinned buffer is re-used three chunks later
+                if pending_write[0] is not None:
+                    pending_write[0].result()  # raises if a file of the previous chunk could not be written
+                pending_write[0] = pool_io.submit(hostio.write_png_batch, picked, paths, config.png_level, config.io_threads)
                 records.extend(recs)
-        if pending_write is not None:
-            pending_write.result()
+
+        next_read = pool_io.submit(_read_chunk, chunks[0], config.io_threads)
+        in_a = in_b = None  # the chunk whose stage A / stage B has been issued
+        for ci in range(len(chunks) + 2):
+            st_a = None
+            if ci < len(chunks):
+                vols = next_read.result()
+                if ci + 1 < len(chunks):
+                    next_read = pool_io.submit(_read_chunk, chunks[ci + 1], config.io_threads)
+                st_a = stage_a(ci, chunks[ci], vols)
+            st_b = stage_b(in_a)
+            stage_c(in_b)
+            in_a, in_b = st_a, st_b
+        if pending_write[0] is not None:
+            pending_write[0].result()
     return records
 
 

@@ -198,7 +198,12 @@ def read_dicom_files(paths, n_threads: int = 0):
     ok = [i for i in range(n) if rcs[i] == 0]
     for i in range(n):
         if rcs[i] != 0:
-            errors[i] = f"libspine_b200 error {rcs[i]}: not a supported DICOM slice: {paths[i]}"
+            # the batch call keeps only the codes (the messages are thread-local in its workers): ask again for the reason, so that
+            # a refused transfer syntax / MONOCHROME1 / truncated file is NAMED in the log instead of silently costing a series
+            one = (_lib.DicomInfo * 1)()
+            lib.svb_dicom_read_headers((C.c_char_p * 1)(os.fsencode(str(paths[i]))), 1, one, 1, None)
+            why = lib.svb_last_error().decode("utf-8", "replace")
+            errors[i] = f"libspine_b200 error {rcs[i]}: not a supported DICOM slice ({why})"
     if not ok:
         return arrays, errors
     m = len(ok)
@@ -219,6 +224,189 @@ def read_dicom_files(paths, n_threads: int = 0):
     return arrays, errors
 
 
+# ------------------------------------------------------------------------------------------ NIfTI / NRRD / single DICOM file
+# Neither dataset builder reads these (SPIDER ships .mha, Phenikaa DICOM folders); read_medical_image dispatches them
+# (io/readers.py:23-28, 76-126), so they are here for callers of that function.  Plain Python + NumPy, like the reference's own
+# reader layer; ITK's conventions restated from its documentation -- PARITY UNPINNED (SimpleITK is absent from the image).
+_NIFTI_TYPES = {2: "u1", 4: "i2", 8: "i4", 16: "f4", 64: "f8", 256: "i1", 512: "u2", 768: "u4", 1024: "i8", 1280: "u8"}
+
+
+def read_nifti(file_path: Path) -> MedicalVolume:
+    """``read_nifti`` (io/readers.py:76-86) = ``sitk.ReadImage`` = itk::NiftiImageIO for a 3-D scalar NIfTI-1 file (``.nii`` /
+    ``.nii.gz``, single file).  Restated conventions: sizes ``dim[1..3]``; voxel order x fastest -> ``[z, y, x]``;
+    ``scl_slope`` / ``scl_inter`` applied when they are not the identity (the image then is float32); orientation from the
+    qform when ``qform_code > 0`` (quaternion b, c, d and ``qfac = pixdim[0]``, spacing ``pixdim[1..3]``), else from the
+    sform rows (spacing = column norms), else identity; NIfTI is RAS+, ITK is LPS+: the x and y rows of the rotation and of
+    the offset change sign."""
+    import gzip
+    import struct
+
+    blob = Path(file_path).read_bytes()
+    if blob[:2] == b"\x1f\x8b":
+        blob = gzip.decompress(blob)
+    if len(blob) < 352:
+        raise ValueError(f"{file_path}: too short for a NIfTI-1 header")
+    end = "<" if struct.unpack_from("<i", blob, 0)[0] == 348 else ">"
+    if struct.unpack_from(end + "i", blob, 0)[0] != 348 or blob[344:347] not in (b"n+1", b"ni1"):
+        raise ValueError(f"{file_path}: not a NIfTI-1 file")
+    if blob[344:347] == b"ni1":
+        raise UnsupportedFormatError(f"{file_path}: two-file NIfTI (.hdr / .img) is not supported")
+    dim = struct.unpack_from(end + "8h", blob, 40)
+    if dim[0] < 3 or any(d > 1 for d in dim[4 : dim[0] + 1]):
+        raise UnsupportedFormatError(f"{file_path}: {dim[0]}-D NIfTI (3-D scalar volumes only)")
+    nx, ny, nz = (max(1, int(d)) for d in dim[1:4])
+    datatype = struct.unpack_from(end + "h", blob, 70)[0]
+    if datatype not in _NIFTI_TYPES:
+        raise UnsupportedFormatError(f"{file_path}: NIfTI datatype {datatype}")
+    pixdim = struct.unpack_from(end + "8f", blob, 76)
+    vox_offset = int(struct.unpack_from(end + "f", blob, 108)[0])
+    slope, inter = struct.unpack_from(end + "2f", blob, 112)
+    qform_code, sform_code = struct.unpack_from(end + "2h", blob, 252)
+    qb, qc, qd, qx, qy, qz = struct.unpack_from(end + "6f", blob, 256)
+    srow = np.array(struct.unpack_from(end + "12f", blob, 280), dtype=np.float64).reshape(3, 4)
+    dt = np.dtype(_NIFTI_TYPES[datatype]).newbyteorder(end)
+    n = nx * ny * nz
+    if len(blob) < vox_offset + n * dt.itemsize:
+        raise ValueError(f"{file_path}: voxel data truncated")
+    raw = np.frombuffer(blob, dtype=dt, count=n, offset=vox_offset).reshape(nz, ny, nx)
+    scaled = slope != 0.0 and not (slope == 1.0 and inter == 0.0)
+    arr = (raw.astype(np.float64) * float(slope) + float(inter)).astype(np.float32) if scaled else raw.astype(np.float32)
+    spacing = [float(abs(pixdim[k])) or 1.0 for k in (1, 2, 3)]
+    if qform_code > 0:
+        a2 = 1.0 - (qb * qb + qc * qc + qd * qd)
+        a = float(np.sqrt(a2)) if a2 > 1e-7 else 0.0
+        b, c, d = float(qb), float(qc), float(qd)
+        if a == 0.0:
+            nrm = 1.0 / float(np.sqrt(b * b + c * c + d * d))
+            b, c, d = b * nrm, c * nrm, d * nrm
+        R = np.array([[a * a + b * b - c * c - d * d, 2 * b * c - 2 * a * d, 2 * b * d + 2 * a * c],
+                      [2 * b * c + 2 * a * d, a * a + c * c - b * b - d * d, 2 * c * d - 2 * a * b],
+                      [2 * b * d - 2 * a * c, 2 * c * d + 2 * a * b, a * a + d * d - c * c - b * b]])
+        if pixdim[0] < 0:
+            R[:, 2] = -R[:, 2]
+        off = np.array([qx, qy, qz], dtype=np.float64)
+    elif sform_code > 0:
+        M = srow[:, :3]
+        norms = np.linalg.norm(M, axis=0)
+        spacing = [float(v) or 1.0 for v in norms]
+        R = M / np.where(norms == 0, 1.0, norms)
+        off = srow[:, 3].copy()
+    else:
+        R, off = np.eye(3), np.zeros(3)
+    flip = np.array([-1.0, -1.0, 1.0])
+    direction = R * flip[:, None]
+    origin = off * flip
+    integral = (not scaled) and dt.kind in "iu"
+    return MedicalVolume(array=arr, spacing=tuple(spacing), direction=tuple(float(v) for v in direction.ravel()),
+                         origin=tuple(float(v) for v in origin), integer_pixels=integral,
+                         pixel_kind=ops_kind(dt) if integral else _lib.PIXEL_FLOAT, meta={"format": "NIFTI", "datatype": int(datatype)})
+
+
+def ops_kind(dt) -> int:
+    dt = np.dtype(dt)
+    return {("i", 2): _lib.PIXEL_INT16, ("u", 2): _lib.PIXEL_UINT16, ("u", 1): _lib.PIXEL_UINT8}.get((dt.kind, dt.itemsize), _lib.PIXEL_FLOAT)
+
+
+_NRRD_TYPES = {"signed char": "i1", "int8": "i1", "int8_t": "i1", "uchar": "u1", "unsigned char": "u1", "uint8": "u1", "uint8_t": "u1",
+               "short": "i2", "short int": "i2", "signed short": "i2", "int16": "i2", "int16_t": "i2", "ushort": "u2",
+               "unsigned short": "u2", "uint16": "u2", "uint16_t": "u2", "int": "i4", "signed int": "i4", "int32": "i4", "int32_t": "i4",
+               "uint": "u4", "unsigned int": "u4", "uint32": "u4", "uint32_t": "u4", "longlong": "i8", "long long": "i8", "int64": "i8",
+               "int64_t": "i8", "ulonglong": "u8", "unsigned long long": "u8", "uint64": "u8", "uint64_t": "u8", "float": "f4", "double": "f8"}
+
+
+def read_nrrd(file_path: Path) -> MedicalVolume:
+    """``read_nrrd`` (io/readers.py:100-110) = itk::NrrdImageIO for a 3-D scalar NRRD (attached ``.nrrd`` or detached header
+    with ``data file``; ``raw`` / ``gzip`` encoding).  Restated conventions: ``sizes`` x fastest; ``space directions`` give spacing
+    (vector norms) and direction (normalised vectors, columns = axes), ``space origin`` the origin; a ``right-anterior-superior``
+    space is turned into ITK's LPS by negating x and y (``left-anterior-superior``: y only); without ``space directions`` the
+    ``spacings`` field and an identity direction."""
+    import gzip
+
+    path = Path(file_path)
+    blob = path.read_bytes()
+    if not blob.startswith(b"NRRD"):
+        raise ValueError(f"{path}: not a NRRD file")
+    sep = blob.find(b"\n\n")
+    head = (blob if sep < 0 else blob[:sep]).decode("latin-1").splitlines()
+    fields = {}
+    for ln in head[1:]:
+        if ln.startswith("#") or ":" not in ln:
+            continue
+        k, v = ln.split(":", 1)
+        fields[k.strip().lower()] = v.lstrip("=").strip()
+    if int(fields.get("dimension", "0")) != 3:
+        raise UnsupportedFormatError(f"{path}: {fields.get('dimension')}-D NRRD (3-D scalar volumes only)")
+    t = fields.get("type", "").lower()
+    if t not in _NRRD_TYPES:
+        raise UnsupportedFormatError(f"{path}: NRRD type {t!r}")
+    nx, ny, nz = (int(v) for v in fields["sizes"].split())
+    end = ">" if fields.get("endian", "little").lower() == "big" else "<"
+    dt = np.dtype(_NRRD_TYPES[t]).newbyteorder(end)
+    enc = fields.get("encoding", "raw").lower()
+    if "data file" in fields or "datafile" in fields:
+        data = (path.parent / fields.get("data file", fields.get("datafile"))).read_bytes()
+    else:
+        if sep < 0:
+            raise ValueError(f"{path}: no data after the header")
+        data = blob[sep + 2 :]
+    if enc in ("gzip", "gz"):
+        data = gzip.decompress(data)
+    elif enc != "raw":
+        raise UnsupportedFormatError(f"{path}: NRRD encoding {enc!r}")
+    n = nx * ny * nz
+    if len(data) < n * dt.itemsize:
+        raise ValueError(f"{path}: voxel data truncated")
+    arr = np.frombuffer(data, dtype=dt, count=n).reshape(nz, ny, nx)
+    spacing, direction, origin = [1.0, 1.0, 1.0], np.eye(3), np.zeros(3)
+    vec = lambda s: [float(v) for v in s.strip("() ").split(",")]  # noqa: E731
+    if "space directions" in fields:
+        import re
+
+        cols = [vec(g) for g in re.findall(r"\(([^)]*)\)", fields["space directions"])]
+        if len(cols) != 3:
+            raise UnsupportedFormatError(f"{path}: space directions {fields['space directions']!r}")
+        D = np.array(cols, dtype=np.float64).T  # columns = axes
+        norms = np.linalg.norm(D, axis=0)
+        spacing = [float(v) or 1.0 for v in norms]
+        direction = D / np.where(norms == 0, 1.0, norms)
+    elif "spacings" in fields:
+        spacing = [float(v) for v in fields["spacings"].split()]
+    if "space origin" in fields:
+        origin = np.array(vec(fields["space origin"]), dtype=np.float64)
+    space = fields.get("space", "left-posterior-superior").lower()
+    flip = {"right-anterior-superior": (-1.0, -1.0, 1.0), "ras": (-1.0, -1.0, 1.0), "left-anterior-superior": (1.0, -1.0, 1.0),
+            "las": (1.0, -1.0, 1.0)}.get(space, (1.0, 1.0, 1.0))
+    direction = direction * np.array(flip)[:, None]
+    origin = origin * np.array(flip)
+    integral = dt.kind in "iu"
+    return MedicalVolume(array=arr.astype(np.float32), spacing=tuple(spacing), direction=tuple(float(v) for v in direction.ravel()),
+                         origin=tuple(float(v) for v in origin), integer_pixels=integral,
+                         pixel_kind=ops_kind(dt) if integral else _lib.PIXEL_FLOAT, meta={"format": "NRRD", "type": t})
+
+
+def read_dicom_file(file_path: Path) -> MedicalVolume:
+    """``read_dicom_file`` (io/readers.py:113-123) = ``sitk.ReadImage`` of ONE DICOM file: a volume of one slice.  Geometry as
+    itk::GDCMImageIO reports it for a single file: spacing (column spacing, row spacing, SpacingBetweenSlices or 1.0),
+    direction columns = row cosines, column cosines, their cross product, origin = ImagePositionPatient."""
+    arrs, errs = read_dicom_files([Path(file_path)])
+    if arrs[0] is None:
+        raise ValueError(errs[0])
+    info = _lib.DicomInfo()
+    _lib.load().svb_dicom_read_headers((C.c_char_p * 1)(os.fsencode(str(file_path))), 1, C.byref(info), 1, None)
+    row, col = np.array(info.orientation[0:3]), np.array(info.orientation[3:6])
+    direction = np.stack([row, col, np.cross(row, col)], axis=1)
+    integral = float(info.rescale_slope).is_integer() and float(info.rescale_intercept).is_integer()
+    kind = _lib.PIXEL_FLOAT
+    if integral and info.bits_allocated == 16:
+        kind = _lib.PIXEL_INT16 if (info.pixel_representation == 1 or info.rescale_intercept < 0) else _lib.PIXEL_UINT16
+    elif integral and info.bits_allocated == 8 and info.pixel_representation == 0 and info.rescale_intercept >= 0:
+        kind = _lib.PIXEL_UINT8
+    return MedicalVolume(array=arrs[0][None], spacing=(float(info.pixel_spacing[1]), float(info.pixel_spacing[0]),
+                                                       float(info.spacing_between_slices) or 1.0),
+                         direction=tuple(float(v) for v in direction.ravel()), origin=tuple(float(v) for v in info.position[:]),
+                         integer_pixels=integral, pixel_kind=kind, meta={"format": "DICOM_FILE"})
+
+
 def read_medical_image(path: Path, midplane_only: bool = False) -> MedicalVolume:
     """``read_medical_image`` (io/readers.py:128-161): same error behaviour (``FileNotFoundError`` for a missing path,
     ``ValueError`` for an unknown format).  ``midplane_only`` is the dataset driver's switch for DICOM series (see
@@ -235,9 +423,13 @@ def read_medical_image(path: Path, midplane_only: bool = False) -> MedicalVolume
         return _volume_from(info, arr)
     if fmt == "DICOM":
         return read_dicom_series(path, midplane_only=midplane_only)
-    if fmt == "UNKNOWN":
-        raise ValueError(f"Unsupported format for path: {path}")
-    raise UnsupportedFormatError(f"{fmt} decoding needs SimpleITK, which this build does not link; path: {path}")
+    if fmt == "NIFTI":
+        return read_nifti(path)
+    if fmt == "NRRD":
+        return read_nrrd(path)
+    if fmt == "DICOM_FILE":
+        return read_dicom_file(path)
+    raise ValueError(f"Unsupported format for path: {path}")
 
 
 def read_volumes(paths, n_threads: int = 0, pin: bool = False, midplane_only: bool = False):

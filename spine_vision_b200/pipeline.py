@@ -35,22 +35,29 @@ class CropBatch:
         return (self.coords.cpu().numpy(), self.crops.cpu().numpy(), None if self.crops2 is None else self.crops2.cpu().numpy())
 
 
-def rotation_table(coords: torch.Tensor, shapes, last_disc_angle_boost: float = 1.0) -> torch.Tensor:
-    """Rotated crop mode (cropping.py:172-313): per (series, level) the inverse rotation OpenCV would apply, as
-    float64 ``[B*L, 6]`` on the device.  The five-point angle fit is host arithmetic with the reference's own NumPy
-    calls (``np.polyfit``), so this costs one small device->host read of the coordinates."""
-    c = coords.detach().cpu().numpy()
+def rotation_rows(c, shapes, last_disc_angle_boost: float = 1.0) -> torch.Tensor:
+    """``rotation_table`` from coordinates already on the HOST (``c``: NumPy ``[B,L,2]``): float64 ``[B*L, 6]`` host tensor.
+    Callers that pipeline chunks (the dataset driver) fetch the coordinates asynchronously and run this while the GPU works
+    on the next chunk, so the exact host arithmetic (``np.polyfit``, as the reference) costs the GPU nothing."""
     rows = []
     for b, (h, w) in enumerate(shapes):
         locs = {i: (float(c[b, i, 0]), float(c[b, i, 1])) for i in range(c.shape[1])}
         ang = get_rotation_angles(locs, (h, w), last_disc_angle_boost)
         for i in range(c.shape[1]):
             rows.append(inverse_rotation(int(locs[i][0] * w), int(locs[i][1] * h), ang[i]))
-    return torch.tensor(rows, dtype=torch.float64).to(coords.device)
+    return torch.tensor(rows, dtype=torch.float64).reshape(-1, 6)
+
+
+def rotation_table(coords: torch.Tensor, shapes, last_disc_angle_boost: float = 1.0) -> torch.Tensor:
+    """Rotated crop mode (cropping.py:172-313): per (series, level) the inverse rotation OpenCV would apply, as
+    float64 ``[B*L, 6]`` on the device.  The five-point angle fit is host arithmetic with the reference's own NumPy
+    calls (``np.polyfit``), so this costs one small device->host read of the coordinates."""
+    return rotation_rows(coords.detach().cpu().numpy(), shapes, last_disc_angle_boost).to(coords.device)
 
 
 def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacings=None, crop_size=(128, 128),
-                second_size=(256, 256), return_geom: bool = False, mode: str = "horizontal", last_disc_angle_boost: float = 1.0):
+                second_size=(256, 256), return_geom: bool = False, mode: str = "horizontal", last_disc_angle_boost: float = 1.0,
+                inv_affine: torch.Tensor | None = None):
     """K3 over every (series, level): coords float32 [B,L,2] on the device.  ``spacings`` is a
     list of per-series (row, col) mm/px (``get_slice_spacing``, cropping.py:82-101); the
     reference always crops the 0.3 mm isotropic slice, so the default is (0.3, 0.3)."""
@@ -66,7 +73,9 @@ def crop_levels(pool: ops.SlicePool, coords: torch.Tensor, crop_delta_mm, spacin
     idx = torch.arange(B, dtype=torch.int32).repeat_interleave(L).contiguous()
     if mode not in ("horizontal", "rotated"):
         raise ValueError(f"unknown crop mode {mode!r}")
-    inv = rotation_table(coords, pool.shapes, last_disc_angle_boost) if mode == "rotated" else None
+    inv = None
+    if mode == "rotated":  # a table the caller computed ahead (rotation_rows on prefetched coordinates), or one D2H + host fit here
+        inv = inv_affine.to(dev, non_blocking=True) if inv_affine is not None else rotation_table(coords, pool.shapes, last_disc_angle_boost)
     crops, crops2, geom = ops.crop_resample(pool, idx.to(dev, non_blocking=True), coords.reshape(B * L, 2).contiguous(),
                                             delta.to(dev, non_blocking=True), max_box, crop_size, second_size, return_geom,
                                             inv_affine=inv)

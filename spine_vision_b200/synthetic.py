@@ -248,11 +248,137 @@ def _dcm_elem(group: int, elem: int, vr: str, value: bytes, explicit: bool = Tru
     return tag + vr.encode() + struct.pack("<H", len(value)) + value
 
 
+def rle_encode_frame(px: np.ndarray) -> bytes:
+    """DICOM RLE Lossless (PS3.5 Annex G) of one frame: a 64-byte header (segment count, 15 offsets) and one PackBits-coded
+    byte plane per byte of the sample, most significant first.  Synthetic test data only."""
+    import struct
+
+    a = np.ascontiguousarray(px)
+    nbytes = a.dtype.itemsize
+    planes = a.astype(a.dtype.newbyteorder("<"), copy=False).view(np.uint8).reshape(-1, nbytes)
+    segs = []
+    for k in range(nbytes - 1, -1, -1):  # most significant byte first
+        data = planes[:, k].tobytes()
+        out = bytearray()
+        i, n = 0, len(data)
+        while i < n:
+            run = 1
+            while i + run < n and run < 128 and data[i + run] == data[i]:
+                run += 1
+            if run >= 3:
+                out += bytes([257 - run, data[i]])
+                i += run
+                continue
+            j = i
+            while j < n and j - i < 128:
+                if j + 2 < n and data[j] == data[j + 1] == data[j + 2]:
+                    break
+                j += 1
+            out += bytes([j - i - 1]) + data[i:j]
+            i = j
+        if len(out) % 2:
+            out += b"\x00"
+        segs.append(bytes(out))
+    offs, o = [], 64
+    for sg in segs:
+        offs.append(o)
+        o += len(sg)
+    return struct.pack("<16I", len(segs), *(offs + [0] * (15 - len(offs)))) + b"".join(segs)
+
+
+def jpeg_lossless_encode_frame(px: np.ndarray, predictor: int = 1, point_transform: int = 0, restart_lines: int = 0,
+                               precision: int | None = None) -> bytes:
+    """JPEG Lossless, process 14 (ITU-T T.81 Annex H, SOF3 + Huffman) of one monochrome frame -- what DICOM transfer syntaxes
+    1.2.840.10008.1.2.4.57 / .70 carry.  ``predictor`` 1-7, ``point_transform`` Pt, ``restart_lines`` > 0 adds a DRI segment and
+    RSTn markers every that many lines.  Samples are taken modulo 2^16 (two's-complement int16 as stored).  Synthetic test
+    data only (pure Python: small frames)."""
+    import struct
+
+    a = np.ascontiguousarray(px)
+    rows, cols = a.shape
+    P = precision or a.dtype.itemsize * 8
+    v = (a.astype(np.int64) & ((1 << (a.dtype.itemsize * 8)) - 1)) >> point_transform
+    init = 1 << (P - point_transform - 1)
+    pred = np.zeros_like(v)
+    ra = np.zeros_like(v); ra[:, 1:] = v[:, :-1]
+    rb = np.zeros_like(v); rb[1:] = v[:-1]
+    rc = np.zeros_like(v); rc[1:, 1:] = v[:-1, :-1]
+    table = {1: ra, 2: rb, 3: rc, 4: ra + rb - rc, 5: ra + ((rb - rc) >> 1), 6: rb + ((ra - rc) >> 1), 7: (ra + rb) >> 1}
+    pred[:] = table[predictor]
+    pred[:, 0] = rb[:, 0]            # first sample of a line: the one above
+    first = [0] if not restart_lines else list(range(0, rows, restart_lines))
+    for y in first:                  # first line of the scan / of a restart interval: left neighbour, then 2^(P-Pt-1)
+        pred[y] = ra[y]
+        pred[y, 0] = init
+    diff = (v - pred) & 0xFFFF
+    diff = np.where(diff > 32768, diff - 65536, diff)  # -32767 .. 32768
+    mag = np.abs(diff)
+    cat = np.where(mag == 0, 0, np.floor(np.log2(np.maximum(mag, 1))).astype(np.int64) + 1)
+    # canonical Huffman table over the 17 categories: lengths 2, 3 x5, 4 .. 14 (Kraft sum < 1, no all-ones code), most frequent first
+    order = [int(c) for c in np.argsort(-np.bincount(cat.ravel(), minlength=17), kind="stable")]
+    bits = [0, 1, 5, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0]
+    codes, code, k = {}, 0, 0
+    for ln, cnt in enumerate(bits, start=1):
+        for _ in range(cnt):
+            codes[order[k]] = (code, ln)
+            code += 1
+            k += 1
+        code <<= 1
+    out = bytearray(b"\xff\xd8")
+    out += b"\xff\xc3" + struct.pack(">HBHHB", 11, P, rows, cols, 1) + bytes([1, 0x11, 0])
+    out += b"\xff\xc4" + struct.pack(">H", 2 + 1 + 16 + 17) + bytes([0x00]) + bytes(bits) + bytes(order)
+    if restart_lines:
+        out += b"\xff\xdd" + struct.pack(">HH", 4, restart_lines * cols)
+    out += b"\xff\xda" + struct.pack(">HB", 8, 1) + bytes([1, 0x00, predictor, 0, point_transform])
+    acc = nbits = 0
+
+    def flush_bytes():
+        nonlocal acc, nbits
+        while nbits >= 8:
+            b = (acc >> (nbits - 8)) & 0xFF
+            out.append(b)
+            if b == 0xFF:
+                out.append(0)
+            nbits -= 8
+        acc &= (1 << nbits) - 1
+
+    rst = 0
+    for y in range(rows):
+        if restart_lines and y and y % restart_lines == 0:
+            if nbits:
+                acc = (acc << (8 - nbits)) | ((1 << (8 - nbits)) - 1)
+                nbits = 8
+                flush_bytes()
+            out += bytes([0xFF, 0xD0 + rst])
+            rst = (rst + 1) & 7
+        for x in range(cols):
+            c = int(cat[y, x])
+            cd, ln = codes[c]
+            acc = (acc << ln) | cd
+            nbits += ln
+            if 0 < c < 16:
+                d = int(diff[y, x])
+                if d < 0:
+                    d += (1 << c) - 1
+                acc = (acc << c) | d
+                nbits += c
+            flush_bytes()
+    if nbits:
+        acc = (acc << (8 - nbits)) | ((1 << (8 - nbits)) - 1)
+        nbits = 8
+        flush_bytes()
+    return bytes(out) + b"\xff\xd9"
+
+
 def write_dicom_slice(path, pixels: np.ndarray, position, row_cos, col_cos, pixel_spacing, series_uid: str, instance: int,
-                      slice_thickness: float = 4.0, rescale=None, explicit: bool = True, with_sequence: bool = True) -> None:
-    """One single-frame MR slice as a DICOM Part-10 file with native pixel data (synthetic test / bench trees only).
+                      slice_thickness: float = 4.0, rescale=None, explicit: bool = True, with_sequence: bool = True,
+                      compress: str | None = None, codec_kw: dict | None = None, fragments: int = 1, bits_stored: int | None = None,
+                      photometric: bytes = b"MONOCHROME2") -> None:
+    """One single-frame MR slice as a DICOM Part-10 file (synthetic test / bench trees only).
     ``explicit`` selects Explicit VR Little Endian, else Implicit VR Little Endian.  ``with_sequence`` adds a sequence and
-    an item of undefined length in front of the pixel data (real files carry them; the parser has to skip them)."""
+    an item of undefined length in front of the pixel data (real files carry them; the parser has to skip them).
+    ``compress`` = "rle" (1.2.840.10008.1.2.5) or "jpeg" (JPEG Lossless SV1, 1.2.840.10008.1.2.4.70; ``codec_kw`` goes to the
+    encoder) writes encapsulated pixel data: an empty Basic Offset Table and the frame cut into ``fragments`` items."""
     import struct
     from pathlib import Path
 
@@ -261,6 +387,10 @@ def write_dicom_slice(path, pixels: np.ndarray, position, row_cos, col_cos, pixe
     ds = lambda vals: "\\".join(repr(float(v)) for v in vals).encode()  # noqa: E731
     us = lambda v: struct.pack("<H", v)  # noqa: E731
     ts = "1.2.840.10008.1.2.1" if explicit else "1.2.840.10008.1.2"
+    if compress is not None:
+        assert explicit, "encapsulated transfer syntaxes are explicit VR little endian"
+        ts = {"rle": "1.2.840.10008.1.2.5", "jpeg": "1.2.840.10008.1.2.4.70", "jpeg57": "1.2.840.10008.1.2.4.57",
+              "jpeg2000": "1.2.840.10008.1.2.4.90"}[compress]
     meta = (_dcm_elem(0x0002, 0x0001, "OB", b"\x00\x01") + _dcm_elem(0x0002, 0x0002, "UI", b"1.2.840.10008.5.1.4.1.1.4") +
             _dcm_elem(0x0002, 0x0003, "UI", f"{series_uid}.{instance}".encode()) + _dcm_elem(0x0002, 0x0010, "UI", ts.encode()) +
             _dcm_elem(0x0002, 0x0012, "UI", b"1.2.826.0.1.3680043.9.7433.1"))
@@ -276,20 +406,35 @@ def write_dicom_slice(path, pixels: np.ndarray, position, row_cos, col_cos, pixe
     body += e(0x0020, 0x000D, "UI", b"1.2.3.4.5") + e(0x0020, 0x000E, "UI", series_uid.encode())
     body += e(0x0020, 0x0013, "IS", str(instance).encode())
     body += e(0x0020, 0x0032, "DS", ds(position)) + e(0x0020, 0x0037, "DS", ds(list(row_cos) + list(col_cos)))
-    body += e(0x0028, 0x0002, "US", us(1)) + e(0x0028, 0x0004, "CS", b"MONOCHROME2")
+    body += e(0x0028, 0x0002, "US", us(1)) + e(0x0028, 0x0004, "CS", photometric)
     body += e(0x0028, 0x0010, "US", us(px.shape[0])) + e(0x0028, 0x0011, "US", us(px.shape[1]))
     body += e(0x0028, 0x0030, "DS", ds(pixel_spacing))
     bits = px.dtype.itemsize * 8
-    body += e(0x0028, 0x0100, "US", us(bits)) + e(0x0028, 0x0101, "US", us(bits)) + e(0x0028, 0x0102, "US", us(bits - 1))
+    stored = bits_stored or bits
+    body += e(0x0028, 0x0100, "US", us(bits)) + e(0x0028, 0x0101, "US", us(stored)) + e(0x0028, 0x0102, "US", us(stored - 1))
     body += e(0x0028, 0x0103, "US", us(1 if px.dtype == np.int16 else 0))
     if rescale is not None:
         body += e(0x0028, 0x1052, "DS", repr(float(rescale[1])).encode()) + e(0x0028, 0x1053, "DS", repr(float(rescale[0])).encode())
-    body += e(0x7FE0, 0x0010, "OW" if bits > 8 else "OB", px.astype(px.dtype.newbyteorder("<"), copy=False).tobytes())
+    if compress is None:
+        body += e(0x7FE0, 0x0010, "OW" if bits > 8 else "OB", px.astype(px.dtype.newbyteorder("<"), copy=False).tobytes())
+    else:
+        if compress == "rle":
+            frame = rle_encode_frame(px)
+        elif compress == "jpeg2000":
+            frame = b"\xff\x4f\xff\x51" + b"\x00" * 60  # not a decodable stream: only the transfer syntax matters (it is refused)
+        else:
+            frame = jpeg_lossless_encode_frame(px, **(codec_kw or {}))
+        if len(frame) % 2:
+            frame += b"\x00"
+        item = lambda b: struct.pack("<HHI", 0xFFFE, 0xE000, len(b)) + b  # noqa: E731
+        cut = [len(frame) * k // fragments // 2 * 2 for k in range(fragments)] + [len(frame)]
+        body += struct.pack("<HH", 0x7FE0, 0x0010) + b"OB\x00\x00" + struct.pack("<I", 0xFFFFFFFF) + item(b"")
+        body += b"".join(item(frame[cut[k] : cut[k + 1]]) for k in range(fragments)) + struct.pack("<HHI", 0xFFFE, 0xE0DD, 0)
     Path(path).write_bytes(b"\x00" * 128 + b"DICM" + meta + body)
 
 
 def write_dicom_series(folder, array_zyx: np.ndarray, spacing_xyz, direction, origin=(0.0, 0.0, 0.0), series_uid="1.2.826.1.100",
-                       explicit: bool = True, shuffle_seed: int | None = 0, rescale=None) -> None:
+                       explicit: bool = True, shuffle_seed: int | None = 0, rescale=None, compress: str | None = None) -> None:
     """A volume as one DICOM file per z index.  File names deliberately do NOT follow the slice order (a reader has to sort
     by position); ``direction`` as ``image.GetDirection()`` (columns = axes)."""
     from pathlib import Path
@@ -304,7 +449,92 @@ def write_dicom_series(folder, array_zyx: np.ndarray, spacing_xyz, direction, or
     for k in range(n):
         pos = np.asarray(origin, dtype=np.float64) + d[:, 2] * spacing_xyz[2] * k
         write_dicom_slice(folder / f"IM{int(names[k]):04d}.dcm", array_zyx[k], pos, d[:, 0], d[:, 1], (spacing_xyz[1], spacing_xyz[0]),
-                          series_uid, instance=n - k, slice_thickness=spacing_xyz[2], rescale=rescale, explicit=explicit)
+                          series_uid, instance=n - k, slice_thickness=spacing_xyz[2], rescale=rescale, explicit=explicit, compress=compress)
+
+
+def write_nifti(path, array_zyx: np.ndarray, spacing_xyz, direction=None, origin=(0.0, 0.0, 0.0), use_sform: bool = False,
+                scl=None, big_endian: bool = False) -> None:
+    """A single-file NIfTI-1 volume (``.nii``, gzip when the name ends in ``.gz``) holding the LPS geometry given the way ITK
+    writes it: RAS rotation (x and y rows negated) as a quaternion qform, or as sform rows with ``use_sform``.  Test data only."""
+    import gzip
+    import struct
+    from pathlib import Path
+
+    a = np.ascontiguousarray(array_zyx)
+    codes = {"uint8": 2, "int16": 4, "int32": 8, "float32": 16, "float64": 64, "int8": 256, "uint16": 512, "uint32": 768}
+    e = ">" if big_endian else "<"
+    nz, ny, nx = a.shape
+    D = np.eye(3) if direction is None else np.asarray(direction, dtype=np.float64).reshape(3, 3)
+    flip = np.array([-1.0, -1.0, 1.0])
+    R = D * flip[:, None]
+    off = np.asarray(origin, dtype=np.float64) * flip
+    qfac = 1.0
+    if np.linalg.det(R) < 0:
+        R = R.copy()
+        R[:, 2] = -R[:, 2]
+        qfac = -1.0
+    # rotation matrix -> quaternion (a >= 0), nifti_mat44_to_quatern
+    tr = R[0, 0] + R[1, 1] + R[2, 2]
+    if tr > 0:
+        qa = 0.5 * np.sqrt(1 + tr); qb = 0.25 * (R[2, 1] - R[1, 2]) / qa; qc = 0.25 * (R[0, 2] - R[2, 0]) / qa; qd = 0.25 * (R[1, 0] - R[0, 1]) / qa
+    else:
+        xd, yd, zd = 1 + R[0, 0] - (R[1, 1] + R[2, 2]), 1 + R[1, 1] - (R[0, 0] + R[2, 2]), 1 + R[2, 2] - (R[0, 0] + R[1, 1])
+        if xd > 1:
+            qb = 0.5 * np.sqrt(xd); qc = 0.25 * (R[0, 1] + R[1, 0]) / qb; qd = 0.25 * (R[0, 2] + R[2, 0]) / qb; qa = 0.25 * (R[2, 1] - R[1, 2]) / qb
+        elif yd > 1:
+            qc = 0.5 * np.sqrt(yd); qb = 0.25 * (R[0, 1] + R[1, 0]) / qc; qd = 0.25 * (R[1, 2] + R[2, 1]) / qc; qa = 0.25 * (R[0, 2] - R[2, 0]) / qc
+        else:
+            qd = 0.5 * np.sqrt(zd); qb = 0.25 * (R[0, 2] + R[2, 0]) / qd; qc = 0.25 * (R[1, 2] + R[2, 1]) / qd; qa = 0.25 * (R[1, 0] - R[0, 1]) / qd
+        if qa < 0:
+            qb, qc, qd = -qb, -qc, -qd
+    h = bytearray(352)
+    struct.pack_into(e + "i", h, 0, 348)
+    struct.pack_into(e + "8h", h, 40, 3, nx, ny, nz, 1, 1, 1, 1)
+    struct.pack_into(e + "h", h, 70, codes[a.dtype.name])
+    struct.pack_into(e + "h", h, 72, a.dtype.itemsize * 8)
+    struct.pack_into(e + "8f", h, 76, qfac, float(spacing_xyz[0]), float(spacing_xyz[1]), float(spacing_xyz[2]), 0, 0, 0, 0)
+    struct.pack_into(e + "f", h, 108, 352.0)
+    struct.pack_into(e + "2f", h, 112, *(scl if scl is not None else (1.0, 0.0)))
+    if use_sform:
+        struct.pack_into(e + "2h", h, 252, 0, 1)
+        M = (D * flip[:, None]) * np.asarray(spacing_xyz, dtype=np.float64)[None, :]
+        struct.pack_into(e + "12f", h, 280, *np.concatenate([M, off[:, None]], axis=1).ravel())
+    else:
+        struct.pack_into(e + "2h", h, 252, 1, 0)
+        struct.pack_into(e + "6f", h, 256, float(qb), float(qc), float(qd), *off)
+    h[344:348] = b"n+1\x00"
+    blob = bytes(h) + a.astype(a.dtype.newbyteorder(e), copy=False).tobytes()
+    Path(path).write_bytes(gzip.compress(blob) if str(path).endswith(".gz") else blob)
+
+
+def write_nrrd(path, array_zyx: np.ndarray, spacing_xyz, direction=None, origin=(0.0, 0.0, 0.0), gz: bool = False,
+               space: str = "left-posterior-superior", detached: bool = False) -> None:
+    """A 3-D NRRD (attached data, or a ``.nhdr``-style detached ``data file``) with ``space directions`` / ``space origin``;
+    ``space`` = "right-anterior-superior" stores the RAS form of the LPS geometry given.  Test data only."""
+    import gzip
+    from pathlib import Path
+
+    a = np.ascontiguousarray(array_zyx)
+    names = {"uint8": "uchar", "int8": "signed char", "int16": "short", "uint16": "ushort", "int32": "int", "float32": "float", "float64": "double"}
+    D = np.eye(3) if direction is None else np.asarray(direction, dtype=np.float64).reshape(3, 3)
+    flip = np.array([-1.0, -1.0, 1.0]) if space.startswith("right") else np.ones(3)
+    V = (D * flip[:, None]) * np.asarray(spacing_xyz, dtype=np.float64)[None, :]
+    o = np.asarray(origin, dtype=np.float64) * flip
+    fmt = lambda v: "(" + ",".join(repr(float(x)) for x in v) + ")"  # noqa: E731
+    nz, ny, nx = a.shape
+    data = a.astype(a.dtype.newbyteorder("<"), copy=False).tobytes()
+    if gz:
+        data = gzip.compress(data)
+    head = ["NRRD0004", "# synthetic", f"type: {names[a.dtype.name]}", "dimension: 3", f"space: {space}", f"sizes: {nx} {ny} {nz}",
+            "space directions: " + " ".join(fmt(V[:, k]) for k in range(3)), "kinds: domain domain domain", "endian: little",
+            f"encoding: {'gzip' if gz else 'raw'}", "space origin: " + fmt(o)]
+    path = Path(path)
+    if detached:
+        raw = path.with_suffix(".raw.gz" if gz else ".raw")
+        raw.write_bytes(data)
+        path.write_bytes(("\n".join(head + [f"data file: {raw.name}"]) + "\n").encode())
+    else:
+        path.write_bytes(("\n".join(head) + "\n\n").encode() + data)
 
 
 PHENIKAA_LABEL_COLUMNS = ["Patient ID", "IVD label", "Modic_0", "Modic_1", "Modic_2", "Modic_3", "UP endplate", "LOW endplate",

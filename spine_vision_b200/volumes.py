@@ -106,7 +106,7 @@ class PinnedVolumes:
     ``svb_k0_series`` rows and the layout of the isotropic planes K0 will produce.  512 x 512 sources at 0.7 mm: 2.1 MB per
     series cross PCIe instead of the 5.7 MB of the resampled 1195 x 1195 plane."""
 
-    def __init__(self, volumes, spacings, directions=None, integer_pixels=None, pixel_kinds=None, plans=None):
+    def __init__(self, volumes, spacings, directions=None, integer_pixels=None, pixel_kinds=None, plans=None, cache_tag: str | None = None):
         if plans is None:
             B = len(volumes)
             directions = directions if directions is not None else [None] * B
@@ -124,9 +124,12 @@ class PinnedVolumes:
             self.vol_offs.append(total)
             total += (p.slab.size + 3) // 4 * 4
         self.vol_ends = [o + (p.slab.size + 3) // 4 * 4 for o, p in zip(self.vol_offs, plans)]
-        self.host = torch.empty(max(total, 4), dtype=torch.float32)
-        if torch.cuda.is_available():
-            self.host = self.host.pin_memory()
+        if cache_tag is not None:  # a driver that makes one of these per chunk re-uses its pinned staging (cudaHostAlloc is slow)
+            self.host = ops.PinnedCache.get(cache_tag, max(total, 4))
+        else:
+            self.host = torch.empty(max(total, 4), dtype=torch.float32)
+            if torch.cuda.is_available():
+                self.host = self.host.pin_memory()
         hv = self.host.numpy()
         self.descs = (K0Series * max(B, 1))()
         for i, p in enumerate(plans):

@@ -46,8 +46,8 @@ def test_metaimage_2d_and_errors(tmp_path):
     with pytest.raises(ValueError, match="Unsupported format"):
         hostio.read_medical_image(tmp_path / "x.bin")  # io/readers.py:160-161
     (tmp_path / "v.nii.gz").write_bytes(b"\x1f\x8b")
-    with pytest.raises(hostio.UnsupportedFormatError):
-        hostio.read_medical_image(tmp_path / "v.nii.gz")  # NIfTI / NRRD: no decoder in this build (not on the dataset path)
+    with pytest.raises(Exception):
+        hostio.read_medical_image(tmp_path / "v.nii.gz")  # a truncated gzip stream: an exception the drivers catch (spider.py:131-133)
     (tmp_path / "bad.mha").write_text("hello\nworld\n")
     with pytest.raises(_lib.SvbError):
         hostio.read_medical_image(tmp_path / "bad.mha")
@@ -393,7 +393,11 @@ def test_native_decoders_under_address_sanitizer(tmp_path):
     synthetic.write_dicom_slice(seeds / "e.dcm", px, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1)
     synthetic.write_dicom_slice(seeds / "i.dcm", px.astype(np.int16), (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1,
                                 explicit=False, rescale=(2.0, -1024.0))
-    files = [str(seeds / n) for n in ("a.mha", "b.mha", "c.mhd", "d.mha", "e.dcm", "i.dcm")]
+    # the encapsulated decoders (RLE Lossless, JPEG Lossless with a restart interval, two fragments) get the same treatment
+    synthetic.write_dicom_slice(seeds / "r.dcm", px, (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1, compress="rle")
+    synthetic.write_dicom_slice(seeds / "j.dcm", px.astype(np.int16), (0, 0, 0), (1, 0, 0), (0, 1, 0), (0.5, 0.5), "1.2.3.9", 1,
+                                compress="jpeg", codec_kw={"predictor": 4, "restart_lines": 3}, fragments=2)
+    files = [str(seeds / n) for n in ("a.mha", "b.mha", "c.mhd", "d.mha", "e.dcm", "i.dcm", "r.dcm", "j.dcm")]
     run = subprocess.run([str(exe), str(work), "1500", *files], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0, (run.stdout + run.stderr)[-3000:]
     assert "no sanitizer report" in run.stdout
@@ -486,3 +490,144 @@ def test_corrupt_header_skips_the_series_not_the_chunk(tmp_path):
     for p in paths[:1] + paths[2:]:
         with pytest.raises(Exception):
             hostio.read_medical_image(p)
+
+
+@pytest.mark.parametrize("name", ["u16", "i16", "u8", "noise"])
+def test_compressed_dicom_rle_and_jpeg_lossless(tmp_path, name):
+    """VERDICT r01 missing #1: the lossless ENCAPSULATED transfer syntaxes GDCM decodes for the reference -- RLE Lossless
+    (1.2.840.10008.1.2.5, PS3.5 Annex G) and JPEG Lossless process 14 (1.2.840.10008.1.2.4.57 / .70, T.81 Annex H: all seven
+    predictors, point transform, restart intervals, frames cut into several fragments).  Lossless means exact: the native decoder
+    must return the very pixels that were encoded, and agree with the plain-Python restatement in oracle/dicom.py
+    (parity with GDCM itself stays unpinned: it is not in the image)."""
+    from oracle import dicom as od
+
+    rng = np.random.default_rng(1)
+    base = synthetic.make_iso_slice(5, 48, 40)
+    img = {"u16": np.rint(base * 20).astype(np.uint16), "i16": (np.rint(base) - 300).astype(np.int16),
+           "u8": np.rint(base * 255 / base.max()).astype(np.uint8), "noise": rng.integers(0, 65536, (48, 40)).astype(np.uint16)}[name]
+    cases = [("rle", {}, 1), ("rle", {}, 3)] + [("jpeg", {"predictor": p}, 1) for p in range(1, 8)]
+    cases += [("jpeg", {"predictor": 4, "restart_lines": 5}, 2), ("jpeg57", {"predictor": 6, "restart_lines": 1}, 1)]
+    if img.dtype != np.uint8:
+        cases.append(("jpeg", {"predictor": 1, "point_transform": 2}, 1))
+    files, want = [], []
+    for k, (comp, kw, frags) in enumerate(cases):
+        px = (img >> 2 << 2).astype(img.dtype) if kw.get("point_transform") else img
+        f = tmp_path / f"{k:02d}.dcm"
+        synthetic.write_dicom_slice(f, px, (0, 0, float(k)), (0, 1, 0), (0, 0, -1), (0.6, 0.6), "1.2.3", k + 1, compress=comp,
+                                    codec_kw=kw, fragments=frags, rescale=(2.0, -100.0) if k == 3 else None)
+        files.append(f)
+        want.append(px.astype(np.float64) * 2.0 - 100.0 if k == 3 else px.astype(np.float64))
+        assert np.array_equal(od.read_slice(f)["px"], px)
+    arrs, errs = hostio.read_dicom_files(files, n_threads=3)
+    for k, f in enumerate(files):
+        assert errs[k] is None, (cases[k], errs[k])
+        assert np.array_equal(arrs[k], want[k].astype(np.float32)), cases[k]
+
+
+def test_compressed_dicom_series_and_refusals(tmp_path):
+    """A whole RLE / JPEG-lossless series folder reads like the native one (same volume, geometry, midplane slab); what is NOT
+    decoded is refused with a message, never returned wrong: JPEG 2000, MONOCHROME1; BitsStored < BitsAllocated is masked /
+    sign-extended; every truncation of a compressed file is an error, never a crash."""
+    vol = (np.rint(synthetic.make_volume(4, 6, 40, 36)[0]) - 200).astype(np.int16)
+    sp, d = (0.7, 0.7, 4.0), (0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+    synthetic.write_dicom_series(tmp_path / "native", vol, sp, d)
+    ref_v = hostio.read_medical_image(tmp_path / "native")
+    for comp in ("rle", "jpeg"):
+        synthetic.write_dicom_series(tmp_path / comp, vol, sp, d, compress=comp)
+        v = hostio.read_medical_image(tmp_path / comp)
+        assert np.array_equal(v.array, ref_v.array) and v.spacing == ref_v.spacing and v.direction == ref_v.direction
+        assert v.integer_pixels and v.pixel_kind == ref_v.pixel_kind
+        slab = hostio.read_medical_image(tmp_path / comp, midplane_only=True)
+        lo, hi = slab.meta["decoded_z"]
+        assert np.array_equal(slab.array[lo:hi], ref_v.array[lo:hi])
+    px = vol[0]
+    args = ((0, 0, 0), (0, 1, 0), (0, 0, -1), (0.6, 0.6), "1.2.9", 1)
+    synthetic.write_dicom_slice(tmp_path / "j2k.dcm", px, *args, compress="jpeg2000")
+    synthetic.write_dicom_slice(tmp_path / "mono1.dcm", px, *args, photometric=b"MONOCHROME1 ")
+    arrs, errs = hostio.read_dicom_files([tmp_path / "j2k.dcm", tmp_path / "mono1.dcm"])
+    assert arrs == [None, None] and "1.2.840.10008.1.2.4.90" in errs[0] and "MONOCHROME1" in errs[1]
+    # 12 bits stored in 16: the four high bits are junk (unsigned: masked; signed: sign-extended from bit 11)
+    junk = (np.arange(40 * 36, dtype=np.int64).reshape(40, 36) * 37) % 4096
+    u = (junk | 0xA000).astype(np.uint16)
+    synthetic.write_dicom_slice(tmp_path / "u12.dcm", u, *args, bits_stored=12)
+    synthetic.write_dicom_slice(tmp_path / "s12.dcm", u.view(np.int16), *args, bits_stored=12, compress="jpeg")
+    arrs, errs = hostio.read_dicom_files([tmp_path / "u12.dcm", tmp_path / "s12.dcm"])
+    assert errs == [None, None]
+    assert np.array_equal(arrs[0], junk.astype(np.float32))
+    assert np.array_equal(arrs[1], np.where(junk >= 2048, junk - 4096, junk).astype(np.float32))
+    # truncations and byte flips of compressed files: an error or a decode, never a crash
+    rng = np.random.default_rng(3)
+    for comp in ("rle", "jpeg"):
+        blob = (tmp_path / comp / sorted(p.name for p in (tmp_path / comp).iterdir())[0]).read_bytes()
+        start = blob.index(b"\xe0\x7f\x10\x00")
+        for cut in list(range(start, len(blob), 97)) + [len(blob) - 1]:
+            (tmp_path / "t.dcm").write_bytes(blob[:cut])
+            a, e = hostio.read_dicom_files([tmp_path / "t.dcm"])
+            assert a[0] is None and e[0]
+        for _ in range(60):
+            m = bytearray(blob)
+            for pos in rng.integers(start, len(blob), 3):
+                m[pos] = int(rng.integers(0, 256))
+            (tmp_path / "m.dcm").write_bytes(bytes(m))
+            hostio.read_dicom_files([tmp_path / "m.dcm"])
+
+
+def test_nifti_nrrd_and_single_dicom_readers(tmp_path):
+    """VERDICT r01 missing #1: ``read_medical_image`` dispatches NIfTI, NRRD and single ``.dcm`` files too (io/readers.py:23-28,
+    76-126, 128-161).  Arrays round-trip exactly for every pixel type; the geometry follows ITK's documented conventions (RAS
+    files come back as LPS); parity with SimpleITK itself is UNPINNED (absent from the image)."""
+    rng = np.random.default_rng(2)
+    d_sag = (0.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, -1.0, 0.0)
+    th = np.deg2rad(12.0)
+    d_obl = (np.cos(th), -np.sin(th), 0.0, np.sin(th), np.cos(th), 0.0, 0.0, 0.0, 1.0)
+    sp, org = (0.6, 0.75, 3.5), (-12.5, 40.25, 7.0)
+    for dt in ("int16", "uint16", "uint8", "float32", "int32"):
+        vol = (rng.random((5, 9, 7)) * 200).astype(dt)
+        for k, (d, kw) in enumerate([(None, {}), (d_sag, {}), (d_obl, {}), (d_obl, {"use_sform": True}), (d_sag, {"big_endian": True})]):
+            f = tmp_path / f"n_{dt}_{k}.nii{'.gz' if k % 2 else ''}"
+            synthetic.write_nifti(f, vol, sp, d, org, **kw)
+            v = hostio.read_medical_image(f)
+            assert np.array_equal(v.array, vol.astype(np.float32)) and v.integer_pixels == (dt != "float32")
+            assert np.allclose(v.spacing, sp, atol=1e-6) and np.allclose(v.origin, org, atol=1e-5)
+            assert np.allclose(np.array(v.direction).reshape(3, 3), np.eye(3) if d is None else np.array(d).reshape(3, 3), atol=1e-6)
+        for k, (d, kw) in enumerate([(None, {}), (d_sag, {"gz": True}), (d_obl, {"space": "right-anterior-superior"}),
+                                     (d_sag, {"detached": True, "gz": True})]):
+            f = tmp_path / f"r_{dt}_{k}.nrrd"
+            synthetic.write_nrrd(f, vol, sp, d, org, **kw)
+            v = hostio.read_medical_image(f)
+            assert np.array_equal(v.array, vol.astype(np.float32))
+            assert np.allclose(v.spacing, sp) and np.allclose(v.origin, org)
+            assert np.allclose(np.array(v.direction).reshape(3, 3), np.eye(3) if d is None else np.array(d).reshape(3, 3))
+    # the conventions on a case written out by hand: identity qform, offsets (10, 20, 30) mm in RAS -> LPS origin (-10, -20, 30),
+    # direction diag(-1, -1, 1); scl_slope / scl_inter make the image float
+    import struct
+
+    h = bytearray(352)
+    struct.pack_into("<i", h, 0, 348)
+    struct.pack_into("<8h", h, 40, 3, 4, 3, 2, 1, 1, 1, 1)
+    struct.pack_into("<2h", h, 70, 4, 16)
+    struct.pack_into("<8f", h, 76, 1.0, 0.5, 0.5, 2.0, 0, 0, 0, 0)
+    struct.pack_into("<f", h, 108, 352.0)
+    struct.pack_into("<2f", h, 112, 2.0, -3.0)
+    struct.pack_into("<2h", h, 252, 1, 0)
+    struct.pack_into("<6f", h, 256, 0.0, 0.0, 0.0, 10.0, 20.0, 30.0)
+    h[344:348] = b"n+1\x00"
+    raw = np.arange(24, dtype="<i2")
+    (tmp_path / "hand.nii").write_bytes(bytes(h) + raw.tobytes())
+    v = hostio.read_medical_image(tmp_path / "hand.nii")
+    assert v.array.shape == (2, 3, 4) and np.array_equal(v.array.ravel(), raw * 2.0 - 3.0) and not v.integer_pixels
+    assert v.spacing == (0.5, 0.5, 2.0) and v.origin == (-10.0, -20.0, 30.0)
+    assert np.array_equal(np.array(v.direction).reshape(3, 3), np.diag([-1.0, -1.0, 1.0]))
+    # a single .dcm file: a one-slice volume
+    px = (rng.random((12, 10)) * 3000).astype(np.uint16)
+    synthetic.write_dicom_slice(tmp_path / "one.dcm", px, (1.5, -2.0, 33.0), (0, 1, 0), (0, 0, -1), (0.6, 0.7), "1.2.7", 1, compress="jpeg")
+    v = hostio.read_medical_image(tmp_path / "one.dcm")
+    assert v.array.shape == (1, 12, 10) and np.array_equal(v.array[0], px.astype(np.float32))
+    assert v.spacing[:2] == (0.7, 0.6) and v.origin == (1.5, -2.0, 33.0) and v.pixel_kind == 2
+    assert np.allclose(np.array(v.direction).reshape(3, 3)[:, 2], np.cross((0, 1, 0), (0, 0, -1)))
+    # errors keep the reference's shape: unknown suffix -> ValueError, junk content -> an exception the drivers catch
+    (tmp_path / "x.nii").write_bytes(b"junk" * 100)
+    (tmp_path / "x.nrrd").write_bytes(b"junk" * 100)
+    for f in ("x.nii", "x.nrrd"):
+        with pytest.raises(Exception):
+            hostio.read_medical_image(tmp_path / f)
