@@ -1156,9 +1156,18 @@ __global__ void k0_table_kernel(const svb_k0_series* __restrict__ desc, int max_
     taps[((size_t)blockIdx.z * 2 + which) * (size_t)max(max_h, max_w) + i] = t;
 }
 
-// grid (ceil(max_w / 32), ceil(max_h / K0_ROWS), B), block (32, 8): a thread owns one output column of a K0_ROWS-row band
-// (column tap loaded once, rows strided by 8) -- no index division per pixel, coalesced stores along the row.
-constexpr int K0_ROWS = 32;
+// grid (ceil(max_w / 32), ceil(max_h / K0_ROWS), B), block (32, 8): a warp owns 32 output columns of a band of K0_BAND
+// consecutive output rows (a thread: one column of it) -- no index division per pixel, coalesced stores along the row.
+//
+// The nested lerp runs over the IMAGE axes in the order x, y, z (ITK's LinearInterpolateImageFunction).  For the orientation
+// every sagittal acquisition has (SPIDER .mha, Phenikaa DICOM series, BASELINE config 1: image x = columns, y = rows, z = the
+// fixed Left-Right axis) the x-lerp of a (plane, source row, output column) is shared by every output row that reads that
+// source row -- 0.3 mm output rows over 0.7 mm source rows: each x-lerp is needed by 2.3 output rows twice over.  A thread
+// walking DOWN its column keeps the x-lerps of its last two source rows in registers and only computes the rows that are new:
+// 3.9 instead of 7 double lerps and 1.7 instead of 8 loads + float->double conversions per pixel, the SAME operations in the
+// SAME order for every output pixel (bit-identical to the generic path, which serves every other orientation).
+constexpr int K0_BAND = 8;              // consecutive output rows per thread
+constexpr int K0_ROWS = 8 * K0_BAND;    // output rows per CTA (8 warps)
 __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restrict__ vol, const svb_k0_series* __restrict__ desc,
                                                           int max_h, int max_w, const K0Tap* __restrict__ taps,
                                                           float* __restrict__ out, uint32_t* __restrict__ keys) {
@@ -1173,36 +1182,67 @@ __global__ void __launch_bounds__(256) k0_midplane_kernel(const float* __restric
     const long long s_col = d.ax_col == 0 ? sx : (d.ax_col == 1 ? sy : sz);
     const long long s_fix = d.ax_fix == 0 ? sx : (d.ax_fix == 1 ? sy : sz);
     const int c = blockIdx.x * 32 + threadIdx.x;
-    const int r0 = blockIdx.y * K0_ROWS;
+    const int r0 = blockIdx.y * K0_ROWS + threadIdx.y * K0_BAND;
+    const int r1 = min(r0 + K0_BAND, d.out_h);
+    auto lerp = [](double a, double b, double f) -> double { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), f)); };
     float mn = INFINITY, mx = -INFINITY;
     if (c < d.out_w && r0 < d.out_h) {
         const K0Tap tc = ct[c];
-        for (int r = r0 + threadIdx.y; r < min(r0 + K0_ROWS, d.out_h); r += 8) {
-            const K0Tap tr = rt[r];
-            float res = 0.0f;
-            if (tr.inside && tc.inside && d.fix_inside) {
-                // per image axis a: (lo, hi, frac); the nested lerp always runs x, then y, then z
-                long long lo[3], hi[3];
-                double fr[3];
-                lo[d.ax_row] = tr.lo * s_row; hi[d.ax_row] = tr.hi * s_row; fr[d.ax_row] = tr.frac;
-                lo[d.ax_col] = tc.lo * s_col; hi[d.ax_col] = tc.hi * s_col; fr[d.ax_col] = tc.frac;
-                lo[d.ax_fix] = d.fix_lo * s_fix; hi[d.ax_fix] = d.fix_hi * s_fix; fr[d.ax_fix] = d.fix_frac;
-                auto g = [&](long long z, long long y, long long x) -> double { return (double)__ldg(v + z + y + x); };
-                auto lerp = [](double a, double b, double f) -> double { return __dadd_rn(a, __dmul_rn(__dsub_rn(b, a), f)); };
-                double pl[2];
-#pragma unroll
-                for (int k = 0; k < 2; ++k) {
-                    const long long z = k == 0 ? lo[2] : hi[2];
-                    const double a = lerp(g(z, lo[1], lo[0]), g(z, lo[1], hi[0]), fr[0]);
-                    const double b = lerp(g(z, hi[1], lo[0]), g(z, hi[1], hi[0]), fr[0]);
-                    pl[k] = lerp(a, b, fr[1]);
+        if (d.ax_col == 0 && d.ax_row == 1) {
+            // ---- x = columns, y = rows, z = fixed
+            const float* p0 = v + (long long)d.fix_lo * sz;
+            const float* p1 = v + (long long)d.fix_hi * sz;
+            int ya = -1, yb = -1;            // source rows whose x-lerps are held
+            double a0 = 0, a1 = 0, b0 = 0, b1 = 0;  // x-lerp at (plane 0 / 1, source row ya / yb)
+            auto xrow = [&](int y, double& q0, double& q1) {
+                const long long ro = (long long)y * sy;
+                q0 = lerp((double)__ldg(p0 + ro + tc.lo), (double)__ldg(p0 + ro + tc.hi), tc.frac);
+                q1 = lerp((double)__ldg(p1 + ro + tc.lo), (double)__ldg(p1 + ro + tc.hi), tc.frac);
+            };
+            for (int r = r0; r < r1; ++r) {
+                const K0Tap tr = rt[r];
+                float res = 0.0f;
+                if (tr.inside && tc.inside && d.fix_inside) {
+                    if (tr.lo != ya) {
+                        if (tr.lo == yb) { ya = yb; a0 = b0; a1 = b1; }
+                        else { ya = tr.lo; xrow(ya, a0, a1); }
+                    }
+                    if (tr.hi != yb) {
+                        if (tr.hi == ya) { yb = ya; b0 = a0; b1 = a1; }
+                        else { yb = tr.hi; xrow(yb, b0, b1); }
+                    }
+                    const double rd = lerp(lerp(a0, b0, tr.frac), lerp(a1, b1, tr.frac), d.fix_frac);
+                    res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
                 }
-                const double rd = lerp(pl[0], pl[1], fr[2]);
-                res = (float)(d.integer_pixels ? trunc(rd) : rd);  // integer pixel types: ITK's static_cast<PixelType>
+                o[(long long)r * d.out_w + c] = res;
+                mn = fminf(mn, res);
+                mx = fmaxf(mx, res);
             }
-            o[(long long)r * d.out_w + c] = res;
-            mn = fminf(mn, res);
-            mx = fmaxf(mx, res);
+        } else {
+            // ---- any other orientation: (lo, hi, frac) per IMAGE axis, selected without indexed local arrays
+            const int ar = d.ax_row, ac = d.ax_col;
+            for (int r = r0; r < r1; ++r) {
+                const K0Tap tr = rt[r];
+                float res = 0.0f;
+                if (tr.inside && tc.inside && d.fix_inside) {
+                    const long long rl = tr.lo * s_row, rh = tr.hi * s_row, cl = tc.lo * s_col, ch = tc.hi * s_col;
+                    const long long fl = d.fix_lo * s_fix, fh = d.fix_hi * s_fix;
+                    auto pick = [&](int axis, long long vr, long long vc, long long vf) { return ar == axis ? vr : (ac == axis ? vc : vf); };
+                    auto pickf = [&](int axis) { return ar == axis ? tr.frac : (ac == axis ? tc.frac : d.fix_frac); };
+                    const long long xl = pick(0, rl, cl, fl), xh = pick(0, rh, ch, fh);
+                    const long long yl = pick(1, rl, cl, fl), yh = pick(1, rh, ch, fh);
+                    const long long zl = pick(2, rl, cl, fl), zh = pick(2, rh, ch, fh);
+                    const double fx = pickf(0), fy = pickf(1), fz = pickf(2);
+                    auto g = [&](long long z, long long y, long long x) -> double { return (double)__ldg(v + z + y + x); };
+                    const double qa = lerp(lerp(g(zl, yl, xl), g(zl, yl, xh), fx), lerp(g(zl, yh, xl), g(zl, yh, xh), fx), fy);
+                    const double qb = lerp(lerp(g(zh, yl, xl), g(zh, yl, xh), fx), lerp(g(zh, yh, xl), g(zh, yh, xh), fx), fy);
+                    const double rd = lerp(qa, qb, fz);
+                    res = (float)(d.integer_pixels ? trunc(rd) : rd);
+                }
+                o[(long long)r * d.out_w + c] = res;
+                mn = fminf(mn, res);
+                mx = fmaxf(mx, res);
+            }
         }
     }
     if (keys != nullptr) {
