@@ -260,6 +260,14 @@ int svb_stem_ln(const uint8_t* d_in, const float* d_wf, const float* d_bf, const
                 void* d_out, int B, int H, int W, int C0, int dtype, void* stream);
 int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* d_bias, const float* d_lnw,
                   const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream);
+/* Depthwise 7x7 + bias with the block's LayerNorm FOLDED INTO fc1 (the default forward): d_out = the raw convolution, 16-bit
+ * [B,H,W,C] (fc1's A operand); d_rowstat = float32 [B*H*W, 2] = (rstd, -mean * rstd) of each token's C rounded values.  fc1 is
+ * then svb_gemm(mode 3): GELU(rstd_m * (A @ (W1 diag(g))^T)[m,n] + (-mean_m rstd_m) * s_n + t_n), with d_w = r16(W1 * g),
+ * d_gamma = s_n = sum_k r16(W1 g)[n,k], d_bias = t_n = W1 @ ln_bias + b1, d_resid = d_rowstat.
+ * (timm ConvNeXt block: conv_dw -> norm -> mlp.fc1 -> act; generic.py:389-391 over backbone.py:165-172.) */
+int svb_dwconv_raw(const void* d_x, const float* d_taps, const float* d_bias, void* d_out, float* d_rowstat, int B, int H, int W,
+                   int C, int dtype, void* stream);
+
 /* Same operator on the tensor cores (shifted-view diagonal tcgen05 MMAs); taps16 = the taps as 16-bit
  * [49][C] of `dtype`.  Supported for C = 256 / 512 while the halo tile fits in shared memory, else SVB_ERR_UNSUPPORTED_MODEL. */
 int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,

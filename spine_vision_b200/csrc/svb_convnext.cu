@@ -26,6 +26,7 @@ static const double IMAGENET_STD[3] = {0.229, 0.224, 0.225};   // cropping.py:24
 struct BlockParams {
     float *wdw, *bdw, *lnw, *lnb, *b1, *b2, *gamma;
     float *grn_w = nullptr, *grn_b = nullptr;  // ConvNeXt-V2: GlobalResponseNorm weight / bias [4C]; gamma is all ones then
+    float* s1 = nullptr;  // LayerNorm folded into fc1 (svb_model::ln_fold): s_n = sum_k r16(W1[n,k] g_k); b1 then holds t_n
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
     void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
     CUtensorMap wdw_map, wdw16_map, w1_map, w2_map;
@@ -40,6 +41,7 @@ struct ActPlan {  // tensor maps that depend on the workspace pointer and the mi
     const void* ws = nullptr;
     int nb = 0, H = 0, W = 0;
     CUtensorMap x_map[4];   // 4-D NHWC halo maps per stage
+    CUtensorMap xr_map[4];  // the same for dwconv_raw_kernel (16-pixel-wide tiles: box {64, 22, 14, 1})
     CUtensorMap xtc_map[4]; // 4-D NHWC maps of the tensor-core depthwise kernel: box {64, W+6, rows, 1}, 128B swizzle
     int tc_rows[4] = {0, 0, 0, 0};  // rows per box; 0 = the stage runs the CUDA-core kernel
     CUtensorMap a_map[4];   // [M, C]   fc1 A operand
@@ -58,6 +60,7 @@ struct svb_model {
     int hid = 0, nout = 0;
     int device = 0;
     bool v2 = false;  // ConvNeXt-V2: GRN in every block's MLP, no layer scale
+    bool ln_fold = true;  // the block LayerNorm is folded into fc1 (dwconv_raw_kernel + GEMM_LNGELU); SVB_LN_FOLD=0 at creation: separate LN
     // two micro-batches in flight (svb_model_forward): odd micro-batches run on this stream with the second half of the
     // workspace, so that the ramp-up and tail of one chain's persistent kernels are back-filled by the other chain's CTAs
     cudaStream_t aux_stream = nullptr;
@@ -187,6 +190,12 @@ static bool gemm_half_env() {
     return e && e[0] == '1';
 }
 static int gemm_bn_for(int N, bool half) { return half ? 128 : gemm_bn(N); }
+// SVB_LN_FOLD=0 (read when a model is created): keep the round-1 block -- dwconv_ln_kernel writes the NORMALISED fc1 operand,
+// fc1 is a plain bias + GELU GEMM.  Default: folded (see dwconv_raw_kernel).
+static bool ln_fold_env() {
+    const char* e = getenv("SVB_LN_FOLD");
+    return !(e && e[0] == '0');
+}
 // SVB_CARVEOUT=1: ask for the maximum shared-memory carve-out on the persistent kernels.  Two kernels whose preferred L1 /
 // shared split differs cannot be resident on one SM at the same time (the split is an SM-wide setting), so a half-SM GEMM
 // CTA and a depthwise CTA only ever share an SM when both ask for the same split.
@@ -317,6 +326,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
     }
     SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
     m->v2 = hwts.get("backbone.stages.0.blocks.0.mlp.grn.weight") != nullptr;  // timm convnextv2_*: GRN instead of layer scale
+    m->ln_fold = ln_fold_env();
     SVB_REQUIRE(m->dims[0] == 96 || m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL,
                 "stem width %d unsupported", m->dims[0]);
     NEED(head_w1, "head.2.weight");
@@ -403,7 +413,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             PUT_F32(bp.bdw, bn + "conv_dw.bias", C);
             PUT_F32(bp.lnw, bn + "norm.weight", C);
             PUT_F32(bp.lnb, bn + "norm.bias", C);
-            PUT_F32(bp.b1, bn + "mlp.fc1.bias", 4 * C);
+            if (!m->ln_fold) PUT_F32(bp.b1, bn + "mlp.fc1.bias", 4 * C);
             PUT_F32(bp.b2, bn + "mlp.fc2.bias", C);
             if (m->v2) {
                 std::vector<float> ones((size_t)C, 1.0f);
@@ -418,7 +428,47 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             SVB_REQUIRE(numel(w1) == (int64_t)4 * C * C && numel(w2) == (int64_t)4 * C * C, SVB_ERR_UNSUPPORTED_MODEL,
                         "mlp weights must be [4C,C] and [C,4C]");
             tmp16.resize((size_t)4 * C * C);
-            convert16(w1->data, tmp16.data(), tmp16.size(), dtype);
+            if (m->ln_fold) {
+                // fc1(LN(y)) = rstd * (W1 diag(g)) y - rstd mu * s + t:  W1g = r16(W1 * g) is the GEMM operand, s_n = sum_k W1g[n,k]
+                // (of the ROUNDED values: what the tensor cores multiply), t_n = sum_k W1[n,k] lnb_k + b1_n (double -> float)
+                NEED(lnw_w, bn + "norm.weight");
+                NEED(lnb_w, bn + "norm.bias");
+                NEED(b1_w, bn + "mlp.fc1.bias");
+                SVB_REQUIRE(numel(b1_w) == (int64_t)4 * C, SVB_ERR_UNSUPPORTED_MODEL, "fc1 bias size");
+                std::vector<float> wg((size_t)4 * C * C), sn((size_t)4 * C), tn((size_t)4 * C);
+                const size_t rows = (size_t)4 * C;
+                auto fold_rows = [&](size_t lo, size_t hi) {
+                    for (size_t n = lo; n < hi; ++n) {
+                        const float* wr = w1->data + n * C;
+                        float* gr = wg.data() + n * C;
+                        double t = b1_w->data[n];
+                        for (int k = 0; k < C; ++k) { gr[k] = wr[k] * lnw_w->data[k]; t += (double)wr[k] * (double)lnb_w->data[k]; }
+                        tn[n] = (float)t;
+                    }
+                };
+                {
+                    std::vector<std::thread> th;
+                    const size_t nt = 8, per = (rows + nt - 1) / nt;
+                    for (size_t q = 0; q < nt; ++q) { const size_t lo = q * per, hi = std::min(rows, lo + per); if (lo < hi) th.emplace_back(fold_rows, lo, hi); }
+                    for (auto& x : th) x.join();
+                }
+                convert16(wg.data(), tmp16.data(), tmp16.size(), dtype);
+                for (size_t n = 0; n < rows; ++n) {
+                    double acc = 0.0;
+                    for (int k = 0; k < C; ++k) {
+                        const uint16_t u = tmp16[n * C + k];
+                        float f;
+                        if (dtype == SVB_FP16) { __half hh; memcpy(&hh, &u, 2); f = __half2float(hh); }
+                        else { const uint32_t w32 = (uint32_t)u << 16; memcpy(&f, &w32, 4); }
+                        acc += (double)f;
+                    }
+                    sn[n] = (float)acc;
+                }
+                bp.b1 = static_cast<float*>(slab.put(tn.data(), tn.size() * 4));
+                bp.s1 = static_cast<float*>(slab.put(sn.data(), sn.size() * 4));
+            } else {
+                convert16(w1->data, tmp16.data(), tmp16.size(), dtype);
+            }
             bp.w1 = slab.put(tmp16.data(), tmp16.size() * 2);
             convert16(w2->data, tmp16.data(), tmp16.size(), dtype);
             bp.w2 = slab.put(tmp16.data(), tmp16.size() * 2);
@@ -457,6 +507,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
         for (auto& bp : m->blocks[s]) {
             rebase(bp.wdw, base); rebase(bp.bdw, base); rebase(bp.lnw, base); rebase(bp.lnb, base);
             rebase(bp.b1, base); rebase(bp.b2, base); rebase(bp.gamma, base);
+            if (m->ln_fold) rebase(bp.s1, base);
             if (m->v2) { rebase(bp.grn_w, base); rebase(bp.grn_b, base); }
             bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
             bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
@@ -509,7 +560,7 @@ extern "C" int svb_model_info(const svb_model* m, int32_t out[10]) {
 namespace svb {
 
 struct WsLayout {
-    size_t x, a, h, grn_part, grn_scale, total;
+    size_t x, a, h, stat, grn_part, grn_scale, total;
 };
 static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     // stage 0 is the largest for every buffer (tokens/4, channels*2 per stage)
@@ -520,6 +571,7 @@ static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     L.x = o; o += align_up(t0 * c0 * 2, 1024);
     L.a = o; o += align_up(t0 * c0 * 2, 1024);
     L.h = o; o += align_up(t0 * c0 * 4 * 2, 1024);
+    L.stat = o; o += align_up(t0 * 8, 1024);  // (rstd, -mu rstd) per token: the folded LayerNorm of the current block
     L.grn_part = L.grn_scale = o;
     if (m->v2) {  // partial sums of squares [nb][ceil(tokens / GRN_ROWS)][4C] and scales [nb][4C]: the largest stage of each
         size_t part = 0, scale = 0;
@@ -546,6 +598,14 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
             const uint64_t strides[3] = {C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
             const uint32_t box[4] = {64, 14, (uint32_t)(dw_th((int)C) + 6), 1};
             if (int rc = encode_tmap(&p->x_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE))
+                return rc;
+        }
+        {
+            const uint64_t dims[4] = {C, (uint64_t)w, (uint64_t)h, (uint64_t)nb};
+            const uint64_t strides[3] = {C * 2, (uint64_t)w * C * 2, (uint64_t)h * w * C * 2};
+            const uint32_t box[4] = {64, 22, 14, 1};  // DwRawCfg: TW + 6, TH + 6
+            if (int rc = encode_tmap(&p->xr_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
                                      CU_TENSOR_MAP_SWIZZLE_NONE))
                 return rc;
         }
@@ -588,7 +648,7 @@ static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** o
 // ---- launchers -------------------------------------------------------------------------------
 template <typename T, int BN, int MODE, int CG, int HALF = 0>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
-                         const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st) {
+                         const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st, const float2* rowstat = nullptr) {
     using Cfg = GemmCfg<BN, CG, HALF>;
     auto kern = gemm_kernel<T, BN, MODE, CG, HALF>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -615,14 +675,16 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K));
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K, rowstat));
     count_launch();
     return SVB_OK;
 }
 template <typename T>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
-                       const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st, bool half = false) {
+                       const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st, bool half = false,
+                       const float2* rowstat = nullptr) {
     SVB_REQUIRE(N % 32 == 0 && K % 8 == 0, SVB_ERR_INVALID_ARG, "gemm: N (%d) must be a multiple of 32, K (%d) of 8", N, K);
+    SVB_REQUIRE(mode != GEMM_LNGELU || (rowstat && gamma && !half), SVB_ERR_INVALID_ARG, "gemm: the folded-LayerNorm mode needs rowstat and s_n");
     const int bn = gemm_bn_for(N, half);
     const int cg = gemm_cg(N, K);
     if (half) {
@@ -640,7 +702,11 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     }
 #define SVB_GEMM_CASE(BN_, MODE_, CG_)                                          \
     if (bn == BN_ && mode == MODE_ && cg == CG_)                                \
-        return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st);
+        return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st, rowstat);
+    SVB_GEMM_CASE(256, GEMM_LNGELU, 2)
+    SVB_GEMM_CASE(128, GEMM_LNGELU, 2)
+    SVB_GEMM_CASE(256, GEMM_LNGELU, 1)
+    SVB_GEMM_CASE(128, GEMM_LNGELU, 1)
     SVB_GEMM_CASE(256, GEMM_GELU, 2)
     SVB_GEMM_CASE(128, GEMM_GELU, 2)
     SVB_GEMM_CASE(256, GEMM_RESID, 2)
@@ -721,6 +787,50 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
                                    static_cast<T*>(out), H, W, tx, ty, tiles));
     count_launch();
     return SVB_OK;
+}
+template <typename T, int C>
+static int launch_dwconv_raw_t(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W, cudaStream_t st) {
+    constexpr int TH = 8;
+    using Cfg = DwRawCfg<C, TH>;
+    auto kern = dwconv_raw_kernel<T, C, TH>;
+    static bool attr_done[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (!attr_done[dslot]) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done[dslot] = true;
+    }
+    const int tx = ceil_div(W, Cfg::TW), ty = ceil_div(H, TH);
+    const int tiles = nb * tx * ty;
+    const int slots = num_sms() * 2;  // persistent CTAs, two per SM
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(tiles < slots ? tiles : slots);
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wdw_map, (const float*)bp.bdw, static_cast<T*>(out), rowstat, H, W, tx, ty, tiles));
+    count_launch();
+    return SVB_OK;
+}
+template <typename T>
+static int launch_dwconv_raw(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int C, int nb, int H, int W, cudaStream_t st) {
+    switch (C) {
+        case 128: return launch_dwconv_raw_t<T, 128>(x, bp, out, rowstat, nb, H, W, st);
+        case 256: return launch_dwconv_raw_t<T, 256>(x, bp, out, rowstat, nb, H, W, st);
+        case 512: return launch_dwconv_raw_t<T, 512>(x, bp, out, rowstat, nb, H, W, st);
+        case 1024: return launch_dwconv_raw_t<T, 1024>(x, bp, out, rowstat, nb, H, W, st);
+        case 2048: return launch_dwconv_raw_t<T, 2048>(x, bp, out, rowstat, nb, H, W, st);
+        case 96: return launch_dwconv_raw_t<T, 96>(x, bp, out, rowstat, nb, H, W, st);
+        case 192: return launch_dwconv_raw_t<T, 192>(x, bp, out, rowstat, nb, H, W, st);
+        case 384: return launch_dwconv_raw_t<T, 384>(x, bp, out, rowstat, nb, H, W, st);
+        case 768: return launch_dwconv_raw_t<T, 768>(x, bp, out, rowstat, nb, H, W, st);
+        case 1536: return launch_dwconv_raw_t<T, 1536>(x, bp, out, rowstat, nb, H, W, st);
+    }
+    return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv (raw): unsupported width %d", C);
 }
 template <typename T, int C>
 static int launch_dwconv_tc_t(const CUtensorMap& xtc, const BlockParams& bp, void* out, int nb, int H, int W, int NR, cudaStream_t st) {
@@ -915,7 +1025,18 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                                             nullptr, M2, C, 4 * Cin, GEMM_BIAS, st));
         }
         const int M = nb * h * w;
+        float2* rowstat = reinterpret_cast<float2*>(ws + L.stat);
         for (const BlockParams& bp : m->blocks[s]) {
+            if (m->ln_fold) {
+                RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], bp, A, rowstat, C, nb, h, w, st));
+                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, M, 4 * C, C,
+                                                GEMM_LNGELU, st, false, rowstat));
+                if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd, nb, h * w, 4 * C, bp.grn_w, bp.grn_b, reinterpret_cast<float*>(ws + L.grn_part),
+                                                          reinterpret_cast<float*>(ws + L.grn_scale), st));
+                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
+                                                GEMM_RESID, st, coex_stage(s)));
+                continue;
+            }
             if (plan->tc_rows[s]) {
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv_tc<T>(plan->xtc_map[s], bp, A, C, nb, h, w, plan->tc_rows[s], st));
             } else {
@@ -1044,15 +1165,17 @@ extern "C" int svb_gemm(const void* d_a, const void* d_w, void* d_out, const voi
     if (int rc = check_device_sm100()) return rc;
     SVB_REQUIRE(d_a && d_w && d_out && d_bias, SVB_ERR_INVALID_ARG, "gemm: null argument");
     SVB_REQUIRE(mode != GEMM_RESID || (d_resid && d_gamma), SVB_ERR_INVALID_ARG, "gemm: residual mode needs resid and gamma");
+    SVB_REQUIRE(mode != GEMM_LNGELU || (d_resid && d_gamma), SVB_ERR_INVALID_ARG, "gemm: folded-LayerNorm mode needs the row statistics (d_resid) and s_n (d_gamma)");
     SVB_REQUIRE(M > 0 && N > 0 && K > 0, SVB_ERR_INVALID_ARG, "gemm: bad shape");
     CUtensorMap a_map, w_map, out_map, resid_map;
     if (int rc = make_operand_map(&a_map, dtype, d_a, M, K, 128)) return rc;
-    const bool half = gemm_half_env() && N % 128 == 0;
+    const bool half = gemm_half_env() && N % 128 == 0 && mode != GEMM_LNGELU;
+    const float2* rowstat = mode == GEMM_LNGELU ? static_cast<const float2*>(d_resid) : nullptr;
     if (int rc = make_operand_map(&w_map, dtype, d_w, N, K, gemm_bn_for(N, half) / gemm_cg(N, K))) return rc;
     if (int rc = make_epilogue_map(&out_map, dtype, d_out, M, N)) return rc;
     if (int rc = make_epilogue_map(&resid_map, dtype, mode == GEMM_RESID ? d_resid : d_out, M, N)) return rc;
-    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half);
-    return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half);
+    if (dtype == SVB_FP16) return launch_gemm<__half>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half, rowstat);
+    return launch_gemm<__nv_bfloat16>(a_map, w_map, out_map, resid_map, d_bias, d_gamma, M, N, K, mode, st, half, rowstat);
 }
 
 extern "C" int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
@@ -1131,6 +1254,34 @@ extern "C" int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* 
     }
     if (dtype == SVB_FP16) return launch_dwconv<__half>(x_map, bp, d_out, C, B, H, W, st);
     return launch_dwconv<__nv_bfloat16>(x_map, bp, d_out, C, B, H, W, st);
+}
+
+extern "C" int svb_dwconv_raw(const void* d_x, const float* d_taps, const float* d_bias, void* d_out, float* d_rowstat, int B, int H,
+                              int W, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_taps && d_bias && d_out && d_rowstat && B > 0 && H > 0 && W > 0, SVB_ERR_INVALID_ARG, "dwconv_raw: bad arguments");
+    BlockParams bp{};
+    bp.wdw = const_cast<float*>(d_taps);
+    bp.bdw = const_cast<float*>(d_bias);
+    {
+        const uint64_t dims[2] = {(uint64_t)C, 49};
+        const uint64_t strides[1] = {(uint64_t)C * 4};
+        const uint32_t box[2] = {64, 49};
+        if (int rc = encode_tmap(&bp.wdw_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_taps, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return rc;
+    }
+    CUtensorMap x_map;
+    {
+        const uint64_t uC = C;
+        const uint64_t dims[4] = {uC, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        const uint64_t strides[3] = {uC * 2, (uint64_t)W * uC * 2, (uint64_t)H * W * uC * 2};
+        const uint32_t box[4] = {64, 22, 14, 1};
+        if (int rc = encode_tmap(&x_map, tmap_dtype(dtype), 4, d_x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+    }
+    float2* rs = reinterpret_cast<float2*>(d_rowstat);
+    if (dtype == SVB_FP16) return launch_dwconv_raw<__half>(x_map, bp, d_out, rs, C, B, H, W, st);
+    return launch_dwconv_raw<__nv_bfloat16>(x_map, bp, d_out, rs, C, B, H, W, st);
 }
 
 extern "C" int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,

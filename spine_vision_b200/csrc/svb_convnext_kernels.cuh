@@ -535,6 +535,223 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
     if (wid == TW) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ============================================================================ depthwise 7x7, LayerNorm folded into fc1
+// The LayerNorm that follows the depthwise convolution is an affine map PER TOKEN; composed with fc1 it is
+//     fc1(LN(y))[m, n] = rstd_m * (sum_k W1[n,k] g_k y[m,k]) - rstd_m mu_m * (sum_k W1[n,k] g_k) + (sum_k W1[n,k] b_k + b1[n])
+// so this kernel writes the RAW convolution y (16-bit, the fc1 A operand) plus two numbers per token (rstd_m, -mu_m rstd_m) and
+// the fc1 GEMM applies them in its epilogue (GEMM_LNGELU: acc over W1 * diag(g), column constants s_n and t_n).  What that buys:
+//   * no parking of a tile's fp32 results for a second (LayerNorm) pass: no TMEM capacity limit on the tile, so a warp owns TWO
+//     pixel columns (every halo value feeds both; the loop reaches 83 instead of 70 FMA / clk / SM, scripts/ubench/convloop2.cu)
+//   * the LayerNorm pass itself (a fifth of the old kernel's instructions) shrinks to two accumulations per value
+//   * the A operand is not rounded a second time after normalisation: predicted AND measured coordinate error goes DOWN
+//     (scripts/emulate_precision.py: fp16 trained-like 0.176 -> 0.119 px)
+// The statistics are taken from the 16-bit ROUNDED values (the ones the GEMM multiplies), so that rstd * (acc - mu * s) cancels
+// exactly as LayerNorm's (y - mu) does.  One pass: var = E[y^2] - mu^2 in fp32 over C <= 2048 values.
+// Per thread 16 pixels x (sum, sum of squares) have to live across the channel chunks; 32 more registers next to the
+// convolution's 88 would spill, so between chunks they are parked in 64 columns of TENSOR MEMORY (one tcgen05.st / .ld pair per
+// chunk, against 784 FFMA2).
+template <int C, int TH>
+struct DwRawCfg {
+    static constexpr int NC = 2, WARPS = 8, TW = WARPS * NC, CC = 64, NCH = (C + CC - 1) / CC;
+    static constexpr bool RAGGED = (C % CC) != 0;
+    static constexpr int HALO_H = TH + 6, HALO_W = TW + 6;
+    static constexpr int HALO_BYTES = HALO_H * HALO_W * CC * 2;
+    static constexpr int W_BYTES = 49 * CC * 4;
+    static constexpr int STAGE_BYTES = ((HALO_BYTES + W_BYTES + 127) / 128) * 128;
+    static constexpr int STAGES = NCH < 2 ? NCH : 2;
+    static constexpr int TMEM_COLS = 64;  // two warps per lane quarter x 32 statistics columns
+    // eight warps, no separate producer warp: a ninth warp makes 18 warps per SM = 5 on one scheduler, which caps every thread
+    // at 96 registers (the loop needs ~110); lane 0 of warp 0 issues the TMA loads between its own chunks instead
+    static constexpr int NUM_THREADS = 32 * WARPS;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + align slack
+    static_assert(C % 32 == 0, "C must be a multiple of 32");
+    static_assert(HALO_BYTES % 128 == 0, "halo stage must keep the tap buffer 128B aligned");
+    static_assert(2 * SMEM_BYTES <= 227 * 1024, "two CTAs per SM");
+};
+
+__device__ __forceinline__ void tmem_st_32(uint32_t taddr, const float (&v)[32]) {
+    const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+
+template <typename T, int C, int TH>
+__global__ void __launch_bounds__(DwRawCfg<C, TH>::NUM_THREADS, 2)
+dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map,
+                  const float* __restrict__ bdw, T* __restrict__ out, float2* __restrict__ rowstat, int H, int W, int tiles_x,
+                  int tiles_y, int num_tiles) {
+    using Cfg = DwRawCfg<C, TH>;
+    constexpr int TW = Cfg::TW, CC = Cfg::CC, STAGES = Cfg::STAGES, HALO_W = Cfg::HALO_W, NCH = Cfg::NCH, WARPS = Cfg::WARPS;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* s_stage = smem;
+    uint64_t* s_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* s_empty = s_full + STAGES;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_empty + STAGES);
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) {
+        tma_prefetch_desc(&x_map);
+        tma_prefetch_desc(&w_map);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], WARPS); }
+        mbar_fence_init();
+    }
+    if (wid == 0) tmem_alloc<1>(s_tmem, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    pdl_launch_dependents();
+
+    {
+        // ---- warp = pixel columns x0, x0 + 1; lane = channel pair of the chunk.  Lane 0 of warp 0 is also the TMA producer:
+        // before it starts iteration `it` it issues the load of iteration it + STAGES - 1 (the stage iteration it - 1 used; every
+        // warp has arrived on its "empty" barrier by the time the slowest of them finished it), so a load has one whole chunk of
+        // arithmetic to land.  The ring runs on across tiles.
+        const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int total_it = my_tiles * NCH;
+        int pj = 0;  // next iteration whose load has not been issued (producer lane only)
+        auto produce_to = [&](int last) {
+            for (; pj <= last && pj < total_it; ++pj) {
+                const int stage = pj % STAGES;
+                if (pj >= STAGES) mbar_wait(&s_empty[stage], ((pj / STAGES) - 1) & 1);
+                int t = (int)blockIdx.x + (pj / NCH) * (int)gridDim.x;
+                const int k = pj % NCH;
+                const int tx = t % tiles_x; t /= tiles_x;
+                const int ty = t % tiles_y;
+                const int b = t / tiles_y;
+                uint8_t* dst = s_stage + stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&s_full[stage], Cfg::HALO_BYTES + Cfg::W_BYTES);
+                tma_load_4d(dst, &x_map, &s_full[stage], k * CC, tx * TW - 3, ty * TH - 3, b);
+                tma_load_2d(dst + Cfg::HALO_BYTES, &w_map, &s_full[stage], k * CC, 0);
+            }
+        };
+        const bool producer = wid == 0 && lane == 0;
+        const uint32_t tcol0 = tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((wid >> 2) * 32);
+        int it = 0;
+        pdl_wait();
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            int t = tile;
+            const int tx = t % tiles_x; t /= tiles_x;
+            const int ty = t % tiles_y;
+            const int b = t / tiles_y;
+            const int x0 = tx * TW + 2 * wid, y0 = ty * TH;
+            auto ch_ok = [&](int kk) { return !Cfg::RAGGED || kk * CC + 2 * lane < C; };
+            float2 bias_next = ch_ok(0) ? __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane)) : make_float2(0.f, 0.f);
+            float st[32];  // per pixel p = c * TH + i: st[2p] = sum, st[2p + 1] = sum of squares over this lane's channels so far
+            for (int k = 0; k < NCH; ++k, ++it) {
+                const int stage = it % STAGES;
+                const float2 bias = bias_next;
+                if (k + 1 < NCH) bias_next = ch_ok(k + 1) ? __ldg(reinterpret_cast<const float2*>(bdw + (k + 1) * CC + 2 * lane)) : make_float2(0.f, 0.f);
+                if (producer) produce_to(it + STAGES - 1);
+                __syncwarp();
+                mbar_wait(&s_full[stage], (it / STAGES) & 1);
+                const uint32_t* halo = reinterpret_cast<const uint32_t*>(s_stage + stage * Cfg::STAGE_BYTES) + (2 * wid) * 32 + lane;  // [HALO_H][HALO_W][32] pairs
+                const uint64_t* taps = reinterpret_cast<const uint64_t*>(s_stage + stage * Cfg::STAGE_BYTES + Cfg::HALO_BYTES) + lane;  // [49][32] fp32 pairs
+                uint64_t acc0[TH], acc1[TH];
+#pragma unroll
+                for (int i = 0; i < TH; ++i) acc0[i] = acc1[i] = pk2(bias.x, bias.y);
+                // input column j of the 8 the two outputs read: tap kx = j for output column 0, kx = j - 1 for column 1
+                {
+                    uint64_t col[TH + 6], w0[7];
+#pragma unroll
+                    for (int r = 0; r < TH + 6; ++r) col[r] = unpack2_pk<T>(halo[(r * HALO_W + 0) * 32]);
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky) w0[ky] = taps[(ky * 7 + 0) * 32];
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                        for (int i = 0; i < TH; ++i) acc0[i] = fma2(col[i + ky], w0[ky], acc0[i]);
+                }
+#pragma unroll 1
+                for (int j = 1; j < 7; ++j) {
+                    uint64_t col[TH + 6], w0[7], w1[7];
+#pragma unroll
+                    for (int r = 0; r < TH + 6; ++r) col[r] = unpack2_pk<T>(halo[(r * HALO_W + j) * 32]);
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky) { w0[ky] = taps[(ky * 7 + j) * 32]; w1[ky] = taps[(ky * 7 + j - 1) * 32]; }
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                        for (int i = 0; i < TH; ++i) { acc0[i] = fma2(col[i + ky], w0[ky], acc0[i]); acc1[i] = fma2(col[i + ky], w1[ky], acc1[i]); }
+                }
+                {
+                    uint64_t col[TH + 6], w1[7];
+#pragma unroll
+                    for (int r = 0; r < TH + 6; ++r) col[r] = unpack2_pk<T>(halo[(r * HALO_W + 7) * 32]);
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky) w1[ky] = taps[(ky * 7 + 6) * 32];
+#pragma unroll
+                    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+                        for (int i = 0; i < TH; ++i) acc1[i] = fma2(col[i + ky], w1[ky], acc1[i]);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(&s_empty[stage]);  // the stage is in registers
+                // ---- round to 16 bits, store the fc1 operand, fold the rounded values into the token statistics
+                if (k > 0) {
+                    TmemLd<32>::ld(tcol0, st);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) st[q] = 0.f;
+                }
+                const bool okc = ch_ok(k);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                    for (int i = 0; i < TH; ++i) {
+                        float lo, hi;
+                        upk2(c == 0 ? acc0[i] : acc1[i], lo, hi);
+                        const uint32_t pk = Cvt<T>::pack2(lo, hi);
+                        const float2 r = Cvt<T>::unpack2(pk);
+                        const int p = c * TH + i;
+                        st[2 * p] += r.x + r.y;
+                        st[2 * p + 1] = fmaf(r.x, r.x, fmaf(r.y, r.y, st[2 * p + 1]));
+                        const int x = x0 + c, y = y0 + i;
+                        if (okc && x < W && y < H)
+                            reinterpret_cast<uint32_t*>(out + (((size_t)b * H + y) * W + x) * C)[k * (CC / 2) + lane] = pk;
+                    }
+                }
+                if (k + 1 < NCH) {
+                    tmem_st_32(tcol0, st);
+                    tmem_st_wait();
+                }
+            }
+            // ---- token statistics: sum over the 32 lanes (every channel of the pixel), then (rstd, -mu * rstd)
+#pragma unroll
+            for (int g4 = 0; g4 < (2 * TH) / 4; ++g4) {
+                float s4[4], q4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { s4[j] = st[2 * (4 * g4 + j)]; q4[j] = st[2 * (4 * g4 + j) + 1]; }
+                warp_sum4(s4, lane);
+                warp_sum4(q4, lane);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int p = 4 * g4 + j;
+                    const int x = x0 + p / TH, y = y0 + p % TH;
+                    if (lane == p && x < W && y < H) {
+                        const float mu = s4[j] * (1.0f / C);
+                        const float var = fmaxf(fmaf(-mu, mu, q4[j] * (1.0f / C)), 0.0f);
+                        const float rstd = 1.0f / sqrtf(var + LN_EPS_BACKBONE);
+                        rowstat[((size_t)b * H + y) * W + x] = make_float2(rstd, -mu * rstd);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (wid == 0) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+}
+
 // ============================================================================ tcgen05 GEMM
 // D[M,N] = epilogue(A[M,K] * Wt[N,K]^T); A, Wt K-major 16-bit; fp32 accumulation in TMEM.
 // Persistent CTAs, BK = 64 (one 128-byte swizzle atom), warp roles:
@@ -548,7 +765,9 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 // CG == 2 (cta_group::2): a cluster of two CTAs computes a 256 x BN tile.  Each CTA stages its own
 // 128 rows of A and HALF of the W tile (BN/2 rows), so the W traffic from L2 per output element is
 // halved; the leader issues tcgen05.mma.cta_group::2 for both and multicasts the commits.
-enum GemmMode { GEMM_GELU = 0, GEMM_RESID = 1, GEMM_BIAS = 2 };
+// GEMM_LNGELU: fc1 with the block's LayerNorm folded in (see dwconv_raw_kernel): GELU(rstd_m * acc + (-mu_m rstd_m) * s_n + t_n),
+// (rstd_m, -mu_m rstd_m) = rowstat[m], s_n passed as `gamma`, t_n as `bias`
+enum GemmMode { GEMM_GELU = 0, GEMM_RESID = 1, GEMM_BIAS = 2, GEMM_LNGELU = 3 };
 
 // HALF == 1: the "co-resident" footprint -- at most half of an SM (<= 113.5 KB of shared memory, 256 TMEM columns, 320
 // threads), so that a depthwise-conv CTA of the OTHER micro-batch chain (or a second GEMM CTA) fits beside it and the
@@ -616,7 +835,8 @@ template <typename T, int BN, int MODE, int CG, int HALF = 0>
 __global__ void __launch_bounds__(GemmCfg<BN, CG, HALF>::NUM_THREADS, HALF ? 2 : 1)  // HALF: <= 102 registers, so that it fits beside a depthwise CTA
 gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
             const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap resid_map,
-            const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K) {
+            const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K,
+            const float2* __restrict__ rowstat) {
     using Cfg = GemmCfg<BN, CG, HALF>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -733,6 +953,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
             const int row0 = (m_blk * CG + (int)rank) * Cfg::BM + q * 32;
             const int colw = n_blk * BN + slice * CW;
             const bool active = colw < N && row0 < M;  // warp-uniform
+            uint64_t ra2 = 0, rb2 = 0;  // GEMM_LNGELU: this thread's row (token): (rstd, rstd) and (-mu rstd, -mu rstd)
+            if (MODE == GEMM_LNGELU) {
+                const float2 rs = (active && row0 + lane < M) ? __ldg(rowstat + row0 + lane) : make_float2(0.f, 0.f);
+                ra2 = pk2(rs.x, rs.x);
+                rb2 = pk2(rs.y, rs.y);
+            }
             if (MODE == GEMM_RESID && active && lane == 0) {
                 // the first residual box of the tile arrives while the MMAs are still running
                 bulk_wait_read<0>();
@@ -767,12 +993,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
                     const uint32_t addr = row_off + ((((uint32_t)i) ^ swz) << 4);
                     const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * i);
                     const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col) + 2 * i + 1);
-                    uint64_t v01 = add2(pk2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), pk2(b0.x, b0.y));
-                    uint64_t v23 = add2(pk2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), pk2(b0.z, b0.w));
-                    uint64_t v45 = add2(pk2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), pk2(b1.x, b1.y));
-                    uint64_t v67 = add2(pk2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), pk2(b1.z, b1.w));
+                    uint64_t v01, v23, v45, v67;
+                    if (MODE == GEMM_LNGELU) {
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i);
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i + 1);
+                        v01 = fma2(ra2, pk2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), fma2(rb2, pk2(s0.x, s0.y), pk2(b0.x, b0.y)));
+                        v23 = fma2(ra2, pk2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), fma2(rb2, pk2(s0.z, s0.w), pk2(b0.z, b0.w)));
+                        v45 = fma2(ra2, pk2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), fma2(rb2, pk2(s1.x, s1.y), pk2(b1.x, b1.y)));
+                        v67 = fma2(ra2, pk2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), fma2(rb2, pk2(s1.z, s1.w), pk2(b1.z, b1.w)));
+                    } else {
+                        v01 = add2(pk2(__uint_as_float(r[8 * i + 0]), __uint_as_float(r[8 * i + 1])), pk2(b0.x, b0.y));
+                        v23 = add2(pk2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])), pk2(b0.z, b0.w));
+                        v45 = add2(pk2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])), pk2(b1.x, b1.y));
+                        v67 = add2(pk2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])), pk2(b1.z, b1.w));
+                    }
                     uint4 o;
-                    if (MODE == GEMM_GELU) {
+                    if (MODE == GEMM_GELU || MODE == GEMM_LNGELU) {
                         o = make_uint4(gelu_pack2<T>(v01), gelu_pack2<T>(v23), gelu_pack2<T>(v45), gelu_pack2<T>(v67));
                     } else {
                         if (MODE == GEMM_RESID) {

@@ -470,6 +470,20 @@ def dwconv_ln(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torc
 
 
 @_on_device
+def dwconv_raw(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None):
+    """Depthwise 7x7 + bias, LayerNorm folded into fc1 (``svb_dwconv_raw``): x NHWC 16-bit [B,H,W,C] -> (raw convolution
+    [B,H,W,C] 16-bit, row statistics float32 [B*H*W, 2] = (rstd, -mean * rstd) of each token's rounded values).  The fc1 that
+    consumes them is ``gemm(a, w_g, t, mode=3, resid=rowstat, gamma=s)``."""
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    stat = torch.empty((B * H * W, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().svb_dwconv_raw(x.data_ptr(), taps.data_ptr(), bias.data_ptr(), out.data_ptr(), stat.data_ptr(), B, H, W, Cc,
+                                          _dt(x), _lib.current_stream()))
+    return out, stat
+
+
+@_on_device
 def dwconv_ln_tc(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
     """Same operator as ``dwconv_ln`` on the tensor cores (taps are rounded to the activation dtype)."""
     B, H, W, Cc = x.shape

@@ -98,6 +98,48 @@ def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 128), (1, 37, 21, 128), (2, 64, 64, 256), (3, 32, 32, 512), (2, 16, 16, 1024), (1, 15, 23, 1024),
+                                     (1, 128, 128, 128), (1, 9, 13, 2048), (2, 40, 24, 192), (2, 17, 32, 768), (2, 33, 40, 96), (1, 7, 5, 384)])
+def test_dwconv_raw_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
+    """The default block: ``svb_dwconv_raw`` (raw depthwise convolution in 16 bits + per-token (rstd, -mean * rstd)) followed by the
+    fc1 GEMM with the LayerNorm folded in (``svb_gemm`` mode 3) equals GELU(fc1(LayerNorm(conv(x)))) of plain PyTorch fp32:
+    (a) the raw output is the convolution to 16-bit rounding; (b) the statistics are those of the ROUNDED values; (c) the
+    composite is within the output rounding of the un-folded reference."""
+    g = torch.Generator().manual_seed(B + H + W + C)
+    x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
+    wt = torch.randn(C, 1, 7, 7, generator=g) * 0.1
+    bias = torch.randn(C, generator=g) * 0.1 + 0.3  # a non-zero token mean: the subtraction in the epilogue has something to cancel
+    lnw = 1 + 0.2 * torch.randn(C, generator=g)
+    lnb = 0.1 * torch.randn(C, generator=g)
+    N = 4 * C if C <= 512 else 512
+    w1 = torch.randn(N, C, generator=g) / C ** 0.5
+    b1 = 0.1 * torch.randn(N, generator=g)
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    taps = wt.reshape(C, 49).t().contiguous()
+    raw, stat = ops.dwconv_raw(x.to(dev()), taps.to(dev()), bias.to(dev()))
+    torch.cuda.synchronize()
+    rawf = raw.float().cpu()
+    eps16 = 2.0 ** -8 if dtype == "bf16" else 2.0 ** -11
+    assert int(((rawf - y).abs() > eps16 * (y.abs() + 1.0)).sum()) == 0, f"raw conv: max err {(rawf - y).abs().max().item():.4g}"
+    mu = rawf.mean(-1)
+    var = rawf.var(-1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-6)
+    st = stat.cpu().view(B, H, W, 2)
+    assert torch.allclose(st[..., 0], rstd, rtol=2e-4, atol=1e-6), (st[..., 0] - rstd).abs().max()
+    assert torch.allclose(st[..., 1], -mu * rstd, rtol=2e-4, atol=2e-4), (st[..., 1] + mu * rstd).abs().max()
+    wg = (w1 * lnw[None, :]).to(DT[dtype])
+    s_n = wg.float().sum(1)
+    t_n = (w1.double() @ lnb.double()).float() + b1
+    got = ops.gemm(raw.view(-1, C), wg.to(dev()), t_n.to(dev()), 3, resid=stat, gamma=s_n.to(dev())).float().cpu()
+    want = F.gelu(F.layer_norm(y, (C,), lnw, lnb, 1e-6).reshape(-1, C) @ w1.t() + b1)
+    err = (got - want).abs()
+    # the reference rounds nothing; the device rounds the conv output and W1 * g to 16 bits and accumulates in fp32: the bound is
+    # the operand rounding through a C-term dot product of O(1) terms (same budget as the un-folded pair: LN output + W1 rounded)
+    tol = 4 * eps16 * (want.abs() + 1.0)
+    assert int((err > tol).sum()) == 0, f"{int((err > tol).sum())} beyond tolerance, max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("C0,C", [(192, 192), (192, 384), (256, 768), (96, 96)])
 def test_stem_patchify_other_widths(dtype, C0, C):
     """The widths of convnext_large / xlarge: stem at 192 / 256 channels, LayerNorm + patchify at 192 (a half-empty last lane
