@@ -5,7 +5,7 @@ from pathlib import Path
 import torch
 
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
-from spine_vision_b200 import ops, pipeline, synthetic  # noqa: E402
+from spine_vision_b200 import ops, pipeline, synthetic, volumes  # noqa: E402
 
 dev = "cuda:0"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
@@ -47,7 +47,25 @@ def norm():
     ops.normalize_u8(pool, out=norm_out)
 
 
-for name, fn, nbytes in (("normalize_u8 (no resize)", norm, B * 1195 * 1195 * 5), ("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120),
+# K0 and the fused K0 + K1 call of the end-to-end path, on the source planes of config-1 volumes
+plans = [volumes.plan_midplane(*synthetic.make_volume(s)) for s in range(8)]
+pv = volumes.PinnedVolumes.from_plans([plans[i % 8] for i in range(B)])
+k0_vols, k0_desc = pv.host.to(dev), pv.chunk_descs(0, B).to(dev)
+k0_pool = ops.SlicePool(torch.empty(max(pv.out_total, 4), dtype=torch.float32, device=dev), torch.tensor(pv.out_offs, dtype=torch.int64).to(dev),
+                        torch.tensor(pv.shapes, dtype=torch.int32).reshape(-1, 2).to(dev), list(pv.shapes))
+
+
+def k0():
+    ops.midplane_resample_into(k0_vols, k0_desc, k0_pool)
+
+
+def k01():
+    ops.midplane_normalize_resize(k0_vols, k0_desc, k0_pool, (512, 512), out=planes)
+
+
+for name, fn, nbytes in (("K0 midplane resample", k0, B * (2 * 512 * 512 * 4 + 1195 * 1195 * 4)),
+                         ("K0+K1 fused", k01, B * (2 * 512 * 512 * 4 + 2 * 1195 * 1195 * 4 + 512 * 512)),
+                         ("normalize_u8 (no resize)", norm, B * 1195 * 1195 * 5), ("K1 normalize+resize", k1, B * (1195 * 1195 * 4 + 512 * 512)), ("K3 crop+resample", k3, B * 5 * 269120),
                          ("K4 classifier input", k4, P * 65536 * 14)):
     if REPS == 0:
         fn(); torch.cuda.synchronize(); continue

@@ -44,24 +44,30 @@ for s, (C, hw) in enumerate([(128, 128), (256, 64), (512, 32), (1024, 16)]):
     taps = (torch.randn(49, C, generator=g) * 0.1).to(dev)
     bias = torch.zeros(C, device=dev)
     lnw, lnb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
-    timeit(f"dwconv_ln C={C} {hw}x{hw}", lambda: ops.dwconv_ln(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
-    if C == 512:
-        timeit(f"dwconv_ln_tc C={C} {hw}x{hw}", lambda: ops.dwconv_ln_tc(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
-    a = x.view(M, C)
+    raw = torch.empty_like(x)
+    # the default block: raw depthwise conv + token statistics, fc1 with the LayerNorm folded in
+    timeit(f"dwconv_raw C={C} {hw}x{hw}", lambda: ops.dwconv_raw(x, taps, bias, out=raw), flops=2.0 * M * C * 49, nbytes=M * C * 4)
+    _, stat = ops.dwconv_raw(x, taps, bias, out=raw)
+    if REPS != 0:  # the round-1 block (SVB_LN_FOLD=0), for comparison; not launched in profiling mode
+        timeit(f"dwconv_ln C={C} {hw}x{hw}", lambda: ops.dwconv_ln(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
+    a = raw.view(M, C)
     w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dt).to(dev)
     b1 = torch.zeros(4 * C, device=dev)
+    s1 = w1.float().sum(1)
     hd = torch.empty((M, 4 * C), dtype=dt, device=dev)
-    timeit(f"fc1+gelu  M={M} N={4*C} K={C}", lambda: ops.gemm(a, w1, b1, 0, out=hd), flops=2.0 * M * 4 * C * C, nbytes=M * C * 2 * 5)
+    timeit(f"fc1+LN+gelu M={M} N={4*C} K={C}", lambda: ops.gemm(a, w1, b1, 3, resid=stat, gamma=s1, out=hd), flops=2.0 * M * 4 * C * C, nbytes=M * C * 2 * 5)
+    if REPS != 0:
+        timeit(f"fc1+gelu  M={M} N={4*C} K={C}", lambda: ops.gemm(a, w1, b1, 0, out=hd), flops=2.0 * M * 4 * C * C, nbytes=M * C * 2 * 5)
     w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dt).to(dev)
     b2 = torch.zeros(C, device=dev)
     gam = torch.ones(C, device=dev)
     xo = a.clone()
     timeit(f"fc2+resid M={M} N={C} K={4*C}", lambda: ops.gemm(hd, w2, b2, 1, resid=xo, gamma=gam, out=xo), flops=2.0 * M * 4 * C * C,
            nbytes=M * C * 2 * 6)
-    if C in (128, 256):
+    if C in (128, 256) and REPS != 0:
         xf = a.clone()
         timeit(f"fused MLP M={M} C={C}", lambda: ops.mlp_fused(a, w1, b1, w2, b2, gam, xf), flops=4.0 * M * 4 * C * C, nbytes=M * C * 2 * 3)
-    del x, hd, xo
+    del x, hd, xo, raw
 u8 = torch.randint(0, 256, (NB, 512, 512), generator=g, dtype=torch.uint8).to(dev)
 wf, bf = (torch.randn(128, 16, generator=g) * 0.01).to(dev), torch.zeros(128, device=dev)
 timeit("stem_ln", lambda: ops.stem_ln(u8, wf, bf, torch.ones(128, device=dev), torch.zeros(128, device=dev)), nbytes=NB * (512 * 512 + 16384 * 256))

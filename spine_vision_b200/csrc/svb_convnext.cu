@@ -42,6 +42,7 @@ struct ActPlan {  // tensor maps that depend on the workspace pointer and the mi
     int nb = 0, H = 0, W = 0;
     CUtensorMap x_map[4];   // 4-D NHWC halo maps per stage
     CUtensorMap xr_map[4];  // the same for dwconv_raw_kernel (16-pixel-wide tiles: box {64, 22, 14, 1})
+    CUtensorMap xr4_map[4]; // ... and its 4-row tiles (box {64, 22, 10, 1})
     CUtensorMap xtc_map[4]; // 4-D NHWC maps of the tensor-core depthwise kernel: box {64, W+6, rows, 1}, 128B swizzle
     int tc_rows[4] = {0, 0, 0, 0};  // rows per box; 0 = the stage runs the CUDA-core kernel
     CUtensorMap a_map[4];   // [M, C]   fc1 A operand
@@ -608,6 +609,10 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
             if (int rc = encode_tmap(&p->xr_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
                                      CU_TENSOR_MAP_SWIZZLE_NONE))
                 return rc;
+            const uint32_t box4[4] = {64, 22, 10, 1};
+            if (int rc = encode_tmap(&p->xr4_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box4,
+                                     CU_TENSOR_MAP_SWIZZLE_NONE))
+                return rc;
         }
         p->tc_rows[s] = dw_tc_rows((int)C, w);
         if (p->tc_rows[s]) {
@@ -788,9 +793,8 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
     count_launch();
     return SVB_OK;
 }
-template <typename T, int C>
-static int launch_dwconv_raw_t(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W, cudaStream_t st) {
-    constexpr int TH = 8;
+template <typename T, int C, int TH>
+static int launch_dwconv_raw_th(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W, cudaStream_t st) {
     using Cfg = DwRawCfg<C, TH>;
     auto kern = dwconv_raw_kernel<T, C, TH>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -816,19 +820,27 @@ static int launch_dwconv_raw_t(const CUtensorMap& x, const BlockParams& bp, void
     count_launch();
     return SVB_OK;
 }
+// rows per tile: 8, or 4 when 8-row tiles would leave most of the 2 x 148 CTA slots empty (the last stage: 16 x 16 tokens per image)
+static int dw_raw_th(int nb, int H, int W) { return nb * ceil_div(W, 16) * ceil_div(H, 8) >= num_sms() * 3 / 2 ? 8 : 4; }
+template <typename T, int C>
+static int launch_dwconv_raw_t(const CUtensorMap& x8, const CUtensorMap& x4, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W,
+                               cudaStream_t st) {
+    if (dw_raw_th(nb, H, W) == 8) return launch_dwconv_raw_th<T, C, 8>(x8, bp, out, rowstat, nb, H, W, st);
+    return launch_dwconv_raw_th<T, C, 4>(x4, bp, out, rowstat, nb, H, W, st);
+}
 template <typename T>
-static int launch_dwconv_raw(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int C, int nb, int H, int W, cudaStream_t st) {
+static int launch_dwconv_raw(const CUtensorMap& x, const CUtensorMap& x4, const BlockParams& bp, void* out, float2* rowstat, int C, int nb, int H, int W, cudaStream_t st) {
     switch (C) {
-        case 128: return launch_dwconv_raw_t<T, 128>(x, bp, out, rowstat, nb, H, W, st);
-        case 256: return launch_dwconv_raw_t<T, 256>(x, bp, out, rowstat, nb, H, W, st);
-        case 512: return launch_dwconv_raw_t<T, 512>(x, bp, out, rowstat, nb, H, W, st);
-        case 1024: return launch_dwconv_raw_t<T, 1024>(x, bp, out, rowstat, nb, H, W, st);
-        case 2048: return launch_dwconv_raw_t<T, 2048>(x, bp, out, rowstat, nb, H, W, st);
-        case 96: return launch_dwconv_raw_t<T, 96>(x, bp, out, rowstat, nb, H, W, st);
-        case 192: return launch_dwconv_raw_t<T, 192>(x, bp, out, rowstat, nb, H, W, st);
-        case 384: return launch_dwconv_raw_t<T, 384>(x, bp, out, rowstat, nb, H, W, st);
-        case 768: return launch_dwconv_raw_t<T, 768>(x, bp, out, rowstat, nb, H, W, st);
-        case 1536: return launch_dwconv_raw_t<T, 1536>(x, bp, out, rowstat, nb, H, W, st);
+        case 128: return launch_dwconv_raw_t<T, 128>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 256: return launch_dwconv_raw_t<T, 256>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 512: return launch_dwconv_raw_t<T, 512>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 1024: return launch_dwconv_raw_t<T, 1024>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 2048: return launch_dwconv_raw_t<T, 2048>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 96: return launch_dwconv_raw_t<T, 96>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 192: return launch_dwconv_raw_t<T, 192>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 384: return launch_dwconv_raw_t<T, 384>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 768: return launch_dwconv_raw_t<T, 768>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 1536: return launch_dwconv_raw_t<T, 1536>(x, x4, bp, out, rowstat, nb, H, W, st);
     }
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv (raw): unsupported width %d", C);
 }
@@ -1028,7 +1040,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
         float2* rowstat = reinterpret_cast<float2*>(ws + L.stat);
         for (const BlockParams& bp : m->blocks[s]) {
             if (m->ln_fold) {
-                RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], bp, A, rowstat, C, nb, h, w, st));
+                RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, nb, h, w, st));
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, M, 4 * C, C,
                                                 GEMM_LNGELU, st, false, rowstat));
                 if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd, nb, h * w, 4 * C, bp.grn_w, bp.grn_b, reinterpret_cast<float*>(ws + L.grn_part),
@@ -1271,17 +1283,19 @@ extern "C" int svb_dwconv_raw(const void* d_x, const float* d_taps, const float*
         if (int rc = encode_tmap(&bp.wdw_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d_taps, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE))
             return rc;
     }
-    CUtensorMap x_map;
+    CUtensorMap x_map, x4_map;
     {
         const uint64_t uC = C;
         const uint64_t dims[4] = {uC, (uint64_t)W, (uint64_t)H, (uint64_t)B};
         const uint64_t strides[3] = {uC * 2, (uint64_t)W * uC * 2, (uint64_t)H * W * uC * 2};
         const uint32_t box[4] = {64, 22, 14, 1};
         if (int rc = encode_tmap(&x_map, tmap_dtype(dtype), 4, d_x, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
+        const uint32_t box4[4] = {64, 22, 10, 1};
+        if (int rc = encode_tmap(&x4_map, tmap_dtype(dtype), 4, d_x, dims, strides, box4, CU_TENSOR_MAP_SWIZZLE_NONE)) return rc;
     }
     float2* rs = reinterpret_cast<float2*>(d_rowstat);
-    if (dtype == SVB_FP16) return launch_dwconv_raw<__half>(x_map, bp, d_out, rs, C, B, H, W, st);
-    return launch_dwconv_raw<__nv_bfloat16>(x_map, bp, d_out, rs, C, B, H, W, st);
+    if (dtype == SVB_FP16) return launch_dwconv_raw<__half>(x_map, x4_map, bp, d_out, rs, C, B, H, W, st);
+    return launch_dwconv_raw<__nv_bfloat16>(x_map, x4_map, bp, d_out, rs, C, B, H, W, st);
 }
 
 extern "C" int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,

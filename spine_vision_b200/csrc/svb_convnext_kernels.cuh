@@ -545,11 +545,11 @@ dwconv_ln_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constan
 //   * the LayerNorm pass itself (a fifth of the old kernel's instructions) shrinks to two accumulations per value
 //   * the A operand is not rounded a second time after normalisation: predicted AND measured coordinate error goes DOWN
 //     (scripts/emulate_precision.py: fp16 trained-like 0.176 -> 0.119 px)
-// The statistics are taken from the 16-bit ROUNDED values (the ones the GEMM multiplies), so that rstd * (acc - mu * s) cancels
-// exactly as LayerNorm's (y - mu) does.  One pass: var = E[y^2] - mu^2 in fp32 over C <= 2048 values.
-// Per thread 16 pixels x (sum, sum of squares) have to live across the channel chunks; 32 more registers next to the
-// convolution's 88 would spill, so between chunks they are parked in 64 columns of TENSOR MEMORY (one tcgen05.st / .ld pair per
-// chunk, against 784 FFMA2).
+// The statistics are taken from the fp32 results before rounding (mean of the rounded values differs by the MEAN rounding error,
+// 2^-12 |y| / sqrt(C): far below one element's rounding).  One pass: var = E[y^2] - mu^2 in fp32 over C <= 2048 values.
+// Per thread 16 pixels x packed (sum, sum of squares) pairs have to live across the channel chunks; 64 more registers next to
+// the convolution's 88 would spill, so between chunks they are parked in TENSOR MEMORY (two tcgen05.st / .ld pairs per chunk,
+// against 784 FFMA2) -- the epilogue of a chunk is then one F2FP, one STG and two packed FMA-pipe operations per pixel.
 template <int C, int TH>
 struct DwRawCfg {
     static constexpr int NC = 2, WARPS = 8, TW = WARPS * NC, CC = 64, NCH = (C + CC - 1) / CC;
@@ -559,7 +559,9 @@ struct DwRawCfg {
     static constexpr int W_BYTES = 49 * CC * 4;
     static constexpr int STAGE_BYTES = ((HALO_BYTES + W_BYTES + 127) / 128) * 128;
     static constexpr int STAGES = NCH < 2 ? NCH : 2;
-    static constexpr int TMEM_COLS = 64;  // two warps per lane quarter x 32 statistics columns
+    static constexpr int ST = 4 * NC * TH;  // statistics words per thread: (sum lo, sum hi, sumsq lo, sumsq hi) per pixel
+    static constexpr int TMEM_COLS = 2 * ST < 32 ? 32 : 2 * ST;  // two warps per lane quarter
+    static_assert(ST == 32 || ST == 64, "TH = 4 or 8");
     // eight warps, no separate producer warp: a ninth warp makes 18 warps per SM = 5 on one scheduler, which caps every thread
     // at 96 registers (the loop needs ~110); lane 0 of warp 0 issues the TMA loads between its own chunks instead
     static constexpr int NUM_THREADS = 32 * WARPS;
@@ -634,7 +636,7 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
             }
         };
         const bool producer = wid == 0 && lane == 0;
-        const uint32_t tcol0 = tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((wid >> 2) * 32);
+        const uint32_t tcol0 = tmem_base + ((uint32_t)((wid & 3) * 32) << 16) + (uint32_t)((wid >> 2) * Cfg::ST);
         int it = 0;
         pdl_wait();
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -645,7 +647,12 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
             const int x0 = tx * TW + 2 * wid, y0 = ty * TH;
             auto ch_ok = [&](int kk) { return !Cfg::RAGGED || kk * CC + 2 * lane < C; };
             float2 bias_next = ch_ok(0) ? __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane)) : make_float2(0.f, 0.f);
-            float st[32];  // per pixel p = c * TH + i: st[2p] = sum, st[2p + 1] = sum of squares over this lane's channels so far
+            // per pixel p = c * TH + i: st[4p .. 4p+1] = packed sum, st[4p+2 .. 4p+3] = packed sum of squares of this lane's two
+            // channels over the chunks so far
+            float st[Cfg::ST];
+            const int nrow = min(TH, H - y0);  // rows of the tile inside the image
+            uint32_t* const orow0 = reinterpret_cast<uint32_t*>(out + (((size_t)b * H + y0) * W + x0) * C) + lane;
+            const size_t row_pitch = (size_t)W * (C / 2);
             for (int k = 0; k < NCH; ++k, ++it) {
                 const int stage = it % STAGES;
                 const float2 bias = bias_next;
@@ -695,33 +702,42 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive_relaxed(&s_empty[stage]);  // the stage is in registers
-                // ---- round to 16 bits, store the fc1 operand, fold the rounded values into the token statistics
+                // ---- round to 16 bits and store the fc1 operand; fold the fp32 values into the token statistics
                 if (k > 0) {
                     TmemLd<32>::ld(tcol0, st);
+                    if constexpr (Cfg::ST == 64) TmemLd<32>::ld(tcol0 + 32u, st + 32);
                     tmem_ld_wait();
                 } else {
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) st[q] = 0.f;
+                    for (int q = 0; q < Cfg::ST; ++q) st[q] = 0.f;
                 }
                 const bool okc = ch_ok(k);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
+                    const bool okx = okc && x0 + c < W;
+                    uint32_t* op = orow0 + c * (C / 2) + k * (CC / 2);
 #pragma unroll
                     for (int i = 0; i < TH; ++i) {
+                        const uint64_t v = c == 0 ? acc0[i] : acc1[i];
                         float lo, hi;
-                        upk2(c == 0 ? acc0[i] : acc1[i], lo, hi);
-                        const uint32_t pk = Cvt<T>::pack2(lo, hi);
-                        const float2 r = Cvt<T>::unpack2(pk);
+                        upk2(v, lo, hi);
                         const int p = c * TH + i;
-                        st[2 * p] += r.x + r.y;
-                        st[2 * p + 1] = fmaf(r.x, r.x, fmaf(r.y, r.y, st[2 * p + 1]));
-                        const int x = x0 + c, y = y0 + i;
-                        if (okc && x < W && y < H)
-                            reinterpret_cast<uint32_t*>(out + (((size_t)b * H + y) * W + x) * C)[k * (CC / 2) + lane] = pk;
+                        uint64_t s2 = pk2(st[4 * p], st[4 * p + 1]), q2 = pk2(st[4 * p + 2], st[4 * p + 3]);
+                        s2 = add2(s2, v);
+                        q2 = fma2(v, v, q2);
+                        upk2(s2, st[4 * p], st[4 * p + 1]);
+                        upk2(q2, st[4 * p + 2], st[4 * p + 3]);
+                        if (okx && i < nrow) *op = Cvt<T>::pack2(lo, hi);
+                        op += row_pitch;
                     }
                 }
                 if (k + 1 < NCH) {
-                    tmem_st_32(tcol0, st);
+                    if constexpr (Cfg::ST == 64) {
+                        tmem_st_32(tcol0, *reinterpret_cast<const float(*)[32]>(st));
+                        tmem_st_32(tcol0 + 32u, *reinterpret_cast<const float(*)[32]>(st + 32));
+                    } else {
+                        tmem_st_32(tcol0, *reinterpret_cast<const float(*)[32]>(st));
+                    }
                     tmem_st_wait();
                 }
             }
@@ -730,7 +746,11 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
             for (int g4 = 0; g4 < (2 * TH) / 4; ++g4) {
                 float s4[4], q4[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) { s4[j] = st[2 * (4 * g4 + j)]; q4[j] = st[2 * (4 * g4 + j) + 1]; }
+                for (int j = 0; j < 4; ++j) {
+                    const int p = 4 * g4 + j;
+                    s4[j] = st[4 * p] + st[4 * p + 1];
+                    q4[j] = st[4 * p + 2] + st[4 * p + 3];
+                }
                 warp_sum4(s4, lane);
                 warp_sum4(q4, lane);
 #pragma unroll

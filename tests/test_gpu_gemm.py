@@ -103,8 +103,8 @@ def test_dwconv_ln_vs_torch(B, H, W, C, dtype):
 def test_dwconv_raw_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
     """The default block: ``svb_dwconv_raw`` (raw depthwise convolution in 16 bits + per-token (rstd, -mean * rstd)) followed by the
     fc1 GEMM with the LayerNorm folded in (``svb_gemm`` mode 3) equals GELU(fc1(LayerNorm(conv(x)))) of plain PyTorch fp32:
-    (a) the raw output is the convolution to 16-bit rounding; (b) the statistics are those of the ROUNDED values; (c) the
-    composite is within the output rounding of the un-folded reference."""
+    (a) the raw output is the convolution to 16-bit rounding; (b) the statistics are those of the fp32 convolution (taken before
+    the rounding); (c) the composite is within the output rounding of the un-folded reference."""
     g = torch.Generator().manual_seed(B + H + W + C)
     x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
     wt = torch.randn(C, 1, 7, 7, generator=g) * 0.1
@@ -121,8 +121,8 @@ def test_dwconv_raw_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
     rawf = raw.float().cpu()
     eps16 = 2.0 ** -8 if dtype == "bf16" else 2.0 ** -11
     assert int(((rawf - y).abs() > eps16 * (y.abs() + 1.0)).sum()) == 0, f"raw conv: max err {(rawf - y).abs().max().item():.4g}"
-    mu = rawf.mean(-1)
-    var = rawf.var(-1, unbiased=False)
+    mu = y.mean(-1)
+    var = y.var(-1, unbiased=False)
     rstd = torch.rsqrt(var + 1e-6)
     st = stat.cpu().view(B, H, W, 2)
     assert torch.allclose(st[..., 0], rstd, rtol=2e-4, atol=1e-6), (st[..., 0] - rstd).abs().max()
