@@ -653,7 +653,7 @@ static int get_plan(svb_model* m, uint8_t* ws, int nb, int H, int W, ActPlan** o
 // ---- launchers -------------------------------------------------------------------------------
 template <typename T, int BN, int MODE, int CG, int HALF = 0>
 static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
-                         const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st, const float2* rowstat = nullptr) {
+                         const float* bias, const float* gamma, int M, int N, int K, cudaStream_t st, const float2* rowstat = nullptr, int m0 = 0) {
     using Cfg = GemmCfg<BN, CG, HALF>;
     auto kern = gemm_kernel<T, BN, MODE, CG, HALF>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -663,7 +663,7 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
         if (carveout_max()) SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr_done[dslot] = true;
     }
-    const int tiles = ceil_div(M, 128 * CG) * ceil_div(N, BN);
+    const int tiles = ceil_div(M - m0, 128 * CG) * ceil_div(N, BN);
     const int units = num_sms() / CG;  // CTAs, or CTA pairs
     const int grid = (tiles < units ? tiles : units) * CG;
     cudaLaunchConfig_t cfg{};
@@ -680,14 +680,14 @@ static int launch_gemm_t(const CUtensorMap& a, const CUtensorMap& w, const CUten
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K, rowstat));
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, w, out, resid, bias, gamma, M, N, K, rowstat, m0));
     count_launch();
     return SVB_OK;
 }
 template <typename T>
 static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtensorMap& out, const CUtensorMap& resid,
                        const float* bias, const float* gamma, int M, int N, int K, int mode, cudaStream_t st, bool half = false,
-                       const float2* rowstat = nullptr) {
+                       const float2* rowstat = nullptr, int m0 = 0) {
     SVB_REQUIRE(N % 32 == 0 && K % 8 == 0, SVB_ERR_INVALID_ARG, "gemm: N (%d) must be a multiple of 32, K (%d) of 8", N, K);
     SVB_REQUIRE(mode != GEMM_LNGELU || (rowstat && gamma && !half), SVB_ERR_INVALID_ARG, "gemm: the folded-LayerNorm mode needs rowstat and s_n");
     const int bn = gemm_bn_for(N, half);
@@ -695,7 +695,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     if (half) {
 #define SVB_GEMM_HALF_CASE(MODE_, CG_)                                          \
     if (mode == MODE_ && cg == CG_)                                             \
-        return launch_gemm_t<T, 128, MODE_, CG_, 1>(a, w, out, resid, bias, gamma, M, N, K, st);
+        return launch_gemm_t<T, 128, MODE_, CG_, 1>(a, w, out, resid, bias, gamma, M, N, K, st, nullptr, m0);
         SVB_GEMM_HALF_CASE(GEMM_GELU, 2)
         SVB_GEMM_HALF_CASE(GEMM_RESID, 2)
         SVB_GEMM_HALF_CASE(GEMM_BIAS, 2)
@@ -707,7 +707,7 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     }
 #define SVB_GEMM_CASE(BN_, MODE_, CG_)                                          \
     if (bn == BN_ && mode == MODE_ && cg == CG_)                                \
-        return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st, rowstat);
+        return launch_gemm_t<T, BN_, MODE_, CG_>(a, w, out, resid, bias, gamma, M, N, K, st, rowstat, m0);
     SVB_GEMM_CASE(256, GEMM_LNGELU, 2)
     SVB_GEMM_CASE(128, GEMM_LNGELU, 2)
     SVB_GEMM_CASE(256, GEMM_LNGELU, 1)
@@ -794,7 +794,7 @@ static int launch_dwconv_t(const CUtensorMap& x, const BlockParams& bp, void* ou
     return SVB_OK;
 }
 template <typename T, int C, int TH>
-static int launch_dwconv_raw_th(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W, cudaStream_t st) {
+static int launch_dwconv_raw_th(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W, cudaStream_t st, int b0) {
     using Cfg = DwRawCfg<C, TH>;
     auto kern = dwconv_raw_kernel<T, C, TH>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -816,31 +816,61 @@ static int launch_dwconv_raw_th(const CUtensorMap& x, const BlockParams& bp, voi
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wdw_map, (const float*)bp.bdw, static_cast<T*>(out), rowstat, H, W, tx, ty, tiles));
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wdw_map, (const float*)bp.bdw, static_cast<T*>(out), rowstat, H, W, tx, ty, tiles, b0));
     count_launch();
     return SVB_OK;
 }
+// images per sub-batch of stage s (see forward_chunk): SVB_SUB="a,b,c,d" overrides per stage (0 = the whole micro-batch).
+// Default: as many images as keep the stage's hidden activation [tokens, 4C] x 16 bit near 32 MB per chain (two chains share L2),
+// whole GEMM row tiles only.
+static int sub_batch_images(int s, int nb, int tokens, int C) {
+    static int forced[4] = {-1, -1, -1, -1};
+    static bool parsed = false;
+    if (!parsed) {
+        parsed = true;
+        const char* e = getenv("SVB_SUB");
+        for (int i = 0; e && i < 4 && *e; ++i) {
+            forced[i] = atoi(e);
+            while (*e && *e != ',') ++e;
+            if (*e == ',') ++e;
+        }
+    }
+    int sub;
+    if (forced[s] >= 0) sub = forced[s] == 0 ? nb : forced[s];
+    else {
+        // Measured on B200 (profiles/r02j_subbatch.txt, ms per 256 series): whole micro-batch 69.4; 8/32 images 70.5; 4/16 72.3;
+        // 2/8 72.6; 1/4 75.8.  The hidden tensor does stay in L2, but launches of 8..64 tiles per SM lose more to their tails
+        // and to the second chain's evictions than the HBM round trip costs: off unless SVB_SUB asks for it.
+        (void)tokens; (void)C;
+        return nb;
+    }
+    if (sub < 1) sub = 1;
+    while (sub < nb && ((long long)sub * tokens) % 256 != 0) ++sub;  // whole 256-row tile pairs
+    return sub < nb ? sub : nb;
+}
+
 // rows per tile: 8, or 4 when 8-row tiles would leave most of the 2 x 148 CTA slots empty (the last stage: 16 x 16 tokens per image)
 static int dw_raw_th(int nb, int H, int W) { return nb * ceil_div(W, 16) * ceil_div(H, 8) >= num_sms() * 3 / 2 ? 8 : 4; }
 template <typename T, int C>
 static int launch_dwconv_raw_t(const CUtensorMap& x8, const CUtensorMap& x4, const BlockParams& bp, void* out, float2* rowstat, int nb, int H, int W,
-                               cudaStream_t st) {
-    if (dw_raw_th(nb, H, W) == 8) return launch_dwconv_raw_th<T, C, 8>(x8, bp, out, rowstat, nb, H, W, st);
-    return launch_dwconv_raw_th<T, C, 4>(x4, bp, out, rowstat, nb, H, W, st);
+                               cudaStream_t st, int b0) {
+    if (dw_raw_th(nb, H, W) == 8) return launch_dwconv_raw_th<T, C, 8>(x8, bp, out, rowstat, nb, H, W, st, b0);
+    return launch_dwconv_raw_th<T, C, 4>(x4, bp, out, rowstat, nb, H, W, st, b0);
 }
 template <typename T>
-static int launch_dwconv_raw(const CUtensorMap& x, const CUtensorMap& x4, const BlockParams& bp, void* out, float2* rowstat, int C, int nb, int H, int W, cudaStream_t st) {
+static int launch_dwconv_raw(const CUtensorMap& x, const CUtensorMap& x4, const BlockParams& bp, void* out, float2* rowstat, int C, int nb, int H, int W, cudaStream_t st,
+                             int b0 = 0) {
     switch (C) {
-        case 128: return launch_dwconv_raw_t<T, 128>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 256: return launch_dwconv_raw_t<T, 256>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 512: return launch_dwconv_raw_t<T, 512>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 1024: return launch_dwconv_raw_t<T, 1024>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 2048: return launch_dwconv_raw_t<T, 2048>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 96: return launch_dwconv_raw_t<T, 96>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 192: return launch_dwconv_raw_t<T, 192>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 384: return launch_dwconv_raw_t<T, 384>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 768: return launch_dwconv_raw_t<T, 768>(x, x4, bp, out, rowstat, nb, H, W, st);
-        case 1536: return launch_dwconv_raw_t<T, 1536>(x, x4, bp, out, rowstat, nb, H, W, st);
+        case 128: return launch_dwconv_raw_t<T, 128>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 256: return launch_dwconv_raw_t<T, 256>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 512: return launch_dwconv_raw_t<T, 512>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 1024: return launch_dwconv_raw_t<T, 1024>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 2048: return launch_dwconv_raw_t<T, 2048>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 96: return launch_dwconv_raw_t<T, 96>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 192: return launch_dwconv_raw_t<T, 192>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 384: return launch_dwconv_raw_t<T, 384>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 768: return launch_dwconv_raw_t<T, 768>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
+        case 1536: return launch_dwconv_raw_t<T, 1536>(x, x4, bp, out, rowstat, nb, H, W, st, b0);
     }
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv (raw): unsupported width %d", C);
 }
@@ -1038,17 +1068,29 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
         }
         const int M = nb * h * w;
         float2* rowstat = reinterpret_cast<float2*>(ws + L.stat);
-        for (const BlockParams& bp : m->blocks[s]) {
-            if (m->ln_fold) {
-                RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, nb, h, w, st));
-                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, M, 4 * C, C,
-                                                GEMM_LNGELU, st, false, rowstat));
-                if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd, nb, h * w, 4 * C, bp.grn_w, bp.grn_b, reinterpret_cast<float*>(ws + L.grn_part),
-                                                          reinterpret_cast<float*>(ws + L.grn_scale), st));
-                RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, M, C, 4 * C,
-                                                GEMM_RESID, st, coex_stage(s)));
-                continue;
+        if (m->ln_fold) {
+            // Depth-first over SUB-BATCHES of the micro-batch in the stages whose hidden activation is far larger than L2: the
+            // [tokens, 4C] tensor fc1 writes is read back by fc2 while it is still in the 126 MB L2 (and the depthwise kernel
+            // finds the residual stream fc2 just wrote there), instead of making the round trip through HBM.  A sub-batch is a
+            // whole number of GEMM row tiles, so the tensor maps of the micro-batch serve every sub-batch (row / image offset).
+            const int tok = h * w;
+            int sub = sub_batch_images(s, nb, tok, C);
+            for (int b0 = 0; b0 < nb; b0 += sub) {
+                const int ns = (nb - b0) < sub ? (nb - b0) : sub;
+                const int m0 = b0 * tok, m1 = (b0 + ns) * tok;
+                for (const BlockParams& bp : m->blocks[s]) {
+                    RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
+                    RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, m1, 4 * C, C,
+                                                    GEMM_LNGELU, st, false, rowstat, m0));
+                    if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd + (size_t)m0 * 4 * C, ns, tok, 4 * C, bp.grn_w, bp.grn_b,
+                                                              reinterpret_cast<float*>(ws + L.grn_part), reinterpret_cast<float*>(ws + L.grn_scale), st));
+                    RUN(SVB_KC_GEMM, launch_gemm<T>(plan->h_map[s], bp.w2_map, plan->ox_map[s], plan->ox_map[s], bp.b2, bp.gamma, m1, C, 4 * C,
+                                                    GEMM_RESID, st, false, nullptr, m0));
+                }
             }
+            continue;
+        }
+        for (const BlockParams& bp : m->blocks[s]) {
             if (plan->tc_rows[s]) {
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv_tc<T>(plan->xtc_map[s], bp, A, C, nb, h, w, plan->tc_rows[s], st));
             } else {

@@ -588,7 +588,8 @@ template <typename T, int C, int TH>
 __global__ void __launch_bounds__(DwRawCfg<C, TH>::NUM_THREADS, 2)
 dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap w_map,
                   const float* __restrict__ bdw, T* __restrict__ out, float2* __restrict__ rowstat, int H, int W, int tiles_x,
-                  int tiles_y, int num_tiles) {
+                  int tiles_y, int num_tiles, int b0) {
+    // images [b0, b0 + num_tiles / (tiles_x * tiles_y)) of the micro-batch the tensor map describes
     using Cfg = DwRawCfg<C, TH>;
     constexpr int TW = Cfg::TW, CC = Cfg::CC, STAGES = Cfg::STAGES, HALO_W = Cfg::HALO_W, NCH = Cfg::NCH, WARPS = Cfg::WARPS;
     extern __shared__ uint8_t smem_raw[];
@@ -628,7 +629,7 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
                 const int k = pj % NCH;
                 const int tx = t % tiles_x; t /= tiles_x;
                 const int ty = t % tiles_y;
-                const int b = t / tiles_y;
+                const int b = b0 + t / tiles_y;
                 uint8_t* dst = s_stage + stage * Cfg::STAGE_BYTES;
                 mbar_expect_tx(&s_full[stage], Cfg::HALO_BYTES + Cfg::W_BYTES);
                 tma_load_4d(dst, &x_map, &s_full[stage], k * CC, tx * TW - 3, ty * TH - 3, b);
@@ -643,7 +644,7 @@ dwconv_raw_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_consta
             int t = tile;
             const int tx = t % tiles_x; t /= tiles_x;
             const int ty = t % tiles_y;
-            const int b = t / tiles_y;
+            const int b = b0 + t / tiles_y;
             const int x0 = tx * TW + 2 * wid, y0 = ty * TH;
             auto ch_ok = [&](int kk) { return !Cfg::RAGGED || kk * CC + 2 * lane < C; };
             float2 bias_next = ch_ok(0) ? __ldg(reinterpret_cast<const float2*>(bdw + 2 * lane)) : make_float2(0.f, 0.f);
@@ -856,7 +857,8 @@ __global__ void __launch_bounds__(GemmCfg<BN, CG, HALF>::NUM_THREADS, HALF ? 2 :
 gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w_map,
             const __grid_constant__ CUtensorMap out_map, const __grid_constant__ CUtensorMap resid_map,
             const float* __restrict__ bias, const float* __restrict__ gamma, int M, int N, int K,
-            const float2* __restrict__ rowstat) {
+            const float2* __restrict__ rowstat, int m0) {
+    // rows [m0, M) of the operands the tensor maps describe (m0 a multiple of the tile height: a sub-batch of a micro-batch)
     using Cfg = GemmCfg<BN, CG, HALF>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -875,7 +877,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int tiles_n = (N + BN - 1) / BN;
-    const int tiles_m = (M + Cfg::BM * CG - 1) / (Cfg::BM * CG);
+    const int tiles_m = (M - m0 + Cfg::BM * CG - 1) / (Cfg::BM * CG);
     const int num_tiles = tiles_m * tiles_n;
     const int num_kb = (K + Cfg::BK - 1) / Cfg::BK;
     const int tile0 = (int)blockIdx.x / CG, tile_step = (int)gridDim.x / CG;
@@ -905,7 +907,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
             uint32_t phase = 0;
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-                const int row_a = (m_blk * CG + (int)rank) * Cfg::BM;
+                const int row_a = m0 + (m_blk * CG + (int)rank) * Cfg::BM;
                 const int row_b = n_blk * BN + (int)rank * Cfg::B_ROWS;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
@@ -970,7 +972,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
         pdl_wait();
         for (int tile = tile0; tile < num_tiles; tile += tile_step) {
             const int m_blk = tile / tiles_n, n_blk = tile - m_blk * tiles_n;
-            const int row0 = (m_blk * CG + (int)rank) * Cfg::BM + q * 32;
+            const int row0 = m0 + (m_blk * CG + (int)rank) * Cfg::BM + q * 32;
             const int colw = n_blk * BN + slice * CW;
             const bool active = colw < N && row0 < M;  // warp-uniform
             uint64_t ra2 = 0, rb2 = 0;  // GEMM_LNGELU: this thread's row (token): (rstd, rstd) and (-mu rstd, -mu rstd)
