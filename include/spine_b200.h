@@ -268,7 +268,16 @@ int svb_dwconv_ln(const void* d_x, const float* d_taps, const float* d_bias, con
 int svb_dwconv_raw(const void* d_x, const float* d_taps, const float* d_bias, void* d_out, float* d_rowstat, int B, int H, int W,
                    int C, int dtype, void* stream);
 
-/* Same operator on the tensor cores (shifted-view diagonal tcgen05 MMAs); taps16 = the taps as 16-bit
+/* The same operator on the tensor cores (dwconv_rawtc_kernel: seven row-shifted tcgen05 MMAs per 16 channels with the stencil
+ * columns side by side in N, column sum by warp shuffles); what the model runs for fp16.  Same outputs as
+ * svb_dwconv_raw (d_out, d_rowstat); the taps are 16-bit operands: d_wtc = svb_dwconv_tc_pack(taps) ([C/64][7][112][64] of
+ * `dtype`, packed on the HOST from fp32 [49][C]).  d_stat_part = scratch, float32 [B*H*W][C/64][2] (each token's sum / sum of
+ * squares per 64-channel chunk; a second small launch adds them up into d_rowstat).  C must be a multiple of 64. */
+int svb_dwconv_tc_pack(const float* h_taps, void* h_wtc, int C, int dtype);
+int svb_dwconv_raw_tc(const void* d_x, const void* d_wtc, const float* d_bias, void* d_out, float* d_rowstat, float* d_stat_part, int B,
+                      int H, int W, int C, int dtype, void* stream);
+
+/* The first tensor-core version (one MMA per tap; measured slower, kept as evidence): shifted-view diagonal tcgen05 MMAs; taps16 = the taps as 16-bit
  * [49][C] of `dtype`.  Supported for C = 256 / 512 while the halo tile fits in shared memory, else SVB_ERR_UNSUPPORTED_MODEL. */
 int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,
                      const float* d_lnb, void* d_out, int B, int H, int W, int C, int dtype, void* stream);

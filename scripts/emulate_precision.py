@@ -8,6 +8,8 @@ Schemes per ConvNeXt block:
   ln_fold   y16 = r16(dwconv(x)); stats from y16;             H = r16(gelu(rstd * (y16 @ r16(W1 * g)^T - mu * s) + t))
             (LayerNorm folded into fc1: s_n = sum_k r16(W1*g)[n,k], t = W1 @ b_ln + b1 -- the depthwise kernel then writes the raw
              convolution and two statistics per token; no TMEM parking, no second pass)
+  tc_dw     ln_fold with the depthwise taps rounded to 16 bits (operands of the tensor-core depthwise kernel, dwconv_rawtc_kernel)
+  tc_dw_h   tc_dw with the off-centre column partial sums rounded to 16 bits before the cross-lane sum (packed shuffles)
 Test infrastructure (imports oracle/)."""
 import sys
 from pathlib import Path
@@ -41,9 +43,21 @@ def forward(m, x, scheme):
             w = r16(st.downsample[1].weight)
             x = r16(F.conv2d(a.permute(0, 3, 1, 2), w, st.downsample[1].bias, stride=2).permute(0, 2, 3, 1))
         for blk in st.blocks:
-            y = F.conv2d(x.permute(0, 3, 1, 2), blk.conv_dw.weight, blk.conv_dw.bias, padding=3, groups=x.shape[-1]).permute(0, 2, 3, 1)
+            wdw = r16(blk.conv_dw.weight) if scheme.startswith("tc_dw") else blk.conv_dw.weight  # tc_dw: taps are 16-bit tensor-core operands
+            if scheme == "tc_dw_h":
+                # the six off-centre stencil COLUMNS' partial sums (over the 7 rows) cross lanes as 16-bit values
+                xc = x.permute(0, 3, 1, 2)
+                y = blk.conv_dw.bias[None, :, None, None] + 0 * xc
+                for dx in range(7):
+                    wcol = torch.zeros_like(wdw)
+                    wcol[..., dx] = wdw[..., dx]
+                    part = F.conv2d(xc, wcol, None, padding=3, groups=x.shape[-1])
+                    y = y + (part if dx == 3 else r16(part))
+                y = y.permute(0, 2, 3, 1)
+            else:
+                y = F.conv2d(x.permute(0, 3, 1, 2), wdw, blk.conv_dw.bias, padding=3, groups=x.shape[-1]).permute(0, 2, 3, 1)
             W1, b1 = blk.mlp.fc1.weight, blk.mlp.fc1.bias
-            if scheme == "current":
+            if scheme == "current":  # (the round-1 block; not in the default list any more)
                 a = r16(ln(y, blk.norm.weight, blk.norm.bias))
                 h = a @ r16(W1).t() + b1
             else:
@@ -70,6 +84,6 @@ for trained in (False, True):
     xs = torch.stack([ref.preprocess_slice(synthetic.make_iso_slice(*c), (512, 512))[1] for c in SLICES])
     with torch.no_grad():
         want = m(xs)
-        for scheme in ("current", "ln_fold"):
+        for scheme in ("ln_fold", "tc_dw", "tc_dw_h"):
             got = forward(m, xs, scheme)
             print(f"{DT} trained_like={trained} {scheme:8s}: max coordinate error {float((got - want).abs().max()) * 512:.4f} px at 512^2", flush=True)

@@ -11,7 +11,7 @@ from spine_vision_b200 import ops  # noqa: E402
 dev = "cuda:0"
 NB = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 REPS = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-dt = torch.bfloat16
+dt = torch.float16 if (len(sys.argv) > 3 and sys.argv[3] == "fp16") else torch.bfloat16
 g = torch.Generator().manual_seed(0)
 
 
@@ -48,6 +48,11 @@ for s, (C, hw) in enumerate([(128, 128), (256, 64), (512, 32), (1024, 16)]):
     # the default block: raw depthwise conv + token statistics, fc1 with the LayerNorm folded in
     timeit(f"dwconv_raw C={C} {hw}x{hw}", lambda: ops.dwconv_raw(x, taps, bias, out=raw), flops=2.0 * M * C * 49, nbytes=M * C * 4)
     _, stat = ops.dwconv_raw(x, taps, bias, out=raw)
+    if C % 64 == 0:  # the tensor-core depthwise kernel (what the model runs for fp16) and fc1 fed by its partial statistics
+        wtc = ops.dwconv_tc_pack(taps, dt)
+        raw_tc = torch.empty_like(x)
+        part = torch.empty((M, C // 64, 2), dtype=torch.float32, device=dev)
+        timeit(f"dwconv_raw_tc C={C} {hw}x{hw}", lambda: ops.dwconv_raw_tc(x, wtc, bias, out=raw_tc, part=part), flops=2.0 * M * C * 49, nbytes=M * C * 4)
     if REPS != 0:  # the round-1 block (SVB_LN_FOLD=0), for comparison; not launched in profiling mode
         timeit(f"dwconv_ln C={C} {hw}x{hw}", lambda: ops.dwconv_ln(x, taps, bias, lnw, lnb), flops=2.0 * M * C * 49, nbytes=M * C * 4)
     a = raw.view(M, C)

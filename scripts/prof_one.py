@@ -1,0 +1,26 @@
+"""One launch of one layer kernel for ncu: python scripts/prof_one.py <kind> <C> <hw> <nb> [fp16|bf16]"""
+import sys
+from pathlib import Path
+
+import torch
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from spine_vision_b200 import ops  # noqa: E402
+
+kind, C, hw, NB = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+dt = torch.float16 if (len(sys.argv) > 5 and sys.argv[5] == "fp16") else torch.bfloat16
+dev = "cuda:0"
+g = torch.Generator().manual_seed(0)
+x = torch.randn(NB, hw, hw, C, generator=g).to(dt).to(dev)
+taps = (torch.randn(49, C, generator=g) * 0.1).to(dev)
+bias = torch.zeros(C, device=dev)
+M = NB * hw * hw
+if kind == "dwtc":
+    wtc = ops.dwconv_tc_pack(taps, dt)
+    out = torch.empty_like(x)
+    for _ in range(2):
+        ops.dwconv_raw_tc(x, wtc, bias, out=out)
+elif kind == "dwraw":
+    for _ in range(2):
+        ops.dwconv_raw(x, taps, bias)
+torch.cuda.synchronize()

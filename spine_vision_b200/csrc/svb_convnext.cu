@@ -29,7 +29,8 @@ struct BlockParams {
     float* s1 = nullptr;  // LayerNorm folded into fc1 (svb_model::ln_fold): s_n = sum_k r16(W1[n,k] g_k); b1 then holds t_n
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
     void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
-    CUtensorMap wdw_map, wdw16_map, w1_map, w2_map;
+    void* wtc = nullptr;  // dwconv_rawtc_kernel: [C/64][7 dy][112 = (dx, c')][64 k] 16-bit, zero except k % 16 == c' (see the kernel)
+    CUtensorMap wdw_map, wdw16_map, w1_map, w2_map, wtc_map;
     CUtensorMap w1f_map, w2f_map;  // fused-MLP weight boxes: W1 {64, 32}, W2 {64, C/2} (each CTA of the pair stages half a tile)
 };
 struct DownParams {
@@ -45,6 +46,8 @@ struct ActPlan {  // tensor maps that depend on the workspace pointer and the mi
     CUtensorMap xr4_map[4]; // ... and its 4-row tiles (box {64, 22, 10, 1})
     CUtensorMap xtc_map[4]; // 4-D NHWC maps of the tensor-core depthwise kernel: box {64, W+6, rows, 1}, 128B swizzle
     int tc_rows[4] = {0, 0, 0, 0};  // rows per box; 0 = the stage runs the CUDA-core kernel
+    CUtensorMap xtc2_map[4];         // dwconv_rawtc_kernel: box {64, W, 256 / W + 6, 1} (mode A) or {64, 32, 14, 1} (mode B), 128B swizzle
+    int tc2[4] = {0, 0, 0, 0};       // 0 = the stage runs dwconv_raw_kernel; 1 = mode A; 2 = mode B
     CUtensorMap a_map[4];   // [M, C]   fc1 A operand
     CUtensorMap h_map[4];   // [M, 4C]  fc2 A operand
     CUtensorMap a2_map[4];  // [M/4, 4C_prev] downsample A operand (index = destination stage)
@@ -254,6 +257,47 @@ static int dw_tc_rows(int C, int W) {
     return smem <= 227 * 1024 ? NR : 0;
 }
 
+// dwconv_rawtc_kernel (the 7 x 7 taps as seven row-shifted tcgen05 MMAs with the stencil columns in N).  0 = the stage keeps
+// dwconv_raw_kernel; 1 = mode A (W in {8, 16, 32}: units of whole image rows); 2 = mode B (32-lane windows with an x halo).
+// SVB_DWCONV_TC2=0 switches it off, =2 also allows bf16 (8-bit tap mantissas; fp16 keeps 11).  SVB_TC2_MODEB=0 keeps mode B off.
+static int dw_tc2_mode(int dtype, int C, int H, int W) {
+    static int enabled = -1, modeb = -1;
+    if (enabled < 0) {
+        const char* e = getenv("SVB_DWCONV_TC2");
+        enabled = e ? atoi(e) : 1;
+        const char* b = getenv("SVB_TC2_MODEB");
+        modeb = b ? atoi(b) : 1;
+    }
+    if (!enabled || (dtype != SVB_FP16 && enabled < 2)) return 0;
+    if (C % 64 != 0 || C / 64 > num_sms() || H < 1 || W < 1) return 0;
+    if (W == 8 || W == 16 || W == 32) return 1;
+    return modeb ? 2 : 0;
+}
+// taps fp32 [49][C] -> B operands [C/64][7 dy][112 = dx * 16 + c'][64 = g * 16 + c] (16-bit): w[dy][dx][64 k + 16 g + c] where c == c'
+static void pack_wtc(const float* taps, uint16_t* dst, int C, int dtype) {
+    const int NCH = C / 64;
+    memset(dst, 0, (size_t)NCH * 7 * 112 * 64 * 2);
+    for (int k = 0; k < NCH; ++k)
+        for (int dy = 0; dy < 7; ++dy)
+            for (int dx = 0; dx < 7; ++dx)
+                for (int g = 0; g < 4; ++g)
+                    for (int c = 0; c < 16; ++c)
+                        dst[(((size_t)k * 7 + dy) * 112 + dx * 16 + c) * 64 + g * 16 + c] = to16(taps[(size_t)(dy * 7 + dx) * C + k * 64 + g * 16 + c], dtype);
+}
+static int make_wtc_map(CUtensorMap* map, int dtype, const void* base, int C) {
+    const uint64_t dims[2] = {64, (uint64_t)(C / 64) * 7 * 112};
+    const uint64_t strides[1] = {128};
+    const uint32_t box[2] = {64, 112};
+    return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+static int make_xtc2_map(CUtensorMap* map, int dtype, const void* base, int C, int nb, int H, int W, int mode) {
+    const uint64_t uC = C;
+    const uint64_t dims[4] = {uC, (uint64_t)W, (uint64_t)H, (uint64_t)nb};
+    const uint64_t strides[3] = {uC * 2, (uint64_t)W * uC * 2, (uint64_t)H * W * uC * 2};
+    const uint32_t box[4] = {64, (uint32_t)(mode == 1 ? W : 32), (uint32_t)(mode == 1 ? 256 / W + 6 : 14), 1};
+    return encode_tmap(map, tmap_dtype(dtype), 4, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 struct HostWeights {
     std::map<std::string, const svb_weight_desc*> by_name;
     const svb_weight_desc* get(const std::string& n) const {
@@ -411,6 +455,11 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             tmp16.resize((size_t)49 * C);
             for (size_t i = 0; i < tmp16.size(); ++i) tmp16[i] = to16(taps[i], dtype);
             bp.wdw16 = slab.put(tmp16.data(), tmp16.size() * 2);
+            if (C % 64 == 0) {  // B operands of dwconv_rawtc_kernel (98 KB per 64 channels)
+                tmp16.resize((size_t)(C / 64) * 7 * 112 * 64);
+                pack_wtc(taps.data(), tmp16.data(), C, dtype);
+                bp.wtc = slab.put(tmp16.data(), tmp16.size() * 2);
+            }
             PUT_F32(bp.bdw, bn + "conv_dw.bias", C);
             PUT_F32(bp.lnw, bn + "norm.weight", C);
             PUT_F32(bp.lnb, bn + "norm.bias", C);
@@ -513,6 +562,10 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             bp.w1 = base + reinterpret_cast<size_t>(bp.w1);
             bp.w2 = base + reinterpret_cast<size_t>(bp.w2);
             bp.wdw16 = base + reinterpret_cast<size_t>(bp.wdw16);
+            if (C % 64 == 0) {
+                bp.wtc = base + reinterpret_cast<size_t>(bp.wtc);
+                if (int rc = make_wtc_map(&bp.wtc_map, dtype, bp.wtc, C)) return rc;
+            }
             {
                 const uint64_t dims16[2] = {(uint64_t)C, 49};
                 const uint64_t strides16[1] = {(uint64_t)C * 2};
@@ -561,7 +614,7 @@ extern "C" int svb_model_info(const svb_model* m, int32_t out[10]) {
 namespace svb {
 
 struct WsLayout {
-    size_t x, a, h, stat, grn_part, grn_scale, total;
+    size_t x, a, h, stat, stat_part, grn_part, grn_scale, total;
 };
 static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     // stage 0 is the largest for every buffer (tokens/4, channels*2 per stage)
@@ -573,6 +626,8 @@ static WsLayout ws_layout(const svb_model* m, int nb, int H, int W) {
     L.a = o; o += align_up(t0 * c0 * 2, 1024);
     L.h = o; o += align_up(t0 * c0 * 4 * 2, 1024);
     L.stat = o; o += align_up(t0 * 8, 1024);  // (rstd, -mu rstd) per token: the folded LayerNorm of the current block
+    // dwconv_rawtc_kernel's per-chunk partial (sum, sum of squares) [token][C / 64] (tokens x chunks is largest in stage 0)
+    L.stat_part = o; o += align_up(t0 * 8 * std::max<size_t>(1, c0 / 64), 1024);
     L.grn_part = L.grn_scale = o;
     if (m->v2) {  // partial sums of squares [nb][ceil(tokens / GRN_ROWS)][4C] and scales [nb][4C]: the largest stage of each
         size_t part = 0, scale = 0;
@@ -622,6 +677,10 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
             if (int rc = encode_tmap(&p->xtc_map[s], tmap_dtype(m->dtype), 4, ws + L.x, dims, strides, box,
                                      CU_TENSOR_MAP_SWIZZLE_128B))
                 return rc;
+        }
+        p->tc2[s] = m->ln_fold ? dw_tc2_mode(m->dtype, (int)C, h, w) : 0;
+        if (p->tc2[s]) {
+            if (int rc = make_xtc2_map(&p->xtc2_map[s], m->dtype, ws + L.x, (int)C, nb, h, w, p->tc2[s])) return rc;
         }
         if (int rc = make_operand_map(&p->a_map[s], m->dtype, ws + L.a, M, C, 128)) return rc;
         if (int rc = make_operand_map(&p->h_map[s], m->dtype, ws + L.h, M, 4 * C, 128)) return rc;
@@ -847,6 +906,51 @@ static int sub_batch_images(int s, int nb, int tokens, int C) {
     if (sub < 1) sub = 1;
     while (sub < nb && ((long long)sub * tokens) % 256 != 0) ++sub;  // whole 256-row tile pairs
     return sub < nb ? sub : nb;
+}
+
+template <typename T>
+static int launch_dwconv_rawtc(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, float2* stat_part, int C, int nb, int H,
+                               int W, int mode, cudaStream_t st, int b0 = 0) {
+    // rowstat / stat_part address the micro-batch's first token; images [b0, b0 + nb) are written
+    using Cfg = DwTc2Cfg;
+    auto kern = dwconv_rawtc_kernel<T>;
+    static bool attr_done[MAX_DEVICES] = {};
+    const int dslot = current_device_slot();
+    if (!attr_done[dslot]) {
+        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        attr_done[dslot] = true;
+    }
+    const int NCH = C / 64;
+    const int rowpx = mode == 1 ? W : 32, nwin = mode == 1 ? 1 : ceil_div(W, 26);
+    const int units_y = ceil_div(H, mode == 1 ? 256 / W : 8);
+    const int num_units = nb * nwin * units_y;
+    int per_chunk = num_sms() / NCH;
+    if (per_chunk > num_units) per_chunk = num_units;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(NCH * per_chunk));
+    cfg.blockDim = dim3(Cfg::NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wtc_map, (const float*)bp.bdw, static_cast<T*>(out), stat_part, C, H, W, rowpx, nwin, units_y,
+                                   num_units, b0));
+    count_launch();
+    {
+        const long long t0 = (long long)b0 * H * W, tokens = (long long)nb * H * W;
+        cudaLaunchConfig_t fc{};
+        fc.gridDim = dim3((unsigned)ceil_div<long long>(tokens, 256));
+        fc.blockDim = dim3(256);
+        fc.stream = st;
+        fc.attrs = attr;
+        fc.numAttrs = pdl_enabled() ? 1 : 0;
+        SVB_CUDA_OK(cudaLaunchKernelEx(&fc, ln_stat_finalize_kernel, (const float2*)(stat_part + t0 * NCH), rowstat + t0, tokens, NCH, 1.0f / (float)C));
+        count_launch();
+    }
+    return SVB_OK;
 }
 
 // rows per tile: 8, or 4 when 8-row tiles would leave most of the 2 x 148 CTA slots empty (the last stage: 16 x 16 tokens per image)
@@ -1079,7 +1183,12 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                 const int ns = (nb - b0) < sub ? (nb - b0) : sub;
                 const int m0 = b0 * tok, m1 = (b0 + ns) * tok;
                 for (const BlockParams& bp : m->blocks[s]) {
-                    RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
+                    if (plan->tc2[s]) {
+                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, reinterpret_cast<float2*>(ws + L.stat_part), C, ns, h, w,
+                                                                     plan->tc2[s], st, b0));
+                    } else {
+                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
+                    }
                     RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, m1, 4 * C, C,
                                                     GEMM_LNGELU, st, false, rowstat, m0));
                     if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd + (size_t)m0 * 4 * C, ns, tok, 4 * C, bp.grn_w, bp.grn_b,
@@ -1338,6 +1447,32 @@ extern "C" int svb_dwconv_raw(const void* d_x, const float* d_taps, const float*
     float2* rs = reinterpret_cast<float2*>(d_rowstat);
     if (dtype == SVB_FP16) return launch_dwconv_raw<__half>(x_map, x4_map, bp, d_out, rs, C, B, H, W, st);
     return launch_dwconv_raw<__nv_bfloat16>(x_map, x4_map, bp, d_out, rs, C, B, H, W, st);
+}
+
+extern "C" int svb_dwconv_tc_pack(const float* h_taps, void* h_wtc, int C, int dtype) {
+    SVB_REQUIRE(h_taps && h_wtc && C > 0 && C % 64 == 0, SVB_ERR_INVALID_ARG, "dwconv_tc_pack: C (%d) must be a positive multiple of 64", C);
+    SVB_REQUIRE(dtype == SVB_BF16 || dtype == SVB_FP16, SVB_ERR_INVALID_ARG, "dwconv_tc_pack: dtype %d", dtype);
+    pack_wtc(h_taps, static_cast<uint16_t*>(h_wtc), C, dtype);
+    return SVB_OK;
+}
+
+extern "C" int svb_dwconv_raw_tc(const void* d_x, const void* d_wtc, const float* d_bias, void* d_out, float* d_rowstat, float* d_stat_part,
+                                 int B, int H, int W, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_x && d_wtc && d_bias && d_out && d_rowstat && d_stat_part && B > 0 && H > 0 && W > 0, SVB_ERR_INVALID_ARG,
+                "dwconv_raw_tc: bad arguments");
+    SVB_REQUIRE(C % 64 == 0 && C / 64 <= num_sms(), SVB_ERR_UNSUPPORTED_MODEL, "dwconv_raw_tc: C (%d) must be a multiple of 64", C);
+    const int mode = (W == 8 || W == 16 || W == 32) ? 1 : 2;
+    BlockParams bp{};
+    bp.bdw = const_cast<float*>(d_bias);
+    if (int rc = make_wtc_map(&bp.wtc_map, dtype, d_wtc, C)) return rc;
+    CUtensorMap x_map;
+    if (int rc = make_xtc2_map(&x_map, dtype, d_x, C, B, H, W, mode)) return rc;
+    float2* rs = reinterpret_cast<float2*>(d_rowstat);
+    float2* sp = reinterpret_cast<float2*>(d_stat_part);
+    if (dtype == SVB_FP16) return launch_dwconv_rawtc<__half>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st);
+    return launch_dwconv_rawtc<__nv_bfloat16>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st);
 }
 
 extern "C" int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,

@@ -1424,6 +1424,344 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     if (warp == 1) tmem_dealloc<2>(tmem_base, Cfg::TMEM_COLS);
 }
 
+// ============================================================================ depthwise 7x7 (raw + statistics) on the tensor cores
+// dwconv_raw_kernel's contract (raw 16-bit convolution = the fc1 A operand, (rstd, -mu rstd) per token) with the 49 taps on the
+// tensor pipe.  The first tensor-core version (dwconv_ln_tc_kernel below) issued one MMA per TAP and was bound by the operand
+// feed: each 128 x 16 activation slice was re-read from shared memory 49 times.  Here a slice is read SEVEN times:
+//   * the seven ROWS of the stencil (dy) are seven accumulating MMAs over row-shifted views of one swizzled tile (a row of 32
+//     lanes is 4 KB, so every view starts on a 1024-byte swizzle atom);
+//   * the seven COLUMNS (dx) sit side by side in the N dimension: B_dy[k = c, n = (dx, c')] = w[dy][dx][c] (c == c'), 0 otherwise,
+//     an M = 128, N = 7 x 16 = 112, K = 16 MMA per 16 channels, so TMEM lane p (a SOURCE pixel) ends up holding
+//         D[p][dx][c] = sum_dy in[y(p) + dy - 3, x(p), c] * w[dy][dx][c]
+//   * the epilogue adds the seven column blocks across lanes: out[y, x, c] = sum_dx D[(y, x + dx - 3)][dx][c], six warp shuffles
+//     per value (a warp = 32 consecutive pixels of one image row, or 32 / W whole rows when W <= 32; `shfl` segments of W lanes
+//     give the zero padding at the row ends for free).  13 instructions per output instead of 49 FMAs.
+// Arithmetic: activations and taps are exact 16-bit operands, products are exact in fp32, accumulation is fp32 (tensor core over
+// dy, FFMA over dx): the only difference from dwconv_raw_kernel is the taps' rounding to 16 bits (scripts/emulate_precision.py
+// scheme tc_dw: 0.119 -> 0.143 px for fp16 trained-like weights; 0.5 px gate).
+// Tiling.  A CTA owns ONE 64-channel chunk for the whole launch (its 7 B matrices, 98 KB, are loaded once) and walks "units" of
+// 256 source lanes = two M tiles:
+//   mode A (W in {8, 16, 32}):  a unit = 256 / W whole image rows; no x halo is needed (neighbours beyond the row are padding)
+//   mode B (any other W):       a unit = 8 rows of one 32-lane window [xs, xs + 32), xs = -3 + 26 i; lanes 3..28 produce outputs
+// plus 6 halo rows above / below (TMA zero fill outside the image).  TMEM: one 112-column accumulator per 16-channel group (4 x
+// 128 columns); the MMA warp runs up to a whole M tile ahead of the four epilogue warpgroups.
+//   warp 0        TMA producer          warp 1      MMA issuer (one lane), TMEM allocator
+//   warps 2..17   epilogue: warpgroup g = (warp - 2) / 4 drains group g (channels 16 g .. 16 g + 15 of the chunk)
+// Statistics: the four warpgroups' (sum, sum of squares) of a pixel meet in shared memory; warpgroup 3 writes the chunk's partial
+// to stat_part[token][k] and ln_stat_finalize_kernel adds a token's parts -- deterministic, no atomics.
+struct DwTc2Cfg {
+    static constexpr int CC = 64, NB = 112;
+    static constexpr int B_BYTES = NB * 128;             // one dy: 112 rows (dx, c') x 64 k
+    static constexpr int B_TOTAL = 7 * B_BYTES;          // 98 KB
+    static constexpr int A_STAGE = (256 + 6 * 32) * 128; // 56 KB: two M tiles + 6 halo lane-rows (mode A with W < 32 uses less)
+    static constexpr int A_STAGES = 2;
+    static constexpr int STAT_BYTES = 2 * 3 * 128 * 8;   // [tile parity][warpgroup 0..2][pixel] (sum, sum of squares)
+    static constexpr int EPI_WARPS = 16;
+    static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int SMEM_BYTES = B_TOTAL + A_STAGES * A_STAGE + STAT_BYTES + 256 + 1024;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(B_BYTES % 1024 == 0 && A_STAGE % 1024 == 0, "swizzle atoms");
+    static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+};
+
+// acc += mask * (value of lane + DELTA of this lane's `width`-lane segment).  mask = 1 when that lane exists in the segment, else 0
+// (the shuffle then returns this lane's own finite value); a mask multiply instead of the shuffle's predicate keeps the shuffles
+// free of each other, so the 16 channels' shuffles are in flight together.
+template <int DELTA>
+__device__ __forceinline__ void shfl_add(float& acc, float v, float mask, int width) {
+    if (DELTA == 0) acc += v;
+    else if (DELTA > 0) acc = fmaf(__shfl_down_sync(0xffffffffu, v, DELTA, width), mask, acc);
+    else acc = fmaf(__shfl_up_sync(0xffffffffu, v, -DELTA, width), mask, acc);
+}
+
+// Packed variant for fp16 models: the two channels of a pair cross lanes as ONE 32-bit half2 (half the shuffles -- the LSU / MIO
+// path the shuffles share with the stores is what bounds the epilogue), and the mixed-precision FMA (FHFMA: fp16 x fp16 + fp32)
+// applies the mask and widens in one instruction per value.  The partial sums that travel are rounded to fp16 (the centre column
+// and the accumulation stay fp32): scripts/emulate_precision.py scheme tc_dw_h, 0.137 px against 0.143 px un-rounded.
+template <int DELTA>
+__device__ __forceinline__ void shfl_add_h2(float& a0, float& a1, float v0, float v1, uint32_t mask_h2, int width) {
+    uint32_t h;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(v1), "f"(v0));
+    const uint32_t t = DELTA > 0 ? __shfl_down_sync(0xffffffffu, h, DELTA, width) : __shfl_up_sync(0xffffffffu, h, -DELTA, width);
+    asm("{\n\t.reg .f16 tl, th, ml, mh;\n\tmov.b32 {tl, th}, %2;\n\tmov.b32 {ml, mh}, %3;\n\t"
+        "fma.rn.f32.f16 %0, tl, ml, %0;\n\tfma.rn.f32.f16 %1, th, mh, %1;\n\t}\n"
+        : "+f"(a0), "+f"(a1)
+        : "r"(t), "r"(mask_h2));
+}
+__device__ __forceinline__ void stg256(void* p, const uint32_t (&o)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]),
+                 "r"(o[5]), "r"(o[6]), "r"(o[7])
+                 : "memory");
+}
+
+// tcgen05.mma / commit issued by the lane whose predicate is set, with NO branch around them: the MMA warp of
+// dwconv_rawtc_kernel runs warp-uniform code, so that the descriptors stay in uniform registers.  (With the usual
+// `if (lane == 0) { ... }` around the whole loop every operand went through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence:
+// ~130 clk per MMA against 56 clk of tensor work.)
+__device__ __forceinline__ void tc_mma_f16_if(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t lead, uint64_t* bar) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(lead)
+                 : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(DwTc2Cfg::NUM_THREADS, 1)
+dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map,
+                    const float* __restrict__ bdw, T* __restrict__ out, float2* __restrict__ stat_part, int C, int H, int W,
+                    int rowpx /* lanes per image row inside a unit: W (mode A) or 32 (mode B) */,
+                    int nwin /* windows per image row: 1 in mode A */, int units_y, int num_units, int b0) {
+    using Cfg = DwTc2Cfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sB = smem;
+    uint8_t* sA = smem + Cfg::B_TOTAL;
+    float2* sStat = reinterpret_cast<float2*>(sA + Cfg::A_STAGES * Cfg::A_STAGE);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sStat) + Cfg::STAT_BYTES);
+    uint64_t* bfull = bars;           // the chunk's B matrices landed
+    uint64_t* afull = bars + 1;       // [2]
+    uint64_t* aempty = afull + 2;     // [2]
+    uint64_t* tfull = aempty + 2;     // [4] accumulator of a 16-channel group complete
+    uint64_t* tempty = tfull + 4;     // [4] ... read out by the 4 warps of its warpgroup
+    uint64_t* sfull = tempty + 4;     // [2] warpgroups 0..2 have written their statistics of an M tile
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sfull + 2);
+
+    // the warp index through a shuffle: provably warp-uniform, so the role branches below are uniform branches and the MMA warp's
+    // address arithmetic can live in uniform registers
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int NCH = C / Cfg::CC;
+    const int k = (int)blockIdx.x % NCH;                   // this CTA's channel chunk
+    const int u0 = (int)blockIdx.x / NCH, ustep = (int)gridDim.x / NCH;
+    const bool mode_b = nwin > 1 || rowpx != W;
+    const int rows_unit = mode_b ? 8 : 256 / W;            // output rows per unit
+    const int units_img = nwin * units_y;
+    const uint32_t a_bytes = (uint32_t)(256 + 6 * rowpx) * 128u;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&x_map);
+        tma_prefetch_desc(&b_map);
+        mbar_init(bfull, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); mbar_init(&sfull[s], 12); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 1) tmem_alloc<1>(tmem_ptr, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
+    pdl_launch_dependents();
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            // the taps do not depend on the previous kernel: they are fetched while it is still running
+            mbar_expect_tx(bfull, Cfg::B_TOTAL);
+            for (int dy = 0; dy < 7; ++dy) tma_load_2d(sB + dy * Cfg::B_BYTES, &b_map, bfull, 0, (k * 7 + dy) * Cfg::NB);
+            pdl_wait();
+            int it = 0;
+            for (int u = u0; u < num_units; u += ustep, ++it) {
+                const int stage = it & 1;
+                if (it >= 2) mbar_wait(&aempty[stage], ((it >> 1) - 1) & 1);
+                const int b = u / units_img, r = u - b * units_img;
+                const int wi = r % nwin, uy = r / nwin;
+                const int xs = mode_b ? 26 * wi - 3 : 0;
+                mbar_expect_tx(&afull[stage], a_bytes);
+                tma_load_4d(sA + stage * Cfg::A_STAGE, &x_map, &afull[stage], k * Cfg::CC, xs, uy * rows_unit - 3, b0 + b);
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer (the whole warp, one elected lane issues)
+        {
+            constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(Cfg::NB >> 3) << 17) |
+                                       ((uint32_t)(128 >> 4) << 24);
+            const uint32_t lead = elect_one() ? 1u : 0u;
+            mbar_wait(bfull, 0);
+            // descriptors differ only in the 14-bit start-address field (bytes >> 4): + 2 per 16-channel group (32 B inside the
+            // swizzle atom), + rowpx * 8 per stencil row, + 1024 per M tile, + B_BYTES / 16 per B matrix
+            const uint64_t b0 = make_sw128_kmajor_desc(smem_u32(sB));
+            const uint64_t a00 = make_sw128_kmajor_desc(smem_u32(sA));
+            const uint64_t a_dy = (uint64_t)(rowpx * 8);
+            int it = 0;
+            uint32_t tcount = 0;  // M tiles issued so far: each uses every TMEM accumulator once
+            for (int u = u0; u < num_units; u += ustep, ++it) {
+                const int stage = it & 1;
+                mbar_wait(&afull[stage], (it >> 1) & 1);
+                tc_fence_after();
+                const uint64_t a0 = a00 + (uint64_t)(stage * (Cfg::A_STAGE >> 4));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt, ++tcount) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        // one accumulator after the other: filling two or four in turn (so that an MMA need not wait for its
+                        // predecessor on the same accumulator) was measured slower -- 305 / 316 / 373 us at C = 128 -- because
+                        // the epilogue of group g then starts later
+                        mbar_wait(&tempty[g], (tcount & 1) ^ 1);
+                        tc_fence_after();
+#pragma unroll
+                        for (int dy = 0; dy < 7; ++dy) {
+                            const uint64_t adesc = a0 + (uint64_t)(mt * 1024 + 2 * g) + (uint64_t)dy * a_dy;
+                            const uint64_t bdesc = b0 + (uint64_t)(dy * (Cfg::B_BYTES >> 4) + 2 * g);
+                            tc_mma_f16_if(lead, tmem_base + (uint32_t)(g * 128), adesc, bdesc, idesc, dy != 0 ? 1u : 0u);
+                        }
+                        tc_commit_if(lead, &tfull[g]);
+                    }
+                }
+                tc_commit_if(lead, &aempty[stage]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue
+        const int g = (warp - 2) >> 2;   // 16-channel group = TMEM accumulator
+        const int q = warp & 3;          // TMEM lane quarter
+        const int px = q * 32 + lane;    // pixel (TMEM lane) of the M tile
+        const int width = mode_b ? 32 : W;
+        constexpr bool PACKED = sizeof(T) == 2 && UmmaFmt<T>::v == 0;  // fp16: packed shuffles (see shfl_add_h2); bf16: fp32 shuffles
+        float mk[7];  // mk[dx]: does source lane + dx - 3 lie in this lane's image row (mode A) / window (mode B: its outputs are unused if not)
+        uint32_t mkh[7];
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+            const int sl = (lane & (width - 1)) + dx - 3;
+            mk[dx] = (sl >= 0 && sl < width) ? 1.0f : 0.0f;
+            mkh[dx] = (sl >= 0 && sl < width) ? 0x3C003C00u : 0u;
+        }
+        const int ch0 = k * Cfg::CC + g * 16;
+        float bias[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bdw + ch0) + i);
+            bias[4 * i] = bb.x; bias[4 * i + 1] = bb.y; bias[4 * i + 2] = bb.z; bias[4 * i + 3] = bb.w;
+        }
+        const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 128);
+        uint32_t tcount = 0;
+        pdl_wait();
+        for (int u = u0; u < num_units; u += ustep) {
+            const int b = u / units_img, r = u - b * units_img;
+            const int wi = r % nwin, uy = r / nwin;
+            const int y0 = uy * rows_unit;
+            for (int mt = 0; mt < 2; ++mt, ++tcount) {
+                int x, y;
+                bool valid;
+                if (mode_b) {
+                    y = y0 + mt * 4 + q;
+                    x = 26 * wi - 3 + lane;
+                    valid = lane >= 3 && lane <= 28 && x < W && y < H;
+                } else {
+                    const int p = mt * 128 + px;
+                    y = y0 + p / W;
+                    x = p % W;
+                    valid = y < H;
+                }
+                const size_t tok = ((size_t)(b0 + b) * H + y) * W + x;
+                mbar_wait(&tfull[g], tcount & 1);
+                tc_fence_after();
+                float acc[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) acc[c] = bias[c];
+                float v[2][16];
+                TmemLd<16>::ld(tbase, v[0]);
+#pragma unroll
+                for (int dx = 0; dx < 7; ++dx) {
+                    tmem_ld_wait();
+                    if (dx < 6) TmemLd<16>::ld(tbase + (uint32_t)((dx + 1) * 16), v[(dx + 1) & 1]);
+                    if (PACKED && dx != 3) {
+#pragma unroll
+                        for (int c = 0; c < 16; c += 2) {
+                            switch (dx) {
+                                case 0: shfl_add_h2<-3>(acc[c], acc[c + 1], v[0][c], v[0][c + 1], mkh[0], width); break;
+                                case 1: shfl_add_h2<-2>(acc[c], acc[c + 1], v[1][c], v[1][c + 1], mkh[1], width); break;
+                                case 2: shfl_add_h2<-1>(acc[c], acc[c + 1], v[0][c], v[0][c + 1], mkh[2], width); break;
+                                case 4: shfl_add_h2<1>(acc[c], acc[c + 1], v[0][c], v[0][c + 1], mkh[4], width); break;
+                                case 5: shfl_add_h2<2>(acc[c], acc[c + 1], v[1][c], v[1][c + 1], mkh[5], width); break;
+                                default: shfl_add_h2<3>(acc[c], acc[c + 1], v[0][c], v[0][c + 1], mkh[6], width); break;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            switch (dx) {
+                                case 0: shfl_add<-3>(acc[c], v[0][c], mk[0], width); break;
+                                case 1: shfl_add<-2>(acc[c], v[1][c], mk[1], width); break;
+                                case 2: shfl_add<-1>(acc[c], v[0][c], mk[2], width); break;
+                                case 3: shfl_add<0>(acc[c], v[1][c], mk[3], width); break;
+                                case 4: shfl_add<1>(acc[c], v[0][c], mk[4], width); break;
+                                case 5: shfl_add<2>(acc[c], v[1][c], mk[5], width); break;
+                                default: shfl_add<3>(acc[c], v[0][c], mk[6], width); break;
+                            }
+                        }
+                    }
+                }
+                // the accumulator is in registers: hand it back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[g]);
+                float s = 0.f, sq = 0.f;
+                uint32_t o[8];
+#pragma unroll
+                for (int c = 0; c < 16; c += 2) {
+                    s += acc[c] + acc[c + 1];
+                    sq = fmaf(acc[c], acc[c], sq);
+                    sq = fmaf(acc[c + 1], acc[c + 1], sq);
+                    o[c / 2] = Cvt<T>::pack2(acc[c], acc[c + 1]);
+                }
+                if (valid) {
+                    stg256(out + tok * (size_t)C + ch0, o);  // one 32-byte store: half the LSU wavefronts of two 16-byte ones
+                }
+                // ---- token statistics
+                float2* st = sStat + (tcount & 1) * (3 * 128);
+                if (g < 3) {
+                    st[g * 128 + px] = make_float2(s, sq);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sfull[tcount & 1]);
+                } else {
+                    mbar_wait(&sfull[tcount & 1], (tcount >> 1) & 1);
+                    const float2 p0 = st[px], p1 = st[128 + px], p2 = st[256 + px];
+                    if (valid) stat_part[tok * (size_t)NCH + k] = make_float2(((p0.x + p1.x) + p2.x) + s, ((p0.y + p1.y) + p2.y) + sq);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+}
+
+// Token statistics of dwconv_rawtc_kernel: parts [tokens][NCH] (sum, sum of squares) -> rowstat[token] = (rstd, -mu rstd), parts
+// added in index order.  A separate launch (2-3 us under PDL): finishing them inside fc1's epilogue cost that kernel 15 us at K = 512
+// (its epilogue warps have no registers or issue slots to spare), finishing them inside the depthwise kernel needs a grid-wide
+// hand-over (fence + atomic per tile on an epilogue warpgroup's path: 74 -> 129 us).
+__global__ void __launch_bounds__(256) ln_stat_finalize_kernel(const float2* __restrict__ part, float2* __restrict__ rowstat, long long tokens,
+                                                               int nch, float inv_c) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= tokens) return;
+    const float2* p = part + t * nch;
+    float sm = 0.f, sq = 0.f;
+    if ((nch & 1) == 0) {
+        const float4* p4 = reinterpret_cast<const float4*>(p);
+        for (int i0 = 0; i0 < nch / 2; i0 += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[i] = i0 + i < nch / 2 ? __ldg(p4 + i0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { sm += v[i].x; sq += v[i].y; sm += v[i].z; sq += v[i].w; }
+        }
+    } else {
+        for (int i = 0; i < nch; ++i) { const float2 v = __ldg(p + i); sm += v.x; sq += v.y; }
+    }
+    const float mu = sm * inv_c;
+    const float var = fmaxf(fmaf(-mu, mu, sq * inv_c), 0.0f);
+    const float rstd = 1.0f / sqrtf(var + LN_EPS_BACKBONE);
+    rowstat[t] = make_float2(rstd, -mu * rstd);
+}
+
 // ============================================================================ depthwise 7x7 + LayerNorm on the tensor cores
 // The 49-tap depthwise convolution is run as tcgen05 MMAs over SHIFTED VIEWS of one shared-memory halo tile:
 // the (zero-padded) image rows of a 64-channel chunk sit in shared memory as 128-byte pixel rows (TMA,

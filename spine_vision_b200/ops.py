@@ -483,6 +483,32 @@ def dwconv_raw(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, out: tor
     return out, stat
 
 
+def dwconv_tc_pack(taps: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """taps fp32 [49, C] -> the B operands of ``dwconv_raw_tc`` ([C/64, 7, 112, 64] 16-bit of ``dtype``, on the taps' device);
+    packed on the host by ``svb_dwconv_tc_pack`` (what ``svb_model_create`` does once per block)."""
+    Cc = taps.shape[1]
+    host = taps.detach().to("cpu", torch.float32).contiguous()
+    out = torch.empty((Cc // 64, 7, 112, 64), dtype=dtype)
+    _lib.check(_lib.load().svb_dwconv_tc_pack(host.data_ptr(), out.data_ptr(), Cc, _dt(out)))
+    return out.to(taps.device)
+
+
+@_on_device
+def dwconv_raw_tc(x: torch.Tensor, wtc: torch.Tensor, bias: torch.Tensor, out: torch.Tensor | None = None, part: torch.Tensor | None = None):
+    """``dwconv_raw`` on the tensor cores (``svb_dwconv_raw_tc``): x NHWC 16-bit [B,H,W,C], wtc from ``dwconv_tc_pack`` ->
+    (raw convolution [B,H,W,C] 16-bit, row statistics float32 [B*H*W, 2] = (rstd, -mean * rstd)), as ``dwconv_raw`` returns.
+    ``part`` (scratch, float32 [B*H*W, C/64, 2]) holds the per-chunk partial sums the statistics are added up from."""
+    B, H, W, Cc = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    if part is None:
+        part = torch.empty((B * H * W, Cc // 64, 2), dtype=torch.float32, device=x.device)
+    stat = torch.empty((B * H * W, 2), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().svb_dwconv_raw_tc(x.data_ptr(), wtc.data_ptr(), bias.data_ptr(), out.data_ptr(), stat.data_ptr(), part.data_ptr(),
+                                             B, H, W, Cc, _dt(x), _lib.current_stream()))
+    return out, stat
+
+
 @_on_device
 def dwconv_ln_tc(x: torch.Tensor, taps: torch.Tensor, bias: torch.Tensor, lnw: torch.Tensor, lnb: torch.Tensor):
     """Same operator as ``dwconv_ln`` on the tensor cores (taps are rounded to the activation dtype)."""

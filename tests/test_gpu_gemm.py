@@ -139,6 +139,60 @@ def test_dwconv_raw_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
     assert int((err > tol).sum()) == 0, f"{int((err > tol).sum())} beyond tolerance, max err {err.max().item():.4g}"
 
 
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("B,H,W,C", [(3, 32, 32, 512), (2, 16, 16, 1024), (5, 32, 32, 128), (1, 8, 8, 64), (2, 20, 32, 192), (3, 12, 16, 64),
+                                     (2, 64, 64, 256), (1, 128, 128, 128), (2, 37, 21, 128), (1, 15, 23, 1024), (1, 9, 13, 2048), (2, 33, 40, 64),
+                                     (1, 7, 5, 384), (40, 32, 32, 512)])
+def test_dwconv_raw_tc_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
+    """``svb_dwconv_raw_tc`` (the depthwise stencil on the tensor cores: mode A for W in {8, 16, 32}, mode B windows otherwise)
+    + the fc1 GEMM with the folded LayerNorm: (a) the raw output is the convolution WITH THE TAPS ROUNDED TO 16 BITS (the
+    kernel's operands; activation x tap products are exact, accumulation fp32) to output rounding; (b) the statistics (per-chunk
+    partial sums added up by the finalize launch) are those of the fp32 convolution; (c) the composite equals
+    GELU(fc1(LayerNorm(conv))) of plain PyTorch within the same budget as the FP32-pipe pair; (d) a second launch gives identical
+    bits (fixed summation order, no atomics)."""
+    g = torch.Generator().manual_seed(B + H + W + C + 1)
+    x = torch.randn(B, H, W, C, generator=g).to(DT[dtype])
+    wt = torch.randn(C, 1, 7, 7, generator=g) * 0.1
+    bias = torch.randn(C, generator=g) * 0.1 + 0.3
+    lnw = 1 + 0.2 * torch.randn(C, generator=g)
+    lnb = 0.1 * torch.randn(C, generator=g)
+    N = 4 * C if C <= 512 else 512
+    w1 = torch.randn(N, C, generator=g) / C ** 0.5
+    b1 = 0.1 * torch.randn(N, generator=g)
+    wt16 = wt.to(DT[dtype]).float()
+    y = F.conv2d(x.float().permute(0, 3, 1, 2), wt16, bias, padding=3, groups=C).permute(0, 2, 3, 1)
+    taps = wt.reshape(C, 49).t().contiguous()
+    wtc = ops.dwconv_tc_pack(taps.to(dev()), DT[dtype])
+    xd, bd = x.to(dev()), bias.to(dev())
+    raw, stat = ops.dwconv_raw_tc(xd, wtc, bd)
+    torch.cuda.synchronize()
+    rawf = raw.float().cpu()
+    eps16 = 2.0 ** -8 if dtype == "bf16" else 2.0 ** -11
+    # fp16: the six off-centre stencil columns' partial sums cross lanes as fp16 (packed shuffles), so the bound is their half-ulp
+    # roundings (|partial| <= sum |x| |w| of one column) on top of the output rounding; bf16 keeps fp32 shuffles
+    slack = 1.01 if dtype == "bf16" else 3.0
+    bad = (rawf - y).abs() > eps16 * (y.abs() + 1.0) * slack
+    assert int(bad.sum()) == 0, f"raw conv: {int(bad.sum())} off, max err {(rawf - y).abs().max().item():.4g} at {bad.nonzero()[:4].tolist()}"
+    assert float((rawf - y).abs().mean()) < 0.6 * eps16 * float(y.abs().mean() + 1.0)
+    mu = y.mean(-1)
+    var = y.var(-1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-6)
+    st = stat.cpu().view(B, H, W, 2)
+    assert torch.allclose(st[..., 0], rstd, rtol=2e-4, atol=1e-6), (st[..., 0] - rstd).abs().max()
+    assert torch.allclose(st[..., 1], -mu * rstd, rtol=2e-4, atol=2e-4), (st[..., 1] + mu * rstd).abs().max()
+    wg = (w1 * lnw[None, :]).to(DT[dtype])
+    s_n = wg.float().sum(1)
+    t_n = (w1.double() @ lnb.double()).float() + b1
+    got = ops.gemm(raw.view(-1, C), wg.to(dev()), t_n.to(dev()), 3, resid=stat, gamma=s_n.to(dev())).float().cpu()
+    want = F.gelu(F.layer_norm(y, (C,), lnw, lnb, 1e-6).reshape(-1, C) @ w1.t() + b1)
+    err = (got - want).abs()
+    tol = 4 * eps16 * (want.abs() + 1.0)
+    assert int((err > tol).sum()) == 0, f"{int((err > tol).sum())} beyond tolerance, max err {err.max().item():.4g}"
+    r2, s2 = ops.dwconv_raw_tc(xd, wtc, bd)
+    torch.cuda.synchronize()
+    assert torch.equal(r2, raw) and torch.equal(s2, stat)
+
+
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])
 @pytest.mark.parametrize("C0,C", [(192, 192), (192, 384), (256, 768), (96, 96)])
 def test_stem_patchify_other_widths(dtype, C0, C):
