@@ -359,7 +359,11 @@ def run_b200(args):
                 mm, kk = B * hh * ww, 4 * model.engine.dims[si - 1]
                 gemm_bytes += 2.0 * (mm * kk + cd * kk + mm * cd)
             mm = B * hh * ww
-            gemm_bytes += nd * 2.0 * ((mm * cd + 4 * cd * cd + mm * 4 * cd) + (mm * 4 * cd + 4 * cd * cd + 2 * mm * cd))
+            if cd in (128, 256) and os.environ.get("SVB_MLP_FUSED", "1") != "0":
+                # mlp_fused_kernel: the hidden activation never leaves the SM (A + W1 + W2 + residual in + out)
+                gemm_bytes += nd * 2.0 * (mm * cd + 8 * cd * cd + 2 * mm * cd)
+            else:
+                gemm_bytes += nd * 2.0 * ((mm * cd + 4 * cd * cd + mm * 4 * cd) + (mm * 4 * cd + 4 * cd * cd + 2 * mm * cd))
         dw_ms = times.get("dwconv_ln", 0.0) / args.steps
         dw_flops = 2.0 * 49 * B * sum(d * (IMAGE_SIZE[0] >> (2 + i)) * (IMAGE_SIZE[1] >> (2 + i)) * n
                                       for i, (d, n) in enumerate(zip(model.engine.dims, model.engine.depths)))
@@ -388,7 +392,8 @@ def run_b200(args):
                            "of the previous chunk; D2H on a third stream; batch k+1 is started before batch k is collected (two output slots); "
                            "index tables (offsets, shapes, crop deltas: 44 bytes per series) are uploaded once per batch geometry and reused"},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise/downsample GEMMs, all launches of one step)", "bound": "tensor",
+            "roofline": {"kernel": "gemm_kernel + mlp_fused_kernel (tcgen05 pointwise / downsample GEMMs and the fused fc1-GELU-fc2 of stages 0-1, "
+                                   "all launches of one step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
                          "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{traffic_file} (ncu --set full, per-shape dram bytes x launches)",
                          "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
@@ -397,11 +402,15 @@ def run_b200(args):
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
                                    "k3_crop_resample": k3_ms / args.steps, "k0_midplane_resample (e2e path only)": k0_ms / args.steps,
                                    "k0_k1_fused (e2e path only)": k01_ms / args.steps},
-            "fp32_kernels": {"dwconv_ln": {"flops_per_step": dw_flops, "achieved_tflops": dw_flops / (dw_ms * 1e-3) / 1e12 if dw_ms else None,
-                                           "fp32_peak_tflops_nominal": 72.0, "hbm_bytes_per_step": dw_bytes,
-                                           "achieved_gbs": dw_gbs, "hbm_peak_gbs": hbm, "frac_of_hbm": dw_gbs / hbm if dw_gbs else None,
-                                           "frac_of_fp32_nominal": dw_flops / (dw_ms * 1e-3) / 1e12 / 72.0 if dw_ms else None,
-                                           "note": "FP32-pipe bound (49 FMA per output): FFMA2 issues at ~2.4 clk on B200, measured ceiling of the loop ~78 of 128 FMA/clk/SM (scripts/ubench/convloop2.cu)"}},
+            "depthwise_kernel": {
+                "kernel": "dwconv_rawtc_kernel + ln_stat_finalize_kernel (fp16: the 7x7 stencil as row-shifted tcgen05 MMAs, column sum by packed "
+                          "shuffles) | dwconv_raw_kernel (bf16: FP32 pipe)",
+                "ms_per_step": dw_ms, "useful_flops_per_step": dw_flops, "achieved_useful_tflops": dw_flops / (dw_ms * 1e-3) / 1e12 if dw_ms else None,
+                "tensor_flops_issued_per_step": dw_flops / 49 * 7 * 16 * 7 if args.dtype == "fp16" else 0.0,
+                "bound": "hbm (SURVEY 8d)", "hbm_bytes_per_step": dw_bytes, "achieved_gbs": dw_gbs, "hbm_peak_gbs": hbm,
+                "frac_of_hbm": dw_gbs / hbm if dw_gbs else None,
+                "note": "fp16: bound by the tensor core's shared-memory operand feed (7.5 KB per 128 x 112 x 16 MMA at ~87 B/clk) and the epilogue's "
+                        "TMEM drain, DESIGN.md section 4; the FP32-pipe kernel it replaces ran at 0.16 of HBM"},
             "hbm_kernels": {
                 "k1": {"bytes_per_step": k1_bytes, "achieved_gbs": k1_gbs, "peak_gbs": hbm, "frac": k1_gbs / hbm if k1_gbs else None},
                 "k3": {"bytes_per_step": k3_bytes, "achieved_gbs": k3_gbs, "peak_gbs": hbm, "frac": k3_gbs / hbm if k3_gbs else None},

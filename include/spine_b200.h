@@ -246,6 +246,10 @@ int svb_gemm(const void* d_a, const void* d_w, void* d_out, const void* d_resid,
  * b1 [4C], b2 [C], gamma [C] fp32.  C = 128 or 256 (Y + two hidden accumulators must fit the 512 TMEM columns). */
 int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b1, const void* d_w2, const float* d_b2,
                   const float* d_gamma, void* d_x, int M, int C, int dtype, void* stream);
+/* The same with the block's LayerNorm folded into fc1 (what the model runs at C = 128 / 256): d_a = the RAW depthwise output,
+ * d_w1g = r16(W1 diag(g)), d_t / d_s / d_rowstat as svb_gemm mode 3's d_bias / d_gamma / d_resid. */
+int svb_mlp_fused_ln(const void* d_a, const void* d_w1g, const float* d_t, const float* d_s, const float* d_rowstat, const void* d_w2,
+                     const float* d_b2, const float* d_gamma, void* d_x, int M, int C, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Standalone layer entries (unit tests / ncu captures of one kernel).  Same kernels the model runs.

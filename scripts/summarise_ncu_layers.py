@@ -42,11 +42,12 @@ def mb(r, k):  # ncu prints Mbyte / Gbyte depending on the run: normalise throug
     return col(r, k) * scale
 
 
-gemms = [r for r in data if "gemm_kernel" in r[hdr.index("Kernel Name")]]
-names = ["stage0 C=128 fc1+gelu", "stage0 C=128 fc2+resid", "stage1 C=256 fc1+gelu", "stage1 C=256 fc2+resid",
-         "stage2 C=512 fc1+gelu", "stage2 C=512 fc2+resid", "stage3 C=1024 fc1+gelu", "stage3 C=1024 fc2+resid"]
-launches = [3, 3, 3, 3, 27, 27, 3, 3]
-assert len(gemms) == 8, f"expected 8 GEMM launches in the capture, found {len(gemms)}"
+gemms = [r for r in data if "gemm_kernel" in r[hdr.index("Kernel Name")] or "mlp_fused_kernel" in r[hdr.index("Kernel Name")]]
+# scripts/prof_layers.py <MB> 0 launches the default forward's MLP kernels in this order
+names = ["stage0 C=128 fused MLP (fc1+LN+gelu+fc2+resid)", "stage1 C=256 fused MLP (fc1+LN+gelu+fc2+resid)",
+         "stage2 C=512 fc1+LN+gelu", "stage2 C=512 fc2+resid", "stage3 C=1024 fc1+LN+gelu", "stage3 C=1024 fc2+resid"]
+launches = [3, 3, 27, 27, 3, 3]
+assert len(gemms) == len(names), f"expected {len(names)} MLP launches in the capture, found {len(gemms)}"
 per = []
 total = 0.0
 for r, n, k in zip(gemms, names, launches):

@@ -26,7 +26,7 @@ EXPORTS = (
     "svb_k1_workspace_bytes", "svb_k1_normalize_resize", "svb_normalize_u8_workspace_bytes", "svb_normalize_u8",
     "svb_k3_workspace_bytes", "svb_k3_crop_resample", "svb_k3_crop_resample_rotated",
     "svb_model_create", "svb_model_destroy", "svb_model_workspace_bytes", "svb_model_forward", "svb_model_forward_f32",
-    "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused",
+    "svb_model_info", "svb_model_cost", "svb_gemm", "svb_mlp_fused", "svb_mlp_fused_ln",
     "svb_stem_ln", "svb_dwconv_ln", "svb_dwconv_raw", "svb_dwconv_tc_pack", "svb_dwconv_raw_tc", "svb_dwconv_ln_tc", "svb_ln_patchify", "svb_head",
     "svb_k4_classifier_input",
     "svb_png_bound", "svb_png_encode_gray8", "svb_png_write_gray8_batch", "svb_png_write_gray8_ragged",
@@ -122,6 +122,8 @@ def load() -> C.CDLL:
     lib.svb_gemm.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_mlp_fused.restype = C.c_int
     lib.svb_mlp_fused.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.svb_mlp_fused_ln.restype = C.c_int
+    lib.svb_mlp_fused_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.svb_stem_ln.restype = C.c_int
     lib.svb_stem_ln.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]
     lib.svb_dwconv_ln.restype = C.c_int

@@ -341,6 +341,41 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uin
             : "memory");
     }
 }
+// The same two instructions issued by the lane whose `lead` flag is set, with NO branch around them: the MMA warp runs
+// warp-uniform code (every lane waits on the barriers and computes the descriptors), so the descriptors stay in uniform
+// registers instead of going through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence per instruction.
+template <int CG = 1>
+__device__ __forceinline__ void tc_mma_f16_if(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    if (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+            "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
+            : "memory");
+    }
+}
+template <int CG = 1>
+__device__ __forceinline__ void tc_commit_if(uint32_t lead, uint64_t* bar) {
+    if (CG == 1) {
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                     "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(lead)
+                     : "memory");
+    } else {
+        const uint16_t mask = 3;
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                     "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}\n" ::"r"(
+                         smem_u32(bar)),
+                     "h"(mask), "r"(lead)
+                     : "memory");
+    }
+}
 // 32 lanes x 32 consecutive 32-bit columns: thread i of the warp gets lane (base+i), columns c..c+31
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(

@@ -226,18 +226,21 @@ static bool pdl_enabled() {
     return enabled != 0;
 }
 // fused fc1 -> GELU -> fc2 kernel (hidden activation kept on chip) for the widths whose accumulators fit TMEM:
-// C = 128 / 256 (stages 0-1 of convnext_base).  Correct (12 GPU tests) but on B200 it only TIES the un-fused pair
-// (profiles/r01_mlp_fused.txt: 317-380 us vs 323 us at C=128, 194-228 us vs 197 us at C=256 for 37 images): the GELU
-// epilogue on the FP32/MUFU pipes, not the tensor pipe or HBM, bounds both forms, and the fused form adds a
-// chunk-level MMA <-> epilogue hand-shake.  Off by default; SVB_MLP_FUSED=1 enables it.
-static bool mlp_fused(int C) {
-    static int enabled = -1;
-    if (enabled < 0) {
+// C = 128 / 256 (stages 0-1 of convnext_base).  Round 1 measured a tie with the un-fused pair and left it off; the reason turned
+// out to be the MMA ISSUE path (its 32 / 64-clk MMAs each paid ~130 clk of ELECT / R2UR.BROADCAST latency).  With the warp-uniform
+// issue loop: 644 -> 458 us at C = 128 and 402 -> 318 us at C = 256 per 64 images, against 596 / 335 us for the un-fused pair with
+// the folded LayerNorm (profiles/r02w_fused_uniform.txt).  On by default for the LayerNorm-folded forward; SVB_MLP_FUSED=0 / 1
+// forces it off / on (1 also in the un-folded forward).
+static int mlp_fused_env() {
+    static int v = -2;
+    if (v == -2) {
         const char* e = getenv("SVB_MLP_FUSED");
-        enabled = (e && e[0] == '1') ? 1 : 0;
+        v = e ? (e[0] == '1' ? 1 : 0) : -1;
     }
-    return enabled && (C == 128 || C == 256);
+    return v;
 }
+static bool mlp_fused(int C) { return mlp_fused_env() == 1 && (C == 128 || C == 256); }          // un-folded forward: opt-in
+static bool mlp_fused_lnf(int C) { return mlp_fused_env() != 0 && (C == 128 || C == 256); }      // folded forward: default
 // Tensor-core depthwise kernel (shifted-view diagonal MMAs): C = 256 / 512 when one stage pair of halo tiles fits
 // in shared memory.  SVB_DWCONV_TC=0 forces the CUDA-core kernel everywhere (A/B testing).
 static int dw_tc_rows(int C, int W) {
@@ -787,10 +790,10 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
     return set_error(SVB_ERR_INVALID_ARG, "gemm: unsupported mode %d", mode);
 }
 
-template <typename T, int C>
-static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st) {
+template <typename T, int C, bool LNF>
+static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st, const float2* rowstat) {
     using Cfg = MlpCfg<C>;
-    auto kern = mlp_fused_kernel<T, C>;
+    auto kern = mlp_fused_kernel<T, C, LNF>;
     static bool attr_done[MAX_DEVICES] = {};
     const int dslot = current_device_slot();
     if (!attr_done[dslot]) {
@@ -804,22 +807,26 @@ static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const
     cfg.blockDim = dim3(Cfg::NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, bp.w1f_map, bp.w2f_map, x, (const float*)bp.b1, (const float*)bp.b2,
-                                   (const float*)bp.gamma, M));
+                                   (const float*)bp.gamma, M, (const float*)bp.s1, rowstat));
     count_launch();
     return SVB_OK;
 }
+// rowstat != nullptr: the LayerNorm-folded form (bp.b1 = t_n, bp.s1 = s_n, a = the raw depthwise output)
 template <typename T>
-static int launch_mlp_fused(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int C, int M, cudaStream_t st) {
-    if (C == 128) return launch_mlp_fused_t<T, 128>(a, bp, x, M, st);
-    if (C == 256) return launch_mlp_fused_t<T, 256>(a, bp, x, M, st);
+static int launch_mlp_fused(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int C, int M, cudaStream_t st,
+                            const float2* rowstat = nullptr) {
+    if (C == 128) return rowstat ? launch_mlp_fused_t<T, 128, true>(a, bp, x, M, st, rowstat) : launch_mlp_fused_t<T, 128, false>(a, bp, x, M, st, nullptr);
+    if (C == 256) return rowstat ? launch_mlp_fused_t<T, 256, true>(a, bp, x, M, st, rowstat) : launch_mlp_fused_t<T, 256, false>(a, bp, x, M, st, nullptr);
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "fused MLP: unsupported width %d", C);
 }
 
@@ -1189,6 +1196,10 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                     } else {
                         RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
                     }
+                    if (mlp_fused_lnf(C) && !m->v2 && ns == nb) {
+                        RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, rowstat));
+                        continue;
+                    }
                     RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, m1, 4 * C, C,
                                                     GEMM_LNGELU, st, false, rowstat, m0));
                     if (m->v2) RUN(SVB_KC_GEMM, launch_grn<T>(Hd + (size_t)m0 * 4 * C, ns, tok, 4 * C, bp.grn_w, bp.grn_b,
@@ -1358,6 +1369,27 @@ extern "C" int svb_mlp_fused(const void* d_a, const void* d_w1, const float* d_b
     if (int rc = make_epilogue_map(&x_map, dtype, d_x, M, C)) return rc;
     if (dtype == SVB_FP16) return launch_mlp_fused<__half>(a_map, bp, x_map, C, M, st);
     return launch_mlp_fused<__nv_bfloat16>(a_map, bp, x_map, C, M, st);
+}
+
+extern "C" int svb_mlp_fused_ln(const void* d_a, const void* d_w1g, const float* d_t, const float* d_s, const float* d_rowstat, const void* d_w2,
+                                const float* d_b2, const float* d_gamma, void* d_x, int M, int C, int dtype, void* stream_) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    if (int rc = check_device_sm100()) return rc;
+    SVB_REQUIRE(d_a && d_w1g && d_t && d_s && d_rowstat && d_w2 && d_b2 && d_gamma && d_x && M > 0, SVB_ERR_INVALID_ARG, "mlp_fused_ln: bad arguments");
+    SVB_REQUIRE(C == 128 || C == 256, SVB_ERR_UNSUPPORTED_MODEL, "mlp_fused_ln: width %d (supported: 128, 256)", C);
+    BlockParams bp{};
+    bp.b1 = const_cast<float*>(d_t);
+    bp.s1 = const_cast<float*>(d_s);
+    bp.b2 = const_cast<float*>(d_b2);
+    bp.gamma = const_cast<float*>(d_gamma);
+    CUtensorMap a_map, x_map;
+    if (int rc = make_operand_map(&a_map, dtype, d_a, M, C, 128)) return rc;
+    if (int rc = make_operand_map(&bp.w1f_map, dtype, d_w1g, 4 * (uint64_t)C, C, 32)) return rc;
+    if (int rc = make_operand_map(&bp.w2f_map, dtype, d_w2, C, 4 * (uint64_t)C, C / 2)) return rc;
+    if (int rc = make_epilogue_map(&x_map, dtype, d_x, M, C)) return rc;
+    const float2* rs = reinterpret_cast<const float2*>(d_rowstat);
+    if (dtype == SVB_FP16) return launch_mlp_fused<__half>(a_map, bp, x_map, C, M, st, rs);
+    return launch_mlp_fused<__nv_bfloat16>(a_map, bp, x_map, C, M, st, rs);
 }
 
 // ---------------------------------------------------------------------------------------------

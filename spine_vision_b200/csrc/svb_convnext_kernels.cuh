@@ -874,7 +874,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
     uint64_t* rfull = tempty + 2;          // [EPI_WARPS] residual box landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + Cfg::NUM_BARS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: provably warp-uniform, so the role branches are uniform branches
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
     const int tiles_n = (N + BN - 1) / BN;
     const int tiles_m = (M - m0 + Cfg::BM * CG - 1) / (Cfg::BM * CG);
@@ -927,10 +928,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
+        if (rank == 0) {
+            // The WHOLE warp runs this loop and one elected lane issues (predicated instructions, no branch around them): the
+            // descriptors then stay in uniform registers.  With `if (lane == 0)` around the loop every MMA operand went through an
+            // ELECT / R2UR.BROADCAST / BRA.U.ANY sequence, ~130 clk of issue latency per MMA (measured in dwconv_rawtc_kernel) --
+            // as long as the 128 clk of tensor work of a 128 x 256 x 16 MMA.
             // instruction descriptor: D=f32, A/B = T, both K-major, M = 128*CG, N = BN
             constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) |
                                        ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((Cfg::BM * CG) >> 4) << 24);
+            const uint32_t lead = elect_one() ? 1u : 0u;
+            const uint32_t tm0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint64_t a00 = make_sw128_kmajor_desc(smem_u32(sA)), b00 = make_sw128_kmajor_desc(smem_u32(sB));
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -938,19 +946,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ C
             for (int tile = tile0; tile < num_tiles; tile += tile_step) {
                 mbar_wait(&tempty[as], aphase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tm0 + (uint32_t)(as * BN);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
-                    const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sA + stage * Cfg::A_BYTES));
-                    const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
+                    const uint64_t adesc = a00 + (uint64_t)(stage * (Cfg::A_BYTES >> 4));
+                    const uint64_t bdesc = b00 + (uint64_t)(stage * (Cfg::B_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < Cfg::BK / 16; ++k)  // +32 B per UMMA_K inside the swizzle atom
-                        tc_mma_f16<CG>(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    tc_commit<CG>(&empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
+                        tc_mma_f16_if<CG>(lead, d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_if<CG>(lead, &empty[stage]);  // frees the smem slot (in both CTAs) once these MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                tc_commit<CG>(&tfull[as]);  // accumulator complete -> epilogue (both CTAs)
+                tc_commit_if<CG>(lead, &tfull[as]);  // accumulator complete -> epilogue (both CTAs)
                 if (++as == 2) { as = 0; aphase ^= 1; }
             }
         }
@@ -1115,11 +1123,15 @@ struct MlpCfg {
     static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 
-template <typename T, int C>
+// LNF: the block's LayerNorm folded into fc1 as in GEMM_LNGELU (a = the RAW depthwise output, W1 pre-multiplied by the LayerNorm
+// weight): hidden = GELU(rstd_m * acc + (-mu_m rstd_m) * s_n + t_n) with (rstd_m, -mu_m rstd_m) = rowstat[m], s_n = `s1`, t_n = `b1`.
+// A thread's token is the same for all 4C / 64 chunks of a tile, so the statistics cost one load per tile.
+template <typename T, int C, bool LNF>
 __global__ void __launch_bounds__(MlpCfg<C>::NUM_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w1_map,
                  const __grid_constant__ CUtensorMap w2_map, const __grid_constant__ CUtensorMap x_map,
-                 const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ gamma, int M) {
+                 const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ gamma, int M,
+                 const float* __restrict__ s1, const float2* __restrict__ rowstat) {
     using Cfg = MlpCfg<C>;
     constexpr int NJ = Cfg::NJ, S = Cfg::W_SLOTS, NB = Cfg::NB, CH = Cfg::CH;
     extern __shared__ uint8_t smem_raw[];
@@ -1145,7 +1157,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     uint64_t* rfull = yfree_p + 2;          // [EPI_WARPS] residual boxes landed
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(rfull + Cfg::EPI_WARPS);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;  // provably warp-uniform
     const uint32_t rank = cluster_ctarank();
     const int num_tiles = (M + 255) / 256;
     const int tile0 = (int)blockIdx.x / 2, tile_step = (int)gridDim.x / 2;
@@ -1178,10 +1190,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t tm_y = tmem_base, tm_h = tmem_base + (uint32_t)C;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
+            pdl_wait();
             int slot = 0;
             uint32_t wphase = 0, tcount = 0;
             auto next_slot = [&]() -> uint8_t* {
@@ -1219,8 +1233,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            // -------------------------------------------------------------- MMA issuer (pair leader)
+        if (rank == 0) {
+            // -------------------------------------------------------------- MMA issuer (pair leader): the whole warp runs the loop,
+            // one elected lane issues (see gemm_kernel) -- these MMAs are 32 / 64 clk of tensor work each, so the ~130 clk of issue
+            // latency per MMA of the `if (lane == 0)` form was three times the arithmetic
+            const uint32_t lead = elect_one() ? 1u : 0u;
             constexpr uint32_t idesc1 = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(Cfg::HC >> 3) << 17) |
                                         ((uint32_t)(256 >> 4) << 24);
             constexpr uint32_t idesc2 = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(C >> 3) << 17) |
@@ -1233,7 +1250,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                 return smem_u32(sW + slot * Cfg::SLOT);
             };
             auto release_slot = [&]() {
-                tc_commit<2>(&wempty[slot]);
+                tc_commit_if<2>(lead, &wempty[slot]);
                 if (++slot == S) { slot = 0; wphase ^= 1; }
             };
             for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
@@ -1254,12 +1271,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                                 const uint64_t bdesc = make_sw128_kmajor_desc(wb + kb * Cfg::W1_KB_BYTES);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    tc_mma_f16<2>(d, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
+                                    tc_mma_f16_if<2>(lead, d, adesc + 2 * k, bdesc + 2 * k, idesc1, (kb | k) != 0 ? 1u : 0u);
                             }
                             release_slot();
                         }
-                        if (j == NJ - 1) tc_commit<2>(aempty);  // the A tile has been read for the last time
-                        tc_commit<2>(&hacc_full[hb]);
+                        if (j == NJ - 1) tc_commit_if<2>(lead, aempty);  // the A tile has been read for the last time
+                        tc_commit_if<2>(lead, &hacc_full[hb]);
                         ++j1;
                     }
                     if (j >= NB - 1) {
@@ -1279,14 +1296,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
                             const uint64_t bdesc = make_sw128_kmajor_desc(wb);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_mma_f16<2>(tm_y, adesc + 2 * k, bdesc + 2 * k, idesc2, (jj > 0 || k > 0) ? 1u : 0u);
+                                tc_mma_f16_if<2>(lead, tm_y, adesc + 2 * k, bdesc + 2 * k, idesc2, (jj > 0 || k > 0) ? 1u : 0u);
                             release_slot();
                         }
-                        tc_commit<2>(&hs_free[hb]);
+                        tc_commit_if<2>(lead, &hs_free[hb]);
                         ++j2;
                     }
                 }
-                tc_commit<2>(yfull);
+                tc_commit_if<2>(lead, yfull);
             }
         } else if (lane == 0 && rank == 1) {
             // -------------------------------------------------------------- relay (peer): local barriers -> one arrive at the leader
@@ -1317,8 +1334,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
         uint8_t* stage_p = (Cfg::STAGE_IN_H ? sH : sStage) + ew * CH * 2048;
         const uint32_t stage_a = smem_u32(stage_p);
         constexpr int CW = C / 4;
+        pdl_wait();
         for (int tile = tile0; tile < num_tiles; tile += tile_step, ++tcount) {
             const int row0 = (tile * 2 + (int)rank) * 128 + q * 32;
+            uint64_t ra2 = 0, rb2 = 0;
+            if (LNF) {
+                const float2 rs = row0 + lane < M ? __ldg(rowstat + row0 + lane) : make_float2(0.f, 0.f);
+                ra2 = pk2(rs.x, rs.x);
+                rb2 = pk2(rs.y, rs.y);
+            }
             if (!Cfg::STAGE_IN_H && row0 < M && lane == 0) {
                 // dedicated staging: the residual boxes of this tile arrive while its chunks are computed
                 mbar_expect_tx(&rfull[ew], CH * 2048);
@@ -1328,9 +1352,12 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
             for (int j = 0; j < NJ; ++j, ++j1) {
                 const uint32_t hb = j1 % NB, u = (j1 / NB) & 1;
                 const int hcol = j * Cfg::HC + slice * 16;
-                float4 bias[4];  // in flight before the accumulator is waited for
+                float4 bias[4], sn[4];  // in flight before the accumulator is waited for
 #pragma unroll
-                for (int i = 0; i < 4; ++i) bias[i] = __ldg(reinterpret_cast<const float4*>(b1 + hcol) + i);
+                for (int i = 0; i < 4; ++i) {
+                    bias[i] = __ldg(reinterpret_cast<const float4*>(b1 + hcol) + i);
+                    if (LNF) sn[i] = __ldg(reinterpret_cast<const float4*>(s1 + hcol) + i);
+                }
                 mbar_wait(&hacc_full[hb], u);
                 tc_fence_after();
                 float v[16];
@@ -1344,10 +1371,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const float4 c0 = bias[2 * i], c1 = bias[2 * i + 1];
-                    const uint64_t v01 = add2(pk2(v[8 * i + 0], v[8 * i + 1]), pk2(c0.x, c0.y));
-                    const uint64_t v23 = add2(pk2(v[8 * i + 2], v[8 * i + 3]), pk2(c0.z, c0.w));
-                    const uint64_t v45 = add2(pk2(v[8 * i + 4], v[8 * i + 5]), pk2(c1.x, c1.y));
-                    const uint64_t v67 = add2(pk2(v[8 * i + 6], v[8 * i + 7]), pk2(c1.z, c1.w));
+                    uint64_t v01, v23, v45, v67;
+                    if (LNF) {
+                        const float4 s0 = sn[2 * i], s1v = sn[2 * i + 1];
+                        v01 = fma2(ra2, pk2(v[8 * i + 0], v[8 * i + 1]), fma2(rb2, pk2(s0.x, s0.y), pk2(c0.x, c0.y)));
+                        v23 = fma2(ra2, pk2(v[8 * i + 2], v[8 * i + 3]), fma2(rb2, pk2(s0.z, s0.w), pk2(c0.z, c0.w)));
+                        v45 = fma2(ra2, pk2(v[8 * i + 4], v[8 * i + 5]), fma2(rb2, pk2(s1v.x, s1v.y), pk2(c1.x, c1.y)));
+                        v67 = fma2(ra2, pk2(v[8 * i + 6], v[8 * i + 7]), fma2(rb2, pk2(s1v.z, s1v.w), pk2(c1.z, c1.w)));
+                    } else {
+                        v01 = add2(pk2(v[8 * i + 0], v[8 * i + 1]), pk2(c0.x, c0.y));
+                        v23 = add2(pk2(v[8 * i + 2], v[8 * i + 3]), pk2(c0.z, c0.w));
+                        v45 = add2(pk2(v[8 * i + 4], v[8 * i + 5]), pk2(c1.x, c1.y));
+                        v67 = add2(pk2(v[8 * i + 6], v[8 * i + 7]), pk2(c1.z, c1.w));
+                    }
                     const uint32_t piece = (uint32_t)(slice * 2 + i);
                     sts128(dst + ((piece ^ ((uint32_t)r & 7u)) << 4),
                            make_uint4(gelu_pack2<T>(v01), gelu_pack2<T>(v23), gelu_pack2<T>(v45), gelu_pack2<T>(v67)));
@@ -1494,23 +1530,6 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&o)[8]) {
                  : "memory");
 }
 
-// tcgen05.mma / commit issued by the lane whose predicate is set, with NO branch around them: the MMA warp of
-// dwconv_rawtc_kernel runs warp-uniform code, so that the descriptors stay in uniform registers.  (With the usual
-// `if (lane == 0) { ... }` around the whole loop every operand went through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence:
-// ~130 clk per MMA against 56 clk of tensor work.)
-__device__ __forceinline__ void tc_mma_f16_if(uint32_t lead, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p, q;\n\tsetp.ne.b32 p, %4, 0;\n\tsetp.ne.b32 q, %5, 0;\n\t"
-        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(lead)
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_if(uint32_t lead, uint64_t* bar) {
-    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
-                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n" ::"r"(smem_u32(bar)), "r"(lead)
-                 : "memory");
-}
-
 template <typename T>
 __global__ void __launch_bounds__(DwTc2Cfg::NUM_THREADS, 1)
 dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map,
@@ -1608,12 +1627,12 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                         for (int dy = 0; dy < 7; ++dy) {
                             const uint64_t adesc = a0 + (uint64_t)(mt * 1024 + 2 * g) + (uint64_t)dy * a_dy;
                             const uint64_t bdesc = b0 + (uint64_t)(dy * (Cfg::B_BYTES >> 4) + 2 * g);
-                            tc_mma_f16_if(lead, tmem_base + (uint32_t)(g * 128), adesc, bdesc, idesc, dy != 0 ? 1u : 0u);
+                            tc_mma_f16_if<1>(lead, tmem_base + (uint32_t)(g * 128), adesc, bdesc, idesc, dy != 0 ? 1u : 0u);
                         }
-                        tc_commit_if(lead, &tfull[g]);
+                        tc_commit_if<1>(lead, &tfull[g]);
                     }
                 }
-                tc_commit_if(lead, &aempty[stage]);
+                tc_commit_if<1>(lead, &aempty[stage]);
             }
         }
     } else {

@@ -441,6 +441,18 @@ def mlp_fused(a: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Ten
     return x
 
 
+@_on_device
+def mlp_fused_ln(a: torch.Tensor, w1g: torch.Tensor, t: torch.Tensor, s: torch.Tensor, rowstat: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
+                 gamma: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """Fused MLP with the LayerNorm folded into fc1 (``svb_mlp_fused_ln``): ``a`` is the raw depthwise output, ``rowstat`` its
+    (rstd, -mean * rstd) per token; ``x += gamma * (gelu(rstd * (a @ w1g.T) - rstd * mean * s + t) @ w2.T + b2)`` in place."""
+    assert a.dtype == w1g.dtype == w2.dtype == x.dtype and a.is_contiguous() and x.is_contiguous()
+    M, Cc = a.shape
+    _lib.check(_lib.load().svb_mlp_fused_ln(a.data_ptr(), w1g.data_ptr(), t.data_ptr(), s.data_ptr(), rowstat.data_ptr(), w2.data_ptr(),
+                                            b2.data_ptr(), gamma.data_ptr(), x.data_ptr(), M, Cc, _dt(a), _lib.current_stream()))
+    return x
+
+
 # ------------------------------------------------------------------ standalone layers (tests / ncu)
 def _dt(t: torch.Tensor) -> int:
     assert t.dtype in (torch.bfloat16, torch.float16)

@@ -299,3 +299,38 @@ def test_fused_mlp_vs_torch(M, C, dtype):
     tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0) * 1.5
     bad = int((err > tol).sum())
     assert bad == 0, f"{bad} of {err.numel()} beyond tolerance; max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "fp16"])
+@pytest.mark.parametrize("M,C", [(256, 128), (1000, 128), (256 * 80 + 17, 128), (512, 256), (3000, 256)])
+def test_fused_mlp_folded_layernorm_vs_torch(M, C, dtype):
+    """``svb_mlp_fused_ln`` (what stages 0 / 1 of the model run): the raw depthwise output + per-token statistics in, the block's
+    residual update out -- against x + gamma * fc2(GELU(fc1(LayerNorm(y)))) of plain PyTorch fp32 with the hidden activation rounded
+    to the operand dtype."""
+    g = torch.Generator().manual_seed(M + C + 3)
+    dt = DT[dtype]
+    y = (torch.randn(M, C, generator=g) * 0.7 + 0.3).to(dt)  # raw conv output (16-bit), non-zero token mean
+    lnw = 1 + 0.2 * torch.randn(C, generator=g)
+    lnb = 0.1 * torch.randn(C, generator=g)
+    w1 = torch.randn(4 * C, C, generator=g) / C ** 0.5
+    b1 = 0.1 * torch.randn(4 * C, generator=g)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dt)
+    b2 = torch.randn(C, generator=g) * 0.2
+    gamma = torch.rand(C, generator=g) + 0.1
+    x = torch.randn(M, C, generator=g).to(dt)
+    yf = y.float()
+    mu, var = yf.mean(-1), yf.var(-1, unbiased=False)
+    rstd = torch.rsqrt(var + 1e-6)
+    stat = torch.stack([rstd, -mu * rstd], -1).contiguous()
+    wg = (w1 * lnw[None, :]).to(dt)
+    s_n = wg.float().sum(1)
+    t_n = (w1.double() @ lnb.double()).float() + b1
+    h = F.gelu(F.layer_norm(yf, (C,), lnw, lnb, 1e-6) @ w1.t() + b1).to(dt).float()
+    want = x.float() + gamma * (h @ w2.float().t() + b2)
+    d = dev()
+    got = ops.mlp_fused_ln(y.to(d), wg.to(d), t_n.to(d), s_n.to(d), stat.to(d), w2.to(d), b2.to(d), gamma.to(d), x.to(d).clone()).float().cpu()
+    err = (got - want).abs()
+    # output rounding + the hidden operand's rounding + W1 * g rounded to 16 bits (the un-folded reference rounds nothing there)
+    tol = (2.0 ** -8 if dtype == "bf16" else 2.0 ** -11) * (want.abs() + 1.0) * 3.0
+    bad = int((err > tol).sum())
+    assert bad == 0, f"{bad} of {err.numel()} beyond tolerance; max err {err.max().item():.4g}"
