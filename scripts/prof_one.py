@@ -23,4 +23,12 @@ if kind == "dwtc":
 elif kind == "dwraw":
     for _ in range(2):
         ops.dwconv_raw(x, taps, bias)
+elif kind == "fused":
+    a = torch.randn(M, C, generator=g).to(dt).to(dev)
+    w1 = (torch.randn(4 * C, C, generator=g) / C ** 0.5).to(dt).to(dev)
+    w2 = (torch.randn(C, 4 * C, generator=g) / (4 * C) ** 0.5).to(dt).to(dev)
+    stat = torch.ones((M, 2), device=dev)
+    xo = a.clone()
+    for _ in range(2):
+        ops.mlp_fused_ln(a, w1, torch.zeros(4 * C, device=dev), w1.float().sum(1), stat, w2, torch.zeros(C, device=dev), torch.ones(C, device=dev), xo)
 torch.cuda.synchronize()

@@ -13,7 +13,7 @@ from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
 so = ROOT / "spine_vision_b200" / "libspine_b200.so"
-OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "FFMA2", "HFMA2", "SYNCS", "ACQBULK", "UCGABAR", "LDSM", "STSM"]
+OPS = ["UTCHMMA", "UTCHMMA.2CTA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "FFMA2", "FHFMA", "HFMA2", "SHFL", "SYNCS", "ACQBULK", "UCGABAR", "LDSM", "STSM"]
 sass = subprocess.run(["cuobjdump", "-sass", str(so)], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["cu++filt", n], capture_output=True, text=True).stdout.strip() or n
 counts: dict = collections.OrderedDict()

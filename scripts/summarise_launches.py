@@ -36,7 +36,8 @@ for name, a in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     out.append(f"{a[0]:10.3f} {100 * a[0] / total:5.1f}% {a[1]:6d} {a[2]:8.4f} {a[3]:8.4f}  {name}")
 groups = defaultdict(float)
 for name, a in agg.items():
-    g = ("gemm" if name.startswith("gemm_kernel") else "dwconv_ln" if name.startswith("dwconv_ln") else "k1" if name.startswith("k1_")
+    g = ("gemm" if name.startswith("gemm_kernel") or name.startswith("mlp_fused_kernel")
+         else "dwconv_ln" if name.startswith("dwconv_") or name.startswith("ln_stat_finalize") else "k1" if name.startswith("k1_")
          else "k3" if name.startswith("k3_") else "k4" if name.startswith("k4_") else name.split("<")[0])
     groups[g] += a[0]
 out.append("# by class: " + ", ".join(f"{g} {100 * v / total:.1f} %" for g, v in sorted(groups.items(), key=lambda kv: -kv[1])))

@@ -791,7 +791,8 @@ static int launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const CUtenso
 }
 
 template <typename T, int C, bool LNF>
-static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st, const float2* rowstat) {
+static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int M, cudaStream_t st, const float2* rowstat,
+                              int stat_parts) {
     using Cfg = MlpCfg<C>;
     auto kern = mlp_fused_kernel<T, C, LNF>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -817,16 +818,19 @@ static int launch_mlp_fused_t(const CUtensorMap& a, const BlockParams& bp, const
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 2 : 1;
     SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, a, bp.w1f_map, bp.w2f_map, x, (const float*)bp.b1, (const float*)bp.b2,
-                                   (const float*)bp.gamma, M, (const float*)bp.s1, rowstat));
+                                   (const float*)bp.gamma, M, (const float*)bp.s1, rowstat, stat_parts));
     count_launch();
     return SVB_OK;
 }
-// rowstat != nullptr: the LayerNorm-folded form (bp.b1 = t_n, bp.s1 = s_n, a = the raw depthwise output)
+// rowstat != nullptr: the LayerNorm-folded form (bp.b1 = t_n, bp.s1 = s_n, a = the raw depthwise output); stat_parts > 0: rowstat is
+// dwconv_rawtc_kernel's partial sums [M][stat_parts]
 template <typename T>
 static int launch_mlp_fused(const CUtensorMap& a, const BlockParams& bp, const CUtensorMap& x, int C, int M, cudaStream_t st,
-                            const float2* rowstat = nullptr) {
-    if (C == 128) return rowstat ? launch_mlp_fused_t<T, 128, true>(a, bp, x, M, st, rowstat) : launch_mlp_fused_t<T, 128, false>(a, bp, x, M, st, nullptr);
-    if (C == 256) return rowstat ? launch_mlp_fused_t<T, 256, true>(a, bp, x, M, st, rowstat) : launch_mlp_fused_t<T, 256, false>(a, bp, x, M, st, nullptr);
+                            const float2* rowstat = nullptr, int stat_parts = 0) {
+    if (C == 128)
+        return rowstat ? launch_mlp_fused_t<T, 128, true>(a, bp, x, M, st, rowstat, stat_parts) : launch_mlp_fused_t<T, 128, false>(a, bp, x, M, st, nullptr, 0);
+    if (C == 256)
+        return rowstat ? launch_mlp_fused_t<T, 256, true>(a, bp, x, M, st, rowstat, stat_parts) : launch_mlp_fused_t<T, 256, false>(a, bp, x, M, st, nullptr, 0);
     return set_error(SVB_ERR_UNSUPPORTED_MODEL, "fused MLP: unsupported width %d", C);
 }
 
@@ -917,8 +921,9 @@ static int sub_batch_images(int s, int nb, int tokens, int C) {
 
 template <typename T>
 static int launch_dwconv_rawtc(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, float2* stat_part, int C, int nb, int H,
-                               int W, int mode, cudaStream_t st, int b0 = 0) {
-    // rowstat / stat_part address the micro-batch's first token; images [b0, b0 + nb) are written
+                               int W, int mode, cudaStream_t st, int b0 = 0, bool finalize = true) {
+    // rowstat / stat_part address the micro-batch's first token; images [b0, b0 + nb) are written.  finalize = false: the consumer
+    // (mlp_fused_kernel) adds the partial sums up itself
     using Cfg = DwTc2Cfg;
     auto kern = dwconv_rawtc_kernel<T>;
     static bool attr_done[MAX_DEVICES] = {};
@@ -946,7 +951,7 @@ static int launch_dwconv_rawtc(const CUtensorMap& x, const BlockParams& bp, void
     SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wtc_map, (const float*)bp.bdw, static_cast<T*>(out), stat_part, C, H, W, rowpx, nwin, units_y,
                                    num_units, b0));
     count_launch();
-    {
+    if (finalize) {
         const long long t0 = (long long)b0 * H * W, tokens = (long long)nb * H * W;
         cudaLaunchConfig_t fc{};
         fc.gridDim = dim3((unsigned)ceil_div<long long>(tokens, 256));
@@ -1190,14 +1195,16 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                 const int ns = (nb - b0) < sub ? (nb - b0) : sub;
                 const int m0 = b0 * tok, m1 = (b0 + ns) * tok;
                 for (const BlockParams& bp : m->blocks[s]) {
+                    const bool fused = mlp_fused_lnf(C) && !m->v2 && ns == nb;
+                    float2* stat_part = reinterpret_cast<float2*>(ws + L.stat_part);
                     if (plan->tc2[s]) {
-                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, reinterpret_cast<float2*>(ws + L.stat_part), C, ns, h, w,
-                                                                     plan->tc2[s], st, b0));
+                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, stat_part, C, ns, h, w, plan->tc2[s], st, b0, !fused));
                     } else {
                         RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
                     }
-                    if (mlp_fused_lnf(C) && !m->v2 && ns == nb) {
-                        RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, rowstat));
+                    if (fused) {
+                        if (plan->tc2[s]) { RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, stat_part, C / 64)); }
+                        else { RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, rowstat, 0)); }
                         continue;
                     }
                     RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, m1, 4 * C, C,

@@ -1131,7 +1131,9 @@ __global__ void __launch_bounds__(MlpCfg<C>::NUM_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constant__ CUtensorMap w1_map,
                  const __grid_constant__ CUtensorMap w2_map, const __grid_constant__ CUtensorMap x_map,
                  const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ gamma, int M,
-                 const float* __restrict__ s1, const float2* __restrict__ rowstat) {
+                 const float* __restrict__ s1, const float2* __restrict__ rowstat, int stat_parts) {
+    // stat_parts > 0: rowstat = dwconv_rawtc_kernel's per-chunk partial sums [M][stat_parts] (sum, sum of squares), finished here
+    // (one or two 16-byte loads per thread and TILE; no ln_stat_finalize_kernel launch in front of this kernel)
     using Cfg = MlpCfg<C>;
     constexpr int NJ = Cfg::NJ, S = Cfg::W_SLOTS, NB = Cfg::NB, CH = Cfg::CH;
     extern __shared__ uint8_t smem_raw[];
@@ -1339,7 +1341,20 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
             const int row0 = (tile * 2 + (int)rank) * 128 + q * 32;
             uint64_t ra2 = 0, rb2 = 0;
             if (LNF) {
-                const float2 rs = row0 + lane < M ? __ldg(rowstat + row0 + lane) : make_float2(0.f, 0.f);
+                float2 rs = make_float2(0.f, 0.f);
+                if (row0 + lane < M) {
+                    if (stat_parts == 0) {
+                        rs = __ldg(rowstat + row0 + lane);
+                    } else {
+                        const float2* rp = rowstat + (size_t)(row0 + lane) * (size_t)stat_parts;
+                        float sm = 0.f, sq = 0.f;
+                        for (int p = 0; p < stat_parts; ++p) { const float2 v = __ldg(rp + p); sm += v.x; sq += v.y; }  // C / 64 = 2 or 4 parts
+                        const float mu = sm * (1.0f / (float)C);
+                        const float var = fmaxf(fmaf(-mu, mu, sq * (1.0f / (float)C)), 0.0f);
+                        const float rstd = 1.0f / sqrtf(var + LN_EPS_BACKBONE);
+                        rs = make_float2(rstd, -mu * rstd);
+                    }
+                }
                 ra2 = pk2(rs.x, rs.x);
                 rb2 = pk2(rs.y, rs.y);
             }
@@ -1688,7 +1703,14 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
 #pragma unroll
                 for (int dx = 0; dx < 7; ++dx) {
                     tmem_ld_wait();
-                    if (dx < 6) TmemLd<16>::ld(tbase + (uint32_t)((dx + 1) * 16), v[(dx + 1) & 1]);
+                    if (dx < 6) {
+                        TmemLd<16>::ld(tbase + (uint32_t)((dx + 1) * 16), v[(dx + 1) & 1]);
+                    } else {
+                        // the last column block is in registers: hand the accumulator back to the MMA warp before working on it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[g]);
+                    }
                     if (PACKED && dx != 3) {
 #pragma unroll
                         for (int c = 0; c < 16; c += 2) {
@@ -1716,10 +1738,6 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                         }
                     }
                 }
-                // the accumulator is in registers: hand it back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[g]);
                 float s = 0.f, sq = 0.f;
                 uint32_t o[8];
 #pragma unroll
