@@ -1675,9 +1675,14 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
         const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 128);
         uint32_t tcount = 0;
         pdl_wait();
+        // index arithmetic without integer divisions (they were ~13 % of this loop's instructions): exact multiply-high
+        // reciprocals for the unit decode (u * divisor < 2^32), shifts for the power-of-two row width of mode A
+        const uint32_t inv_units_img = (uint32_t)((0x100000000ull + (uint32_t)units_img - 1) / (uint32_t)units_img);
+        const uint32_t inv_nwin = (uint32_t)((0x100000000ull + (uint32_t)nwin - 1) / (uint32_t)nwin);
+        const int lw = 31 - __clz(W);  // mode A: W = 8, 16 or 32
         for (int u = u0; u < num_units; u += ustep) {
-            const int b = u / units_img, r = u - b * units_img;
-            const int wi = r % nwin, uy = r / nwin;
+            const int b = units_img == 1 ? u : (int)__umulhi((uint32_t)u, inv_units_img), r = u - b * units_img;  // (the reciprocal of 1 does not fit 32 bits)
+            const int uy = nwin == 1 ? r : (int)__umulhi((uint32_t)r, inv_nwin), wi = r - uy * nwin;
             const int y0 = uy * rows_unit;
             for (int mt = 0; mt < 2; ++mt, ++tcount) {
                 int x, y;
@@ -1688,8 +1693,8 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                     valid = lane >= 3 && lane <= 28 && x < W && y < H;
                 } else {
                     const int p = mt * 128 + px;
-                    y = y0 + p / W;
-                    x = p % W;
+                    y = y0 + (p >> lw);
+                    x = p & (W - 1);
                     valid = y < H;
                 }
                 const size_t tok = ((size_t)(b0 + b) * H + y) * W + x;
