@@ -64,6 +64,7 @@ struct svb_model {
     int hid = 0, nout = 0;
     int device = 0;
     bool v2 = false;  // ConvNeXt-V2: GRN in every block's MLP, no layer scale
+    int tc2_setting = 0x11, mlp_fused_setting = -1;  // SVB_DWCONV_TC2 / SVB_TC2_MODEB and SVB_MLP_FUSED as read at creation
     bool ln_fold = true;  // the block LayerNorm is folded into fc1 (dwconv_raw_kernel + GEMM_LNGELU); SVB_LN_FOLD=0 at creation: separate LN
     // two micro-batches in flight (svb_model_forward): odd micro-batches run on this stream with the second half of the
     // workspace, so that the ramp-up and tail of one chain's persistent kernels are back-filled by the other chain's CTAs
@@ -231,16 +232,14 @@ static bool pdl_enabled() {
 // issue loop: 644 -> 458 us at C = 128 and 402 -> 318 us at C = 256 per 64 images, against 596 / 335 us for the un-fused pair with
 // the folded LayerNorm (profiles/r02w_fused_uniform.txt).  On by default for the LayerNorm-folded forward; SVB_MLP_FUSED=0 / 1
 // forces it off / on (1 also in the un-folded forward).
+// (read when a model is created and kept in the handle, like SVB_LN_FOLD / SVB_DWCONV_TC2: a test can create models under
+// different settings in one process)
 static int mlp_fused_env() {
-    static int v = -2;
-    if (v == -2) {
-        const char* e = getenv("SVB_MLP_FUSED");
-        v = e ? (e[0] == '1' ? 1 : 0) : -1;
-    }
-    return v;
+    const char* e = getenv("SVB_MLP_FUSED");
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
 }
-static bool mlp_fused(int C) { return mlp_fused_env() == 1 && (C == 128 || C == 256); }          // un-folded forward: opt-in
-static bool mlp_fused_lnf(int C) { return mlp_fused_env() != 0 && (C == 128 || C == 256); }      // folded forward: default
+static bool mlp_fused(int setting, int C) { return setting == 1 && (C == 128 || C == 256); }          // un-folded forward: opt-in
+static bool mlp_fused_lnf(int setting, int C) { return setting != 0 && (C == 128 || C == 256); }      // folded forward: default
 // Tensor-core depthwise kernel (shifted-view diagonal MMAs): C = 256 / 512 when one stage pair of halo tiles fits
 // in shared memory.  SVB_DWCONV_TC=0 forces the CUDA-core kernel everywhere (A/B testing).
 static int dw_tc_rows(int C, int W) {
@@ -263,14 +262,13 @@ static int dw_tc_rows(int C, int W) {
 // dwconv_rawtc_kernel (the 7 x 7 taps as seven row-shifted tcgen05 MMAs with the stencil columns in N).  0 = the stage keeps
 // dwconv_raw_kernel; 1 = mode A (W in {8, 16, 32}: units of whole image rows); 2 = mode B (32-lane windows with an x halo).
 // SVB_DWCONV_TC2=0 switches it off, =2 also allows bf16 (8-bit tap mantissas; fp16 keeps 11).  SVB_TC2_MODEB=0 keeps mode B off.
-static int dw_tc2_mode(int dtype, int C, int H, int W) {
-    static int enabled = -1, modeb = -1;
-    if (enabled < 0) {
-        const char* e = getenv("SVB_DWCONV_TC2");
-        enabled = e ? atoi(e) : 1;
-        const char* b = getenv("SVB_TC2_MODEB");
-        modeb = b ? atoi(b) : 1;
-    }
+static int dw_tc2_env() {  // bit 0..1: SVB_DWCONV_TC2 (default 1), bit 4: SVB_TC2_MODEB (default 1)
+    const char* e = getenv("SVB_DWCONV_TC2");
+    const char* b = getenv("SVB_TC2_MODEB");
+    return ((e ? atoi(e) : 1) & 3) | (((b ? atoi(b) : 1) != 0) << 4);
+}
+static int dw_tc2_mode(int setting, int dtype, int C, int H, int W) {
+    const int enabled = setting & 3, modeb = (setting >> 4) & 1;
     if (!enabled || (dtype != SVB_FP16 && enabled < 2)) return 0;
     if (C % 64 != 0 || C / 64 > num_sms() || H < 1 || W < 1) return 0;
     if (W == 8 || W == 16 || W == 32) return 1;
@@ -375,6 +373,8 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
     SVB_REQUIRE(m->dims[0] == (int)stem_w->shape[0], SVB_ERR_UNSUPPORTED_MODEL, "stem width != stage-0 width");
     m->v2 = hwts.get("backbone.stages.0.blocks.0.mlp.grn.weight") != nullptr;  // timm convnextv2_*: GRN instead of layer scale
     m->ln_fold = ln_fold_env();
+    m->tc2_setting = dw_tc2_env();
+    m->mlp_fused_setting = mlp_fused_env();
     SVB_REQUIRE(m->dims[0] == 96 || m->dims[0] == 128 || m->dims[0] == 192 || m->dims[0] == 256, SVB_ERR_UNSUPPORTED_MODEL,
                 "stem width %d unsupported", m->dims[0]);
     NEED(head_w1, "head.2.weight");
@@ -681,7 +681,7 @@ static int build_plan(svb_model* m, ActPlan* p, uint8_t* ws, int nb, int H, int 
                                      CU_TENSOR_MAP_SWIZZLE_128B))
                 return rc;
         }
-        p->tc2[s] = m->ln_fold ? dw_tc2_mode(m->dtype, (int)C, h, w) : 0;
+        p->tc2[s] = m->ln_fold ? dw_tc2_mode(m->tc2_setting, m->dtype, (int)C, h, w) : 0;
         if (p->tc2[s]) {
             if (int rc = make_xtc2_map(&p->xtc2_map[s], m->dtype, ws + L.x, (int)C, nb, h, w, p->tc2[s])) return rc;
         }
@@ -1195,7 +1195,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                 const int ns = (nb - b0) < sub ? (nb - b0) : sub;
                 const int m0 = b0 * tok, m1 = (b0 + ns) * tok;
                 for (const BlockParams& bp : m->blocks[s]) {
-                    const bool fused = mlp_fused_lnf(C) && !m->v2 && ns == nb;
+                    const bool fused = mlp_fused_lnf(m->mlp_fused_setting, C) && !m->v2 && ns == nb;
                     float2* stat_part = reinterpret_cast<float2*>(ws + L.stat_part);
                     if (plan->tc2[s]) {
                         RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, stat_part, C, ns, h, w, plan->tc2[s], st, b0, !fused));
@@ -1223,7 +1223,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
             } else {
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
             }
-            if (mlp_fused(C) && !m->v2) {
+            if (mlp_fused(m->mlp_fused_setting, C) && !m->v2) {
                 RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
             } else {
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
