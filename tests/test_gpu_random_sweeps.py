@@ -211,3 +211,40 @@ def test_k0_random_orientations_sizes_types_vs_itk_restatement(seed):
         assert (h_, w_) == w.shape and spacings[i] == wsp, (i, (h_, w_), w.shape, spacings[i], wsp)
         got = flat[offs[i] : offs[i] + h_ * w_].reshape(h_, w_)
         assert np.array_equal(got, w.astype(np.float32)), f"case {i} {cases[i][0].shape} {cases[i][0].dtype} dir {cases[i][2]}: max diff {np.abs(got - w).max()}"
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dwconv_tensor_core_random_shapes_vs_torch_and_fp32_pipe(seed):
+    """The tensor-core depthwise kernel (``svb_dwconv_raw_tc``) on shapes nobody picked: heights and widths 1 .. 70 (mode A for
+    widths 8 / 16 / 32, windows otherwise; images smaller than the stencil; one-row and one-column images), channel counts
+    128 .. 512, batches 1 .. 5, activations with outliers.  Against (a) PyTorch's fp32 depthwise convolution with the taps rounded to
+    fp16 (the kernel's operands) within the packed-shuffle budget, (b) the FP32-pipe kernel ``svb_dwconv_raw`` on the same input:
+    statistics agree to 2e-3 relative."""
+    import torch.nn.functional as F
+    rng = np.random.default_rng(1000 + seed)
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(14):
+        B, C = int(rng.integers(1, 6)), int(rng.choice([128, 192, 256, 384, 512]))  # widths both kernels are built for
+        H = int(rng.choice([1, 2, 3, 5, 7, 8, 9, 16, 17, 31, 32, 33, 40, 64, 70]))
+        W = int(rng.choice([1, 2, 4, 6, 8, 9, 16, 20, 26, 27, 32, 33, 52, 53, 64, 70]))
+        x = torch.randn(B, H, W, C, generator=g)
+        x[torch.rand(B, H, W, C, generator=g) < 0.01] *= 30.0  # outliers
+        x = x.to(torch.float16)
+        wt = torch.randn(C, 1, 7, 7, generator=g) * 0.15
+        bias = torch.randn(C, generator=g) * 0.2
+        y = F.conv2d(x.float().permute(0, 3, 1, 2), wt.to(torch.float16).float(), bias, padding=3, groups=C).permute(0, 2, 3, 1)
+        taps = wt.reshape(C, 49).t().contiguous()
+        xd, td, bd = x.to(dev()), taps.to(dev()), bias.to(dev())
+        raw, stat = ops.dwconv_raw_tc(xd, ops.dwconv_tc_pack(td, torch.float16), bd)
+        ref_raw, ref_stat = ops.dwconv_raw(xd, td, bd)
+        torch.cuda.synchronize()
+        err = (raw.float().cpu() - y).abs()
+        # output rounding + six fp16-rounded column partial sums; partial sums can exceed the total when columns cancel, so the
+        # budget is taken against the magnitude sum of one column's terms
+        mag = F.conv2d(x.float().abs().permute(0, 3, 1, 2), wt.abs(), None, padding=3, groups=C).permute(0, 2, 3, 1)
+        tol = 2.0 ** -11 * (y.abs() + 3.0 * mag + 1.0)
+        assert int((err > tol).sum()) == 0, f"B={B} H={H} W={W} C={C}: max err {err.max().item():.4g}"
+        assert torch.isfinite(stat).all()
+        rs, rr = stat.cpu(), ref_stat.cpu()
+        assert torch.allclose(rs[:, 0], rr[:, 0], rtol=4e-3, atol=1e-6), f"B={B} H={H} W={W} C={C}: rstd {(rs[:, 0] - rr[:, 0]).abs().max()}"
+        assert torch.allclose(rs[:, 1], rr[:, 1], rtol=4e-3, atol=4e-3), f"B={B} H={H} W={W} C={C}: -mu rstd {(rs[:, 1] - rr[:, 1]).abs().max()}"
