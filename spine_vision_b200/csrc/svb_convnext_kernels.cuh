@@ -1486,20 +1486,22 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
 //         D[p][dx][c] = sum_dy in[y(p) + dy - 3, x(p), c] * w[dy][dx][c]
 //   * the epilogue adds the seven column blocks across lanes: out[y, x, c] = sum_dx D[(y, x + dx - 3)][dx][c], six warp shuffles
 //     per value (a warp = 32 consecutive pixels of one image row, or 32 / W whole rows when W <= 32; `shfl` segments of W lanes
-//     give the zero padding at the row ends for free).  13 instructions per output instead of 49 FMAs.
+//     give the zero padding at the row ends for free) -- three packed half2 shuffles per value pair for fp16 (shfl_add_h2).
 // Arithmetic: activations and taps are exact 16-bit operands, products are exact in fp32, accumulation is fp32 (tensor core over
-// dy, FFMA over dx): the only difference from dwconv_raw_kernel is the taps' rounding to 16 bits (scripts/emulate_precision.py
-// scheme tc_dw: 0.119 -> 0.143 px for fp16 trained-like weights; 0.5 px gate).
+// dy, FHFMA / FFMA over dx).  Differences from dwconv_raw_kernel: the taps are rounded to 16 bits, and (fp16) the six off-centre
+// column partial sums cross lanes as fp16 (scripts/emulate_precision.py schemes tc_dw / tc_dw_h: 0.119 -> 0.143 / 0.137 px
+// predicted for fp16 trained-like weights, 0.12 px measured; 0.5 px gate).
 // Tiling.  A CTA owns ONE 64-channel chunk for the whole launch (its 7 B matrices, 98 KB, are loaded once) and walks "units" of
 // 256 source lanes = two M tiles:
 //   mode A (W in {8, 16, 32}):  a unit = 256 / W whole image rows; no x halo is needed (neighbours beyond the row are padding)
 //   mode B (any other W):       a unit = 8 rows of one 32-lane window [xs, xs + 32), xs = -3 + 26 i; lanes 3..28 produce outputs
 // plus 6 halo rows above / below (TMA zero fill outside the image).  TMEM: one 112-column accumulator per 16-channel group (4 x
 // 128 columns); the MMA warp runs up to a whole M tile ahead of the four epilogue warpgroups.
-//   warp 0        TMA producer          warp 1      MMA issuer (one lane), TMEM allocator
+//   warp 0        TMA producer          warp 1      MMA issuer (warp-uniform loop, one elected lane issues), TMEM allocator
 //   warps 2..17   epilogue: warpgroup g = (warp - 2) / 4 drains group g (channels 16 g .. 16 g + 15 of the chunk)
 // Statistics: the four warpgroups' (sum, sum of squares) of a pixel meet in shared memory; warpgroup 3 writes the chunk's partial
-// to stat_part[token][k] and ln_stat_finalize_kernel adds a token's parts -- deterministic, no atomics.
+// to stat_part[token][k]; ln_stat_finalize_kernel (stages 2-3) or mlp_fused_kernel itself (stages 0-1) adds a token's parts --
+// deterministic, no atomics.
 struct DwTc2Cfg {
     static constexpr int CC = 64, NB = 112;
     static constexpr int B_BYTES = NB * 128;             // one dy: 112 rows (dx, c') x 64 k
