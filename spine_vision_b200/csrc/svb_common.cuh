@@ -264,6 +264,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
         : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_pair(void* dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
 // ---- packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): half the issue slots of scalar FP32
 __device__ __forceinline__ uint64_t pk2(float lo, float hi) {
     uint64_t r;

@@ -30,7 +30,7 @@ struct BlockParams {
     void *w1, *w2;  // 16-bit [4C][C], [C][4C]
     void* wdw16;    // depthwise taps as 16-bit [49][C] (the diagonal B operands of the tensor-core depthwise kernel)
     void* wtc = nullptr;  // dwconv_rawtc_kernel: [C/64][7 dy][112 = (dx, c')][64 k] 16-bit, zero except k % 16 == c' (see the kernel)
-    CUtensorMap wdw_map, wdw16_map, w1_map, w2_map, wtc_map;
+    CUtensorMap wdw_map, wdw16_map, w1_map, w2_map, wtc_map, wtc2_map;  // wtc2: 56-row boxes (each CTA of a pair stages half of a B matrix)
     CUtensorMap w1f_map, w2f_map;  // fused-MLP weight boxes: W1 {64, 32}, W2 {64, C/2} (each CTA of the pair stages half a tile)
 };
 struct DownParams {
@@ -262,10 +262,11 @@ static int dw_tc_rows(int C, int W) {
 // dwconv_rawtc_kernel (the 7 x 7 taps as seven row-shifted tcgen05 MMAs with the stencil columns in N).  0 = the stage keeps
 // dwconv_raw_kernel; 1 = mode A (W in {8, 16, 32}: units of whole image rows); 2 = mode B (32-lane windows with an x halo).
 // SVB_DWCONV_TC2=0 switches it off, =2 also allows bf16 (8-bit tap mantissas; fp16 keeps 11).  SVB_TC2_MODEB=0 keeps mode B off.
-static int dw_tc2_env() {  // bit 0..1: SVB_DWCONV_TC2 (default 1), bit 4: SVB_TC2_MODEB (default 1)
+static int dw_tc2_env() {  // bit 0..1: SVB_DWCONV_TC2 (default 1), bit 4: SVB_TC2_MODEB (default 1), bit 5: SVB_TC2_PAIR (default 0)
     const char* e = getenv("SVB_DWCONV_TC2");
     const char* b = getenv("SVB_TC2_MODEB");
-    return ((e ? atoi(e) : 1) & 3) | (((b ? atoi(b) : 1) != 0) << 4);
+    const char* p = getenv("SVB_TC2_PAIR");
+    return ((e ? atoi(e) : 1) & 3) | (((b ? atoi(b) : 1) != 0) << 4) | (((p ? atoi(p) : 0) != 0) << 5);
 }
 static int dw_tc2_mode(int setting, int dtype, int C, int H, int W) {
     const int enabled = setting & 3, modeb = (setting >> 4) & 1;
@@ -285,10 +286,10 @@ static void pack_wtc(const float* taps, uint16_t* dst, int C, int dtype) {
                     for (int c = 0; c < 16; ++c)
                         dst[(((size_t)k * 7 + dy) * 112 + dx * 16 + c) * 64 + g * 16 + c] = to16(taps[(size_t)(dy * 7 + dx) * C + k * 64 + g * 16 + c], dtype);
 }
-static int make_wtc_map(CUtensorMap* map, int dtype, const void* base, int C) {
+static int make_wtc_map(CUtensorMap* map, int dtype, const void* base, int C, int rows = 112) {
     const uint64_t dims[2] = {64, (uint64_t)(C / 64) * 7 * 112};
     const uint64_t strides[1] = {128};
-    const uint32_t box[2] = {64, 112};
+    const uint32_t box[2] = {64, (uint32_t)rows};
     return encode_tmap(map, tmap_dtype(dtype), 2, base, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
 }
 static int make_xtc2_map(CUtensorMap* map, int dtype, const void* base, int C, int nb, int H, int W, int mode) {
@@ -568,6 +569,7 @@ extern "C" int svb_model_create(svb_model** out, const svb_weight_desc* weights,
             if (C % 64 == 0) {
                 bp.wtc = base + reinterpret_cast<size_t>(bp.wtc);
                 if (int rc = make_wtc_map(&bp.wtc_map, dtype, bp.wtc, C)) return rc;
+                if (int rc = make_wtc_map(&bp.wtc2_map, dtype, bp.wtc, C, 56)) return rc;
             }
             {
                 const uint64_t dims16[2] = {(uint64_t)C, 49};
@@ -921,35 +923,46 @@ static int sub_batch_images(int s, int nb, int tokens, int C) {
 
 template <typename T>
 static int launch_dwconv_rawtc(const CUtensorMap& x, const BlockParams& bp, void* out, float2* rowstat, float2* stat_part, int C, int nb, int H,
-                               int W, int mode, cudaStream_t st, int b0 = 0, bool finalize = true) {
+                               int W, int mode, cudaStream_t st, int b0 = 0, bool finalize = true, bool pair = false) {
     // rowstat / stat_part address the micro-batch's first token; images [b0, b0 + nb) are written.  finalize = false: the consumer
-    // (mlp_fused_kernel) adds the partial sums up itself
+    // (mlp_fused_kernel) adds the partial sums up itself.  pair: the cta_group::2 variant (two units at a time per CTA pair)
     using Cfg = DwTc2Cfg;
-    auto kern = dwconv_rawtc_kernel<T>;
     static bool attr_done[MAX_DEVICES] = {};
     const int dslot = current_device_slot();
     if (!attr_done[dslot]) {
-        SVB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SVB_CUDA_OK(cudaFuncSetAttribute(dwconv_rawtc_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        SVB_CUDA_OK(cudaFuncSetAttribute(dwconv_rawtc_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         attr_done[dslot] = true;
     }
     const int NCH = C / 64;
     const int rowpx = mode == 1 ? W : 32, nwin = mode == 1 ? 1 : ceil_div(W, 26);
     const int units_y = ceil_div(H, mode == 1 ? 256 / W : 8);
     const int num_units = nb * nwin * units_y;
-    int per_chunk = num_sms() / NCH;
-    if (per_chunk > num_units) per_chunk = num_units;
+    const int cg = pair ? 2 : 1;
+    int per_chunk = num_sms() / cg / NCH;  // CTAs (or CTA pairs) per channel chunk
+    if (per_chunk > ceil_div(num_units, cg)) per_chunk = ceil_div(num_units, cg);
+    if (per_chunk < 1) return set_error(SVB_ERR_UNSUPPORTED_MODEL, "dwconv (tensor core): %d channel chunks do not fit %d SMs", NCH, num_sms());
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(NCH * per_chunk));
+    cfg.gridDim = dim3((unsigned)(NCH * per_chunk * cg));
     cfg.blockDim = dim3(Cfg::NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, x, bp.wtc_map, (const float*)bp.bdw, static_cast<T*>(out), stat_part, C, H, W, rowpx, nwin, units_y,
-                                   num_units, b0));
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = 2;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.attrs = pdl_enabled() ? attr : attr + 1;
+    cfg.numAttrs = (pdl_enabled() ? 1 : 0) + (pair ? 1 : 0);
+    if (pair) {
+        SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, dwconv_rawtc_kernel<T, 2>, x, bp.wtc2_map, (const float*)bp.bdw, static_cast<T*>(out), stat_part, C, H, W, rowpx,
+                                       nwin, units_y, num_units, b0));
+    } else {
+        SVB_CUDA_OK(cudaLaunchKernelEx(&cfg, dwconv_rawtc_kernel<T, 1>, x, bp.wtc_map, (const float*)bp.bdw, static_cast<T*>(out), stat_part, C, H, W, rowpx,
+                                       nwin, units_y, num_units, b0));
+    }
     count_launch();
     if (finalize) {
         const long long t0 = (long long)b0 * H * W, tokens = (long long)nb * H * W;
@@ -1198,7 +1211,8 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                     const bool fused = mlp_fused_lnf(m->mlp_fused_setting, C) && !m->v2 && ns == nb;
                     float2* stat_part = reinterpret_cast<float2*>(ws + L.stat_part);
                     if (plan->tc2[s]) {
-                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, stat_part, C, ns, h, w, plan->tc2[s], st, b0, !fused));
+                        RUN(SVB_KC_DWCONV_LN, launch_dwconv_rawtc<T>(plan->xtc2_map[s], bp, A, rowstat, stat_part, C, ns, h, w, plan->tc2[s], st, b0, !fused,
+                                                                     (m->tc2_setting >> 5) & 1));
                     } else {
                         RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
                     }
@@ -1510,8 +1524,10 @@ extern "C" int svb_dwconv_raw_tc(const void* d_x, const void* d_wtc, const float
     if (int rc = make_xtc2_map(&x_map, dtype, d_x, C, B, H, W, mode)) return rc;
     float2* rs = reinterpret_cast<float2*>(d_rowstat);
     float2* sp = reinterpret_cast<float2*>(d_stat_part);
-    if (dtype == SVB_FP16) return launch_dwconv_rawtc<__half>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st);
-    return launch_dwconv_rawtc<__nv_bfloat16>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st);
+    if (int rc = make_wtc_map(&bp.wtc2_map, dtype, d_wtc, C, 56)) return rc;
+    const bool pair = (dw_tc2_env() >> 5) & 1;  // SVB_TC2_PAIR=1: the cta_group::2 variant (read per call: tests compare both)
+    if (dtype == SVB_FP16) return launch_dwconv_rawtc<__half>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st, 0, true, pair);
+    return launch_dwconv_rawtc<__nv_bfloat16>(x_map, bp, d_out, rs, sp, C, B, H, W, mode, st, 0, true, pair);
 }
 
 extern "C" int svb_dwconv_ln_tc(const void* d_x, const void* d_taps16, const float* d_bias, const float* d_lnw,

@@ -1547,7 +1547,11 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&o)[8]) {
                  : "memory");
 }
 
-template <typename T>
+// CG == 2 (cta_group::2, clusters of two CTAs): the pair works on the SAME channel chunk and on two units at a time (one per CTA);
+// each CTA stages HALF of every B matrix (56 of its 112 rows) and the leader issues M = 256 MMAs for both, so the B operand feed per
+// CTA and MMA halves (7.5 -> 5.75 KB).  Loads of both CTAs are counted on the leader's barriers, commits are multicast, the peer's
+// epilogue warps hand their accumulators back with cluster-scope arrives -- the protocol of gemm_kernel<.., CG = 2>.
+template <typename T, int CG>
 __global__ void __launch_bounds__(DwTc2Cfg::NUM_THREADS, 1)
 dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_constant__ CUtensorMap b_map,
                     const float* __restrict__ bdw, T* __restrict__ out, float2* __restrict__ stat_part, int C, int H, int W,
@@ -1572,8 +1576,11 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
     // address arithmetic can live in uniform registers
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const int NCH = C / Cfg::CC;
-    const int k = (int)blockIdx.x % NCH;                   // this CTA's channel chunk
-    const int u0 = (int)blockIdx.x / NCH, ustep = (int)gridDim.x / NCH;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+    const int unit_id = (int)blockIdx.x / CG;              // CTA (CG == 1) or CTA pair
+    const int k = unit_id % NCH;                           // this CTA's (pair's) channel chunk
+    const int u0 = unit_id / NCH, ustep = ((int)gridDim.x / CG) / NCH;  // it walks units (u0 + i * ustep) * CG + rank
+    constexpr int B_CTA = Cfg::B_BYTES / CG;               // bytes of one B matrix staged by this CTA
     const bool mode_b = nwin > 1 || rowpx != W;
     const int rows_unit = mode_b ? 8 : 256 / W;            // output rows per unit
     const int units_img = nwin * units_y;
@@ -1584,12 +1591,12 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
         tma_prefetch_desc(&b_map);
         mbar_init(bfull, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); mbar_init(&sfull[s], 12); }
-        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 4; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4 * CG); }
         mbar_fence_init();
     }
-    if (warp == 1) tmem_alloc<1>(tmem_ptr, Cfg::TMEM_COLS);
+    if (warp == 1) tmem_alloc<CG>(tmem_ptr, Cfg::TMEM_COLS);
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
     pdl_launch_dependents();
@@ -1598,25 +1605,38 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             // the taps do not depend on the previous kernel: they are fetched while it is still running
-            mbar_expect_tx(bfull, Cfg::B_TOTAL);
-            for (int dy = 0; dy < 7; ++dy) tma_load_2d(sB + dy * Cfg::B_BYTES, &b_map, bfull, 0, (k * 7 + dy) * Cfg::NB);
+            if (CG == 1) {
+                mbar_expect_tx(bfull, Cfg::B_TOTAL);
+                for (int dy = 0; dy < 7; ++dy) tma_load_2d(sB + dy * B_CTA, &b_map, bfull, 0, (k * 7 + dy) * Cfg::NB);
+            } else {  // both CTAs' halves are counted on the leader's barrier
+                if (rank == 0) mbar_expect_tx(bfull, Cfg::B_TOTAL);
+                const uint32_t lb = mapa_shared(smem_u32(bfull), 0);
+                for (int dy = 0; dy < 7; ++dy) tma_load_2d_pair(sB + dy * B_CTA, &b_map, lb, 0, (k * 7 + dy) * Cfg::NB + (int)rank * (Cfg::NB / 2));
+            }
             pdl_wait();
             int it = 0;
-            for (int u = u0; u < num_units; u += ustep, ++it) {
+            for (int up = u0; up * CG < num_units; up += ustep, ++it) {
+                const int u = up * CG + (int)rank;  // CG == 2: may be one past the end (odd unit count): a box of zeros
                 const int stage = it & 1;
                 if (it >= 2) mbar_wait(&aempty[stage], ((it >> 1) - 1) & 1);
                 const int b = u / units_img, r = u - b * units_img;
                 const int wi = r % nwin, uy = r / nwin;
                 const int xs = mode_b ? 26 * wi - 3 : 0;
-                mbar_expect_tx(&afull[stage], a_bytes);
-                tma_load_4d(sA + stage * Cfg::A_STAGE, &x_map, &afull[stage], k * Cfg::CC, xs, uy * rows_unit - 3, b0 + b);
+                if (CG == 1) {
+                    mbar_expect_tx(&afull[stage], a_bytes);
+                    tma_load_4d(sA + stage * Cfg::A_STAGE, &x_map, &afull[stage], k * Cfg::CC, xs, uy * rows_unit - 3, b0 + b);
+                } else {
+                    if (rank == 0) mbar_expect_tx(&afull[stage], 2 * a_bytes);
+                    tma_load_4d_pair(sA + stage * Cfg::A_STAGE, &x_map, mapa_shared(smem_u32(&afull[stage]), 0), k * Cfg::CC, xs, uy * rows_unit - 3,
+                                     u < num_units ? b0 + b : 0x3fffffff);
+                }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (the whole warp, one elected lane issues)
-        {
+        if (rank == 0) {
             constexpr uint32_t idesc = (1u << 4) | (UmmaFmt<T>::v << 7) | (UmmaFmt<T>::v << 10) | ((uint32_t)(Cfg::NB >> 3) << 17) |
-                                       ((uint32_t)(128 >> 4) << 24);
+                                       ((uint32_t)((128 * CG) >> 4) << 24);
             const uint32_t lead = elect_one() ? 1u : 0u;
             mbar_wait(bfull, 0);
             // descriptors differ only in the 14-bit start-address field (bytes >> 4): + 2 per 16-channel group (32 B inside the
@@ -1626,7 +1646,7 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
             const uint64_t a_dy = (uint64_t)(rowpx * 8);
             int it = 0;
             uint32_t tcount = 0;  // M tiles issued so far: each uses every TMEM accumulator once
-            for (int u = u0; u < num_units; u += ustep, ++it) {
+            for (int up = u0; up * CG < num_units; up += ustep, ++it) {
                 const int stage = it & 1;
                 mbar_wait(&afull[stage], (it >> 1) & 1);
                 tc_fence_after();
@@ -1643,13 +1663,13 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
 #pragma unroll
                         for (int dy = 0; dy < 7; ++dy) {
                             const uint64_t adesc = a0 + (uint64_t)(mt * 1024 + 2 * g) + (uint64_t)dy * a_dy;
-                            const uint64_t bdesc = b0 + (uint64_t)(dy * (Cfg::B_BYTES >> 4) + 2 * g);
-                            tc_mma_f16_if<1>(lead, tmem_base + (uint32_t)(g * 128), adesc, bdesc, idesc, dy != 0 ? 1u : 0u);
+                            const uint64_t bdesc = b0 + (uint64_t)(dy * (B_CTA >> 4) + 2 * g);
+                            tc_mma_f16_if<CG>(lead, tmem_base + (uint32_t)(g * 128), adesc, bdesc, idesc, dy != 0 ? 1u : 0u);
                         }
-                        tc_commit_if<1>(lead, &tfull[g]);
+                        tc_commit_if<CG>(lead, &tfull[g]);
                     }
                 }
-                tc_commit_if<1>(lead, &aempty[stage]);
+                tc_commit_if<CG>(lead, &aempty[stage]);
             }
         }
     } else {
@@ -1682,7 +1702,9 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
         const uint32_t inv_units_img = (uint32_t)((0x100000000ull + (uint32_t)units_img - 1) / (uint32_t)units_img);
         const uint32_t inv_nwin = (uint32_t)((0x100000000ull + (uint32_t)nwin - 1) / (uint32_t)nwin);
         const int lw = 31 - __clz(W);  // mode A: W = 8, 16 or 32
-        for (int u = u0; u < num_units; u += ustep) {
+        for (int up = u0; up * CG < num_units; up += ustep) {
+            const int u = up * CG + (int)rank;
+            const bool unit_ok = CG == 1 || u < num_units;
             const int b = units_img == 1 ? u : (int)__umulhi((uint32_t)u, inv_units_img), r = u - b * units_img;  // (the reciprocal of 1 does not fit 32 bits)
             const int uy = nwin == 1 ? r : (int)__umulhi((uint32_t)r, inv_nwin), wi = r - uy * nwin;
             const int y0 = uy * rows_unit;
@@ -1692,12 +1714,12 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                 if (mode_b) {
                     y = y0 + mt * 4 + q;
                     x = 26 * wi - 3 + lane;
-                    valid = lane >= 3 && lane <= 28 && x < W && y < H;
+                    valid = unit_ok && lane >= 3 && lane <= 28 && x < W && y < H;
                 } else {
                     const int p = mt * 128 + px;
                     y = y0 + (p >> lw);
                     x = p & (W - 1);
-                    valid = y < H;
+                    valid = unit_ok && y < H;
                 }
                 const size_t tok = ((size_t)(b0 + b) * H + y) * W + x;
                 mbar_wait(&tfull[g], tcount & 1);
@@ -1716,7 +1738,11 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
                         // the last column block is in registers: hand the accumulator back to the MMA warp before working on it
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&tempty[g]);
+                        if (lane == 0) {
+                            // the accumulator is in registers (tcgen05.wait::ld above): nothing to publish, relaxed arrives
+                            if (CG == 1 || rank == 0) mbar_arrive_relaxed(&tempty[g]);
+                            else mbar_arrive_cluster_relaxed(mapa_shared(smem_u32(&tempty[g]), 0));
+                        }
                     }
                     if (PACKED && dx != 3) {
 #pragma unroll
@@ -1772,8 +1798,8 @@ dwconv_rawtc_kernel(const __grid_constant__ CUtensorMap x_map, const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc<1>(tmem_base, Cfg::TMEM_COLS);
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    if (warp == 1) tmem_dealloc<CG>(tmem_base, Cfg::TMEM_COLS);
 }
 
 // Token statistics of dwconv_rawtc_kernel: parts [tokens][NCH] (sum, sum of squares) -> rowstat[token] = (rstd, -mu rstd), parts

@@ -191,6 +191,15 @@ def test_dwconv_raw_tc_and_folded_layernorm_vs_torch(B, H, W, C, dtype):
     r2, s2 = ops.dwconv_raw_tc(xd, wtc, bd)
     torch.cuda.synchronize()
     assert torch.equal(r2, raw) and torch.equal(s2, stat)
+    # the cta_group::2 variant (CTA pairs, half of every B matrix per CTA; SVB_TC2_PAIR is read per call here): identical bits
+    import os
+    os.environ["SVB_TC2_PAIR"] = "1"
+    try:
+        r3, s3 = ops.dwconv_raw_tc(xd, wtc, bd)
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["SVB_TC2_PAIR"]
+    assert torch.equal(r3, raw) and torch.equal(s3, stat)
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "fp16"])

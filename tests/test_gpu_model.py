@@ -69,11 +69,12 @@ def test_unfolded_layernorm_path_still_agrees(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"SVB_DWCONV_TC2": "0"}, {"SVB_MLP_FUSED": "0"}, {"SVB_TC2_MODEB": "0"}, {"SVB_DWCONV_TC2": "0", "SVB_MLP_FUSED": "0"},
+                                 {"SVB_TC2_PAIR": "1"},
                                  {"SVB_DWCONV_TC2": "2", "dtype": "bf16"}])
 def test_alternative_block_kernels_still_agree(monkeypatch, env):
     """The A/B switches of the block (read at model creation): FP32-pipe depthwise kernel instead of the tensor-core one, two GEMMs
-    instead of the fused MLP, tensor-core depthwise kernel only where a warp holds whole image rows, and the tensor-core depthwise
-    kernel with bf16 taps (opt-in) -- each holds the gate on trained-like weights and stays close to the default path."""
+    instead of the fused MLP, tensor-core depthwise kernel only where a warp holds whole image rows, its cta_group::2 variant, and the
+    tensor-core depthwise kernel with bf16 taps (opt-in) -- each holds the gate on trained-like weights and stays close to the default path."""
     env = dict(env)
     dtype = env.pop("dtype", None)
     om = make_model("base", seed=0, trained_like=True)
