@@ -336,7 +336,9 @@ def run_b200(args):
             pass
         peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
         peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
-        gemm_ms = times.get("gemm", 0.0) / args.steps
+        fused_ms = times.get("mlp_fused", 0.0) / args.steps  # mlp_fused_kernel (stages 0-1): timed as its own class, part of the GEMM class below
+        gemm_only_ms = times.get("gemm", 0.0) / args.steps
+        gemm_ms = gemm_only_ms + fused_ms
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         hbm = float(peaks.get("hbm_gbs", 6650.0))
         traffic = None
@@ -352,6 +354,7 @@ def run_b200(args):
         # algorithmic HBM bytes of the GEMMs of one step (A + W + out, + the residual read of fc2), 16-bit operands: what `traffic`
         # (measured DRAM bytes) is to be compared with
         gemm_bytes = 0.0
+        fused_flops = 0.0
         hh, ww = IMAGE_SIZE[0] // 4, IMAGE_SIZE[1] // 4
         for si, (cd, nd) in enumerate(zip(model.engine.dims, model.engine.depths)):
             if si > 0:
@@ -360,6 +363,7 @@ def run_b200(args):
                 gemm_bytes += 2.0 * (mm * kk + cd * kk + mm * cd)
             mm = B * hh * ww
             if cd in (128, 256) and os.environ.get("SVB_MLP_FUSED", "1") != "0":
+                fused_flops += nd * 2.0 * 2.0 * mm * 4 * cd * cd
                 # mlp_fused_kernel: the hidden activation never leaves the SM (A + W1 + W2 + residual in + out)
                 gemm_bytes += nd * 2.0 * (mm * cd + 8 * cd * cd + 2 * mm * cd)
             else:
@@ -372,7 +376,7 @@ def run_b200(args):
         k1_bytes = B * (SLICE_HW[0] * SLICE_HW[1] * 4 + IMAGE_SIZE[0] * IMAGE_SIZE[1])
         k3_bytes = n_crops * (234 * 200 * 4 + CROP_SIZE[0] * CROP_SIZE[1] + SECOND_SIZE[0] * SECOND_SIZE[1])
         k4_bytes = k4_p * SECOND_SIZE[0] * SECOND_SIZE[1] * (2 + 3 * 4)  # two uint8 planes in, three float32 planes out
-        model_ms = sum(times.get(k, 0.0) for k in ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")) / args.steps
+        model_ms = sum(times.get(k, 0.0) for k in ("stem", "dwconv_ln", "gemm", "mlp_fused", "ln_patchify", "head")) / args.steps
         dw_gbs = dw_bytes / (dw_ms * 1e-3) / 1e9 if dw_ms else None
         k1_gbs = k1_bytes / (k1_ms / args.steps * 1e-3) / 1e9 if k1_ms else None
         k3_gbs = k3_bytes / (k3_ms / args.steps * 1e-3) / 1e9 if k3_ms else None
@@ -398,7 +402,15 @@ def run_b200(args):
                          "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{traffic_file} (ncu --set full, per-shape dram bytes x launches)",
                          "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
                          "timing": "CUDA event pair around every launch, separate pass over the same steps",
-                         "whole_step_frac_of_tensor_ceiling": value / world / ceiling, "tensor_ceiling_series_per_s": ceiling},
+                         "whole_step_frac_of_tensor_ceiling": value / world / ceiling, "tensor_ceiling_series_per_s": ceiling,
+                         "by_kernel": {
+                             "gemm_kernel": {"ms_per_step": gemm_only_ms, "flops_per_step": gemm_flops - fused_flops,
+                                             "achieved": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms else None,
+                                             "frac": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 / peak_tf if gemm_only_ms else None},
+                             "mlp_fused_kernel": {"ms_per_step": fused_ms, "flops_per_step": fused_flops,
+                                                  "achieved": fused_flops / (fused_ms * 1e-3) / 1e12 if fused_ms else None,
+                                                  "frac": fused_flops / (fused_ms * 1e-3) / 1e12 / peak_tf if fused_ms else None,
+                                                  "note": "bound by its GELU epilogue (FMA / MUFU pipes), DESIGN.md section 4"}}},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
                                    "k3_crop_resample": k3_ms / args.steps, "k0_midplane_resample (e2e path only)": k0_ms / args.steps,
                                    "k0_k1_fused (e2e path only)": k01_ms / args.steps},

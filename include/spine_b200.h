@@ -219,7 +219,7 @@ size_t svb_model_workspace_bytes(const svb_model* m, int micro_batch, int H, int
  *               CUDA events around every launch, synchronises at the end and accumulates
  *               per-kernel-class milliseconds (profiling / roofline only).
  */
-enum { SVB_KC_STEM = 0, SVB_KC_DWCONV_LN = 1, SVB_KC_GEMM = 2, SVB_KC_LN_PATCHIFY = 3, SVB_KC_HEAD = 4, SVB_NUM_KERNEL_CLASSES = 5 };
+enum { SVB_KC_STEM = 0, SVB_KC_DWCONV_LN = 1, SVB_KC_GEMM = 2, SVB_KC_LN_PATCHIFY = 3, SVB_KC_HEAD = 4, SVB_KC_MLP_FUSED = 5, SVB_NUM_KERNEL_CLASSES = 6 };
 int svb_model_forward(svb_model* m, const uint8_t* d_in_u8, int B, int H, int W, float* d_coords,
                       int micro_batch, void* d_ws, size_t ws_bytes, void* stream, float* times_ms);
 /* The same forward from the tensor the reference's callers build themselves: float32 NCHW [B,3,H,W], already /255 and

@@ -16,7 +16,7 @@ LIB_PATH = Path(os.environ.get("SPINE_B200_LIB", _PKG / "libspine_b200.so"))
 SVB_BF16, SVB_FP16, SVB_F32 = 0, 1, 2
 PIXEL_FLOAT, PIXEL_INT16, PIXEL_UINT16, PIXEL_UINT8 = 0, 1, 2, 3  # SVB_PIXEL_*: the file's pixel type of a slice (rotated crops)
 DTYPES = {"bf16": SVB_BF16, "bfloat16": SVB_BF16, "fp16": SVB_FP16, "float16": SVB_FP16, "half": SVB_FP16}
-KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head")
+KERNEL_CLASSES = ("stem", "dwconv_ln", "gemm", "ln_patchify", "head", "mlp_fused")
 
 # every symbol include/spine_b200.h declares
 EXPORTS = (

@@ -1217,8 +1217,8 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                         RUN(SVB_KC_DWCONV_LN, launch_dwconv_raw<T>(plan->xr_map[s], plan->xr4_map[s], bp, A, rowstat, C, ns, h, w, st, b0));
                     }
                     if (fused) {
-                        if (plan->tc2[s]) { RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, stat_part, C / 64)); }
-                        else { RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, rowstat, 0)); }
+                        if (plan->tc2[s]) { RUN(SVB_KC_MLP_FUSED, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, stat_part, C / 64)); }
+                        else { RUN(SVB_KC_MLP_FUSED, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st, rowstat, 0)); }
                         continue;
                     }
                     RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, bp.s1, m1, 4 * C, C,
@@ -1238,7 +1238,7 @@ static int forward_chunk(svb_model* m, const uint8_t* in, const float* in_f32, i
                 RUN(SVB_KC_DWCONV_LN, launch_dwconv<T>(plan->x_map[s], bp, A, C, nb, h, w, st));
             }
             if (mlp_fused(m->mlp_fused_setting, C) && !m->v2) {
-                RUN(SVB_KC_GEMM, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
+                RUN(SVB_KC_MLP_FUSED, launch_mlp_fused<T>(plan->a_map[s], bp, plan->ox_map[s], C, M, st));
             } else {
                 RUN(SVB_KC_GEMM, launch_gemm<T>(plan->a_map[s], bp.w1_map, plan->oh_map[s], plan->oh_map[s], bp.b1, nullptr, M, 4 * C, C,
                                                 GEMM_GELU, st, coex_stage(s)));

@@ -1107,14 +1107,17 @@ struct MlpCfg {
     static constexpr int H_BYTES = 16384;             // one hidden chunk: 128 tokens x 64 (one k-block)
     static constexpr int W1_KB_BYTES = 32 * 128;      // this CTA's 32 of the chunk's 64 W1 rows, one k-block
     static constexpr int SLOT = KB_A * W1_KB_BYTES;   // = (C/2 rows) x 128 B of W2 as well: 8 KB / 16 KB
-    static constexpr int W_SLOTS = C == 128 ? 8 : 6;
+    static constexpr int W_SLOTS = C == 128 ? 7 : 5;  // one slot fewer than would fit: the epilogue's vectors live in shared memory
+    static constexpr int VEC_BYTES = (4 * C + 4 * C + C + C) * 4;  // t_n / b1 [4C], s_n [4C], b2 [C], gamma [C] as fp32: with ~224 KB of
+                                                      // shared memory taken, L1 is ~4 KB and every __ldg of them was an L2 round trip
+                                                      // (long scoreboard: 34 % of the epilogue warps' stall samples)
     static constexpr int EPI_WARPS = 16;
     static constexpr int CH = C / 4 / 32;             // 32x32 output boxes per epilogue warp
     static constexpr bool STAGE_IN_H = C == 256;      // C=256: the output boxes are staged inside the (idle) hidden buffers
     static constexpr int STAGE_BYTES = STAGE_IN_H ? 0 : EPI_WARPS * CH * 2048;
     static constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
     static constexpr int NUM_BARS = 2 * W_SLOTS + 2 + 6 * NB + 4 + EPI_WARPS;
-    static constexpr int SMEM_BYTES = A_BYTES + NB * H_BYTES + STAGE_BYTES + W_SLOTS * SLOT + NUM_BARS * 8 + 64 + 1024;
+    static constexpr int SMEM_BYTES = A_BYTES + NB * H_BYTES + STAGE_BYTES + W_SLOTS * SLOT + VEC_BYTES + NUM_BARS * 8 + 64 + 1024;
     static constexpr int TMEM_COLS = 512;
     static_assert(C == 128 || C == 256, "Y (C columns) + NB 64-column hidden accumulators must fit 512 TMEM columns");
     static_assert(C + NB * HC <= 512, "TMEM budget");
@@ -1142,7 +1145,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
     uint8_t* sH = sA + Cfg::A_BYTES;                   // [NB][2 k-blocks][128 rows x 128 B]
     uint8_t* sStage = sH + NB * Cfg::H_BYTES;          // per-warp 32x32 output boxes (C=128); C=256 reuses sH
     uint8_t* sW = sStage + Cfg::STAGE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + S * Cfg::SLOT);
+    float* sB1 = reinterpret_cast<float*>(sW + S * Cfg::SLOT);  // [4C] fc1 bias (t_n when LNF)
+    float* sS1 = sB1 + 4 * C;                                   // [4C] s_n (LNF)
+    float* sB2 = sS1 + 4 * C;                                   // [C]
+    float* sGm = sB2 + C;                                       // [C]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sB1) + Cfg::VEC_BYTES);
     uint64_t* wfull = bars;                 // [S]  leader's copy counts both CTAs' bytes
     uint64_t* wempty = wfull + S;           // [S]  multicast commit
     uint64_t* afull = wempty + S;           // leader
@@ -1187,6 +1194,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
         mbar_fence_init();
     }
     if (warp == 1) tmem_alloc<2>(tmem_ptr, Cfg::TMEM_COLS);
+    // the epilogue's vectors (weights: they do not depend on the previous kernel) into shared memory, once per CTA
+    for (int i = threadIdx.x; i < 4 * C; i += Cfg::NUM_THREADS) {
+        sB1[i] = __ldg(b1 + i);
+        sS1[i] = LNF ? __ldg(s1 + i) : 0.f;
+    }
+    for (int i = threadIdx.x; i < C; i += Cfg::NUM_THREADS) {
+        sB2[i] = __ldg(b2 + i);
+        sGm[i] = __ldg(gamma + i);
+    }
     tc_fence_before();
     cluster_sync_all();
     tc_fence_after();
@@ -1367,11 +1383,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
             for (int j = 0; j < NJ; ++j, ++j1) {
                 const uint32_t hb = j1 % NB, u = (j1 / NB) & 1;
                 const int hcol = j * Cfg::HC + slice * 16;
-                float4 bias[4], sn[4];  // in flight before the accumulator is waited for
+                float4 bias[4], sn[4];  // broadcast loads from shared memory
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    bias[i] = __ldg(reinterpret_cast<const float4*>(b1 + hcol) + i);
-                    if (LNF) sn[i] = __ldg(reinterpret_cast<const float4*>(s1 + hcol) + i);
+                    bias[i] = reinterpret_cast<const float4*>(sB1 + hcol)[i];
+                    if (LNF) sn[i] = reinterpret_cast<const float4*>(sS1 + hcol)[i];
                 }
                 mbar_wait(&hacc_full[hb], u);
                 tc_fence_after();
@@ -1436,10 +1452,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const uint32_t addr = row_off + ((((uint32_t)i) ^ swz) << 4);
-                        const float4 c0 = __ldg(reinterpret_cast<const float4*>(b2 + col) + 2 * i);
-                        const float4 c1 = __ldg(reinterpret_cast<const float4*>(b2 + col) + 2 * i + 1);
-                        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i);
-                        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + col) + 2 * i + 1);
+                        const float4 c0 = reinterpret_cast<const float4*>(sB2 + col)[2 * i];
+                        const float4 c1 = reinterpret_cast<const float4*>(sB2 + col)[2 * i + 1];
+                        const float4 g0 = reinterpret_cast<const float4*>(sGm + col)[2 * i];
+                        const float4 g1 = reinterpret_cast<const float4*>(sGm + col)[2 * i + 1];
                         const uint4 rv = lds128(addr);
                         const float2 x01 = Cvt<T>::unpack2(rv.x), x23 = Cvt<T>::unpack2(rv.y);
                         const float2 x45 = Cvt<T>::unpack2(rv.z), x67 = Cvt<T>::unpack2(rv.w);
