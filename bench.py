@@ -341,12 +341,15 @@ def run_b200(args):
         gemm_ms = gemm_only_ms + fused_ms
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         hbm = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        traffic = traffic_gemm_only = None
         traffic_file = TRAFFIC_JSON if (ROOT / "profiles" / TRAFFIC_JSON).exists() else "r01e_gemm_traffic.json"
         try:  # DRAM bytes of the GEMM launches of one step, from the committed ncu --set full capture of the same kernels
             tj = json.loads((ROOT / "profiles" / traffic_file).read_text())
             if "gemm_dram_bytes_per_micro_batch" in tj:
                 traffic = float(tj["gemm_dram_bytes_per_micro_batch"]) * B / float(tj["micro_batch"])
+                # gemm_kernel alone (the capture names the fused-MLP launches)
+                traffic_gemm_only = sum(float(e["dram_bytes"]) * e["launches_per_micro_batch"] for e in tj["per_launch"]
+                                        if "fused" not in e["layer"]) * B / float(tj["micro_batch"])
             else:
                 traffic = float(tj["gemm_dram_bytes_per_micro_batch_37"]) * B / 37.0
         except Exception:
@@ -354,6 +357,7 @@ def run_b200(args):
         # algorithmic HBM bytes of the GEMMs of one step (A + W + out, + the residual read of fc2), 16-bit operands: what `traffic`
         # (measured DRAM bytes) is to be compared with
         gemm_bytes = 0.0
+        fused_bytes = 0.0
         fused_flops = 0.0
         hh, ww = IMAGE_SIZE[0] // 4, IMAGE_SIZE[1] // 4
         for si, (cd, nd) in enumerate(zip(model.engine.dims, model.engine.depths)):
@@ -366,6 +370,7 @@ def run_b200(args):
                 fused_flops += nd * 2.0 * 2.0 * mm * 4 * cd * cd
                 # mlp_fused_kernel: the hidden activation never leaves the SM (A + W1 + W2 + residual in + out)
                 gemm_bytes += nd * 2.0 * (mm * cd + 8 * cd * cd + 2 * mm * cd)
+                fused_bytes += nd * 2.0 * (mm * cd + 8 * cd * cd + 2 * mm * cd)
             else:
                 gemm_bytes += nd * 2.0 * ((mm * cd + 4 * cd * cd + mm * 4 * cd) + (mm * 4 * cd + 4 * cd * cd + 2 * mm * cd))
         dw_ms = times.get("dwconv_ln", 0.0) / args.steps
@@ -396,21 +401,24 @@ def run_b200(args):
                            "of the previous chunk; D2H on a third stream; batch k+1 is started before batch k is collected (two output slots); "
                            "index tables (offsets, shapes, crop deltas: 44 bytes per series) are uploaded once per batch geometry and reused"},
             "gpu_launches": int(gpu_launches),
-            "roofline": {"kernel": "gemm_kernel + mlp_fused_kernel (tcgen05 pointwise / downsample GEMMs and the fused fc1-GELU-fc2 of stages 0-1, "
-                                   "all launches of one step)", "bound": "tensor",
-                         "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": (achieved / peak_tf) if achieved else None,
-                         "traffic": traffic, "algorithmic_bytes_per_step": gemm_bytes, "traffic_source": f"profiles/{traffic_file} (ncu --set full, per-shape dram bytes x launches)",
-                         "peak_source": peak_src, "flops_per_step": gemm_flops, "ms_per_step": gemm_ms,
+            # the DOMINANT kernel: gemm_kernel (stage 2-3 MLP GEMMs and the downsample convs: half of the step); the GEMM class as a
+            # whole (with the fused fc1-GELU-fc2 kernel of stages 0-1, whose bound is its GELU epilogue) is in `gemm_class`
+            "roofline": {"kernel": "gemm_kernel (tcgen05 pointwise / downsample GEMMs, all launches of one step)", "bound": "tensor",
+                         "achieved": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms else None, "peak": peak_tf,
+                         "unit": "TFLOP/s",
+                         "frac": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 / peak_tf if gemm_only_ms else None,
+                         "traffic": traffic_gemm_only, "algorithmic_bytes_per_step": gemm_bytes - fused_bytes,
+                         "traffic_source": f"profiles/{traffic_file} (ncu --set full, per-shape dram bytes x launches)",
+                         "peak_source": peak_src, "flops_per_step": gemm_flops - fused_flops, "ms_per_step": gemm_only_ms,
                          "timing": "CUDA event pair around every launch, separate pass over the same steps",
                          "whole_step_frac_of_tensor_ceiling": value / world / ceiling, "tensor_ceiling_series_per_s": ceiling,
-                         "by_kernel": {
-                             "gemm_kernel": {"ms_per_step": gemm_only_ms, "flops_per_step": gemm_flops - fused_flops,
-                                             "achieved": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 if gemm_only_ms else None,
-                                             "frac": (gemm_flops - fused_flops) / (gemm_only_ms * 1e-3) / 1e12 / peak_tf if gemm_only_ms else None},
-                             "mlp_fused_kernel": {"ms_per_step": fused_ms, "flops_per_step": fused_flops,
-                                                  "achieved": fused_flops / (fused_ms * 1e-3) / 1e12 if fused_ms else None,
-                                                  "frac": fused_flops / (fused_ms * 1e-3) / 1e12 / peak_tf if fused_ms else None,
-                                                  "note": "bound by its GELU epilogue (FMA / MUFU pipes), DESIGN.md section 4"}}},
+                         "gemm_class": {"kernels": "gemm_kernel + mlp_fused_kernel", "ms_per_step": gemm_ms, "flops_per_step": gemm_flops,
+                                        "achieved": achieved, "frac": (achieved / peak_tf) if achieved else None, "traffic": traffic,
+                                        "algorithmic_bytes_per_step": gemm_bytes},
+                         "mlp_fused_kernel": {"ms_per_step": fused_ms, "flops_per_step": fused_flops,
+                                              "achieved": fused_flops / (fused_ms * 1e-3) / 1e12 if fused_ms else None,
+                                              "frac": fused_flops / (fused_ms * 1e-3) / 1e12 / peak_tf if fused_ms else None,
+                                              "note": "bound by its GELU epilogue (FMA / MUFU pipes), DESIGN.md section 4"}},
             "kernel_ms_per_step": {**{k: v / args.steps for k, v in times.items()}, "k1_normalize_resize": k1_ms / args.steps,
                                    "k3_crop_resample": k3_ms / args.steps, "k0_midplane_resample (e2e path only)": k0_ms / args.steps,
                                    "k0_k1_fused (e2e path only)": k01_ms / args.steps},
