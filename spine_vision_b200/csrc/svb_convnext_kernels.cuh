@@ -1380,23 +1380,43 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap a_map, const __grid_constan
 #pragma unroll
                 for (int c = 0; c < CH; ++c) tma_load_2d(stage_p + c * 2048, &x_map, &rfull[ew], slice * CW + c * 32, row0);
             }
+            // C = 256: the TMEM read of chunk j + 1 is issued BEFORE the GELU of chunk j (fc1 runs NB - 1 chunks ahead, so its
+            // accumulator is normally complete) and its latency hides under arithmetic: 327 -> 310 us.  At C = 128 the same change
+            // cost registers (spills) and time (463 -> 514 us): there each chunk is read when it is needed.
+            constexpr bool PF = C == 256;
+            float vbuf[2][16];
+            if (PF) {
+                const uint32_t hb = j1 % NB, u = (j1 / NB) & 1;
+                mbar_wait(&hacc_full[hb], u);
+                tc_fence_after();
+                TmemLd<16>::ld(tm_h + lane_sel + hb * Cfg::HC + (uint32_t)(slice * 16), vbuf[0]);
+            }
+#pragma unroll PF ? NJ : 1
             for (int j = 0; j < NJ; ++j, ++j1) {
                 const uint32_t hb = j1 % NB, u = (j1 / NB) & 1;
                 const int hcol = j * Cfg::HC + slice * 16;
+                float (&v)[16] = vbuf[PF ? (j & 1) : 0];
+                if (!PF) {
+                    mbar_wait(&hacc_full[hb], u);
+                    tc_fence_after();
+                    TmemLd<16>::ld(tm_h + lane_sel + hb * Cfg::HC + (uint32_t)(slice * 16), v);
+                }
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_relaxed(&hacc_free_l[hb]);  // accumulator chunk is in registers
+                if (PF && j + 1 < NJ) {
+                    const uint32_t hn = (j1 + 1) % NB, un = ((j1 + 1) / NB) & 1;
+                    mbar_wait(&hacc_full[hn], un);
+                    tc_fence_after();
+                    TmemLd<16>::ld(tm_h + lane_sel + hn * Cfg::HC + (uint32_t)(slice * 16), vbuf[(j + 1) & 1]);
+                }
                 float4 bias[4], sn[4];  // broadcast loads from shared memory
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     bias[i] = reinterpret_cast<const float4*>(sB1 + hcol)[i];
                     if (LNF) sn[i] = reinterpret_cast<const float4*>(sS1 + hcol)[i];
                 }
-                mbar_wait(&hacc_full[hb], u);
-                tc_fence_after();
-                float v[16];
-                TmemLd<16>::ld(tm_h + lane_sel + hb * Cfg::HC + (uint32_t)(slice * 16), v);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_relaxed(&hacc_free_l[hb]);  // accumulator chunk is in registers
                 mbar_wait(&hs_free[hb], u ^ 1);  // fc2 of the chunk that used this operand buffer NB chunks ago is done
                 const uint32_t dst = smem_u32(sH + hb * Cfg::H_BYTES) + (uint32_t)(r * 128);
 #pragma unroll
