@@ -31,7 +31,7 @@ CROP_SIZE = (128, 128)
 SECOND_SIZE = (256, 256)
 IMAGE_SIZE = (512, 512)
 SLICE_HW = (1195, 1195)
-TRAFFIC_JSON = os.environ.get("SVB_TRAFFIC_JSON", "r03m_gemm_traffic.json")  # per-shape DRAM bytes of the GEMM launches (ncu --set full), see scripts/summarise_ncu_layers.py
+TRAFFIC_JSON = os.environ.get("SVB_TRAFFIC_JSON", "r03z_gemm_traffic.json")  # per-shape DRAM bytes of the GEMM launches (ncu --set full), see scripts/summarise_ncu_layers.py
 WORKLOAD = ("configs[1]: 256 synthetic sagittal series per GPU (15x512x512 fp32 @0.7mm; middle plane at 0.3mm iso = 1195x1195), "
             "convnext_base random-init localizer @512x512, 5 IVD levels, crop_delta_mm 50/20/30/30, 128x128 crops + 256x256 classifier input")
 
